@@ -1,0 +1,180 @@
+/*
+ * ising_b200.h -- C ABI of libising_b200.so, the B200 (sm_100a) engine behind the classical
+ * Monte-Carlo path of py_monte_carlo (Renmusxd/PyIsingMonteCarlo).
+ *
+ * The reference has no FFI seam on this path: src/lattice.rs calls the out-of-tree Rust type
+ * qmc::classical::graph::GraphState by static linkage (lattice.rs:5,199).  Each entry point
+ * below names the reference call it replaces; INTEGRATION.md shows the Rust `extern "C"`
+ * block and the patched call sites a maintainer would add.
+ *
+ * Conventions: every function returns ISING_OK (0) or an ISING_E_* code and never aborts;
+ * the message of the last failure is ising_last_error(ctx) (ctx may be NULL for failures of
+ * ising_ctx_create itself).  All buffers are caller-owned HOST memory unless a name ends in
+ * `_dev`.  A context is bound to one CUDA device and one stream and is not re-entrant.
+ * Energies use the reference's convention E = sum_edges J s_a s_b - sum_i b_i s_i with
+ * s = +1 for `true`, so J > 0 is antiferromagnetic (README.md:45-46, lattice.rs:43-44).
+ */
+#ifndef ISING_B200_H
+#define ISING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISING_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ISING_API __attribute__((visibility("default")))
+#else
+#define ISING_API
+#endif
+
+enum {
+    ISING_OK = 0,
+    ISING_E_INVALID = 1,     /* bad argument (reference: PyValueError)                      */
+    ISING_E_CUDA = 2,        /* CUDA runtime failure, no device, or wrong architecture      */
+    ISING_E_UNSUPPORTED = 3, /* valid in the reference but not on the GPU path (D1/D2)      */
+    ISING_E_AMBIGUOUS = 4,   /* replay: a uniform fell within rounding of exp(-beta dE)     */
+    ISING_E_NOMEM = 5
+};
+
+typedef struct ising_ctx ising_ctx;
+typedef struct ising_graph ising_graph;
+typedef struct ising_sim ising_sim;
+
+/* ---- context ---------------------------------------------------------------------------- */
+ISING_API int ising_abi_version(void);
+ISING_API int ising_ctx_create(int device, ising_ctx **out);
+ISING_API void ising_ctx_destroy(ising_ctx *ctx);
+ISING_API const char *ising_last_error(const ising_ctx *ctx);
+
+/* ---- graph layout (replaces GraphState::new's adjacency build, lattice.rs:199) ----------- */
+enum { ISING_KIND_GENERAL = 0, ISING_KIND_STENCIL2D = 2, ISING_KIND_STENCIL3D = 3 };
+
+typedef struct ising_graph_info {
+    uint64_t nvars;
+    uint64_t nedges;
+    int32_t kind;         /* ISING_KIND_*                                                  */
+    int32_t ncolors;      /* colour classes of the sweep                                   */
+    int32_t max_degree;
+    int32_t integer_classes; /* 1: all |J| equal and no bias -> bit-sliced integer kernel  */
+    uint64_t dims[3];     /* stencil extents (x fastest), 1 where unused                   */
+    double jabs;          /* common |J| when integer_classes                               */
+} ising_graph_info;
+
+/* Edge list in SoA form, a copy of Lattice.edges: Vec<((usize,usize),f64)> (lattice.rs:31);
+ * biases = nvars values or NULL for 0 (lattice.rs:186-189).  The host compiles CSR + a
+ * greedy colouring and recognises row-major square / cubic tori (checkerboard layout). */
+ISING_API int ising_graph_from_edges(ising_ctx *ctx, uint64_t nvars, uint64_t nedges, const uint64_t *a,
+                           const uint64_t *b, const double *j, const double *biases,
+                           ising_graph **out);
+/* Additive constructor for lattices too large for a Python edge list: dim in {2,3}, periodic,
+ * site index x + Lx*(y + Ly*z).  pmj = 0: every bond = j0;  pmj = 1: bond = +-|j0| iid with
+ * probability 1/2 from Philox(j_seed) (one disorder sample shared by all experiments). */
+ISING_API int ising_graph_torus(ising_ctx *ctx, int dim, const uint64_t *L, double j0, int pmj,
+                      uint64_t j_seed, ising_graph **out);
+ISING_API void ising_graph_destroy(ising_graph *g);
+ISING_API int ising_graph_get_info(const ising_graph *g, ising_graph_info *out);
+ISING_API int ising_graph_get_colors(const ising_graph *g, uint32_t *colors /* nvars */);
+ISING_API int ising_graph_get_edges(const ising_graph *g, uint64_t *a, uint64_t *b, double *j);
+
+/* ---- seeds (Lattice::make_seeds, lattice.rs:83-91, seed_gen = Some(seed)) ---------------- */
+ISING_API int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t *out);
+
+/* ---- device-resident simulation: E experiments of one graph, replica-bit-packed ---------- */
+/* replica_offset = global index of this shard's first experiment (multiple of 32); it only
+ * enters the Philox counters, so a sharded run reproduces the unsharded one bit for bit.   */
+ISING_API int ising_sim_create(ising_ctx *ctx, const ising_graph *g, uint64_t num_experiments,
+                     uint64_t seed, uint64_t replica_offset, ising_sim **out);
+ISING_API void ising_sim_destroy(ising_sim *sim);
+/* Tuning knobs of the multi-spin-coded kernel; 0 keeps the default.  planes = bit-planes
+ * compared before the per-bit resolver (4..8), rounds = Philox4x32 rounds (7 or 10).      */
+ISING_API int ising_sim_configure(ising_sim *sim, int planes, int rounds);
+/* Random start (GraphState::new's make_random_spin_state, one Philox bit per spin) ...     */
+ISING_API int ising_sim_randomize(ising_sim *sim);
+/* ... or the same given state for every experiment (Lattice.set_initial_state, :201-203).  */
+ISING_API int ising_sim_set_state(ising_sim *sim, const uint8_t *state /* nvars */);
+/* Per-experiment states, bool[E, nvars] (ClassicIsing.add_graph(initial_state)).           */
+ISING_API int ising_sim_set_states(ising_sim *sim, const uint8_t *states /* E*nvars */);
+/* nsweeps colour-class sweeps (1 sweep = every site attempted once = one reference
+ * "timestep" of nvars attempts); sweep k runs at betas[k].  If energies_per_sweep != NULL it
+ * receives double[E, nsweeps] (GraphState::get_energy after every timestep, lattice.rs:454). */
+ISING_API int ising_sim_sweeps(ising_sim *sim, const double *betas, uint64_t nsweeps,
+                     double *energies_per_sweep);
+ISING_API int ising_sim_get_energies(ising_sim *sim, double *energies /* E */);
+ISING_API int ising_sim_get_states(ising_sim *sim, uint8_t *states /* E*nvars, bool */);
+/* Opt-in packed read-back: uint32[nvars, ceil(E/32)] in natural site order (bit e%32 of word
+ * e/32 is experiment e) -- 8x less D2H than bool[E, nvars].                                 */
+ISING_API int ising_sim_get_packed(ising_sim *sim, uint32_t *words);
+/* per-experiment magnetisation sum_i s_i */
+ISING_API int ising_sim_get_magnetization(ising_sim *sim, double *m /* E */);
+
+typedef struct ising_sim_stats {
+    uint64_t kernel_launches;  /* kernels launched by this sim since creation / last reset   */
+    uint64_t sweeps;
+    uint64_t flip_attempts;    /* E_padded-free count: E * nvars * sweeps                    */
+    double sweep_device_ms;    /* CUDA-event time of the sweep kernels (on the ctx stream)   */
+    double sweep_kernel_ms;    /* same, summed over sweep-kernel launches only               */
+    uint64_t sweep_kernel_launches;
+} ising_sim_stats;
+ISING_API int ising_sim_get_stats(ising_sim *sim, ising_sim_stats *out);
+ISING_API int ising_sim_reset_stats(ising_sim *sim);
+
+/* ---- one blocking call per pymethod (host buffers in, host buffers out) ------------------ */
+enum {
+    ISING_FLAG_ONLY_BASIC_MOVES = 1u << 0,  /* informational: the GPU path is always basic  */
+    ISING_FLAG_PER_STEP_ENERGIES = 1u << 1, /* annealing_and_get_energies                   */
+    ISING_FLAG_LINEAR_SCHEDULE = 1u << 2,   /* documented interpolation instead of quirk Q1 */
+    ISING_FLAG_EDGE_IMPORTANCE = 1u << 3    /* -> ISING_E_UNSUPPORTED (deviation D2)        */
+};
+
+typedef struct ising_run_args {
+    uint32_t struct_size;        /* sizeof(ising_run_args)                                  */
+    uint32_t flags;
+    double beta;                 /* run / sampling                                          */
+    const uint64_t *sched_t;     /* annealing stops (time, beta), any order, may be empty   */
+    const double *sched_beta;
+    uint64_t sched_len;
+    uint64_t timesteps;
+    uint64_t num_experiments;
+    uint64_t thermalization;     /* sampling                                                */
+    uint64_t sampling_freq;      /* sampling; 0 -> ISING_E_INVALID                          */
+    uint64_t seed;               /* Philox key (Lattice.seed_gen or entropy drawn by caller) */
+    uint64_t replica_offset;     /* see ising_sim_create                                    */
+    const uint8_t *initial_state; /* nvars bools or NULL                                    */
+} ising_run_args;
+
+/* Lattice::run_monte_carlo, lattice.rs:171-221: energies[E], states bool[E, nvars]. */
+ISING_API int ising_run_monte_carlo(ising_ctx *ctx, const ising_graph *g, const ising_run_args *args,
+                          double *energies, uint8_t *states);
+/* Lattice::run_monte_carlo_sampling, lattice.rs:231-299: energies[E, n_s], states[E, n_s, nvars]
+ * with n_s = timesteps / sampling_freq. */
+ISING_API int ising_run_monte_carlo_sampling(ising_ctx *ctx, const ising_graph *g,
+                                   const ising_run_args *args, double *energies,
+                                   uint8_t *states);
+/* Lattice::run_monte_carlo_annealing (lattice.rs:309-385; energies[E]) and
+ * ..._and_get_energies (395-470; ISING_FLAG_PER_STEP_ENERGIES, energies[E, timesteps]). */
+ISING_API int ising_run_monte_carlo_annealing(ising_ctx *ctx, const ising_graph *g,
+                                    const ising_run_args *args, double *energies,
+                                    uint8_t *states);
+/* The per-timestep betas the annealing entry points use (schedule normalisation of
+ * lattice.rs:320-334 and the beta expression of :357-365).  out[timesteps]. */
+ISING_API int ising_schedule_betas(const uint64_t *sched_t, const double *sched_beta, uint64_t sched_len,
+                         uint64_t timesteps, int linear, double *out);
+
+/* ---- replay mode: the reference's own (site, uniform) sequence, bit-exact ---------------- */
+/* Sequential random-site Metropolis exactly as GraphState::do_spin_flip / should_flip:
+ * dE summed over the adjacency in ascending neighbour order in f64, accept iff
+ * !(dE > 0) || u < exp(-beta dE).  sites[E, nattempts], u[E, nattempts] (entries of attempts
+ * with dE <= 0 are ignored), init bool[E, nvars]; energies[E], states bool[E, nvars]. */
+ISING_API int ising_replay(ising_ctx *ctx, const ising_graph *g, double beta, uint64_t num_experiments,
+                 uint64_t nattempts, const uint32_t *sites, const double *u,
+                 const uint8_t *init, double *energies, uint8_t *states);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISING_B200_H */

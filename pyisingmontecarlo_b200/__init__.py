@@ -1,0 +1,10 @@
+"""B200-native classical Ising Monte Carlo engine behind the `py_monte_carlo.Lattice` API.
+
+Only the data-parallel classical path is here: `Lattice.run_monte_carlo*`,
+the annealing runs, replay mode and the parallel-tempering loop.  Compute lives in
+`libising_b200.so` (hand-written sm_100a CUDA behind the C ABI of include/ising_b200.h).
+"""
+from ._native import AmbiguousReplay, Context, Graph, NativeLibraryMissing, Sim  # noqa: F401
+from .lattice import Lattice  # noqa: F401
+
+__all__ = ["Lattice", "Sim", "Graph", "Context", "AmbiguousReplay", "NativeLibraryMissing"]

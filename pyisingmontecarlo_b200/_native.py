@@ -1,0 +1,353 @@
+"""ctypes binding of libising_b200.so (include/ising_b200.h).
+
+This is the only door to the compute path: if the shared library (built by
+``pyisingmontecarlo_b200._build.build_native`` / ``__graft_entry__.build``) is missing, or no
+sm_100 device is visible, the calls fail loudly -- there is no CPU or eager fallback.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libising_b200.so")
+
+ISING_OK, ISING_E_INVALID, ISING_E_CUDA, ISING_E_UNSUPPORTED, ISING_E_AMBIGUOUS, ISING_E_NOMEM = range(6)
+
+FLAG_ONLY_BASIC_MOVES = 1 << 0
+FLAG_PER_STEP_ENERGIES = 1 << 1
+FLAG_LINEAR_SCHEDULE = 1 << 2
+FLAG_EDGE_IMPORTANCE = 1 << 3
+
+KIND_GENERAL, KIND_STENCIL2D, KIND_STENCIL3D = 0, 2, 3
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class AmbiguousReplay(RuntimeError):
+    pass
+
+
+class GraphInfo(C.Structure):
+    _fields_ = [
+        ("nvars", C.c_uint64),
+        ("nedges", C.c_uint64),
+        ("kind", C.c_int32),
+        ("ncolors", C.c_int32),
+        ("max_degree", C.c_int32),
+        ("integer_classes", C.c_int32),
+        ("dims", C.c_uint64 * 3),
+        ("jabs", C.c_double),
+    ]
+
+
+class SimStats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64),
+        ("sweeps", C.c_uint64),
+        ("flip_attempts", C.c_uint64),
+        ("sweep_device_ms", C.c_double),
+        ("sweep_kernel_ms", C.c_double),
+        ("sweep_kernel_launches", C.c_uint64),
+    ]
+
+
+class RunArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("beta", C.c_double),
+        ("sched_t", C.c_void_p),
+        ("sched_beta", C.c_void_p),
+        ("sched_len", C.c_uint64),
+        ("timesteps", C.c_uint64),
+        ("num_experiments", C.c_uint64),
+        ("thermalization", C.c_uint64),
+        ("sampling_freq", C.c_uint64),
+        ("seed", C.c_uint64),
+        ("replica_offset", C.c_uint64),
+        ("initial_state", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "ising_abi_version": (C.c_int, []),
+    "ising_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "ising_ctx_destroy": (None, [_P]),
+    "ising_last_error": (C.c_char_p, [_P]),
+    "ising_graph_from_edges": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, C.POINTER(_P)]),
+    "ising_graph_torus": (C.c_int, [_P, C.c_int, _P, C.c_double, C.c_int, C.c_uint64, C.POINTER(_P)]),
+    "ising_graph_destroy": (None, [_P]),
+    "ising_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),
+    "ising_graph_get_colors": (C.c_int, [_P, _P]),
+    "ising_graph_get_edges": (C.c_int, [_P, _P, _P, _P]),
+    "ising_make_seeds": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
+    "ising_sim_create": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
+    "ising_sim_destroy": (None, [_P]),
+    "ising_sim_configure": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ising_sim_randomize": (C.c_int, [_P]),
+    "ising_sim_set_state": (C.c_int, [_P, _P]),
+    "ising_sim_set_states": (C.c_int, [_P, _P]),
+    "ising_sim_sweeps": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "ising_sim_get_energies": (C.c_int, [_P, _P]),
+    "ising_sim_get_states": (C.c_int, [_P, _P]),
+    "ising_sim_get_packed": (C.c_int, [_P, _P]),
+    "ising_sim_get_magnetization": (C.c_int, [_P, _P]),
+    "ising_sim_get_stats": (C.c_int, [_P, C.POINTER(SimStats)]),
+    "ising_sim_reset_stats": (C.c_int, [_P]),
+    "ising_run_monte_carlo": (C.c_int, [_P, _P, C.POINTER(RunArgs), _P, _P]),
+    "ising_run_monte_carlo_sampling": (C.c_int, [_P, _P, C.POINTER(RunArgs), _P, _P]),
+    "ising_run_monte_carlo_annealing": (C.c_int, [_P, _P, C.POINTER(RunArgs), _P, _P]),
+    "ising_schedule_betas": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_int, _P]),
+    "ising_replay": (C.c_int, [_P, _P, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def exported_symbols():
+    """Every entry point include/ising_b200.h declares."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Loads libising_b200.so once; raises NativeLibraryMissing if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeLibraryMissing(
+                    f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                    "pyisingmontecarlo_b200 has no CPU fallback."
+                )
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def _err(ctx):
+    msg = lib().ising_last_error(ctx)
+    return msg.decode("utf-8", "replace") if msg else "unknown error"
+
+
+def check(rc, ctx=None):
+    if rc == ISING_OK:
+        return
+    msg = _err(ctx)
+    if rc == ISING_E_INVALID:
+        raise ValueError(msg)
+    if rc == ISING_E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == ISING_E_AMBIGUOUS:
+        raise AmbiguousReplay(msg)
+    if rc == ISING_E_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(arr):
+    return None if arr is None else arr.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + stream (ising_ctx)."""
+
+    _cache = {}
+
+    def __init__(self, device=0):
+        self.device = int(device)
+        h = C.c_void_p()
+        check(lib().ising_ctx_create(self.device, C.byref(h)), None)
+        self.handle = h
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if "LOCAL_RANK" in os.environ else 0
+        key = (os.getpid(), int(device))
+        if key not in cls._cache:
+            cls._cache[key] = Context(device)
+        return cls._cache[key]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().ising_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Graph:
+    """Compiled coupling graph (ising_graph): CSR + colouring, or a checkerboard stencil."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.handle = handle
+        info = GraphInfo()
+        check(lib().ising_graph_get_info(handle, C.byref(info)), ctx.handle)
+        self.nvars = int(info.nvars)
+        self.nedges = int(info.nedges)
+        self.kind = int(info.kind)
+        self.ncolors = int(info.ncolors)
+        self.max_degree = int(info.max_degree)
+        self.integer_classes = bool(info.integer_classes)
+        self.dims = tuple(int(d) for d in info.dims)
+        self.jabs = float(info.jabs)
+
+    @classmethod
+    def from_edges(cls, ctx, nvars, a, b, j, biases=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        j = np.ascontiguousarray(j, dtype=np.float64)
+        bias = None if biases is None else np.ascontiguousarray(biases, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().ising_graph_from_edges(ctx.handle, int(nvars), len(a), ptr(a), ptr(b), ptr(j),
+                                           ptr(bias), C.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def torus(cls, ctx, dims, j0=-1.0, pmj=False, j_seed=0):
+        L = np.ascontiguousarray(list(dims) + [1] * (3 - len(dims)), dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().ising_graph_torus(ctx.handle, len(dims), ptr(L), float(j0), int(bool(pmj)),
+                                      int(j_seed), C.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    def colors(self):
+        out = np.empty(self.nvars, dtype=np.uint32)
+        check(lib().ising_graph_get_colors(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def edges(self):
+        a = np.empty(self.nedges, dtype=np.uint64)
+        b = np.empty(self.nedges, dtype=np.uint64)
+        j = np.empty(self.nedges, dtype=np.float64)
+        check(lib().ising_graph_get_edges(self.handle, ptr(a), ptr(b), ptr(j)), self.ctx.handle)
+        return a, b, j
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().ising_graph_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Sim:
+    """Device-resident replica-bit-packed experiments (ising_sim)."""
+
+    def __init__(self, graph, num_experiments, seed, replica_offset=0, planes=0, rounds=0):
+        self.graph = graph
+        self.ctx = graph.ctx
+        self.E = int(num_experiments)
+        h = C.c_void_p()
+        check(lib().ising_sim_create(self.ctx.handle, graph.handle, self.E, int(seed) & (2**64 - 1),
+                                     int(replica_offset), C.byref(h)), self.ctx.handle)
+        self.handle = h
+        if planes or rounds:
+            check(lib().ising_sim_configure(h, int(planes), int(rounds)), self.ctx.handle)
+
+    def randomize(self):
+        check(lib().ising_sim_randomize(self.handle), self.ctx.handle)
+
+    def set_state(self, state):
+        s = np.ascontiguousarray(state, dtype=np.uint8)
+        if s.shape != (self.graph.nvars,):
+            raise ValueError("state must have nvars entries")
+        check(lib().ising_sim_set_state(self.handle, ptr(s)), self.ctx.handle)
+
+    def set_states(self, states):
+        s = np.ascontiguousarray(states, dtype=np.uint8)
+        if s.shape != (self.E, self.graph.nvars):
+            raise ValueError("states must be [num_experiments, nvars]")
+        check(lib().ising_sim_set_states(self.handle, ptr(s)), self.ctx.handle)
+
+    def sweeps(self, betas, per_sweep_energies=False):
+        b = np.ascontiguousarray(betas, dtype=np.float64)
+        out = np.empty((self.E, len(b)), dtype=np.float64) if per_sweep_energies else None
+        check(lib().ising_sim_sweeps(self.handle, ptr(b), len(b), ptr(out)), self.ctx.handle)
+        return out
+
+    def energies(self):
+        out = np.empty(self.E, dtype=np.float64)
+        check(lib().ising_sim_get_energies(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def magnetization(self):
+        out = np.empty(self.E, dtype=np.float64)
+        check(lib().ising_sim_get_magnetization(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def states(self, out=None):
+        if out is None:
+            out = np.empty((self.E, self.graph.nvars), dtype=np.bool_)
+        check(lib().ising_sim_get_states(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def packed(self):
+        out = np.empty((self.graph.nvars, (self.E + 31) // 32), dtype=np.uint32)
+        check(lib().ising_sim_get_packed(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def stats(self):
+        st = SimStats()
+        check(lib().ising_sim_get_stats(self.handle, C.byref(st)), self.ctx.handle)
+        return {k: getattr(st, k) for k, _ in SimStats._fields_}
+
+    def reset_stats(self):
+        check(lib().ising_sim_reset_stats(self.handle), self.ctx.handle)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().ising_sim_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_seeds(seed_gen, n):
+    out = np.empty(int(n), dtype=np.uint64)
+    check(lib().ising_make_seeds(int(seed_gen) & (2**64 - 1), int(n), ptr(out)))
+    return out
+
+
+def schedule_betas(stops, timesteps, linear=False):
+    """Per-timestep betas of the annealing entry points (lattice.rs:320-334, 357-365)."""
+    t = np.ascontiguousarray([s[0] for s in stops], dtype=np.uint64)
+    b = np.ascontiguousarray([s[1] for s in stops], dtype=np.float64)
+    out = np.empty(int(timesteps), dtype=np.float64)
+    check(lib().ising_schedule_betas(ptr(t), ptr(b), len(t), int(timesteps), int(bool(linear)), ptr(out)))
+    return out
+
+
+def run_args(**kw):
+    a = RunArgs()
+    a.struct_size = C.sizeof(RunArgs)
+    keep = []
+    for k, v in kw.items():
+        if k in ("sched_t", "sched_beta", "initial_state"):
+            if v is not None:
+                keep.append(v)
+                setattr(a, k, v.ctypes.data)
+        else:
+            setattr(a, k, v)
+    a._keepalive = keep
+    return a

@@ -1,0 +1,764 @@
+// C ABI of libising_b200.so (include/ising_b200.h).  Host orchestration only: argument
+// checks with the reference's error behaviour, device buffers, kernel launches, CUDA-event
+// timing.  There is deliberately no CPU implementation behind these entry points: without a
+// CUDA device every compute call fails with ISING_E_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ising_b200.h"
+#include "graph.h"
+#include "kernels.h"
+#include "philox.h"
+
+using namespace ising;
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_global_error;
+
+struct ising_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int sm_count = 0;
+};
+
+struct ising_graph {
+    ising_ctx* ctx = nullptr;
+    HostGraph h;
+    // device copies
+    uint32_t* d_jmask = nullptr;   // stencil +-J bond masks [2][2*dim][halfN]
+    uint64_t* d_row = nullptr;     // CSR for replay / general kernels (uploaded on demand)
+    uint32_t* d_nbr = nullptr;
+    double* d_jv = nullptr;
+    double* d_bias = nullptr;
+};
+
+struct ising_sim {
+    ising_ctx* ctx = nullptr;
+    const ising_graph* g = nullptr;
+    uint64_t E = 0;
+    uint64_t seed = 0;
+    uint64_t replica_offset = 0;
+    Layout lay{};
+    uint32_t* d_spins = nullptr;
+    unsigned long long* d_counts = nullptr;  // per-experiment integer accumulator [W*32]
+    uint64_t sweep_counter = 0;
+    int planes = 6, rounds = 10;
+    ising_sim_stats stats{};
+};
+
+static int fail(ising_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_global_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                          \
+    do {                                                                             \
+        cudaError_t _e = (call);                                                     \
+        if (_e != cudaSuccess)                                                       \
+            return fail((ctx), ISING_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int ising_abi_version(void) { return ISING_ABI_VERSION; }
+
+extern "C" const char* ising_last_error(const ising_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_global_error.c_str();
+}
+
+extern "C" int ising_ctx_create(int device, ising_ctx** out) {
+    if (!out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ISING_E_CUDA,
+                    "no CUDA device available (%s); libising_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, ISING_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, ISING_E_CUDA,
+                    "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    std::unique_ptr<ising_ctx> ctx(new ising_ctx);
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev1));
+    *out = ctx.release();
+    return ISING_OK;
+}
+
+extern "C" void ising_ctx_destroy(ising_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------
+// graph
+// ------------------------------------------------------------------------------------------
+static int upload_stencil_masks(ising_ctx* ctx, ising_graph* g) {
+    const HostGraph& h = g->h;
+    if (h.kind == ISING_KIND_GENERAL || h.uniform_sign) return ISING_OK;
+    const int dim = h.kind == ISING_KIND_STENCIL3D ? 3 : 2;
+    const uint64_t Lx = h.dims[0], Ly = h.dims[1], Lz = h.dims[2];
+    const uint64_t Lxh = Lx / 2, rows = Ly * Lz, halfN = h.nvars / 2;
+    std::vector<uint32_t> m((size_t)2 * 2 * dim * halfN);
+    auto sgn = [&](uint64_t x, uint64_t y, uint64_t z, int d) -> uint32_t {
+        const uint64_t n = x + Lx * (y + Ly * z);
+        return ((h.fwd_sign[n] >> d) & 1) ? 0xFFFFFFFFu : 0u;
+    };
+    for (uint32_t c = 0; c < 2; ++c)
+        for (uint64_t r = 0; r < rows; ++r) {
+            const uint64_t z = r / Ly, y = r % Ly;
+            const uint32_t p = (uint32_t)((y + z + c) & 1);
+            for (uint64_t xh = 0; xh < Lxh; ++xh) {
+                const uint64_t x = 2 * xh + p;
+                const uint64_t xm = x == 0 ? Lx - 1 : x - 1;
+                const uint64_t ym = y == 0 ? Ly - 1 : y - 1, zm = z == 0 ? Lz - 1 : z - 1;
+                uint32_t* base = m.data() + (size_t)c * 2 * dim * halfN + r * Lxh + xh;
+                // k = 0: neighbour stored at the same half-index (x+1 if p == 0 else x-1)
+                // k = 1: the other x neighbour;  2: y-1  3: y+1  4: z-1  5: z+1
+                const uint32_t jxp = sgn(x, y, z, 0), jxm = sgn(xm, y, z, 0);
+                base[0 * halfN] = p == 0 ? jxp : jxm;
+                base[1 * halfN] = p == 0 ? jxm : jxp;
+                base[2 * halfN] = sgn(x, ym, z, 1);
+                base[3 * halfN] = sgn(x, y, z, 1);
+                if (dim == 3) {
+                    base[4 * halfN] = sgn(x, y, zm, 2);
+                    base[5 * halfN] = sgn(x, y, z, 2);
+                }
+            }
+        }
+    CUDA_TRY(ctx, dev_alloc(&g->d_jmask, m.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jmask, m.data(), m.size() * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice));
+    return ISING_OK;
+}
+
+static int ensure_csr_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->d_row) return ISING_OK;
+    g->h.build_csr();
+    const HostGraph& h = g->h;
+    CUDA_TRY(ctx, dev_alloc(&g->d_row, h.row.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_nbr, h.nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_jv, h.jv.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_bias, h.nvars));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_row, h.row.data(), h.row.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_nbr, h.nbr.data(), h.nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jv, h.jv.data(), h.jv.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<double> b(h.nvars, 0.0);
+    if (h.has_bias) b = h.bias;
+    CUDA_TRY(ctx, cudaMemcpy(g->d_bias, b.data(), h.nvars * 8, cudaMemcpyHostToDevice));
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_from_edges(ising_ctx* ctx, uint64_t nvars, uint64_t nedges,
+                                      const uint64_t* a, const uint64_t* b, const double* j,
+                                      const double* biases, ising_graph** out) {
+    if (!ctx || !out) return fail(ctx, ISING_E_INVALID, "ctx/out is NULL");
+    *out = nullptr;
+    if (nedges && (!a || !b || !j)) return fail(ctx, ISING_E_INVALID, "edge arrays are NULL");
+    std::unique_ptr<ising_graph> g(new ising_graph);
+    g->ctx = ctx;
+    const std::string msg = compile_from_edges(nvars, nedges, a, b, j, biases, &g->h);
+    if (!msg.empty()) return fail(ctx, ISING_E_INVALID, "%s", msg.c_str());
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int rc = upload_stencil_masks(ctx, g.get());
+    if (rc) return rc;
+    *out = g.release();
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_torus(ising_ctx* ctx, int dim, const uint64_t* L, double j0, int pmj,
+                                 uint64_t j_seed, ising_graph** out) {
+    if (!ctx || !out || !L) return fail(ctx, ISING_E_INVALID, "ctx/out/L is NULL");
+    *out = nullptr;
+    std::unique_ptr<ising_graph> g(new ising_graph);
+    g->ctx = ctx;
+    const std::string msg = make_torus(dim, L, j0, pmj, j_seed, &g->h);
+    if (!msg.empty()) return fail(ctx, ISING_E_INVALID, "%s", msg.c_str());
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int rc = upload_stencil_masks(ctx, g.get());
+    if (rc) return rc;
+    *out = g.release();
+    return ISING_OK;
+}
+
+extern "C" void ising_graph_destroy(ising_graph* g) {
+    if (!g) return;
+    if (g->ctx) cudaSetDevice(g->ctx->device);
+    cudaFree(g->d_jmask);
+    cudaFree(g->d_row);
+    cudaFree(g->d_nbr);
+    cudaFree(g->d_jv);
+    cudaFree(g->d_bias);
+    delete g;
+}
+
+extern "C" int ising_graph_get_info(const ising_graph* g, ising_graph_info* out) {
+    if (!g || !out) return fail(nullptr, ISING_E_INVALID, "graph/out is NULL");
+    const HostGraph& h = g->h;
+    out->nvars = h.nvars;
+    out->nedges = h.nedges;
+    out->kind = h.kind;
+    out->ncolors = h.ncolors;
+    out->max_degree = h.max_degree;
+    out->integer_classes = h.integer_classes ? 1 : 0;
+    out->dims[0] = h.dims[0];
+    out->dims[1] = h.dims[1];
+    out->dims[2] = h.dims[2];
+    out->jabs = h.jabs;
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_get_colors(const ising_graph* g, uint32_t* colors) {
+    if (!g || !colors) return fail(nullptr, ISING_E_INVALID, "graph/colors is NULL");
+    for (uint64_t n = 0; n < g->h.nvars; ++n) colors[n] = g->h.color_of(n);
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_get_edges(const ising_graph* g, uint64_t* a, uint64_t* b, double* j) {
+    if (!g || !a || !b || !j) return fail(nullptr, ISING_E_INVALID, "graph/arrays NULL");
+    for (uint64_t e = 0; e < g->h.nedges; ++e) g->h.edge_at(e, a + e, b + e, j + e);
+    return ISING_OK;
+}
+
+extern "C" int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t* out) {
+    if (n && !out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
+    make_seeds(seed_gen, n, out);
+    return ISING_OK;
+}
+
+extern "C" int ising_schedule_betas(const uint64_t* st, const double* sb, uint64_t n,
+                                    uint64_t timesteps, int linear, double* out) {
+    if ((n && (!st || !sb)) || (timesteps && !out))
+        return fail(nullptr, ISING_E_INVALID, "schedule arrays are NULL");
+    if (!schedule_betas(st, sb, n, timesteps, linear != 0, out))
+        return fail(nullptr, ISING_E_INVALID, "annealing schedule has fewer than two stops");
+    return ISING_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// simulation object
+// ------------------------------------------------------------------------------------------
+static void count_launch(ising_sim* s, int n) {
+    if (n > 0) s->stats.kernel_launches += (uint64_t)n;
+}
+
+extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E, uint64_t seed,
+                                uint64_t replica_offset, ising_sim** out) {
+    if (!ctx || !g || !out) return fail(ctx, ISING_E_INVALID, "ctx/graph/out is NULL");
+    *out = nullptr;
+    if (g->ctx != ctx) return fail(ctx, ISING_E_INVALID, "graph belongs to another context");
+    if (E == 0) return fail(ctx, ISING_E_INVALID, "num_experiments must be > 0");
+    if (replica_offset % 32) return fail(ctx, ISING_E_INVALID, "replica_offset must be a multiple of 32");
+    const HostGraph& h = g->h;
+    if (h.kind == ISING_KIND_GENERAL)
+        return fail(ctx, ISING_E_UNSUPPORTED,
+                    "general-graph production sweeps are not built yet in this revision");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<ising_sim> s(new ising_sim);
+    s->ctx = ctx;
+    s->g = g;
+    s->E = E;
+    s->seed = seed;
+    s->replica_offset = replica_offset;
+    Layout& L = s->lay;
+    L.kind = h.kind;
+    L.Lx = (uint32_t)h.dims[0];
+    L.Ly = (uint32_t)h.dims[1];
+    L.Lz = (uint32_t)h.dims[2];
+    L.Lxh = L.Lx / 2;
+    L.rows = L.Ly * L.Lz;
+    L.W = (uint32_t)((E + 31) / 32);
+    L.nvars = h.nvars;
+    L.halfN = h.nvars / 2;
+    const size_t words = (size_t)h.nvars * L.W;
+    CUDA_TRY(ctx, dev_alloc(&s->d_spins, words));
+    CUDA_TRY(ctx, dev_alloc(&s->d_counts, (size_t)L.W * 32));
+    *out = s.release();
+    return ising_sim_randomize(*out);
+}
+
+extern "C" void ising_sim_destroy(ising_sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_spins);
+    cudaFree(s->d_counts);
+    delete s;
+}
+
+extern "C" int ising_sim_configure(ising_sim* s, int planes, int rounds) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    if (planes) {
+        if (planes < 4 || planes > 8) return fail(s->ctx, ISING_E_INVALID, "planes must be 4..8");
+        s->planes = planes;
+    }
+    if (rounds) {
+        if (rounds != 7 && rounds != 10) return fail(s->ctx, ISING_E_INVALID, "rounds must be 7 or 10");
+        s->rounds = rounds;
+    }
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_randomize(ising_sim* s) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    count_launch(s, launch_init_random(s->d_spins, s->lay, (uint32_t)s->seed,
+                                       (uint32_t)(s->seed >> 32),
+                                       (uint32_t)(s->replica_offset / 32), ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_set_state(ising_sim* s, const uint8_t* state) {
+    if (!s || !state) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/state is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    uint8_t* d = nullptr;
+    CUDA_TRY(ctx, dev_alloc(&d, s->lay.nvars));
+    cudaError_t e = cudaMemcpyAsync(d, state, s->lay.nvars, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        count_launch(s, launch_init_broadcast(s->d_spins, s->lay, d, ctx->stream));
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d);
+    CUDA_TRY(ctx, e);
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_set_states(ising_sim* s, const uint8_t* states) {
+    if (!s || !states) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/states is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    uint8_t* d = nullptr;
+    const size_t bytes = (size_t)s->E * s->lay.nvars;
+    CUDA_TRY(ctx, dev_alloc(&d, bytes));
+    cudaError_t e = cudaMemcpyAsync(d, states, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        count_launch(s, launch_pack_states(s->d_spins, s->lay, d, s->E, ctx->stream));
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d);
+    CUDA_TRY(ctx, e);
+    return ISING_OK;
+}
+
+// dE of the uphill classes in units of |J|: stencil 2D {4, 8}, 3D {4, 8, 12}
+static void fill_thresholds(const HostGraph& h, double beta, int K, MscThresholds* th) {
+    const int dim = h.kind == ISING_KIND_STENCIL3D ? 3 : 2;
+    memset(th, 0, sizeof *th);
+    for (int c = 0; c < dim; ++c) {
+        const double de = 4.0 * (c + 1) * h.jabs;
+        const double p = exp(-beta * de);
+        const double scaled = ldexp(p, K + 32);
+        const uint64_t tmax = (1ull << (K + 32)) - 1;
+        uint64_t T;
+        if (!(scaled >= 0.0)) T = 0;  // NaN beta: never accept uphill
+        else if (scaled >= (double)tmax) T = tmax;
+        else T = (uint64_t)floor(scaled);
+        for (int pl = 0; pl < K; ++pl)
+            th->plane[c][pl] = ((T >> (K + 31 - pl)) & 1ull) ? 0xFFFFFFFFu : 0u;
+        th->low[c] = (uint32_t)(T & 0xFFFFFFFFull);
+    }
+}
+
+static int sim_one_sweep(ising_sim* s, double beta) {
+    ising_ctx* ctx = s->ctx;
+    const HostGraph& h = s->g->h;
+    SweepArgs a;
+    a.spins = s->d_spins;
+    a.jmask = s->g->d_jmask;
+    a.lay = s->lay;
+    a.sweep = (uint32_t)s->sweep_counter;
+    a.key0 = (uint32_t)s->seed;
+    a.key1 = (uint32_t)(s->seed >> 32);
+    a.gw0 = (uint32_t)(s->replica_offset / 32);
+    a.antiferro = h.uniform_antiferro ? 0xFFFFFFFFu : 0u;
+    a.planes = s->planes;
+    a.rounds = s->rounds;
+    fill_thresholds(h, beta, s->planes, &a.th);
+    const int n = launch_sweep_stencil(a, ctx->stream);
+    if (n < 0) return fail(ctx, ISING_E_CUDA, "sweep launch failed: %s",
+                           cudaGetErrorString(cudaGetLastError()));
+    count_launch(s, n);
+    s->stats.sweep_kernel_launches += (uint64_t)n;
+    s->sweep_counter++;
+    s->stats.sweeps++;
+    s->stats.flip_attempts += s->E * h.nvars;
+    return ISING_OK;
+}
+
+// n_sat per experiment into s->d_counts (zeroed first)
+static int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
+    ising_ctx* ctx = s->ctx;
+    const HostGraph& h = s->g->h;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)s->lay.W * 32 * sizeof(unsigned long long),
+                                  ctx->stream));
+    const int n = launch_nsat_stencil(s->d_spins, s->g->d_jmask, s->lay,
+                                      h.uniform_antiferro ? 0xFFFFFFFFu : 0u, d_counts,
+                                      ctx->stream);
+    if (n < 0) return fail(ctx, ISING_E_CUDA, "energy launch failed");
+    count_launch(s, n);
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps,
+                                double* energies_per_sweep) {
+    if (!s || (nsweeps && !betas)) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const HostGraph& h = s->g->h;
+    const uint64_t E = s->E;
+    if (!energies_per_sweep) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        for (uint64_t t = 0; t < nsweeps; ++t) {
+            const int rc = sim_one_sweep(s, betas[t]);
+            if (rc) return rc;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        s->stats.sweep_device_ms += ms;
+        s->stats.sweep_kernel_ms += ms;
+        return ISING_OK;
+    }
+    // per-sweep energies: integer n_sat history on the device, converted and transposed to
+    // double[E, nsweeps] there, one D2H per chunk
+    const uint64_t chunk_max = 2048;
+    const size_t cw = (size_t)s->lay.W * 32;
+    unsigned long long* d_hist = nullptr;
+    double* d_out = nullptr;
+    CUDA_TRY(ctx, dev_alloc(&d_hist, cw * std::min(chunk_max, nsweeps)));
+    cudaError_t e = dev_alloc(&d_out, (size_t)E * std::min(chunk_max, nsweeps));
+    if (e != cudaSuccess) { cudaFree(d_hist); CUDA_TRY(ctx, e); }
+    std::vector<double> host;
+    int rc = ISING_OK;
+    for (uint64_t t0 = 0; t0 < nsweeps && rc == ISING_OK; t0 += chunk_max) {
+        const uint64_t nt = std::min(chunk_max, nsweeps - t0);
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t) {
+            rc = sim_one_sweep(s, betas[t0 + t]);
+            if (rc == ISING_OK) rc = sim_count_nsat(s, d_hist + t * cw);
+            if (rc == ISING_OK)
+                count_launch(s, launch_energy_from_nsat(d_hist + t * cw, E, h.jabs, h.nedges,
+                                                        d_out, nt, t, ctx->stream));
+        }
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        if (rc != ISING_OK) break;
+        host.resize((size_t)E * nt);
+        e = cudaMemcpyAsync(host.data(), d_out, host.size() * sizeof(double),
+                            cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, ISING_E_CUDA, "energy read-back: %s", cudaGetErrorString(e)); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        s->stats.sweep_device_ms += ms;
+        for (uint64_t ex = 0; ex < E; ++ex)
+            memcpy(energies_per_sweep + ex * nsweeps + t0, host.data() + ex * nt, nt * sizeof(double));
+    }
+    cudaFree(d_hist);
+    cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
+    if (!s || !energies) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/energies is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const HostGraph& h = s->g->h;
+    int rc = sim_count_nsat(s, s->d_counts);
+    if (rc) return rc;
+    double* d_out = nullptr;
+    CUDA_TRY(ctx, dev_alloc(&d_out, s->E));
+    count_launch(s, launch_energy_from_nsat(s->d_counts, s->E, h.jabs, h.nedges, d_out, 1, 0,
+                                            ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(energies, d_out, s->E * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    CUDA_TRY(ctx, e);
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_get_magnetization(ising_sim* s, double* m) {
+    if (!s || !m) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/m is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t cw = (size_t)s->lay.W * 32;
+    CUDA_TRY(ctx, cudaMemsetAsync(s->d_counts, 0, cw * sizeof(unsigned long long), ctx->stream));
+    count_launch(s, launch_count_up(s->d_spins, s->lay, s->d_counts, ctx->stream));
+    std::vector<unsigned long long> up(cw);
+    CUDA_TRY(ctx, cudaMemcpyAsync(up.data(), s->d_counts, cw * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint64_t e = 0; e < s->E; ++e)
+        m[e] = 2.0 * (double)up[e] - (double)s->lay.nvars;
+    return ISING_OK;
+}
+
+// bool[E, nvars] to host memory, staged through a device buffer in slabs of experiments
+static int sim_states_to_host(ising_sim* s, uint8_t* states) {
+    ising_ctx* ctx = s->ctx;
+    const uint64_t N = s->lay.nvars;
+    const size_t bytes = (size_t)s->E * N;
+    uint8_t* d = nullptr;
+    CUDA_TRY(ctx, dev_alloc(&d, bytes));
+    count_launch(s, launch_unpack_states(s->d_spins, s->lay, d, s->E, N, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(states, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CUDA_TRY(ctx, e);
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_get_states(ising_sim* s, uint8_t* states) {
+    if (!s || !states) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/states is NULL");
+    CUDA_TRY(s->ctx, cudaSetDevice(s->ctx->device));
+    return sim_states_to_host(s, states);
+}
+
+extern "C" int ising_sim_get_packed(ising_sim* s, uint32_t* words) {
+    if (!s || !words) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/words is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)s->lay.nvars * s->lay.W;
+    uint32_t* d = nullptr;
+    CUDA_TRY(ctx, dev_alloc(&d, n));
+    count_launch(s, launch_export_natural(s->d_spins, s->lay, d, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(words, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CUDA_TRY(ctx, e);
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_get_stats(ising_sim* s, ising_sim_stats* out) {
+    if (!s || !out) return fail(nullptr, ISING_E_INVALID, "sim/out is NULL");
+    *out = s->stats;
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_reset_stats(ising_sim* s) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    s->stats = ising_sim_stats{};
+    return ISING_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one blocking call per pymethod
+// ------------------------------------------------------------------------------------------
+static int check_run_args(ising_ctx* ctx, const ising_graph* g, const ising_run_args* a,
+                          const void* energies, const void* states) {
+    if (!ctx || !g || !a) return fail(ctx, ISING_E_INVALID, "ctx/graph/args is NULL");
+    if (a->struct_size != sizeof(ising_run_args))
+        return fail(ctx, ISING_E_INVALID, "ising_run_args.struct_size mismatch (%u != %zu)",
+                    a->struct_size, sizeof(ising_run_args));
+    if (a->flags & ISING_FLAG_EDGE_IMPORTANCE)
+        return fail(ctx, ISING_E_UNSUPPORTED,
+                    "edge_move_importance_sampling only affects the reference's non-basic edge "
+                    "moves, which the GPU path does not perform");
+    if (a->num_experiments && (!energies || !states))
+        return fail(ctx, ISING_E_INVALID, "output buffers are NULL");
+    return ISING_OK;
+}
+
+static int make_sim_for_run(ising_ctx* ctx, const ising_graph* g, const ising_run_args* a,
+                            ising_sim** sim) {
+    int rc = ising_sim_create(ctx, g, a->num_experiments, a->seed, a->replica_offset, sim);
+    if (rc) return rc;
+    if (a->initial_state) rc = ising_sim_set_state(*sim, a->initial_state);
+    if (rc) { ising_sim_destroy(*sim); *sim = nullptr; }
+    return rc;
+}
+
+extern "C" int ising_run_monte_carlo(ising_ctx* ctx, const ising_graph* g,
+                                     const ising_run_args* a, double* energies, uint8_t* states) {
+    int rc = check_run_args(ctx, g, a, energies, states);
+    if (rc) return rc;
+    if (a->num_experiments == 0) return ISING_OK;
+    ising_sim* sim = nullptr;
+    rc = make_sim_for_run(ctx, g, a, &sim);
+    if (rc) return rc;
+    std::vector<double> betas(a->timesteps, a->beta);
+    rc = ising_sim_sweeps(sim, betas.data(), a->timesteps, nullptr);
+    if (rc == ISING_OK) rc = ising_sim_get_energies(sim, energies);
+    if (rc == ISING_OK) rc = ising_sim_get_states(sim, states);
+    ising_sim_destroy(sim);
+    return rc;
+}
+
+extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph* g,
+                                              const ising_run_args* a, double* energies,
+                                              uint8_t* states) {
+    int rc = check_run_args(ctx, g, a, energies, states);
+    if (rc) return rc;
+    if (a->sampling_freq == 0)
+        return fail(ctx, ISING_E_INVALID, "sampling_freq must be > 0 (the reference divides by it)");
+    if (a->num_experiments == 0) return ISING_OK;
+    const uint64_t ns = a->timesteps / a->sampling_freq;
+    const uint64_t E = a->num_experiments, N = g->h.nvars;
+    ising_sim* sim = nullptr;
+    rc = make_sim_for_run(ctx, g, a, &sim);
+    if (rc) return rc;
+    std::vector<double> betas(std::max<uint64_t>(a->thermalization, a->sampling_freq), a->beta);
+    rc = ising_sim_sweeps(sim, betas.data(), a->thermalization, nullptr);
+    // states[E, ns, N]: sample k of experiment e lands at (e * ns + k) * N; unpack straight
+    // into a device image of that layout slab by slab
+    uint8_t* d = nullptr;
+    double* d_en = nullptr;
+    cudaError_t ce = cudaSuccess;
+    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, (1ull << 30) / std::max<uint64_t>(1, E * N)));
+    if (rc == ISING_OK && ns) {
+        ce = dev_alloc(&d, (size_t)E * slab * N);
+        if (ce == cudaSuccess) ce = dev_alloc(&d_en, (size_t)E * slab);
+        if (ce != cudaSuccess) rc = fail(ctx, ISING_E_NOMEM, "sampling staging: %s", cudaGetErrorString(ce));
+    }
+    std::vector<double> en_host;
+    std::vector<uint8_t> st_host;
+    for (uint64_t k0 = 0; k0 < ns && rc == ISING_OK; k0 += slab) {
+        const uint64_t nk = std::min(slab, ns - k0);
+        for (uint64_t k = 0; k < nk && rc == ISING_OK; ++k) {
+            rc = ising_sim_sweeps(sim, betas.data(), a->sampling_freq, nullptr);
+            if (rc) break;
+            count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d + k * N, E, nk * N,
+                                                   ctx->stream));
+            rc = sim_count_nsat(sim, sim->d_counts);
+            if (rc) break;
+            count_launch(sim, launch_energy_from_nsat(sim->d_counts, E, g->h.jabs, g->h.nedges,
+                                                      d_en, nk, k, ctx->stream));
+        }
+        if (rc) break;
+        en_host.resize((size_t)E * nk);
+        st_host.resize(nk == ns ? 0 : (size_t)E * nk * N);
+        uint8_t* dst = nk == ns ? states : st_host.data();
+        ce = cudaMemcpyAsync(dst, d, (size_t)E * nk * N, cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess)
+            ce = cudaMemcpyAsync(en_host.data(), d_en, en_host.size() * 8, cudaMemcpyDeviceToHost,
+                                 ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) { rc = fail(ctx, ISING_E_CUDA, "sampling read-back: %s", cudaGetErrorString(ce)); break; }
+        for (uint64_t e = 0; e < E; ++e) {
+            memcpy(energies + e * ns + k0, en_host.data() + e * nk, nk * sizeof(double));
+            if (nk != ns)
+                memcpy(states + (e * ns + k0) * N, st_host.data() + e * nk * N, (size_t)nk * N);
+        }
+    }
+    cudaFree(d);
+    cudaFree(d_en);
+    ising_sim_destroy(sim);
+    return rc;
+}
+
+extern "C" int ising_run_monte_carlo_annealing(ising_ctx* ctx, const ising_graph* g,
+                                               const ising_run_args* a, double* energies,
+                                               uint8_t* states) {
+    int rc = check_run_args(ctx, g, a, energies, states);
+    if (rc) return rc;
+    if (a->sched_len && (!a->sched_t || !a->sched_beta))
+        return fail(ctx, ISING_E_INVALID, "schedule arrays are NULL");
+    std::vector<double> betas(a->timesteps);
+    if (!schedule_betas(a->sched_t, a->sched_beta, a->sched_len, a->timesteps,
+                        (a->flags & ISING_FLAG_LINEAR_SCHEDULE) != 0, betas.data()))
+        return fail(ctx, ISING_E_INVALID, "annealing schedule has fewer than two stops");
+    if (a->num_experiments == 0) return ISING_OK;
+    ising_sim* sim = nullptr;
+    rc = make_sim_for_run(ctx, g, a, &sim);
+    if (rc) return rc;
+    if (a->flags & ISING_FLAG_PER_STEP_ENERGIES) {
+        rc = ising_sim_sweeps(sim, betas.data(), a->timesteps, energies);
+    } else {
+        rc = ising_sim_sweeps(sim, betas.data(), a->timesteps, nullptr);
+        if (rc == ISING_OK) rc = ising_sim_get_energies(sim, energies);
+    }
+    if (rc == ISING_OK) rc = ising_sim_get_states(sim, states);
+    ising_sim_destroy(sim);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// replay
+// ------------------------------------------------------------------------------------------
+extern "C" int ising_replay(ising_ctx* ctx, const ising_graph* g, double beta, uint64_t E,
+                            uint64_t A, const uint32_t* sites, const double* u,
+                            const uint8_t* init, double* energies, uint8_t* states) {
+    if (!ctx || !g) return fail(ctx, ISING_E_INVALID, "ctx/graph is NULL");
+    if (E == 0) return ISING_OK;
+    if (!init || !energies || !states || (A && (!sites || !u)))
+        return fail(ctx, ISING_E_INVALID, "replay buffers are NULL");
+    const uint64_t N = g->h.nvars;
+    for (uint64_t i = 0; i < E * A; ++i)
+        if (sites[i] >= N) return fail(ctx, ISING_E_INVALID, "trace site %u out of range", sites[i]);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_csr_on_device(ctx, const_cast<ising_graph*>(g));
+    if (rc) return rc;
+    uint32_t* d_sites = nullptr;
+    double* d_u = nullptr;
+    uint8_t* d_states = nullptr;
+    double* d_en = nullptr;
+    unsigned int* d_amb = nullptr;
+    cudaError_t e = dev_alloc(&d_sites, E * A);
+    if (e == cudaSuccess) e = dev_alloc(&d_u, E * A);
+    if (e == cudaSuccess) e = dev_alloc(&d_states, E * N);
+    if (e == cudaSuccess) e = dev_alloc(&d_en, E);
+    if (e == cudaSuccess) e = dev_alloc(&d_amb, 1);
+    unsigned int amb = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sites, sites, E * A * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u, E * A * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_states, init, E * N, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_amb, 0, sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess) {
+        ReplayArgs ra;
+        ra.E = E; ra.N = N; ra.A = A;
+        ra.row = g->d_row; ra.nbr = g->d_nbr; ra.jv = g->d_jv; ra.bias = g->d_bias;
+        ra.sites = d_sites; ra.u = d_u; ra.states = d_states; ra.energies = d_en;
+        ra.beta = beta; ra.ambiguous = d_amb;
+        if (launch_replay(ra, ctx->stream) < 0) e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(states, d_states, E * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(energies, d_en, E * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&amb, d_amb, sizeof amb, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sites); cudaFree(d_u); cudaFree(d_states); cudaFree(d_en); cudaFree(d_amb);
+    CUDA_TRY(ctx, e);
+    if (amb)
+        return fail(ctx, ISING_E_AMBIGUOUS,
+                    "%u replayed decisions had u within 4e-15 of exp(-beta dE); not certified", amb);
+    return ISING_OK;
+}

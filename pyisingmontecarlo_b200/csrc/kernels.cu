@@ -1,0 +1,613 @@
+// sm_100a kernels of the classical Ising engine.  See DESIGN.md for the algorithm; every
+// kernel here is integer / bitwise work on replica-bit-packed words (no tensor cores: the path
+// is not a contraction).
+#include "kernels.h"
+
+#include "../../include/ising_b200.h"
+#include "philox.h"
+
+namespace ising {
+
+// ------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t site_word_base(const Layout& L, uint64_t n) {
+    if (L.kind == ISING_KIND_GENERAL) return (size_t)n * L.W;
+    const uint32_t x = (uint32_t)(n % L.Lx);
+    const uint32_t r = (uint32_t)(n / L.Lx);  // row = z * Ly + y
+    const uint32_t y = r % L.Ly, z = r / L.Ly;
+    const uint32_t c = (x + y + z) & 1u;
+    return (((size_t)c * L.rows + r) * L.Lxh + (x >> 1)) * L.W;
+}
+
+// ------------------------------------------------------------------------------------------
+// bit-sliced satisfied-bond count of one word: planes (b0, b1, b2) of n_sat in 0..2*DIM
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    return (a & b) | (c & (a ^ b));
+}
+
+template <int DIM>
+__device__ __forceinline__ void count_sat(const uint32_t (&a)[2 * DIM], uint32_t& b0,
+                                          uint32_t& b1, uint32_t& b2) {
+    if (DIM == 3) {
+        const uint32_t s0 = a[0] ^ a[1] ^ a[2], c0 = maj3(a[0], a[1], a[2]);
+        const uint32_t s1 = a[3] ^ a[4] ^ a[5], c1 = maj3(a[3], a[4], a[5]);
+        const uint32_t k = s0 & s1;
+        b0 = s0 ^ s1;
+        b1 = c0 ^ c1 ^ k;
+        b2 = maj3(c0, c1, k);
+    } else {
+        const uint32_t s0 = a[0] ^ a[1] ^ a[2], c0 = maj3(a[0], a[1], a[2]);
+        const uint32_t k = s0 & a[3];
+        b0 = s0 ^ a[3];
+        b1 = c0 ^ k;
+        b2 = c0 & k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Metropolis acceptance of the uphill bits of one word.
+//   up   : bits with dE > 0;  (sel1, sel0) select the class of each such bit
+//   K bit-planes R_0..R_{K-1} are compared MSB-first against the class threshold; a bit still
+//   undecided afterwards (probability 2^-K) is resolved by a fresh 32-bit word against the low
+//   32 threshold bits, undecided bits taken in ascending position.  Word R_m is output m%4 of
+//   Philox call m/4 on counter (site, replica word, sweep, call).
+// returns the mask of accepted uphill bits
+// ------------------------------------------------------------------------------------------
+template <int NCLS, int K, int ROUNDS>
+__device__ __forceinline__ uint32_t msc_accept(uint32_t up, uint32_t sel0, uint32_t sel1,
+                                               const MscThresholds& th, uint32_t site,
+                                               uint32_t gw, uint32_t sweep, uint32_t k0,
+                                               uint32_t k1) {
+    constexpr int NCALL = K / 4 + 1;
+    uint32_t r[NCALL * 4];
+#pragma unroll
+    for (int q = 0; q < NCALL; ++q) {
+        const u32x4 o = philox4x32<ROUNDS>(site, gw, sweep, (uint32_t)q | (TAG_ACCEPT << 24), k0, k1);
+        r[4 * q + 0] = o.x;
+        r[4 * q + 1] = o.y;
+        r[4 * q + 2] = o.z;
+        r[4 * q + 3] = o.w;
+    }
+    uint32_t eq = up, lt = 0;
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+        uint32_t t = (sel0 & th.plane[1][p]) | (~sel0 & th.plane[0][p]);
+        if (NCLS == 3) t = (sel1 & th.plane[2][p]) | (~sel1 & t);
+        lt |= eq & ~r[p] & t;
+        eq &= ~(r[p] ^ t);
+    }
+    if (eq) {  // rare per bit (2^-K), handled per lane
+        int j = K;
+        u32x4 cur = {r[4 * (NCALL - 1)], r[4 * (NCALL - 1) + 1], r[4 * (NCALL - 1) + 2],
+                     r[4 * (NCALL - 1) + 3]};
+        do {
+            const int b = __ffs((int)eq) - 1;
+            if ((j & 3) == 0 && j >= 4 * NCALL)
+                cur = philox4x32<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24),
+                                         k0, k1);
+            const int m = j & 3;
+            const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
+            uint32_t lo = ((sel0 >> b) & 1u) ? th.low[1] : th.low[0];
+            if (NCLS == 3 && ((sel1 >> b) & 1u)) lo = th.low[2];
+            if (v < lo) lt |= 1u << b;
+            eq &= eq - 1;
+            ++j;
+        } while (eq);
+    }
+    return lt;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: one colour phase of a checkerboard sweep on a square / cubic torus
+// block = (WX lanes over replica words, BY over half-row positions); one row per iteration
+// ------------------------------------------------------------------------------------------
+template <int DIM, bool PMJ, int K, int ROUNDS>
+__global__ void __launch_bounds__(256)
+k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
+                const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
+                uint32_t k0, uint32_t k1, uint32_t gw0, uint32_t antiferro, MscThresholds th) {
+    const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
+    const size_t rowlen = (size_t)Lxh * W;
+    for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
+        const uint32_t z = row / Ly, y = row - z * Ly;
+        const uint32_t p = (y + z + c) & 1u;
+        const uint32_t ym = y == 0 ? Ly - 1 : y - 1, yp = y + 1 == Ly ? 0 : y + 1;
+        uint32_t* __restrict__ o_c = own + (size_t)row * rowlen;
+        const uint32_t* __restrict__ n_x = oth + (size_t)row * rowlen;
+        const uint32_t* __restrict__ n_ym = oth + (size_t)(z * Ly + ym) * rowlen;
+        const uint32_t* __restrict__ n_yp = oth + (size_t)(z * Ly + yp) * rowlen;
+        const uint32_t* __restrict__ n_zm = nullptr;
+        const uint32_t* __restrict__ n_zp = nullptr;
+        if (DIM == 3) {
+            const uint32_t zm = z == 0 ? Lz - 1 : z - 1, zp = z + 1 == Lz ? 0 : z + 1;
+            n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
+            n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
+        }
+        for (uint32_t xh = threadIdx.y; xh < Lxh; xh += blockDim.y) {
+            const uint32_t xs = p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
+            uint32_t m[2 * DIM];
+#pragma unroll
+            for (int k = 0; k < 2 * DIM; ++k)
+                m[k] = PMJ ? __ldg(jm + (size_t)k * L.halfN + (size_t)row * Lxh + xh) : antiferro;
+            const uint32_t site = row * L.Lx + 2 * xh + p;
+            for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) {
+                const size_t i = (size_t)xh * W + w;
+                const uint32_t s = o_c[i];
+                uint32_t a[2 * DIM];
+                a[0] = ~(s ^ n_x[i] ^ m[0]);
+                a[1] = ~(s ^ n_x[(size_t)xs * W + w] ^ m[1]);
+                a[2] = ~(s ^ n_ym[i] ^ m[2]);
+                a[3] = ~(s ^ n_yp[i] ^ m[3]);
+                if (DIM == 3) {
+                    a[4] = ~(s ^ n_zm[i] ^ m[4]);
+                    a[5] = ~(s ^ n_zp[i] ^ m[5]);
+                }
+                uint32_t b0, b1, b2;
+                count_sat<DIM>(a, b0, b1, b2);
+                uint32_t up, lt;
+                if (DIM == 3) {  // n_sat 4,5,6 -> dE = 4,8,12 |J|
+                    up = b2;
+                    lt = msc_accept<3, K, ROUNDS>(up, b0, b1, th, site, gw0 + w, sweep, k0, k1);
+                } else {  // n_sat 3,4 -> dE = 4,8 |J|
+                    up = b2 | (b1 & b0);
+                    lt = msc_accept<2, K, ROUNDS>(up, b2, 0u, th, site, gw0 + w, sweep, k0, k1);
+                }
+                o_c[i] = s ^ (~up | lt);
+            }
+        }
+    }
+}
+
+template <int DIM, bool PMJ, int K>
+static int sweep_dispatch_rounds(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block) {
+    const Layout& L = a.lay;
+    const size_t csz = (size_t)L.halfN * L.W;
+    const size_t jsz = (size_t)2 * DIM * L.halfN;
+    for (uint32_t c = 0; c < 2; ++c) {
+        uint32_t* own = a.spins + c * csz;
+        const uint32_t* oth = a.spins + (1 - c) * csz;
+        const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
+        if (a.rounds == 7)
+            k_sweep_stencil<DIM, PMJ, K, 7><<<grid, block, 0, st>>>(
+                own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th);
+        else
+            k_sweep_stencil<DIM, PMJ, K, 10><<<grid, block, 0, st>>>(
+                own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th);
+    }
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+template <int DIM, bool PMJ>
+static int sweep_dispatch_planes(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block) {
+    switch (a.planes) {
+        case 4: return sweep_dispatch_rounds<DIM, PMJ, 4>(a, st, grid, block);
+        case 5: return sweep_dispatch_rounds<DIM, PMJ, 5>(a, st, grid, block);
+        case 6: return sweep_dispatch_rounds<DIM, PMJ, 6>(a, st, grid, block);
+        case 7: return sweep_dispatch_rounds<DIM, PMJ, 7>(a, st, grid, block);
+        case 8: return sweep_dispatch_rounds<DIM, PMJ, 8>(a, st, grid, block);
+        default: return -1;
+    }
+}
+
+static uint32_t pow2_ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static void stencil_block_shape(const Layout& L, dim3* grid, dim3* block, bool persistent) {
+    const uint32_t wx = L.W >= 32 ? 32 : pow2_ceil(L.W);
+    uint32_t by = 256 / wx;
+    const uint32_t need = pow2_ceil(L.Lxh);
+    if (by > need) by = need;
+    if (wx * by < 32) by = 32 / wx;
+    *block = dim3(wx, by, 1);
+    uint32_t g = L.rows;
+    if (persistent && g > 148u * 8u) g = 148u * 8u;
+    *grid = dim3(g, 1, 1);
+}
+
+int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
+    dim3 grid, block;
+    stencil_block_shape(a.lay, &grid, &block, false);
+    const bool pmj = a.jmask != nullptr;
+    if (a.lay.kind == ISING_KIND_STENCIL3D)
+        return pmj ? sweep_dispatch_planes<3, true>(a, st, grid, block)
+                   : sweep_dispatch_planes<3, false>(a, st, grid, block);
+    if (a.lay.kind == ISING_KIND_STENCIL2D)
+        return pmj ? sweep_dispatch_planes<2, true>(a, st, grid, block)
+                   : sweep_dispatch_planes<2, false>(a, st, grid, block);
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: positional popcount (per-experiment integer observables from packed words)
+// vertical counters: plane l of VCount holds bit l of 32 independent counters
+// ------------------------------------------------------------------------------------------
+template <int NP>
+struct VCount {
+    uint32_t v[NP];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int l = 0; l < NP; ++l) v[l] = 0;
+    }
+    // counters += b0 + 2 b1 + 4 b2
+    __device__ __forceinline__ void add3(uint32_t b0, uint32_t b1, uint32_t b2) {
+        uint32_t c = v[0] & b0;
+        v[0] ^= b0;
+        uint32_t t = v[1] ^ b1, c2 = (v[1] & b1) | (c & t);
+        v[1] = t ^ c;
+        c = c2;
+        t = v[2] ^ b2;
+        c2 = (v[2] & b2) | (c & t);
+        v[2] = t ^ c;
+        c = c2;
+#pragma unroll
+        for (int l = 3; l < NP; ++l) {
+            t = v[l] & c;
+            v[l] ^= c;
+            c = t;
+        }
+    }
+    __device__ __forceinline__ void add1(uint32_t b0) {
+        uint32_t c = b0;
+#pragma unroll
+        for (int l = 0; l < NP; ++l) {
+            const uint32_t t = v[l] & c;
+            v[l] ^= c;
+            c = t;
+        }
+    }
+    // sm is int[32][nthreads]; adds this thread's 32 counters to its column
+    __device__ __forceinline__ void flush(int* sm, int tid, int nthreads) {
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b) {
+            int cnt = 0;
+#pragma unroll
+            for (int l = 0; l < NP; ++l) cnt |= (int)((v[l] >> b) & 1u) << l;
+            sm[b * nthreads + tid] += cnt;
+        }
+        clear();
+    }
+};
+
+constexpr int VC_PLANES = 12;           // counters up to 4095
+constexpr int VC_FLUSH_ADD3 = 4095 / 7; // adds of <= 7 before a flush
+constexpr int VC_FLUSH_ADD1 = 4095;
+
+// reduce sm[32][nthreads] over threadIdx.y and add to out[(w0 + tx) * 32 + b]
+__device__ __forceinline__ void block_reduce_counts(int* sm, unsigned long long* out, uint32_t w0,
+                                                    uint32_t W) {
+    const int wx = blockDim.x, by = blockDim.y, nthreads = wx * by;
+    const int tid = threadIdx.y * wx + threadIdx.x;
+    __syncthreads();
+    for (int idx = tid; idx < 32 * wx; idx += nthreads) {
+        const int b = idx / wx, tx = idx - b * wx;
+        if (w0 + tx >= W) continue;
+        long long sum = 0;
+        for (int ty = 0; ty < by; ++ty) sum += sm[b * nthreads + ty * wx + tx];
+        if (sum) atomicAdd(out + (size_t)(w0 + tx) * 32 + b, (unsigned long long)sum);
+    }
+    __syncthreads();
+}
+
+template <int DIM, bool PMJ>
+__global__ void __launch_bounds__(256)
+k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ jm, Layout L,
+               uint32_t antiferro, unsigned long long* __restrict__ nsat) {
+    __shared__ int sm[32 * 256];
+    const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
+    const size_t rowlen = (size_t)Lxh * W;
+    const size_t csz = (size_t)L.halfN * W;
+    const uint32_t* __restrict__ own = spins;        // colour 0 sites: every bond exactly once
+    const uint32_t* __restrict__ oth = spins + csz;
+    const int nthreads = blockDim.x * blockDim.y;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (uint32_t w0 = 0; w0 < W; w0 += blockDim.x) {
+        for (int b = 0; b < 32; ++b) sm[b * nthreads + tid] = 0;
+        const uint32_t w = w0 + threadIdx.x;
+        VCount<VC_PLANES> vc;
+        vc.clear();
+        int pending = 0;
+        if (w < W) {
+            for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
+                const uint32_t z = row / Ly, y = row - z * Ly;
+                const uint32_t p = (y + z) & 1u;
+                const uint32_t ym = y == 0 ? Ly - 1 : y - 1, yp = y + 1 == Ly ? 0 : y + 1;
+                const uint32_t* o_c = own + (size_t)row * rowlen;
+                const uint32_t* n_x = oth + (size_t)row * rowlen;
+                const uint32_t* n_ym = oth + (size_t)(z * Ly + ym) * rowlen;
+                const uint32_t* n_yp = oth + (size_t)(z * Ly + yp) * rowlen;
+                const uint32_t* n_zm = nullptr;
+                const uint32_t* n_zp = nullptr;
+                if (DIM == 3) {
+                    const uint32_t zm = z == 0 ? Lz - 1 : z - 1, zp = z + 1 == Lz ? 0 : z + 1;
+                    n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
+                    n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
+                }
+                for (uint32_t xh = threadIdx.y; xh < Lxh; xh += blockDim.y) {
+                    const uint32_t xs =
+                        p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
+                    const size_t i = (size_t)xh * W + w;
+                    const uint32_t s = o_c[i];
+                    uint32_t m[2 * DIM], a[2 * DIM];
+#pragma unroll
+                    for (int k = 0; k < 2 * DIM; ++k)
+                        m[k] = PMJ ? __ldg(jm + (size_t)k * L.halfN + (size_t)row * Lxh + xh)
+                                   : antiferro;
+                    a[0] = ~(s ^ n_x[i] ^ m[0]);
+                    a[1] = ~(s ^ n_x[(size_t)xs * W + w] ^ m[1]);
+                    a[2] = ~(s ^ n_ym[i] ^ m[2]);
+                    a[3] = ~(s ^ n_yp[i] ^ m[3]);
+                    if (DIM == 3) {
+                        a[4] = ~(s ^ n_zm[i] ^ m[4]);
+                        a[5] = ~(s ^ n_zp[i] ^ m[5]);
+                    }
+                    uint32_t b0, b1, b2;
+                    count_sat<DIM>(a, b0, b1, b2);
+                    vc.add3(b0, b1, b2);
+                    if (++pending == VC_FLUSH_ADD3) {
+                        vc.flush(sm, tid, nthreads);
+                        pending = 0;
+                    }
+                }
+            }
+            vc.flush(sm, tid, nthreads);
+        }
+        block_reduce_counts(sm, nsat, w0, W);
+    }
+}
+
+int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
+                        uint32_t antiferro, unsigned long long* nsat, cudaStream_t st) {
+    dim3 grid, block;
+    stencil_block_shape(lay, &grid, &block, true);
+    const bool pmj = jmask != nullptr;
+    if (lay.kind == ISING_KIND_STENCIL3D) {
+        if (pmj) k_nsat_stencil<3, true><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
+        else k_nsat_stencil<3, false><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
+    } else if (lay.kind == ISING_KIND_STENCIL2D) {
+        if (pmj) k_nsat_stencil<2, true><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
+        else k_nsat_stencil<2, false><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
+    } else {
+        return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// up-spin count over all sites (any layout: the sum runs over every stored site word)
+__global__ void __launch_bounds__(256)
+k_count_up(const uint32_t* __restrict__ spins, uint64_t nsites, uint32_t W,
+           unsigned long long* __restrict__ up) {
+    __shared__ int sm[32 * 256];
+    const int nthreads = blockDim.x * blockDim.y;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (uint32_t w0 = 0; w0 < W; w0 += blockDim.x) {
+        for (int b = 0; b < 32; ++b) sm[b * nthreads + tid] = 0;
+        const uint32_t w = w0 + threadIdx.x;
+        VCount<VC_PLANES> vc;
+        vc.clear();
+        int pending = 0;
+        if (w < W) {
+            for (uint64_t n = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y; n < nsites;
+                 n += (uint64_t)gridDim.x * blockDim.y) {
+                vc.add1(spins[(size_t)n * W + w]);
+                if (++pending == VC_FLUSH_ADD1) {
+                    vc.flush(sm, tid, nthreads);
+                    pending = 0;
+                }
+            }
+            vc.flush(sm, tid, nthreads);
+        }
+        block_reduce_counts(sm, up, w0, W);
+    }
+}
+
+int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long* up,
+                    cudaStream_t st) {
+    const uint32_t wx = lay.W >= 32 ? 32 : pow2_ceil(lay.W);
+    dim3 block(wx, 256 / wx, 1);
+    uint64_t g = (lay.nvars + block.y - 1) / block.y;
+    if (g > 148u * 8u) g = 148u * 8u;
+    if (g == 0) g = 1;
+    k_count_up<<<dim3((unsigned)g), block, 0, st>>>(spins, lay.nvars, lay.W, up);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void k_energy_from_nsat(const unsigned long long* __restrict__ nsat, uint64_t E,
+                                   double scale, uint64_t nbonds, double* __restrict__ out,
+                                   uint64_t estride, uint64_t eoff) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const long long v = (long long)nbonds - 2ll * (long long)nsat[e];
+    out[e * estride + eoff] = scale * (double)v;
+}
+
+int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,
+                            uint64_t nbonds, double* out_dev, uint64_t estride, uint64_t eoff,
+                            cudaStream_t st) {
+    const unsigned g = (unsigned)((E + 255) / 256);
+    k_energy_from_nsat<<<g ? g : 1, 256, 0, st>>>(nsat, E, scale, nbonds, out_dev, estride, eoff);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// state initialisation / import / export (not hot)
+// ------------------------------------------------------------------------------------------
+__global__ void k_init_random(uint32_t* __restrict__ spins, Layout L, uint32_t k0, uint32_t k1,
+                              uint32_t gw0) {
+    const uint64_t total = L.nvars * L.W;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t n = i / L.W;
+        const uint32_t w = (uint32_t)(i - n * L.W);
+        const u32x4 r = philox4x32<10>((uint32_t)n, gw0 + w, 0u, TAG_INIT << 24, k0, k1);
+        spins[site_word_base(L, n) + w] = r.x;
+    }
+}
+
+int launch_init_random(uint32_t* spins, const Layout& lay, uint32_t key0, uint32_t key1,
+                       uint32_t gw0, cudaStream_t st) {
+    k_init_random<<<148 * 8, 256, 0, st>>>(spins, lay, key0, key1, gw0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void k_init_broadcast(uint32_t* __restrict__ spins, Layout L,
+                                 const uint8_t* __restrict__ state) {
+    const uint64_t total = L.nvars * L.W;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t n = i / L.W;
+        const uint32_t w = (uint32_t)(i - n * L.W);
+        spins[site_word_base(L, n) + w] = state[n] ? 0xFFFFFFFFu : 0u;
+    }
+}
+
+int launch_init_broadcast(uint32_t* spins, const Layout& lay, const uint8_t* state_dev,
+                          cudaStream_t st) {
+    k_init_broadcast<<<148 * 8, 256, 0, st>>>(spins, lay, state_dev);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// bool[E, N] -> packed; lanes run over sites so the byte reads coalesce
+__global__ void k_pack_states(uint32_t* __restrict__ spins, Layout L,
+                              const uint8_t* __restrict__ states, uint64_t E) {
+    const uint64_t total = L.nvars * L.W;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(i / L.nvars);
+        const uint64_t n = i - (uint64_t)w * L.nvars;
+        uint32_t word = 0;
+        for (int b = 0; b < 32; ++b) {
+            const uint64_t e = (uint64_t)w * 32 + b;
+            if (e < E && states[e * L.nvars + n]) word |= 1u << b;
+        }
+        spins[site_word_base(L, n) + w] = word;
+    }
+}
+
+int launch_pack_states(uint32_t* spins, const Layout& lay, const uint8_t* states_dev, uint64_t E,
+                       cudaStream_t st) {
+    k_pack_states<<<148 * 8, 256, 0, st>>>(spins, lay, states_dev, E);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// K8: packed -> bool[E, N].  A warp takes 128 consecutive sites of one replica word: lane l
+// holds sites 4l..4l+3 and writes one 32-bit store (4 bools) per experiment, so each warp
+// store covers 128 contiguous bytes of one output row.
+__global__ void __launch_bounds__(256)
+k_unpack_states(const uint32_t* __restrict__ spins, Layout L, uint8_t* __restrict__ out,
+                uint64_t E, uint64_t out_stride) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t chunks = (L.nvars + 127) / 128;
+    const bool vec_ok = (L.nvars % 4 == 0) && (out_stride % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(out) & 3u) == 0);
+    for (uint64_t item = warp; item < chunks * L.W; item += nwarps) {
+        const uint64_t chunk = item / L.W;
+        const uint32_t w = (uint32_t)(item - chunk * L.W);
+        const uint64_t n0 = chunk * 128 + 4 * lane;
+        uint32_t word[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            word[k] = (n0 + k < L.nvars) ? spins[site_word_base(L, n0 + k) + w] : 0u;
+        const uint64_t e0 = (uint64_t)w * 32;
+        const int nb = (int)(E - e0 < 32 ? E - e0 : 32);
+        if (vec_ok) {
+            if (n0 < L.nvars)
+                for (int b = 0; b < nb; ++b) {
+                    const uint32_t v = ((word[0] >> b) & 1u) | (((word[1] >> b) & 1u) << 8) |
+                                       (((word[2] >> b) & 1u) << 16) |
+                                       (((word[3] >> b) & 1u) << 24);
+                    *reinterpret_cast<uint32_t*>(out + (e0 + b) * out_stride + n0) = v;
+                }
+        } else {
+            for (int b = 0; b < nb; ++b)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (n0 + k < L.nvars)
+                        out[(e0 + b) * out_stride + n0 + k] = (uint8_t)((word[k] >> b) & 1u);
+        }
+    }
+}
+
+int launch_unpack_states(const uint32_t* spins, const Layout& lay, uint8_t* out_dev, uint64_t E,
+                         uint64_t out_stride, cudaStream_t st) {
+    k_unpack_states<<<148 * 8, 256, 0, st>>>(spins, lay, out_dev, E, out_stride);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void k_export_natural(const uint32_t* __restrict__ spins, Layout L,
+                                 uint32_t* __restrict__ out) {
+    const uint64_t total = L.nvars * L.W;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t n = i / L.W;
+        const uint32_t w = (uint32_t)(i - n * L.W);
+        out[i] = spins[site_word_base(L, n) + w];
+    }
+}
+
+int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* out_dev,
+                          cudaStream_t st) {
+    k_export_natural<<<148 * 8, 256, 0, st>>>(spins, lay, out_dev);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: replay of the reference's (site, uniform) sequence; one thread per experiment, f64,
+// no fused multiply-add so every rounding matches the CPU restatement
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_replay(ReplayArgs a) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.E) return;
+    uint8_t* st = a.states + e * a.N;
+    const uint32_t* sites = a.sites + e * a.A;
+    const double* u = a.u + e * a.A;
+    unsigned int amb = 0;
+    for (uint64_t t = 0; t < a.A; ++t) {
+        const uint32_t site = sites[t];
+        const uint8_t cur = st[site];
+        double de = 0.0;
+        for (uint64_t k = a.row[site]; k < a.row[site + 1]; ++k) {
+            const double coupling = (cur == st[a.nbr[k]]) ? 1.0 : -1.0;
+            de = __dadd_rn(de, __dmul_rn(__dmul_rn(-2.0, a.jv[k]), coupling));
+        }
+        de = __dadd_rn(de, __dmul_rn(__dmul_rn(2.0, a.bias[site]), cur ? 1.0 : -1.0));
+        bool flip = true;
+        if (de > 0.0) {
+            const double chance = exp(__dmul_rn(-a.beta, de));
+            const double uu = u[t];
+            flip = uu < chance;
+            // device exp and the host libm may differ in the last place: refuse to certify a
+            // decision that close to the threshold instead of guessing
+            if (fabs(uu - chance) <= chance * 4.0e-15) ++amb;
+        }
+        if (flip) st[site] = cur ^ 1;
+    }
+    // GraphState::get_energy order: per site sum_adj(J*coupling/2), then + bias term
+    double acc = 0.0;
+    for (uint64_t i = 0; i < a.N; ++i) {
+        double total = 0.0;
+        const uint8_t si = st[i];
+        for (uint64_t k = a.row[i]; k < a.row[i + 1]; ++k) {
+            const double coupling = (si == st[a.nbr[k]]) ? 1.0 : -1.0;
+            total = __dadd_rn(total, __dmul_rn(a.jv[k], coupling) / 2.0);
+        }
+        const double bias_e = si ? -a.bias[i] : a.bias[i];
+        acc = __dadd_rn(__dadd_rn(acc, total), bias_e);
+    }
+    a.energies[e] = acc;
+    if (amb) atomicAdd(a.ambiguous, amb);
+}
+
+int launch_replay(const ReplayArgs& a, cudaStream_t st) {
+    const unsigned g = (unsigned)((a.E + 127) / 128);
+    k_replay<<<g ? g : 1, 128, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace ising

@@ -1,0 +1,82 @@
+// Launch wrappers of the sm_100a kernels (kernels.cu).  Host-callable, no CUDA types beyond
+// cudaStream_t so that api.cpp stays plain C++.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ising {
+
+// Replica-bit-packed spin storage.  One 32-bit word = one site in 32 experiments.
+//   general graph : word(n, w) at n * W + w                          (natural site order)
+//   stencil       : colour-compacted checkerboard, word(c, row, xh, w) at
+//                   ((c * rows + row) * Lxh + xh) * W + w, row = z * Ly + y,
+//                   x = 2 * xh + ((y + z + c) & 1)
+struct Layout {
+    int32_t kind;  // ISING_KIND_*
+    uint32_t Lx, Ly, Lz, Lxh, rows;
+    uint32_t W;    // words per site = ceil(E / 32)
+    uint64_t nvars;
+    uint64_t halfN;  // sites per colour (stencil)
+};
+
+// Acceptance thresholds of the multi-spin-coded Metropolis step for <= 3 uphill classes.
+// T_c = floor(exp(-beta dE_c) * 2^(K+32)); plane[c][p] is all-ones iff bit (K+31-p) of T_c
+// is set (MSB first), low[c] = T_c mod 2^32 is what the per-bit resolver compares against.
+struct MscThresholds {
+    uint32_t plane[3][8];
+    uint32_t low[3];
+};
+
+struct SweepArgs {
+    uint32_t* spins;
+    const uint32_t* jmask;  // stencil +-J: [colour][6 or 4][halfN] bond masks, else nullptr
+    Layout lay;
+    uint32_t sweep;         // global sweep index (Philox counter word 2)
+    uint32_t key0, key1;    // Philox key = seed
+    uint32_t gw0;           // global replica-word index of local word 0
+    uint32_t antiferro;     // uniform-sign lattices: all-ones iff J > 0
+    int planes, rounds;
+    MscThresholds th;
+};
+
+// both colour phases of one sweep (2 launches); returns launches made or -1
+int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st);
+// n_sat[e] += number of satisfied bonds of experiment e (one colour's sites cover every bond)
+int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
+                        uint32_t antiferro, unsigned long long* nsat, cudaStream_t st);
+// up[e] += number of up spins of experiment e
+int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long* up,
+                    cudaStream_t st);
+int launch_init_random(uint32_t* spins, const Layout& lay, uint32_t key0, uint32_t key1,
+                       uint32_t gw0, cudaStream_t st);
+int launch_init_broadcast(uint32_t* spins, const Layout& lay, const uint8_t* state_dev,
+                          cudaStream_t st);
+int launch_pack_states(uint32_t* spins, const Layout& lay, const uint8_t* states_dev,
+                       uint64_t E, cudaStream_t st);
+// bool[E, nvars] (row stride = out_stride bytes between experiments) from packed words
+int launch_unpack_states(const uint32_t* spins, const Layout& lay, uint8_t* out_dev, uint64_t E,
+                         uint64_t out_stride, cudaStream_t st);
+// packed words in natural order [nvars][W]
+int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* out_dev,
+                          cudaStream_t st);
+// energies[e * estride + eoff] = scale * (double)(nbonds - 2 * nsat[e])
+int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,
+                            uint64_t nbonds, double* out_dev, uint64_t estride, uint64_t eoff,
+                            cudaStream_t st);
+
+struct ReplayArgs {
+    uint64_t E, N, A;
+    const uint64_t* row;   // CSR offsets (nvars + 1)
+    const uint32_t* nbr;
+    const double* jv;
+    const double* bias;
+    const uint32_t* sites;  // [E, A]
+    const double* u;        // [E, A]
+    uint8_t* states;        // [E, N], holds init on entry, final state on exit
+    double* energies;       // [E]
+    double beta;
+    unsigned int* ambiguous;  // incremented when u is within rounding of exp(-beta dE)
+};
+int launch_replay(const ReplayArgs& a, cudaStream_t st);
+
+}  // namespace ising

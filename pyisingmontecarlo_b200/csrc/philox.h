@@ -1,0 +1,51 @@
+// Philox4x32 counter-based RNG (Salmon et al., SC'11), host + device.
+// Stream layout used by every kernel of this library (DESIGN.md "Randomness"):
+//   key = (seed_lo, seed_hi)
+//   ctr = (site, global replica word, sweep, call | tag << 24)
+// so a draw is a pure function of (seed, site, replica word, sweep) and does not depend on
+// the launch geometry, the colour layout or how experiments are sharded over GPUs.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ISING_HD __host__ __device__ __forceinline__
+#else
+#define ISING_HD inline
+#endif
+
+namespace ising {
+
+enum : uint32_t {
+    TAG_ACCEPT = 0u,  // Metropolis acceptance planes / resolver words
+    TAG_INIT = 1u,    // random initial state
+    TAG_SWAP = 2u,    // parallel-tempering swap decisions
+    TAG_BOND = 3u,    // +-J disorder of ising_graph_torus
+};
+
+struct u32x4 {
+    uint32_t x, y, z, w;
+};
+
+template <int ROUNDS>
+ISING_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                          uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0;
+        const uint64_t p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += W0;
+        k1 += W1;
+    }
+    u32x4 out = {c0, c1, c2, c3};
+    return out;
+}
+
+}  // namespace ising

@@ -1,0 +1,273 @@
+"""`Lattice` -- host-side mirror of the reference pyclass (src/lattice.rs:27-470) for the
+classical Monte-Carlo path, running on libising_b200 (CUDA, sm_100a) through its C ABI.
+
+Same names, argument order, defaults, return dtypes/shapes and error behaviour as the
+reference's `py_monte_carlo.Lattice`; the quantum methods (lattice.rs:472-1069) stay on the
+reference.  Documented deviations of the GPU path:
+  D1  only single-spin Metropolis moves are performed whatever `only_basic_moves` says;
+  D2  `edge_move_importance_sampling=True` raises NotImplementedError instead of being ignored;
+  D3  a timestep is one colour-class sweep (every site attempted once) instead of nvars
+      attempts at uniformly random sites: same Boltzmann law, different transient.
+"""
+import secrets
+
+import numpy as np
+
+from . import _native as nat
+
+_U64 = 2**64 - 1
+
+
+def _edges_to_arrays(edges):
+    n = len(edges)
+    a = np.empty(n, dtype=np.uint64)
+    b = np.empty(n, dtype=np.uint64)
+    j = np.empty(n, dtype=np.float64)
+    for k, ((x, y), w) in enumerate(edges):
+        if x < 0 or y < 0:
+            raise OverflowError("can't convert negative int to unsigned")  # pyo3's usize conversion
+        a[k], b[k], j[k] = x, y, w
+    return a, b, j
+
+
+class Lattice:
+    """A lattice for running ising monte carlo simulations. Takes a list of edges: ((a, b), j), ...
+
+    Creates new initial conditions each time simulations are run, does not preserve any internal
+    state for the lattice variables (spins).  (lattice.rs:24-39)
+    """
+
+    def __init__(self, edges, seed_gen=None, use_allocator=None, *, device=None):
+        # lattice.rs:46-73
+        if len(edges) == 0:
+            raise ValueError("Must supply some edges for graph")
+        self._a, self._b, self._j = _edges_to_arrays(edges)
+        self._init_common(int(max(self._a.max(), self._b.max())) + 1, seed_gen, use_allocator, device)
+
+    def _init_common(self, nvars, seed_gen, use_allocator, device):
+        self.nvars = nvars
+        self._torus = None
+        self._bias_global = 0.0
+        self._bias_individual = None
+        self._transverse = None
+        self._initial_state = None
+        self._enable_rvb_updates = False
+        self._enable_heatbath = False
+        self._seed_gen = None if seed_gen is None else int(seed_gen) & _U64
+        self._use_allocator = True if use_allocator is None else bool(use_allocator)
+        self._device = device
+        self._graph = None
+        # knobs of the device path that do not exist in the reference (defaults = parity mode)
+        self.linear_annealing = False   # False reproduces the reference's schedule quirk Q1
+        self.msc_planes = 0             # 0 = library default
+        self.philox_rounds = 0
+
+    # ---- additive constructors (the edge-list form cannot express configs 2/3/5) -------------
+    @classmethod
+    def from_arrays(cls, a, b, j, seed_gen=None, *, device=None):
+        """Edge list as three arrays instead of a list of ((a, b), j) tuples."""
+        self = cls.__new__(cls)
+        self._a = np.ascontiguousarray(a, dtype=np.uint64)
+        self._b = np.ascontiguousarray(b, dtype=np.uint64)
+        self._j = np.ascontiguousarray(j, dtype=np.float64)
+        if len(self._a) == 0:
+            raise ValueError("Must supply some edges for graph")
+        self._init_common(int(max(self._a.max(), self._b.max())) + 1, seed_gen, None, device)
+        return self
+
+    @classmethod
+    def torus(cls, dims, j=-1.0, pmj=False, j_seed=0, seed_gen=None, *, device=None):
+        """Periodic square / cubic lattice, site index x + Lx*(y + Ly*z); pmj=True draws every
+        bond as +-|j| (one disorder sample shared by all experiments, as lattice.rs:199 shares
+        `&self.edges`)."""
+        self = cls.__new__(cls)
+        dims = tuple(int(d) for d in dims)
+        n = 1
+        for d in dims:
+            n *= d
+        self._a = self._b = self._j = None
+        self._init_common(n, seed_gen, None, device)
+        self._torus = (dims, float(j), bool(pmj), int(j_seed))
+        return self
+
+    # ---- configuration surface, lattice.rs:76-161 ---------------------------------------------
+    def set_seed_gen(self, seed_gen=None):
+        self._seed_gen = None if seed_gen is None else int(seed_gen) & _U64
+
+    def make_seeds(self, num_experiments):
+        """lattice.rs:83-91: master SmallRng(seed_gen | entropy) -> one u64 per experiment."""
+        seed = self._seed_gen if self._seed_gen is not None else secrets.randbits(64)
+        return [int(s) for s in nat.make_seeds(seed, num_experiments)]
+
+    def set_enable_rvb_update(self, enable_updates):
+        self._enable_rvb_updates = bool(enable_updates)
+
+    def set_enable_heatbath_update(self, enable_heatbath):
+        self._enable_heatbath = bool(enable_heatbath)
+
+    def set_individual_bias(self, var, bias):
+        if not 0 <= var < self.nvars:
+            raise ValueError(f"Index out of bounds: variable {var} out of {self.nvars}")
+        if self._bias_individual is None:
+            self._bias_individual = np.full(self.nvars, self._bias_global, dtype=np.float64)
+        self._bias_individual[var] = bias
+        self._graph = None
+
+    def set_global_bias(self, bias):
+        self._bias_global = float(bias)
+        self._bias_individual = None
+        self._graph = None
+
+    def set_transverse_field(self, transverse):
+        if transverse > 0.0:
+            self._transverse = float(transverse)
+        elif transverse == 0.0:
+            self._transverse = None
+        else:
+            raise ValueError("Transverse field must be positive")
+
+    def set_initial_state(self, initial_state):
+        initial_state = list(initial_state)
+        if len(initial_state) == self.nvars:
+            self._initial_state = np.asarray(initial_state, dtype=np.bool_)
+        elif len(initial_state) == 0:
+            self._initial_state = None
+        else:
+            raise ValueError("Initial state must be of the same size as biases, or 0.")
+
+    def clone(self):
+        import copy
+
+        other = copy.copy(self)
+        if self._bias_individual is not None:
+            other._bias_individual = self._bias_individual.copy()
+        return other
+
+    # ---- plumbing --------------------------------------------------------------------------
+    def _biases(self):
+        if self._bias_individual is not None:
+            return self._bias_individual
+        if self._bias_global != 0.0:
+            return np.full(self.nvars, self._bias_global, dtype=np.float64)
+        return None
+
+    def graph(self):
+        """Compiled device graph (cached until the biases change)."""
+        if self._graph is None:
+            ctx = nat.Context.get(self._device)
+            if self._torus is not None:
+                if self._biases() is not None:
+                    raise NotImplementedError("biases on Lattice.torus lattices are not supported")
+                dims, j, pmj, j_seed = self._torus
+                self._graph = nat.Graph.torus(ctx, dims, j, pmj, j_seed)
+            else:
+                self._graph = nat.Graph.from_edges(ctx, self.nvars, self._a, self._b, self._j,
+                                                   self._biases())
+        return self._graph
+
+    def _check_classical(self, edge_move_importance_sampling):
+        if self._transverse is not None:
+            raise ValueError("Cannot run classic monte carlo with transverse field")
+        return nat.FLAG_EDGE_IMPORTANCE if edge_move_importance_sampling else 0
+
+    def _run_seed(self):
+        return self._seed_gen if self._seed_gen is not None else secrets.randbits(64)
+
+    def _args(self, flags, **kw):
+        init = None
+        if self._initial_state is not None:
+            init = np.ascontiguousarray(self._initial_state, dtype=np.uint8)
+        return nat.run_args(flags=flags, seed=self._run_seed(), initial_state=init, **kw)
+
+    def _call(self, fn, args, energies, states):
+        g = self.graph()
+        if self.msc_planes or self.philox_rounds:
+            raise NotImplementedError("msc_planes/philox_rounds are set per Sim; use pyisingmontecarlo_b200.Sim")
+        nat.check(fn(g.ctx.handle, g.handle, args, nat.ptr(energies), nat.ptr(states)), g.ctx.handle)
+
+    # ---- classical runs, lattice.rs:163-470 -------------------------------------------------
+    def run_monte_carlo(self, beta, timesteps, num_experiments, only_basic_moves=None,
+                        edge_move_importance_sampling=None):
+        """lattice.rs:171-221 -> (energies float64[E], states bool[E, nvars])"""
+        flags = self._check_classical(edge_move_importance_sampling)
+        energies = np.zeros(num_experiments, dtype=np.float64)
+        states = np.zeros((num_experiments, self.nvars), dtype=np.bool_)
+        args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
+                          num_experiments=int(num_experiments))
+        self._call(nat.lib().ising_run_monte_carlo, args, energies, states)
+        return energies, states
+
+    def run_monte_carlo_sampling(self, beta, timesteps, num_experiments, only_basic_moves=None,
+                                 thermalization_time=None, sampling_freq=None,
+                                 edge_move_importance_sampling=None):
+        """lattice.rs:231-299 -> (energies float64[E, n_s], states bool[E, n_s, nvars])"""
+        flags = self._check_classical(edge_move_importance_sampling)
+        thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
+        sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
+        if sampling_freq == 0:
+            raise ZeroDivisionError("sampling_freq must be non-zero (the reference panics)")
+        n_samples = int(timesteps) // sampling_freq
+        energies = np.zeros((num_experiments, n_samples), dtype=np.float64)
+        states = np.zeros((num_experiments, n_samples, self.nvars), dtype=np.bool_)
+        args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
+                          num_experiments=int(num_experiments), thermalization=thermalization_time,
+                          sampling_freq=sampling_freq)
+        self._call(nat.lib().ising_run_monte_carlo_sampling, args, energies, states)
+        return energies, states
+
+    def _annealing(self, betas, timesteps, num_experiments, edge_move_importance_sampling, per_step):
+        flags = self._check_classical(edge_move_importance_sampling)
+        if per_step:
+            flags |= nat.FLAG_PER_STEP_ENERGIES
+        if self.linear_annealing:
+            flags |= nat.FLAG_LINEAR_SCHEDULE
+        betas = list(betas)
+        st = np.ascontiguousarray([int(t) for t, _ in betas], dtype=np.uint64)
+        sb = np.ascontiguousarray([float(v) for _, v in betas], dtype=np.float64)
+        shape = (num_experiments, int(timesteps)) if per_step else (num_experiments,)
+        energies = np.zeros(shape, dtype=np.float64)
+        states = np.zeros((num_experiments, self.nvars), dtype=np.bool_)
+        args = self._args(flags, sched_t=st if len(st) else None, sched_beta=sb if len(sb) else None,
+                          sched_len=len(st), timesteps=int(timesteps),
+                          num_experiments=int(num_experiments))
+        self._call(nat.lib().ising_run_monte_carlo_annealing, args, energies, states)
+        return energies, states
+
+    def run_monte_carlo_annealing(self, betas, timesteps, num_experiments, only_basic_moves=None,
+                                  edge_move_importance_sampling=None):
+        """lattice.rs:309-385 -> (energies float64[E], states bool[E, nvars])"""
+        return self._annealing(betas, timesteps, num_experiments, edge_move_importance_sampling, False)
+
+    def run_monte_carlo_annealing_and_get_energies(self, betas, timesteps, num_experiments,
+                                                   only_basic_moves=None,
+                                                   edge_move_importance_sampling=None):
+        """lattice.rs:395-470 -> (energies float64[E, timesteps], states bool[E, nvars])"""
+        return self._annealing(betas, timesteps, num_experiments, edge_move_importance_sampling, True)
+
+    # ---- replay mode (north-star correctness check 1) -----------------------------------------
+    def replay(self, beta, sites, uniforms, init_states):
+        """Re-runs the reference's own (site, uniform) sequence on the GPU, bit-exactly.
+
+        sites uint32[E, A], uniforms float64[E, A] (ignored where dE <= 0), init bool[E, nvars]."""
+        sites = np.ascontiguousarray(sites, dtype=np.uint32)
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        init = np.ascontiguousarray(init_states, dtype=np.uint8)
+        E, A = sites.shape
+        if uniforms.shape != (E, A) or init.shape != (E, self.nvars):
+            raise ValueError("replay trace shapes disagree")
+        g = self.graph()
+        energies = np.zeros(E, dtype=np.float64)
+        states = np.zeros((E, self.nvars), dtype=np.bool_)
+        nat.check(nat.lib().ising_replay(g.ctx.handle, g.handle, float(beta), E, A, nat.ptr(sites),
+                                         nat.ptr(uniforms), nat.ptr(init), nat.ptr(energies),
+                                         nat.ptr(states)), g.ctx.handle)
+        return energies, states
+
+    # ---- quantum path: out of scope, stays on the reference (lattice.rs:472-1069) -------------
+    def __getattr__(self, name):
+        if name.startswith("run_quantum_monte_carlo") or name in (
+                "average_on_and_off_diagonal_and_consts", "get_offset"):
+            raise NotImplementedError(
+                f"{name}: the SSE quantum Monte Carlo path is out of scope of the B200 engine and "
+                "remains on the reference py_monte_carlo build")
+        raise AttributeError(name)
