@@ -1,0 +1,105 @@
+"""CPU-side checks of the C-ABI library and the host layer (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    inc = os.path.join(ROOT, "include")
+    for f in sorted(os.listdir(inc)):
+        if f.endswith(".h"):
+            text = open(os.path.join(inc, f)).read()
+            names += re.findall(r"ISING_API\s+[\w\s\*]+?\b(ising_\w+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(native):
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    handle = C.CDLL(native.LIB_PATH)
+    missing = [n for n in declared if not hasattr(handle, n)]
+    assert not missing, missing
+    # the ctypes binding covers the same set
+    assert sorted(native.exported_symbols()) == declared
+    assert native.lib().ising_abi_version() == 1
+
+
+def test_library_is_sm100a_cuda(native):
+    """The product is CUDA for sm_100a: the .so must embed an sm_100a cubin with our kernels."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device(native):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the loud-failure path is for CPU boxes")
+    with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback|failed"):
+        native.Context(0)
+
+
+def test_make_seeds_matches_oracle_and_goldens(native, oracle):
+    assert list(native.make_seeds(0, 4)) == [5987356902031041503, 7051070477665621255,
+                                             6633766593972829180, 211316841551650330]
+    for seed in (1, 42, 2**63 + 5):
+        assert (native.make_seeds(seed, 100) == oracle.make_seeds(seed, 100)).all()
+
+
+@pytest.mark.parametrize("stops,timesteps", [
+    ([(0, 0.1), (1000, 1.2)], 1000), ([(500, 2.0), (10, 0.5)], 1000), ([], 10), ([(0, 0.7)], 10),
+    ([(0, 0.2), (0, 0.9)], 10), ([(3, 0.2), (7, 0.9), (7, 0.4)], 9), ([(0, 0.1), (2000, 1.2)], 50),
+])
+def test_schedule_matches_oracle(native, oracle, stops, timesteps):
+    for linear in (False, True):
+        a = native.schedule_betas(stops, timesteps, linear=linear)
+        b = oracle.schedule_betas(stops, timesteps, q1_compat=not linear)
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_lattice_config_surface_without_gpu(native, oracle):
+    import pyisingmontecarlo_b200 as pkg
+    import py_monte_carlo
+
+    assert py_monte_carlo.Lattice is pkg.Lattice
+    with pytest.raises(ValueError, match="Must supply some edges for graph"):
+        pkg.Lattice([])
+    lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -1.0)], 0)
+    assert lat.nvars == 3
+    assert lat.make_seeds(4) == [5987356902031041503, 7051070477665621255,
+                                 6633766593972829180, 211316841551650330]
+    lat.set_seed_gen(None)
+    assert lat.make_seeds(2) != lat.make_seeds(2)
+    with pytest.raises(ValueError, match="Index out of bounds: variable 3 out of 3"):
+        lat.set_individual_bias(3, 1.0)
+    lat.set_individual_bias(1, 0.5)
+    lat.set_global_bias(0.0)
+    with pytest.raises(ValueError, match="Transverse field must be positive"):
+        lat.set_transverse_field(-0.1)
+    lat.set_transverse_field(1.0)
+    with pytest.raises(ValueError, match="Cannot run classic monte carlo with transverse field"):
+        lat.run_monte_carlo(1.0, 1, 1)
+    with pytest.raises(ValueError, match="Cannot run classic monte carlo with transverse field"):
+        lat.run_monte_carlo_annealing_and_get_energies([], 1, 1)
+    lat.set_transverse_field(0.0)
+    with pytest.raises(ValueError, match="Initial state must be of the same size"):
+        lat.set_initial_state([True])
+    lat.set_initial_state([True, False, True])
+    lat.set_initial_state([])
+    c = lat.clone()
+    c.set_global_bias(2.0)
+    assert lat._bias_global == 0.0
+    with pytest.raises(NotImplementedError, match="remains on the reference"):
+        lat.run_quantum_monte_carlo_sampling
