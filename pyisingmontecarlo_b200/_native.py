@@ -11,7 +11,8 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libising_b200.so")
+# ISING_B200_LIB lets kernel experiments point at an alternative build of the same library
+LIB_PATH = os.environ.get("ISING_B200_LIB") or os.path.join(HERE, "libising_b200.so")
 
 ISING_OK, ISING_E_INVALID, ISING_E_CUDA, ISING_E_UNSUPPORTED, ISING_E_AMBIGUOUS, ISING_E_NOMEM = range(6)
 

@@ -49,17 +49,19 @@ __device__ __forceinline__ void count_sat(const uint32_t (&a)[2 * DIM], uint32_t
 // ------------------------------------------------------------------------------------------
 // Metropolis acceptance of the uphill bits of one word.
 //   up   : bits with dE > 0;  (sel1, sel0) select the class of each such bit
-//   K bit-planes R_0..R_{K-1} are compared MSB-first against the class threshold; a bit still
-//   undecided afterwards (probability 2^-K) is resolved by a fresh 32-bit word against the low
-//   32 threshold bits, undecided bits taken in ascending position.  Word R_m is output m%4 of
-//   Philox call m/4 on counter (site, replica word, sweep, call).
-// returns the mask of accepted uphill bits
+//   K bit-planes R_0..R_{K-1} are the K most significant bits of a uniform U per replica and
+//   are compared against the class threshold T: U_top < T_top is the borrow of the bit-sliced
+//   subtraction U_top - T_top (one majority LOP3 per plane, LSB first); bits whose top K bits
+//   tie (probability 2^-K) are resolved by a fresh 32-bit word against the low 32 threshold
+//   bits, tied bits taken in ascending position.  Word R_m is output m%4 of Philox call m/4
+//   on counter (site, replica word, sweep, call).
+// returns the flip mask (downhill bits always flip)
 // ------------------------------------------------------------------------------------------
 template <int NCLS, int K, int ROUNDS>
-__device__ __forceinline__ uint32_t msc_accept(uint32_t up, uint32_t sel0, uint32_t sel1,
-                                               const MscThresholds& th, uint32_t site,
-                                               uint32_t gw, uint32_t sweep, uint32_t k0,
-                                               uint32_t k1) {
+__device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, uint32_t sel1,
+                                                  const MscThresholds& th, uint32_t site,
+                                                  uint32_t gw, uint32_t sweep, uint32_t k0,
+                                                  uint32_t k1) {
     constexpr int NCALL = K / 4 + 1;
     uint32_t r[NCALL * 4];
 #pragma unroll
@@ -70,16 +72,29 @@ __device__ __forceinline__ uint32_t msc_accept(uint32_t up, uint32_t sel0, uint3
         r[4 * q + 2] = o.z;
         r[4 * q + 3] = o.w;
     }
-    uint32_t eq = up, lt = 0;
+    uint32_t eq = up, borrow = 0;
 #pragma unroll
-    for (int p = 0; p < K; ++p) {
+    for (int p = K - 1; p >= 0; --p) {
         uint32_t t = (sel0 & th.plane[1][p]) | (~sel0 & th.plane[0][p]);
         if (NCLS == 3) t = (sel1 & th.plane[2][p]) | (~sel1 & t);
-        lt |= eq & ~r[p] & t;
+        borrow = maj3(~r[p], t, borrow);
         eq &= ~(r[p] ^ t);
     }
-    if (eq) {  // rare per bit (2^-K), handled per lane
-        int j = K;
+    uint32_t flip = ~up | (borrow & ~eq);
+    // Tied bits (2^-K each).  The first SPARE of them use the words left over from the calls
+    // above in straight-line predicated code (no divergent loop for the common case); anything
+    // beyond that, rare, draws further Philox calls in a loop.
+    constexpr int SPARE = (4 * NCALL - K) < 2 ? (4 * NCALL - K) : 2;
+#pragma unroll
+    for (int j = 0; j < SPARE; ++j) {
+        const uint32_t bit = eq & (0u - eq);  // lowest tied bit, 0 when nothing is tied
+        uint32_t lo = (sel0 & bit) ? th.low[1] : th.low[0];
+        if (NCLS == 3 && (sel1 & bit)) lo = th.low[2];
+        if (r[K + j] < lo) flip |= bit;
+        eq ^= bit;
+    }
+    if (eq) {
+        int j = K + SPARE;
         u32x4 cur = {r[4 * (NCALL - 1)], r[4 * (NCALL - 1) + 1], r[4 * (NCALL - 1) + 2],
                      r[4 * (NCALL - 1) + 3]};
         do {
@@ -91,25 +106,61 @@ __device__ __forceinline__ uint32_t msc_accept(uint32_t up, uint32_t sel0, uint3
             const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
             uint32_t lo = ((sel0 >> b) & 1u) ? th.low[1] : th.low[0];
             if (NCLS == 3 && ((sel1 >> b) & 1u)) lo = th.low[2];
-            if (v < lo) lt |= 1u << b;
+            if (v < lo) flip |= 1u << b;
             eq &= eq - 1;
             ++j;
         } while (eq);
     }
-    return lt;
+    return flip;
+}
+
+// V consecutive replica words as one vector load / store (128-bit when V == 4)
+template <int V> struct WordVec;
+template <> struct WordVec<1> { typedef uint32_t type; };
+template <> struct WordVec<2> { typedef uint2 type; };
+template <> struct WordVec<4> { typedef uint4 type; };
+
+template <int V>
+__device__ __forceinline__ void load_words(const uint32_t* p, uint32_t (&out)[V]) {
+    typedef typename WordVec<V>::type T;
+    const T v = *reinterpret_cast<const T*>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = w[k];
+}
+
+template <int V>
+__device__ __forceinline__ void store_words(uint32_t* p, const uint32_t (&in)[V]) {
+    typedef typename WordVec<V>::type T;
+    T v;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) w[k] = in[k];
+    *reinterpret_cast<T*>(p) = v;
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: one colour phase of a checkerboard sweep on a square / cubic torus
-// block = (WX lanes over replica words, BY over half-row positions); one row per iteration
+// block = (WX lanes over groups of V replica words, BY over half-row positions); one row of
+// the colour-compacted lattice per iteration; all seven spin loads are coalesced vector loads
 // ------------------------------------------------------------------------------------------
-template <int DIM, bool PMJ, int K, int ROUNDS>
-__global__ void __launch_bounds__(256)
+#ifndef ISING_SWEEP_MIN_BLOCKS
+#define ISING_SWEEP_MIN_BLOCKS 3
+#endif
+#ifndef ISING_SWEEP_UNROLL_V
+#define ISING_SWEEP_UNROLL_V 4
+#endif
+#ifndef ISING_SWEEP_MAXV
+#define ISING_SWEEP_MAXV 4
+#endif
+template <int DIM, bool PMJ, int K, int ROUNDS, int V>
+__global__ void __launch_bounds__(256, ISING_SWEEP_MIN_BLOCKS)
 k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                 const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
                 uint32_t k0, uint32_t k1, uint32_t gw0, uint32_t antiferro, MscThresholds th) {
+    constexpr int kUnrollV = ISING_SWEEP_UNROLL_V;
     const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
-    const size_t rowlen = (size_t)Lxh * W;
+    const uint32_t rowlen = Lxh * W;  // words per colour row (< 2^32: checked on the host)
     for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
         const uint32_t z = row / Ly, y = row - z * Ly;
         const uint32_t p = (y + z + c) & 1u;
@@ -132,35 +183,41 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
             for (int k = 0; k < 2 * DIM; ++k)
                 m[k] = PMJ ? __ldg(jm + (size_t)k * L.halfN + (size_t)row * Lxh + xh) : antiferro;
             const uint32_t site = row * L.Lx + 2 * xh + p;
-            for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) {
-                const size_t i = (size_t)xh * W + w;
-                const uint32_t s = o_c[i];
-                uint32_t a[2 * DIM];
-                a[0] = ~(s ^ n_x[i] ^ m[0]);
-                a[1] = ~(s ^ n_x[(size_t)xs * W + w] ^ m[1]);
-                a[2] = ~(s ^ n_ym[i] ^ m[2]);
-                a[3] = ~(s ^ n_yp[i] ^ m[3]);
+            for (uint32_t w = V * threadIdx.x; w < W; w += V * blockDim.x) {
+                const uint32_t i = xh * W + w;
+                uint32_t s[V], n[2 * DIM][V];
+                load_words<V>(o_c + i, s);
+                load_words<V>(n_x + i, n[0]);
+                load_words<V>(n_x + xs * W + w, n[1]);
+                load_words<V>(n_ym + i, n[2]);
+                load_words<V>(n_yp + i, n[3]);
                 if (DIM == 3) {
-                    a[4] = ~(s ^ n_zm[i] ^ m[4]);
-                    a[5] = ~(s ^ n_zp[i] ^ m[5]);
+                    load_words<V>(n_zm + i, n[4]);
+                    load_words<V>(n_zp + i, n[5]);
                 }
-                uint32_t b0, b1, b2;
-                count_sat<DIM>(a, b0, b1, b2);
-                uint32_t up, lt;
-                if (DIM == 3) {  // n_sat 4,5,6 -> dE = 4,8,12 |J|
-                    up = b2;
-                    lt = msc_accept<3, K, ROUNDS>(up, b0, b1, th, site, gw0 + w, sweep, k0, k1);
-                } else {  // n_sat 3,4 -> dE = 4,8 |J|
-                    up = b2 | (b1 & b0);
-                    lt = msc_accept<2, K, ROUNDS>(up, b2, 0u, th, site, gw0 + w, sweep, k0, k1);
+#pragma unroll(kUnrollV)
+                for (int v = 0; v < V; ++v) {
+                    uint32_t a[2 * DIM];
+#pragma unroll
+                    for (int k = 0; k < 2 * DIM; ++k) a[k] = ~(s[v] ^ n[k][v] ^ m[k]);
+                    uint32_t b0, b1, b2;
+                    count_sat<DIM>(a, b0, b1, b2);
+                    uint32_t flip;
+                    if (DIM == 3)  // n_sat 4,5,6 -> dE = 4,8,12 |J|
+                        flip = msc_flip_mask<3, K, ROUNDS>(b2, b0, b1, th, site, gw0 + w + v, sweep,
+                                                           k0, k1);
+                    else  // n_sat 3,4 -> dE = 4,8 |J|
+                        flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, site,
+                                                           gw0 + w + v, sweep, k0, k1);
+                    s[v] ^= flip;
                 }
-                o_c[i] = s ^ (~up | lt);
+                store_words<V>(o_c + i, s);
             }
         }
     }
 }
 
-template <int DIM, bool PMJ, int K>
+template <int DIM, bool PMJ, int K, int V>
 static int sweep_dispatch_rounds(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block) {
     const Layout& L = a.lay;
     const size_t csz = (size_t)L.halfN * L.W;
@@ -170,23 +227,23 @@ static int sweep_dispatch_rounds(const SweepArgs& a, cudaStream_t st, dim3 grid,
         const uint32_t* oth = a.spins + (1 - c) * csz;
         const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
         if (a.rounds == 7)
-            k_sweep_stencil<DIM, PMJ, K, 7><<<grid, block, 0, st>>>(
+            k_sweep_stencil<DIM, PMJ, K, 7, V><<<grid, block, 0, st>>>(
                 own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th);
         else
-            k_sweep_stencil<DIM, PMJ, K, 10><<<grid, block, 0, st>>>(
+            k_sweep_stencil<DIM, PMJ, K, 10, V><<<grid, block, 0, st>>>(
                 own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th);
     }
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
-template <int DIM, bool PMJ>
+template <int DIM, bool PMJ, int V>
 static int sweep_dispatch_planes(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block) {
     switch (a.planes) {
-        case 4: return sweep_dispatch_rounds<DIM, PMJ, 4>(a, st, grid, block);
-        case 5: return sweep_dispatch_rounds<DIM, PMJ, 5>(a, st, grid, block);
-        case 6: return sweep_dispatch_rounds<DIM, PMJ, 6>(a, st, grid, block);
-        case 7: return sweep_dispatch_rounds<DIM, PMJ, 7>(a, st, grid, block);
-        case 8: return sweep_dispatch_rounds<DIM, PMJ, 8>(a, st, grid, block);
+        case 4: return sweep_dispatch_rounds<DIM, PMJ, 4, V>(a, st, grid, block);
+        case 5: return sweep_dispatch_rounds<DIM, PMJ, 5, V>(a, st, grid, block);
+        case 6: return sweep_dispatch_rounds<DIM, PMJ, 6, V>(a, st, grid, block);
+        case 7: return sweep_dispatch_rounds<DIM, PMJ, 7, V>(a, st, grid, block);
+        case 8: return sweep_dispatch_rounds<DIM, PMJ, 8, V>(a, st, grid, block);
         default: return -1;
     }
 }
@@ -197,8 +254,10 @@ static uint32_t pow2_ceil(uint32_t v) {
     return p;
 }
 
-static void stencil_block_shape(const Layout& L, dim3* grid, dim3* block, bool persistent) {
-    const uint32_t wx = L.W >= 32 ? 32 : pow2_ceil(L.W);
+static void stencil_block_shape(const Layout& L, uint32_t V, dim3* grid, dim3* block,
+                                bool persistent) {
+    const uint32_t groups = (L.W + V - 1) / V;  // vector groups of replica words per site
+    const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
     uint32_t by = 256 / wx;
     const uint32_t need = pow2_ceil(L.Lxh);
     if (by > need) by = need;
@@ -209,17 +268,25 @@ static void stencil_block_shape(const Layout& L, dim3* grid, dim3* block, bool p
     *grid = dim3(g, 1, 1);
 }
 
-int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
+template <int V>
+static int sweep_dispatch_kind(const SweepArgs& a, cudaStream_t st) {
     dim3 grid, block;
-    stencil_block_shape(a.lay, &grid, &block, false);
+    stencil_block_shape(a.lay, V, &grid, &block, false);
     const bool pmj = a.jmask != nullptr;
     if (a.lay.kind == ISING_KIND_STENCIL3D)
-        return pmj ? sweep_dispatch_planes<3, true>(a, st, grid, block)
-                   : sweep_dispatch_planes<3, false>(a, st, grid, block);
+        return pmj ? sweep_dispatch_planes<3, true, V>(a, st, grid, block)
+                   : sweep_dispatch_planes<3, false, V>(a, st, grid, block);
     if (a.lay.kind == ISING_KIND_STENCIL2D)
-        return pmj ? sweep_dispatch_planes<2, true>(a, st, grid, block)
-                   : sweep_dispatch_planes<2, false>(a, st, grid, block);
+        return pmj ? sweep_dispatch_planes<2, true, V>(a, st, grid, block)
+                   : sweep_dispatch_planes<2, false, V>(a, st, grid, block);
     return -1;
+}
+
+int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
+    // widest vector the replica-word count allows (rows then stay 16-byte aligned)
+    if (ISING_SWEEP_MAXV >= 4 && a.lay.W % 4 == 0) return sweep_dispatch_kind<4>(a, st);
+    if (ISING_SWEEP_MAXV >= 2 && a.lay.W % 2 == 0) return sweep_dispatch_kind<2>(a, st);
+    return sweep_dispatch_kind<1>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -363,7 +430,7 @@ k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ 
 int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
                         uint32_t antiferro, unsigned long long* nsat, cudaStream_t st) {
     dim3 grid, block;
-    stencil_block_shape(lay, &grid, &block, true);
+    stencil_block_shape(lay, 1, &grid, &block, true);
     const bool pmj = jmask != nullptr;
     if (lay.kind == ISING_KIND_STENCIL3D) {
         if (pmj) k_nsat_stencil<3, true><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
