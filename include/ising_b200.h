@@ -51,6 +51,12 @@ ISING_API int ising_ctx_create(int device, ising_ctx **out);
 ISING_API void ising_ctx_destroy(ising_ctx *ctx);
 ISING_API const char *ising_last_error(const ising_ctx *ctx);
 
+/* Page-locked host memory for output arrays.  The reference allocates its outputs itself
+ * (lattice.rs:183-184) and hands them to numpy; a host layer that allocates them here gets
+ * D2H copies at PCIe speed instead of pageable staging. */
+ISING_API int ising_host_alloc(size_t bytes, void **out);
+ISING_API void ising_host_free(void *p);
+
 /* ---- graph layout (replaces GraphState::new's adjacency build, lattice.rs:199) ----------- */
 enum { ISING_KIND_GENERAL = 0, ISING_KIND_STENCIL2D = 2, ISING_KIND_STENCIL3D = 3 };
 

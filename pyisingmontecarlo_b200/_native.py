@@ -81,6 +81,8 @@ _SIGNATURES = {
     "ising_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "ising_ctx_destroy": (None, [_P]),
     "ising_last_error": (C.c_char_p, [_P]),
+    "ising_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "ising_host_free": (None, [_P]),
     "ising_graph_from_edges": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, C.POINTER(_P)]),
     "ising_graph_torus": (C.c_int, [_P, C.c_int, _P, C.c_double, C.c_int, C.c_uint64, C.POINTER(_P)]),
     "ising_graph_destroy": (None, [_P]),
@@ -160,6 +162,53 @@ def check(rc, ctx=None):
 
 def ptr(arr):
     return None if arr is None else arr.ctypes.data_as(C.c_void_p)
+
+
+class PinnedPool:
+    """Output arrays in page-locked host memory, recycled when the numpy array is collected.
+
+    The reference allocates its outputs in the host layer and hands them to numpy without a
+    copy (lattice.rs:183-184, 213-214); doing the same here with cudaHostAlloc memory makes the
+    device->host copies of bool[E, N] run at PCIe speed.  Blocks go back to a free list keyed
+    by size when the last view of the array dies, so steady-state calls allocate nothing."""
+
+    GRAIN = 1 << 21
+    MAX_CACHED = 8 << 30
+    _free = {}
+    _cached = 0
+    _lk = threading.Lock()
+
+    @classmethod
+    def _release(cls, addr, size):
+        with cls._lk:
+            if cls._cached + size <= cls.MAX_CACHED:
+                cls._free.setdefault(size, []).append(addr)
+                cls._cached += size
+                return
+        lib().ising_host_free(addr)
+
+    @classmethod
+    def empty(cls, shape, dtype):
+        import weakref
+
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes < (1 << 20):
+            return np.empty(shape, dtype=dtype)
+        size = (nbytes + cls.GRAIN - 1) // cls.GRAIN * cls.GRAIN
+        addr = None
+        with cls._lk:
+            lst = cls._free.get(size)
+            if lst:
+                addr = lst.pop()
+                cls._cached -= size
+        if addr is None:
+            p = C.c_void_p()
+            check(lib().ising_host_alloc(size, C.byref(p)))
+            addr = p.value
+        buf = (C.c_uint8 * size).from_address(addr)
+        weakref.finalize(buf, cls._release, addr, size)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
 
 class Context:

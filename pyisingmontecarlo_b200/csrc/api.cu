@@ -31,7 +31,55 @@ struct ising_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int sm_count = 0;
+    // grow-only device scratch (staging of outputs), so that repeated calls do not pay
+    // cudaMalloc/cudaFree of hundreds of MB every time
+    void* scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_bytes[3] = {0, 0, 0};
+    // free list of device buffers released by destroyed sims: a stateless Lattice run creates
+    // and destroys a sim per call, and cudaMalloc/cudaFree (device-wide synchronising, tens
+    // of ms with large pinned regions mapped) must not be on that path
+    std::vector<std::pair<void*, size_t>> free_bufs;
+    size_t free_bytes = 0;
 };
+
+static cudaError_t ctx_buf_get(ising_ctx* ctx, size_t bytes, void** out) {
+    bytes = std::max<size_t>(bytes, 256);
+    for (size_t i = 0; i < ctx->free_bufs.size(); ++i)
+        if (ctx->free_bufs[i].second >= bytes && ctx->free_bufs[i].second <= bytes + bytes / 4 + 4096) {
+            *out = ctx->free_bufs[i].first;
+            ctx->free_bytes -= ctx->free_bufs[i].second;
+            ctx->free_bufs.erase(ctx->free_bufs.begin() + i);
+            return cudaSuccess;
+        }
+    return cudaMalloc(out, bytes);
+}
+
+
+static void ctx_buf_put(ising_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>(bytes, 256);
+    const size_t cap = (size_t)8 << 30;
+    if (ctx->free_bytes + bytes > cap || ctx->free_bufs.size() >= 64) {
+        cudaFree(p);
+        return;
+    }
+    ctx->free_bufs.emplace_back(p, bytes);
+    ctx->free_bytes += bytes;
+}
+
+static cudaError_t ctx_scratch(ising_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+        ctx->scratch[slot] = nullptr;
+        ctx->scratch_bytes[slot] = 0;
+        const size_t want = std::max<size_t>(bytes, 1 << 20);
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess) return e;
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return cudaSuccess;
+}
 
 struct ising_graph {
     ising_ctx* ctx = nullptr;
@@ -53,6 +101,7 @@ struct ising_sim {
     Layout lay{};
     uint32_t* d_spins = nullptr;
     unsigned long long* d_counts = nullptr;  // per-experiment integer accumulator [W*32]
+    size_t spins_bytes = 0, counts_bytes = 0;
     uint64_t sweep_counter = 0;
     int planes = 6, rounds = 10;
     ising_sim_stats stats{};
@@ -124,7 +173,22 @@ extern "C" void ising_ctx_destroy(ising_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (void* p : ctx->scratch) cudaFree(p);
+    for (auto& b : ctx->free_bufs) cudaFree(b.first);
     delete ctx;
+}
+
+extern "C" int ising_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return fail(nullptr, ISING_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return ISING_OK;
+}
+
+extern "C" void ising_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -308,8 +372,17 @@ extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E
     L.nvars = h.nvars;
     L.halfN = h.nvars / 2;
     const size_t words = (size_t)h.nvars * L.W;
-    CUDA_TRY(ctx, dev_alloc(&s->d_spins, words));
-    CUDA_TRY(ctx, dev_alloc(&s->d_counts, (size_t)L.W * 32));
+    s->spins_bytes = words * sizeof(uint32_t);
+    s->counts_bytes = (size_t)L.W * 32 * sizeof(unsigned long long);
+    void* p = nullptr;
+    CUDA_TRY(ctx, ctx_buf_get(ctx, s->spins_bytes, &p));
+    s->d_spins = (uint32_t*)p;
+    cudaError_t ce = ctx_buf_get(ctx, s->counts_bytes, &p);
+    if (ce != cudaSuccess) {
+        ctx_buf_put(ctx, s->d_spins, s->spins_bytes);
+        CUDA_TRY(ctx, ce);
+    }
+    s->d_counts = (unsigned long long*)p;
     *out = s.release();
     return ising_sim_randomize(*out);
 }
@@ -317,8 +390,9 @@ extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E
 extern "C" void ising_sim_destroy(ising_sim* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->d_spins);
-    cudaFree(s->d_counts);
+    cudaStreamSynchronize(s->ctx->stream);
+    ctx_buf_put(s->ctx, s->d_spins, s->spins_bytes);
+    ctx_buf_put(s->ctx, s->d_counts, s->counts_bytes);
     delete s;
 }
 
@@ -350,14 +424,14 @@ extern "C" int ising_sim_set_state(ising_sim* s, const uint8_t* state) {
     if (!s || !state) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/state is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    uint8_t* d = nullptr;
-    CUDA_TRY(ctx, dev_alloc(&d, s->lay.nvars));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, s->lay.nvars, &dv));
+    uint8_t* d = (uint8_t*)dv;
     cudaError_t e = cudaMemcpyAsync(d, state, s->lay.nvars, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         count_launch(s, launch_init_broadcast(s->d_spins, s->lay, d, ctx->stream));
         e = cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(d);
     CUDA_TRY(ctx, e);
     return ISING_OK;
 }
@@ -366,15 +440,15 @@ extern "C" int ising_sim_set_states(ising_sim* s, const uint8_t* states) {
     if (!s || !states) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/states is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    uint8_t* d = nullptr;
     const size_t bytes = (size_t)s->E * s->lay.nvars;
-    CUDA_TRY(ctx, dev_alloc(&d, bytes));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, bytes, &dv));
+    uint8_t* d = (uint8_t*)dv;
     cudaError_t e = cudaMemcpyAsync(d, states, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         count_launch(s, launch_pack_states(s->d_spins, s->lay, d, s->E, ctx->stream));
         e = cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(d);
     CUDA_TRY(ctx, e);
     return ISING_OK;
 }
@@ -398,7 +472,7 @@ static void fill_thresholds(const HostGraph& h, double beta, int K, MscThreshold
     }
 }
 
-static int sim_one_sweep(ising_sim* s, double beta) {
+static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr) {
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
     SweepArgs a;
@@ -413,6 +487,7 @@ static int sim_one_sweep(ising_sim* s, double beta) {
     a.planes = s->planes;
     a.rounds = s->rounds;
     fill_thresholds(h, beta, s->planes, &a.th);
+    a.nsat_out = nsat_out;
     const int n = launch_sweep_stencil(a, ctx->stream);
     if (n < 0) return fail(ctx, ISING_E_CUDA, "sweep launch failed: %s",
                            cudaGetErrorString(cudaGetLastError()));
@@ -465,21 +540,25 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     const size_t cw = (size_t)s->lay.W * 32;
     unsigned long long* d_hist = nullptr;
     double* d_out = nullptr;
-    CUDA_TRY(ctx, dev_alloc(&d_hist, cw * std::min(chunk_max, nsweeps)));
-    cudaError_t e = dev_alloc(&d_out, (size_t)E * std::min(chunk_max, nsweeps));
-    if (e != cudaSuccess) { cudaFree(d_hist); CUDA_TRY(ctx, e); }
+    void* sp = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 1, cw * std::min(chunk_max, nsweeps) * sizeof(unsigned long long), &sp));
+    d_hist = (unsigned long long*)sp;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 2, (size_t)E * std::min(chunk_max, nsweeps) * sizeof(double), &sp));
+    d_out = (double*)sp;
+    cudaError_t e = cudaSuccess;
     std::vector<double> host;
     int rc = ISING_OK;
     for (uint64_t t0 = 0; t0 < nsweeps && rc == ISING_OK; t0 += chunk_max) {
         const uint64_t nt = std::min(chunk_max, nsweeps - t0);
         cudaEventRecord(ctx->ev0, ctx->stream);
-        for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t) {
-            rc = sim_one_sweep(s, betas[t0 + t]);
-            if (rc == ISING_OK) rc = sim_count_nsat(s, d_hist + t * cw);
-            if (rc == ISING_OK)
-                count_launch(s, launch_energy_from_nsat(d_hist + t * cw, E, h.jabs, h.nedges,
-                                                        d_out, nt, t, ctx->stream));
-        }
+        cudaMemsetAsync(d_hist, 0, cw * nt * sizeof(unsigned long long), ctx->stream);
+        // the second colour phase of every sweep adds its post-flip satisfied-bond counts
+        // into that sweep's slot of the history (fused, no separate energy pass)
+        for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t)
+            rc = sim_one_sweep(s, betas[t0 + t], d_hist + t * cw);
+        if (rc == ISING_OK)
+            count_launch(s, launch_energy_from_hist(d_hist, E, cw, nt, h.jabs, h.nedges, d_out,
+                                                    ctx->stream));
         cudaEventRecord(ctx->ev1, ctx->stream);
         if (rc != ISING_OK) break;
         host.resize((size_t)E * nt);
@@ -493,8 +572,6 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
         for (uint64_t ex = 0; ex < E; ++ex)
             memcpy(energies_per_sweep + ex * nsweeps + t0, host.data() + ex * nt, nt * sizeof(double));
     }
-    cudaFree(d_hist);
-    cudaFree(d_out);
     return rc;
 }
 
@@ -505,15 +582,14 @@ extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
     const HostGraph& h = s->g->h;
     int rc = sim_count_nsat(s, s->d_counts);
     if (rc) return rc;
-    double* d_out = nullptr;
-    CUDA_TRY(ctx, dev_alloc(&d_out, s->E));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 2, s->E * sizeof(double), &dv));
+    double* d_out = (double*)dv;
     count_launch(s, launch_energy_from_nsat(s->d_counts, s->E, h.jabs, h.nedges, d_out, 1, 0,
                                             ctx->stream));
-    cudaError_t e = cudaMemcpyAsync(energies, d_out, s->E * sizeof(double), cudaMemcpyDeviceToHost,
-                                    ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_out);
-    CUDA_TRY(ctx, e);
+    CUDA_TRY(ctx, cudaMemcpyAsync(energies, d_out, s->E * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ISING_OK;
 }
 
@@ -538,13 +614,12 @@ static int sim_states_to_host(ising_sim* s, uint8_t* states) {
     ising_ctx* ctx = s->ctx;
     const uint64_t N = s->lay.nvars;
     const size_t bytes = (size_t)s->E * N;
-    uint8_t* d = nullptr;
-    CUDA_TRY(ctx, dev_alloc(&d, bytes));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, bytes, &dv));
+    uint8_t* d = (uint8_t*)dv;
     count_launch(s, launch_unpack_states(s->d_spins, s->lay, d, s->E, N, ctx->stream));
-    cudaError_t e = cudaMemcpyAsync(states, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    CUDA_TRY(ctx, e);
+    CUDA_TRY(ctx, cudaMemcpyAsync(states, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ISING_OK;
 }
 
@@ -559,13 +634,12 @@ extern "C" int ising_sim_get_packed(ising_sim* s, uint32_t* words) {
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)s->lay.nvars * s->lay.W;
-    uint32_t* d = nullptr;
-    CUDA_TRY(ctx, dev_alloc(&d, n));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, n * 4, &dv));
+    uint32_t* d = (uint32_t*)dv;
     count_launch(s, launch_export_natural(s->d_spins, s->lay, d, ctx->stream));
-    cudaError_t e = cudaMemcpyAsync(words, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    CUDA_TRY(ctx, e);
+    CUDA_TRY(ctx, cudaMemcpyAsync(words, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ISING_OK;
 }
 

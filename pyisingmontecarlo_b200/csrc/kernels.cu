@@ -47,6 +47,134 @@ __device__ __forceinline__ void count_sat(const uint32_t (&a)[2 * DIM], uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
+// vertical (bit-sliced) counters: plane l holds bit l of 32 independent per-replica counters
+// ------------------------------------------------------------------------------------------
+template <int NP>
+struct VCount {
+    uint32_t v[NP];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int l = 0; l < NP; ++l) v[l] = 0;
+    }
+    // counters += b0 + 2 b1 + 4 b2
+    __device__ __forceinline__ void add3(uint32_t b0, uint32_t b1, uint32_t b2) {
+        uint32_t c = v[0] & b0;
+        v[0] ^= b0;
+        uint32_t t = v[1] ^ b1, c2 = (v[1] & b1) | (c & t);
+        v[1] = t ^ c;
+        c = c2;
+        t = v[2] ^ b2;
+        c2 = (v[2] & b2) | (c & t);
+        v[2] = t ^ c;
+        c = c2;
+#pragma unroll
+        for (int l = 3; l < NP; ++l) {
+            t = v[l] & c;
+            v[l] ^= c;
+            c = t;
+        }
+    }
+    __device__ __forceinline__ void add1(uint32_t b0) {
+        uint32_t c = b0;
+#pragma unroll
+        for (int l = 0; l < NP; ++l) {
+            const uint32_t t = v[l] & c;
+            v[l] ^= c;
+            c = t;
+        }
+    }
+    // sm is int[32][nthreads]; adds this thread's 32 counters to its column
+    __device__ __forceinline__ void flush(int* sm, int tid, int nthreads) {
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b) {
+            int cnt = 0;
+#pragma unroll
+            for (int l = 0; l < NP; ++l) cnt |= (int)((v[l] >> b) & 1u) << l;
+            sm[b * nthreads + tid] += cnt;
+        }
+        clear();
+    }
+};
+
+// --- bit-sliced helpers for the cross-thread reduction of vertical counters --------------------
+// acc (NR planes) += x (NX planes), both little-endian bit-sliced integers
+template <int NR, int NX>
+__device__ __forceinline__ void vadd(uint32_t (&acc)[NR], const uint32_t (&x)[NX]) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int l = 0; l < NR; ++l) {
+        const uint32_t xi = l < NX ? x[l] : 0u;
+        const uint32_t t = acc[l] ^ xi;
+        const uint32_t c2 = (acc[l] & xi) | (c & t);
+        acc[l] = t ^ c;
+        c = c2;
+    }
+}
+
+constexpr int NS_NR = 16;  // block-level counter planes: up to 65535 per replica and block
+
+// Block-wide reduction of per-thread vertical counters (NP planes, V replica words per thread,
+// block = (wx, by)) into per-experiment integers: bit-sliced tree through shared memory, then
+// one SWAR bit-transpose per word column and 32 integer atomics per column.
+//   sm: max(NP * V, NS_NR) * nthreads words;  out[(w0 + column) * 32 + bit] += count
+template <int NP, int V>
+__device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], uint32_t* sm,
+                                                    unsigned long long* __restrict__ out,
+                                                    uint32_t w0, uint32_t W) {
+    const uint32_t wx = blockDim.x, by = blockDim.y, nthreads = wx * by;
+    const uint32_t tid = threadIdx.y * wx + threadIdx.x;
+    const uint32_t C = wx * V;  // word columns of this chunk (C divides nthreads)
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int l = 0; l < NP; ++l) sm[(l * V + v) * nthreads + tid] = vc[v].v[l];
+    __syncthreads();
+    // stage A: thread (column c, part q) adds the counters of every Q-th row-thread
+    const uint32_t Q = nthreads / C;
+    const uint32_t c = tid % C, q = tid / C;
+    const uint32_t cx = c / V, cv = c % V;
+    uint32_t acc[NS_NR];
+#pragma unroll
+    for (int l = 0; l < NS_NR; ++l) acc[l] = 0;
+    for (uint32_t ty = q; ty < by; ty += Q) {
+        uint32_t x[NP];
+#pragma unroll
+        for (int l = 0; l < NP; ++l) x[l] = sm[(l * V + cv) * nthreads + ty * wx + cx];
+        vadd<NS_NR, NP>(acc, x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < NS_NR; ++l) sm[l * nthreads + tid] = acc[l];  // [plane][q][c]
+    __syncthreads();
+    // stage B: one thread per column finishes the sum and transposes it to integers
+    if (tid < C && w0 + c < W) {
+        for (uint32_t qq = 1; qq < Q; ++qq) {
+            uint32_t x[NS_NR];
+#pragma unroll
+            for (int l = 0; l < NS_NR; ++l) x[l] = sm[l * nthreads + qq * C + c];
+            vadd<NS_NR, NS_NR>(acc, x);
+        }
+        unsigned long long* o = out + (size_t)(w0 + c) * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {  // SWAR: bits g, g+8, g+16, g+24 in four byte lanes
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                lo += ((acc[l] >> g) & 0x01010101u) << l;
+                hi += ((acc[l + 8] >> g) & 0x01010101u) << l;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t cnt = ((lo >> (8 * k)) & 0xFFu) | (((hi >> (8 * k)) & 0xFFu) << 8);
+                if (cnt) atomicAdd(o + g + 8 * k, (unsigned long long)cnt);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
 // Metropolis acceptance of the uphill bits of one word.
 //   up   : bits with dE > 0;  (sel1, sel0) select the class of each such bit
 //   K bit-planes R_0..R_{K-1} are the K most significant bits of a uniform U per replica and
@@ -153,37 +281,52 @@ __device__ __forceinline__ void store_words(uint32_t* p, const uint32_t (&in)[V]
 #ifndef ISING_SWEEP_MAXV
 #define ISING_SWEEP_MAXV 4
 #endif
-template <int DIM, bool PMJ, int K, int ROUNDS, int V>
-__global__ void __launch_bounds__(256, ISING_SWEEP_MIN_BLOCKS)
+constexpr int SW_NP = 7;                     // fused n_sat counters: up to 127 per thread
+constexpr int SW_MAX_ITEMS = 127 / 6;        // sites a thread may accumulate (n_sat <= 6)
+
+// ACC: this phase also accumulates the post-flip satisfied-bond count of every replica into
+// nsat[] (used for the second colour: its sites see every bond once, so after the phase
+// nsat[e] is the total of experiment e and E = |J| (n_bonds - 2 nsat), lattice.rs:454).
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
+__global__ void __launch_bounds__(256, ACC ? 2 : ISING_SWEEP_MIN_BLOCKS)
 k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                 const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
-                uint32_t k0, uint32_t k1, uint32_t gw0, uint32_t antiferro, MscThresholds th) {
+                uint32_t k0, uint32_t k1, uint32_t gw0, uint32_t antiferro, MscThresholds th,
+                unsigned long long* __restrict__ nsat) {
+    extern __shared__ uint32_t sm[];
     constexpr int kUnrollV = ISING_SWEEP_UNROLL_V;
     const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
     const uint32_t rowlen = Lxh * W;  // words per colour row (< 2^32: checked on the host)
-    for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
-        const uint32_t z = row / Ly, y = row - z * Ly;
-        const uint32_t p = (y + z + c) & 1u;
-        const uint32_t ym = y == 0 ? Ly - 1 : y - 1, yp = y + 1 == Ly ? 0 : y + 1;
-        uint32_t* __restrict__ o_c = own + (size_t)row * rowlen;
-        const uint32_t* __restrict__ n_x = oth + (size_t)row * rowlen;
-        const uint32_t* __restrict__ n_ym = oth + (size_t)(z * Ly + ym) * rowlen;
-        const uint32_t* __restrict__ n_yp = oth + (size_t)(z * Ly + yp) * rowlen;
-        const uint32_t* __restrict__ n_zm = nullptr;
-        const uint32_t* __restrict__ n_zp = nullptr;
-        if (DIM == 3) {
-            const uint32_t zm = z == 0 ? Lz - 1 : z - 1, zp = z + 1 == Lz ? 0 : z + 1;
-            n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
-            n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
-        }
-        for (uint32_t xh = threadIdx.y; xh < Lxh; xh += blockDim.y) {
-            const uint32_t xs = p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
-            uint32_t m[2 * DIM];
+    for (uint32_t w0 = 0; w0 < W; w0 += V * blockDim.x) {
+        const uint32_t w = w0 + V * threadIdx.x;
+        VCount<ACC ? SW_NP : 1> vc[V];
+        if constexpr (ACC) {
 #pragma unroll
-            for (int k = 0; k < 2 * DIM; ++k)
-                m[k] = PMJ ? __ldg(jm + (size_t)k * L.halfN + (size_t)row * Lxh + xh) : antiferro;
-            const uint32_t site = row * L.Lx + 2 * xh + p;
-            for (uint32_t w = V * threadIdx.x; w < W; w += V * blockDim.x) {
+            for (int v = 0; v < V; ++v) vc[v].clear();
+        }
+        if (w < W)
+        for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
+            const uint32_t z = row / Ly, y = row - z * Ly;
+            const uint32_t p = (y + z + c) & 1u;
+            const uint32_t ym = y == 0 ? Ly - 1 : y - 1, yp = y + 1 == Ly ? 0 : y + 1;
+            uint32_t* __restrict__ o_c = own + (size_t)row * rowlen;
+            const uint32_t* __restrict__ n_x = oth + (size_t)row * rowlen;
+            const uint32_t* __restrict__ n_ym = oth + (size_t)(z * Ly + ym) * rowlen;
+            const uint32_t* __restrict__ n_yp = oth + (size_t)(z * Ly + yp) * rowlen;
+            const uint32_t* __restrict__ n_zm = nullptr;
+            const uint32_t* __restrict__ n_zp = nullptr;
+            if (DIM == 3) {
+                const uint32_t zm = z == 0 ? Lz - 1 : z - 1, zp = z + 1 == Lz ? 0 : z + 1;
+                n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
+                n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
+            }
+            for (uint32_t xh = threadIdx.y; xh < Lxh; xh += blockDim.y) {
+                const uint32_t xs = p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
+                uint32_t m[2 * DIM];
+#pragma unroll
+                for (int k = 0; k < 2 * DIM; ++k)
+                    m[k] = PMJ ? __ldg(jm + (size_t)k * L.halfN + (size_t)row * Lxh + xh) : antiferro;
+                const uint32_t site = row * L.Lx + 2 * xh + p;
                 const uint32_t i = xh * W + w;
                 uint32_t s[V], n[2 * DIM][V];
                 load_words<V>(o_c + i, s);
@@ -210,28 +353,61 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                         flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, site,
                                                            gw0 + w + v, sweep, k0, k1);
                     s[v] ^= flip;
+                    if constexpr (ACC) {
+                        // a flipped spin turns its n_sat satisfied bonds into 2*DIM - n_sat
+                        uint32_t c1, c2;
+                        if (DIM == 3) {
+                            c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
+                            c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
+                        } else {
+                            c1 = (flip & (b1 ^ b0)) | (~flip & b1);
+                            c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
+                        }
+                        vc[v].add3(b0, c1, c2);
+                    }
                 }
                 store_words<V>(o_c + i, s);
             }
         }
+        if constexpr (ACC) block_reduce_vcount<SW_NP, V>(vc, sm, nsat, w0, W);
     }
+}
+
+template <int DIM, bool PMJ, int K, int ROUNDS, int V>
+static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block,
+                               uint32_t c, bool acc) {
+    const Layout& L = a.lay;
+    const size_t csz = (size_t)L.halfN * L.W;
+    const size_t jsz = (size_t)2 * DIM * L.halfN;
+    uint32_t* own = a.spins + c * csz;
+    const uint32_t* oth = a.spins + (1 - c) * csz;
+    const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
+    if (!acc) {
+        k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, false><<<grid, block, 0, st>>>(
+            own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th, nullptr);
+        return;
+    }
+    // fused accumulation: persistent blocks so that the per-block reduction is amortised, but
+    // never more sites per thread than the SW_NP-plane counters can hold
+    if (block.y < (unsigned)V) block.y = V;
+    const uint32_t per_row = (L.Lxh + block.y - 1) / block.y;
+    uint64_t g = 148ull * 2;
+    const uint64_t need = ((uint64_t)L.rows * per_row + SW_MAX_ITEMS - 1) / SW_MAX_ITEMS;
+    if (g < need) g = need;
+    if (g > L.rows) g = L.rows;
+    const int nthreads = block.x * block.y;
+    const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
+    const size_t smem = (size_t)planes * nthreads * sizeof(uint32_t);
+    k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, true><<<dim3((unsigned)g), block, smem, st>>>(
+        own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th, a.nsat_out);
 }
 
 template <int DIM, bool PMJ, int K, int V>
 static int sweep_dispatch_rounds(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block) {
-    const Layout& L = a.lay;
-    const size_t csz = (size_t)L.halfN * L.W;
-    const size_t jsz = (size_t)2 * DIM * L.halfN;
     for (uint32_t c = 0; c < 2; ++c) {
-        uint32_t* own = a.spins + c * csz;
-        const uint32_t* oth = a.spins + (1 - c) * csz;
-        const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
-        if (a.rounds == 7)
-            k_sweep_stencil<DIM, PMJ, K, 7, V><<<grid, block, 0, st>>>(
-                own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th);
-        else
-            k_sweep_stencil<DIM, PMJ, K, 10, V><<<grid, block, 0, st>>>(
-                own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th);
+        const bool acc = a.nsat_out != nullptr && c == 1;
+        if (a.rounds == 7) sweep_launch_phase<DIM, PMJ, K, 7, V>(a, st, grid, block, c, acc);
+        else sweep_launch_phase<DIM, PMJ, K, 10, V>(a, st, grid, block, c, acc);
     }
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
@@ -293,55 +469,7 @@ int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
 // K3: positional popcount (per-experiment integer observables from packed words)
 // vertical counters: plane l of VCount holds bit l of 32 independent counters
 // ------------------------------------------------------------------------------------------
-template <int NP>
-struct VCount {
-    uint32_t v[NP];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int l = 0; l < NP; ++l) v[l] = 0;
-    }
-    // counters += b0 + 2 b1 + 4 b2
-    __device__ __forceinline__ void add3(uint32_t b0, uint32_t b1, uint32_t b2) {
-        uint32_t c = v[0] & b0;
-        v[0] ^= b0;
-        uint32_t t = v[1] ^ b1, c2 = (v[1] & b1) | (c & t);
-        v[1] = t ^ c;
-        c = c2;
-        t = v[2] ^ b2;
-        c2 = (v[2] & b2) | (c & t);
-        v[2] = t ^ c;
-        c = c2;
-#pragma unroll
-        for (int l = 3; l < NP; ++l) {
-            t = v[l] & c;
-            v[l] ^= c;
-            c = t;
-        }
-    }
-    __device__ __forceinline__ void add1(uint32_t b0) {
-        uint32_t c = b0;
-#pragma unroll
-        for (int l = 0; l < NP; ++l) {
-            const uint32_t t = v[l] & c;
-            v[l] ^= c;
-            c = t;
-        }
-    }
-    // sm is int[32][nthreads]; adds this thread's 32 counters to its column
-    __device__ __forceinline__ void flush(int* sm, int tid, int nthreads) {
-#pragma unroll 4
-        for (int b = 0; b < 32; ++b) {
-            int cnt = 0;
-#pragma unroll
-            for (int l = 0; l < NP; ++l) cnt |= (int)((v[l] >> b) & 1u) << l;
-            sm[b * nthreads + tid] += cnt;
-        }
-        clear();
-    }
-};
-
 constexpr int VC_PLANES = 12;           // counters up to 4095
-constexpr int VC_FLUSH_ADD3 = 4095 / 7; // adds of <= 7 before a flush
 constexpr int VC_FLUSH_ADD1 = 4095;
 
 // reduce sm[32][nthreads] over threadIdx.y and add to out[(w0 + tx) * 32 + b]
@@ -360,24 +488,31 @@ __device__ __forceinline__ void block_reduce_counts(int* sm, unsigned long long*
     __syncthreads();
 }
 
-template <int DIM, bool PMJ>
+constexpr int NS_NP = 10;   // per-thread counter planes: up to 1023 = 146 sites x 7
+constexpr int NS_MAX_ITEMS = 1023 / 7;
+
+// n_sat[e] += satisfied bonds of experiment e.  Colour-0 sites see every bond exactly once.
+// Per thread: V replica words, carry-save vertical counters over all its sites (no per-site
+// integer work); per block: bit-sliced tree reduction through shared memory, one SWAR
+// bit-transpose per word column, 32 integer atomics per column.
+template <int DIM, bool PMJ, int V>
 __global__ void __launch_bounds__(256)
 k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ jm, Layout L,
                uint32_t antiferro, unsigned long long* __restrict__ nsat) {
-    __shared__ int sm[32 * 256];
+    extern __shared__ uint32_t sm[];  // [max(NS_NP * V, NS_NR)][256]
     const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
-    const size_t rowlen = (size_t)Lxh * W;
+    const uint32_t rowlen = Lxh * W;
     const size_t csz = (size_t)L.halfN * W;
-    const uint32_t* __restrict__ own = spins;        // colour 0 sites: every bond exactly once
+    const uint32_t* __restrict__ own = spins;
     const uint32_t* __restrict__ oth = spins + csz;
-    const int nthreads = blockDim.x * blockDim.y;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (uint32_t w0 = 0; w0 < W; w0 += blockDim.x) {
-        for (int b = 0; b < 32; ++b) sm[b * nthreads + tid] = 0;
-        const uint32_t w = w0 + threadIdx.x;
-        VCount<VC_PLANES> vc;
-        vc.clear();
-        int pending = 0;
+    const uint32_t wx = blockDim.x, by = blockDim.y, nthreads = wx * by;
+    const uint32_t tid = threadIdx.y * wx + threadIdx.x;
+    const uint32_t C = wx * V;  // word columns handled per chunk
+    for (uint32_t w0 = 0; w0 < W; w0 += C) {
+        const uint32_t w = w0 + V * threadIdx.x;
+        VCount<NS_NP> vc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) vc[v].clear();
         if (w < W) {
             for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
                 const uint32_t z = row / Ly, y = row - z * Ly;
@@ -394,54 +529,82 @@ k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ 
                     n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
                     n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
                 }
-                for (uint32_t xh = threadIdx.y; xh < Lxh; xh += blockDim.y) {
+                for (uint32_t xh = threadIdx.y; xh < Lxh; xh += by) {
                     const uint32_t xs =
                         p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
-                    const size_t i = (size_t)xh * W + w;
-                    const uint32_t s = o_c[i];
-                    uint32_t m[2 * DIM], a[2 * DIM];
+                    const uint32_t i = xh * W + w;
+                    uint32_t m[2 * DIM];
 #pragma unroll
                     for (int k = 0; k < 2 * DIM; ++k)
                         m[k] = PMJ ? __ldg(jm + (size_t)k * L.halfN + (size_t)row * Lxh + xh)
                                    : antiferro;
-                    a[0] = ~(s ^ n_x[i] ^ m[0]);
-                    a[1] = ~(s ^ n_x[(size_t)xs * W + w] ^ m[1]);
-                    a[2] = ~(s ^ n_ym[i] ^ m[2]);
-                    a[3] = ~(s ^ n_yp[i] ^ m[3]);
+                    uint32_t s[V], n[2 * DIM][V];
+                    load_words<V>(o_c + i, s);
+                    load_words<V>(n_x + i, n[0]);
+                    load_words<V>(n_x + xs * W + w, n[1]);
+                    load_words<V>(n_ym + i, n[2]);
+                    load_words<V>(n_yp + i, n[3]);
                     if (DIM == 3) {
-                        a[4] = ~(s ^ n_zm[i] ^ m[4]);
-                        a[5] = ~(s ^ n_zp[i] ^ m[5]);
+                        load_words<V>(n_zm + i, n[4]);
+                        load_words<V>(n_zp + i, n[5]);
                     }
-                    uint32_t b0, b1, b2;
-                    count_sat<DIM>(a, b0, b1, b2);
-                    vc.add3(b0, b1, b2);
-                    if (++pending == VC_FLUSH_ADD3) {
-                        vc.flush(sm, tid, nthreads);
-                        pending = 0;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        uint32_t a[2 * DIM];
+#pragma unroll
+                        for (int k = 0; k < 2 * DIM; ++k) a[k] = ~(s[v] ^ n[k][v] ^ m[k]);
+                        uint32_t b0, b1, b2;
+                        count_sat<DIM>(a, b0, b1, b2);
+                        vc[v].add3(b0, b1, b2);
                     }
                 }
             }
-            vc.flush(sm, tid, nthreads);
         }
-        block_reduce_counts(sm, nsat, w0, W);
+        block_reduce_vcount<NS_NP, V>(vc, sm, nsat, w0, W);
     }
+}
+
+template <int V>
+static int nsat_dispatch(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
+                         uint32_t antiferro, unsigned long long* nsat, cudaStream_t st) {
+    dim3 grid, block;
+    stencil_block_shape(lay, V, &grid, &block, false);
+    if (block.y < (unsigned)V) block.y = V;  // the reduction needs >= one thread per word column
+    // every thread may accumulate at most NS_MAX_ITEMS sites before its counters overflow
+    const uint32_t per_row = (lay.Lxh + block.y - 1) / block.y;
+    uint64_t g = 148ull * 2;
+    const uint64_t need = ((uint64_t)lay.rows * per_row + NS_MAX_ITEMS - 1) / NS_MAX_ITEMS;
+    if (g < need) g = need;
+    if (g > lay.rows) g = lay.rows;
+    if ((uint64_t)((lay.rows + g - 1) / g) * per_row > NS_MAX_ITEMS) return -1;
+    grid = dim3((unsigned)g, 1, 1);
+    const int nthreads = block.x * block.y;
+    const int planes = NS_NP * V > NS_NR ? NS_NP * V : NS_NR;
+    const size_t smem = (size_t)planes * nthreads * sizeof(uint32_t);
+    const bool pmj = jmask != nullptr;
+#define NSAT_LAUNCH(D, P)                                                                     \
+    do {                                                                                      \
+        if (smem > 48 * 1024)                                                                 \
+            cudaFuncSetAttribute(k_nsat_stencil<D, P, V>,                                     \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        k_nsat_stencil<D, P, V><<<grid, block, smem, st>>>(spins, jmask, lay, antiferro, nsat); \
+    } while (0)
+    if (lay.kind == ISING_KIND_STENCIL3D) {
+        if (pmj) NSAT_LAUNCH(3, true); else NSAT_LAUNCH(3, false);
+    } else if (lay.kind == ISING_KIND_STENCIL2D) {
+        if (pmj) NSAT_LAUNCH(2, true); else NSAT_LAUNCH(2, false);
+    } else {
+        return -1;
+    }
+#undef NSAT_LAUNCH
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
                         uint32_t antiferro, unsigned long long* nsat, cudaStream_t st) {
-    dim3 grid, block;
-    stencil_block_shape(lay, 1, &grid, &block, true);
-    const bool pmj = jmask != nullptr;
-    if (lay.kind == ISING_KIND_STENCIL3D) {
-        if (pmj) k_nsat_stencil<3, true><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
-        else k_nsat_stencil<3, false><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
-    } else if (lay.kind == ISING_KIND_STENCIL2D) {
-        if (pmj) k_nsat_stencil<2, true><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
-        else k_nsat_stencil<2, false><<<grid, block, 0, st>>>(spins, jmask, lay, antiferro, nsat);
-    } else {
-        return -1;
-    }
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (lay.W % 4 == 0) return nsat_dispatch<4>(spins, jmask, lay, antiferro, nsat, st);
+    if (lay.W % 2 == 0) return nsat_dispatch<2>(spins, jmask, lay, antiferro, nsat, st);
+    return nsat_dispatch<1>(spins, jmask, lay, antiferro, nsat, st);
 }
 
 // up-spin count over all sites (any layout: the sum runs over every stored site word)
@@ -490,6 +653,25 @@ __global__ void k_energy_from_nsat(const unsigned long long* __restrict__ nsat, 
     if (e >= E) return;
     const long long v = (long long)nbonds - 2ll * (long long)nsat[e];
     out[e * estride + eoff] = scale * (double)v;
+}
+
+// energies[e * nt + t] = scale * (nbonds - 2 * hist[t * cw + e]) for a chunk of nt sweeps
+__global__ void k_energy_from_hist(const unsigned long long* __restrict__ hist, uint64_t E,
+                                   uint64_t cw, uint64_t nt, double scale, uint64_t nbonds,
+                                   double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * nt) return;
+    const uint64_t e = i / nt, t = i - e * nt;
+    const long long v = (long long)nbonds - 2ll * (long long)hist[t * cw + e];
+    out[i] = scale * (double)v;
+}
+
+int launch_energy_from_hist(const unsigned long long* hist, uint64_t E, uint64_t cw, uint64_t nt,
+                            double scale, uint64_t nbonds, double* out_dev, cudaStream_t st) {
+    const uint64_t n = E * nt;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    k_energy_from_hist<<<g ? g : 1, 256, 0, st>>>(hist, E, cw, nt, scale, nbonds, out_dev);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,

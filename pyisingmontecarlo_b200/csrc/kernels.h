@@ -37,6 +37,9 @@ struct SweepArgs {
     uint32_t antiferro;     // uniform-sign lattices: all-ones iff J > 0
     int planes, rounds;
     MscThresholds th;
+    // when non-null the second colour phase also accumulates the per-experiment satisfied-bond
+    // count after the sweep into nsat_out[W * 32] (must be zeroed by the caller)
+    unsigned long long* nsat_out;
 };
 
 // both colour phases of one sweep (2 launches); returns launches made or -1
@@ -63,6 +66,9 @@ int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* ou
 int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,
                             uint64_t nbonds, double* out_dev, uint64_t estride, uint64_t eoff,
                             cudaStream_t st);
+
+int launch_energy_from_hist(const unsigned long long* hist, uint64_t E, uint64_t cw, uint64_t nt,
+                            double scale, uint64_t nbonds, double* out_dev, cudaStream_t st);
 
 struct ReplayArgs {
     uint64_t E, N, A;

@@ -127,9 +127,9 @@ class Lattice:
             raise ValueError("Transverse field must be positive")
 
     def set_initial_state(self, initial_state):
-        initial_state = list(initial_state)
+        initial_state = np.asarray(initial_state, dtype=np.bool_).ravel()
         if len(initial_state) == self.nvars:
-            self._initial_state = np.asarray(initial_state, dtype=np.bool_)
+            self._initial_state = initial_state.copy()
         elif len(initial_state) == 0:
             self._initial_state = None
         else:
@@ -191,7 +191,7 @@ class Lattice:
         """lattice.rs:171-221 -> (energies float64[E], states bool[E, nvars])"""
         flags = self._check_classical(edge_move_importance_sampling)
         energies = np.zeros(num_experiments, dtype=np.float64)
-        states = np.zeros((num_experiments, self.nvars), dtype=np.bool_)
+        states = nat.PinnedPool.empty((num_experiments, self.nvars), np.bool_)
         args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
                           num_experiments=int(num_experiments))
         self._call(nat.lib().ising_run_monte_carlo, args, energies, states)
@@ -208,7 +208,7 @@ class Lattice:
             raise ZeroDivisionError("sampling_freq must be non-zero (the reference panics)")
         n_samples = int(timesteps) // sampling_freq
         energies = np.zeros((num_experiments, n_samples), dtype=np.float64)
-        states = np.zeros((num_experiments, n_samples, self.nvars), dtype=np.bool_)
+        states = nat.PinnedPool.empty((num_experiments, n_samples, self.nvars), np.bool_)
         args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
                           num_experiments=int(num_experiments), thermalization=thermalization_time,
                           sampling_freq=sampling_freq)
@@ -225,8 +225,8 @@ class Lattice:
         st = np.ascontiguousarray([int(t) for t, _ in betas], dtype=np.uint64)
         sb = np.ascontiguousarray([float(v) for _, v in betas], dtype=np.float64)
         shape = (num_experiments, int(timesteps)) if per_step else (num_experiments,)
-        energies = np.zeros(shape, dtype=np.float64)
-        states = np.zeros((num_experiments, self.nvars), dtype=np.bool_)
+        energies = nat.PinnedPool.empty(shape, np.float64)
+        states = nat.PinnedPool.empty((num_experiments, self.nvars), np.bool_)
         args = self._args(flags, sched_t=st if len(st) else None, sched_beta=sb if len(sb) else None,
                           sched_len=len(st), timesteps=int(timesteps),
                           num_experiments=int(num_experiments))
