@@ -44,6 +44,7 @@ enum {
 typedef struct ising_ctx ising_ctx;
 typedef struct ising_graph ising_graph;
 typedef struct ising_sim ising_sim;
+typedef struct ising_pt ising_pt;
 
 /* ---- context ---------------------------------------------------------------------------- */
 ISING_API int ising_abi_version(void);
@@ -95,7 +96,15 @@ ISING_API int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t *out);
  * enters the Philox counters, so a sharded run reproduces the unsharded one bit for bit.   */
 ISING_API int ising_sim_create(ising_ctx *ctx, const ising_graph *g, uint64_t num_experiments,
                      uint64_t seed, uint64_t replica_offset, ising_sim **out);
+/* flags: ISING_SIM_GENERAL_LAYOUT runs a recognised torus through the general (colour x degree
+ * group) kernels in natural site order -- needed for per-experiment betas. */
+enum { ISING_SIM_GENERAL_LAYOUT = 1u << 0 };
+ISING_API int ising_sim_create_ex(ising_ctx *ctx, const ising_graph *g, uint64_t num_experiments,
+                        uint64_t seed, uint64_t replica_offset, uint32_t flags, ising_sim **out);
 ISING_API void ising_sim_destroy(ising_sim *sim);
+/* Experiment e runs at betas[e] from now on (parallel tempering: one replica bit per
+ * temperature); afterwards ising_sim_sweeps takes betas = NULL. */
+ISING_API int ising_sim_set_betas(ising_sim *sim, const double *betas /* E */);
 /* Tuning knobs of the multi-spin-coded kernel; 0 keeps the default.  planes = bit-planes
  * compared before the per-bit resolver (4..8), rounds = Philox4x32 rounds (7 or 10).      */
 ISING_API int ising_sim_configure(ising_sim *sim, int planes, int rounds);
@@ -179,6 +188,38 @@ ISING_API int ising_schedule_betas(const uint64_t *sched_t, const double *sched_
 ISING_API int ising_replay(ising_ctx *ctx, const ising_graph *g, double beta, uint64_t num_experiments,
                  uint64_t nattempts, const uint32_t *sites, const double *u,
                  const uint8_t *init, double *energies, uint8_t *states);
+
+/* ---- classical parallel tempering with the cadence of tempering.rs:156-222 --------------- */
+/* One configuration per inverse temperature ("slot"), every configuration one replica bit of
+ * the packed layout, so a whole temperature ladder advances in one sweep.  A swap exchanges the
+ * betas of two configurations (equivalent to exchanging the configurations, tempering.rs:192),
+ * nothing moves.  Multi-GPU: rank r owns configurations [cfg_lo, cfg_hi); after an all-gather
+ * of the per-configuration energies every rank takes identical swap decisions (Philox keyed
+ * by seed and swap step), so there is no second collective. */
+ISING_API int ising_pt_create(ising_ctx *ctx, const ising_graph *g, const double *betas, uint64_t nbetas,
+                    uint64_t cfg_lo, uint64_t cfg_hi, uint64_t seed, ising_pt **out);
+ISING_API void ising_pt_destroy(ising_pt *pt);
+ISING_API int ising_pt_configure(ising_pt *pt, int planes, int rounds);
+/* t sweeps of the local configurations, then their energies, local_energies[cfg_hi - cfg_lo]
+ * (may be NULL).  Replaces graph.timesteps(t, beta) of tempering.rs:179-186. */
+ISING_API int ising_pt_sweeps(ising_pt *pt, uint64_t t, double *local_energies);
+/* TemperingContainer::parallel_tempering_step (tempering.rs:192); all_energies[nbetas] by
+ * configuration. */
+ISING_API int ising_pt_swap_step(ising_pt *pt, const double *all_energies);
+/* The decision rule alone (host only, no device): even pairs then odd pairs of slots, pair
+ * (a, a+1) swaps with probability min(1, exp((b_a - b_{a+1})(E_a - E_{a+1}))), uniform =
+ * Philox(seed; a, parity, swap_step).  Updates the two permutations in place. */
+ISING_API int ising_pt_decide_swaps(const double *betas, uint64_t nbetas, const double *all_energies,
+                          uint64_t seed, uint64_t swap_step, uint32_t *slot_of_config,
+                          uint32_t *config_of_slot, uint64_t *nswaps);
+ISING_API int ising_pt_get_slots(const ising_pt *pt, uint32_t *slot_of_config /* nbetas */);
+ISING_API int ising_pt_get_local_states(ising_pt *pt, uint8_t *states /* (cfg_hi-cfg_lo)*nvars */);
+/* LatticeTempering::get_total_swaps, tempering.rs:297-299 */
+ISING_API int ising_pt_total_swaps(const ising_pt *pt, uint64_t *out);
+/* LatticeTempering::qmc_timesteps_sample (tempering.rs:156-222) on one rank:
+ * states bool[R, timesteps / sampling_freq, nvars], energies[R]. */
+ISING_API int ising_pt_timesteps_sample(ising_pt *pt, uint64_t timesteps, uint64_t replica_swap_freq,
+                              uint64_t sampling_freq, uint8_t *states, double *energies);
 
 #ifdef __cplusplus
 }

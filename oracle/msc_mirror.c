@@ -64,107 +64,203 @@ static uint64_t threshold(double beta, double de, int K) {
     return (uint64_t)floor(scaled);
 }
 
+typedef struct {
+    uint64_t nvars, nedges;
+    const uint64_t *ea, *eb;
+    const double *ej;
+    const uint32_t *colors;
+    uint32_t ncolors;
+    uint64_t *row, *nbr;
+    uint8_t *anti;
+    double jabs;
+    uint32_t k0, k1, gw0;
+    int K, rounds;
+} mirror_t;
+
+static int mirror_init(mirror_t *m, uint64_t nvars, uint64_t nedges, const uint64_t *ea,
+                       const uint64_t *eb, const double *ej, const uint32_t *colors,
+                       uint32_t ncolors, uint64_t seed, uint64_t replica_offset, int K, int rounds) {
+    if (nedges == 0 || K < 1 || K > 8) return -1;
+    m->jabs = fabs(ej[0]);
+    for (uint64_t e = 0; e < nedges; ++e)
+        if (fabs(ej[e]) != m->jabs) return -2;
+    m->nvars = nvars; m->nedges = nedges; m->ea = ea; m->eb = eb; m->ej = ej;
+    m->colors = colors; m->ncolors = ncolors;
+    m->k0 = (uint32_t)seed; m->k1 = (uint32_t)(seed >> 32);
+    m->gw0 = (uint32_t)(replica_offset / 32);
+    m->K = K; m->rounds = rounds;
+    m->row = (uint64_t *)calloc(nvars + 1, sizeof(uint64_t));
+    for (uint64_t e = 0; e < nedges; ++e) { m->row[ea[e] + 1]++; m->row[eb[e] + 1]++; }
+    for (uint64_t i = 0; i < nvars; ++i) m->row[i + 1] += m->row[i];
+    m->nbr = (uint64_t *)malloc(sizeof(uint64_t) * 2 * nedges);
+    m->anti = (uint8_t *)malloc(2 * nedges);
+    uint64_t *fill = (uint64_t *)calloc(nvars, sizeof(uint64_t));
+    for (uint64_t e = 0; e < nedges; ++e) {
+        uint64_t a = ea[e], b = eb[e];
+        m->nbr[m->row[a] + fill[a]] = b; m->anti[m->row[a] + fill[a]++] = ej[e] > 0;
+        m->nbr[m->row[b] + fill[b]] = a; m->anti[m->row[b] + fill[b]++] = ej[e] > 0;
+    }
+    free(fill);
+    return 0;
+}
+
+static void mirror_free(mirror_t *m) { free(m->row); free(m->nbr); free(m->anti); }
+
+static void mirror_randomize(const mirror_t *m, uint64_t E, uint8_t *states) {
+    const uint64_t W = (E + 31) / 32;
+    for (uint64_t n = 0; n < m->nvars; ++n)
+        for (uint64_t w = 0; w < W; ++w) {
+            uint32_t c[4] = {(uint32_t)n, m->gw0 + (uint32_t)w, 0u, 1u << 24};
+            philox4x32(10, c, m->k0, m->k1);
+            for (uint64_t b = 0; b < 32 && w * 32 + b < E; ++b)
+                states[(w * 32 + b) * m->nvars + n] = (c[0] >> b) & 1u;
+        }
+}
+
+/* one colour-class sweep; replica e runs at beta[e] (beta_stride = 0: one beta for all) */
+static void mirror_sweep(const mirror_t *m, uint64_t E, uint8_t *states, const double *beta,
+                         int beta_stride, uint32_t sweep) {
+    const uint64_t W = (E + 31) / 32, nvars = m->nvars;
+    const int K = m->K;
+    for (uint32_t col = 0; col < m->ncolors; ++col)
+        for (uint64_t n = 0; n < nvars; ++n) {
+            if (m->colors[n] != col) continue;
+            const int d = (int)(m->row[n + 1] - m->row[n]);
+            for (uint64_t w = 0; w < W; ++w) {
+                int j = 0; /* resolver rank within the word */
+                for (uint64_t b = 0; b < 32 && w * 32 + b < E; ++b) {
+                    uint8_t *st = states + (w * 32 + b) * nvars;
+                    int nsat = 0;
+                    for (uint64_t k = m->row[n]; k < m->row[n + 1]; ++k) {
+                        const int equal = st[n] == st[m->nbr[k]];
+                        nsat += m->anti[k] ? !equal : equal;
+                    }
+                    const int cls = 2 * nsat - d;
+                    if (cls <= 0) { st[n] ^= 1; continue; }
+                    const double bt = beta[beta_stride ? (w * 32 + b) : 0];
+                    const uint64_t T = threshold(bt, 2.0 * m->jabs * (double)cls, K);
+                    int decided = 0, accept = 0;
+                    for (int p = 0; p < K && !decided; ++p) {
+                        const uint32_t rb = (stream_word(m->rounds, (uint32_t)n, m->gw0 + (uint32_t)w,
+                                                         sweep, (uint32_t)p, m->k0, m->k1) >> b) & 1u;
+                        const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
+                        if (rb != tb) { decided = 1; accept = rb < tb; }
+                    }
+                    if (!decided) {
+                        const uint32_t v = stream_word(m->rounds, (uint32_t)n, m->gw0 + (uint32_t)w,
+                                                       sweep, (uint32_t)(K + j), m->k0, m->k1);
+                        accept = v < (uint32_t)(T & 0xFFFFFFFFull);
+                        ++j;
+                    }
+                    if (accept) st[n] ^= 1;
+                }
+            }
+        }
+}
+
+static double mirror_energy(const mirror_t *m, const uint8_t *st) {
+    long long nsat = 0;
+    for (uint64_t k = 0; k < m->nedges; ++k) {
+        const int equal = st[m->ea[k]] == st[m->eb[k]];
+        nsat += (m->ej[k] > 0) ? !equal : equal;
+    }
+    return m->jabs * (double)((long long)m->nedges - 2 * nsat);
+}
+
 /* states: bool[E, nvars], in/out (filled from Philox when randomize != 0, or broadcast from
  * init_state when given).  energies_per_sweep: double[E, nsweeps] or NULL.  final_energies:
- * double[E] or NULL. */
+ * double[E] or NULL.  per_replica_beta != 0: betas is double[E] (one per replica, constant over
+ * the sweeps) instead of double[nsweeps]. */
 ORC_EXPORT int msc_mirror_run(uint64_t nvars, uint64_t nedges, const uint64_t *ea,
                               const uint64_t *eb, const double *ej, const uint32_t *colors,
                               uint32_t ncolors, uint64_t E, uint64_t seed,
                               uint64_t replica_offset, int K, int rounds, int randomize,
                               const uint8_t *init_state, const double *betas, uint64_t nsweeps,
                               uint64_t sweep0, uint8_t *states, double *energies_per_sweep,
-                              double *final_energies) {
-    if (nedges == 0 || K < 1 || K > 8) return -1;
-    const double jabs = fabs(ej[0]);
-    for (uint64_t e = 0; e < nedges; ++e)
-        if (fabs(ej[e]) != jabs) return -2;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const uint32_t gw0 = (uint32_t)(replica_offset / 32);
-    /* adjacency with antiferro flag */
-    uint64_t *row = (uint64_t *)calloc(nvars + 1, sizeof(uint64_t));
-    for (uint64_t e = 0; e < nedges; ++e) { row[ea[e] + 1]++; row[eb[e] + 1]++; }
-    for (uint64_t i = 0; i < nvars; ++i) row[i + 1] += row[i];
-    uint64_t *nbr = (uint64_t *)malloc(sizeof(uint64_t) * 2 * nedges);
-    uint8_t *anti = (uint8_t *)malloc(2 * nedges);
-    uint64_t *fill = (uint64_t *)calloc(nvars, sizeof(uint64_t));
-    for (uint64_t e = 0; e < nedges; ++e) {
-        uint64_t a = ea[e], b = eb[e];
-        nbr[row[a] + fill[a]] = b; anti[row[a] + fill[a]++] = ej[e] > 0;
-        nbr[row[b] + fill[b]] = a; anti[row[b] + fill[b]++] = ej[e] > 0;
-    }
-    free(fill);
-    const uint64_t W = (E + 31) / 32;
-    if (randomize)
-        for (uint64_t n = 0; n < nvars; ++n)
-            for (uint64_t w = 0; w < W; ++w) {
-                uint32_t c[4] = {(uint32_t)n, gw0 + (uint32_t)w, 0u, 1u << 24};
-                philox4x32(10, c, k0, k1);
-                for (uint64_t b = 0; b < 32 && w * 32 + b < E; ++b)
-                    states[(w * 32 + b) * nvars + n] = (c[0] >> b) & 1u;
-            }
+                              double *final_energies, int per_replica_beta) {
+    mirror_t m;
+    int rc = mirror_init(&m, nvars, nedges, ea, eb, ej, colors, ncolors, seed, replica_offset, K, rounds);
+    if (rc) return rc;
+    if (randomize) mirror_randomize(&m, E, states);
     else if (init_state)
         for (uint64_t e = 0; e < E; ++e) memcpy(states + e * nvars, init_state, nvars);
-
     for (uint64_t t = 0; t < nsweeps; ++t) {
-        const double beta = betas[t];
-        const uint32_t sweep = (uint32_t)(sweep0 + t);
-        for (uint32_t col = 0; col < ncolors; ++col)
-            for (uint64_t n = 0; n < nvars; ++n) {
-                if (colors[n] != col) continue;
-                const int d = (int)(row[n + 1] - row[n]);
-                for (uint64_t w = 0; w < W; ++w) {
-                    int j = 0; /* resolver rank within the word */
-                    for (uint64_t b = 0; b < 32 && w * 32 + b < E; ++b) {
-                        uint8_t *st = states + (w * 32 + b) * nvars;
-                        int nsat = 0;
-                        for (uint64_t k = row[n]; k < row[n + 1]; ++k) {
-                            const int equal = st[n] == st[nbr[k]];
-                            nsat += anti[k] ? !equal : equal;
-                        }
-                        const int cls = 2 * nsat - d;
-                        if (cls <= 0) { st[n] ^= 1; continue; }
-                        const uint64_t T = threshold(beta, 2.0 * jabs * (double)cls, K);
-                        int decided = 0, accept = 0;
-                        for (int p = 0; p < K && !decided; ++p) {
-                            const uint32_t rb =
-                                (stream_word(rounds, (uint32_t)n, gw0 + (uint32_t)w, sweep,
-                                             (uint32_t)p, k0, k1) >> b) & 1u;
-                            const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
-                            if (rb != tb) { decided = 1; accept = rb < tb; }
-                        }
-                        if (!decided) {
-                            const uint32_t v = stream_word(rounds, (uint32_t)n, gw0 + (uint32_t)w,
-                                                           sweep, (uint32_t)(K + j), k0, k1);
-                            accept = v < (uint32_t)(T & 0xFFFFFFFFull);
-                            ++j;
-                        }
-                        if (accept) st[n] ^= 1;
+        if (per_replica_beta) mirror_sweep(&m, E, states, betas, 1, (uint32_t)(sweep0 + t));
+        else mirror_sweep(&m, E, states, betas + t, 0, (uint32_t)(sweep0 + t));
+        if (energies_per_sweep)
+            for (uint64_t e = 0; e < E; ++e)
+                energies_per_sweep[e * nsweeps + t] = mirror_energy(&m, states + e * nvars);
+    }
+    if (final_energies)
+        for (uint64_t e = 0; e < E; ++e) final_energies[e] = mirror_energy(&m, states + e * nvars);
+    mirror_free(&m);
+    return 0;
+}
+
+/* Parallel tempering exactly as libising_b200 runs it (ising_pt_timesteps_sample): one
+ * configuration per replica bit, betas[R] by slot, cadence of tempering.rs:156-222, swap rule
+ * and Philox draw of ising_pt_decide_swaps.  states[R, n_s, nvars], energies[R]. */
+ORC_EXPORT int msc_mirror_pt(uint64_t nvars, uint64_t nedges, const uint64_t *ea,
+                             const uint64_t *eb, const double *ej, const uint32_t *colors,
+                             uint32_t ncolors, uint64_t R, const double *betas, uint64_t seed, int K,
+                             int rounds, uint64_t timesteps, uint64_t swap_freq,
+                             uint64_t sampling_freq, uint8_t *states_out, double *energies_out,
+                             uint64_t *total_swaps, uint32_t *slot_of_cfg_out) {
+    if (swap_freq == 0 || sampling_freq == 0) return -3;
+    mirror_t m;
+    int rc = mirror_init(&m, nvars, nedges, ea, eb, ej, colors, ncolors, seed, 0, K, rounds);
+    if (rc) return rc;
+    uint8_t *cfg = (uint8_t *)malloc(R * nvars);
+    mirror_randomize(&m, R, cfg);
+    uint32_t *slot_of_cfg = (uint32_t *)malloc(sizeof(uint32_t) * R);
+    uint32_t *cfg_of_slot = (uint32_t *)malloc(sizeof(uint32_t) * R);
+    double *bcfg = (double *)malloc(sizeof(double) * R), *en = (double *)malloc(sizeof(double) * R);
+    double *acc = (double *)calloc(R, sizeof(double));
+    for (uint64_t r = 0; r < R; ++r) slot_of_cfg[r] = cfg_of_slot[r] = (uint32_t)r;
+    const uint64_t ns = timesteps / sampling_freq;
+    uint64_t remaining = timesteps, to_swap = swap_freq, to_sample = sampling_freq, k = 0;
+    uint64_t swaps = 0, swap_step = 0, sweep = 0;
+    while (remaining > 0) {
+        uint64_t t = to_sample < to_swap ? to_sample : to_swap;
+        if (remaining < t) t = remaining;
+        for (uint64_t c = 0; c < R; ++c) bcfg[c] = betas[slot_of_cfg[c]];
+        for (uint64_t i = 0; i < t; ++i) mirror_sweep(&m, R, cfg, bcfg, 1, (uint32_t)sweep++);
+        for (uint64_t c = 0; c < R; ++c) en[c] = mirror_energy(&m, cfg + c * nvars);
+        for (uint64_t s = 0; s < R; ++s) acc[s] += en[cfg_of_slot[s]] * (double)t;
+        to_sample -= t; to_swap -= t; remaining -= t;
+        if (to_swap == 0) {
+            for (int parity = 0; parity < 2; ++parity)
+                for (uint64_t a = parity; a + 1 < R; a += 2) {
+                    const uint32_t ca = cfg_of_slot[a], cb = cfg_of_slot[a + 1];
+                    const double d = (betas[a] - betas[a + 1]) * (en[ca] - en[cb]);
+                    int accept = 1;
+                    if (d < 0.0) {
+                        uint32_t c4[4] = {(uint32_t)a, (uint32_t)parity, (uint32_t)swap_step, 2u << 24};
+                        philox4x32(10, c4, m.k0, m.k1);
+                        const double uu = ((double)c4[0] + 0.5) * (1.0 / 4294967296.0);
+                        accept = uu < exp(d);
+                    }
+                    if (accept) {
+                        cfg_of_slot[a] = cb; cfg_of_slot[a + 1] = ca;
+                        slot_of_cfg[cb] = (uint32_t)a; slot_of_cfg[ca] = (uint32_t)(a + 1);
+                        ++swaps;
                     }
                 }
-            }
-        if (energies_per_sweep || (final_energies && t + 1 == nsweeps))
-            for (uint64_t e = 0; e < E; ++e) {
-                const uint8_t *st = states + e * nvars;
-                long long nsat = 0;
-                for (uint64_t k = 0; k < nedges; ++k) {
-                    const int equal = st[ea[k]] == st[eb[k]];
-                    nsat += (ej[k] > 0) ? !equal : equal;
-                }
-                const double en = jabs * (double)((long long)nedges - 2 * nsat);
-                if (energies_per_sweep) energies_per_sweep[e * nsweeps + t] = en;
-                if (final_energies && t + 1 == nsweeps) final_energies[e] = en;
-            }
-    }
-    if (final_energies && nsweeps == 0)
-        for (uint64_t e = 0; e < E; ++e) {
-            const uint8_t *st = states + e * nvars;
-            long long nsat = 0;
-            for (uint64_t k = 0; k < nedges; ++k) {
-                const int equal = st[ea[k]] == st[eb[k]];
-                nsat += (ej[k] > 0) ? !equal : equal;
-            }
-            final_energies[e] = jabs * (double)((long long)nedges - 2 * nsat);
+            ++swap_step;
+            to_swap = swap_freq;
         }
-    free(row); free(nbr); free(anti);
+        if (to_sample == 0) {
+            if (k < ns)
+                for (uint64_t s = 0; s < R; ++s)
+                    memcpy(states_out + (s * ns + k) * nvars, cfg + (uint64_t)cfg_of_slot[s] * nvars, nvars);
+            ++k;
+            to_sample = sampling_freq;
+        }
+    }
+    for (uint64_t s = 0; s < R; ++s) energies_out[s] = acc[s] / (double)timesteps;
+    if (total_swaps) *total_swaps = swaps;
+    if (slot_of_cfg_out) memcpy(slot_of_cfg_out, slot_of_cfg, sizeof(uint32_t) * R);
+    free(cfg); free(slot_of_cfg); free(cfg_of_slot); free(bcfg); free(en); free(acc);
+    mirror_free(&m);
     return 0;
 }

@@ -4,7 +4,10 @@ Only the data-parallel classical path is here: `Lattice.ru
 the annealing runs, replay mode and the parallel-tempering loop.  Compute lives in
 `libising_b200.so` (hand-written sm_100a CUDA behind the C ABI of include/ising_b200.h).
 """
-from ._native import AmbiguousReplay, Context, Graph, NativeLibraryMissing, Sim  # noqa: F401
+from ._native import (AmbiguousReplay, Context, Graph, NativeLibraryMissing, Sim,  # noqa: F401
+                      Tempering)
 from .lattice import Lattice  # noqa: F401
+from .tempering import LatticeTempering, run_tempering_loop, shard_range  # noqa: F401
 
-__all__ = ["Lattice", "Sim", "Graph", "Context", "AmbiguousReplay", "NativeLibraryMissing"]
+__all__ = ["Lattice", "LatticeTempering", "Sim", "Tempering", "Graph", "Context",
+           "AmbiguousReplay", "NativeLibraryMissing", "run_tempering_loop", "shard_range"]

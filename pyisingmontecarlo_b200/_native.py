@@ -91,6 +91,8 @@ _SIGNATURES = {
     "ising_graph_get_edges": (C.c_int, [_P, _P, _P, _P]),
     "ising_make_seeds": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
     "ising_sim_create": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
+    "ising_sim_create_ex": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
+    "ising_sim_set_betas": (C.c_int, [_P, _P]),
     "ising_sim_destroy": (None, [_P]),
     "ising_sim_configure": (C.c_int, [_P, C.c_int, C.c_int]),
     "ising_sim_randomize": (C.c_int, [_P]),
@@ -107,6 +109,16 @@ _SIGNATURES = {
     "ising_run_monte_carlo_sampling": (C.c_int, [_P, _P, C.POINTER(RunArgs), _P, _P]),
     "ising_run_monte_carlo_annealing": (C.c_int, [_P, _P, C.POINTER(RunArgs), _P, _P]),
     "ising_schedule_betas": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_int, _P]),
+    "ising_pt_create": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
+    "ising_pt_destroy": (None, [_P]),
+    "ising_pt_configure": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ising_pt_sweeps": (C.c_int, [_P, C.c_uint64, _P]),
+    "ising_pt_swap_step": (C.c_int, [_P, _P]),
+    "ising_pt_decide_swaps": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_uint64, _P, _P, C.POINTER(C.c_uint64)]),
+    "ising_pt_get_slots": (C.c_int, [_P, _P]),
+    "ising_pt_get_local_states": (C.c_int, [_P, _P]),
+    "ising_pt_total_swaps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "ising_pt_timesteps_sample": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "ising_replay": (C.c_int, [_P, _P, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
 }
 
@@ -300,13 +312,15 @@ class Graph:
 class Sim:
     """Device-resident replica-bit-packed experiments (ising_sim)."""
 
-    def __init__(self, graph, num_experiments, seed, replica_offset=0, planes=0, rounds=0):
+    def __init__(self, graph, num_experiments, seed, replica_offset=0, planes=0, rounds=0,
+                 general_layout=False):
         self.graph = graph
         self.ctx = graph.ctx
         self.E = int(num_experiments)
         h = C.c_void_p()
-        check(lib().ising_sim_create(self.ctx.handle, graph.handle, self.E, int(seed) & (2**64 - 1),
-                                     int(replica_offset), C.byref(h)), self.ctx.handle)
+        check(lib().ising_sim_create_ex(self.ctx.handle, graph.handle, self.E, int(seed) & (2**64 - 1),
+                                        int(replica_offset), 1 if general_layout else 0,
+                                        C.byref(h)), self.ctx.handle)
         self.handle = h
         if planes or rounds:
             check(lib().ising_sim_configure(h, int(planes), int(rounds)), self.ctx.handle)
@@ -327,10 +341,22 @@ class Sim:
         check(lib().ising_sim_set_states(self.handle, ptr(s)), self.ctx.handle)
 
     def sweeps(self, betas, per_sweep_energies=False):
-        b = np.ascontiguousarray(betas, dtype=np.float64)
-        out = np.empty((self.E, len(b)), dtype=np.float64) if per_sweep_energies else None
-        check(lib().ising_sim_sweeps(self.handle, ptr(b), len(b), ptr(out)), self.ctx.handle)
+        """betas: one inverse temperature per sweep, or an int = number of sweeps at the
+        per-experiment betas installed with set_betas()."""
+        if isinstance(betas, (int, np.integer)):
+            n, b = int(betas), None
+        else:
+            b = np.ascontiguousarray(betas, dtype=np.float64)
+            n = len(b)
+        out = np.empty((self.E, n), dtype=np.float64) if per_sweep_energies else None
+        check(lib().ising_sim_sweeps(self.handle, ptr(b), n, ptr(out)), self.ctx.handle)
         return out
+
+    def set_betas(self, betas):
+        b = np.ascontiguousarray(betas, dtype=np.float64)
+        if b.shape != (self.E,):
+            raise ValueError("betas must have one entry per experiment")
+        check(lib().ising_sim_set_betas(self.handle, ptr(b)), self.ctx.handle)
 
     def energies(self):
         out = np.empty(self.E, dtype=np.float64)
@@ -371,6 +397,83 @@ class Sim:
             self.close()
         except Exception:
             pass
+
+
+class Tempering:
+    """Classical parallel tempering on the device (ising_pt): configurations [cfg_lo, cfg_hi)
+    of a ladder of `betas` live on this rank."""
+
+    def __init__(self, graph, betas, seed, cfg_lo=0, cfg_hi=None, planes=0, rounds=0):
+        self.graph = graph
+        self.ctx = graph.ctx
+        self.betas = np.ascontiguousarray(betas, dtype=np.float64)
+        self.R = len(self.betas)
+        self.lo = int(cfg_lo)
+        self.hi = self.R if cfg_hi is None else int(cfg_hi)
+        h = C.c_void_p()
+        check(lib().ising_pt_create(self.ctx.handle, graph.handle, ptr(self.betas), self.R, self.lo,
+                                    self.hi, int(seed) & (2**64 - 1), C.byref(h)), self.ctx.handle)
+        self.handle = h
+        if planes or rounds:
+            check(lib().ising_pt_configure(h, int(planes), int(rounds)), self.ctx.handle)
+
+    def sweeps(self, t, want_energies=True):
+        out = np.empty(self.hi - self.lo, dtype=np.float64) if want_energies else None
+        check(lib().ising_pt_sweeps(self.handle, int(t), ptr(out)), self.ctx.handle)
+        return out
+
+    def swap_step(self, all_energies):
+        e = np.ascontiguousarray(all_energies, dtype=np.float64)
+        if e.shape != (self.R,):
+            raise ValueError("all_energies must have one entry per configuration")
+        check(lib().ising_pt_swap_step(self.handle, ptr(e)), self.ctx.handle)
+
+    def slots(self):
+        out = np.empty(self.R, dtype=np.uint32)
+        check(lib().ising_pt_get_slots(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def local_states(self):
+        out = np.empty((self.hi - self.lo, self.graph.nvars), dtype=np.bool_)
+        check(lib().ising_pt_get_local_states(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def total_swaps(self):
+        n = C.c_uint64(0)
+        check(lib().ising_pt_total_swaps(self.handle, C.byref(n)), self.ctx.handle)
+        return int(n.value)
+
+    def timesteps_sample(self, timesteps, replica_swap_freq=1, sampling_freq=1):
+        ns = int(timesteps) // int(sampling_freq) if sampling_freq else 0
+        states = PinnedPool.empty((self.R, ns, self.graph.nvars), np.bool_)
+        energies = np.empty(self.R, dtype=np.float64)
+        check(lib().ising_pt_timesteps_sample(self.handle, int(timesteps), int(replica_swap_freq),
+                                              int(sampling_freq), ptr(states), ptr(energies)),
+              self.ctx.handle)
+        return states, energies
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().ising_pt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decide_swaps(betas, all_energies, seed, swap_step, slot_of_config, config_of_slot):
+    """Host-only swap decisions of one tempering step (ising_pt_decide_swaps); the two
+    permutation arrays (uint32) are updated in place, returns the number of swaps."""
+    b = np.ascontiguousarray(betas, dtype=np.float64)
+    e = np.ascontiguousarray(all_energies, dtype=np.float64)
+    assert slot_of_config.dtype == np.uint32 and config_of_slot.dtype == np.uint32
+    n = C.c_uint64(0)
+    check(lib().ising_pt_decide_swaps(ptr(b), len(b), ptr(e), int(seed) & (2**64 - 1), int(swap_step),
+                                      ptr(slot_of_config), ptr(config_of_slot), C.byref(n)))
+    return int(n.value)
 
 
 def make_seeds(seed_gen, n):

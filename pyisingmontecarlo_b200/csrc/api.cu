@@ -90,6 +90,17 @@ struct ising_graph {
     uint32_t* d_nbr = nullptr;
     double* d_jv = nullptr;
     double* d_bias = nullptr;
+    // general-graph sweep data (built on demand): colour x degree groups in ELL form
+    bool gen_built = false;
+    std::vector<GenGroup> gen_groups;
+    std::vector<int> gen_group_color;
+    int gen_ncolors = 0;
+    uint32_t* d_gsites = nullptr;
+    uint32_t* d_gnbr = nullptr;
+    uint32_t* d_ganti = nullptr;
+    uint32_t* d_row32 = nullptr;   // CSR for the energy kernel
+    uint32_t* d_nbr32 = nullptr;
+    uint8_t* d_anti8 = nullptr;
 };
 
 struct ising_sim {
@@ -105,6 +116,13 @@ struct ising_sim {
     uint64_t sweep_counter = 0;
     int planes = 6, rounds = 10;
     ising_sim_stats stats{};
+    bool general = false;          // natural-order layout + colour/degree groups
+    // per-replica inverse temperatures (parallel tempering); general layout only
+    bool perbeta = false;
+    unsigned long long* d_t64 = nullptr;
+    uint32_t* d_slot = nullptr;
+    uint32_t* d_tplane = nullptr;
+    uint32_t* d_tlow = nullptr;
 };
 
 static int fail(ising_ctx* ctx, int code, const char* fmt, ...) {
@@ -250,6 +268,78 @@ static int ensure_csr_on_device(ising_ctx* ctx, ising_graph* g) {
     return ISING_OK;
 }
 
+// colour x degree groups of a graph whose couplings all have the same magnitude
+static int ensure_general_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->gen_built) return ISING_OK;
+    HostGraph& h = g->h;
+    if (!h.integer_classes)
+        return fail(ctx, ISING_E_UNSUPPORTED,
+                    "production sweeps on general graphs need all |J| equal and no bias in this "
+                    "revision (replay mode handles arbitrary couplings and biases)");
+    h.build_csr();
+    if (h.max_degree > GEN_MAX_DEG)
+        return fail(ctx, ISING_E_UNSUPPORTED, "maximum degree %d exceeds %d", h.max_degree, GEN_MAX_DEG);
+    if (2 * h.nedges > 0xFFFFFFFFull) return fail(ctx, ISING_E_UNSUPPORTED, "too many edges");
+    const uint64_t N = h.nvars;
+    const int ncol = h.ncolors;
+    // bucket sites by (colour, degree)
+    std::vector<std::vector<uint32_t>> bucket((size_t)ncol * (GEN_MAX_DEG + 1));
+    for (uint64_t n = 0; n < N; ++n) {
+        const uint32_t deg = (uint32_t)(h.row[n + 1] - h.row[n]);
+        bucket[(size_t)h.color_of(n) * (GEN_MAX_DEG + 1) + deg].push_back((uint32_t)n);
+    }
+    std::vector<uint32_t> sites, nbr, anti;
+    struct Off { size_t s, n; uint32_t count, deg; int color; };
+    std::vector<Off> offs;
+    for (int c = 0; c < ncol; ++c)
+        for (int d = 0; d <= GEN_MAX_DEG; ++d) {
+            const auto& b = bucket[(size_t)c * (GEN_MAX_DEG + 1) + d];
+            if (b.empty()) continue;
+            Off o{sites.size(), nbr.size(), (uint32_t)b.size(), (uint32_t)d, c};
+            sites.insert(sites.end(), b.begin(), b.end());
+            nbr.resize(nbr.size() + (size_t)d * b.size());
+            for (size_t i = 0; i < b.size(); ++i) {
+                const uint64_t lo = h.row[b[i]];
+                uint32_t bits = 0;
+                for (int k = 0; k < d; ++k) {
+                    nbr[o.n + (size_t)k * b.size() + i] = h.nbr[lo + k];
+                    if (h.jv[lo + k] > 0) bits |= 1u << k;
+                }
+                anti.push_back(bits);
+            }
+            offs.push_back(o);
+        }
+    std::vector<uint32_t> row32(N + 1);
+    for (uint64_t n = 0; n <= N; ++n) row32[n] = (uint32_t)h.row[n];
+    std::vector<uint8_t> anti8(h.jv.size());
+    for (size_t k = 0; k < h.jv.size(); ++k) anti8[k] = h.jv[k] > 0;
+    CUDA_TRY(ctx, dev_alloc(&g->d_gsites, sites.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_gnbr, nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_ganti, anti.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_row32, row32.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_nbr32, h.nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_anti8, anti8.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_gsites, sites.data(), sites.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_gnbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_ganti, anti.data(), anti.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_row32, row32.data(), row32.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_nbr32, h.nbr.data(), h.nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_anti8, anti8.data(), anti8.size(), cudaMemcpyHostToDevice));
+    for (const Off& o : offs) {
+        GenGroup gg;
+        gg.sites = g->d_gsites + o.s;
+        gg.nbr = g->d_gnbr + o.n;
+        gg.anti = g->d_ganti + o.s;
+        gg.count = o.count;
+        gg.deg = o.deg;
+        g->gen_groups.push_back(gg);
+        g->gen_group_color.push_back(o.color);
+    }
+    g->gen_ncolors = ncol;
+    g->gen_built = true;
+    return ISING_OK;
+}
+
 extern "C" int ising_graph_from_edges(ising_ctx* ctx, uint64_t nvars, uint64_t nedges,
                                       const uint64_t* a, const uint64_t* b, const double* j,
                                       const double* biases, ising_graph** out) {
@@ -290,6 +380,12 @@ extern "C" void ising_graph_destroy(ising_graph* g) {
     cudaFree(g->d_nbr);
     cudaFree(g->d_jv);
     cudaFree(g->d_bias);
+    cudaFree(g->d_gsites);
+    cudaFree(g->d_gnbr);
+    cudaFree(g->d_ganti);
+    cudaFree(g->d_row32);
+    cudaFree(g->d_nbr32);
+    cudaFree(g->d_anti8);
     delete g;
 }
 
@@ -343,26 +439,29 @@ static void count_launch(ising_sim* s, int n) {
     if (n > 0) s->stats.kernel_launches += (uint64_t)n;
 }
 
-extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E, uint64_t seed,
-                                uint64_t replica_offset, ising_sim** out) {
+extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_t E, uint64_t seed,
+                                   uint64_t replica_offset, uint32_t flags, ising_sim** out) {
     if (!ctx || !g || !out) return fail(ctx, ISING_E_INVALID, "ctx/graph/out is NULL");
     *out = nullptr;
     if (g->ctx != ctx) return fail(ctx, ISING_E_INVALID, "graph belongs to another context");
     if (E == 0) return fail(ctx, ISING_E_INVALID, "num_experiments must be > 0");
     if (replica_offset % 32) return fail(ctx, ISING_E_INVALID, "replica_offset must be a multiple of 32");
     const HostGraph& h = g->h;
-    if (h.kind == ISING_KIND_GENERAL)
-        return fail(ctx, ISING_E_UNSUPPORTED,
-                    "general-graph production sweeps are not built yet in this revision");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool general = h.kind == ISING_KIND_GENERAL || (flags & ISING_SIM_GENERAL_LAYOUT);
+    if (general) {
+        const int rc = ensure_general_on_device(ctx, const_cast<ising_graph*>(g));
+        if (rc) return rc;
+    }
     std::unique_ptr<ising_sim> s(new ising_sim);
     s->ctx = ctx;
     s->g = g;
     s->E = E;
     s->seed = seed;
     s->replica_offset = replica_offset;
+    s->general = general;
     Layout& L = s->lay;
-    L.kind = h.kind;
+    L.kind = general ? ISING_KIND_GENERAL : h.kind;
     L.Lx = (uint32_t)h.dims[0];
     L.Ly = (uint32_t)h.dims[1];
     L.Lz = (uint32_t)h.dims[2];
@@ -371,6 +470,8 @@ extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E
     L.W = (uint32_t)((E + 31) / 32);
     L.nvars = h.nvars;
     L.halfN = h.nvars / 2;
+    if (!general && (uint64_t)L.Lxh * L.W > 0xFFFFFFFFull)
+        return fail(ctx, ISING_E_UNSUPPORTED, "lattice row too long for 32-bit word offsets");
     const size_t words = (size_t)h.nvars * L.W;
     s->spins_bytes = words * sizeof(uint32_t);
     s->counts_bytes = (size_t)L.W * 32 * sizeof(unsigned long long);
@@ -387,12 +488,21 @@ extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E
     return ising_sim_randomize(*out);
 }
 
+extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E, uint64_t seed,
+                                uint64_t replica_offset, ising_sim** out) {
+    return ising_sim_create_ex(ctx, g, E, seed, replica_offset, 0u, out);
+}
+
 extern "C" void ising_sim_destroy(ising_sim* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     ctx_buf_put(s->ctx, s->d_spins, s->spins_bytes);
     ctx_buf_put(s->ctx, s->d_counts, s->counts_bytes);
+    cudaFree(s->d_t64);
+    cudaFree(s->d_slot);
+    cudaFree(s->d_tplane);
+    cudaFree(s->d_tlow);
     delete s;
 }
 
@@ -472,7 +582,66 @@ static void fill_thresholds(const HostGraph& h, double beta, int K, MscThreshold
     }
 }
 
+// T = floor(exp(-beta dE) 2^(K+32)) clipped to K+32 bits; NaN -> 0 (never accept uphill)
+static uint64_t threshold64(double beta, double de, int K) {
+    const double scaled = ldexp(exp(-beta * de), K + 32);
+    const uint64_t tmax = (1ull << (K + 32)) - 1;
+    if (!(scaled >= 0.0)) return 0;
+    if (scaled >= (double)tmax) return tmax;
+    return (uint64_t)floor(scaled);
+}
+
+// uphill classes of a degree-d site: n_sat = d/2+1 .. d, dE = 2|J|(2 n_sat - d)
+static void fill_gen_thresholds(double jabs, double beta, int K, uint32_t deg, GenThresholds* th) {
+    memset(th, 0, sizeof *th);
+    const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
+    for (uint32_t j = 0; j < ncls && j < (uint32_t)GEN_MAX_CLS; ++j) {
+        const int cls = 2 * (int)(cmin + j) - (int)deg;
+        const uint64_t T = threshold64(beta, 2.0 * jabs * (double)cls, K);
+        for (int pl = 0; pl < K; ++pl)
+            th->plane[j][pl] = ((T >> (K + 31 - pl)) & 1ull) ? 0xFFFFFFFFu : 0u;
+        th->low[j] = (uint32_t)(T & 0xFFFFFFFFull);
+    }
+}
+
+static int sim_one_sweep_general(ising_sim* s, double beta) {
+    ising_ctx* ctx = s->ctx;
+    const ising_graph* g = s->g;
+    const HostGraph& h = g->h;
+    GenSweepArgs a;
+    a.spins = s->d_spins;
+    a.W = s->lay.W;
+    a.sweep = (uint32_t)s->sweep_counter;
+    a.key0 = (uint32_t)s->seed;
+    a.key1 = (uint32_t)(s->seed >> 32);
+    a.gw0 = (uint32_t)(s->replica_offset / 32);
+    a.planes = s->planes;
+    a.rounds = s->rounds;
+    a.tables.plane = s->perbeta ? s->d_tplane : nullptr;
+    a.tables.low = s->perbeta ? s->d_tlow : nullptr;
+    memset(&a.th, 0, sizeof a.th);
+    int launches = 0;
+    for (int c = 0; c < g->gen_ncolors; ++c)
+        for (size_t k = 0; k < g->gen_groups.size(); ++k) {
+            if (g->gen_group_color[k] != c) continue;
+            const GenGroup& gg = g->gen_groups[k];
+            if (gg.deg == 0) continue;  // isolated site: dE = 0, the reference flips it every time
+            if (!s->perbeta) fill_gen_thresholds(h.jabs, beta, s->planes, gg.deg, &a.th);
+            const int n = launch_sweep_general(a, gg, ctx->stream);
+            if (n < 0) return fail(ctx, ISING_E_CUDA, "general sweep launch failed: %s",
+                                   cudaGetErrorString(cudaGetLastError()));
+            launches += n;
+        }
+    count_launch(s, launches);
+    s->stats.sweep_kernel_launches += (uint64_t)launches;
+    s->sweep_counter++;
+    s->stats.sweeps++;
+    s->stats.flip_attempts += s->E * h.nvars;
+    return ISING_OK;
+}
+
 static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr) {
+    if (s->general) return sim_one_sweep_general(s, beta);
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
     SweepArgs a;
@@ -505,6 +674,13 @@ static int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
     const HostGraph& h = s->g->h;
     CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)s->lay.W * 32 * sizeof(unsigned long long),
                                   ctx->stream));
+    if (s->general) {
+        const int n = launch_nsat_general(s->d_spins, s->lay.nvars, s->lay.W, s->g->d_row32,
+                                          s->g->d_nbr32, s->g->d_anti8, d_counts, ctx->stream);
+        if (n < 0) return fail(ctx, ISING_E_CUDA, "energy launch failed");
+        count_launch(s, n);
+        return ISING_OK;
+    }
     const int n = launch_nsat_stencil(s->d_spins, s->g->d_jmask, s->lay,
                                       h.uniform_antiferro ? 0xFFFFFFFFu : 0u, d_counts,
                                       ctx->stream);
@@ -515,15 +691,20 @@ static int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
 
 extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps,
                                 double* energies_per_sweep) {
-    if (!s || (nsweeps && !betas)) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
+    if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    if (s->perbeta ? betas != nullptr : (nsweeps && !betas))
+        return fail(s->ctx, ISING_E_INVALID,
+                    s->perbeta ? "sim runs at per-experiment betas (ising_sim_set_betas): pass betas = NULL"
+                               : "betas is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const HostGraph& h = s->g->h;
     const uint64_t E = s->E;
+    const int mult = s->general ? 1 : 2;
     if (!energies_per_sweep) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         for (uint64_t t = 0; t < nsweeps; ++t) {
-            const int rc = sim_one_sweep(s, betas[t]);
+            const int rc = sim_one_sweep(s, betas ? betas[t] : 0.0);
             if (rc) return rc;
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -554,11 +735,19 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
         cudaMemsetAsync(d_hist, 0, cw * nt * sizeof(unsigned long long), ctx->stream);
         // the second colour phase of every sweep adds its post-flip satisfied-bond counts
         // into that sweep's slot of the history (fused, no separate energy pass)
-        for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t)
-            rc = sim_one_sweep(s, betas[t0 + t], d_hist + t * cw);
+        for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t) {
+            rc = sim_one_sweep(s, betas ? betas[t0 + t] : 0.0, d_hist + t * cw);
+            if (rc == ISING_OK && s->general) {  // no fused accumulation on general graphs
+                const int n = launch_nsat_general(s->d_spins, s->lay.nvars, s->lay.W, s->g->d_row32,
+                                                  s->g->d_nbr32, s->g->d_anti8, d_hist + t * cw,
+                                                  ctx->stream);
+                if (n < 0) rc = fail(ctx, ISING_E_CUDA, "energy launch failed");
+                else count_launch(s, n);
+            }
+        }
         if (rc == ISING_OK)
-            count_launch(s, launch_energy_from_hist(d_hist, E, cw, nt, h.jabs, h.nedges, d_out,
-                                                    ctx->stream));
+            count_launch(s, launch_energy_from_hist(d_hist, E, cw, nt, h.jabs, h.nedges, mult,
+                                                    d_out, ctx->stream));
         cudaEventRecord(ctx->ev1, ctx->stream);
         if (rc != ISING_OK) break;
         host.resize((size_t)E * nt);
@@ -585,8 +774,8 @@ extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
     void* dv = nullptr;
     CUDA_TRY(ctx, ctx_scratch(ctx, 2, s->E * sizeof(double), &dv));
     double* d_out = (double*)dv;
-    count_launch(s, launch_energy_from_nsat(s->d_counts, s->E, h.jabs, h.nedges, d_out, 1, 0,
-                                            ctx->stream));
+    count_launch(s, launch_energy_from_nsat(s->d_counts, s->E, h.jabs, h.nedges,
+                                            s->general ? 1 : 2, d_out, 1, 0, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(energies, d_out, s->E * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -652,6 +841,235 @@ extern "C" int ising_sim_get_stats(ising_sim* s, ising_sim_stats* out) {
 extern "C" int ising_sim_reset_stats(ising_sim* s) {
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     s->stats = ising_sim_stats{};
+    return ISING_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-experiment inverse temperatures and classical parallel tempering
+// ------------------------------------------------------------------------------------------
+extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
+    if (!s || !betas) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
+    ising_ctx* ctx = s->ctx;
+    if (!s->general)
+        return fail(ctx, ISING_E_UNSUPPORTED,
+                    "per-experiment betas need the general layout (ISING_SIM_GENERAL_LAYOUT)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const HostGraph& h = s->g->h;
+    const uint32_t W = s->lay.W, E32 = 32 * W;
+    const size_t per = (size_t)(GEN_MAX_DEG + 1) * GEN_MAX_CLS;
+    std::vector<unsigned long long> t64((size_t)E32 * per, 0ull);
+    std::vector<uint32_t> slot(E32);
+    for (uint32_t e = 0; e < E32; ++e) {
+        slot[e] = e;
+        const double beta = betas[e < s->E ? e : 0];  // padding bits: any valid beta
+        for (uint32_t deg = 1; deg <= (uint32_t)GEN_MAX_DEG; ++deg) {
+            const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
+            for (uint32_t j = 0; j < ncls; ++j) {
+                const int cls = 2 * (int)(cmin + j) - (int)deg;
+                t64[(size_t)e * per + (size_t)deg * GEN_MAX_CLS + j] =
+                    threshold64(beta, 2.0 * h.jabs * (double)cls, s->planes);
+            }
+        }
+    }
+    if (!s->d_t64) {
+        CUDA_TRY(ctx, dev_alloc(&s->d_t64, t64.size()));
+        CUDA_TRY(ctx, dev_alloc(&s->d_slot, (size_t)E32));
+        CUDA_TRY(ctx, dev_alloc(&s->d_tplane, (size_t)(GEN_MAX_DEG + 1) * W * GEN_MAX_CLS * 8));
+        CUDA_TRY(ctx, dev_alloc(&s->d_tlow, (size_t)(GEN_MAX_DEG + 1) * E32 * GEN_MAX_CLS));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(s->d_t64, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(s->d_slot, slot.data(), slot.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    count_launch(s, launch_build_tables(s->d_t64, s->d_slot, W, s->planes, s->d_tplane, s->d_tlow,
+                                        ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // t64/slot are stack-lifetime host buffers
+    s->perbeta = true;
+    return ISING_OK;
+}
+
+struct ising_pt {
+    ising_ctx* ctx = nullptr;
+    const ising_graph* g = nullptr;
+    ising_sim* sim = nullptr;
+    uint64_t R = 0, lo = 0, hi = 0;   // this rank owns configurations [lo, hi)
+    uint64_t word_lo = 0;             // first replica word held locally
+    std::vector<double> betas;        // by slot
+    std::vector<uint32_t> slot_of_cfg, cfg_of_slot;
+    uint64_t seed = 0, swap_step = 0, total_swaps = 0;
+};
+
+// betas of the locally held replica bits from the slot permutation
+static int pt_push_betas(ising_pt* pt) {
+    const uint64_t E = pt->sim->E;
+    std::vector<double> b(E);
+    for (uint64_t e = 0; e < E; ++e) {
+        const uint64_t cfg = pt->word_lo * 32 + e;
+        b[e] = pt->betas[cfg < pt->R ? pt->slot_of_cfg[cfg] : 0];
+    }
+    return ising_sim_set_betas(pt->sim, b.data());
+}
+
+extern "C" int ising_pt_create(ising_ctx* ctx, const ising_graph* g, const double* betas,
+                               uint64_t nbetas, uint64_t cfg_lo, uint64_t cfg_hi, uint64_t seed,
+                               ising_pt** out) {
+    if (!ctx || !g || !betas || !out) return fail(ctx, ISING_E_INVALID, "ctx/graph/betas/out is NULL");
+    *out = nullptr;
+    if (nbetas == 0 || cfg_lo >= cfg_hi || cfg_hi > nbetas)
+        return fail(ctx, ISING_E_INVALID, "need 0 <= cfg_lo < cfg_hi <= nbetas");
+    std::unique_ptr<ising_pt> pt(new ising_pt);
+    pt->ctx = ctx;
+    pt->g = g;
+    pt->R = nbetas;
+    pt->lo = cfg_lo;
+    pt->hi = cfg_hi;
+    pt->seed = seed;
+    pt->betas.assign(betas, betas + nbetas);
+    pt->slot_of_cfg.resize(nbetas);
+    pt->cfg_of_slot.resize(nbetas);
+    for (uint64_t r = 0; r < nbetas; ++r) pt->slot_of_cfg[r] = pt->cfg_of_slot[r] = (uint32_t)r;
+    // whole replica words: configuration c always lives at bit c%32 of global word c/32, so a
+    // sharded run draws exactly the random numbers of the unsharded one
+    pt->word_lo = cfg_lo / 32;
+    const uint64_t word_hi = (cfg_hi + 31) / 32;
+    const uint64_t E = std::min<uint64_t>((word_hi - pt->word_lo) * 32, nbetas - pt->word_lo * 32);
+    int rc = ising_sim_create_ex(ctx, g, E, seed, pt->word_lo * 32, ISING_SIM_GENERAL_LAYOUT, &pt->sim);
+    if (rc) return rc;
+    rc = pt_push_betas(pt.get());
+    if (rc) { ising_sim_destroy(pt->sim); return rc; }
+    *out = pt.release();
+    return ISING_OK;
+}
+
+extern "C" void ising_pt_destroy(ising_pt* pt) {
+    if (!pt) return;
+    ising_sim_destroy(pt->sim);
+    delete pt;
+}
+
+extern "C" int ising_pt_configure(ising_pt* pt, int planes, int rounds) {
+    if (!pt) return fail(nullptr, ISING_E_INVALID, "pt is NULL");
+    const int rc = ising_sim_configure(pt->sim, planes, rounds);
+    return rc ? rc : pt_push_betas(pt);
+}
+
+extern "C" int ising_pt_sweeps(ising_pt* pt, uint64_t t, double* local_energies) {
+    if (!pt) return fail(nullptr, ISING_E_INVALID, "pt is NULL");
+    int rc = ising_sim_sweeps(pt->sim, nullptr, t, nullptr);
+    if (rc || !local_energies) return rc;
+    std::vector<double> en(pt->sim->E);
+    rc = ising_sim_get_energies(pt->sim, en.data());
+    if (rc) return rc;
+    for (uint64_t c = pt->lo; c < pt->hi; ++c) local_energies[c - pt->lo] = en[c - pt->word_lo * 32];
+    return ISING_OK;
+}
+
+// One tempering step (the shape of TemperingContainer::parallel_tempering_step as driven from
+// tempering.rs:191-194): even slot pairs (0,1),(2,3).. then odd pairs (1,2),(3,4)..; the pair
+// (a, a+1) exchanges configurations with probability min(1, exp((b_a - b_{a+1})(E_a - E_{a+1}))).
+// The uniform is Philox(seed; slot a, swap step), so every rank takes the same decisions from
+// the all-gathered energies.  all_energies is indexed by CONFIGURATION.
+extern "C" int ising_pt_decide_swaps(const double* betas, uint64_t R, const double* all_energies,
+                                     uint64_t seed, uint64_t swap_step, uint32_t* slot_of_cfg,
+                                     uint32_t* cfg_of_slot, uint64_t* nswaps) {
+    if (!betas || !all_energies || !slot_of_cfg || !cfg_of_slot)
+        return fail(nullptr, ISING_E_INVALID, "ising_pt_decide_swaps: NULL argument");
+    uint64_t swaps = 0;
+    for (int parity = 0; parity < 2; ++parity)
+        for (uint64_t a = parity; a + 1 < R; a += 2) {
+            const uint32_t ca = cfg_of_slot[a], cb = cfg_of_slot[a + 1];
+            const double d = (betas[a] - betas[a + 1]) * (all_energies[ca] - all_energies[cb]);
+            bool acc = true;
+            if (d < 0.0) {
+                const u32x4 r = philox4x32<10>((uint32_t)a, (uint32_t)parity, (uint32_t)swap_step,
+                                               TAG_SWAP << 24, (uint32_t)seed, (uint32_t)(seed >> 32));
+                const double uu = ((double)r.x + 0.5) * (1.0 / 4294967296.0);
+                acc = uu < exp(d);
+            }
+            if (acc) {
+                cfg_of_slot[a] = cb;
+                cfg_of_slot[a + 1] = ca;
+                slot_of_cfg[cb] = (uint32_t)a;
+                slot_of_cfg[ca] = (uint32_t)(a + 1);
+                ++swaps;
+            }
+        }
+    if (nswaps) *nswaps = swaps;
+    return ISING_OK;
+}
+
+extern "C" int ising_pt_swap_step(ising_pt* pt, const double* all_energies) {
+    if (!pt || !all_energies) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/energies is NULL");
+    uint64_t swaps = 0;
+    const int rc = ising_pt_decide_swaps(pt->betas.data(), pt->R, all_energies, pt->seed, pt->swap_step,
+                                         pt->slot_of_cfg.data(), pt->cfg_of_slot.data(), &swaps);
+    if (rc) return rc;
+    pt->total_swaps += swaps;
+    pt->swap_step++;
+    return pt_push_betas(pt);
+}
+
+extern "C" int ising_pt_get_slots(const ising_pt* pt, uint32_t* slot_of_config) {
+    if (!pt || !slot_of_config) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
+    for (uint64_t c = 0; c < pt->R; ++c) slot_of_config[c] = pt->slot_of_cfg[c];
+    return ISING_OK;
+}
+
+extern "C" int ising_pt_get_local_states(ising_pt* pt, uint8_t* states) {
+    if (!pt || !states) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/states is NULL");
+    const uint64_t N = pt->g->h.nvars;
+    std::vector<uint8_t> all((size_t)pt->sim->E * N);
+    const int rc = ising_sim_get_states(pt->sim, all.data());
+    if (rc) return rc;
+    for (uint64_t c = pt->lo; c < pt->hi; ++c)
+        memcpy(states + (c - pt->lo) * N, all.data() + (c - pt->word_lo * 32) * N, N);
+    return ISING_OK;
+}
+
+extern "C" int ising_pt_total_swaps(const ising_pt* pt, uint64_t* out) {
+    if (!pt || !out) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
+    *out = pt->total_swaps;
+    return ISING_OK;
+}
+
+// LatticeTempering::qmc_timesteps_sample, tempering.rs:156-222, single rank (cfg range = all):
+// run min(to_sample, to_swap, remaining) -> swap step -> sample; states[R, n_s, nvars] holds
+// "the configuration currently at beta_r", energies[R] = sum(E_r after chunk * chunk) / timesteps.
+extern "C" int ising_pt_timesteps_sample(ising_pt* pt, uint64_t timesteps, uint64_t replica_swap_freq,
+                                         uint64_t sampling_freq, uint8_t* states, double* energies) {
+    if (!pt || !energies) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/energies is NULL");
+    if (pt->lo != 0 || pt->hi != pt->R)
+        return fail(pt->ctx, ISING_E_INVALID, "ising_pt_timesteps_sample needs all configurations on this rank");
+    if (replica_swap_freq == 0 || sampling_freq == 0)
+        return fail(pt->ctx, ISING_E_INVALID,
+                    "replica_swap_freq and sampling_freq must be > 0 (the reference loops forever on 0)");
+    const uint64_t R = pt->R, N = pt->g->h.nvars, ns = timesteps / sampling_freq;
+    if (ns && !states) return fail(pt->ctx, ISING_E_INVALID, "states is NULL");
+    std::vector<double> acc(R, 0.0), en(R);
+    std::vector<uint8_t> local;
+    uint64_t remaining = timesteps, to_swap = replica_swap_freq, to_sample = sampling_freq, k = 0;
+    while (remaining > 0) {
+        const uint64_t t = std::min(std::min(to_sample, to_swap), remaining);
+        int rc = ising_pt_sweeps(pt, t, en.data());
+        if (rc) return rc;
+        for (uint64_t slot = 0; slot < R; ++slot) acc[slot] += en[pt->cfg_of_slot[slot]] * (double)t;
+        to_sample -= t; to_swap -= t; remaining -= t;
+        if (to_swap == 0) {
+            rc = ising_pt_swap_step(pt, en.data());
+            if (rc) return rc;
+            to_swap = replica_swap_freq;
+        }
+        if (to_sample == 0) {
+            if (k < ns) {
+                local.resize((size_t)R * N);
+                rc = ising_pt_get_local_states(pt, local.data());
+                if (rc) return rc;
+                for (uint64_t slot = 0; slot < R; ++slot)
+                    memcpy(states + (slot * ns + k) * N, local.data() + (size_t)pt->cfg_of_slot[slot] * N, N);
+            }
+            ++k;
+            to_sample = sampling_freq;
+        }
+    }
+    for (uint64_t slot = 0; slot < R; ++slot) energies[slot] = acc[slot] / (double)timesteps;
     return ISING_OK;
 }
 
@@ -736,7 +1154,8 @@ extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph*
             rc = sim_count_nsat(sim, sim->d_counts);
             if (rc) break;
             count_launch(sim, launch_energy_from_nsat(sim->d_counts, E, g->h.jabs, g->h.nedges,
-                                                      d_en, nk, k, ctx->stream));
+                                                      sim->general ? 1 : 2, d_en, nk, k,
+                                                      ctx->stream));
         }
         if (rc) break;
         en_host.resize((size_t)E * nk);

@@ -647,38 +647,241 @@ int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long
 }
 
 __global__ void k_energy_from_nsat(const unsigned long long* __restrict__ nsat, uint64_t E,
-                                   double scale, uint64_t nbonds, double* __restrict__ out,
-                                   uint64_t estride, uint64_t eoff) {
+                                   double scale, uint64_t nbonds, int mult,
+                                   double* __restrict__ out, uint64_t estride, uint64_t eoff) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const long long v = (long long)nbonds - 2ll * (long long)nsat[e];
+    const long long v = (long long)nbonds - (long long)mult * (long long)nsat[e];
     out[e * estride + eoff] = scale * (double)v;
 }
 
 // energies[e * nt + t] = scale * (nbonds - 2 * hist[t * cw + e]) for a chunk of nt sweeps
 __global__ void k_energy_from_hist(const unsigned long long* __restrict__ hist, uint64_t E,
                                    uint64_t cw, uint64_t nt, double scale, uint64_t nbonds,
-                                   double* __restrict__ out) {
+                                   int mult, double* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E * nt) return;
     const uint64_t e = i / nt, t = i - e * nt;
-    const long long v = (long long)nbonds - 2ll * (long long)hist[t * cw + e];
+    const long long v = (long long)nbonds - (long long)mult * (long long)hist[t * cw + e];
     out[i] = scale * (double)v;
 }
 
 int launch_energy_from_hist(const unsigned long long* hist, uint64_t E, uint64_t cw, uint64_t nt,
-                            double scale, uint64_t nbonds, double* out_dev, cudaStream_t st) {
+                            double scale, uint64_t nbonds, int mult, double* out_dev,
+                            cudaStream_t st) {
     const uint64_t n = E * nt;
     const unsigned g = (unsigned)((n + 255) / 256);
-    k_energy_from_hist<<<g ? g : 1, 256, 0, st>>>(hist, E, cw, nt, scale, nbonds, out_dev);
+    k_energy_from_hist<<<g ? g : 1, 256, 0, st>>>(hist, E, cw, nt, scale, nbonds, mult, out_dev);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,
-                            uint64_t nbonds, double* out_dev, uint64_t estride, uint64_t eoff,
-                            cudaStream_t st) {
+                            uint64_t nbonds, int mult, double* out_dev, uint64_t estride,
+                            uint64_t eoff, cudaStream_t st) {
     const unsigned g = (unsigned)((E + 255) / 256);
-    k_energy_from_nsat<<<g ? g : 1, 256, 0, st>>>(nsat, E, scale, nbonds, out_dev, estride, eoff);
+    k_energy_from_nsat<<<g ? g : 1, 256, 0, st>>>(nsat, E, scale, nbonds, mult, out_dev, estride, eoff);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: colour-class sweep on an arbitrary graph (CSR/ELL), all |J| equal, no bias.
+// Same decision rule and Philox stream as the stencil kernel (DESIGN.md "Production sweep"),
+// generic in the degree: n_sat is a 4-plane vertical counter, the uphill classes are
+// n_sat = deg/2+1 .. deg.  PERBETA: thresholds differ per replica (parallel tempering).
+// ------------------------------------------------------------------------------------------
+template <int K, int ROUNDS, bool PERBETA>
+__global__ void __launch_bounds__(256)
+k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t sweep, uint32_t k0,
+                uint32_t k1, uint32_t gw0, GenThresholds th, GenTables tab) {
+    constexpr int NCALL = K / 4 + 1;
+    const uint32_t deg = g.deg;
+    const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
+    const uint64_t total = (uint64_t)g.count * W;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(item / W), w = (uint32_t)(item - (uint64_t)i * W);
+        const uint32_t n = g.sites[i];
+        const uint32_t ab = g.anti[i];
+        const uint32_t s = spins[(size_t)n * W + w];
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        for (uint32_t k = 0; k < deg; ++k) {
+            const uint32_t nb = g.nbr[(size_t)k * g.count + i];
+            const uint32_t x = spins[(size_t)nb * W + w];
+            const uint32_t m = 0u - ((ab >> k) & 1u);
+            uint32_t c = ~(s ^ x ^ m);  // satisfied bond
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const uint32_t t = cnt[l] & c;
+                cnt[l] ^= c;
+                c = t;
+            }
+        }
+        // one-hot masks of the uphill classes
+        uint32_t oh[GEN_MAX_CLS];
+        uint32_t up = 0;
+#pragma unroll
+        for (int j = 0; j < GEN_MAX_CLS; ++j) {
+            oh[j] = 0;
+            if ((uint32_t)j < ncls) {
+                const uint32_t v = cmin + j;
+                uint32_t o = 0xFFFFFFFFu;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) o &= ((v >> l) & 1u) ? cnt[l] : ~cnt[l];
+                oh[j] = o;
+                up |= o;
+            }
+        }
+        uint32_t r[NCALL * 4];
+#pragma unroll
+        for (int q = 0; q < NCALL; ++q) {
+            const u32x4 o = philox4x32<ROUNDS>(n, gw0 + w, sweep, (uint32_t)q | (TAG_ACCEPT << 24), k0, k1);
+            r[4 * q + 0] = o.x; r[4 * q + 1] = o.y; r[4 * q + 2] = o.z; r[4 * q + 3] = o.w;
+        }
+        const uint32_t* tp = PERBETA ? tab.plane + ((size_t)deg * W + w) * GEN_MAX_CLS * 8 : nullptr;
+        uint32_t eq = up, borrow = 0;
+#pragma unroll
+        for (int p = K - 1; p >= 0; --p) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int j = 0; j < GEN_MAX_CLS; ++j)
+                if ((uint32_t)j < ncls) t |= oh[j] & (PERBETA ? __ldg(tp + j * 8 + p) : th.plane[j][p]);
+            borrow = maj3(~r[p], t, borrow);
+            eq &= ~(r[p] ^ t);
+        }
+        uint32_t flip = ~up | (borrow & ~eq);
+        if (eq) {
+            int jj = K;
+            u32x4 cur = {r[4 * (NCALL - 1)], r[4 * (NCALL - 1) + 1], r[4 * (NCALL - 1) + 2],
+                         r[4 * (NCALL - 1) + 3]};
+            do {
+                const int b = __ffs((int)eq) - 1;
+                if ((jj & 3) == 0 && jj >= 4 * NCALL)
+                    cur = philox4x32<ROUNDS>(n, gw0 + w, sweep, (uint32_t)(jj >> 2) | (TAG_ACCEPT << 24), k0, k1);
+                const int m = jj & 3;
+                const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
+                uint32_t cls = 0;
+#pragma unroll
+                for (int j = 1; j < GEN_MAX_CLS; ++j)
+                    if ((oh[j] >> b) & 1u) cls = j;
+                const uint32_t lo = PERBETA
+                    ? __ldg(tab.low + ((size_t)deg * 32 * W + (size_t)w * 32 + b) * GEN_MAX_CLS + cls)
+                    : th.low[cls];
+                if (v < lo) flip |= 1u << b;
+                eq &= eq - 1;
+                ++jj;
+            } while (eq);
+        }
+        spins[(size_t)n * W + w] = s ^ flip;
+    }
+}
+
+int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st) {
+    if (g.count == 0) return 0;
+    if (g.deg > (uint32_t)GEN_MAX_DEG) return -1;
+    const uint64_t total = (uint64_t)g.count * a.W;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    const dim3 grid((unsigned)blocks), block(256);
+    const bool pb = a.tables.plane != nullptr;
+#define GEN_LAUNCH(KK, RR)                                                                        \
+    do {                                                                                          \
+        if (pb) k_sweep_general<KK, RR, true><<<grid, block, 0, st>>>(                            \
+                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+        else k_sweep_general<KK, RR, false><<<grid, block, 0, st>>>(                              \
+                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+    } while (0)
+#define GEN_ROUNDS(KK)                                                                            \
+    do { if (a.rounds == 7) GEN_LAUNCH(KK, 7); else GEN_LAUNCH(KK, 10); } while (0)
+    switch (a.planes) {
+        case 4: GEN_ROUNDS(4); break;
+        case 5: GEN_ROUNDS(5); break;
+        case 6: GEN_ROUNDS(6); break;
+        case 7: GEN_ROUNDS(7); break;
+        case 8: GEN_ROUNDS(8); break;
+        default: return -1;
+    }
+#undef GEN_ROUNDS
+#undef GEN_LAUNCH
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// per-replica threshold tables from host-computed 64-bit thresholds (integer work only, so the
+// bits are exactly the host's): T64[(slot * (GEN_MAX_DEG+1) + deg) * GEN_MAX_CLS + cls]
+__global__ void k_build_tables(const unsigned long long* __restrict__ t64,
+                               const uint32_t* __restrict__ slot_of_replica, uint32_t W, int K,
+                               uint32_t* __restrict__ plane_out, uint32_t* __restrict__ low_out) {
+    const uint32_t total = (GEN_MAX_DEG + 1) * W * GEN_MAX_CLS;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += gridDim.x * blockDim.x) {
+        const uint32_t cls = idx % GEN_MAX_CLS;
+        const uint32_t w = (idx / GEN_MAX_CLS) % W;
+        const uint32_t deg = idx / (GEN_MAX_CLS * W);
+        uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t b = 0; b < 32; ++b) {
+            const uint32_t e = w * 32 + b;
+            const uint32_t slot = slot_of_replica[e];
+            const unsigned long long T =
+                t64[((size_t)slot * (GEN_MAX_DEG + 1) + deg) * GEN_MAX_CLS + cls];
+            for (int p = 0; p < K; ++p)
+                if ((T >> (K + 31 - p)) & 1ull) pl[p] |= 1u << b;
+            low_out[((size_t)deg * 32 * W + e) * GEN_MAX_CLS + cls] = (uint32_t)(T & 0xFFFFFFFFull);
+        }
+        for (int p = 0; p < 8; ++p)
+            plane_out[(((size_t)deg * W + w) * GEN_MAX_CLS + cls) * 8 + p] = pl[p];
+    }
+}
+
+int launch_build_tables(const unsigned long long* t64, const uint32_t* slot_of_replica, uint32_t W,
+                        int K, uint32_t* plane_out, uint32_t* low_out, cudaStream_t st) {
+    const uint32_t total = (GEN_MAX_DEG + 1) * W * GEN_MAX_CLS;
+    k_build_tables<<<(total + 127) / 128, 128, 0, st>>>(t64, slot_of_replica, W, K, plane_out, low_out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// satisfied bonds per experiment on a general graph (each bond seen from both ends)
+__global__ void __launch_bounds__(256)
+k_nsat_general(const uint32_t* __restrict__ spins, uint64_t nvars, uint32_t W,
+               const uint32_t* __restrict__ row, const uint32_t* __restrict__ nbr,
+               const uint8_t* __restrict__ anti, unsigned long long* __restrict__ nsat2) {
+    __shared__ int sm[32 * 256];
+    const int nthreads = blockDim.x * blockDim.y;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (uint32_t w0 = 0; w0 < W; w0 += blockDim.x) {
+        for (int b = 0; b < 32; ++b) sm[b * nthreads + tid] = 0;
+        const uint32_t w = w0 + threadIdx.x;
+        VCount<VC_PLANES> vc;
+        vc.clear();
+        int pending = 0;
+        if (w < W) {
+            for (uint64_t n = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y; n < nvars;
+                 n += (uint64_t)gridDim.x * blockDim.y) {
+                const uint32_t s = spins[(size_t)n * W + w];
+                const uint32_t lo = row[n], hi = row[n + 1];
+                for (uint32_t k = lo; k < hi; ++k) {
+                    const uint32_t x = spins[(size_t)nbr[k] * W + w];
+                    const uint32_t m = anti[k] ? 0xFFFFFFFFu : 0u;
+                    vc.add1(~(s ^ x ^ m));
+                    if (++pending == VC_FLUSH_ADD1) {
+                        vc.flush(sm, tid, nthreads);
+                        pending = 0;
+                    }
+                }
+            }
+            vc.flush(sm, tid, nthreads);
+        }
+        block_reduce_counts(sm, nsat2, w0, W);
+    }
+}
+
+int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const uint32_t* row,
+                        const uint32_t* nbr, const uint8_t* anti, unsigned long long* nsat2,
+                        cudaStream_t st) {
+    const uint32_t wx = W >= 32 ? 32 : pow2_ceil(W);
+    dim3 block(wx, 256 / wx, 1);
+    uint64_t g = (nvars + block.y - 1) / block.y;
+    if (g > 148u * 8u) g = 148u * 8u;
+    if (g == 0) g = 1;
+    k_nsat_general<<<dim3((unsigned)g), block, 0, st>>>(spins, nvars, W, row, nbr, anti, nsat2);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

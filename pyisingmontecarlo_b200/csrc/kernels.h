@@ -62,13 +62,58 @@ int launch_unpack_states(const uint32_t* spins, const Layout& lay, uint8_t* out_
 // packed words in natural order [nvars][W]
 int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* out_dev,
                           cudaStream_t st);
-// energies[e * estride + eoff] = scale * (double)(nbonds - 2 * nsat[e])
+// energies[e * estride + eoff] = scale * (double)(nbonds - mult * nsat[e]); mult = 2 when
+// nsat counts every satisfied bond once (stencil), 1 when it counts it from both ends
 int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,
-                            uint64_t nbonds, double* out_dev, uint64_t estride, uint64_t eoff,
-                            cudaStream_t st);
+                            uint64_t nbonds, int mult, double* out_dev, uint64_t estride,
+                            uint64_t eoff, cudaStream_t st);
 
 int launch_energy_from_hist(const unsigned long long* hist, uint64_t E, uint64_t cw, uint64_t nt,
-                            double scale, uint64_t nbonds, double* out_dev, cudaStream_t st);
+                            double scale, uint64_t nbonds, int mult, double* out_dev,
+                            cudaStream_t st);
+
+// ---- general graphs (arbitrary edge list, greedy colouring), all |J| equal, no bias -----------
+constexpr int GEN_MAX_DEG = 15;   // satisfied-bond count fits 4 bit-planes
+constexpr int GEN_MAX_CLS = 8;    // uphill classes of one degree: n_sat = deg/2+1 .. deg
+
+struct GenGroup {             // the sites of one colour that have the same degree
+    const uint32_t* sites;    // [count] natural site index
+    const uint32_t* nbr;      // [deg][count] neighbour site index
+    const uint32_t* anti;     // [count] bit k set iff the bond to neighbour k has J > 0
+    uint32_t count, deg;
+};
+
+// thresholds of one degree, same for every replica (uniform beta)
+struct GenThresholds {
+    uint32_t plane[GEN_MAX_CLS][8];
+    uint32_t low[GEN_MAX_CLS];
+};
+
+// thresholds that differ per replica (parallel tempering): bit-sliced in device memory
+//   plane[((deg * W + w) * GEN_MAX_CLS + cls) * 8 + p]: bit b = threshold bit p of replica 32w+b
+//   low[((deg * E32 + e) * GEN_MAX_CLS + cls)],  E32 = 32 * W
+struct GenTables {
+    const uint32_t* plane;
+    const uint32_t* low;
+};
+
+struct GenSweepArgs {
+    uint32_t* spins;          // [nvars][W]
+    uint32_t W;
+    uint32_t sweep, key0, key1, gw0;
+    int planes, rounds;
+    GenThresholds th;         // used when tables.plane == nullptr
+    GenTables tables;
+};
+int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st);
+// T64[slot][deg 0..GEN_MAX_DEG][cls] (host-computed) + slot_of_replica[E32] -> GenTables
+int launch_build_tables(const unsigned long long* t64, const uint32_t* slot_of_replica,
+                        uint32_t W, int K, uint32_t* plane_out, uint32_t* low_out,
+                        cudaStream_t st);
+// nsat2[e] += sum over sites of the satisfied bonds at that site (every bond counted twice)
+int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const uint32_t* row,
+                        const uint32_t* nbr, const uint8_t* anti, unsigned long long* nsat2,
+                        cudaStream_t st);
 
 struct ReplayArgs {
     uint64_t E, N, A;

@@ -73,7 +73,11 @@ def lib():
         h.msc_philox4x32.argtypes = [C.c_int, _P, _P, _P]
         h.msc_mirror_run.restype = C.c_int
         h.msc_mirror_run.argtypes = [_U64, _U64, _P, _P, _P, _P, C.c_uint32, _U64, _U64, _U64,
-                                     C.c_int, C.c_int, C.c_int, _P, _P, _U64, _U64, _P, _P, _P]
+                                     C.c_int, C.c_int, C.c_int, _P, _P, _U64, _U64, _P, _P, _P,
+                                     C.c_int]
+        h.msc_mirror_pt.restype = C.c_int
+        h.msc_mirror_pt.argtypes = [_U64, _U64, _P, _P, _P, _P, C.c_uint32, _U64, _P, _U64, C.c_int,
+                                    C.c_int, _U64, _U64, _U64, _P, _P, _P, _P]
         _lib = h
     return _lib
 
@@ -238,24 +242,56 @@ def philox4x32(ctr, key, rounds=10):
 
 
 def msc_mirror(a, b, j, nvars, colors, E, seed, betas, *, replica_offset=0, planes=6, rounds=10,
-               init_state=None, states=None, sweep0=0, per_sweep=False):
-    """Scalar restatement of the production sweep (oracle/msc_mirror.c)."""
+               init_state=None, states=None, sweep0=0, per_sweep=False, per_replica_beta=None,
+               nsweeps=None):
+    """Scalar restatement of the production sweep (oracle/msc_mirror.c).
+
+    betas: one per sweep; or pass per_replica_beta=[E values] and nsweeps for a run where
+    experiment e stays at its own beta (parallel-tempering style)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    j = np.ascontiguousarray(j, dtype=np.float64)
+    colors = np.ascontiguousarray(colors, dtype=np.uint32)
+    if per_replica_beta is not None:
+        betas = np.ascontiguousarray(per_replica_beta, dtype=np.float64)
+        assert len(betas) == E and nsweeps is not None
+        nsw = int(nsweeps)
+    else:
+        betas = np.ascontiguousarray(betas, dtype=np.float64)
+        nsw = len(betas)
+    randomize = int(states is None and init_state is None)
+    st = np.zeros((E, nvars), dtype=np.uint8) if states is None else np.ascontiguousarray(
+        states, dtype=np.uint8).copy()
+    init = None if init_state is None else np.ascontiguousarray(init_state, dtype=np.uint8)
+    eps = np.zeros((E, nsw)) if per_sweep else None
+    fin = np.zeros(E)
+    rc = lib().msc_mirror_run(nvars, len(a), _p(a), _p(b), _p(j), _p(colors), int(colors.max()) + 1,
+                              E, int(seed), replica_offset, planes, rounds, randomize, _p(init),
+                              _p(betas), nsw, sweep0, _p(st), _p(eps), _p(fin),
+                              int(per_replica_beta is not None))
+    assert rc == 0, rc
+    return (eps if per_sweep else fin), st.astype(bool)
+
+
+def msc_mirror_pt(a, b, j, nvars, colors, betas, seed, timesteps, replica_swap_freq=1,
+                  sampling_freq=1, planes=6, rounds=10):
+    """Parallel tempering as the device runs it (oracle/msc_mirror.c: msc_mirror_pt)."""
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
     j = np.ascontiguousarray(j, dtype=np.float64)
     colors = np.ascontiguousarray(colors, dtype=np.uint32)
     betas = np.ascontiguousarray(betas, dtype=np.float64)
-    randomize = int(states is None and init_state is None)
-    st = np.zeros((E, nvars), dtype=np.uint8) if states is None else np.ascontiguousarray(
-        states, dtype=np.uint8).copy()
-    init = None if init_state is None else np.ascontiguousarray(init_state, dtype=np.uint8)
-    eps = np.zeros((E, len(betas))) if per_sweep else None
-    fin = np.zeros(E)
-    rc = lib().msc_mirror_run(nvars, len(a), _p(a), _p(b), _p(j), _p(colors), int(colors.max()) + 1,
-                              E, int(seed), replica_offset, planes, rounds, randomize, _p(init),
-                              _p(betas), len(betas), sweep0, _p(st), _p(eps), _p(fin))
+    R = len(betas)
+    ns = timesteps // sampling_freq
+    states = np.zeros((R, ns, nvars), dtype=np.uint8)
+    energies = np.zeros(R)
+    swaps = C.c_uint64(0)
+    slots = np.zeros(R, dtype=np.uint32)
+    rc = lib().msc_mirror_pt(nvars, len(a), _p(a), _p(b), _p(j), _p(colors), int(colors.max()) + 1, R,
+                             _p(betas), int(seed), planes, rounds, timesteps, replica_swap_freq,
+                             sampling_freq, _p(states), _p(energies), C.byref(swaps), _p(slots))
     assert rc == 0, rc
-    return (eps if per_sweep else fin), st.astype(bool)
+    return states.astype(bool), energies, int(swaps.value), slots
 
 
 # ---- lattice helpers shared by the tests ---------------------------------------------------

@@ -1,0 +1,218 @@
+"""GPU parity tests for arbitrary graphs (CSR/ELL colour-class kernel) and parallel tempering."""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg(native):
+    import pyisingmontecarlo_b200 as pkg
+
+    native.Context.get(0)
+    return pkg
+
+
+def random_regular(n, d, rng):
+    """pairing model with rejection of self loops / multi-edges"""
+    while True:
+        stubs = np.repeat(np.arange(n), d)
+        rng.shuffle(stubs)
+        pairs = stubs.reshape(-1, 2)
+        if (pairs[:, 0] == pairs[:, 1]).any():
+            continue
+        key = np.sort(pairs, axis=1)
+        if len(np.unique(key, axis=0)) != len(key):
+            continue
+        return [(int(a), int(b)) for a, b in pairs]
+
+
+def irregular_graph(n, rng, maxdeg=7):
+    edges = set()
+    for i in range(n):
+        for j in rng.choice(n, rng.integers(1, 4), replace=False):
+            if i != j:
+                edges.add((min(i, int(j)), max(i, int(j))))
+    deg = np.zeros(n, int)
+    out = []
+    for a, b in sorted(edges):
+        if deg[a] < maxdeg and deg[b] < maxdeg:
+            out.append((a, b))
+            deg[a] += 1
+            deg[b] += 1
+    return out
+
+
+def _check_vs_mirror(native, oracle, graph, E, seed, betas, planes=6, rounds=10, general=False):
+    a, b, j = graph.edges()
+    sim = native.Sim(graph, E, seed, planes=planes, rounds=rounds, general_layout=general)
+    en = sim.sweeps(betas, per_sweep_energies=True)
+    st = sim.states()
+    en_ref, st_ref = oracle.msc_mirror(a, b, j, graph.nvars, graph.colors(), E, seed, betas,
+                                       planes=planes, rounds=rounds, per_sweep=True)
+    assert (st == st_ref).all()
+    assert (en == en_ref).all()
+    assert (sim.energies() == en_ref[:, -1]).all()
+    return sim
+
+
+def test_random_regular_graph_matches_mirror(native, oracle, pkg):
+    """BASELINE config 4's graph family at test size: random 3-regular, J = -1."""
+    rng = np.random.default_rng(1)
+    pairs = random_regular(300, 3, rng)
+    lat = pkg.Lattice([(p, -1.0) for p in pairs], seed_gen=3)
+    g = lat.graph()
+    assert g.kind == native.KIND_GENERAL and g.max_degree == 3 and g.ncolors >= 3
+    colors = g.colors()
+    a, b, _ = g.edges()
+    assert (colors[a.astype(int)] != colors[b.astype(int)]).all()   # proper colouring
+    _check_vs_mirror(native, oracle, g, 70, 11, np.linspace(0.1, 1.5, 6))
+    _check_vs_mirror(native, oracle, g, 33, 12, [0.8, 0.8], planes=4, rounds=7)
+
+
+def test_irregular_pmj_graph_matches_mirror(native, oracle, pkg):
+    rng = np.random.default_rng(2)
+    pairs = irregular_graph(150, rng)
+    edges = [(p, float(rng.choice([-0.5, 0.5]))) for p in pairs]
+    g = pkg.Lattice(edges).graph()
+    assert g.kind == native.KIND_GENERAL and g.integer_classes
+    _check_vs_mirror(native, oracle, g, 64, 5, [0.3, 1.1, 2.0, 0.6])
+    # bipartite irregular graph: a tree gets exactly two colours
+    tree = [((i, (i - 1) // 2), 1.0) for i in range(1, 64)]
+    gt = pkg.Lattice(tree).graph()
+    assert gt.ncolors == 2
+    _check_vs_mirror(native, oracle, gt, 40, 6, [0.5, 0.9, 1.4])
+
+
+def test_general_layout_equals_stencil_path(native, oracle, pkg):
+    """The same torus through the checkerboard stencil kernels and through the general kernels:
+    both implement one algorithm, so the bits must agree."""
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (6, 4, 8), j0=1.0, pmj=True, j_seed=9)
+    betas = np.linspace(0.2, 1.2, 5)
+    s1 = native.Sim(g, 96, 77)
+    s2 = native.Sim(g, 96, 77, general_layout=True)
+    e1 = s1.sweeps(betas, per_sweep_energies=True)
+    e2 = s2.sweeps(betas, per_sweep_energies=True)
+    assert (s1.states() == s2.states()).all() and (e1 == e2).all()
+    assert (s1.magnetization() == s2.magnetization()).all()
+    g2 = native.Graph.torus(ctx, (8, 6), j0=-1.0)
+    s1, s2 = native.Sim(g2, 40, 5), native.Sim(g2, 40, 5, general_layout=True)
+    s1.sweeps([0.44] * 4)
+    s2.sweeps([0.44] * 4)
+    assert (s1.states() == s2.states()).all()
+
+
+def test_lattice_api_on_general_graph(pkg, oracle):
+    rng = np.random.default_rng(4)
+    pairs = random_regular(12, 3, rng)
+    edges = [(p, 1.0 if k % 3 else -1.0) for k, p in enumerate(pairs)]
+    lat = pkg.Lattice(edges, seed_gen=8)
+    en, st = lat.run_monte_carlo(0.7, 400, 4096)
+    g = oracle.Graph(edges)
+    assert all(en[k] == g.energy(st[k]) for k in range(0, 4096, 512))
+    # exact <E> by enumeration
+    a = np.array([e[0][0] for e in edges]); b = np.array([e[0][1] for e in edges])
+    jj = np.array([e[1] for e in edges])
+    s = np.array(list(itertools.product([-1, 1], repeat=12)), dtype=float)
+    E = (s[:, a] * s[:, b] * jj).sum(1)
+    w = np.exp(-0.7 * (E - E.min())); w /= w.sum()
+    exact, var = (w * E).sum(), (w * E * E).sum() - (w * E).sum() ** 2
+    assert abs(en.mean() - exact) < 4 * np.sqrt(var / 4096), (en.mean(), exact)
+    en2, st2 = lat.run_monte_carlo_annealing_and_get_energies([(0, 0.2), (10, 0.9)], 10, 6)
+    assert en2.shape == (6, 10) and all(en2[k, -1] == g.energy(st2[k]) for k in range(6))
+
+
+def test_unsupported_production_inputs_fail_loudly(pkg):
+    lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -0.3)], seed_gen=1)      # |J| differ
+    with pytest.raises(NotImplementedError):
+        lat.run_monte_carlo(0.5, 2, 2)
+    lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -1.0)], seed_gen=1)
+    lat.set_global_bias(0.2)
+    with pytest.raises(NotImplementedError):
+        lat.run_monte_carlo(0.5, 2, 2)
+
+
+def test_per_experiment_betas_match_mirror(native, oracle, pkg):
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (4, 4, 6), j0=1.0, pmj=True, j_seed=21)
+    E = 45
+    betas = np.linspace(0.1, 1.6, E)
+    sim = native.Sim(g, E, 99, general_layout=True)
+    sim.set_betas(betas)
+    sim.sweeps(7)
+    a, b, j = g.edges()
+    en_ref, st_ref = oracle.msc_mirror(a, b, j, g.nvars, g.colors(), E, 99, None,
+                                       per_replica_beta=betas, nsweeps=7)
+    assert (sim.states() == st_ref).all() and (sim.energies() == en_ref).all()
+    with pytest.raises(ValueError):
+        sim.sweeps([0.5])          # a per-beta sim takes a sweep count
+    with pytest.raises(NotImplementedError):
+        native.Sim(g, E, 99).set_betas(betas)   # checkerboard layout has no per-beta tables
+
+
+def test_parallel_tempering_matches_mirror(native, oracle, pkg):
+    rng = np.random.default_rng(6)
+    pairs = random_regular(60, 3, rng)
+    edges = [(p, -1.0) for p in pairs]
+    g = pkg.Lattice(edges).graph()
+    betas = np.geomspace(0.1, 1.5, 20)
+    pt = native.Tempering(g, betas, seed=314)
+    states, energies = pt.timesteps_sample(37, replica_swap_freq=3, sampling_freq=5)
+    a, b, j = g.edges()
+    st_ref, en_ref, swaps_ref, slots_ref = oracle.msc_mirror_pt(
+        a, b, j, g.nvars, g.colors(), betas, 314, 37, replica_swap_freq=3, sampling_freq=5)
+    assert states.shape == (20, 7, 60)
+    assert (states == st_ref).all()
+    assert (energies == en_ref).all()
+    assert pt.total_swaps() == swaps_ref and swaps_ref > 0
+    assert (pt.slots() == slots_ref).all()
+
+
+def test_sharded_tempering_equals_single(native, pkg):
+    """Two shards holding configurations [0, 12) and [12, 40) stepped in lock-step with a host
+    concatenation of their energies (what the all-gather does) == one unsharded ladder."""
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (4, 4, 4), j0=1.0, pmj=True, j_seed=2)
+    betas = np.linspace(0.2, 1.4, 40)
+    full = native.Tempering(g, betas, seed=5)
+    lo = native.Tempering(g, betas, seed=5, cfg_lo=0, cfg_hi=12)
+    hi = native.Tempering(g, betas, seed=5, cfg_lo=12, cfg_hi=40)
+    for step in range(6):
+        ef = full.sweeps(2)
+        es = np.concatenate([lo.sweeps(2), hi.sweeps(2)])
+        assert (ef == es).all()
+        full.swap_step(ef)
+        lo.swap_step(es)
+        hi.swap_step(es)
+        assert (full.slots() == lo.slots()).all() and (full.slots() == hi.slots()).all()
+    assert (full.local_states() == np.concatenate([lo.local_states(), hi.local_states()])).all()
+    assert full.total_swaps() == lo.total_swaps() == hi.total_swaps() > 0
+
+
+def test_lattice_tempering_class_and_statistics(pkg, oracle):
+    """tempering.rs surface; time-averaged energies per beta against exact enumeration."""
+    edges = oracle.square_edges(4)      # 16 spins: exact by enumeration
+    lt = pkg.LatticeTempering(edges, seed=7)
+    betas = [0.2, 0.3, 0.4, 0.5, 0.6]
+    for b in betas:
+        lt.add_graph(0.0, 0.0, b)
+    with pytest.raises(NotImplementedError):
+        lt.add_graph(1.0, 0.0, 0.5)
+    assert lt.get_num_graphs() == 5
+    lt.qmc_timesteps(200)
+    states, energies = lt.qmc_timesteps_sample(20000, replica_swap_freq=2, sampling_freq=2000)
+    assert states.shape == (5, 10, 16) and states.dtype == np.bool_ and energies.shape == (5,)
+    assert lt.get_total_swaps() > 100
+    a = np.array([e[0][0] for e in edges]); b = np.array([e[0][1] for e in edges])
+    s = np.array(list(itertools.product([-1, 1], repeat=16)), dtype=float)
+    E = -(s[:, a] * s[:, b]).sum(1)
+    for beta, got in zip(betas, energies):
+        w = np.exp(-beta * (E - E.min())); w /= w.sum()
+        exact = (w * E).sum()
+        sd = np.sqrt((w * E * E).sum() - exact**2)
+        assert abs(got - exact) < 0.15 * sd + 0.05, (beta, got, exact)
+    with pytest.raises(ValueError):
+        lt.qmc_timesteps_sample(10, replica_swap_freq=0)
