@@ -133,6 +133,12 @@ def betas_for(w):
 def oracle_sample(w, steps, warmup, sample_sweeps=None):
     import oracle_lib
 
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    oracle_lib.lib().orc_set_num_threads(ncores)
     threads = oracle_lib.lib().orc_num_threads()
     dims = w["dims"]
     n = int(np.prod(dims))

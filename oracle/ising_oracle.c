@@ -439,6 +439,15 @@ ORC_EXPORT int orc_pt_run(const orc_graph *g, uint64_t R, const double *betas,
     return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline leg wants every host core */
+ORC_EXPORT void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_EXPORT int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

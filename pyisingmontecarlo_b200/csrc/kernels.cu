@@ -281,14 +281,20 @@ __device__ __forceinline__ void store_words(uint32_t* p, const uint32_t (&in)[V]
 #ifndef ISING_SWEEP_MAXV
 #define ISING_SWEEP_MAXV 4
 #endif
-constexpr int SW_NP = 7;                     // fused n_sat counters: up to 127 per thread
-constexpr int SW_MAX_ITEMS = 127 / 6;        // sites a thread may accumulate (n_sat <= 6)
+#ifndef ISING_SW_NP
+#define ISING_SW_NP 7
+#endif
+#ifndef ISING_ACC_MIN_BLOCKS
+#define ISING_ACC_MIN_BLOCKS 2
+#endif
+constexpr int SW_NP = ISING_SW_NP;                       // fused n_sat counter planes per thread
+constexpr int SW_MAX_ITEMS = ((1 << SW_NP) - 1) / 6;    // sites a thread may accumulate (n_sat <= 6)
 
 // ACC: this phase also accumulates the post-flip satisfied-bond count of every replica into
 // nsat[] (used for the second colour: its sites see every bond once, so after the phase
 // nsat[e] is the total of experiment e and E = |J| (n_bonds - 2 nsat), lattice.rs:454).
 template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
-__global__ void __launch_bounds__(256, ACC ? 2 : ISING_SWEEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, ACC ? ISING_ACC_MIN_BLOCKS : ISING_SWEEP_MIN_BLOCKS)
 k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                 const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
                 uint32_t k0, uint32_t k1, uint32_t gw0, uint32_t antiferro, MscThresholds th,
@@ -391,7 +397,7 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     // never more sites per thread than the SW_NP-plane counters can hold
     if (block.y < (unsigned)V) block.y = V;
     const uint32_t per_row = (L.Lxh + block.y - 1) / block.y;
-    uint64_t g = 148ull * 2;
+    uint64_t g = 148ull * ISING_ACC_MIN_BLOCKS;
     const uint64_t need = ((uint64_t)L.rows * per_row + SW_MAX_ITEMS - 1) / SW_MAX_ITEMS;
     if (g < need) g = need;
     if (g > L.rows) g = L.rows;

@@ -69,6 +69,8 @@ def lib():
         h.orc_pt_run.argtypes = [_P, _U64, _P, _U64, _U64, _U64, _U64, _U64, _P, _P, _P]
         h.orc_num_threads.restype = C.c_int
         h.orc_num_threads.argtypes = []
+        h.orc_set_num_threads.restype = None
+        h.orc_set_num_threads.argtypes = [C.c_int]
         h.msc_philox4x32.restype = None
         h.msc_philox4x32.argtypes = [C.c_int, _P, _P, _P]
         h.msc_mirror_run.restype = C.c_int
