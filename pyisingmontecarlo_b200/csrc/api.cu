@@ -101,6 +101,12 @@ struct ising_graph {
     uint32_t* d_row32 = nullptr;   // CSR for the energy kernel
     uint32_t* d_nbr32 = nullptr;
     uint8_t* d_anti8 = nullptr;
+    // real couplings / biases: sites ordered by colour + float CSR values
+    bool real_built = false;
+    uint32_t* d_csites = nullptr;
+    std::vector<uint32_t> color_off;   // ncolors + 1 offsets into d_csites
+    float* d_jf = nullptr;
+    float* d_biasf = nullptr;
 };
 
 struct ising_sim {
@@ -117,6 +123,7 @@ struct ising_sim {
     int planes = 6, rounds = 10;
     ising_sim_stats stats{};
     bool general = false;          // natural-order layout + colour/degree groups
+    bool real = false;             // general layout, float local fields (real J / biases)
     // per-replica inverse temperatures (parallel tempering); general layout only
     bool perbeta = false;
     unsigned long long* d_t64 = nullptr;
@@ -268,18 +275,63 @@ static int ensure_csr_on_device(ising_ctx* ctx, ising_graph* g) {
     return ISING_OK;
 }
 
+static int ensure_csr32_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->d_row32) return ISING_OK;
+    HostGraph& h = g->h;
+    h.build_csr();
+    if (2 * h.nedges > 0xFFFFFFFFull) return fail(ctx, ISING_E_UNSUPPORTED, "too many edges");
+    const uint64_t N = h.nvars;
+    std::vector<uint32_t> row32(N + 1);
+    for (uint64_t n = 0; n <= N; ++n) row32[n] = (uint32_t)h.row[n];
+    std::vector<uint8_t> anti8(h.jv.size());
+    for (size_t k = 0; k < h.jv.size(); ++k) anti8[k] = h.jv[k] > 0;
+    CUDA_TRY(ctx, dev_alloc(&g->d_row32, row32.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_nbr32, h.nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_anti8, anti8.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_row32, row32.data(), row32.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_nbr32, h.nbr.data(), h.nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_anti8, anti8.data(), anti8.size(), cudaMemcpyHostToDevice));
+    return ISING_OK;
+}
+
+// arbitrary real couplings and biases: colour-ordered site list + float CSR values
+static int ensure_real_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->real_built) return ISING_OK;
+    int rc = ensure_csr32_on_device(ctx, g);
+    if (rc) return rc;
+    rc = ensure_csr_on_device(ctx, g);  // f64 couplings / biases for the energy kernel
+    if (rc) return rc;
+    HostGraph& h = g->h;
+    const uint64_t N = h.nvars;
+    std::vector<uint32_t> order(N);
+    g->color_off.assign(h.ncolors + 1, 0);
+    for (uint64_t n = 0; n < N; ++n) g->color_off[h.color_of(n) + 1]++;
+    for (int c = 0; c < h.ncolors; ++c) g->color_off[c + 1] += g->color_off[c];
+    std::vector<uint32_t> fill(g->color_off.begin(), g->color_off.end() - 1);
+    for (uint64_t n = 0; n < N; ++n) order[fill[h.color_of(n)]++] = (uint32_t)n;
+    std::vector<float> jf(h.jv.begin(), h.jv.end());
+    std::vector<float> bf(N, 0.f);
+    if (h.has_bias) for (uint64_t n = 0; n < N; ++n) bf[n] = (float)h.bias[n];
+    CUDA_TRY(ctx, dev_alloc(&g->d_csites, order.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_jf, jf.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_biasf, bf.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_csites, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jf, jf.data(), jf.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_biasf, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice));
+    g->real_built = true;
+    return ISING_OK;
+}
+
 // colour x degree groups of a graph whose couplings all have the same magnitude
 static int ensure_general_on_device(ising_ctx* ctx, ising_graph* g) {
     if (g->gen_built) return ISING_OK;
     HostGraph& h = g->h;
     if (!h.integer_classes)
-        return fail(ctx, ISING_E_UNSUPPORTED,
-                    "production sweeps on general graphs need all |J| equal and no bias in this "
-                    "revision (replay mode handles arbitrary couplings and biases)");
-    h.build_csr();
-    if (h.max_degree > GEN_MAX_DEG)
-        return fail(ctx, ISING_E_UNSUPPORTED, "maximum degree %d exceeds %d", h.max_degree, GEN_MAX_DEG);
-    if (2 * h.nedges > 0xFFFFFFFFull) return fail(ctx, ISING_E_UNSUPPORTED, "too many edges");
+        return fail(ctx, ISING_E_INVALID, "internal: integer-class kernels on a real-valued graph");
+    {
+        const int rc32 = ensure_csr32_on_device(ctx, g);
+        if (rc32) return rc32;
+    }
     const uint64_t N = h.nvars;
     const int ncol = h.ncolors;
     // bucket sites by (colour, degree)
@@ -309,22 +361,12 @@ static int ensure_general_on_device(ising_ctx* ctx, ising_graph* g) {
             }
             offs.push_back(o);
         }
-    std::vector<uint32_t> row32(N + 1);
-    for (uint64_t n = 0; n <= N; ++n) row32[n] = (uint32_t)h.row[n];
-    std::vector<uint8_t> anti8(h.jv.size());
-    for (size_t k = 0; k < h.jv.size(); ++k) anti8[k] = h.jv[k] > 0;
     CUDA_TRY(ctx, dev_alloc(&g->d_gsites, sites.size()));
     CUDA_TRY(ctx, dev_alloc(&g->d_gnbr, nbr.size()));
     CUDA_TRY(ctx, dev_alloc(&g->d_ganti, anti.size()));
-    CUDA_TRY(ctx, dev_alloc(&g->d_row32, row32.size()));
-    CUDA_TRY(ctx, dev_alloc(&g->d_nbr32, h.nbr.size()));
-    CUDA_TRY(ctx, dev_alloc(&g->d_anti8, anti8.size()));
     CUDA_TRY(ctx, cudaMemcpy(g->d_gsites, sites.data(), sites.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(g->d_gnbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(g->d_ganti, anti.data(), anti.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(g->d_row32, row32.data(), row32.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(g->d_nbr32, h.nbr.data(), h.nbr.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(g->d_anti8, anti8.data(), anti8.size(), cudaMemcpyHostToDevice));
     for (const Off& o : offs) {
         GenGroup gg;
         gg.sites = g->d_gsites + o.s;
@@ -386,6 +428,9 @@ extern "C" void ising_graph_destroy(ising_graph* g) {
     cudaFree(g->d_row32);
     cudaFree(g->d_nbr32);
     cudaFree(g->d_anti8);
+    cudaFree(g->d_csites);
+    cudaFree(g->d_jf);
+    cudaFree(g->d_biasf);
     delete g;
 }
 
@@ -448,8 +493,15 @@ extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_
     if (replica_offset % 32) return fail(ctx, ISING_E_INVALID, "replica_offset must be a multiple of 32");
     const HostGraph& h = g->h;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const bool general = h.kind == ISING_KIND_GENERAL || (flags & ISING_SIM_GENERAL_LAYOUT);
-    if (general) {
+    // integer energy classes (all |J| equal, no bias, degree <= 15) use the bit-sliced kernels;
+    // anything else the reference accepts runs on the float-field kernel
+    const_cast<ising_graph*>(g)->h.build_csr();
+    const bool real = !h.integer_classes || (h.kind == ISING_KIND_GENERAL && h.max_degree > GEN_MAX_DEG);
+    const bool general = real || h.kind == ISING_KIND_GENERAL || (flags & ISING_SIM_GENERAL_LAYOUT);
+    if (real) {
+        const int rc = ensure_real_on_device(ctx, const_cast<ising_graph*>(g));
+        if (rc) return rc;
+    } else if (general) {
         const int rc = ensure_general_on_device(ctx, const_cast<ising_graph*>(g));
         if (rc) return rc;
     }
@@ -460,6 +512,7 @@ extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_
     s->seed = seed;
     s->replica_offset = replica_offset;
     s->general = general;
+    s->real = real;
     Layout& L = s->lay;
     L.kind = general ? ISING_KIND_GENERAL : h.kind;
     L.Lx = (uint32_t)h.dims[0];
@@ -640,7 +693,53 @@ static int sim_one_sweep_general(ising_sim* s, double beta) {
     return ISING_OK;
 }
 
+static int sim_one_sweep_real(ising_sim* s, double beta) {
+    ising_ctx* ctx = s->ctx;
+    const ising_graph* g = s->g;
+    RealSweepArgs a;
+    a.spins = s->d_spins;
+    a.row = g->d_row32;
+    a.nbr = g->d_nbr32;
+    a.jf = g->d_jf;
+    a.biasf = g->d_biasf;
+    a.W = s->lay.W;
+    a.beta = (float)beta;
+    a.sweep = (uint32_t)s->sweep_counter;
+    a.key0 = (uint32_t)s->seed;
+    a.key1 = (uint32_t)(s->seed >> 32);
+    a.gw0 = (uint32_t)(s->replica_offset / 32);
+    a.rounds = s->rounds;
+    int launches = 0;
+    for (int c = 0; c < g->h.ncolors; ++c) {
+        a.sites = g->d_csites + g->color_off[c];
+        a.count = g->color_off[c + 1] - g->color_off[c];
+        const int n = launch_sweep_real(a, ctx->stream);
+        if (n < 0) return fail(ctx, ISING_E_CUDA, "real-coupling sweep launch failed: %s",
+                               cudaGetErrorString(cudaGetLastError()));
+        launches += n;
+    }
+    count_launch(s, launches);
+    s->stats.sweep_kernel_launches += (uint64_t)launches;
+    s->sweep_counter++;
+    s->stats.sweeps++;
+    s->stats.flip_attempts += s->E * g->h.nvars;
+    return ISING_OK;
+}
+
+// f64 energies of a real-coupling sim into d_out[e * estride + eoff]
+static int sim_energy_real(ising_sim* s, double* d_tmp /* [32 W] */) {
+    ising_ctx* ctx = s->ctx;
+    const ising_graph* g = s->g;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_tmp, 0, (size_t)s->lay.W * 32 * sizeof(double), ctx->stream));
+    const int n = launch_energy_real(s->d_spins, s->lay.nvars, s->lay.W, g->d_row32, g->d_nbr32,
+                                     g->d_jv, g->d_bias, d_tmp, ctx->stream);
+    if (n < 0) return fail(ctx, ISING_E_CUDA, "energy launch failed");
+    count_launch(s, n);
+    return ISING_OK;
+}
+
 static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr) {
+    if (s->real) return sim_one_sweep_real(s, beta);
     if (s->general) return sim_one_sweep_general(s, beta);
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
@@ -737,7 +836,9 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
         // into that sweep's slot of the history (fused, no separate energy pass)
         for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t) {
             rc = sim_one_sweep(s, betas ? betas[t0 + t] : 0.0, d_hist + t * cw);
-            if (rc == ISING_OK && s->general) {  // no fused accumulation on general graphs
+            if (rc == ISING_OK && s->real) {
+                rc = sim_energy_real(s, reinterpret_cast<double*>(d_hist + t * cw));
+            } else if (rc == ISING_OK && s->general) {  // no fused accumulation on general graphs
                 const int n = launch_nsat_general(s->d_spins, s->lay.nvars, s->lay.W, s->g->d_row32,
                                                   s->g->d_nbr32, s->g->d_anti8, d_hist + t * cw,
                                                   ctx->stream);
@@ -745,7 +846,10 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
                 else count_launch(s, n);
             }
         }
-        if (rc == ISING_OK)
+        if (rc == ISING_OK && s->real)
+            count_launch(s, launch_transpose_hist_f64(reinterpret_cast<double*>(d_hist), E, cw, nt,
+                                                      d_out, ctx->stream));
+        else if (rc == ISING_OK)
             count_launch(s, launch_energy_from_hist(d_hist, E, cw, nt, h.jabs, h.nedges, mult,
                                                     d_out, ctx->stream));
         cudaEventRecord(ctx->ev1, ctx->stream);
@@ -764,18 +868,33 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     return rc;
 }
 
+// current energies of all experiments into d_out[e * estride + eoff] (device)
+static int sim_energies_to_device(ising_sim* s, double* d_out, uint64_t estride, uint64_t eoff) {
+    ising_ctx* ctx = s->ctx;
+    const HostGraph& h = s->g->h;
+    if (s->real) {
+        double* tmp = reinterpret_cast<double*>(s->d_counts);  // same size as the u64 counters
+        const int rc = sim_energy_real(s, tmp);
+        if (rc) return rc;
+        count_launch(s, launch_copy_strided_f64(tmp, s->E, d_out, estride, eoff, ctx->stream));
+        return ISING_OK;
+    }
+    const int rc = sim_count_nsat(s, s->d_counts);
+    if (rc) return rc;
+    count_launch(s, launch_energy_from_nsat(s->d_counts, s->E, h.jabs, h.nedges, s->general ? 1 : 2,
+                                            d_out, estride, eoff, ctx->stream));
+    return ISING_OK;
+}
+
 extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
     if (!s || !energies) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/energies is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const HostGraph& h = s->g->h;
-    int rc = sim_count_nsat(s, s->d_counts);
-    if (rc) return rc;
     void* dv = nullptr;
     CUDA_TRY(ctx, ctx_scratch(ctx, 2, s->E * sizeof(double), &dv));
     double* d_out = (double*)dv;
-    count_launch(s, launch_energy_from_nsat(s->d_counts, s->E, h.jabs, h.nedges,
-                                            s->general ? 1 : 2, d_out, 1, 0, ctx->stream));
+    const int rc = sim_energies_to_device(s, d_out, 1, 0);
+    if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(energies, d_out, s->E * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -850,9 +969,10 @@ extern "C" int ising_sim_reset_stats(ising_sim* s) {
 extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
     if (!s || !betas) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
     ising_ctx* ctx = s->ctx;
-    if (!s->general)
+    if (!s->general || s->real)
         return fail(ctx, ISING_E_UNSUPPORTED,
-                    "per-experiment betas need the general layout (ISING_SIM_GENERAL_LAYOUT)");
+                    "per-experiment betas need the general layout (ISING_SIM_GENERAL_LAYOUT) and "
+                    "integer energy classes (all |J| equal, no bias)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const HostGraph& h = s->g->h;
     const uint32_t W = s->lay.W, E32 = 32 * W;
@@ -1151,11 +1271,8 @@ extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph*
             if (rc) break;
             count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d + k * N, E, nk * N,
                                                    ctx->stream));
-            rc = sim_count_nsat(sim, sim->d_counts);
+            rc = sim_energies_to_device(sim, d_en, nk, k);
             if (rc) break;
-            count_launch(sim, launch_energy_from_nsat(sim->d_counts, E, g->h.jabs, g->h.nedges,
-                                                      sim->general ? 1 : 2, d_en, nk, k,
-                                                      ctx->stream));
         }
         if (rc) break;
         en_host.resize((size_t)E * nk);

@@ -681,6 +681,36 @@ int launch_energy_from_hist(const unsigned long long* hist, uint64_t E, uint64_t
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// out[e * estride + eoff] = in[e]   /   out[e * nt + t] = hist[t * cw + e]  (f64 energies)
+__global__ void k_copy_strided_f64(const double* __restrict__ in, uint64_t E,
+                                   double* __restrict__ out, uint64_t estride, uint64_t eoff) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) out[e * estride + eoff] = in[e];
+}
+
+__global__ void k_transpose_hist_f64(const double* __restrict__ hist, uint64_t E, uint64_t cw,
+                                     uint64_t nt, double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * nt) return;
+    const uint64_t e = i / nt, t = i - e * nt;
+    out[i] = hist[t * cw + e];
+}
+
+int launch_copy_strided_f64(const double* in, uint64_t E, double* out, uint64_t estride,
+                            uint64_t eoff, cudaStream_t st) {
+    const unsigned g = (unsigned)((E + 255) / 256);
+    k_copy_strided_f64<<<g ? g : 1, 256, 0, st>>>(in, E, out, estride, eoff);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_transpose_hist_f64(const double* hist, uint64_t E, uint64_t cw, uint64_t nt, double* out,
+                              cudaStream_t st) {
+    const uint64_t n = E * nt;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    k_transpose_hist_f64<<<g ? g : 1, 256, 0, st>>>(hist, E, cw, nt, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double scale,
                             uint64_t nbonds, int mult, double* out_dev, uint64_t estride,
                             uint64_t eoff, cudaStream_t st) {
@@ -888,6 +918,104 @@ int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const
     if (g > 148u * 8u) g = 148u * 8u;
     if (g == 0) g = 1;
     k_nsat_general<<<dim3((unsigned)g), block, 0, st>>>(spins, nvars, W, row, nbr, anti, nsat2);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Colour-class sweep for arbitrary real couplings and biases (lattice.rs:31, 104-131): the local
+// field is not an integer class, so every replica bit gets its own float field, its own
+// exp(-beta dE) and its own 32-bit uniform (word b%4 of Philox call b/4 on the usual counter).
+// dE = -2 s_i sum_k J_ik s_k + 2 b_i s_i  (qmc GraphState::do_spin_flip); accept iff dE <= 0 or
+// R < floor(exp(-beta dE) 2^32).  Validated statistically (f32 field / __expf), not bit-exactly.
+// ------------------------------------------------------------------------------------------
+template <int ROUNDS>
+__global__ void __launch_bounds__(256)
+k_sweep_real(RealSweepArgs a) {
+    const uint64_t total = (uint64_t)a.count * a.W;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(item / a.W), w = (uint32_t)(item - (uint64_t)i * a.W);
+        const uint32_t n = a.sites[i];
+        const uint32_t s = a.spins[(size_t)n * a.W + w];
+        const uint32_t lo = a.row[n], hi = a.row[n + 1];
+        const float bias = a.biasf[n];
+        uint32_t flip = 0;
+        for (uint32_t b0 = 0; b0 < 32; b0 += 4) {
+            const u32x4 r = philox4x32<ROUNDS>(n, a.gw0 + w, a.sweep, (b0 >> 2) | (TAG_ACCEPT << 24),
+                                               a.key0, a.key1);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            float h[4] = {0.f, 0.f, 0.f, 0.f};
+            for (uint32_t k = lo; k < hi; ++k) {
+                const uint32_t x = a.spins[(size_t)a.nbr[k] * a.W + w] >> b0;
+                const uint32_t jb = __float_as_uint(a.jf[k]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)  // J * s_k: flip the sign bit where the spin is down
+                    h[q] += __uint_as_float(jb ^ ((~(x >> q) & 1u) << 31));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float si = ((s >> (b0 + q)) & 1u) ? 1.f : -1.f;
+                const float de = 2.f * si * (bias - h[q]);
+                bool acc = true;
+                if (de > 0.f) {
+                    const float pth = __expf(-a.beta * de) * 4294967296.f;
+                    acc = rr[q] < __float2uint_rz(pth);  // saturating conversion
+                }
+                if (acc) flip |= 1u << (b0 + q);
+            }
+        }
+        a.spins[(size_t)n * a.W + w] = s ^ flip;
+    }
+}
+
+int launch_sweep_real(const RealSweepArgs& a, cudaStream_t st) {
+    if (a.count == 0) return 0;
+    const uint64_t total = (uint64_t)a.count * a.W;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    if (a.rounds == 7) k_sweep_real<7><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else k_sweep_real<10><<<(unsigned)blocks, 256, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void __launch_bounds__(256)
+k_energy_real(const uint32_t* __restrict__ spins, uint64_t nvars, uint32_t W,
+              const uint32_t* __restrict__ row, const uint32_t* __restrict__ nbr,
+              const double* __restrict__ jv, const double* __restrict__ bias,
+              double* __restrict__ energies) {
+    // block = (wx word columns, by site lanes); each thread keeps 32 f64 partial energies
+    const uint32_t w = blockIdx.y * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.0;
+    for (uint64_t n = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y; n < nvars;
+         n += (uint64_t)gridDim.x * blockDim.y) {
+        const uint32_t s = spins[(size_t)n * W + w];
+        const double bi = bias[n];
+        for (uint32_t k = row[n]; k < row[n + 1]; ++k) {
+            const uint32_t eqm = ~(s ^ spins[(size_t)nbr[k] * W + w]);  // 1 where s_i == s_k
+            const double hj = 0.5 * jv[k];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) acc[b] += ((eqm >> b) & 1u) ? hj : -hj;
+        }
+#pragma unroll
+        for (int b = 0; b < 32; ++b) acc[b] += ((s >> b) & 1u) ? -bi : bi;
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) atomicAdd(energies + (size_t)w * 32 + b, acc[b]);
+}
+
+int launch_energy_real(const uint32_t* spins, uint64_t nvars, uint32_t W, const uint32_t* row,
+                       const uint32_t* nbr, const double* jv, const double* bias, double* energies,
+                       cudaStream_t st) {
+    const uint32_t wx = W >= 32 ? 32 : pow2_ceil(W);
+    dim3 block(wx, 128 / wx, 1);
+    uint64_t g = (nvars + block.y - 1) / block.y;
+    if (g > 148u * 4u) g = 148u * 4u;
+    if (g == 0) g = 1;
+    dim3 grid((unsigned)g, (W + wx - 1) / wx, 1);
+    k_energy_real<<<grid, block, 0, st>>>(spins, nvars, W, row, nbr, jv, bias, energies);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

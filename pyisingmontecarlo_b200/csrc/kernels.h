@@ -115,6 +115,31 @@ int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const
                         const uint32_t* nbr, const uint8_t* anti, unsigned long long* nsat2,
                         cudaStream_t st);
 
+// ---- arbitrary real couplings and biases (float local field per replica bit) -----------------
+struct RealSweepArgs {
+    uint32_t* spins;          // [nvars][W]
+    const uint32_t* sites;    // sites of the colour being updated
+    uint32_t count;
+    const uint32_t* row;      // CSR (u32 offsets), neighbours ascending
+    const uint32_t* nbr;
+    const float* jf;          // coupling per CSR entry
+    const float* biasf;       // per site
+    uint32_t W;
+    float beta;
+    uint32_t sweep, key0, key1, gw0;
+    int rounds;
+};
+int launch_sweep_real(const RealSweepArgs& a, cudaStream_t st);
+// energies[e] += sum_edges J s s - sum_i b_i s_i in f64 (every bond seen from both ends, halved)
+int launch_energy_real(const uint32_t* spins, uint64_t nvars, uint32_t W, const uint32_t* row,
+                       const uint32_t* nbr, const double* jv, const double* bias,
+                       double* energies /* [32 W], zeroed */, cudaStream_t st);
+
+int launch_copy_strided_f64(const double* in, uint64_t E, double* out, uint64_t estride,
+                            uint64_t eoff, cudaStream_t st);
+int launch_transpose_hist_f64(const double* hist, uint64_t E, uint64_t cw, uint64_t nt, double* out,
+                              cudaStream_t st);
+
 struct ReplayArgs {
     uint64_t E, N, A;
     const uint64_t* row;   // CSR offsets (nvars + 1)

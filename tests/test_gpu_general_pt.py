@@ -125,14 +125,58 @@ def test_lattice_api_on_general_graph(pkg, oracle):
     assert en2.shape == (6, 10) and all(en2[k, -1] == g.energy(st2[k]) for k in range(6))
 
 
-def test_unsupported_production_inputs_fail_loudly(pkg):
-    lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -0.3)], seed_gen=1)      # |J| differ
-    with pytest.raises(NotImplementedError):
-        lat.run_monte_carlo(0.5, 2, 2)
-    lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -1.0)], seed_gen=1)
-    lat.set_global_bias(0.2)
-    with pytest.raises(NotImplementedError):
-        lat.run_monte_carlo(0.5, 2, 2)
+def _exact(edges, n, beta, biases=None):
+    a = np.array([e[0][0] for e in edges]); b = np.array([e[0][1] for e in edges])
+    jj = np.array([e[1] for e in edges], dtype=float)
+    bias = np.zeros(n) if biases is None else np.asarray(biases, float)
+    s = np.array(list(itertools.product([-1, 1], repeat=n)), dtype=float)
+    E = (s[:, a] * s[:, b] * jj).sum(1) - s @ bias
+    w = np.exp(-beta * (E - E.min())); w /= w.sum()
+    mean = (w * E).sum()
+    return mean, np.sqrt((w * E * E).sum() - mean**2), w @ s
+
+
+@pytest.mark.parametrize("case", ["k4_mixed_bias", "ring_real", "star_degree20", "global_bias_torus"])
+def test_real_couplings_and_biases(pkg, oracle, case):
+    """Inputs outside the integer-class kernels (real J, biases, degree > 15) run on the
+    float-field kernel: energies are those of the returned states, <E> and <s_i> agree with
+    exact enumeration."""
+    rng = np.random.default_rng(11)
+    if case == "k4_mixed_bias":
+        edges = [((0, 1), -1.0), ((0, 2), 0.5), ((0, 3), 1.5), ((1, 2), -0.7), ((1, 3), 0.3), ((2, 3), 1.0)]
+        n, biases, beta = 4, [0.3, -0.2, 0.0, 0.6], 0.5
+    elif case == "ring_real":
+        n = 10
+        edges = [((i, (i + 1) % n), float(rng.normal())) for i in range(n)]
+        biases, beta = None, 0.8
+    elif case == "star_degree20":
+        n = 15
+        edges = [((0, i), -1.0) for i in range(1, n)] + [((1, i), 1.0) for i in range(2, 9)] + \
+                [((0, i), -1.0) for i in range(1, 8)]          # multi-edges: hub degree 21
+        biases, beta = None, 0.25
+    else:
+        edges, n, biases, beta = oracle.square_edges(4), 16, [0.15] * 16, 0.35
+    lat = pkg.Lattice(edges, seed_gen=5)
+    if biases is not None:
+        if case == "global_bias_torus":
+            lat.set_global_bias(0.15)
+        else:
+            for v, b in enumerate(biases):
+                lat.set_individual_bias(v, b)
+    E = 8192
+    en, st = lat.run_monte_carlo(beta, 300, E)
+    g = oracle.Graph(edges, nvars=n, biases=biases)
+    for k in range(0, E, 1024):
+        assert abs(en[k] - g.energy(st[k])) < 1e-9 * max(1.0, abs(en[k]))
+    mean, sd, mag = _exact(edges, n, beta, biases)
+    assert abs(en.mean() - mean) < 4 * sd / np.sqrt(E) + 1e-6, (en.mean(), mean, sd)
+    m = (st * 2.0 - 1).mean(0)
+    assert np.abs(m - mag).max() < 5 / np.sqrt(E), (m, mag)
+    # the other drivers work on this path too
+    en2, st2 = lat.run_monte_carlo_annealing_and_get_energies([(0, 0.1), (5, beta)], 5, 64)
+    assert en2.shape == (64, 5) and abs(en2[3, -1] - g.energy(st2[3])) < 1e-9 * max(1.0, abs(en2[3, -1]))
+    en3, st3 = lat.run_monte_carlo_sampling(beta, 6, 32, None, 1, 2)
+    assert en3.shape == (32, 3) and abs(en3[5, 1] - g.energy(st3[5, 1])) < 1e-9 * max(1.0, abs(en3[5, 1]))
 
 
 def test_per_experiment_betas_match_mirror(native, oracle, pkg):
