@@ -119,6 +119,12 @@ ISING_API int ising_sim_set_states(ising_sim *sim, const uint8_t *states /* E*nv
  * receives double[E, nsweeps] (GraphState::get_energy after every timestep, lattice.rs:454). */
 ISING_API int ising_sim_sweeps(ising_sim *sim, const double *betas, uint64_t nsweeps,
                      double *energies_per_sweep);
+/* thermalization sweeps, then n_samples x (sampling_freq sweeps, state copy, energy) on the
+ * resident state: ClassicIsing::run_monte_carlo_sampling (classicising.rs:119-179) and the body
+ * of Lattice::run_monte_carlo_sampling.  energies[E, n_samples], states bool[E, n_samples, nvars] */
+ISING_API int ising_sim_run_sampling(ising_sim *sim, double beta, uint64_t thermalization,
+                           uint64_t sampling_freq, uint64_t n_samples, double *energies,
+                           uint8_t *states);
 ISING_API int ising_sim_get_energies(ising_sim *sim, double *energies /* E */);
 ISING_API int ising_sim_get_states(ising_sim *sim, uint8_t *states /* E*nvars, bool */);
 /* Opt-in packed read-back: uint32[nvars, ceil(E/32)] in natural site order (bit e%32 of word

@@ -6,8 +6,9 @@ the annealing runs, replay mode and the parallel-tempering loop.  Compute lives 
 """
 from ._native import (AmbiguousReplay, Context, Graph, NativeLibraryMissing, Sim,  # noqa: F401
                       Tempering)
+from .classic import ClassicIsing  # noqa: F401
 from .lattice import Lattice  # noqa: F401
 from .tempering import LatticeTempering, run_tempering_loop, shard_range  # noqa: F401
 
-__all__ = ["Lattice", "LatticeTempering", "Sim", "Tempering", "Graph", "Context",
+__all__ = ["Lattice", "ClassicIsing", "LatticeTempering", "Sim", "Tempering", "Graph", "Context",
            "AmbiguousReplay", "NativeLibraryMissing", "run_tempering_loop", "shard_range"]

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "ising_sim_set_state": (C.c_int, [_P, _P]),
     "ising_sim_set_states": (C.c_int, [_P, _P]),
     "ising_sim_sweeps": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "ising_sim_run_sampling": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "ising_sim_get_energies": (C.c_int, [_P, _P]),
     "ising_sim_get_states": (C.c_int, [_P, _P]),
     "ising_sim_get_packed": (C.c_int, [_P, _P]),
@@ -357,6 +358,14 @@ class Sim:
         if b.shape != (self.E,):
             raise ValueError("betas must have one entry per experiment")
         check(lib().ising_sim_set_betas(self.handle, ptr(b)), self.ctx.handle)
+
+    def run_sampling(self, beta, thermalization, sampling_freq, n_samples):
+        energies = np.empty((self.E, n_samples), dtype=np.float64)
+        states = PinnedPool.empty((self.E, n_samples, self.graph.nvars), np.bool_)
+        check(lib().ising_sim_run_sampling(self.handle, float(beta), int(thermalization),
+                                           int(sampling_freq), int(n_samples), ptr(energies),
+                                           ptr(states)), self.ctx.handle)
+        return energies, states
 
     def energies(self):
         out = np.empty(self.E, dtype=np.float64)

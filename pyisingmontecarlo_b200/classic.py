@@ -1,0 +1,86 @@
+"""`ClassicIsing` -- the stateful classical API of the reference (src/classicising.rs:1-180):
+the same kernels as `Lattice`, but the experiments live on the device between calls."""
+import secrets
+
+import numpy as np
+
+from . import _native as nat
+from .lattice import _edges_to_arrays
+
+_U64 = 2**64 - 1
+
+
+class ClassicIsing:
+    """Unlike the Lattice class this maintains a set of graphs with internal state."""
+
+    def __init__(self, edges, longitudinal=None, num_experiments=None, seed=None, use_basic_moves=None,
+                 *, device=None):
+        # classicising.rs:26-60 (the reference unwraps the max index: an empty list panics)
+        if len(edges) == 0:
+            raise ValueError("Must supply some edges for graph")
+        self._a, self._b, self._j = _edges_to_arrays(edges)
+        self.nvars = int(max(self._a.max(), self._b.max())) + 1
+        self._longitudinal = 0.0 if longitudinal is None else float(longitudinal)
+        self._seed = (int(seed) & _U64) if seed is not None else secrets.randbits(64)
+        self._use_basic_moves = bool(use_basic_moves) if use_basic_moves is not None else False
+        self._device = device
+        ctx = nat.Context.get(device)
+        bias = None if self._longitudinal == 0.0 else np.full(self.nvars, self._longitudinal)
+        self._graph = nat.Graph.from_edges(ctx, self.nvars, self._a, self._b, self._j, bias)
+        self._sim = None
+        self._n = 0
+        for _ in range(1 if num_experiments is None else int(num_experiments)):
+            self.add_graph(None, None)
+
+    def add_graph(self, initial_state=None, edge_move_importance_sampling=None):
+        """classicising.rs:62-79: one more experiment, random start or the given state."""
+        if edge_move_importance_sampling:
+            raise NotImplementedError("edge_move_importance_sampling only affects the reference's "
+                                      "non-basic edge moves, which the GPU path does not perform")
+        old = None if self._sim is None else self._sim.states()
+        self._n += 1
+        sim = nat.Sim(self._graph, self._n, self._seed)      # experiment e always owns stream e
+        if old is not None or initial_state is not None:
+            st = sim.states()                                   # random start of the new experiment
+            if old is not None:
+                st[: self._n - 1] = old
+            if initial_state is not None:
+                init = np.asarray(initial_state, dtype=np.bool_).ravel()
+                if len(init) != self.nvars:
+                    raise ValueError("initial_state must have nvars entries")
+                st[self._n - 1] = init
+            sim.set_states(st)
+        if self._sim is not None:
+            self._sim.close()
+        self._sim = sim
+
+    def _check_moves(self, nspinupdates, nedgeupdates, nwormupdates):
+        if nspinupdates not in (None, self.nvars):
+            raise NotImplementedError("a timestep is one sweep of nvars single-spin attempts on the GPU path")
+        if nedgeupdates or nwormupdates:
+            raise NotImplementedError("edge / worm updates are not performed on the GPU path")
+
+    def run_monte_carlo(self, beta, timesteps, nspinupdates=None, nedgeupdates=None, nwormupdates=None,
+                        only_basic_moves=None):
+        """classicising.rs:88-110: advances every experiment, returns nothing."""
+        self._check_moves(nspinupdates, nedgeupdates, nwormupdates)
+        self._sim.sweeps(np.full(int(timesteps), float(beta)))
+
+    def run_monte_carlo_sampling(self, beta, timesteps, nspinupdates=None, nedgeupdates=None,
+                                 nwormupdates=None, only_basic_moves=None, thermalization_time=None,
+                                 sampling_freq=None):
+        """classicising.rs:119-179 -> (energies float64[E, n_s], states bool[E, n_s, nvars])"""
+        self._check_moves(nspinupdates, nedgeupdates, nwormupdates)
+        thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
+        sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
+        if sampling_freq == 0:
+            raise ZeroDivisionError("sampling_freq must be non-zero (the reference panics)")
+        return self._sim.run_sampling(beta, thermalization_time, sampling_freq,
+                                      int(timesteps) // sampling_freq)
+
+    # additive: the resident state, for tests and users
+    def get_states(self):
+        return self._sim.states()
+
+    def get_energies(self):
+        return self._sim.energies()

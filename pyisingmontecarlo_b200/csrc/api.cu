@@ -1236,6 +1236,56 @@ extern "C" int ising_run_monte_carlo(ising_ctx* ctx, const ising_graph* g,
     return rc;
 }
 
+// thermalise, then n_s x (sampling_freq sweeps, copy state, energy): lattice.rs:271-287 and
+// classicising.rs:146-171 on a device-resident sim.  energies[E, n_s], states[E, n_s, nvars].
+extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t thermalization,
+                                      uint64_t sampling_freq, uint64_t ns, double* energies,
+                                      uint8_t* states) {
+    if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    ising_ctx* ctx = sim->ctx;
+    if (ns && (!energies || !states)) return fail(ctx, ISING_E_INVALID, "output buffers are NULL");
+    if (sim->perbeta) return fail(ctx, ISING_E_INVALID, "sampling runs at one beta");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t E = sim->E, N = sim->lay.nvars;
+    std::vector<double> betas(std::max<uint64_t>(thermalization, sampling_freq), beta);
+    int rc = ising_sim_sweeps(sim, betas.data(), thermalization, nullptr);
+    if (rc || ns == 0) return rc;
+    // states[E, ns, N]: sample k of experiment e lands at (e * ns + k) * N; unpack straight
+    // into a device image of that layout, slab by slab (<= 1 GiB of staging)
+    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, (1ull << 30) / std::max<uint64_t>(1, E * N)));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, (size_t)E * slab * N, &dv));
+    uint8_t* d = (uint8_t*)dv;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 2, (size_t)E * slab * sizeof(double), &dv));
+    double* d_en = (double*)dv;
+    std::vector<double> en_host;
+    std::vector<uint8_t> st_host;
+    for (uint64_t k0 = 0; k0 < ns; k0 += slab) {
+        const uint64_t nk = std::min(slab, ns - k0);
+        for (uint64_t k = 0; k < nk; ++k) {
+            rc = ising_sim_sweeps(sim, betas.data(), sampling_freq, nullptr);
+            if (rc) return rc;
+            count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d + k * N, E, nk * N,
+                                                   ctx->stream));
+            rc = sim_energies_to_device(sim, d_en, nk, k);
+            if (rc) return rc;
+        }
+        en_host.resize((size_t)E * nk);
+        st_host.resize(nk == ns ? 0 : (size_t)E * nk * N);
+        uint8_t* dst = nk == ns ? states : st_host.data();
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, d, (size_t)E * nk * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(en_host.data(), d_en, en_host.size() * 8, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (uint64_t e = 0; e < E; ++e) {
+            memcpy(energies + e * ns + k0, en_host.data() + e * nk, nk * sizeof(double));
+            if (nk != ns)
+                memcpy(states + (e * ns + k0) * N, st_host.data() + e * nk * N, (size_t)nk * N);
+        }
+    }
+    return ISING_OK;
+}
+
 extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph* g,
                                               const ising_run_args* a, double* energies,
                                               uint8_t* states) {
@@ -1244,54 +1294,11 @@ extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph*
     if (a->sampling_freq == 0)
         return fail(ctx, ISING_E_INVALID, "sampling_freq must be > 0 (the reference divides by it)");
     if (a->num_experiments == 0) return ISING_OK;
-    const uint64_t ns = a->timesteps / a->sampling_freq;
-    const uint64_t E = a->num_experiments, N = g->h.nvars;
     ising_sim* sim = nullptr;
     rc = make_sim_for_run(ctx, g, a, &sim);
     if (rc) return rc;
-    std::vector<double> betas(std::max<uint64_t>(a->thermalization, a->sampling_freq), a->beta);
-    rc = ising_sim_sweeps(sim, betas.data(), a->thermalization, nullptr);
-    // states[E, ns, N]: sample k of experiment e lands at (e * ns + k) * N; unpack straight
-    // into a device image of that layout slab by slab
-    uint8_t* d = nullptr;
-    double* d_en = nullptr;
-    cudaError_t ce = cudaSuccess;
-    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, (1ull << 30) / std::max<uint64_t>(1, E * N)));
-    if (rc == ISING_OK && ns) {
-        ce = dev_alloc(&d, (size_t)E * slab * N);
-        if (ce == cudaSuccess) ce = dev_alloc(&d_en, (size_t)E * slab);
-        if (ce != cudaSuccess) rc = fail(ctx, ISING_E_NOMEM, "sampling staging: %s", cudaGetErrorString(ce));
-    }
-    std::vector<double> en_host;
-    std::vector<uint8_t> st_host;
-    for (uint64_t k0 = 0; k0 < ns && rc == ISING_OK; k0 += slab) {
-        const uint64_t nk = std::min(slab, ns - k0);
-        for (uint64_t k = 0; k < nk && rc == ISING_OK; ++k) {
-            rc = ising_sim_sweeps(sim, betas.data(), a->sampling_freq, nullptr);
-            if (rc) break;
-            count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d + k * N, E, nk * N,
-                                                   ctx->stream));
-            rc = sim_energies_to_device(sim, d_en, nk, k);
-            if (rc) break;
-        }
-        if (rc) break;
-        en_host.resize((size_t)E * nk);
-        st_host.resize(nk == ns ? 0 : (size_t)E * nk * N);
-        uint8_t* dst = nk == ns ? states : st_host.data();
-        ce = cudaMemcpyAsync(dst, d, (size_t)E * nk * N, cudaMemcpyDeviceToHost, ctx->stream);
-        if (ce == cudaSuccess)
-            ce = cudaMemcpyAsync(en_host.data(), d_en, en_host.size() * 8, cudaMemcpyDeviceToHost,
-                                 ctx->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-        if (ce != cudaSuccess) { rc = fail(ctx, ISING_E_CUDA, "sampling read-back: %s", cudaGetErrorString(ce)); break; }
-        for (uint64_t e = 0; e < E; ++e) {
-            memcpy(energies + e * ns + k0, en_host.data() + e * nk, nk * sizeof(double));
-            if (nk != ns)
-                memcpy(states + (e * ns + k0) * N, st_host.data() + e * nk * N, (size_t)nk * N);
-        }
-    }
-    cudaFree(d);
-    cudaFree(d_en);
+    rc = ising_sim_run_sampling(sim, a->beta, a->thermalization, a->sampling_freq,
+                                a->timesteps / a->sampling_freq, energies, states);
     ising_sim_destroy(sim);
     return rc;
 }

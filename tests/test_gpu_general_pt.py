@@ -260,3 +260,35 @@ def test_lattice_tempering_class_and_statistics(pkg, oracle):
         assert abs(got - exact) < 0.15 * sd + 0.05, (beta, got, exact)
     with pytest.raises(ValueError):
         lt.qmc_timesteps_sample(10, replica_swap_freq=0)
+
+
+def test_classic_ising_stateful_api(pkg, oracle, native):
+    """classicising.rs: state persists between calls; sampling continues from it."""
+    edges = oracle.square_edges(8)
+    ci = pkg.ClassicIsing(edges, None, 5, 42)
+    s0 = ci.get_states()
+    assert s0.shape == (5, 64)
+    ci.run_monte_carlo(0.4, 10)
+    s1 = ci.get_states()
+    assert (s1 != s0).any()
+    # identical to one uninterrupted sim of the same seed (the state really is resident)
+    sim = native.Sim(pkg.Lattice(edges).graph(), 5, 42)
+    sim.sweeps([0.4] * 10)
+    assert (sim.states() == s1).all()
+    en, st = ci.run_monte_carlo_sampling(0.4, 6, None, None, None, None, 2, 3)
+    assert en.shape == (5, 2) and st.shape == (5, 2, 64)
+    sim.sweeps([0.4] * (2 + 6))
+    assert (st[:, 1] == sim.states()).all() and (ci.get_states() == st[:, 1]).all()
+    g = oracle.Graph(edges)
+    assert en[2, 1] == g.energy(st[2, 1])
+    # add_graph keeps the existing experiments and appends one with the given state
+    init = np.arange(64) % 2 == 0
+    ci.add_graph(init)
+    s2 = ci.get_states()
+    assert s2.shape == (6, 64) and (s2[:5] == st[:, 1]).all() and (s2[5] == init).all()
+    with pytest.raises(NotImplementedError):
+        ci.run_monte_carlo(0.4, 1, 5)
+    cb = pkg.ClassicIsing([((0, 1), 1.0), ((1, 2), 1.0)], 0.7, 2000, 3)   # longitudinal field
+    cb.run_monte_carlo(0.5, 200)
+    mean, sd, mag = _exact([((0, 1), 1.0), ((1, 2), 1.0)], 3, 0.5, [0.7] * 3)
+    assert abs(cb.get_energies().mean() - mean) < 4 * sd / np.sqrt(2000)
