@@ -111,7 +111,7 @@ __device__ __forceinline__ void vadd(uint32_t (&acc)[NR], const uint32_t (&x)[NX
     }
 }
 
-constexpr int NS_NR = 16;  // block-level counter planes: up to 65535 per replica and block
+constexpr int NS_NR = 20;  // block-level counter planes: 256 threads x 1023 fits 18 bits
 
 // Block-wide reduction of per-thread vertical counters (NP planes, V replica words per thread,
 // block = (wx, by)) into per-experiment integers: bit-sliced tree through shared memory, then
@@ -158,15 +158,17 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
         unsigned long long* o = out + (size_t)(w0 + c) * 32;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {  // SWAR: bits g, g+8, g+16, g+24 in four byte lanes
-            uint32_t lo = 0, hi = 0;
+            uint32_t lo = 0, hi = 0, top = 0;
 #pragma unroll
             for (int l = 0; l < 8; ++l) {
                 lo += ((acc[l] >> g) & 0x01010101u) << l;
                 hi += ((acc[l + 8] >> g) & 0x01010101u) << l;
+                if (l + 16 < NS_NR) top += ((acc[l + 16] >> g) & 0x01010101u) << l;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t cnt = ((lo >> (8 * k)) & 0xFFu) | (((hi >> (8 * k)) & 0xFFu) << 8);
+                const uint32_t cnt = ((lo >> (8 * k)) & 0xFFu) | (((hi >> (8 * k)) & 0xFFu) << 8) |
+                                     (((top >> (8 * k)) & 0xFFu) << 16);
                 if (cnt) atomicAdd(o + g + 8 * k, (unsigned long long)cnt);
             }
         }
@@ -310,7 +312,7 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
 #pragma unroll
             for (int v = 0; v < V; ++v) vc[v].clear();
         }
-        if (w < W)
+        int pending = 0;  // block-uniform count of accumulated sites per thread
         for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
             const uint32_t z = row / Ly, y = row - z * Ly;
             const uint32_t p = (y + z + c) & 1u;
@@ -326,7 +328,9 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                 n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
                 n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
             }
-            for (uint32_t xh = threadIdx.y; xh < Lxh; xh += blockDim.y) {
+            for (uint32_t xh0 = 0; xh0 < Lxh; xh0 += blockDim.y) {
+                const uint32_t xh = xh0 + threadIdx.y;
+                if (xh < Lxh && w < W) {
                 const uint32_t xs = p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
                 uint32_t m[2 * DIM];
 #pragma unroll
@@ -373,6 +377,15 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                     }
                 }
                 store_words<V>(o_c + i, s);
+                }
+                if constexpr (ACC) {
+                    if (++pending == SW_MAX_ITEMS) {  // counters full: reduce and start over
+                        block_reduce_vcount<SW_NP, V>(vc, sm, nsat, w0, W);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) vc[v].clear();
+                        pending = 0;
+                    }
+                }
             }
         }
         if constexpr (ACC) block_reduce_vcount<SW_NP, V>(vc, sm, nsat, w0, W);
@@ -396,10 +409,7 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     // fused accumulation: persistent blocks so that the per-block reduction is amortised, but
     // never more sites per thread than the SW_NP-plane counters can hold
     if (block.y < (unsigned)V) block.y = V;
-    const uint32_t per_row = (L.Lxh + block.y - 1) / block.y;
     uint64_t g = 148ull * ISING_ACC_MIN_BLOCKS;
-    const uint64_t need = ((uint64_t)L.rows * per_row + SW_MAX_ITEMS - 1) / SW_MAX_ITEMS;
-    if (g < need) g = need;
     if (g > L.rows) g = L.rows;
     const int nthreads = block.x * block.y;
     const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
@@ -519,7 +529,8 @@ k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ 
         VCount<NS_NP> vc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) vc[v].clear();
-        if (w < W) {
+        int pending = 0;
+        {
             for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
                 const uint32_t z = row / Ly, y = row - z * Ly;
                 const uint32_t p = (y + z) & 1u;
@@ -535,7 +546,9 @@ k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ 
                     n_zm = oth + (size_t)(zm * Ly + y) * rowlen;
                     n_zp = oth + (size_t)(zp * Ly + y) * rowlen;
                 }
-                for (uint32_t xh = threadIdx.y; xh < Lxh; xh += by) {
+                for (uint32_t xh0 = 0; xh0 < Lxh; xh0 += by) {
+                    const uint32_t xh = xh0 + threadIdx.y;
+                    if (xh < Lxh && w < W) {
                     const uint32_t xs =
                         p ? (xh + 1 == Lxh ? 0 : xh + 1) : (xh == 0 ? Lxh - 1 : xh - 1);
                     const uint32_t i = xh * W + w;
@@ -563,6 +576,13 @@ k_nsat_stencil(const uint32_t* __restrict__ spins, const uint32_t* __restrict__ 
                         count_sat<DIM>(a, b0, b1, b2);
                         vc[v].add3(b0, b1, b2);
                     }
+                    }
+                    if (++pending == NS_MAX_ITEMS) {
+                        block_reduce_vcount<NS_NP, V>(vc, sm, nsat, w0, W);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) vc[v].clear();
+                        pending = 0;
+                    }
                 }
             }
         }
@@ -576,13 +596,8 @@ static int nsat_dispatch(const uint32_t* spins, const uint32_t* jmask, const Lay
     dim3 grid, block;
     stencil_block_shape(lay, V, &grid, &block, false);
     if (block.y < (unsigned)V) block.y = V;  // the reduction needs >= one thread per word column
-    // every thread may accumulate at most NS_MAX_ITEMS sites before its counters overflow
-    const uint32_t per_row = (lay.Lxh + block.y - 1) / block.y;
-    uint64_t g = 148ull * 2;
-    const uint64_t need = ((uint64_t)lay.rows * per_row + NS_MAX_ITEMS - 1) / NS_MAX_ITEMS;
-    if (g < need) g = need;
+    uint64_t g = 148ull * 2;  // persistent; counters are reduced every NS_MAX_ITEMS sites
     if (g > lay.rows) g = lay.rows;
-    if ((uint64_t)((lay.rows + g - 1) / g) * per_row > NS_MAX_ITEMS) return -1;
     grid = dim3((unsigned)g, 1, 1);
     const int nthreads = block.x * block.y;
     const int planes = NS_NP * V > NS_NR ? NS_NP * V : NS_NR;
