@@ -41,6 +41,10 @@ WORKLOADS = {
     "c2": dict(dims=(4096, 4096), pmj=False, j0=-1.0, replicas=1024, sweeps=20, beta=(0.43, 0.43),
                desc="2D square ferromagnet 4096x4096 checkerboard, 1024 experiments/GPU, "
                     "beta=0.43, 20 sweeps/step"),
+    "c4": dict(kind="tempering", n=1_000_000, degree=3, replicas=64, sweeps=100, swap_every=10,
+               beta=(0.1, 1.5), dims=(1_000_000,), pmj=False, j0=-1.0,
+               desc="random 3-regular graph N=1e6 (greedy colouring), parallel tempering 64 betas "
+                    "geometric in [0.1, 1.5], swap every 10 sweeps, 100 sweeps/step, one ladder per GPU"),
     "tiny": dict(dims=(16, 16, 16), pmj=True, j0=1.0, replicas=64, sweeps=20, beta=(0.1, 1.2),
                  desc="3D +-J L=16, 64 replicas (CI-size)"),
 }
@@ -198,6 +202,73 @@ def run_reference(args, w, world, rank):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def run_tempering(args, w, world, rank, local):
+    """config 4: one temperature ladder per GPU (a temperature is one replica bit, so 64 betas
+    are 2 words per site); wall-clock timed with device synchronisation around K steps."""
+    import torch
+
+    import pyisingmontecarlo_b200 as pkg
+    from pyisingmontecarlo_b200 import _native as nat
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    rng = np.random.default_rng(2026)
+    n, d = w["n"], w["degree"]
+    while True:
+        stubs = np.repeat(np.arange(n, dtype=np.int64), d)
+        rng.shuffle(stubs)
+        a, b = stubs[0::2], stubs[1::2]
+        key = np.minimum(a, b) * n + np.maximum(a, b)
+        if not (a == b).any() and len(np.unique(key)) == len(key):
+            break
+    lat = pkg.Lattice.from_arrays(a, b, np.full(len(a), w["j0"]), device=local)
+    g = lat.graph()
+    betas = np.geomspace(w["beta"][0], w["beta"][1], w["replicas"])
+    pt = nat.Tempering(g, betas, seed=7 + rank)
+
+    def step():
+        for _ in range(w["sweeps"] // w["swap_every"]):
+            en = pt.sweeps(w["swap_every"])
+            pt.swap_step(en)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    flips = world * w["replicas"] * n * w["sweeps"] * args.steps
+    # SURVEY 8(d): 2 spin bits + CSR indices streamed once per sweep per replica block
+    bpf = (2 * w["replicas"] / 8 + d * 4 + 4 + 4) / w["replicas"]
+    peak, peak_src = peaks()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "spin_flip_attempts_per_sec", "value": flips / dt, "unit": "flips/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-sliced (1 bit per spin per replica)", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + w["desc"], "ncolors": g.ncolors,
+                       "timing": "host clock around synchronised steps (includes swap decisions on the host)"},
+            "roofline": {"bound": "hbm", "achieved": bpf * flips / dt / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bpf * flips / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_sweep_general", "algorithmic_bytes_per_flip": bpf},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": None,
+            "total_swaps": pt.total_swaps(),
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args, w, world, rank, local):
     import torch
 
@@ -366,7 +437,11 @@ def main():
         w["desc"] += f" [sweeps/step overridden to {args.sweeps}]"
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
+        if w.get("kind") == "tempering":
+            raise SystemExit("--impl reference is defined for the lattice workloads")
         run_reference(args, w, world, rank)
+    elif w.get("kind") == "tempering":
+        run_tempering(args, w, world, rank, local)
     else:
         run_b200(args, w, world, rank, local)
 

@@ -45,6 +45,7 @@ typedef struct ising_ctx ising_ctx;
 typedef struct ising_graph ising_graph;
 typedef struct ising_sim ising_sim;
 typedef struct ising_pt ising_pt;
+typedef struct ising_strip ising_strip;
 
 /* ---- context ---------------------------------------------------------------------------- */
 ISING_API int ising_abi_version(void);
@@ -226,6 +227,27 @@ ISING_API int ising_pt_total_swaps(const ising_pt *pt, uint64_t *out);
  * states bool[R, timesteps / sampling_freq, nvars], energies[R]. */
 ISING_API int ising_pt_timesteps_sample(ising_pt *pt, uint64_t timesteps, uint64_t replica_swap_freq,
                               uint64_t sampling_freq, uint8_t *states, double *energies);
+
+/* ---- one large 2D lattice, domain-decomposed in row strips (BASELINE config 5) ---------- */
+/* The reference cannot run this at all (one experiment = one thread, lattice.rs:197-212; the
+ * 8.6e9-edge list would not fit).  One uniform-J periodic Lx x Ly lattice, spins bit-packed along
+ * x; this rank owns rows [row_lo, row_hi) plus two ghost rows.  Per colour phase the caller
+ * moves one boundary row (Lx/64 words) to each neighbouring strip -- get_boundary / set_ghost
+ * take host or device pointers, so the exchange can be NCCL send/recv between ranks -- or calls
+ * wrap_local when a single strip holds the whole lattice.  The random numbers are keyed by the
+ * global row, so any strip decomposition produces the same configuration. */
+ISING_API int ising_strip_create(ising_ctx *ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo, uint64_t row_hi,
+                       double j, uint64_t seed, ising_strip **out);
+ISING_API void ising_strip_destroy(ising_strip *s);
+ISING_API int ising_strip_configure(ising_strip *s, int planes, int rounds);
+ISING_API int ising_strip_set_all(ising_strip *s, int up);
+ISING_API int ising_strip_phase(ising_strip *s, int colour, double beta);
+ISING_API int ising_strip_get_boundary(ising_strip *s, int colour, int which, void *dst_words);
+ISING_API int ising_strip_set_ghost(ising_strip *s, int colour, int which, const void *src_words);
+ISING_API int ising_strip_wrap_local(ising_strip *s, int colour);
+ISING_API int ising_strip_observables(ising_strip *s, uint64_t *nsat_local, uint64_t *up_local);
+ISING_API int ising_strip_get_rows(ising_strip *s, uint8_t *rows_out /* (row_hi-row_lo)*Lx bool */);
+ISING_API int ising_strip_get_stats(ising_strip *s, uint64_t *launches, double *device_ms, int reset);
 
 #ifdef __cplusplus
 }

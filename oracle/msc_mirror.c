@@ -264,3 +264,70 @@ ORC_EXPORT int msc_mirror_pt(uint64_t nvars, uint64_t nedges, const uint64_t *ea
     mirror_free(&m);
     return 0;
 }
+
+/* One large 2D lattice, bit-packed along x (libising_b200 ising_strip_*, DESIGN.md "Single
+ * lattice"): same decision rule, but the word of a decision is (row y, colour c, j = (x/2)/32),
+ * its bit (x/2)%32, and the Philox counter (y, c << 30 | j, sweep, call).  state: bool[Ly, Lx]. */
+ORC_EXPORT int msc_mirror_single(uint64_t Lx, uint64_t Ly, double jcoupling, uint64_t seed, int K,
+                                 int rounds, int randomize, const double *betas, uint64_t nsweeps,
+                                 uint8_t *state, double *energies_per_sweep) {
+    if (Lx % 64 || (Ly & 1) || K < 1 || K > 8) return -1;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const double jabs = fabs(jcoupling);
+    const int anti = jcoupling > 0;
+    const uint64_t Wr = Lx / 64;
+    if (randomize)
+        for (uint64_t y = 0; y < Ly; ++y)
+            for (uint32_t c = 0; c < 2; ++c)
+                for (uint64_t j = 0; j < Wr; ++j) {
+                    uint32_t ctr[4] = {(uint32_t)y, (c << 30) | (uint32_t)j, 0u, 1u << 24};
+                    philox4x32(10, ctr, k0, k1);
+                    for (uint32_t b = 0; b < 32; ++b) {
+                        const uint64_t x = 2 * (32 * j + b) + ((y + c) & 1);
+                        state[y * Lx + x] = (ctr[0] >> b) & 1u;
+                    }
+                }
+    for (uint64_t t = 0; t < nsweeps; ++t) {
+        for (uint32_t c = 0; c < 2; ++c)
+            for (uint64_t y = 0; y < Ly; ++y)
+                for (uint64_t j = 0; j < Wr; ++j) {
+                    int tie_rank = 0;
+                    for (uint32_t b = 0; b < 32; ++b) {
+                        const uint64_t x = 2 * (32 * j + b) + ((y + c) & 1);
+                        const uint8_t s = state[y * Lx + x];
+                        const uint8_t nb[4] = {state[y * Lx + (x + 1) % Lx], state[y * Lx + (x + Lx - 1) % Lx],
+                                               state[((y + 1) % Ly) * Lx + x], state[((y + Ly - 1) % Ly) * Lx + x]};
+                        int nsat = 0;
+                        for (int k = 0; k < 4; ++k) nsat += anti ? (s != nb[k]) : (s == nb[k]);
+                        const int cls = 2 * nsat - 4;
+                        if (cls <= 0) { state[y * Lx + x] ^= 1; continue; }
+                        const uint64_t T = threshold(betas[t], 2.0 * jabs * (double)cls, K);
+                        const uint32_t gw = (c << 30) | (uint32_t)j;
+                        int decided = 0, accept = 0;
+                        for (int p = 0; p < K && !decided; ++p) {
+                            const uint32_t rb = (stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)p, k0, k1) >> b) & 1u;
+                            const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
+                            if (rb != tb) { decided = 1; accept = rb < tb; }
+                        }
+                        if (!decided) {
+                            const uint32_t v = stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)(K + tie_rank), k0, k1);
+                            accept = v < (uint32_t)(T & 0xFFFFFFFFull);
+                            ++tie_rank;
+                        }
+                        if (accept) state[y * Lx + x] ^= 1;
+                    }
+                }
+        if (energies_per_sweep) {
+            long long nsat = 0;
+            for (uint64_t y = 0; y < Ly; ++y)
+                for (uint64_t x = 0; x < Lx; ++x) {
+                    const uint8_t s = state[y * Lx + x];
+                    const uint8_t r = state[y * Lx + (x + 1) % Lx], d = state[((y + 1) % Ly) * Lx + x];
+                    nsat += anti ? (s != r) : (s == r);
+                    nsat += anti ? (s != d) : (s == d);
+                }
+            energies_per_sweep[t] = jabs * (double)(2 * (long long)(Lx * Ly) - 2 * nsat);
+        }
+    }
+    return 0;
+}

@@ -120,6 +120,17 @@ _SIGNATURES = {
     "ising_pt_get_local_states": (C.c_int, [_P, _P]),
     "ising_pt_total_swaps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ising_pt_timesteps_sample": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
+    "ising_strip_create": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(_P)]),
+    "ising_strip_destroy": (None, [_P]),
+    "ising_strip_configure": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ising_strip_set_all": (C.c_int, [_P, C.c_int]),
+    "ising_strip_phase": (C.c_int, [_P, C.c_int, C.c_double]),
+    "ising_strip_get_boundary": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ising_strip_set_ghost": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ising_strip_wrap_local": (C.c_int, [_P, C.c_int]),
+    "ising_strip_observables": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ising_strip_get_rows": (C.c_int, [_P, _P]),
+    "ising_strip_get_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_int]),
     "ising_replay": (C.c_int, [_P, _P, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
 }
 
@@ -464,6 +475,72 @@ class Tempering:
     def close(self):
         if getattr(self, "handle", None):
             lib().ising_pt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Strip:
+    """Rows [row_lo, row_hi) of one large bit-packed 2D lattice (ising_strip)."""
+
+    def __init__(self, ctx, Lx, Ly, row_lo, row_hi, j=-1.0, seed=0, planes=0, rounds=0):
+        self.ctx, self.Lx, self.Ly = ctx, int(Lx), int(Ly)
+        self.row_lo, self.row_hi = int(row_lo), int(row_hi)
+        self.words = self.Lx // 64
+        h = C.c_void_p()
+        check(lib().ising_strip_create(ctx.handle, self.Lx, self.Ly, self.row_lo, self.row_hi, float(j),
+                                       int(seed) & (2**64 - 1), C.byref(h)), ctx.handle)
+        self.handle = h
+        if planes or rounds:
+            check(lib().ising_strip_configure(h, int(planes), int(rounds)), ctx.handle)
+
+    def set_all(self, up):
+        check(lib().ising_strip_set_all(self.handle, int(bool(up))), self.ctx.handle)
+
+    def phase(self, colour, beta):
+        check(lib().ising_strip_phase(self.handle, int(colour), float(beta)), self.ctx.handle)
+
+    def get_boundary(self, colour, which, dst=None):
+        """dst: numpy uint32[words] (host) or an integer device pointer."""
+        if dst is None:
+            dst = np.empty(self.words, dtype=np.uint32)
+        p = ptr(dst) if isinstance(dst, np.ndarray) else C.c_void_p(int(dst))
+        check(lib().ising_strip_get_boundary(self.handle, int(colour), int(which), p), self.ctx.handle)
+        return dst
+
+    def set_ghost(self, colour, which, src):
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src, dtype=np.uint32)
+            p = ptr(src)
+        else:
+            p = C.c_void_p(int(src))
+        check(lib().ising_strip_set_ghost(self.handle, int(colour), int(which), p), self.ctx.handle)
+
+    def wrap_local(self, colour):
+        check(lib().ising_strip_wrap_local(self.handle, int(colour)), self.ctx.handle)
+
+    def observables(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib().ising_strip_observables(self.handle, C.byref(a), C.byref(b)), self.ctx.handle)
+        return int(a.value), int(b.value)
+
+    def rows(self):
+        out = np.empty((self.row_hi - self.row_lo, self.Lx), dtype=np.bool_)
+        check(lib().ising_strip_get_rows(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def stats(self, reset=False):
+        a, b = C.c_uint64(0), C.c_double(0)
+        check(lib().ising_strip_get_stats(self.handle, C.byref(a), C.byref(b), int(reset)), self.ctx.handle)
+        return {"launches": int(a.value), "device_ms": float(b.value)}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().ising_strip_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -1035,6 +1035,150 @@ int launch_energy_real(const uint32_t* spins, uint64_t nvars, uint32_t W, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// K7: one large 2D lattice bit-packed along x (config 5).  Same decision rule as the replica-
+// packed kernels; here the 32 bits of a word are 32 same-colour sites of one row, so the two
+// x neighbours are the other-colour word at the same index and that word funnel-shifted by one
+// bit (carry from the adjacent word).  Philox counter = (global row, colour << 30 | word, sweep,
+// call): a draw does not depend on how rows are split into strips.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint32_t r, uint32_t j) {
+    return ((size_t)c * (g.rows + 2) + r) * g.Wr + j;
+}
+
+template <int K, int ROUNDS>
+__global__ void __launch_bounds__(256)
+k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, uint32_t k0,
+              uint32_t k1, uint32_t antiferro, MscThresholds th) {
+    const uint64_t total = (uint64_t)g.rows * g.Wr;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(item / g.Wr) + 1, j = (uint32_t)(item % g.Wr);
+        const uint32_t y = g.row0 + r - 1;  // global row
+        const uint32_t p = (y + c) & 1u;
+        const uint32_t s = spins[strip_off(g, c, r, j)];
+        const uint32_t o = 1u - c;
+        const uint32_t nx = spins[strip_off(g, o, r, j)];
+        uint32_t nsh;
+        if (p) {  // x + 1 of bit b is bit b + 1 of the other colour: shift right, carry from j + 1
+            const uint32_t nb = spins[strip_off(g, o, r, j + 1 == g.Wr ? 0 : j + 1)];
+            nsh = __funnelshift_r(nx, nb, 1);
+        } else {  // x - 1 is bit b - 1: shift left, carry from j - 1
+            const uint32_t nb = spins[strip_off(g, o, r, j == 0 ? g.Wr - 1 : j - 1)];
+            nsh = __funnelshift_l(nb, nx, 1);
+        }
+        const uint32_t nu = spins[strip_off(g, o, r - 1, j)];
+        const uint32_t nd = spins[strip_off(g, o, r + 1, j)];
+        uint32_t a[4] = {~(s ^ nx ^ antiferro), ~(s ^ nsh ^ antiferro), ~(s ^ nu ^ antiferro),
+                         ~(s ^ nd ^ antiferro)};
+        uint32_t b0, b1, b2;
+        count_sat<2>(a, b0, b1, b2);
+        const uint32_t flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, y, (c << 30) | j,
+                                                          sweep, k0, k1);
+        spins[strip_off(g, c, r, j)] = s ^ flip;
+    }
+}
+
+int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
+    const uint64_t total = (uint64_t)a.g.rows * a.g.Wr;
+    if (total == 0) return 0;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 32) blocks = 148ull * 32;
+    const dim3 grid((unsigned)blocks), block(256);
+#define STRIP_LAUNCH(KK, RR)                                                                     \
+    k_strip_phase<KK, RR><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep, a.key0, a.key1, \
+                                                  a.antiferro, a.th)
+#define STRIP_ROUNDS(KK)                                                                         \
+    do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
+    switch (a.planes) {
+        case 4: STRIP_ROUNDS(4); break;
+        case 5: STRIP_ROUNDS(5); break;
+        case 6: STRIP_ROUNDS(6); break;
+        case 7: STRIP_ROUNDS(7); break;
+        case 8: STRIP_ROUNDS(8); break;
+        default: return -1;
+    }
+#undef STRIP_ROUNDS
+#undef STRIP_LAUNCH
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void k_strip_init_random(uint32_t* __restrict__ spins, StripGeom g, uint32_t k0,
+                                    uint32_t k1) {
+    const uint64_t total = 2ull * g.rows * g.Wr;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / ((uint64_t)g.rows * g.Wr));
+        const uint64_t rem = i - (uint64_t)c * g.rows * g.Wr;
+        const uint32_t r = (uint32_t)(rem / g.Wr) + 1, j = (uint32_t)(rem % g.Wr);
+        const u32x4 v = philox4x32<10>(g.row0 + r - 1, (c << 30) | j, 0u, TAG_INIT << 24, k0, k1);
+        spins[strip_off(g, c, r, j)] = v.x;
+    }
+}
+
+int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,
+                             cudaStream_t st) {
+    k_strip_init_random<<<148 * 8, 256, 0, st>>>(spins, g, key0, key1);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// per-lattice observables are plain popcounts in this layout
+__global__ void __launch_bounds__(256)
+k_strip_observables(const uint32_t* __restrict__ spins, StripGeom g, uint32_t antiferro,
+                    unsigned long long* __restrict__ acc) {
+    unsigned long long nsat = 0, up = 0;
+    const uint64_t total = (uint64_t)g.rows * g.Wr;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(item / g.Wr) + 1, j = (uint32_t)(item % g.Wr);
+        const uint32_t y = g.row0 + r - 1;
+        const uint32_t p = y & 1u;  // colour 0
+        const uint32_t s = spins[strip_off(g, 0, r, j)];
+        const uint32_t nx = spins[strip_off(g, 1, r, j)];
+        uint32_t nsh;
+        if (p) nsh = __funnelshift_r(nx, spins[strip_off(g, 1, r, j + 1 == g.Wr ? 0 : j + 1)], 1);
+        else nsh = __funnelshift_l(spins[strip_off(g, 1, r, j == 0 ? g.Wr - 1 : j - 1)], nx, 1);
+        const uint32_t nu = spins[strip_off(g, 1, r - 1, j)];
+        const uint32_t nd = spins[strip_off(g, 1, r + 1, j)];
+        nsat += __popc(~(s ^ nx ^ antiferro)) + __popc(~(s ^ nsh ^ antiferro)) +
+                __popc(~(s ^ nu ^ antiferro)) + __popc(~(s ^ nd ^ antiferro));
+        up += __popc(s) + __popc(nx);
+    }
+    for (int off = 16; off; off >>= 1) {
+        nsat += __shfl_xor_sync(0xFFFFFFFFu, nsat, off);
+        up += __shfl_xor_sync(0xFFFFFFFFu, up, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nsat) atomicAdd(acc, nsat);
+        if (up) atomicAdd(acc + 1, up);
+    }
+}
+
+int launch_strip_observables(const uint32_t* spins, const StripGeom& g, uint32_t antiferro,
+                             unsigned long long* acc, cudaStream_t st) {
+    k_strip_observables<<<148 * 4, 256, 0, st>>>(spins, g, antiferro, acc);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void k_strip_unpack(const uint32_t* __restrict__ spins, StripGeom g,
+                               uint8_t* __restrict__ out) {
+    const uint64_t Lx = 64ull * g.Wr;
+    const uint64_t total = (uint64_t)g.rows * Lx;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / Lx) + 1;
+        const uint32_t x = (uint32_t)(i % Lx);
+        const uint32_t y = g.row0 + r - 1;
+        const uint32_t c = (x + y) & 1u, xh = x >> 1;
+        out[i] = (uint8_t)((spins[strip_off(g, c, r, xh >> 5)] >> (xh & 31u)) & 1u);
+    }
+}
+
+int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st) {
+    k_strip_unpack<<<148 * 8, 256, 0, st>>>(spins, g, out_dev);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
 // state initialisation / import / export (not hot)
 // ------------------------------------------------------------------------------------------
 __global__ void k_init_random(uint32_t* __restrict__ spins, Layout L, uint32_t k0, uint32_t k1,

@@ -140,6 +140,32 @@ int launch_copy_strided_f64(const double* in, uint64_t E, double* out, uint64_t 
 int launch_transpose_hist_f64(const double* hist, uint64_t E, uint64_t cw, uint64_t nt, double* out,
                               cudaStream_t st);
 
+// ---- one large 2D lattice, bit-packed along x (config 5), uniform J, row strips ---------------
+// Colour-compacted: S[c][r][j], r = 0 .. rows+1 (r = 0 and rows+1 are ghost rows holding the
+// neighbouring strips' boundary rows), j = 0 .. Wr-1, Wr = Lx / 64 words per colour row; bit b
+// of word j of global row y is site x = 2 (32 j + b) + ((y + c) & 1).
+struct StripGeom {
+    uint32_t Wr;        // words per colour row
+    uint32_t rows;      // local rows
+    uint32_t row0;      // global index of local row 1
+    uint32_t Ly;        // global number of rows
+};
+struct StripSweepArgs {
+    uint32_t* spins;    // [2][rows + 2][Wr]
+    StripGeom g;
+    uint32_t colour, sweep, key0, key1, antiferro;
+    int planes, rounds;
+    MscThresholds th;   // classes: n_sat = 3 -> dE = 4|J|, n_sat = 4 -> dE = 8|J|
+};
+int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st);
+int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,
+                             cudaStream_t st);
+// acc[0] += satisfied bonds seen from colour-0 sites (every bond once), acc[1] += up spins
+int launch_strip_observables(const uint32_t* spins, const StripGeom& g, uint32_t antiferro,
+                             unsigned long long* acc, cudaStream_t st);
+// bool rows [rows][Lx] from the packed strip
+int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st);
+
 struct ReplayArgs {
     uint64_t E, N, A;
     const uint64_t* row;   // CSR offsets (nvars + 1)

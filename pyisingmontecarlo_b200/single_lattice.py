@@ -1,0 +1,117 @@
+"""One large 2D Ising lattice domain-decomposed in row strips (BASELINE config 5).
+
+The reference cannot express this workload (one experiment = one rayon task, lattice.rs:197-212,
+and a 65536^2 edge list would need 206 GB); it is the "one lattice too big for one thread"
+analogue of SURVEY.md 5.7.  Spins are bit-packed along x, every rank owns a block of rows, and
+per colour phase one boundary row (Lx/64 words, 8 KiB at Lx = 65536) goes to each neighbour:
+NCCL send/recv over NVLink between GPUs (gloo in the CPU tests), a device copy when one strip
+holds the whole lattice.
+"""
+import numpy as np
+
+from . import _native as nat
+from .tempering import shard_range
+
+
+def exchange_halos(strip, colour, rank, world, dist=None, group=None, device=None):
+    """Boundary rows of `colour` -> the neighbouring strips' ghost rows (periodic ring).
+
+    strip: .get_boundary(colour, which, dst), .set_ghost(colour, which, src), .wrap_local(colour),
+    .words.  With world == 1 the strip wraps onto itself."""
+    if world == 1:
+        strip.wrap_local(colour)
+        return
+    import torch
+
+    up, down = (rank - 1) % world, (rank + 1) % world
+    on_gpu = device is not None and device.type == "cuda"
+    kw = dict(dtype=torch.int32, device=device if on_gpu else "cpu")
+    send_top, send_bot = torch.empty(strip.words, **kw), torch.empty(strip.words, **kw)
+    recv_top, recv_bot = torch.empty(strip.words, **kw), torch.empty(strip.words, **kw)
+    if on_gpu:
+        strip.get_boundary(colour, 0, send_top.data_ptr())
+        strip.get_boundary(colour, 1, send_bot.data_ptr())
+    else:
+        send_top.copy_(torch.from_numpy(strip.get_boundary(colour, 0).view(np.int32)))
+        send_bot.copy_(torch.from_numpy(strip.get_boundary(colour, 1).view(np.int32)))
+    if world == 2:
+        # both neighbours are the same peer: order the four messages explicitly
+        ops = [dist.P2POp(dist.isend, send_top, up, group=group, tag=0),
+               dist.P2POp(dist.isend, send_bot, down, group=group, tag=1),
+               dist.P2POp(dist.irecv, recv_bot, down, group=group, tag=0),   # peer's top row
+               dist.P2POp(dist.irecv, recv_top, up, group=group, tag=1)]     # peer's bottom row
+    else:
+        ops = [dist.P2POp(dist.isend, send_top, up, group=group),
+               dist.P2POp(dist.isend, send_bot, down, group=group),
+               dist.P2POp(dist.irecv, recv_top, up, group=group),
+               dist.P2POp(dist.irecv, recv_bot, down, group=group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    if on_gpu:
+        torch.cuda.synchronize(device)
+        strip.set_ghost(colour, 0, recv_top.data_ptr())
+        strip.set_ghost(colour, 1, recv_bot.data_ptr())
+    else:
+        strip.set_ghost(colour, 0, recv_top.numpy().view(np.uint32))
+        strip.set_ghost(colour, 1, recv_bot.numpy().view(np.uint32))
+
+
+class SingleLattice2D:
+    """Periodic Lx x Ly lattice with uniform coupling j (j < 0 ferromagnetic, README.md:45-46)."""
+
+    def __init__(self, Lx, Ly=None, j=-1.0, seed=0, *, device=None, process_group=None, planes=0, rounds=0):
+        import torch.distributed as dist
+
+        self.Lx, self.Ly, self.j = int(Lx), int(Lx if Ly is None else Ly), float(j)
+        self._dist, self._group = dist, process_group
+        active = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.rank = dist.get_rank(process_group) if active else 0
+        self.world = dist.get_world_size(process_group) if active else 1
+        self.row_lo, self.row_hi = shard_range(self.Ly, self.rank, self.world)
+        ctx = nat.Context.get(device)
+        self._torch_device = None
+        if active:
+            import torch
+
+            self._torch_device = (torch.device("cuda", ctx.device)
+                                  if dist.get_backend(process_group) == "nccl" else torch.device("cpu"))
+        self.strip = nat.Strip(ctx, self.Lx, self.Ly, self.row_lo, self.row_hi, j, seed, planes, rounds)
+        self.nsites = self.Lx * self.Ly
+
+    def _exchange(self, colour):
+        exchange_halos(self.strip, colour, self.rank, self.world, self._dist, self._group, self._torch_device)
+
+    def set_all(self, up=True):
+        self.strip.set_all(up)
+
+    def sweeps(self, betas):
+        """One checkerboard sweep per beta: exchange the rows of the colour about to be read,
+        update the other colour."""
+        for beta in np.atleast_1d(np.asarray(betas, dtype=np.float64)):
+            for colour in (0, 1):
+                self._exchange(1 - colour)
+                self.strip.phase(colour, beta)
+
+    def _global_sums(self):
+        self._exchange(1)
+        nsat, up = self.strip.observables()
+        if self.world > 1:
+            import torch
+
+            t = torch.tensor([nsat, up], dtype=torch.int64, device=self._torch_device)
+            self._dist.all_reduce(t, group=self._group)
+            nsat, up = int(t[0]), int(t[1])
+        return nsat, up
+
+    def energy(self):
+        """E = sum J s s over the 2 Lx Ly bonds."""
+        nsat, _ = self._global_sums()
+        return abs(self.j) * (2 * self.nsites - 2 * nsat)
+
+    def magnetization(self):
+        _, up = self._global_sums()
+        return 2 * up - self.nsites
+
+    def local_rows(self):
+        """bool[row_hi - row_lo, Lx] of this rank's rows."""
+        return self.strip.rows()

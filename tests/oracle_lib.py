@@ -80,6 +80,9 @@ def lib():
         h.msc_mirror_pt.restype = C.c_int
         h.msc_mirror_pt.argtypes = [_U64, _U64, _P, _P, _P, _P, C.c_uint32, _U64, _P, _U64, C.c_int,
                                     C.c_int, _U64, _U64, _U64, _P, _P, _P, _P]
+        h.msc_mirror_single.restype = C.c_int
+        h.msc_mirror_single.argtypes = [_U64, _U64, C.c_double, _U64, C.c_int, C.c_int, C.c_int, _P,
+                                        _U64, _P, _P]
         _lib = h
     return _lib
 
@@ -294,6 +297,17 @@ def msc_mirror_pt(a, b, j, nvars, colors, betas, seed, timesteps, replica_swap_f
                              sampling_freq, _p(states), _p(energies), C.byref(swaps), _p(slots))
     assert rc == 0, rc
     return states.astype(bool), energies, int(swaps.value), slots
+
+
+def msc_mirror_single(Lx, Ly, j, seed, betas, planes=6, rounds=10, state=None):
+    """One bit-packed 2D lattice as the device runs it (oracle/msc_mirror.c: msc_mirror_single)."""
+    betas = np.ascontiguousarray(betas, dtype=np.float64)
+    st = np.zeros((Ly, Lx), dtype=np.uint8) if state is None else np.ascontiguousarray(state, dtype=np.uint8).copy()
+    en = np.zeros(len(betas))
+    rc = lib().msc_mirror_single(Lx, Ly, float(j), int(seed), planes, rounds, int(state is None),
+                                 _p(betas), len(betas), _p(st), _p(en))
+    assert rc == 0, rc
+    return en, st.astype(bool)
 
 
 # ---- lattice helpers shared by the tests ---------------------------------------------------
