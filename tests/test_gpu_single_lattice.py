@@ -62,3 +62,22 @@ def test_large_lattice_vs_onsager(native):
     ex = GOLD["onsager"]["b0.6"]
     assert abs(lat.energy() / L**2 - ex["e_per_site"]) < 1.5e-3
     assert abs(lat.magnetization() / L**2 - ex["m"]) < 1.5e-3
+
+
+def test_multi_gpu_parity_under_torchrun(native):
+    """Runs tests/multi_gpu_check.py on every visible GPU (skipped on a 1-GPU box)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(n, 4)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "multi_gpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
