@@ -45,6 +45,9 @@ WORKLOADS = {
                beta=(0.1, 1.5), dims=(1_000_000,), pmj=False, j0=-1.0,
                desc="random 3-regular graph N=1e6 (greedy colouring), parallel tempering 64 betas "
                     "geometric in [0.1, 1.5], swap every 10 sweeps, 100 sweeps/step, one ladder per GPU"),
+    "c5": dict(kind="single", dims=(65536, 65536), pmj=False, j0=-1.0, sweeps=20, beta=(0.44, 0.44), replicas=1,
+               desc="2D ferromagnet 65536x65536 single lattice bit-packed along x, row strips over the "
+                    "ranks with halo exchange, beta=0.44, 20 sweeps/step"),
     "tiny": dict(dims=(16, 16, 16), pmj=True, j0=1.0, replicas=64, sweeps=20, beta=(0.1, 1.2),
                  desc="3D +-J L=16, 64 replicas (CI-size)"),
 }
@@ -269,6 +272,61 @@ def run_tempering(args, w, world, rank, local):
         dist.destroy_process_group()
 
 
+def run_single(args, w, world, rank, local):
+    """config 5: ONE lattice split in row strips (strong scaling: total work fixed)."""
+    import torch
+
+    import pyisingmontecarlo_b200 as pkg
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    Lx, Ly = w["dims"]
+    lat = pkg.SingleLattice2D(Lx, Ly, j=w["j0"], seed=9, device=local, planes=args.planes, rounds=args.rounds)
+    betas = [w["beta"][0]] * w["sweeps"]
+    for _ in range(args.warmup):
+        lat.sweeps(betas)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    lat.strip.stats(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lat.sweeps(betas)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    kernel_ms = lat.strip.stats()["device_ms"]
+    if world > 1:
+        t = torch.tensor([dt, kernel_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, kernel_ms = float(t[0]), float(t[1])
+    flips = float(Lx) * Ly * w["sweeps"] * args.steps
+    launches = 2 * w["sweeps"] * args.steps
+    peak, peak_src = peaks()
+    bpf = 0.25
+    k_ms = kernel_ms / launches
+    if rank == 0:
+        print(json.dumps({
+            "metric": "spin_flip_attempts_per_sec", "value": flips / dt, "unit": "flips/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 bit-sliced (1 bit per spin)", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + w["desc"],
+                       "timing": "host clock around synchronised steps (kernels + halo exchange); "
+                                 "kernel_ms from CUDA events on the library stream",
+                       "l2": "512 MiB lattice, larger than L2"},
+            "kernel_only_value": flips / (kernel_ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": bpf * (flips / launches) / (k_ms * 1e-3) / 1e9 / world,
+                         "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+                         "frac": bpf * (flips / launches) / (k_ms * 1e-3) / 1e9 / world / peak,
+                         "kernel": "k_strip_phase (per GPU)", "kernel_ms": k_ms, "algorithmic_bytes_per_flip": bpf},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args, w, world, rank, local):
     import torch
 
@@ -437,11 +495,13 @@ def main():
         w["desc"] += f" [sweeps/step overridden to {args.sweeps}]"
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
-        if w.get("kind") == "tempering":
+        if w.get("kind") in ("tempering", "single"):
             raise SystemExit("--impl reference is defined for the lattice workloads")
         run_reference(args, w, world, rank)
     elif w.get("kind") == "tempering":
         run_tempering(args, w, world, rank, local)
+    elif w.get("kind") == "single":
+        run_single(args, w, world, rank, local)
     else:
         run_b200(args, w, world, rank, local)
 

@@ -190,13 +190,12 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
 template <int NCLS, int K, int ROUNDS>
 __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, uint32_t sel1,
                                                   const MscThresholds& th, uint32_t site,
-                                                  uint32_t gw, uint32_t sweep, uint32_t k0,
-                                                  uint32_t k1) {
+                                                  uint32_t gw, uint32_t sweep, const PhiloxKeys& pk) {
     constexpr int NCALL = K / 4 + 1;
     uint32_t r[NCALL * 4];
 #pragma unroll
     for (int q = 0; q < NCALL; ++q) {
-        const u32x4 o = philox4x32<ROUNDS>(site, gw, sweep, (uint32_t)q | (TAG_ACCEPT << 24), k0, k1);
+        const u32x4 o = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)q | (TAG_ACCEPT << 24), pk);
         r[4 * q + 0] = o.x;
         r[4 * q + 1] = o.y;
         r[4 * q + 2] = o.z;
@@ -230,8 +229,7 @@ __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, ui
         do {
             const int b = __ffs((int)eq) - 1;
             if ((j & 3) == 0 && j >= 4 * NCALL)
-                cur = philox4x32<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24),
-                                         k0, k1);
+                cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
             const int m = j & 3;
             const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
             uint32_t lo = ((sel0 >> b) & 1u) ? th.low[1] : th.low[0];
@@ -299,7 +297,7 @@ template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
 __global__ void __launch_bounds__(256, ACC ? ISING_ACC_MIN_BLOCKS : ISING_SWEEP_MIN_BLOCKS)
 k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                 const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
-                uint32_t k0, uint32_t k1, uint32_t gw0, uint32_t antiferro, MscThresholds th,
+                PhiloxKeys pk, uint32_t gw0, uint32_t antiferro, MscThresholds th,
                 unsigned long long* __restrict__ nsat) {
     extern __shared__ uint32_t sm[];
     constexpr int kUnrollV = ISING_SWEEP_UNROLL_V;
@@ -357,11 +355,10 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                     count_sat<DIM>(a, b0, b1, b2);
                     uint32_t flip;
                     if (DIM == 3)  // n_sat 4,5,6 -> dE = 4,8,12 |J|
-                        flip = msc_flip_mask<3, K, ROUNDS>(b2, b0, b1, th, site, gw0 + w + v, sweep,
-                                                           k0, k1);
+                        flip = msc_flip_mask<3, K, ROUNDS>(b2, b0, b1, th, site, gw0 + w + v, sweep, pk);
                     else  // n_sat 3,4 -> dE = 4,8 |J|
                         flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, site,
-                                                           gw0 + w + v, sweep, k0, k1);
+                                                           gw0 + w + v, sweep, pk);
                     s[v] ^= flip;
                     if constexpr (ACC) {
                         // a flipped spin turns its n_sat satisfied bonds into 2*DIM - n_sat
@@ -401,9 +398,10 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     uint32_t* own = a.spins + c * csz;
     const uint32_t* oth = a.spins + (1 - c) * csz;
     const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
+    const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
     if (!acc) {
         k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, false><<<grid, block, 0, st>>>(
-            own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th, nullptr);
+            own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.th, nullptr);
         return;
     }
     // fused accumulation: persistent blocks so that the per-block reduction is amortised, but
@@ -415,7 +413,7 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
     const size_t smem = (size_t)planes * nthreads * sizeof(uint32_t);
     k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, true><<<dim3((unsigned)g), block, smem, st>>>(
-        own, oth, jm, L, c, a.sweep, a.key0, a.key1, a.gw0, a.antiferro, a.th, a.nsat_out);
+        own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.th, a.nsat_out);
 }
 
 template <int DIM, bool PMJ, int K, int V>
@@ -1047,8 +1045,8 @@ __device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint
 
 template <int K, int ROUNDS>
 __global__ void __launch_bounds__(256)
-k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, uint32_t k0,
-              uint32_t k1, uint32_t antiferro, MscThresholds th) {
+k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, PhiloxKeys pk,
+              uint32_t antiferro, MscThresholds th) {
     const uint64_t total = (uint64_t)g.rows * g.Wr;
     for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
          item += (uint64_t)gridDim.x * blockDim.x) {
@@ -1073,7 +1071,7 @@ k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sw
         uint32_t b0, b1, b2;
         count_sat<2>(a, b0, b1, b2);
         const uint32_t flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, y, (c << 30) | j,
-                                                          sweep, k0, k1);
+                                                          sweep, pk);
         spins[strip_off(g, c, r, j)] = s ^ flip;
     }
 }
@@ -1085,8 +1083,8 @@ int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
     if (blocks > 148ull * 32) blocks = 148ull * 32;
     const dim3 grid((unsigned)blocks), block(256);
 #define STRIP_LAUNCH(KK, RR)                                                                     \
-    k_strip_phase<KK, RR><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep, a.key0, a.key1, \
-                                                  a.antiferro, a.th)
+    k_strip_phase<KK, RR><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,                 \
+                                                  philox_round_keys(a.key0, a.key1), a.antiferro, a.th)
 #define STRIP_ROUNDS(KK)                                                                         \
     do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {

@@ -48,4 +48,39 @@ ISING_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     return out;
 }
 
+// Round keys precomputed on the host (key schedule k += W per round): passed as a kernel
+// parameter they sit in the constant bank and feed LOP3 directly, instead of 2 integer adds per
+// round per thread.
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+
+inline PhiloxKeys philox_round_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys pk;
+    for (int r = 0; r < 10; ++r) {
+        pk.k[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        pk.k[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    return pk;
+}
+
+template <int ROUNDS>
+ISING_HD u32x4 philox4x32_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                               const PhiloxKeys& pk) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0;
+        const uint64_t p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk.k[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    u32x4 out = {c0, c1, c2, c3};
+    return out;
+}
+
 }  // namespace ising
