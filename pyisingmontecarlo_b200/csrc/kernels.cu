@@ -3,6 +3,8 @@
 // is not a contraction).
 #include "kernels.h"
 
+#include <stdlib.h>
+
 #include "../../include/ising_b200.h"
 #include "philox.h"
 
@@ -298,7 +300,8 @@ __global__ void __launch_bounds__(256, ACC ? ISING_ACC_MIN_BLOCKS : ISING_SWEEP_
 k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
                 const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
                 PhiloxKeys pk, uint32_t gw0, uint32_t antiferro, MscThresholds th,
-                unsigned long long* __restrict__ nsat) {
+                unsigned long long* __restrict__ nsat, uint32_t row_step, uint32_t step_y,
+                uint32_t step_z) {
     extern __shared__ uint32_t sm[];
     constexpr int kUnrollV = ISING_SWEEP_UNROLL_V;
     const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
@@ -311,8 +314,24 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
             for (int v = 0; v < V; ++v) vc[v].clear();
         }
         int pending = 0;  // block-uniform count of accumulated sites per thread
-        for (uint32_t row = blockIdx.x; row < L.rows; row += gridDim.x) {
-            const uint32_t z = row / Ly, y = row - z * Ly;
+        // Row walk without per-row integer division: the one-row-per-block launch reads (y, z)
+        // from its 2D block index; the persistent (ACC) launch divides once and then steps by
+        // the grid size with a carry.
+        uint32_t y, z, row;
+        if constexpr (ACC) {
+            row = blockIdx.x;
+            z = row / Ly;
+            y = row - z * Ly;
+        } else {
+            y = blockIdx.x;
+            z = blockIdx.y;
+            row = z * Ly + y;
+        }
+        for (; row < L.rows; row += row_step, y += step_y, z += step_z) {
+            if (y >= Ly) {
+                y -= Ly;
+                ++z;
+            }
             const uint32_t p = (y + z + c) & 1u;
             const uint32_t ym = y == 0 ? Ly - 1 : y - 1, yp = y + 1 == Ly ? 0 : y + 1;
             uint32_t* __restrict__ o_c = own + (size_t)row * rowlen;
@@ -400,20 +419,21 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
     const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
     if (!acc) {
-        k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, false><<<grid, block, 0, st>>>(
-            own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.th, nullptr);
+        const dim3 grid2(L.Ly, L.Lz > 65535u ? 65535u : L.Lz, 1);
+        k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, false><<<grid2, block, 0, st>>>(
+            own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.th, nullptr, L.rows, 0u, 0u);
         return;
     }
     // fused accumulation: persistent blocks so that the per-block reduction is amortised, but
     // never more sites per thread than the SW_NP-plane counters can hold
     if (block.y < (unsigned)V) block.y = V;
-    uint64_t g = 148ull * ISING_ACC_MIN_BLOCKS;
+    uint32_t g = 148u * ISING_ACC_MIN_BLOCKS;
     if (g > L.rows) g = L.rows;
     const int nthreads = block.x * block.y;
     const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
     const size_t smem = (size_t)planes * nthreads * sizeof(uint32_t);
-    k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, true><<<dim3((unsigned)g), block, smem, st>>>(
-        own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.th, a.nsat_out);
+    k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, true><<<dim3(g, 1, 1), block, smem, st>>>(
+        own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.th, a.nsat_out, g, g % L.Ly, g / L.Ly);
 }
 
 template <int DIM, bool PMJ, int K, int V>
