@@ -149,17 +149,27 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
 #pragma unroll
     for (int l = 0; l < NS_NR; ++l) sm[l * nthreads + tid] = acc[l];  // [plane][q][c]
     __syncthreads();
-    // stage B: one thread per column finishes the sum and transposes it to integers
-    if (tid < C && w0 + c < W) {
-        for (uint32_t qq = 1; qq < Q; ++qq) {
+    // stage B1: tree over the Q parts of every column (all threads of the surviving parts work)
+    for (uint32_t half = Q >> 1; half >= 1; half >>= 1) {
+        if (q < half) {
             uint32_t x[NS_NR];
 #pragma unroll
-            for (int l = 0; l < NS_NR; ++l) x[l] = sm[l * nthreads + qq * C + c];
+            for (int l = 0; l < NS_NR; ++l) x[l] = sm[l * nthreads + (q + half) * C + c];
             vadd<NS_NR, NS_NR>(acc, x);
+#pragma unroll
+            for (int l = 0; l < NS_NR; ++l) sm[l * nthreads + tid] = acc[l];
+        }
+        __syncthreads();
+    }
+    // stage B2: SWAR bit-transpose of the column totals (part 0), byte-lane group g per thread:
+    // bits g, g+8, g+16, g+24 of the planes land in four byte lanes; 4 integer atomics each
+    if (w0 + c < W) {
+        if (q != 0) {
+#pragma unroll
+            for (int l = 0; l < NS_NR; ++l) acc[l] = sm[l * nthreads + c];
         }
         unsigned long long* o = out + (size_t)(w0 + c) * 32;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {  // SWAR: bits g, g+8, g+16, g+24 in four byte lanes
+        for (uint32_t g = q; g < 8; g += Q) {
             uint32_t lo = 0, hi = 0, top = 0;
 #pragma unroll
             for (int l = 0; l < 8; ++l) {
