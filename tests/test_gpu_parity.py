@@ -111,6 +111,17 @@ def test_msc_2d_variants_match_mirror(native, oracle, pkg):
     _mirror_check(native, oracle, g, 5, 44, betas, 6, 10, init=init)
 
 
+def test_many_replica_words_match_mirror(native, oracle, pkg):
+    """More replica words than one block covers (chunk loop over words, all vector widths):
+    E = 4100 -> 129 words (scalar path), 4128 -> 129.. words, 8192 -> 256 words (128-bit path)."""
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (4, 4, 4), j0=1.0, pmj=True, j_seed=8)
+    for E in (4100, 4160, 8192):
+        _mirror_check(native, oracle, g, E, 17, [0.6, 1.0], 6, 10)
+    g2 = native.Graph.torus(ctx, (4, 6), j0=-1.0)
+    _mirror_check(native, oracle, g2, 2080, 18, [0.44, 0.5], 6, 10)
+
+
 def test_edge_list_torus_is_recognised_and_equal(native, oracle, pkg):
     """The same lattice through Lattice(edges) (config-1 labelling) and through the additive
     torus constructor takes the stencil path and gives identical bits."""
