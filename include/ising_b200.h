@@ -50,6 +50,9 @@ typedef struct ising_strip ising_strip;
 /* ---- context ---------------------------------------------------------------------------- */
 ISING_API int ising_abi_version(void);
 ISING_API int ising_ctx_create(int device, ising_ctx **out);
+/* Same, on the caller's CUDA stream (cudaStream_t passed as void*): launches are then ordered
+ * with the caller's own kernels and NCCL calls without host synchronisation. */
+ISING_API int ising_ctx_create_on_stream(int device, void *cuda_stream, ising_ctx **out);
 ISING_API void ising_ctx_destroy(ising_ctx *ctx);
 ISING_API const char *ising_last_error(const ising_ctx *ctx);
 
@@ -242,6 +245,12 @@ ISING_API void ising_strip_destroy(ising_strip *s);
 ISING_API int ising_strip_configure(ising_strip *s, int planes, int rounds);
 ISING_API int ising_strip_set_all(ising_strip *s, int up);
 ISING_API int ising_strip_phase(ising_strip *s, int colour, double beta);
+/* local rows [r0, r1) of a colour phase; sync = 0 only enqueues on the context's stream */
+ISING_API int ising_strip_phase_rows(ising_strip *s, int colour, double beta, uint64_t r0, uint64_t r1,
+                           int advance_sweep, int sync);
+/* device-side halo staging without host wait: dir 0 = boundary rows -> buf_dev[2*Lx/64 words],
+ * dir 1 = buf_dev -> ghost rows */
+ISING_API int ising_strip_halo_async(ising_strip *s, int colour, int dir, void *buf_dev);
 ISING_API int ising_strip_get_boundary(ising_strip *s, int colour, int which, void *dst_words);
 ISING_API int ising_strip_set_ghost(ising_strip *s, int colour, int which, const void *src_words);
 ISING_API int ising_strip_wrap_local(ising_strip *s, int colour);

@@ -79,6 +79,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "ising_abi_version": (C.c_int, []),
     "ising_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "ising_ctx_create_on_stream": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "ising_ctx_destroy": (None, [_P]),
     "ising_last_error": (C.c_char_p, [_P]),
     "ising_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
@@ -125,6 +126,8 @@ _SIGNATURES = {
     "ising_strip_configure": (C.c_int, [_P, C.c_int, C.c_int]),
     "ising_strip_set_all": (C.c_int, [_P, C.c_int]),
     "ising_strip_phase": (C.c_int, [_P, C.c_int, C.c_double]),
+    "ising_strip_phase_rows": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint64, C.c_uint64, C.c_int, C.c_int]),
+    "ising_strip_halo_async": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ising_strip_get_boundary": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ising_strip_set_ghost": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ising_strip_wrap_local": (C.c_int, [_P, C.c_int]),
@@ -240,10 +243,15 @@ class Context:
 
     _cache = {}
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, stream=None):
+        """stream: a cudaStream_t as integer (e.g. torch.cuda.current_stream().cuda_stream) to run
+        on the caller's stream instead of a private one."""
         self.device = int(device)
         h = C.c_void_p()
-        check(lib().ising_ctx_create(self.device, C.byref(h)), None)
+        if stream is None:
+            check(lib().ising_ctx_create(self.device, C.byref(h)), None)
+        else:
+            check(lib().ising_ctx_create_on_stream(self.device, C.c_void_p(int(stream)), C.byref(h)), None)
         self.handle = h
 
     @classmethod
@@ -503,6 +511,14 @@ class Strip:
 
     def phase(self, colour, beta):
         check(lib().ising_strip_phase(self.handle, int(colour), float(beta)), self.ctx.handle)
+
+    def phase_rows(self, colour, beta, r0, r1, advance=False, sync=False):
+        check(lib().ising_strip_phase_rows(self.handle, int(colour), float(beta), int(r0), int(r1),
+                                           int(advance), int(sync)), self.ctx.handle)
+
+    def halo_async(self, colour, direction, buf_ptr):
+        check(lib().ising_strip_halo_async(self.handle, int(colour), int(direction),
+                                           C.c_void_p(int(buf_ptr))), self.ctx.handle)
 
     def get_boundary(self, colour, which, dst=None):
         """dst: numpy uint32[words] (host) or an integer device pointer."""

@@ -28,6 +28,7 @@ static thread_local std::string g_global_error;
 struct ising_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int sm_count = 0;
@@ -164,7 +165,20 @@ extern "C" const char* ising_last_error(const ising_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_global_error.c_str();
 }
 
+static int ctx_create_impl(int device, cudaStream_t external, bool use_external, ising_ctx** out);
+
 extern "C" int ising_ctx_create(int device, ising_ctx** out) {
+    return ctx_create_impl(device, nullptr, false, out);
+}
+
+// Same, but every launch and copy of this context goes to the caller's stream (e.g. torch's
+// current stream): work is then ordered with the caller's own kernels and NCCL calls without
+// host synchronisation.
+extern "C" int ising_ctx_create_on_stream(int device, void* cuda_stream, ising_ctx** out) {
+    return ctx_create_impl(device, (cudaStream_t)cuda_stream, true, out);
+}
+
+static int ctx_create_impl(int device, cudaStream_t external, bool use_external, ising_ctx** out) {
     if (!out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -185,7 +199,12 @@ extern "C" int ising_ctx_create(int device, ising_ctx** out) {
     std::unique_ptr<ising_ctx> ctx(new ising_ctx);
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (use_external) {
+        ctx->stream = external;
+        ctx->owns_stream = false;
+    } else {
+        CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    }
     CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev0));
     CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev1));
     *out = ctx.release();
@@ -197,7 +216,7 @@ extern "C" void ising_ctx_destroy(ising_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     for (void* p : ctx->scratch) cudaFree(p);
     for (auto& b : ctx->free_bufs) cudaFree(b.first);
     delete ctx;
@@ -1274,11 +1293,14 @@ extern "C" int ising_strip_set_all(ising_strip* s, int up) {
     return ISING_OK;
 }
 
-// one colour phase; the ghost rows of the OTHER colour must hold the neighbours' boundary rows.
-// The sweep counter advances after colour 1.
-extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
+// Local rows [r0, r1) of one colour phase; the ghost rows of the OTHER colour must hold the
+// neighbours' boundary rows when r0 == 0 or r1 == rows.  sync = 0 only enqueues (no host wait,
+// no event timing); advance != 0 bumps the sweep counter (call it on the last piece of colour 1).
+extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
+                                      int advance, int sync) {
     if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
     ising_ctx* ctx = s->ctx;
+    if (r0 > r1 || r1 > s->g.rows) return fail(ctx, ISING_E_INVALID, "bad row range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     StripSweepArgs a;
     a.spins = s->d_spins;
@@ -1290,6 +1312,8 @@ extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
     a.antiferro = s->j > 0 ? 0xFFFFFFFFu : 0u;
     a.planes = s->planes;
     a.rounds = s->rounds;
+    a.r_begin = (uint32_t)r0;
+    a.r_count = (uint32_t)(r1 - r0);
     memset(&a.th, 0, sizeof a.th);
     for (int c = 0; c < 2; ++c) {
         const uint64_t T = threshold64(beta, 4.0 * (c + 1) * fabs(s->j), s->planes);
@@ -1297,17 +1321,25 @@ extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
             a.th.plane[c][pl] = ((T >> (s->planes + 31 - pl)) & 1ull) ? 0xFFFFFFFFu : 0u;
         a.th.low[c] = (uint32_t)(T & 0xFFFFFFFFull);
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (sync) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (launch_strip_phase(a, ctx->stream) < 0)
         return fail(ctx, ISING_E_CUDA, "strip phase launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f;
-    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    s->device_ms += ms;
-    s->launches++;
-    if (colour == 1) s->sweep++;
+    if (a.r_count) s->launches++;
+    if (sync) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        s->device_ms += ms;
+    }
+    if (advance) s->sweep++;
     return ISING_OK;
+}
+
+// one whole colour phase, blocking; the sweep counter advances after colour 1
+extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    return ising_strip_phase_rows(s, colour, beta, 0, s->g.rows, colour == 1, 1);
 }
 
 static uint32_t* strip_row_ptr(ising_strip* s, int colour, uint32_t r) {
@@ -1322,6 +1354,26 @@ extern "C" int ising_strip_get_boundary(ising_strip* s, int colour, int which, v
     CUDA_TRY(ctx, cudaMemcpyAsync(dst, strip_row_ptr(s, colour, which ? s->g.rows : 1),
                                   (size_t)s->g.Wr * 4, cudaMemcpyDefault, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// Device-to-device halo staging without a host wait, for contexts created on the caller's
+// stream: dir = 0 copies both boundary rows of `colour` into buf_dev[0..Wr) (first row) and
+// buf_dev[Wr..2Wr) (last row); dir = 1 copies buf_dev[0..Wr) into the ghost row above the first
+// row and buf_dev[Wr..2Wr) into the ghost row below the last row.
+extern "C" int ising_strip_halo_async(ising_strip* s, int colour, int dir, void* buf_dev) {
+    if (!s || !buf_dev || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)s->g.Wr * 4;
+    uint8_t* b = (uint8_t*)buf_dev;
+    if (dir == 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(b, strip_row_ptr(s, colour, 1), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(b + nb, strip_row_ptr(s, colour, s->g.rows), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, 0), b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.rows + 1), b + nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return ISING_OK;
 }
 

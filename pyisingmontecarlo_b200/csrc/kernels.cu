@@ -1076,11 +1076,11 @@ __device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint
 template <int K, int ROUNDS>
 __global__ void __launch_bounds__(256)
 k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, PhiloxKeys pk,
-              uint32_t antiferro, MscThresholds th) {
-    const uint64_t total = (uint64_t)g.rows * g.Wr;
+              uint32_t antiferro, MscThresholds th, uint32_t r_begin, uint32_t r_count) {
+    const uint64_t total = (uint64_t)r_count * g.Wr;  // local rows [r_begin, r_begin + r_count)
     for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
          item += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(item / g.Wr) + 1, j = (uint32_t)(item % g.Wr);
+        const uint32_t r = r_begin + (uint32_t)(item / g.Wr) + 1, j = (uint32_t)(item % g.Wr);
         const uint32_t y = g.row0 + r - 1;  // global row
         const uint32_t p = (y + c) & 1u;
         const uint32_t s = spins[strip_off(g, c, r, j)];
@@ -1107,14 +1107,15 @@ k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sw
 }
 
 int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
-    const uint64_t total = (uint64_t)a.g.rows * a.g.Wr;
+    const uint64_t total = (uint64_t)a.r_count * a.g.Wr;
     if (total == 0) return 0;
     uint64_t blocks = (total + 255) / 256;
     if (blocks > 148ull * 32) blocks = 148ull * 32;
     const dim3 grid((unsigned)blocks), block(256);
 #define STRIP_LAUNCH(KK, RR)                                                                     \
     k_strip_phase<KK, RR><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,                 \
-                                                  philox_round_keys(a.key0, a.key1), a.antiferro, a.th)
+                                                  philox_round_keys(a.key0, a.key1), a.antiferro, a.th, \
+                                                  a.r_begin, a.r_count)
 #define STRIP_ROUNDS(KK)                                                                         \
     do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {

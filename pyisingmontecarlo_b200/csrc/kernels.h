@@ -156,6 +156,7 @@ struct StripSweepArgs {
     uint32_t colour, sweep, key0, key1, antiferro;
     int planes, rounds;
     MscThresholds th;   // classes: n_sat = 3 -> dE = 4|J|, n_sat = 4 -> dE = 8|J|
+    uint32_t r_begin, r_count;  // local rows to update (interior / boundary split)
 };
 int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st);
 int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,

@@ -68,15 +68,31 @@ class SingleLattice2D:
         self.rank = dist.get_rank(process_group) if active else 0
         self.world = dist.get_world_size(process_group) if active else 1
         self.row_lo, self.row_hi = shard_range(self.Ly, self.rank, self.world)
-        ctx = nat.Context.get(device)
         self._torch_device = None
-        if active:
+        self._async = False
+        if active and dist.get_backend(process_group) == "nccl":
+            # multi-GPU: run the library on torch's current stream, so that halo copies, NCCL
+            # send/recv and the sweep kernels are ordered on the device without host waits
             import torch
 
-            self._torch_device = (torch.device("cuda", ctx.device)
-                                  if dist.get_backend(process_group) == "nccl" else torch.device("cpu"))
+            dev = int(device) if device is not None else int(torch.cuda.current_device())
+            self._torch_device = torch.device("cuda", dev)
+            ctx = nat.Context(dev, stream=torch.cuda.current_stream(self._torch_device).cuda_stream)
+            self._async = True
+        else:
+            ctx = nat.Context.get(device)
+            if active:
+                import torch
+
+                self._torch_device = torch.device("cpu")
         self.strip = nat.Strip(ctx, self.Lx, self.Ly, self.row_lo, self.row_hi, j, seed, planes, rounds)
         self.nsites = self.Lx * self.Ly
+        if self._async:
+            import torch
+
+            w = self.strip.words
+            self._send = torch.empty(2 * w, dtype=torch.int32, device=self._torch_device)
+            self._recv = torch.empty(2 * w, dtype=torch.int32, device=self._torch_device)
 
     def _exchange(self, colour):
         exchange_halos(self.strip, colour, self.rank, self.world, self._dist, self._group, self._torch_device)
@@ -84,15 +100,55 @@ class SingleLattice2D:
     def set_all(self, up=True):
         self.strip.set_all(up)
 
+    def _phase_overlapped(self, colour, beta):
+        """Stage the boundary rows, start the NCCL exchange, update the interior rows while it
+        is in flight, then the two boundary rows once the ghosts have arrived.  Everything is
+        enqueued on one stream; the host never waits."""
+        dist, w, other = self._dist, self.strip.words, 1 - colour
+        rows = self.row_hi - self.row_lo
+        up, down = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        self.strip.halo_async(other, 0, self._send.data_ptr())
+        send_top, send_bot = self._send[:w], self._send[w:]
+        recv_top, recv_bot = self._recv[:w], self._recv[w:]
+        if self.world == 2:   # both neighbours are the same peer: match messages by order
+            ops = [dist.P2POp(dist.isend, send_top, up, group=self._group),
+                   dist.P2POp(dist.isend, send_bot, down, group=self._group),
+                   dist.P2POp(dist.irecv, recv_bot, down, group=self._group),
+                   dist.P2POp(dist.irecv, recv_top, up, group=self._group)]
+        else:
+            ops = [dist.P2POp(dist.isend, send_top, up, group=self._group),
+                   dist.P2POp(dist.isend, send_bot, down, group=self._group),
+                   dist.P2POp(dist.irecv, recv_top, up, group=self._group),
+                   dist.P2POp(dist.irecv, recv_bot, down, group=self._group)]
+        reqs = dist.batch_isend_irecv(ops)
+        last = colour == 1
+        if rows > 2:
+            self.strip.phase_rows(colour, beta, 1, rows - 1)           # interior: no ghost rows read
+        for r in reqs:
+            r.wait()                                                    # stream-side wait for NCCL
+        self.strip.halo_async(other, 1, self._recv.data_ptr())
+        if rows > 2:
+            self.strip.phase_rows(colour, beta, 0, 1)
+            self.strip.phase_rows(colour, beta, rows - 1, rows, advance=last)
+        else:
+            self.strip.phase_rows(colour, beta, 0, rows, advance=last)
+
     def sweeps(self, betas):
         """One checkerboard sweep per beta: exchange the rows of the colour about to be read,
         update the other colour."""
         for beta in np.atleast_1d(np.asarray(betas, dtype=np.float64)):
             for colour in (0, 1):
-                self._exchange(1 - colour)
-                self.strip.phase(colour, beta)
+                if self._async:
+                    self._phase_overlapped(colour, beta)
+                else:
+                    self._exchange(1 - colour)
+                    self.strip.phase(colour, beta)
 
     def _global_sums(self):
+        if self._async:
+            import torch
+
+            torch.cuda.current_stream(self._torch_device).synchronize()
         self._exchange(1)
         nsat, up = self.strip.observables()
         if self.world > 1:
