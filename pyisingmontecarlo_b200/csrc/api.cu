@@ -697,7 +697,7 @@ static int sim_one_sweep_general(ising_sim* s, double beta) {
         for (size_t k = 0; k < g->gen_groups.size(); ++k) {
             if (g->gen_group_color[k] != c) continue;
             const GenGroup& gg = g->gen_groups[k];
-            if (gg.deg == 0) continue;  // isolated site: dE = 0, the reference flips it every time
+            // (an isolated site has dE = 0 and, as in the reference's dE <= 0 rule, always flips)
             if (!s->perbeta) fill_gen_thresholds(h.jabs, beta, s->planes, gg.deg, &a.th);
             const int n = launch_sweep_general(a, gg, ctx->stream);
             if (n < 0) return fail(ctx, ISING_E_CUDA, "general sweep launch failed: %s",

@@ -86,6 +86,19 @@ def test_irregular_pmj_graph_matches_mirror(native, oracle, pkg):
     _check_vs_mirror(native, oracle, gt, 40, 6, [0.5, 0.9, 1.4])
 
 
+def test_isolated_and_leaf_sites(native, oracle, pkg):
+    """Index gaps make isolated variables (nvars = max index + 1, lattice.rs:51-55): dE = 0, so the
+    Metropolis rule flips them at every attempt, in the mirror and on the device alike."""
+    edges = [((0, 1), -1.0), ((1, 2), -1.0), ((5, 6), 1.0), ((9, 2), -1.0)]   # 3, 4, 7, 8 isolated
+    lat = pkg.Lattice(edges, seed_gen=3)
+    assert lat.nvars == 10
+    g = lat.graph()
+    _check_vs_mirror(native, oracle, g, 40, 21, [0.5, 0.9, 0.2])
+    lat.set_initial_state([True] * 10)
+    _, st = lat.run_monte_carlo(0.7, 3, 8)
+    assert (~st[:, [3, 4, 7, 8]]).all()        # three forced flips from the all-up start
+
+
 def test_general_layout_equals_stencil_path(native, oracle, pkg):
     """The same torus through the checkerboard stencil kernels and through the general kernels:
     both implement one algorithm, so the bits must agree."""
