@@ -59,6 +59,12 @@ class Lattice:
         self._graph = None
         # knobs of the device path that do not exist in the reference (defaults = parity mode)
         self.linear_annealing = False   # False reproduces the reference's schedule quirk Q1
+        # multi-GPU (one process per GPU, torch.distributed initialised): shard the experiments
+        # over the ranks in blocks of 32 (the reference's rayon axis, lattice.rs:192-197) and,
+        # when gather_results is set, all-gather so that every rank returns the full arrays
+        self.distributed = False
+        self.gather_results = True
+        self.process_group = None
         self.msc_planes = 0             # 0 = library default
         self.philox_rounds = 0
 
@@ -183,7 +189,35 @@ class Lattice:
         g = self.graph()
         if self.msc_planes or self.philox_rounds:
             raise NotImplementedError("msc_planes/philox_rounds are set per Sim; use pyisingmontecarlo_b200.Sim")
+        if self.distributed:
+            return self._call_sharded(fn, args, energies, states, g)
         nat.check(fn(g.ctx.handle, g.handle, args, nat.ptr(energies), nat.ptr(states)), g.ctx.handle)
+        return energies, states
+
+    def _call_sharded(self, fn, args, energies, states, g):
+        """This rank runs experiments [32 w_lo, min(E, 32 w_hi)); replica_offset keeps every
+        experiment on the random stream it has in the unsharded run."""
+        from .tempering import _Collective, shard_range
+
+        if self._seed_gen is None:
+            raise ValueError("a seed_gen is required when experiments are sharded across ranks")
+        coll = _Collective(self.process_group)
+        E = int(args.num_experiments)
+        words = (E + 31) // 32
+        blocks = [shard_range(words, r, coll.world) for r in range(coll.world)]
+        counts = [max(0, min(E, 32 * hi) - 32 * lo) for lo, hi in blocks]
+        lo = 32 * blocks[coll.rank][0]
+        n = counts[coll.rank]
+        loc_e = np.zeros((n,) + energies.shape[1:], dtype=np.float64)
+        loc_s = nat.PinnedPool.empty((n,) + states.shape[1:], np.bool_)
+        if n:
+            args.num_experiments = n
+            args.replica_offset = lo
+            nat.check(fn(g.ctx.handle, g.handle, args, nat.ptr(loc_e), nat.ptr(loc_s)), g.ctx.handle)
+        self.local_range = (lo, lo + n)
+        if not self.gather_results or not coll.active:
+            return loc_e, loc_s
+        return coll.allgather_concat(loc_e, counts), coll.allgather_concat(loc_s, counts)
 
     # ---- classical runs, lattice.rs:163-470 -------------------------------------------------
     def run_monte_carlo(self, beta, timesteps, num_experiments, only_basic_moves=None,
@@ -194,8 +228,7 @@ class Lattice:
         states = nat.PinnedPool.empty((num_experiments, self.nvars), np.bool_)
         args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
                           num_experiments=int(num_experiments))
-        self._call(nat.lib().ising_run_monte_carlo, args, energies, states)
-        return energies, states
+        return self._call(nat.lib().ising_run_monte_carlo, args, energies, states)
 
     def run_monte_carlo_sampling(self, beta, timesteps, num_experiments, only_basic_moves=None,
                                  thermalization_time=None, sampling_freq=None,
@@ -212,8 +245,7 @@ class Lattice:
         args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
                           num_experiments=int(num_experiments), thermalization=thermalization_time,
                           sampling_freq=sampling_freq)
-        self._call(nat.lib().ising_run_monte_carlo_sampling, args, energies, states)
-        return energies, states
+        return self._call(nat.lib().ising_run_monte_carlo_sampling, args, energies, states)
 
     def _annealing(self, betas, timesteps, num_experiments, edge_move_importance_sampling, per_step):
         flags = self._check_classical(edge_move_importance_sampling)
@@ -230,8 +262,7 @@ class Lattice:
         args = self._args(flags, sched_t=st if len(st) else None, sched_beta=sb if len(sb) else None,
                           sched_len=len(st), timesteps=int(timesteps),
                           num_experiments=int(num_experiments))
-        self._call(nat.lib().ising_run_monte_carlo_annealing, args, energies, states)
-        return energies, states
+        return self._call(nat.lib().ising_run_monte_carlo_annealing, args, energies, states)
 
     def run_monte_carlo_annealing(self, betas, timesteps, num_experiments, only_basic_moves=None,
                                   edge_move_importance_sampling=None):

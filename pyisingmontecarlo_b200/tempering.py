@@ -49,7 +49,7 @@ class _Collective:
         backend = self.dist.get_backend(self.group)
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         width = int(np.prod(arr.shape[1:])) if arr.ndim > 1 else 1
-        cmax = max(counts)
+        cmax = max(max(counts), 1)
         buf = np.zeros((cmax, width), dtype=arr.dtype)
         buf[: arr.shape[0]] = arr.reshape(arr.shape[0], width)
         t = torch.from_numpy(buf.view(np.uint8) if arr.dtype == np.bool_ else buf).to(dev)

@@ -36,6 +36,19 @@ def main():
     full.sweeps(betas)
     assert (full.states()[64 * rank:64 * (rank + 1)] == mine.states()).all()
 
+    # (1b) the Lattice API with distributed = True: every rank returns the full, identical arrays
+    sq = [((x * 8 + y, ((x + 1) % 8) * 8 + y), -1.0) for x in range(8) for y in range(8)] + \
+         [((x * 8 + y, x * 8 + (y + 1) % 8), -1.0) for x in range(8) for y in range(8)]
+    lat = pkg.Lattice(sq, seed_gen=5, device=local)
+    e_full, s_full = lat.run_monte_carlo_annealing_and_get_energies([(0, 0.2), (6, 0.8)], 6, 100)
+    lat.distributed = True
+    e_sh, s_sh = lat.run_monte_carlo_annealing_and_get_energies([(0, 0.2), (6, 0.8)], 6, 100)
+    assert e_sh.shape == (100, 6) and (s_sh == s_full).all() and (e_sh == e_full).all()
+    en_s, st_s = lat.run_monte_carlo_sampling(0.4, 6, 70, None, 1, 2)
+    lat.distributed = False
+    en_f, st_f = lat.run_monte_carlo_sampling(0.4, 6, 70, None, 1, 2)
+    assert (st_s == st_f).all() and (en_s == en_f).all()
+
     # (2) sharded tempering == single-rank tempering
     edges = [((x * 6 + y, ((x + 1) % 6) * 6 + y), -1.0) for x in range(6) for y in range(6)] + \
             [((x * 6 + y, x * 6 + (y + 1) % 6), -1.0) for x in range(6) for y in range(6)]
