@@ -411,6 +411,12 @@ def run_b200(args, w, world, rank, local):
     flips_per_launch = E * n / 2.0  # one colour class per launch
     achieved = bpf * flips_per_launch / (k_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
+    traffic = None   # dram__bytes_read + write per launch of this kernel, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(args.workload)
+        if tj:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     sweep_only_value = sum_over_ranks(float(st2["flip_attempts"])) / (max_over_ranks(st2["sweep_device_ms"]) * 1e-3)
 
     # -------- e2e: the public API with host buffers
@@ -464,7 +470,9 @@ def run_b200(args, w, world, rank, local):
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "sweep_only_value": sweep_only_value,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "traffic_note": "ncu --set full capture (profiles/r01_sweep_metrics.md), cold caches; "
+                                         "algorithmic bytes per launch = %d" % int(bpf * flips_per_launch),
                          "kernel": "k_sweep_stencil (one colour class per launch)",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_flip": bpf,
                          "note": "kernel is integer-ALU bound (bit-sliced Metropolis + Philox), see DESIGN.md"},
