@@ -34,8 +34,8 @@ struct ising_ctx {
     int sm_count = 0;
     // grow-only device scratch (staging of outputs), so that repeated calls do not pay
     // cudaMalloc/cudaFree of hundreds of MB every time
-    void* scratch[3] = {nullptr, nullptr, nullptr};
-    size_t scratch_bytes[3] = {0, 0, 0};
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
     // free list of device buffers released by destroyed sims: a stateless Lattice run creates
     // and destroys a sim per call, and cudaMalloc/cudaFree (device-wide synchronising, tens
     // of ms with large pinned regions mapped) must not be on that path
@@ -786,6 +786,62 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
     return ISING_OK;
 }
 
+// Launch-bound sizes: a whole chunk of sweeps in one cooperative launch.  Returns 1 when done
+// that way, 0 when the caller should fall back to per-phase launches, < 0 on error (rc in *err).
+static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsigned long long* hist,
+                           int* err) {
+    *err = ISING_OK;
+    if (s->general || s->real || s->perbeta || nt == 0) return 0;
+    if ((uint64_t)s->lay.halfN * s->lay.W > (1ull << 19)) return 0;  // big enough to fill the GPU
+    // measured on B200 (32^2 and 16^3): with fused energies the per-block reduction in lock-step
+    // only pays off for few replica words (6.6 vs 10.2 us/sweep at W = 2, 18.9 vs 13.6 at W = 32)
+    if (hist && s->lay.W > 8) return 0;
+    ising_ctx* ctx = s->ctx;
+    const HostGraph& h = s->g->h;
+    std::vector<MscThresholds> th(nt);
+    for (uint64_t t = 0; t < nt; ++t) fill_thresholds(h, betas[t], s->planes, &th[t]);
+    void* dv = nullptr;
+    cudaError_t e = ctx_scratch(ctx, 3, nt * sizeof(MscThresholds), &dv);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dv, th.data(), nt * sizeof(MscThresholds), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        *err = fail(ctx, ISING_E_CUDA, "threshold table upload: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    SweepArgs a;
+    a.spins = s->d_spins;
+    a.jmask = s->g->d_jmask;
+    a.lay = s->lay;
+    a.sweep = (uint32_t)s->sweep_counter;
+    a.key0 = (uint32_t)s->seed;
+    a.key1 = (uint32_t)(s->seed >> 32);
+    a.gw0 = (uint32_t)(s->replica_offset / 32);
+    a.antiferro = h.uniform_antiferro ? 0xFFFFFFFFu : 0u;
+    a.planes = s->planes;
+    a.rounds = s->rounds;
+    a.nsat_out = nullptr;
+    memset(&a.th, 0, sizeof a.th);
+    const int rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
+                                              (uint32_t)(s->lay.W * 32), ctx->stream);
+    if (rc < 0) {
+        cudaGetLastError();
+        return 0;  // e.g. too many blocks to be co-resident: use the per-phase launches
+    }
+    if (rc == 0) return 0;
+    // the host table must outlive the copy
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        *err = fail(ctx, ISING_E_CUDA, "cooperative sweep: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    count_launch(s, 1);
+    s->stats.sweep_kernel_launches += 1;
+    s->sweep_counter += nt;
+    s->stats.sweeps += nt;
+    s->stats.flip_attempts += nt * s->E * h.nvars;
+    return 1;
+}
+
 // n_sat per experiment into s->d_counts (zeroed first)
 static int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
     ising_ctx* ctx = s->ctx;
@@ -821,9 +877,18 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     const int mult = s->general ? 1 : 2;
     if (!energies_per_sweep) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        for (uint64_t t = 0; t < nsweeps; ++t) {
-            const int rc = sim_one_sweep(s, betas ? betas[t] : 0.0);
-            if (rc) return rc;
+        uint64_t t = 0;
+        while (t < nsweeps) {
+            const uint64_t nt = std::min<uint64_t>(4096, nsweeps - t);
+            int err = ISING_OK;
+            const int done = betas ? sim_sweeps_coop(s, betas + t, nt, nullptr, &err) : 0;
+            if (done < 0) return err;
+            if (done) { t += nt; continue; }
+            for (uint64_t k = 0; k < nt; ++k) {
+                const int rc = sim_one_sweep(s, betas ? betas[t + k] : 0.0);
+                if (rc) return rc;
+            }
+            t += nt;
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -853,7 +918,10 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
         cudaMemsetAsync(d_hist, 0, cw * nt * sizeof(unsigned long long), ctx->stream);
         // the second colour phase of every sweep adds its post-flip satisfied-bond counts
         // into that sweep's slot of the history (fused, no separate energy pass)
-        for (uint64_t t = 0; t < nt && rc == ISING_OK; ++t) {
+        int coop_err = ISING_OK;
+        const int coop = betas ? sim_sweeps_coop(s, betas + t0, nt, d_hist, &coop_err) : 0;
+        if (coop < 0) rc = coop_err;
+        for (uint64_t t = 0; coop == 0 && t < nt && rc == ISING_OK; ++t) {
             rc = sim_one_sweep(s, betas ? betas[t0 + t] : 0.0, d_hist + t * cw);
             if (rc == ISING_OK && s->real) {
                 rc = sim_energy_real(s, reinterpret_cast<double*>(d_hist + t * cw));

@@ -3,10 +3,14 @@
 // is not a contraction).
 #include "kernels.h"
 
+#include <cooperative_groups.h>
+
 #include <stdlib.h>
 
 #include "../../include/ising_b200.h"
 #include "philox.h"
+
+namespace cg = cooperative_groups;
 
 namespace ising {
 
@@ -305,14 +309,14 @@ constexpr int SW_MAX_ITEMS = ((1 << SW_NP) - 1) / 6;    // sites a thread may ac
 // ACC: this phase also accumulates the post-flip satisfied-bond count of every replica into
 // nsat[] (used for the second colour: its sites see every bond once, so after the phase
 // nsat[e] is the total of experiment e and E = |J| (n_bonds - 2 nsat), lattice.rs:454).
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
-__global__ void __launch_bounds__(256, ACC ? ISING_ACC_MIN_BLOCKS : ISING_SWEEP_MIN_BLOCKS)
-k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
-                const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
-                PhiloxKeys pk, uint32_t gw0, uint32_t antiferro, MscThresholds th,
-                unsigned long long* __restrict__ nsat, uint32_t row_step, uint32_t step_y,
-                uint32_t step_z) {
-    extern __shared__ uint32_t sm[];
+// GRID2D: one row per block, (y, z) = 2D block index; otherwise blocks walk the rows with stride
+// row_step (persistent launch).
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool GRID2D>
+__device__ __forceinline__ void sweep_colour_phase(
+    uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, const uint32_t* __restrict__ jm,
+    const Layout& L, uint32_t c, uint32_t sweep, const PhiloxKeys& pk, uint32_t gw0,
+    uint32_t antiferro, const MscThresholds& th, unsigned long long* __restrict__ nsat,
+    uint32_t row_step, uint32_t step_y, uint32_t step_z, uint32_t* sm) {
     constexpr int kUnrollV = ISING_SWEEP_UNROLL_V;
     const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
     const uint32_t rowlen = Lxh * W;  // words per colour row (< 2^32: checked on the host)
@@ -328,14 +332,14 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
         // from its 2D block index; the persistent (ACC) launch divides once and then steps by
         // the grid size with a carry.
         uint32_t y, z, row;
-        if constexpr (ACC) {
-            row = blockIdx.x;
-            z = row / Ly;
-            y = row - z * Ly;
-        } else {
+        if constexpr (GRID2D) {
             y = blockIdx.x;
             z = blockIdx.y;
             row = z * Ly + y;
+        } else {
+            row = blockIdx.x;
+            z = row / Ly;
+            y = row - z * Ly;
         }
         for (; row < L.rows; row += row_step, y += step_y, z += step_z) {
             if (y >= Ly) {
@@ -415,6 +419,49 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
             }
         }
         if constexpr (ACC) block_reduce_vcount<SW_NP, V>(vc, sm, nsat, w0, W);
+    }
+}
+
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
+__global__ void __launch_bounds__(256, ACC ? ISING_ACC_MIN_BLOCKS : ISING_SWEEP_MIN_BLOCKS)
+k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
+                const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
+                PhiloxKeys pk, uint32_t gw0, uint32_t antiferro, MscThresholds th,
+                unsigned long long* __restrict__ nsat, uint32_t row_step, uint32_t step_y,
+                uint32_t step_z) {
+    extern __shared__ uint32_t sm[];
+    sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, !ACC>(own, oth, jm, L, c, sweep, pk, gw0, antiferro,
+                                                         th, nsat, row_step, step_y, step_z, sm);
+}
+
+// Small lattices are launch-bound (a colour phase of config 1 is ~2 us of work): one cooperative
+// launch runs a whole chunk of sweeps, both colours, with a grid barrier between phases.  The
+// per-sweep thresholds come from a table in global memory, staged in shared memory.
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
+__global__ void __launch_bounds__(256, 2)
+k_sweep_stencil_coop(uint32_t* __restrict__ spins, const uint32_t* __restrict__ jmask, Layout L,
+                     uint32_t sweep0, uint32_t nsweeps, PhiloxKeys pk, uint32_t gw0,
+                     uint32_t antiferro, const MscThresholds* __restrict__ th_table,
+                     unsigned long long* __restrict__ nsat_hist, uint32_t cw) {
+    extern __shared__ uint32_t sm[];
+    __shared__ MscThresholds th;
+    cg::grid_group grid = cg::this_grid();
+    const size_t csz = (size_t)L.halfN * L.W;
+    const size_t jsz = (size_t)2 * DIM * L.halfN;
+    const uint32_t g = gridDim.x, tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (uint32_t t = 0; t < nsweeps; ++t) {
+        __syncthreads();
+        if (tid < sizeof(MscThresholds) / 4)
+            reinterpret_cast<uint32_t*>(&th)[tid] = reinterpret_cast<const uint32_t*>(th_table + t)[tid];
+        __syncthreads();
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, false, false>(
+            spins, spins + csz, PMJ ? jmask : nullptr, L, 0u, sweep0 + t, pk, gw0, antiferro, th,
+            nullptr, g, g % L.Ly, g / L.Ly, sm);
+        grid.sync();
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, false>(
+            spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, th,
+            ACC ? nsat_hist + (size_t)t * cw : nullptr, g, g % L.Ly, g / L.Ly, sm);
+        grid.sync();
     }
 }
 
@@ -507,6 +554,64 @@ int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
     if (ISING_SWEEP_MAXV >= 4 && a.lay.W % 4 == 0) return sweep_dispatch_kind<4>(a, st);
     if (ISING_SWEEP_MAXV >= 2 && a.lay.W % 2 == 0) return sweep_dispatch_kind<2>(a, st);
     return sweep_dispatch_kind<1>(a, st);
+}
+
+// ---- cooperative multi-sweep launch (small lattices) -------------------------------------------
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
+static int coop_launch(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                       unsigned long long* hist, uint32_t cw, cudaStream_t st) {
+    dim3 grid, block;
+    stencil_block_shape(a.lay, V, &grid, &block, false);
+    if (ACC && block.y < (unsigned)V) block.y = V;
+    const int nthreads = block.x * block.y;
+    const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
+    const size_t smem = ACC ? (size_t)planes * nthreads * sizeof(uint32_t) : 0;
+    auto kern = k_sweep_stencil_coop<DIM, PMJ, K, ROUNDS, V, ACC>;
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem) != cudaSuccess ||
+        per_sm < 1)
+        return -1;
+    uint32_t g = a.lay.rows;
+    const uint32_t resident = (uint32_t)per_sm * (uint32_t)sms;
+    if (g > resident) g = resident;
+    Layout L = a.lay;
+    uint32_t* spins = a.spins;
+    const uint32_t* jmask = a.jmask;
+    uint32_t sweep0 = a.sweep, gw0 = a.gw0, antiferro = a.antiferro;
+    PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
+    void* params[] = {&spins, &jmask, &L, &sweep0, &nsweeps, &pk, &gw0, &antiferro, &th_dev, &hist, &cw};
+    if (cudaLaunchCooperativeKernel((void*)kern, dim3(g, 1, 1), block, params, smem, st) != cudaSuccess)
+        return -1;
+    return 1;
+}
+
+template <int DIM, bool PMJ, int V>
+static int coop_dispatch(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                         unsigned long long* hist, uint32_t cw, cudaStream_t st) {
+    // the cooperative path is an optimisation for launch-bound sizes: default planes / rounds only
+    if (a.planes != 6 || a.rounds != 10) return 0;
+    return hist ? coop_launch<DIM, PMJ, 6, 10, V, true>(a, th_dev, nsweeps, hist, cw, st)
+                : coop_launch<DIM, PMJ, 6, 10, V, false>(a, th_dev, nsweeps, nullptr, cw, st);
+}
+
+// returns 1 when the chunk was launched cooperatively, 0 when this configuration has no
+// cooperative variant (caller falls back to one launch per colour phase), -1 on error
+int launch_sweeps_stencil_coop(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                               unsigned long long* hist, uint32_t cw, cudaStream_t st) {
+    const bool pmj = a.jmask != nullptr;
+    const bool d3 = a.lay.kind == ISING_KIND_STENCIL3D;
+    if (!d3 && a.lay.kind != ISING_KIND_STENCIL2D) return 0;
+#define COOP_V(VV)                                                                              \
+    (d3 ? (pmj ? coop_dispatch<3, true, VV>(a, th_dev, nsweeps, hist, cw, st)                     \
+               : coop_dispatch<3, false, VV>(a, th_dev, nsweeps, hist, cw, st))                   \
+        : (pmj ? coop_dispatch<2, true, VV>(a, th_dev, nsweeps, hist, cw, st)                     \
+               : coop_dispatch<2, false, VV>(a, th_dev, nsweeps, hist, cw, st)))
+    if (a.lay.W % 4 == 0) return COOP_V(4);
+    if (a.lay.W % 2 == 0) return COOP_V(2);
+    return COOP_V(1);
+#undef COOP_V
 }
 
 // ------------------------------------------------------------------------------------------

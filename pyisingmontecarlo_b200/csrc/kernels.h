@@ -44,6 +44,12 @@ struct SweepArgs {
 
 // both colour phases of one sweep (2 launches); returns launches made or -1
 int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st);
+// A chunk of nsweeps whole sweeps in ONE cooperative launch (grid barrier between colour phases):
+// for lattices so small that a colour phase is launch-bound.  th_dev[nsweeps] = thresholds per
+// sweep (device memory); hist (or nullptr) receives the per-sweep n_sat at hist[t * cw + e].
+// Returns 1 if launched, 0 if this configuration has no cooperative variant, -1 on error.
+int launch_sweeps_stencil_coop(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                               unsigned long long* hist, uint32_t cw, cudaStream_t st);
 // n_sat[e] += number of satisfied bonds of experiment e (one colour's sites cover every bond)
 int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
                         uint32_t antiferro, unsigned long long* nsat, cudaStream_t st);
