@@ -880,10 +880,9 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
     constexpr int NCALL = K / 4 + 1;
     const uint32_t deg = g.deg;
     const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
-    const uint64_t total = (uint64_t)g.count * W;
-    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
-         item += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t i = (uint32_t)(item / W), w = (uint32_t)(item - (uint64_t)i * W);
+    // block = (wx lanes over replica words, by over sites): no division to split an item index
+    for (uint32_t i = blockIdx.x * blockDim.y + threadIdx.y; i < g.count; i += gridDim.x * blockDim.y)
+    for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) {
         const uint32_t n = g.sites[i];
         const uint32_t ab = g.anti[i];
         const uint32_t s = spins[(size_t)n * W + w];
@@ -962,10 +961,11 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
 int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st) {
     if (g.count == 0) return 0;
     if (g.deg > (uint32_t)GEN_MAX_DEG) return -1;
-    const uint64_t total = (uint64_t)g.count * a.W;
-    uint64_t blocks = (total + 255) / 256;
+    const uint32_t wx = a.W >= 32 ? 32 : pow2_ceil(a.W);
+    const dim3 block(wx, 256 / wx, 1);
+    uint64_t blocks = ((uint64_t)g.count + block.y - 1) / block.y;
     if (blocks > 148ull * 16) blocks = 148ull * 16;
-    const dim3 grid((unsigned)blocks), block(256);
+    const dim3 grid((unsigned)blocks);
     const bool pb = a.tables.plane != nullptr;
 #define GEN_LAUNCH(KK, RR)                                                                        \
     do {                                                                                          \
@@ -1079,10 +1079,8 @@ int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const
 template <int ROUNDS>
 __global__ void __launch_bounds__(256)
 k_sweep_real(RealSweepArgs a) {
-    const uint64_t total = (uint64_t)a.count * a.W;
-    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
-         item += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t i = (uint32_t)(item / a.W), w = (uint32_t)(item - (uint64_t)i * a.W);
+    for (uint32_t i = blockIdx.x * blockDim.y + threadIdx.y; i < a.count; i += gridDim.x * blockDim.y)
+    for (uint32_t w = threadIdx.x; w < a.W; w += blockDim.x) {
         const uint32_t n = a.sites[i];
         const uint32_t s = a.spins[(size_t)n * a.W + w];
         const uint32_t lo = a.row[n], hi = a.row[n + 1];
@@ -1118,11 +1116,12 @@ k_sweep_real(RealSweepArgs a) {
 
 int launch_sweep_real(const RealSweepArgs& a, cudaStream_t st) {
     if (a.count == 0) return 0;
-    const uint64_t total = (uint64_t)a.count * a.W;
-    uint64_t blocks = (total + 255) / 256;
+    const uint32_t wx = a.W >= 32 ? 32 : pow2_ceil(a.W);
+    const dim3 block(wx, 256 / wx, 1);
+    uint64_t blocks = ((uint64_t)a.count + block.y - 1) / block.y;
     if (blocks > 148ull * 16) blocks = 148ull * 16;
-    if (a.rounds == 7) k_sweep_real<7><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else k_sweep_real<10><<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (a.rounds == 7) k_sweep_real<7><<<(unsigned)blocks, block, 0, st>>>(a);
+    else k_sweep_real<10><<<(unsigned)blocks, block, 0, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
