@@ -525,7 +525,11 @@ static void stencil_block_shape(const Layout& L, uint32_t V, dim3* grid, dim3* b
                                 bool persistent) {
     const uint32_t groups = (L.W + V - 1) / V;  // vector groups of replica words per site
     const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
-    uint32_t by = 256 / wx;
+    uint32_t threads = 256;
+    if (const char* env = getenv("ISING_BLOCK_THREADS")) threads = (uint32_t)atoi(env);  // tuning knob
+    if (threads < 32 || threads > 256 || (threads & (threads - 1))) threads = 256;
+    uint32_t by = threads / wx;
+    if (by < 1) by = 1;
     const uint32_t need = pow2_ceil(L.Lxh);
     if (by > need) by = need;
     if (wx * by < 32) by = 32 / wx;

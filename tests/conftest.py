@@ -27,5 +27,11 @@ def native():
     """The C-ABI library; GPU tests must fail loudly (not skip) when it cannot be loaded."""
     from pyisingmontecarlo_b200 import _native
 
-    _native.lib()
+    try:
+        _native.lib()
+    except _native.NativeLibraryMissing:
+        from pyisingmontecarlo_b200._build import build_native
+
+        build_native()          # nvcc cross-compiles without a GPU
+        _native.lib()
     return _native
