@@ -877,12 +877,13 @@ int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double s
 // generic in the degree: n_sat is a 4-plane vertical counter, the uphill classes are
 // n_sat = deg/2+1 .. deg.  PERBETA: thresholds differ per replica (parallel tempering).
 // ------------------------------------------------------------------------------------------
-template <int K, int ROUNDS, bool PERBETA>
+// DEG > 0: compile-time degree (neighbour loads unrolled and in flight together); DEG = 0: runtime
+template <int K, int ROUNDS, bool PERBETA, int DEG>
 __global__ void __launch_bounds__(256)
 k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t sweep, uint32_t k0,
                 uint32_t k1, uint32_t gw0, GenThresholds th, GenTables tab) {
     constexpr int NCALL = K / 4 + 1;
-    const uint32_t deg = g.deg;
+    const uint32_t deg = DEG > 0 ? (uint32_t)DEG : g.deg;
     const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
     // block = (wx lanes over replica words, by over sites): no division to split an item index
     for (uint32_t i = blockIdx.x * blockDim.y + threadIdx.y; i < g.count; i += gridDim.x * blockDim.y)
@@ -891,16 +892,33 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
         const uint32_t ab = g.anti[i];
         const uint32_t s = spins[(size_t)n * W + w];
         uint32_t cnt[4] = {0, 0, 0, 0};
-        for (uint32_t k = 0; k < deg; ++k) {
-            const uint32_t nb = g.nbr[(size_t)k * g.count + i];
-            const uint32_t x = spins[(size_t)nb * W + w];
-            const uint32_t m = 0u - ((ab >> k) & 1u);
-            uint32_t c = ~(s ^ x ^ m);  // satisfied bond
+        if constexpr (DEG > 0) {
+            uint32_t x[DEG];
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const uint32_t t = cnt[l] & c;
-                cnt[l] ^= c;
-                c = t;
+            for (int k = 0; k < DEG; ++k)
+                x[k] = spins[(size_t)g.nbr[(size_t)k * g.count + i] * W + w];
+#pragma unroll
+            for (int k = 0; k < DEG; ++k) {
+                uint32_t c = ~(s ^ x[k] ^ (0u - ((ab >> k) & 1u)));  // satisfied bond
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const uint32_t t = cnt[l] & c;
+                    cnt[l] ^= c;
+                    c = t;
+                }
+            }
+        } else {
+            for (uint32_t k = 0; k < deg; ++k) {
+                const uint32_t nb = g.nbr[(size_t)k * g.count + i];
+                const uint32_t x = spins[(size_t)nb * W + w];
+                const uint32_t m = 0u - ((ab >> k) & 1u);
+                uint32_t c = ~(s ^ x ^ m);  // satisfied bond
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const uint32_t t = cnt[l] & c;
+                    cnt[l] ^= c;
+                    c = t;
+                }
             }
         }
         // one-hot masks of the uphill classes
@@ -971,12 +989,19 @@ int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t 
     if (blocks > 148ull * 16) blocks = 148ull * 16;
     const dim3 grid((unsigned)blocks);
     const bool pb = a.tables.plane != nullptr;
+#define GEN_LAUNCH_D(KK, RR, DD)                                                                  \
+    do {                                                                                          \
+        if (pb) k_sweep_general<KK, RR, true, DD><<<grid, block, 0, st>>>(                        \
+                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+        else k_sweep_general<KK, RR, false, DD><<<grid, block, 0, st>>>(                          \
+                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+    } while (0)
 #define GEN_LAUNCH(KK, RR)                                                                        \
     do {                                                                                          \
-        if (pb) k_sweep_general<KK, RR, true><<<grid, block, 0, st>>>(                            \
-                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
-        else k_sweep_general<KK, RR, false><<<grid, block, 0, st>>>(                              \
-                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+        if (KK == 6 && RR == 10 && g.deg == 3) GEN_LAUNCH_D(KK, RR, 3);                           \
+        else if (KK == 6 && RR == 10 && g.deg == 4) GEN_LAUNCH_D(KK, RR, 4);                      \
+        else if (KK == 6 && RR == 10 && g.deg == 6) GEN_LAUNCH_D(KK, RR, 6);                      \
+        else GEN_LAUNCH_D(KK, RR, 0);                                                             \
     } while (0)
 #define GEN_ROUNDS(KK)                                                                            \
     do { if (a.rounds == 7) GEN_LAUNCH(KK, 7); else GEN_LAUNCH(KK, 10); } while (0)
@@ -990,6 +1015,7 @@ int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t 
     }
 #undef GEN_ROUNDS
 #undef GEN_LAUNCH
+#undef GEN_LAUNCH_D
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
