@@ -419,6 +419,20 @@ def run_b200(args, w, world, rank, local):
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     sweep_only_value = sum_over_ranks(float(st2["flip_attempts"])) / (max_over_ranks(st2["sweep_device_ms"]) * 1e-3)
 
+    # -------- the same sweep-only region with Philox4x32-7 (Crush-resistant minimum of the
+    # Random123 paper; the library default stays at 10 rounds)
+    philox7_value = None
+    if not args.rounds:
+        sim7 = nat.Sim(graph, E, seed=31337, replica_offset=rank * E, planes=args.planes, rounds=7)
+        sim7.sweeps(betas[: max(1, len(betas) // 10)])
+        sim7.reset_stats()
+        barrier()
+        sim7.sweeps(betas)
+        barrier()
+        s7 = sim7.stats()
+        philox7_value = sum_over_ranks(float(s7["flip_attempts"])) / (max_over_ranks(s7["sweep_device_ms"]) * 1e-3)
+        sim7.close()
+
     # -------- e2e: the public API with host buffers
     if len(w["dims"]) == 3 or args.e2e_full:
         lat = pkg.Lattice.torus(w["dims"], j=w["j0"], pmj=w["pmj"], j_seed=2024, seed_gen=31337 + rank,
@@ -469,6 +483,7 @@ def run_b200(args, w, world, rank, local):
                        "msc_planes": args.planes or 6, "philox_rounds": args.rounds or 10},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "sweep_only_value": sweep_only_value,
+            "sweep_only_value_philox7": philox7_value,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "traffic_note": "ncu --set full capture (profiles/r01_sweep_metrics.md), cold caches; "

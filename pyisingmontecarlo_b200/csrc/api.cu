@@ -514,7 +514,7 @@ extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     // integer energy classes (all |J| equal, no bias, degree <= 15) use the bit-sliced kernels;
     // anything else the reference accepts runs on the float-field kernel
-    const_cast<ising_graph*>(g)->h.build_csr();
+    // (max_degree is known without the CSR: compile_from_edges builds it, make_torus sets 2*dim)
     const bool real = !h.integer_classes || (h.kind == ISING_KIND_GENERAL && h.max_degree > GEN_MAX_DEG);
     const bool general = real || h.kind == ISING_KIND_GENERAL || (flags & ISING_SIM_GENERAL_LAYOUT);
     if (real) {
