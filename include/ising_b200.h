@@ -101,13 +101,14 @@ ISING_API int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t *out);
 ISING_API int ising_sim_create(ising_ctx *ctx, const ising_graph *g, uint64_t num_experiments,
                      uint64_t seed, uint64_t replica_offset, ising_sim **out);
 /* flags: ISING_SIM_GENERAL_LAYOUT runs a recognised torus through the general (colour x degree
- * group) kernels in natural site order -- needed for per-experiment betas. */
+ * group) kernels in natural site order (cross-check of the two kernel families). */
 enum { ISING_SIM_GENERAL_LAYOUT = 1u << 0 };
 ISING_API int ising_sim_create_ex(ising_ctx *ctx, const ising_graph *g, uint64_t num_experiments,
                         uint64_t seed, uint64_t replica_offset, uint32_t flags, ising_sim **out);
 ISING_API void ising_sim_destroy(ising_sim *sim);
 /* Experiment e runs at betas[e] from now on (parallel tempering: one replica bit per
- * temperature); afterwards ising_sim_sweeps takes betas = NULL. */
+ * temperature); afterwards ising_sim_sweeps takes betas = NULL.  Needs integer energy classes
+ * (all |J| equal, no bias); on lattices the threshold tables exist for planes = 6. */
 ISING_API int ising_sim_set_betas(ising_sim *sim, const double *betas /* E */);
 /* Tuning knobs of the multi-spin-coded kernel; 0 keeps the default.  planes = bit-planes
  * compared before the per-bit resolver (4..8), rounds = Philox4x32 rounds (7 or 10).      */

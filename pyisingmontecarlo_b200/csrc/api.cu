@@ -773,8 +773,11 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
     a.antiferro = h.uniform_antiferro ? 0xFFFFFFFFu : 0u;
     a.planes = s->planes;
     a.rounds = s->rounds;
-    fill_thresholds(h, beta, s->planes, &a.th);
+    if (s->perbeta) memset(&a.th, 0, sizeof a.th);
+    else fill_thresholds(h, beta, s->planes, &a.th);
     a.nsat_out = nsat_out;
+    a.tplane = s->perbeta ? s->d_tplane : nullptr;
+    a.tlow = s->perbeta ? s->d_tlow : nullptr;
     const int n = launch_sweep_stencil(a, ctx->stream);
     if (n < 0) return fail(ctx, ISING_E_CUDA, "sweep launch failed: %s",
                            cudaGetErrorString(cudaGetLastError()));
@@ -820,6 +823,8 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     a.planes = s->planes;
     a.rounds = s->rounds;
     a.nsat_out = nullptr;
+    a.tplane = nullptr;
+    a.tlow = nullptr;
     memset(&a.th, 0, sizeof a.th);
     const int rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
                                               (uint32_t)(s->lay.W * 32), ctx->stream);
@@ -1056,13 +1061,34 @@ extern "C" int ising_sim_reset_stats(ising_sim* s) {
 extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
     if (!s || !betas) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
     ising_ctx* ctx = s->ctx;
-    if (!s->general || s->real)
+    if (s->real)
         return fail(ctx, ISING_E_UNSUPPORTED,
-                    "per-experiment betas need the general layout (ISING_SIM_GENERAL_LAYOUT) and "
-                    "integer energy classes (all |J| equal, no bias)");
+                    "per-experiment betas need integer energy classes (all |J| equal, no bias)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const HostGraph& h = s->g->h;
     const uint32_t W = s->lay.W, E32 = 32 * W;
+    if (!s->general) {
+        // checkerboard layout: classes dE = 4|J|, 8|J| (, 12|J|); tables are built for 6 planes
+        if (s->planes != 6)
+            return fail(ctx, ISING_E_UNSUPPORTED, "per-experiment betas on a lattice need planes = 6");
+        std::vector<unsigned long long> t64((size_t)E32 * 3, 0ull);
+        const int ncls = h.kind == ISING_KIND_STENCIL3D ? 3 : 2;
+        for (uint32_t e = 0; e < E32; ++e) {
+            const double beta = betas[e < s->E ? e : 0];
+            for (int c = 0; c < ncls; ++c)
+                t64[(size_t)e * 3 + c] = threshold64(beta, 4.0 * (c + 1) * h.jabs, s->planes);
+        }
+        if (!s->d_t64) {
+            CUDA_TRY(ctx, dev_alloc(&s->d_t64, t64.size()));
+            CUDA_TRY(ctx, dev_alloc(&s->d_tplane, (size_t)W * 3 * 8));
+            CUDA_TRY(ctx, dev_alloc(&s->d_tlow, (size_t)E32 * 3));
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(s->d_t64, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        count_launch(s, launch_build_tables_stencil(s->d_t64, W, s->planes, s->d_tplane, s->d_tlow, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        s->perbeta = true;
+        return ISING_OK;
+    }
     const size_t per = (size_t)(GEN_MAX_DEG + 1) * GEN_MAX_CLS;
     std::vector<unsigned long long> t64((size_t)E32 * per, 0ull);
     std::vector<uint32_t> slot(E32);
@@ -1138,7 +1164,8 @@ extern "C" int ising_pt_create(ising_ctx* ctx, const ising_graph* g, const doubl
     pt->word_lo = cfg_lo / 32;
     const uint64_t word_hi = (cfg_hi + 31) / 32;
     const uint64_t E = std::min<uint64_t>((word_hi - pt->word_lo) * 32, nbetas - pt->word_lo * 32);
-    int rc = ising_sim_create_ex(ctx, g, E, seed, pt->word_lo * 32, ISING_SIM_GENERAL_LAYOUT, &pt->sim);
+    // lattices temper on the checkerboard kernels, other graphs on the colour x degree kernels
+    int rc = ising_sim_create_ex(ctx, g, E, seed, pt->word_lo * 32, 0u, &pt->sim);
     if (rc) return rc;
     rc = pt_push_betas(pt.get());
     if (rc) { ising_sim_destroy(pt->sim); return rc; }

@@ -203,10 +203,15 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
 //   on counter (site, replica word, sweep, call).
 // returns the flip mask (downhill bits always flip)
 // ------------------------------------------------------------------------------------------
-template <int NCLS, int K, int ROUNDS>
+// PERBETA: every replica bit has its own inverse temperature (parallel tempering): the plane
+// masks are words tp[cls * 8 + p] whose bit b is the threshold bit of replica b of this word,
+// the resolver thresholds tl[b * 3 + cls].
+template <int NCLS, int K, int ROUNDS, bool PERBETA = false>
 __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, uint32_t sel1,
                                                   const MscThresholds& th, uint32_t site,
-                                                  uint32_t gw, uint32_t sweep, const PhiloxKeys& pk) {
+                                                  uint32_t gw, uint32_t sweep, const PhiloxKeys& pk,
+                                                  const uint32_t* __restrict__ tp = nullptr,
+                                                  const uint32_t* __restrict__ tl = nullptr) {
     constexpr int NCALL = K / 4 + 1;
     uint32_t r[NCALL * 4];
 #pragma unroll
@@ -220,8 +225,13 @@ __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, ui
     uint32_t eq = up, borrow = 0;
 #pragma unroll
     for (int p = K - 1; p >= 0; --p) {
-        uint32_t t = (sel0 & th.plane[1][p]) | (~sel0 & th.plane[0][p]);
-        if (NCLS == 3) t = (sel1 & th.plane[2][p]) | (~sel1 & t);
+        const uint32_t P0 = PERBETA ? __ldg(tp + 0 * 8 + p) : th.plane[0][p];
+        const uint32_t P1 = PERBETA ? __ldg(tp + 1 * 8 + p) : th.plane[1][p];
+        uint32_t t = (sel0 & P1) | (~sel0 & P0);
+        if (NCLS == 3) {
+            const uint32_t P2 = PERBETA ? __ldg(tp + 2 * 8 + p) : th.plane[2][p];
+            t = (sel1 & P2) | (~sel1 & t);
+        }
         borrow = maj3(~r[p], t, borrow);
         eq &= ~(r[p] ^ t);
     }
@@ -233,8 +243,15 @@ __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, ui
 #pragma unroll
     for (int j = 0; j < SPARE; ++j) {
         const uint32_t bit = eq & (0u - eq);  // lowest tied bit, 0 when nothing is tied
-        uint32_t lo = (sel0 & bit) ? th.low[1] : th.low[0];
-        if (NCLS == 3 && (sel1 & bit)) lo = th.low[2];
+        uint32_t lo;
+        if (PERBETA) {
+            const int b = (__ffs((int)eq) - 1) & 31;
+            const uint32_t cls = (NCLS == 3 && (sel1 & bit)) ? 2u : ((sel0 & bit) ? 1u : 0u);
+            lo = __ldg(tl + b * 3 + cls);
+        } else {
+            lo = (sel0 & bit) ? th.low[1] : th.low[0];
+            if (NCLS == 3 && (sel1 & bit)) lo = th.low[2];
+        }
         if (r[K + j] < lo) flip |= bit;
         eq ^= bit;
     }
@@ -248,8 +265,14 @@ __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, ui
                 cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
             const int m = j & 3;
             const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
-            uint32_t lo = ((sel0 >> b) & 1u) ? th.low[1] : th.low[0];
-            if (NCLS == 3 && ((sel1 >> b) & 1u)) lo = th.low[2];
+            uint32_t lo;
+            if (PERBETA) {
+                const uint32_t cls = (NCLS == 3 && ((sel1 >> b) & 1u)) ? 2u : (((sel0 >> b) & 1u) ? 1u : 0u);
+                lo = __ldg(tl + b * 3 + cls);
+            } else {
+                lo = ((sel0 >> b) & 1u) ? th.low[1] : th.low[0];
+                if (NCLS == 3 && ((sel1 >> b) & 1u)) lo = th.low[2];
+            }
             if (v < lo) flip |= 1u << b;
             eq &= eq - 1;
             ++j;
@@ -311,12 +334,13 @@ constexpr int SW_MAX_ITEMS = ((1 << SW_NP) - 1) / 6;    // sites a thread may ac
 // nsat[e] is the total of experiment e and E = |J| (n_bonds - 2 nsat), lattice.rs:454).
 // GRID2D: one row per block, (y, z) = 2D block index; otherwise blocks walk the rows with stride
 // row_step (persistent launch).
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool GRID2D>
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool GRID2D, bool PERBETA = false>
 __device__ __forceinline__ void sweep_colour_phase(
     uint32_t* __restrict__ own, const uint32_t* __restrict__ oth, const uint32_t* __restrict__ jm,
     const Layout& L, uint32_t c, uint32_t sweep, const PhiloxKeys& pk, uint32_t gw0,
     uint32_t antiferro, const MscThresholds& th, unsigned long long* __restrict__ nsat,
-    uint32_t row_step, uint32_t step_y, uint32_t step_z, uint32_t* sm) {
+    uint32_t row_step, uint32_t step_y, uint32_t step_z, uint32_t* sm,
+    const uint32_t* __restrict__ tplane = nullptr, const uint32_t* __restrict__ tlow = nullptr) {
     constexpr int kUnrollV = ISING_SWEEP_UNROLL_V;
     const uint32_t Lxh = L.Lxh, W = L.W, Ly = L.Ly, Lz = L.Lz;
     const uint32_t rowlen = Lxh * W;  // words per colour row (< 2^32: checked on the host)
@@ -388,10 +412,15 @@ __device__ __forceinline__ void sweep_colour_phase(
                     count_sat<DIM>(a, b0, b1, b2);
                     uint32_t flip;
                     if (DIM == 3)  // n_sat 4,5,6 -> dE = 4,8,12 |J|
-                        flip = msc_flip_mask<3, K, ROUNDS>(b2, b0, b1, th, site, gw0 + w + v, sweep, pk);
+                        flip = msc_flip_mask<3, K, ROUNDS, PERBETA>(
+                            b2, b0, b1, th, site, gw0 + w + v, sweep, pk,
+                            PERBETA ? tplane + (size_t)(w + v) * 24 : nullptr,
+                            PERBETA ? tlow + (size_t)(w + v) * 96 : nullptr);
                     else  // n_sat 3,4 -> dE = 4,8 |J|
-                        flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, site,
-                                                           gw0 + w + v, sweep, pk);
+                        flip = msc_flip_mask<2, K, ROUNDS, PERBETA>(
+                            b2 | (b1 & b0), b2, 0u, th, site, gw0 + w + v, sweep, pk,
+                            PERBETA ? tplane + (size_t)(w + v) * 24 : nullptr,
+                            PERBETA ? tlow + (size_t)(w + v) * 96 : nullptr);
                     s[v] ^= flip;
                     if constexpr (ACC) {
                         // a flipped spin turns its n_sat satisfied bonds into 2*DIM - n_sat
@@ -432,6 +461,23 @@ k_sweep_stencil(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
     extern __shared__ uint32_t sm[];
     sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, !ACC>(own, oth, jm, L, c, sweep, pk, gw0, antiferro,
                                                          th, nsat, row_step, step_y, step_z, sm);
+}
+
+// per-replica inverse temperatures (parallel tempering on lattices): thresholds from tables
+//   tplane[(w * 3 + cls) * 8 + p], tlow[(w * 32 + b) * 3 + cls]
+template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC>
+__global__ void __launch_bounds__(256, 2)
+k_sweep_stencil_perbeta(uint32_t* __restrict__ own, const uint32_t* __restrict__ oth,
+                        const uint32_t* __restrict__ jm, Layout L, uint32_t c, uint32_t sweep,
+                        PhiloxKeys pk, uint32_t gw0, uint32_t antiferro,
+                        const uint32_t* __restrict__ tplane, const uint32_t* __restrict__ tlow,
+                        unsigned long long* __restrict__ nsat, uint32_t row_step, uint32_t step_y,
+                        uint32_t step_z) {
+    extern __shared__ uint32_t sm[];
+    MscThresholds unused{};
+    sweep_colour_phase<DIM, PMJ, 6, ROUNDS, V, ACC, !ACC, true>(own, oth, jm, L, c, sweep, pk, gw0, antiferro,
+                                                               unused, nsat, row_step, step_y, step_z, sm,
+                                                               tplane, tlow);
 }
 
 // Small lattices are launch-bound (a colour phase of config 1 is ~2 us of work): one cooperative
@@ -475,6 +521,27 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     const uint32_t* oth = a.spins + (1 - c) * csz;
     const uint32_t* jm = a.jmask ? a.jmask + c * jsz : nullptr;
     const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
+    if (a.tplane) {  // per-replica betas (K == 6 checked by the caller)
+        if constexpr (K == 6) {
+            if (!acc) {
+                const dim3 grid2(L.Ly, L.Lz > 65535u ? 65535u : L.Lz, 1);
+                k_sweep_stencil_perbeta<DIM, PMJ, ROUNDS, V, false><<<grid2, block, 0, st>>>(
+                    own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.tplane, a.tlow, nullptr, L.rows,
+                    0u, 0u);
+            } else {
+                if (block.y < (unsigned)V) block.y = V;
+                uint32_t g = 148u * ISING_ACC_MIN_BLOCKS;
+                if (g > L.rows) g = L.rows;
+                const int nthreads = block.x * block.y;
+                const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
+                const size_t smem = (size_t)planes * nthreads * sizeof(uint32_t);
+                k_sweep_stencil_perbeta<DIM, PMJ, ROUNDS, V, true><<<dim3(g, 1, 1), block, smem, st>>>(
+                    own, oth, jm, L, c, a.sweep, pk, a.gw0, a.antiferro, a.tplane, a.tlow, a.nsat_out, g,
+                    g % L.Ly, g / L.Ly);
+            }
+        }
+        return;
+    }
     if (!acc) {
         const dim3 grid2(L.Ly, L.Lz > 65535u ? 65535u : L.Lz, 1);
         k_sweep_stencil<DIM, PMJ, K, ROUNDS, V, false><<<grid2, block, 0, st>>>(
@@ -554,6 +621,7 @@ static int sweep_dispatch_kind(const SweepArgs& a, cudaStream_t st) {
 }
 
 int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
+    if (a.tplane && a.planes != 6) return -1;  // per-replica tables are built for K = 6
     // widest vector the replica-word count allows (rows then stay 16-byte aligned)
     if (ISING_SWEEP_MAXV >= 4 && a.lay.W % 4 == 0) return sweep_dispatch_kind<4>(a, st);
     if (ISING_SWEEP_MAXV >= 2 && a.lay.W % 2 == 0) return sweep_dispatch_kind<2>(a, st);
@@ -1043,6 +1111,29 @@ __global__ void k_build_tables(const unsigned long long* __restrict__ t64,
         for (int p = 0; p < 8; ++p)
             plane_out[(((size_t)deg * W + w) * GEN_MAX_CLS + cls) * 8 + p] = pl[p];
     }
+}
+
+// stencil variant: T64[e * 3 + cls] per replica -> tplane[(w * 3 + cls) * 8 + p], tlow[(e) * 3 + cls]
+__global__ void k_build_tables_stencil(const unsigned long long* __restrict__ t64, uint32_t W, int K,
+                                       uint32_t* __restrict__ plane_out, uint32_t* __restrict__ low_out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W * 3) return;
+    const uint32_t cls = idx % 3, w = idx / 3;
+    uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t e = w * 32 + b;
+        const unsigned long long T = t64[(size_t)e * 3 + cls];
+        for (int p = 0; p < K; ++p)
+            if ((T >> (K + 31 - p)) & 1ull) pl[p] |= 1u << b;
+        low_out[(size_t)e * 3 + cls] = (uint32_t)(T & 0xFFFFFFFFull);
+    }
+    for (int p = 0; p < 8; ++p) plane_out[((size_t)w * 3 + cls) * 8 + p] = pl[p];
+}
+
+int launch_build_tables_stencil(const unsigned long long* t64, uint32_t W, int K, uint32_t* plane_out,
+                                uint32_t* low_out, cudaStream_t st) {
+    k_build_tables_stencil<<<(W * 3 + 127) / 128, 128, 0, st>>>(t64, W, K, plane_out, low_out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_build_tables(const unsigned long long* t64, const uint32_t* slot_of_replica, uint32_t W,

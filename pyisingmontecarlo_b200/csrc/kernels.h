@@ -40,7 +40,13 @@ struct SweepArgs {
     // when non-null the second colour phase also accumulates the per-experiment satisfied-bond
     // count after the sweep into nsat_out[W * 32] (must be zeroed by the caller)
     unsigned long long* nsat_out;
+    // per-replica inverse temperatures (planes must be 6): bit-sliced threshold tables
+    //   tplane[(w * 3 + cls) * 8 + p], tlow[(w * 32 + b) * 3 + cls];  nullptr = one beta (th)
+    const uint32_t* tplane;
+    const uint32_t* tlow;
 };
+int launch_build_tables_stencil(const unsigned long long* t64, uint32_t W, int K, uint32_t* plane_out,
+                                uint32_t* low_out, cudaStream_t st);
 
 // both colour phases of one sweep (2 launches); returns launches made or -1
 int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st);

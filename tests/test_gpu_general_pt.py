@@ -193,21 +193,43 @@ def test_real_couplings_and_biases(pkg, oracle, case):
 
 
 def test_per_experiment_betas_match_mirror(native, oracle, pkg):
+    """One inverse temperature per replica bit, on the checkerboard kernels and on the general
+    kernels: both equal the mirror (and therefore each other)."""
     ctx = native.Context.get(0)
-    g = native.Graph.torus(ctx, (4, 4, 6), j0=1.0, pmj=True, j_seed=21)
-    E = 45
-    betas = np.linspace(0.1, 1.6, E)
-    sim = native.Sim(g, E, 99, general_layout=True)
-    sim.set_betas(betas)
-    sim.sweeps(7)
-    a, b, j = g.edges()
-    en_ref, st_ref = oracle.msc_mirror(a, b, j, g.nvars, g.colors(), E, 99, None,
-                                       per_replica_beta=betas, nsweeps=7)
-    assert (sim.states() == st_ref).all() and (sim.energies() == en_ref).all()
-    with pytest.raises(ValueError):
-        sim.sweeps([0.5])          # a per-beta sim takes a sweep count
+    for dims, E in (((4, 4, 6), 45), ((6, 8), 130), ((4, 6, 4), 256)):
+        g = native.Graph.torus(ctx, dims, j0=1.0, pmj=len(dims) == 3, j_seed=21)
+        betas = np.linspace(0.1, 1.6, E)
+        a, b, j = g.edges()
+        en_ref, st_ref = oracle.msc_mirror(a, b, j, g.nvars, g.colors(), E, 99, None,
+                                           per_replica_beta=betas, nsweeps=7)
+        for general in (False, True):
+            sim = native.Sim(g, E, 99, general_layout=general)
+            sim.set_betas(betas)
+            sim.sweeps(7)
+            assert (sim.states() == st_ref).all() and (sim.energies() == en_ref).all()
+            if not general:   # fused per-sweep energies with per-replica thresholds
+                sim2 = native.Sim(g, E, 99)
+                sim2.set_betas(betas)
+                en = sim2.sweeps(7, per_sweep_energies=True)
+                assert (en[:, -1] == en_ref).all() and (sim2.states() == st_ref).all()
+            with pytest.raises(ValueError):
+                sim.sweeps([0.5])          # a per-beta sim takes a sweep count
     with pytest.raises(NotImplementedError):
-        native.Sim(g, E, 99).set_betas(betas)   # checkerboard layout has no per-beta tables
+        native.Sim(g, E, 99, planes=7).set_betas(betas)   # lattice tables exist for 6 planes
+
+
+def test_lattice_tempering_uses_checkerboard_kernels(native, oracle, pkg):
+    """Parallel tempering of a 3D +-J lattice (the common spin-glass use) against the mirror."""
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (4, 4, 4), j0=1.0, pmj=True, j_seed=5)
+    betas = np.geomspace(0.2, 1.4, 40)
+    pt = native.Tempering(g, betas, seed=2718)
+    states, energies = pt.timesteps_sample(30, replica_swap_freq=2, sampling_freq=10)
+    a, b, j = g.edges()
+    st_ref, en_ref, swaps_ref, slots_ref = oracle.msc_mirror_pt(
+        a, b, j, g.nvars, g.colors(), betas, 2718, 30, replica_swap_freq=2, sampling_freq=10)
+    assert (states == st_ref).all() and (energies == en_ref).all()
+    assert pt.total_swaps() == swaps_ref > 0 and (pt.slots() == slots_ref).all()
 
 
 def test_parallel_tempering_matches_mirror(native, oracle, pkg):
