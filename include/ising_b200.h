@@ -111,7 +111,7 @@ ISING_API void ising_sim_destroy(ising_sim *sim);
  * (all |J| equal, no bias); on lattices the threshold tables exist for planes = 6. */
 ISING_API int ising_sim_set_betas(ising_sim *sim, const double *betas /* E */);
 /* Tuning knobs of the multi-spin-coded kernel; 0 keeps the default.  planes = bit-planes
- * compared before the per-bit resolver (4..8), rounds = Philox4x32 rounds (7 or 10).      */
+ * compared before the per-bit resolver (5..7), rounds = Philox4x32 rounds (7 or 10).      */
 ISING_API int ising_sim_configure(ising_sim *sim, int planes, int rounds);
 /* Random start (GraphState::new's make_random_spin_state, one Philox bit per spin) ...     */
 ISING_API int ising_sim_randomize(ising_sim *sim);

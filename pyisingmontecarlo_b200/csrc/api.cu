@@ -581,7 +581,7 @@ extern "C" void ising_sim_destroy(ising_sim* s) {
 extern "C" int ising_sim_configure(ising_sim* s, int planes, int rounds) {
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     if (planes) {
-        if (planes < 4 || planes > 8) return fail(s->ctx, ISING_E_INVALID, "planes must be 4..8");
+        if (planes < 5 || planes > 7) return fail(s->ctx, ISING_E_INVALID, "planes must be 5..7");
         s->planes = planes;
     }
     if (rounds) {
@@ -1370,7 +1370,7 @@ extern "C" void ising_strip_destroy(ising_strip* s) {
 extern "C" int ising_strip_configure(ising_strip* s, int planes, int rounds) {
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     if (planes) {
-        if (planes < 4 || planes > 8) return fail(s->ctx, ISING_E_INVALID, "planes must be 4..8");
+        if (planes < 5 || planes > 7) return fail(s->ctx, ISING_E_INVALID, "planes must be 5..7");
         s->planes = planes;
     }
     if (rounds) {

@@ -573,11 +573,9 @@ static int sweep_dispatch_rounds(const SweepArgs& a, cudaStream_t st, dim3 grid,
 template <int DIM, bool PMJ, int V>
 static int sweep_dispatch_planes(const SweepArgs& a, cudaStream_t st, dim3 grid, dim3 block) {
     switch (a.planes) {
-        case 4: return sweep_dispatch_rounds<DIM, PMJ, 4, V>(a, st, grid, block);
         case 5: return sweep_dispatch_rounds<DIM, PMJ, 5, V>(a, st, grid, block);
         case 6: return sweep_dispatch_rounds<DIM, PMJ, 6, V>(a, st, grid, block);
         case 7: return sweep_dispatch_rounds<DIM, PMJ, 7, V>(a, st, grid, block);
-        case 8: return sweep_dispatch_rounds<DIM, PMJ, 8, V>(a, st, grid, block);
         default: return -1;
     }
 }
@@ -1074,11 +1072,9 @@ int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t 
 #define GEN_ROUNDS(KK)                                                                            \
     do { if (a.rounds == 7) GEN_LAUNCH(KK, 7); else GEN_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {
-        case 4: GEN_ROUNDS(4); break;
         case 5: GEN_ROUNDS(5); break;
         case 6: GEN_ROUNDS(6); break;
         case 7: GEN_ROUNDS(7); break;
-        case 8: GEN_ROUNDS(8); break;
         default: return -1;
     }
 #undef GEN_ROUNDS
@@ -1344,11 +1340,9 @@ int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
 #define STRIP_ROUNDS(KK)                                                                         \
     do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {
-        case 4: STRIP_ROUNDS(4); break;
         case 5: STRIP_ROUNDS(5); break;
         case 6: STRIP_ROUNDS(6); break;
         case 7: STRIP_ROUNDS(7); break;
-        case 8: STRIP_ROUNDS(8); break;
         default: return -1;
     }
 #undef STRIP_ROUNDS

@@ -89,7 +89,7 @@ def _mirror_check(native, oracle, graph, E, seed, betas, planes, rounds, offset=
     sim.close()
 
 
-@pytest.mark.parametrize("planes,rounds", [(6, 10), (4, 10), (5, 7), (7, 10), (8, 7)])
+@pytest.mark.parametrize("planes,rounds", [(6, 10), (5, 10), (5, 7), (7, 10), (7, 7)])
 def test_msc_3d_pmj_matches_mirror(native, oracle, pkg, planes, rounds):
     ctx = native.Context.get(0)
     g = native.Graph.torus(ctx, (4, 6, 4), j0=1.0, pmj=True, j_seed=77)

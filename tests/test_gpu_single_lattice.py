@@ -13,7 +13,7 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "exact_2
 def test_single_strip_matches_mirror(native, oracle):
     import pyisingmontecarlo_b200 as pkg
 
-    for (Lx, Ly, j, planes, rounds) in [(64, 6, -1.0, 6, 10), (128, 8, 1.0, 4, 7), (192, 4, -0.5, 7, 10)]:
+    for (Lx, Ly, j, planes, rounds) in [(64, 6, -1.0, 6, 10), (128, 8, 1.0, 5, 7), (192, 4, -0.5, 7, 10)]:
         lat = pkg.SingleLattice2D(Lx, Ly, j=j, seed=77, planes=planes, rounds=rounds)
         betas = [0.3, 0.44, 0.8, 0.44]
         en = []
