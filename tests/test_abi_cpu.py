@@ -74,6 +74,9 @@ def test_lattice_config_surface_without_gpu(native, oracle):
     import py_monte_carlo
 
     assert py_monte_carlo.Lattice is pkg.Lattice
+    assert py_monte_carlo.ClassicIsing is pkg.ClassicIsing
+    with pytest.raises(NotImplementedError, match="remain on the reference"):
+        py_monte_carlo.QmcIsing
     with pytest.raises(ValueError, match="Must supply some edges for graph"):
         pkg.Lattice([])
     lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -1.0)], 0)
