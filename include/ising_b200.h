@@ -135,6 +135,12 @@ ISING_API int ising_sim_get_states(ising_sim *sim, uint8_t *states /* E*nvars, b
 /* Opt-in packed read-back: uint32[nvars, ceil(E/32)] in natural site order (bit e%32 of word
  * e/32 is experiment e) -- 8x less D2H than bool[E, nvars].                                 */
 ISING_API int ising_sim_get_packed(ising_sim *sim, uint32_t *words);
+/* Checkpointing (the reference saves only its QMC classes, tempering.rs:307-347, and never the
+ * RNG state; here seed + sweep counter + packed spins are the complete state, so a restored
+ * run continues bit for bit).  words: uint32[nvars, ceil(E/32)] as from ising_sim_get_packed. */
+ISING_API int ising_sim_set_packed(ising_sim *sim, const uint32_t *words);
+ISING_API int ising_sim_get_counter(const ising_sim *sim, uint64_t *sweeps_done);
+ISING_API int ising_sim_set_counter(ising_sim *sim, uint64_t sweeps_done);
 /* per-experiment magnetisation sum_i s_i */
 ISING_API int ising_sim_get_magnetization(ising_sim *sim, double *m /* E */);
 
@@ -225,6 +231,12 @@ ISING_API int ising_pt_decide_swaps(const double *betas, uint64_t nbetas, const 
                           uint32_t *config_of_slot, uint64_t *nswaps);
 ISING_API int ising_pt_get_slots(const ising_pt *pt, uint32_t *slot_of_config /* nbetas */);
 ISING_API int ising_pt_get_local_states(ising_pt *pt, uint8_t *states /* (cfg_hi-cfg_lo)*nvars */);
+/* checkpoint support: the sim holding the ladder's configurations (borrowed, do not destroy),
+ * the swap counters, and restoring the slot permutation */
+ISING_API int ising_pt_get_sim(ising_pt *pt, ising_sim **out);
+ISING_API int ising_pt_get_counters(const ising_pt *pt, uint64_t *swap_step, uint64_t *total_swaps);
+ISING_API int ising_pt_restore(ising_pt *pt, const uint32_t *slot_of_config, uint64_t swap_step,
+                     uint64_t total_swaps);
 /* LatticeTempering::get_total_swaps, tempering.rs:297-299 */
 ISING_API int ising_pt_total_swaps(const ising_pt *pt, uint64_t *out);
 /* LatticeTempering::qmc_timesteps_sample (tempering.rs:156-222) on one rank:

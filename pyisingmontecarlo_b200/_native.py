@@ -105,6 +105,12 @@ _SIGNATURES = {
     "ising_sim_get_states": (C.c_int, [_P, _P]),
     "ising_sim_get_packed": (C.c_int, [_P, _P]),
     "ising_sim_get_magnetization": (C.c_int, [_P, _P]),
+    "ising_sim_set_packed": (C.c_int, [_P, _P]),
+    "ising_sim_get_counter": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "ising_sim_set_counter": (C.c_int, [_P, C.c_uint64]),
+    "ising_pt_get_sim": (C.c_int, [_P, C.POINTER(_P)]),
+    "ising_pt_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ising_pt_restore": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64]),
     "ising_sim_get_stats": (C.c_int, [_P, C.POINTER(SimStats)]),
     "ising_sim_reset_stats": (C.c_int, [_P]),
     "ising_run_monte_carlo": (C.c_int, [_P, _P, C.POINTER(RunArgs), _P, _P]),
@@ -407,6 +413,22 @@ class Sim:
         check(lib().ising_sim_get_packed(self.handle, ptr(out)), self.ctx.handle)
         return out
 
+    def set_packed(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        if w.shape != (self.graph.nvars, (self.E + 31) // 32):
+            raise ValueError("packed state must be uint32[nvars, ceil(E/32)]")
+        check(lib().ising_sim_set_packed(self.handle, ptr(w)), self.ctx.handle)
+
+    @property
+    def counter(self):
+        n = C.c_uint64(0)
+        check(lib().ising_sim_get_counter(self.handle, C.byref(n)), self.ctx.handle)
+        return int(n.value)
+
+    @counter.setter
+    def counter(self, value):
+        check(lib().ising_sim_set_counter(self.handle, int(value)), self.ctx.handle)
+
     def stats(self):
         st = SimStats()
         check(lib().ising_sim_get_stats(self.handle, C.byref(st)), self.ctx.handle)
@@ -435,6 +457,7 @@ class Tempering:
         self.graph = graph
         self.ctx = graph.ctx
         self.betas = np.ascontiguousarray(betas, dtype=np.float64)
+        self.seed = int(seed) & (2**64 - 1)
         self.R = len(self.betas)
         self.lo = int(cfg_lo)
         self.hi = self.R if cfg_hi is None else int(cfg_hi)
@@ -470,6 +493,29 @@ class Tempering:
         n = C.c_uint64(0)
         check(lib().ising_pt_total_swaps(self.handle, C.byref(n)), self.ctx.handle)
         return int(n.value)
+
+    def checkpoint(self):
+        """Everything needed to continue this ladder bit for bit (see restore)."""
+        sim = C.c_void_p()
+        check(lib().ising_pt_get_sim(self.handle, C.byref(sim)), self.ctx.handle)
+        E = min(((self.hi + 31) // 32 - self.lo // 32) * 32, self.R - (self.lo // 32) * 32)
+        words = np.empty((self.graph.nvars, (E + 31) // 32), dtype=np.uint32)
+        check(lib().ising_sim_get_packed(sim, ptr(words)), self.ctx.handle)
+        cnt, a, b = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().ising_sim_get_counter(sim, C.byref(cnt)), self.ctx.handle)
+        check(lib().ising_pt_get_counters(self.handle, C.byref(a), C.byref(b)), self.ctx.handle)
+        return {"packed": words, "sweeps": int(cnt.value), "slots": self.slots(),
+                "swap_step": int(a.value), "total_swaps": int(b.value)}
+
+    def restore(self, ck):
+        sim = C.c_void_p()
+        check(lib().ising_pt_get_sim(self.handle, C.byref(sim)), self.ctx.handle)
+        words = np.ascontiguousarray(ck["packed"], dtype=np.uint32)
+        check(lib().ising_sim_set_packed(sim, ptr(words)), self.ctx.handle)
+        check(lib().ising_sim_set_counter(sim, int(ck["sweeps"])), self.ctx.handle)
+        slots = np.ascontiguousarray(ck["slots"], dtype=np.uint32)
+        check(lib().ising_pt_restore(self.handle, ptr(slots), int(ck["swap_step"]), int(ck["total_swaps"])),
+              self.ctx.handle)
 
     def timesteps_sample(self, timesteps, replica_swap_freq=1, sampling_freq=1):
         ns = int(timesteps) // int(sampling_freq) if sampling_freq else 0

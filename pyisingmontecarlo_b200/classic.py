@@ -78,6 +78,29 @@ class ClassicIsing:
         return self._sim.run_sampling(beta, thermalization_time, sampling_freq,
                                       int(timesteps) // sampling_freq)
 
+    # checkpointing (additive: the reference persists only its QMC classes).  seed + sweep counter
+    # + packed spins are the whole state, so a restored object continues bit for bit.
+    def save_to_file(self, path):
+        with open(path, "wb") as f:
+            np.savez_compressed(f, kind="ClassicIsing", a=self._a, b=self._b, j=self._j,
+                                longitudinal=self._longitudinal, n=self._n,
+                                seed=np.uint64(self._seed), sweeps=np.uint64(self._sim.counter),
+                                packed=self._sim.packed())
+
+    @staticmethod
+    def read_from_file(path, reseed=None, *, device=None):
+        """reseed=None resumes the saved random streams exactly; a value starts new ones (the
+        reference's read_from_file(path, reseed), tempering.rs:332-338)."""
+        with np.load(path) as d:
+            if str(d["kind"]) != "ClassicIsing":
+                raise IOError(f"{path} is not a ClassicIsing checkpoint")
+            edges = [((int(x), int(y)), float(w)) for x, y, w in zip(d["a"], d["b"], d["j"])]
+            obj = ClassicIsing(edges, float(d["longitudinal"]), int(d["n"]),
+                               int(d["seed"]) if reseed is None else int(reseed), device=device)
+            obj._sim.set_packed(d["packed"])
+            obj._sim.counter = int(d["sweeps"]) if reseed is None else 0
+        return obj
+
     # additive: the resident state, for tests and users
     def get_states(self):
         return self._sim.states()

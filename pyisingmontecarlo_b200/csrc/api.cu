@@ -1043,6 +1043,33 @@ extern "C" int ising_sim_get_packed(ising_sim* s, uint32_t* words) {
     return ISING_OK;
 }
 
+// checkpoint support: the packed state in natural order plus the sweep counter are the whole
+// state of a sim (the RNG is counter-based: seed + counter, nothing else to save)
+extern "C" int ising_sim_set_packed(ising_sim* s, const uint32_t* words) {
+    if (!s || !words) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/words is NULL");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)s->lay.nvars * s->lay.W;
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, n * 4, &dv));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dv, words, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    count_launch(s, launch_import_natural(s->d_spins, s->lay, (const uint32_t*)dv, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_get_counter(const ising_sim* s, uint64_t* sweeps_done) {
+    if (!s || !sweeps_done) return fail(nullptr, ISING_E_INVALID, "sim/out is NULL");
+    *sweeps_done = s->sweep_counter;
+    return ISING_OK;
+}
+
+extern "C" int ising_sim_set_counter(ising_sim* s, uint64_t sweeps_done) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    s->sweep_counter = sweeps_done;
+    return ISING_OK;
+}
+
 extern "C" int ising_sim_get_stats(ising_sim* s, ising_sim_stats* out) {
     if (!s || !out) return fail(nullptr, ISING_E_INVALID, "sim/out is NULL");
     *out = s->stats;
@@ -1256,6 +1283,38 @@ extern "C" int ising_pt_get_local_states(ising_pt* pt, uint8_t* states) {
     for (uint64_t c = pt->lo; c < pt->hi; ++c)
         memcpy(states + (c - pt->lo) * N, all.data() + (c - pt->word_lo * 32) * N, N);
     return ISING_OK;
+}
+
+// checkpoint support: the sim behind the ladder, and the permutation / counters
+extern "C" int ising_pt_get_sim(ising_pt* pt, ising_sim** out) {
+    if (!pt || !out) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
+    *out = pt->sim;
+    return ISING_OK;
+}
+
+extern "C" int ising_pt_get_counters(const ising_pt* pt, uint64_t* swap_step, uint64_t* total_swaps) {
+    if (!pt || !swap_step || !total_swaps) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
+    *swap_step = pt->swap_step;
+    *total_swaps = pt->total_swaps;
+    return ISING_OK;
+}
+
+extern "C" int ising_pt_restore(ising_pt* pt, const uint32_t* slot_of_config, uint64_t swap_step,
+                                uint64_t total_swaps) {
+    if (!pt || !slot_of_config) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/slots is NULL");
+    std::vector<uint8_t> seen(pt->R, 0);
+    for (uint64_t c = 0; c < pt->R; ++c) {
+        if (slot_of_config[c] >= pt->R || seen[slot_of_config[c]])
+            return fail(pt->ctx, ISING_E_INVALID, "slot_of_config is not a permutation");
+        seen[slot_of_config[c]] = 1;
+    }
+    for (uint64_t c = 0; c < pt->R; ++c) {
+        pt->slot_of_cfg[c] = slot_of_config[c];
+        pt->cfg_of_slot[slot_of_config[c]] = (uint32_t)c;
+    }
+    pt->swap_step = swap_step;
+    pt->total_swaps = total_swaps;
+    return pt_push_betas(pt);
 }
 
 extern "C" int ising_pt_total_swaps(const ising_pt* pt, uint64_t* out) {

@@ -1544,6 +1544,22 @@ __global__ void k_export_natural(const uint32_t* __restrict__ spins, Layout L,
     }
 }
 
+__global__ void k_import_natural(uint32_t* __restrict__ spins, Layout L,
+                                 const uint32_t* __restrict__ in) {
+    const uint64_t total = L.nvars * L.W;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t n = i / L.W;
+        const uint32_t w = (uint32_t)(i - n * L.W);
+        spins[site_word_base(L, n) + w] = in[i];
+    }
+}
+
+int launch_import_natural(uint32_t* spins, const Layout& lay, const uint32_t* in_dev, cudaStream_t st) {
+    k_import_natural<<<148 * 8, 256, 0, st>>>(spins, lay, in_dev);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* out_dev,
                           cudaStream_t st) {
     k_export_natural<<<148 * 8, 256, 0, st>>>(spins, lay, out_dev);

@@ -71,6 +71,7 @@ int launch_pack_states(uint32_t* spins, const Layout& lay, const uint8_t* states
 // bool[E, nvars] (row stride = out_stride bytes between experiments) from packed words
 int launch_unpack_states(const uint32_t* spins, const Layout& lay, uint8_t* out_dev, uint64_t E,
                          uint64_t out_stride, cudaStream_t st);
+int launch_import_natural(uint32_t* spins, const Layout& lay, const uint32_t* in_dev, cudaStream_t st);
 // packed words in natural order [nvars][W]
 int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* out_dev,
                           cudaStream_t st);

@@ -178,11 +178,39 @@ class LatticeTempering:
     timesteps = qmc_timesteps
     timesteps_sample = qmc_timesteps_sample
 
+    # tempering.rs:307-347 (save_to_file / read_from_file) for the classical ladder.  Unlike the
+    # reference ("Does not save state of RNG") a restored ladder continues bit for bit: the RNG
+    # is counter-based, so seed + counters are its whole state.  Single rank only.
+    def save_to_file(self, path):
+        pt = self._ensure()
+        if self._coll.active:
+            raise NotImplementedError("checkpointing a ladder that is sharded over ranks")
+        ck = pt.checkpoint()
+        with open(path, "wb") as f:
+            np.savez_compressed(f, kind="LatticeTempering", a=self._a, b=self._b, j=self._j,
+                                betas=np.asarray(self._betas), seed=np.uint64(pt.seed), **ck)
+
+    @staticmethod
+    def read_from_file(path, reseed=None, *, device=None):
+        with np.load(path) as d:
+            if str(d["kind"]) != "LatticeTempering":
+                raise IOError(f"{path} is not a LatticeTempering checkpoint")
+            edges = [((int(x), int(y)), float(w)) for x, y, w in zip(d["a"], d["b"], d["j"])]
+            obj = LatticeTempering(edges, int(d["seed"]) if reseed is None else int(reseed), device=device)
+            for b in d["betas"]:
+                obj.add_graph(0.0, 0.0, float(b))
+            pt = obj._ensure()
+            ck = {k: d[k] for k in ("packed", "sweeps", "slots", "swap_step", "total_swaps")}
+            if reseed is not None:
+                ck["sweeps"], ck["swap_step"] = 0, 0
+            pt.restore(ck)
+        return obj
+
     def get_total_swaps(self):
         return 0 if self._pt is None else self._pt.total_swaps()
 
     def __getattr__(self, name):
-        if name in ("get_graph_itime", "save_to_file", "read_from_file", "clone") or name.startswith(
+        if name in ("get_graph_itime", "clone") or name.startswith(
                 "run_quantum_monte_carlo"):
             raise NotImplementedError(f"{name}: only the classical replica loop is provided here")
         raise AttributeError(name)

@@ -327,3 +327,39 @@ def test_classic_ising_stateful_api(pkg, oracle, native):
     cb.run_monte_carlo(0.5, 200)
     mean, sd, mag = _exact([((0, 1), 1.0), ((1, 2), 1.0)], 3, 0.5, [0.7] * 3)
     assert abs(cb.get_energies().mean() - mean) < 4 * sd / np.sqrt(2000)
+
+
+def test_checkpoints_resume_bit_for_bit(pkg, oracle, tmp_path):
+    """save_to_file / read_from_file (tempering.rs:307-347 shape): the RNG is counter-based, so a
+    restored run is indistinguishable from an uninterrupted one."""
+    edges = oracle.square_edges(6)
+    a = pkg.ClassicIsing(edges, None, 37, 9)
+    a.run_monte_carlo(0.45, 7)
+    path = str(tmp_path / "classic.npz")
+    a.save_to_file(path)
+    b = pkg.ClassicIsing.read_from_file(path)
+    assert (b.get_states() == a.get_states()).all()
+    a.run_monte_carlo(0.5, 6)
+    b.run_monte_carlo(0.5, 6)
+    assert (b.get_states() == a.get_states()).all() and (b.get_energies() == a.get_energies()).all()
+    c = pkg.ClassicIsing.read_from_file(path, reseed=123)     # new streams from the saved state
+    c.run_monte_carlo(0.5, 6)
+    assert (c.get_states() != a.get_states()).any()
+
+    def ladder():
+        lt = pkg.LatticeTempering(edges, seed=4)
+        for beta in np.linspace(0.2, 0.7, 9):
+            lt.add_graph(0.0, 0.0, beta)
+        return lt
+
+    x, y = ladder(), ladder()
+    sx1, ex1 = x.qmc_timesteps_sample(20, 3, 5)
+    path = str(tmp_path / "pt.npz")
+    x.save_to_file(path)
+    z = pkg.LatticeTempering.read_from_file(path)
+    assert z.get_total_swaps() == x.get_total_swaps() > 0
+    sx2, ex2 = x.qmc_timesteps_sample(21, 3, 7)
+    sz2, ez2 = z.qmc_timesteps_sample(21, 3, 7)
+    assert (sx2 == sz2).all() and (ex2 == ez2).all() and x.get_total_swaps() == z.get_total_swaps()
+    with pytest.raises(IOError):
+        pkg.ClassicIsing.read_from_file(path)
