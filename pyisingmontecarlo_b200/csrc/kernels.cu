@@ -1294,49 +1294,58 @@ __device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint
     return ((size_t)c * (g.rows + 2) + r) * g.Wr + j;
 }
 
-template <int K, int ROUNDS>
+// V consecutive words of a row per thread (128-bit loads when V == 4; needs Wr % V == 0)
+template <int K, int ROUNDS, int V>
 __global__ void __launch_bounds__(256)
 k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, PhiloxKeys pk,
               uint32_t antiferro, MscThresholds th, uint32_t r_begin, uint32_t r_count) {
-    const uint64_t total = (uint64_t)r_count * g.Wr;  // local rows [r_begin, r_begin + r_count)
-    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
-         item += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = r_begin + (uint32_t)(item / g.Wr) + 1, j = (uint32_t)(item % g.Wr);
+    const uint32_t groups = g.Wr / V;
+    // block = (x over the word groups of a row, y over rows): local rows [r_begin, r_begin + r_count)
+    for (uint32_t rr = blockIdx.y * blockDim.y + threadIdx.y; rr < r_count; rr += gridDim.y * blockDim.y)
+    for (uint32_t jg = blockIdx.x * blockDim.x + threadIdx.x; jg < groups; jg += gridDim.x * blockDim.x) {
+        const uint32_t j = jg * V;
+        const uint32_t r = r_begin + rr + 1;
         const uint32_t y = g.row0 + r - 1;  // global row
         const uint32_t p = (y + c) & 1u;
-        const uint32_t s = spins[strip_off(g, c, r, j)];
         const uint32_t o = 1u - c;
-        const uint32_t nx = spins[strip_off(g, o, r, j)];
-        uint32_t nsh;
-        if (p) {  // x + 1 of bit b is bit b + 1 of the other colour: shift right, carry from j + 1
-            const uint32_t nb = spins[strip_off(g, o, r, j + 1 == g.Wr ? 0 : j + 1)];
-            nsh = __funnelshift_r(nx, nb, 1);
-        } else {  // x - 1 is bit b - 1: shift left, carry from j - 1
-            const uint32_t nb = spins[strip_off(g, o, r, j == 0 ? g.Wr - 1 : j - 1)];
-            nsh = __funnelshift_l(nb, nx, 1);
+        uint32_t s[V], nx[V], nu[V], nd[V];
+        load_words<V>(spins + strip_off(g, c, r, j), s);
+        load_words<V>(spins + strip_off(g, o, r, j), nx);
+        load_words<V>(spins + strip_off(g, o, r - 1, j), nu);
+        load_words<V>(spins + strip_off(g, o, r + 1, j), nd);
+        // the x neighbour one bit over: funnel shift with carry from the adjacent word
+        const uint32_t edge = p ? spins[strip_off(g, o, r, j + V == g.Wr ? 0 : j + V)]
+                                : spins[strip_off(g, o, r, j == 0 ? g.Wr - 1 : j - 1)];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            uint32_t nsh;
+            if (p) nsh = __funnelshift_r(nx[v], v + 1 < V ? nx[v + 1 < V ? v + 1 : v] : edge, 1);
+            else nsh = __funnelshift_l(v > 0 ? nx[v > 0 ? v - 1 : 0] : edge, nx[v], 1);
+            uint32_t a[4] = {~(s[v] ^ nx[v] ^ antiferro), ~(s[v] ^ nsh ^ antiferro),
+                             ~(s[v] ^ nu[v] ^ antiferro), ~(s[v] ^ nd[v] ^ antiferro)};
+            uint32_t b0, b1, b2;
+            count_sat<2>(a, b0, b1, b2);
+            s[v] ^= msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, y, (c << 30) | (j + v), sweep, pk);
         }
-        const uint32_t nu = spins[strip_off(g, o, r - 1, j)];
-        const uint32_t nd = spins[strip_off(g, o, r + 1, j)];
-        uint32_t a[4] = {~(s ^ nx ^ antiferro), ~(s ^ nsh ^ antiferro), ~(s ^ nu ^ antiferro),
-                         ~(s ^ nd ^ antiferro)};
-        uint32_t b0, b1, b2;
-        count_sat<2>(a, b0, b1, b2);
-        const uint32_t flip = msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, y, (c << 30) | j,
-                                                          sweep, pk);
-        spins[strip_off(g, c, r, j)] = s ^ flip;
+        store_words<V>(spins + strip_off(g, c, r, j), s);
     }
 }
 
-int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
-    const uint64_t total = (uint64_t)a.r_count * a.g.Wr;
-    if (total == 0) return 0;
-    uint64_t blocks = (total + 255) / 256;
-    if (blocks > 148ull * 32) blocks = 148ull * 32;
-    const dim3 grid((unsigned)blocks), block(256);
+template <int V>
+static int strip_phase_dispatch(const StripSweepArgs& a, cudaStream_t st) {
+    const uint32_t groups = a.g.Wr / V;
+    const uint32_t bx = groups >= 256 ? 256 : pow2_ceil(groups);
+    const dim3 block(bx, 256 / bx, 1);
+    uint32_t gx = (groups + bx - 1) / bx;
+    if (gx > 64) gx = 64;
+    uint32_t gy = (a.r_count + block.y - 1) / block.y;
+    const uint32_t gy_cap = (148u * 32u + gx - 1) / gx;
+    if (gy > gy_cap) gy = gy_cap;
+    const dim3 grid(gx, gy, 1);
 #define STRIP_LAUNCH(KK, RR)                                                                     \
-    k_strip_phase<KK, RR><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,                 \
-                                                  philox_round_keys(a.key0, a.key1), a.antiferro, a.th, \
-                                                  a.r_begin, a.r_count)
+    k_strip_phase<KK, RR, V><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,              \
+                                                     philox_round_keys(a.key0, a.key1), a.antiferro, \
+                                                     a.th, a.r_begin, a.r_count)
 #define STRIP_ROUNDS(KK)                                                                         \
     do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {
@@ -1348,6 +1357,14 @@ int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
 #undef STRIP_ROUNDS
 #undef STRIP_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
+    if (a.r_count == 0 || a.g.Wr == 0) return 0;
+    // rows are 16-byte aligned when Wr % 4 == 0 (every row starts at a multiple of Wr words)
+    if (a.g.Wr % 4 == 0) return strip_phase_dispatch<4>(a, st);
+    if (a.g.Wr % 2 == 0) return strip_phase_dispatch<2>(a, st);
+    return strip_phase_dispatch<1>(a, st);
 }
 
 __global__ void k_strip_init_random(uint32_t* __restrict__ spins, StripGeom g, uint32_t k0,
