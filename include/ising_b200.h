@@ -130,6 +130,13 @@ ISING_API int ising_sim_sweeps(ising_sim *sim, const double *betas, uint64_t nsw
 ISING_API int ising_sim_run_sampling(ising_sim *sim, double beta, uint64_t thermalization,
                            uint64_t sampling_freq, uint64_t n_samples, double *energies,
                            uint8_t *states);
+/* The same loop without the state read-back (additive; feeds SURVEY 8(f)2): per sample the
+ * energy, the magnetisation M = sum_i s_i and the overlap Q = sum_i s_i^(2p) s_i^(2p+1) of the
+ * experiment pairs (2p, 2p+1), all reduced on the device.  energies / mags double[E, n_samples],
+ * overlaps double[E / 2, n_samples]; any of the three may be NULL.                           */
+ISING_API int ising_sim_run_observables(ising_sim *sim, double beta, uint64_t thermalization,
+                              uint64_t sampling_freq, uint64_t n_samples, double *energies,
+                              double *mags, double *overlaps);
 ISING_API int ising_sim_get_energies(ising_sim *sim, double *energies /* E */);
 ISING_API int ising_sim_get_states(ising_sim *sim, uint8_t *states /* E*nvars, bool */);
 /* Opt-in packed read-back: uint32[nvars, ceil(E/32)] in natural site order (bit e%32 of word

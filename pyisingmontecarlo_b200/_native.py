@@ -101,6 +101,7 @@ _SIGNATURES = {
     "ising_sim_set_states": (C.c_int, [_P, _P]),
     "ising_sim_sweeps": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "ising_sim_run_sampling": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
+    "ising_sim_run_observables": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "ising_sim_get_energies": (C.c_int, [_P, _P]),
     "ising_sim_get_states": (C.c_int, [_P, _P]),
     "ising_sim_get_packed": (C.c_int, [_P, _P]),
@@ -391,6 +392,17 @@ class Sim:
                                            int(sampling_freq), int(n_samples), ptr(energies),
                                            ptr(states)), self.ctx.handle)
         return energies, states
+
+    def run_observables(self, beta, thermalization, sampling_freq, n_samples, overlaps=True):
+        """(energies[E, n_s], magnetisations[E, n_s], overlaps[E // 2, n_s] or None), reduced on
+        the device: no state read-back."""
+        energies = np.zeros((self.E, n_samples), dtype=np.float64)
+        mags = np.zeros((self.E, n_samples), dtype=np.float64)
+        q = np.zeros((self.E // 2, n_samples), dtype=np.float64) if overlaps else None
+        check(lib().ising_sim_run_observables(self.handle, float(beta), int(thermalization),
+                                              int(sampling_freq), int(n_samples), ptr(energies),
+                                              ptr(mags), ptr(q)), self.ctx.handle)
+        return energies, mags, q
 
     def energies(self):
         out = np.empty(self.E, dtype=np.float64)

@@ -78,6 +78,17 @@ class ClassicIsing:
         return self._sim.run_sampling(beta, thermalization_time, sampling_freq,
                                       int(timesteps) // sampling_freq)
 
+    def run_monte_carlo_observables(self, beta, timesteps, thermalization_time=None, sampling_freq=None,
+                                    overlaps=True):
+        """Additive: the sampling loop of classicising.rs:119-179 with the per-sample state copy
+        replaced by on-device reductions -> (energies[E, n_s], M[E, n_s], Q[E // 2, n_s])."""
+        thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
+        sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
+        if sampling_freq == 0:
+            raise ZeroDivisionError("sampling_freq must be non-zero (the reference panics)")
+        return self._sim.run_observables(beta, thermalization_time, sampling_freq,
+                                         int(timesteps) // sampling_freq, overlaps)
+
     # checkpointing (additive: the reference persists only its QMC classes).  seed + sweep counter
     # + packed spins are the whole state, so a restored object continues bit for bit.
     def save_to_file(self, path):

@@ -34,8 +34,11 @@ struct ising_ctx {
     int sm_count = 0;
     // grow-only device scratch (staging of outputs), so that repeated calls do not pay
     // cudaMalloc/cudaFree of hundreds of MB every time
-    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[4] = {0, 0, 0, 0};
+    void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+    // second stream + events for the double-buffered device-to-host copies of the sampling path
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
     // free list of device buffers released by destroyed sims: a stateless Lattice run creates
     // and destroys a sim per call, and cudaMalloc/cudaFree (device-wide synchronising, tens
     // of ms with large pinned regions mapped) must not be on that path
@@ -216,6 +219,11 @@ extern "C" void ising_ctx_destroy(ising_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->ev_filled[b]) cudaEventDestroy(ctx->ev_filled[b]);
+        if (ctx->ev_drained[b]) cudaEventDestroy(ctx->ev_drained[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     for (void* p : ctx->scratch) cudaFree(p);
     for (auto& b : ctx->free_bufs) cudaFree(b.first);
@@ -1638,8 +1646,36 @@ extern "C" int ising_run_monte_carlo(ising_ctx* ctx, const ising_graph* g,
     return rc;
 }
 
+static cudaError_t ctx_copy_stream(ising_ctx* ctx) {
+    if (ctx->copy_stream) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaEventCreateWithFlags(&ctx->ev_filled[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_drained[b], cudaEventDisableTiming);
+    }
+    return e;
+}
+
+// rows of `width` bytes, device (pitch spitch) to host (pitch dpitch); the 2D copy engine path
+// is limited to pitches below 2^31, longer rows go one by one
+static cudaError_t copy_rows_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                                 size_t height, cudaStream_t st) {
+    if (width == 0 || height == 0) return cudaSuccess;
+    if (dpitch < (1ull << 31) && spitch < (1ull << 31))
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, st);
+    for (size_t r = 0; r < height; ++r) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst + r * dpitch, (const char*)src + r * spitch, width,
+                                        cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // thermalise, then n_s x (sampling_freq sweeps, copy state, energy): lattice.rs:271-287 and
 // classicising.rs:146-171 on a device-resident sim.  energies[E, n_s], states[E, n_s, nvars].
+// At scale: samples are unpacked into one of two device slabs laid out
+// [E, nk, N]; while the sweeps of the next slab run, the copy stream drains the previous one
+// straight into the caller's [E, ns, N] array with a strided (2D) copy -- no host staging.
 extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t thermalization,
                                       uint64_t sampling_freq, uint64_t ns, double* energies,
                                       uint8_t* states) {
@@ -1652,38 +1688,102 @@ extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t ther
     std::vector<double> betas(std::max<uint64_t>(thermalization, sampling_freq), beta);
     int rc = ising_sim_sweeps(sim, betas.data(), thermalization, nullptr);
     if (rc || ns == 0) return rc;
-    // states[E, ns, N]: sample k of experiment e lands at (e * ns + k) * N; unpack straight
-    // into a device image of that layout, slab by slab (<= 1 GiB of staging)
-    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, (1ull << 30) / std::max<uint64_t>(1, E * N)));
-    void* dv = nullptr;
-    CUDA_TRY(ctx, ctx_scratch(ctx, 0, (size_t)E * slab * N, &dv));
-    uint8_t* d = (uint8_t*)dv;
-    CUDA_TRY(ctx, ctx_scratch(ctx, 2, (size_t)E * slab * sizeof(double), &dv));
-    double* d_en = (double*)dv;
-    std::vector<double> en_host;
-    std::vector<uint8_t> st_host;
-    for (uint64_t k0 = 0; k0 < ns; k0 += slab) {
+    CUDA_TRY(ctx, ctx_copy_stream(ctx));
+    uint64_t slab_bytes = 1ull << 29;
+    if (const char* env = getenv("ISING_SAMPLING_SLAB_BYTES")) slab_bytes = strtoull(env, nullptr, 10);  // test knob
+    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, slab_bytes / std::max<uint64_t>(1, E * N)));
+    const int nbuf = slab < ns ? 2 : 1;
+    uint8_t* d_st[2] = {nullptr, nullptr};
+    double* d_en[2] = {nullptr, nullptr};
+    for (int b = 0; b < nbuf; ++b) {
+        void* dv = nullptr;
+        CUDA_TRY(ctx, ctx_scratch(ctx, b ? 4 : 0, (size_t)E * slab * N, &dv));
+        d_st[b] = (uint8_t*)dv;
+        CUDA_TRY(ctx, ctx_scratch(ctx, b ? 5 : 2, (size_t)E * slab * sizeof(double), &dv));
+        d_en[b] = (double*)dv;
+    }
+    uint64_t islab = 0;
+    for (uint64_t k0 = 0; k0 < ns; k0 += slab, ++islab) {
         const uint64_t nk = std::min(slab, ns - k0);
+        const int b = (int)(islab & 1);
+        if (islab >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_drained[b], 0));
         for (uint64_t k = 0; k < nk; ++k) {
             rc = ising_sim_sweeps(sim, betas.data(), sampling_freq, nullptr);
             if (rc) return rc;
-            count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d + k * N, E, nk * N,
+            count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d_st[b] + k * N, E, nk * N,
                                                    ctx->stream));
-            rc = sim_energies_to_device(sim, d_en, nk, k);
+            rc = sim_energies_to_device(sim, d_en[b], nk, k);
             if (rc) return rc;
         }
-        en_host.resize((size_t)E * nk);
-        st_host.resize(nk == ns ? 0 : (size_t)E * nk * N);
-        uint8_t* dst = nk == ns ? states : st_host.data();
-        CUDA_TRY(ctx, cudaMemcpyAsync(dst, d, (size_t)E * nk * N, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(en_host.data(), d_en, en_host.size() * 8, cudaMemcpyDeviceToHost,
-                                      ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        for (uint64_t e = 0; e < E; ++e) {
-            memcpy(energies + e * ns + k0, en_host.data() + e * nk, nk * sizeof(double));
-            if (nk != ns)
-                memcpy(states + (e * ns + k0) * N, st_host.data() + e * nk * N, (size_t)nk * N);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_filled[b], ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_filled[b], 0));
+        CUDA_TRY(ctx, copy_rows_d2h(states + k0 * N, (size_t)ns * N, d_st[b], (size_t)nk * N,
+                                    (size_t)nk * N, E, ctx->copy_stream));
+        CUDA_TRY(ctx, copy_rows_d2h(energies + k0, (size_t)ns * 8, d_en[b], (size_t)nk * 8,
+                                    (size_t)nk * 8, E, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_drained[b], ctx->copy_stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// The sampling loop without the state read-back (a sample of config 2 is 17 GB of bools):
+// per sample the energy, the magnetisation M = sum_i s_i and, when asked for, the overlap
+// Q = sum_i s_i^(2p) s_i^(2p+1) of adjacent experiment pairs (the spin-glass order parameter
+// when all experiments share the couplings, lattice.rs:199).  Outputs are [E, ns] / [E/2, ns].
+extern "C" int ising_sim_run_observables(ising_sim* sim, double beta, uint64_t thermalization,
+                                         uint64_t sampling_freq, uint64_t ns, double* energies,
+                                         double* mags, double* overlaps) {
+    if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    ising_ctx* ctx = sim->ctx;
+    if (sim->perbeta) return fail(ctx, ISING_E_INVALID, "sampling runs at one beta");
+    if (sampling_freq == 0) return fail(ctx, ISING_E_INVALID, "sampling_freq must be > 0");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t E = sim->E, N = sim->lay.nvars, P = E / 2;
+    const size_t cw = (size_t)sim->lay.W * 32;
+    std::vector<double> betas(std::max<uint64_t>(thermalization, sampling_freq), beta);
+    int rc = ising_sim_sweeps(sim, betas.data(), thermalization, nullptr);
+    if (rc || ns == 0) return rc;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(ns, (1ull << 23) / std::max<uint64_t>(1, E)));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 2, (size_t)E * chunk * sizeof(double), &dv));
+    double* d_en = (double*)dv;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 4, (size_t)E * chunk * sizeof(double), &dv));
+    double* d_m = (double*)dv;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 5, (size_t)std::max<uint64_t>(P, 1) * chunk * sizeof(double), &dv));
+    double* d_q = (double*)dv;
+    for (uint64_t k0 = 0; k0 < ns; k0 += chunk) {
+        const uint64_t nk = std::min(chunk, ns - k0);
+        for (uint64_t k = 0; k < nk; ++k) {
+            rc = ising_sim_sweeps(sim, betas.data(), sampling_freq, nullptr);
+            if (rc) return rc;
+            if (energies) {
+                rc = sim_energies_to_device(sim, d_en, nk, k);
+                if (rc) return rc;
+            }
+            if (mags) {
+                CUDA_TRY(ctx, cudaMemsetAsync(sim->d_counts, 0, cw * sizeof(unsigned long long), ctx->stream));
+                count_launch(sim, launch_count_up(sim->d_spins, sim->lay, sim->d_counts, ctx->stream));
+                // M = 2 up - N = -(N - 2 up)
+                count_launch(sim, launch_energy_from_nsat(sim->d_counts, E, -1.0, N, 2, d_m, nk, k, ctx->stream));
+            }
+            if (overlaps && P) {
+                CUDA_TRY(ctx, cudaMemsetAsync(sim->d_counts, 0, cw * sizeof(unsigned long long), ctx->stream));
+                count_launch(sim, launch_count_up(sim->d_spins, sim->lay, sim->d_counts, ctx->stream, true));
+                count_launch(sim, launch_overlap_from_counts(sim->d_counts, P, N, d_q, nk, k, ctx->stream));
+            }
         }
+        if (energies)
+            CUDA_TRY(ctx, copy_rows_d2h(energies + k0, (size_t)ns * 8, d_en, (size_t)nk * 8, (size_t)nk * 8, E,
+                                        ctx->stream));
+        if (mags)
+            CUDA_TRY(ctx, copy_rows_d2h(mags + k0, (size_t)ns * 8, d_m, (size_t)nk * 8, (size_t)nk * 8, E,
+                                        ctx->stream));
+        if (overlaps && P)
+            CUDA_TRY(ctx, copy_rows_d2h(overlaps + k0, (size_t)ns * 8, d_q, (size_t)nk * 8, (size_t)nk * 8, P,
+                                        ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return ISING_OK;
 }

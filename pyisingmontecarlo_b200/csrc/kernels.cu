@@ -834,7 +834,7 @@ int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layo
 // up-spin count over all sites (any layout: the sum runs over every stored site word)
 __global__ void __launch_bounds__(256)
 k_count_up(const uint32_t* __restrict__ spins, uint64_t nsites, uint32_t W,
-           unsigned long long* __restrict__ up) {
+           unsigned long long* __restrict__ up, uint32_t pair) {
     __shared__ int sm[32 * 256];
     const int nthreads = blockDim.x * blockDim.y;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -847,7 +847,10 @@ k_count_up(const uint32_t* __restrict__ spins, uint64_t nsites, uint32_t W,
         if (w < W) {
             for (uint64_t n = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y; n < nsites;
                  n += (uint64_t)gridDim.x * blockDim.y) {
-                vc.add1(spins[(size_t)n * W + w]);
+                uint32_t x = spins[(size_t)n * W + w];
+                // pair mode: bit 2p = experiments 2p and 2p+1 disagree on this site
+                if (pair) x = (x ^ (x >> 1)) & 0x55555555u;
+                vc.add1(x);
                 if (++pending == VC_FLUSH_ADD1) {
                     vc.flush(sm, tid, nthreads);
                     pending = 0;
@@ -860,13 +863,29 @@ k_count_up(const uint32_t* __restrict__ spins, uint64_t nsites, uint32_t W,
 }
 
 int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long* up,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool pair) {
     const uint32_t wx = lay.W >= 32 ? 32 : pow2_ceil(lay.W);
     dim3 block(wx, 256 / wx, 1);
     uint64_t g = (lay.nvars + block.y - 1) / block.y;
     if (g > 148u * 8u) g = 148u * 8u;
     if (g == 0) g = 1;
-    k_count_up<<<dim3((unsigned)g), block, 0, st>>>(spins, lay.nvars, lay.W, up);
+    k_count_up<<<dim3((unsigned)g), block, 0, st>>>(spins, lay.nvars, lay.W, up, pair ? 1u : 0u);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// overlap of the experiment pair (2p, 2p+1) from the pair-mode counts: q = N - 2 * disagreements
+__global__ void k_overlap_from_counts(const unsigned long long* __restrict__ dis, uint64_t P,
+                                      uint64_t nsites, double* __restrict__ out, uint64_t stride,
+                                      uint64_t off) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    out[p * stride + off] = (double)((long long)nsites - 2ll * (long long)dis[2 * p]);
+}
+
+int launch_overlap_from_counts(const unsigned long long* dis, uint64_t P, uint64_t nsites,
+                               double* out_dev, uint64_t stride, uint64_t off, cudaStream_t st) {
+    const unsigned g = (unsigned)((P + 255) / 256);
+    k_overlap_from_counts<<<g ? g : 1, 256, 0, st>>>(dis, P, nsites, out_dev, stride, off);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -61,7 +61,9 @@ int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layo
                         uint32_t antiferro, unsigned long long* nsat, cudaStream_t st);
 // up[e] += number of up spins of experiment e
 int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long* up,
-                    cudaStream_t st);
+                    cudaStream_t st, bool pair = false);
+int launch_overlap_from_counts(const unsigned long long* dis, uint64_t P, uint64_t nsites,
+                               double* out_dev, uint64_t stride, uint64_t off, cudaStream_t st);
 int launch_init_random(uint32_t* spins, const Layout& lay, uint32_t key0, uint32_t key1,
                        uint32_t gw0, cudaStream_t st);
 int launch_init_broadcast(uint32_t* spins, const Layout& lay, const uint8_t* state_dev,

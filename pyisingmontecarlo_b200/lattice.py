@@ -247,6 +247,29 @@ class Lattice:
                           sampling_freq=sampling_freq)
         return self._call(nat.lib().ising_run_monte_carlo_sampling, args, energies, states)
 
+    def run_monte_carlo_observables(self, beta, timesteps, num_experiments, thermalization_time=None,
+                                    sampling_freq=None, overlaps=True):
+        """Additive: the loop of lattice.rs:231-299 with the per-sample state copy
+        replaced by on-device reductions.  Same trajectories as run_monte_carlo_sampling for the
+        same seed_gen -> (energies[E, n_s], M[E, n_s] = sum_i s_i, Q[E // 2, n_s] = overlap of
+        the experiment pairs (2p, 2p+1)); Binder ratios etc. follow on the host from M and Q."""
+        self._check_classical(None)
+        if self.distributed:
+            raise NotImplementedError("run_monte_carlo_observables on a sharded Lattice")
+        thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
+        sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
+        if sampling_freq == 0:
+            raise ZeroDivisionError("sampling_freq must be non-zero (the reference panics)")
+        sim = nat.Sim(self.graph(), int(num_experiments), self._run_seed(),
+                      planes=self.msc_planes or 0, rounds=self.philox_rounds or 0)
+        try:
+            if self._initial_state is not None:
+                sim.set_state(self._initial_state)
+            return sim.run_observables(beta, thermalization_time, sampling_freq,
+                                       int(timesteps) // sampling_freq, overlaps)
+        finally:
+            sim.close()
+
     def _annealing(self, betas, timesteps, num_experiments, edge_move_importance_sampling, per_step):
         flags = self._check_classical(edge_move_importance_sampling)
         if per_step:

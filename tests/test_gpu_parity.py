@@ -256,6 +256,42 @@ def test_sampling_equals_plain_runs(pkg, oracle):
         assert (st[:, k] == s_k).all() and (en[:, k] == e_k).all()
 
 
+def test_sampling_double_buffered_slabs(pkg, oracle, monkeypatch):
+    """Many small slabs (two device buffers draining on the copy stream) give the same arrays as
+    one slab; the strided device-to-host copies land every sample at [e, k]."""
+    lat = pkg.Lattice(oracle.square_edges(8), seed_gen=5)
+    en1, st1 = lat.run_monte_carlo_sampling(0.4, 23, 70, None, 2, 1)
+    monkeypatch.setenv("ISING_SAMPLING_SLAB_BYTES", str(70 * 64 * 3))  # 3 samples per slab
+    en2, st2 = lat.run_monte_carlo_sampling(0.4, 23, 70, None, 2, 1)
+    assert en1.shape == (70, 23) and st1.shape == (70, 23, 64)
+    assert (en1 == en2).all() and (st1 == st2).all()
+
+
+@pytest.mark.parametrize("kind", ["2d", "3d_pmj", "general"])
+def test_device_observables_match_sampled_states(pkg, oracle, kind):
+    """run_monte_carlo_observables follows the same trajectories as run_monte_carlo_sampling;
+    E, M and the pair overlaps Q reduced on the device equal the ones computed from the states."""
+    if kind == "2d":
+        lat = pkg.Lattice(oracle.square_edges(10), seed_gen=3)
+    elif kind == "3d_pmj":
+        lat = pkg.Lattice.torus((6, 4, 8), pmj=True, j_seed=2, seed_gen=3)
+    else:
+        rng = np.random.default_rng(0)
+        edges = [((i, (i + 1) % 37), -1.0) for i in range(37)]
+        edges += [((int(a), int(b)), 1.0) for a, b in rng.integers(0, 37, size=(20, 2)) if a != b
+                  and abs(a - b) not in (1, 36)]
+        edges = list({(min(a, b), max(a, b)): ((a, b), j) for (a, b), j in edges}.values())
+        lat = pkg.Lattice(edges, seed_gen=3)
+    E = 77
+    en, st = lat.run_monte_carlo_sampling(0.6, 10, E, None, 4, 2)
+    e2, m, q = lat.run_monte_carlo_observables(0.6, 10, E, 4, 2)
+    s = st.astype(np.int64) * 2 - 1
+    assert e2.shape == (E, 5) and m.shape == (E, 5) and q.shape == (E // 2, 5)
+    assert (e2 == en).all()
+    assert (m == s.sum(-1)).all()
+    assert (q == (s[0:2 * (E // 2):2] * s[1:2 * (E // 2):2]).sum(-1)).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # statistics: production mode must sample the same Boltzmann law as the reference algorithm
 # ---------------------------------------------------------------------------------------------
