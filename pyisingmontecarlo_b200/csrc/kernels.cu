@@ -965,9 +965,11 @@ int launch_energy_from_nsat(const unsigned long long* nsat, uint64_t E, double s
 // DEG > 0: compile-time degree (neighbour loads unrolled and in flight together); DEG = 0: runtime
 template <int K, int ROUNDS, bool PERBETA, int DEG>
 __global__ void __launch_bounds__(256)
-k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t sweep, uint32_t k0,
-                uint32_t k1, uint32_t gw0, GenThresholds th, GenTables tab) {
+k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t sweep, PhiloxKeys pk,
+                uint32_t gw0, GenThresholds th, GenTables tab) {
     constexpr int NCALL = K / 4 + 1;
+    // planes of the n_sat counter: enough for DEG when it is known at compile time
+    constexpr int NPL = DEG == 0 ? 4 : (DEG < 2 ? 1 : (DEG < 4 ? 2 : (DEG < 8 ? 3 : 4)));
     const uint32_t deg = DEG > 0 ? (uint32_t)DEG : g.deg;
     const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
     // block = (wx lanes over replica words, by over sites): no division to split an item index
@@ -986,7 +988,7 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
             for (int k = 0; k < DEG; ++k) {
                 uint32_t c = ~(s ^ x[k] ^ (0u - ((ab >> k) & 1u)));  // satisfied bond
 #pragma unroll
-                for (int l = 0; l < 4; ++l) {
+                for (int l = 0; l < NPL; ++l) {
                     const uint32_t t = cnt[l] & c;
                     cnt[l] ^= c;
                     c = t;
@@ -1016,7 +1018,7 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
                 const uint32_t v = cmin + j;
                 uint32_t o = 0xFFFFFFFFu;
 #pragma unroll
-                for (int l = 0; l < 4; ++l) o &= ((v >> l) & 1u) ? cnt[l] : ~cnt[l];
+                for (int l = 0; l < NPL; ++l) o &= ((v >> l) & 1u) ? cnt[l] : ~cnt[l];
                 oh[j] = o;
                 up |= o;
             }
@@ -1024,7 +1026,7 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
         uint32_t r[NCALL * 4];
 #pragma unroll
         for (int q = 0; q < NCALL; ++q) {
-            const u32x4 o = philox4x32<ROUNDS>(n, gw0 + w, sweep, (uint32_t)q | (TAG_ACCEPT << 24), k0, k1);
+            const u32x4 o = philox4x32_keys<ROUNDS>(n, gw0 + w, sweep, (uint32_t)q | (TAG_ACCEPT << 24), pk);
             r[4 * q + 0] = o.x; r[4 * q + 1] = o.y; r[4 * q + 2] = o.z; r[4 * q + 3] = o.w;
         }
         const uint32_t* tp = PERBETA ? tab.plane + ((size_t)deg * W + w) * GEN_MAX_CLS * 8 : nullptr;
@@ -1039,14 +1041,37 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
             eq &= ~(r[p] ^ t);
         }
         uint32_t flip = ~up | (borrow & ~eq);
+        // tied bits: the first SPARE in straight-line code on the words left over from the calls
+        // above (as in msc_flip_mask), the rare rest in a loop
+        constexpr int SPARE = (4 * NCALL - K) < 2 ? (4 * NCALL - K) : 2;
+#pragma unroll
+        for (int j2 = 0; j2 < SPARE; ++j2) {
+            const uint32_t bit = eq & (0u - eq);
+            const int b = (__ffs((int)eq) - 1) & 31;
+            uint32_t cls = 0;
+#pragma unroll
+            for (int j = 1; j < GEN_MAX_CLS; ++j)
+                if ((uint32_t)j < ncls && (oh[j] & bit)) cls = j;
+            uint32_t lo;
+            if (PERBETA) {
+                lo = __ldg(tab.low + ((size_t)deg * 32 * W + (size_t)w * 32 + b) * GEN_MAX_CLS + cls);
+            } else {
+                lo = th.low[0];
+#pragma unroll
+                for (int j = 1; j < GEN_MAX_CLS; ++j)
+                    if (cls == (uint32_t)j) lo = th.low[j];
+            }
+            if (r[K + j2] < lo) flip |= bit;
+            eq ^= bit;
+        }
         if (eq) {
-            int jj = K;
+            int jj = K + SPARE;
             u32x4 cur = {r[4 * (NCALL - 1)], r[4 * (NCALL - 1) + 1], r[4 * (NCALL - 1) + 2],
                          r[4 * (NCALL - 1) + 3]};
             do {
                 const int b = __ffs((int)eq) - 1;
                 if ((jj & 3) == 0 && jj >= 4 * NCALL)
-                    cur = philox4x32<ROUNDS>(n, gw0 + w, sweep, (uint32_t)(jj >> 2) | (TAG_ACCEPT << 24), k0, k1);
+                    cur = philox4x32_keys<ROUNDS>(n, gw0 + w, sweep, (uint32_t)(jj >> 2) | (TAG_ACCEPT << 24), pk);
                 const int m = jj & 3;
                 const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
                 uint32_t cls = 0;
@@ -1074,12 +1099,13 @@ int launch_sweep_general(const GenSweepArgs& a, const GenGroup& g, cudaStream_t 
     if (blocks > 148ull * 16) blocks = 148ull * 16;
     const dim3 grid((unsigned)blocks);
     const bool pb = a.tables.plane != nullptr;
+    const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
 #define GEN_LAUNCH_D(KK, RR, DD)                                                                  \
     do {                                                                                          \
         if (pb) k_sweep_general<KK, RR, true, DD><<<grid, block, 0, st>>>(                        \
-                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+                    a.spins, g, a.W, a.sweep, pk, a.gw0, a.th, a.tables);                       \
         else k_sweep_general<KK, RR, false, DD><<<grid, block, 0, st>>>(                          \
-                    a.spins, g, a.W, a.sweep, a.key0, a.key1, a.gw0, a.th, a.tables);             \
+                    a.spins, g, a.W, a.sweep, pk, a.gw0, a.th, a.tables);                       \
     } while (0)
 #define GEN_LAUNCH(KK, RR)                                                                        \
     do {                                                                                          \
