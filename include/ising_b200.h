@@ -261,6 +261,20 @@ ISING_API int ising_pt_timesteps_sample(ising_pt *pt, uint64_t timesteps, uint64
  * global row, so any strip decomposition produces the same configuration. */
 ISING_API int ising_strip_create(ising_ctx *ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo, uint64_t row_hi,
                        double j, uint64_t seed, ising_strip **out);
+/* Communication-avoiding variant: `ghost` ghost rows on each side (1 <= ghost <= rows).  After
+ * ONE exchange of 2k boundary rows of both colours (halo_deep / wrap_deep) the strip runs k
+ * sweeps without talking to its neighbours: phase q = 0 .. 2k-1 of the batch updates the local
+ * rows plus ext = 2k-1-q ghost rows on each side (phase_ext); the redundant ghost updates
+ * reproduce the neighbour's bits because the random numbers are keyed by the global row. */
+ISING_API int ising_strip_create_ex(ising_ctx *ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo, uint64_t row_hi,
+                          double j, uint64_t seed, uint32_t ghost, ising_strip **out);
+ISING_API int ising_strip_phase_ext(ising_strip *s, int colour, double beta, uint32_t ext, int advance_sweep,
+                          int sync);
+/* buf = uint32[2 sides][2 colours][depth][Lx/64], host or device.  dir 0: side 0 <- first `depth`
+ * local rows, side 1 <- last `depth` local rows; dir 1: side 0 -> ghost rows above, side 1 ->
+ * ghost rows below.  A strip sends side 0 up and side 1 down. */
+ISING_API int ising_strip_halo_deep(ising_strip *s, int dir, uint32_t depth, void *buf, int sync);
+ISING_API int ising_strip_wrap_deep(ising_strip *s, uint32_t depth);
 ISING_API void ising_strip_destroy(ising_strip *s);
 ISING_API int ising_strip_configure(ising_strip *s, int planes, int rounds);
 ISING_API int ising_strip_set_all(ising_strip *s, int up);

@@ -129,6 +129,10 @@ _SIGNATURES = {
     "ising_pt_total_swaps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ising_pt_timesteps_sample": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "ising_strip_create": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(_P)]),
+    "ising_strip_create_ex": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
+    "ising_strip_phase_ext": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32, C.c_int, C.c_int]),
+    "ising_strip_halo_deep": (C.c_int, [_P, C.c_int, C.c_uint32, _P, C.c_int]),
+    "ising_strip_wrap_deep": (C.c_int, [_P, C.c_uint32]),
     "ising_strip_destroy": (None, [_P]),
     "ising_strip_configure": (C.c_int, [_P, C.c_int, C.c_int]),
     "ising_strip_set_all": (C.c_int, [_P, C.c_int]),
@@ -553,13 +557,14 @@ class Tempering:
 class Strip:
     """Rows [row_lo, row_hi) of one large bit-packed 2D lattice (ising_strip)."""
 
-    def __init__(self, ctx, Lx, Ly, row_lo, row_hi, j=-1.0, seed=0, planes=0, rounds=0):
+    def __init__(self, ctx, Lx, Ly, row_lo, row_hi, j=-1.0, seed=0, planes=0, rounds=0, ghost=1):
         self.ctx, self.Lx, self.Ly = ctx, int(Lx), int(Ly)
         self.row_lo, self.row_hi = int(row_lo), int(row_hi)
         self.words = self.Lx // 64
+        self.ghost = int(ghost)
         h = C.c_void_p()
-        check(lib().ising_strip_create(ctx.handle, self.Lx, self.Ly, self.row_lo, self.row_hi, float(j),
-                                       int(seed) & (2**64 - 1), C.byref(h)), ctx.handle)
+        check(lib().ising_strip_create_ex(ctx.handle, self.Lx, self.Ly, self.row_lo, self.row_hi, float(j),
+                                          int(seed) & (2**64 - 1), self.ghost, C.byref(h)), ctx.handle)
         self.handle = h
         if planes or rounds:
             check(lib().ising_strip_configure(h, int(planes), int(rounds)), ctx.handle)
@@ -573,6 +578,20 @@ class Strip:
     def phase_rows(self, colour, beta, r0, r1, advance=False, sync=False):
         check(lib().ising_strip_phase_rows(self.handle, int(colour), float(beta), int(r0), int(r1),
                                            int(advance), int(sync)), self.ctx.handle)
+
+    def phase_ext(self, colour, beta, ext, advance=False, sync=False):
+        """local rows + ext ghost rows on each side (communication-avoiding batches)"""
+        check(lib().ising_strip_phase_ext(self.handle, int(colour), float(beta), int(ext), int(advance),
+                                          int(sync)), self.ctx.handle)
+
+    def halo_deep(self, direction, depth, buf, sync=True):
+        """buf: numpy uint32[2, 2, depth, words] (host) or an integer device pointer."""
+        p = ptr(buf) if isinstance(buf, np.ndarray) else C.c_void_p(int(buf))
+        check(lib().ising_strip_halo_deep(self.handle, int(direction), int(depth), p, int(sync)),
+              self.ctx.handle)
+
+    def wrap_deep(self, depth):
+        check(lib().ising_strip_wrap_deep(self.handle, int(depth)), self.ctx.handle)
 
     def halo_async(self, colour, direction, buf_ptr):
         check(lib().ising_strip_halo_async(self.handle, int(colour), int(direction),

@@ -1390,10 +1390,13 @@ struct ising_strip {
     double device_ms = 0.0;
 };
 
-extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
-                                  uint64_t row_hi, double j, uint64_t seed, ising_strip** out) {
+extern "C" int ising_strip_create_ex(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
+                                     uint64_t row_hi, double j, uint64_t seed, uint32_t ghost,
+                                     ising_strip** out) {
     if (!ctx || !out) return fail(ctx, ISING_E_INVALID, "ctx/out is NULL");
     *out = nullptr;
+    if (ghost < 1 || ghost > row_hi - row_lo || ghost > 1024)
+        return fail(ctx, ISING_E_INVALID, "ghost depth must be 1..min(rows, 1024)");
     if (Lx < 64 || Lx % 64) return fail(ctx, ISING_E_INVALID, "Lx must be a positive multiple of 64");
     if (Ly < 2 || (Ly & 1)) return fail(ctx, ISING_E_INVALID, "Ly must be even");
     if (row_lo >= row_hi || row_hi > Ly) return fail(ctx, ISING_E_INVALID, "need 0 <= row_lo < row_hi <= Ly");
@@ -1407,9 +1410,10 @@ extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint
     s->g.rows = (uint32_t)(row_hi - row_lo);
     s->g.row0 = (uint32_t)row_lo;
     s->g.Ly = (uint32_t)Ly;
+    s->g.ghost = ghost;
     s->j = j;
     s->seed = seed;
-    s->bytes = (size_t)2 * (s->g.rows + 2) * s->g.Wr * sizeof(uint32_t);
+    s->bytes = (size_t)2 * (s->g.rows + 2 * ghost) * s->g.Wr * sizeof(uint32_t);
     void* p = nullptr;
     CUDA_TRY(ctx, ctx_buf_get(ctx, s->bytes, &p));
     s->d_spins = (uint32_t*)p;
@@ -1423,6 +1427,11 @@ extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *out = s.release();
     return ISING_OK;
+}
+
+extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
+                                  uint64_t row_hi, double j, uint64_t seed, ising_strip** out) {
+    return ising_strip_create_ex(ctx, Lx, Ly, row_lo, row_hi, j, seed, 1, out);
 }
 
 extern "C" void ising_strip_destroy(ising_strip* s) {
@@ -1458,11 +1467,9 @@ extern "C" int ising_strip_set_all(ising_strip* s, int up) {
 // Local rows [r0, r1) of one colour phase; the ghost rows of the OTHER colour must hold the
 // neighbours' boundary rows when r0 == 0 or r1 == rows.  sync = 0 only enqueues (no host wait,
 // no event timing); advance != 0 bumps the sweep counter (call it on the last piece of colour 1).
-extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
-                                      int advance, int sync) {
-    if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
+static int strip_phase_storage_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
+                                    int advance, int sync) {
     ising_ctx* ctx = s->ctx;
-    if (r0 > r1 || r1 > s->g.rows) return fail(ctx, ISING_E_INVALID, "bad row range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     StripSweepArgs a;
     a.spins = s->d_spins;
@@ -1498,14 +1505,83 @@ extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, u
     return ISING_OK;
 }
 
+extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
+                                      int advance, int sync) {
+    if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
+    if (r0 > r1 || r1 > s->g.rows) return fail(s->ctx, ISING_E_INVALID, "bad row range");
+    return strip_phase_storage_rows(s, colour, beta, s->g.ghost + r0, s->g.ghost + r1, advance, sync);
+}
+
+// The local rows plus `ext` ghost rows on each side (ext < ghost): the redundant update of
+// ghost rows reproduces the neighbour's bits (Philox is keyed by the global row), so that after
+// one deep exchange of 2k rows a strip can run k sweeps without communicating: phase q of the
+// batch (q = 0 .. 2k-1) is called with ext = 2k - 1 - q.
+extern "C" int ising_strip_phase_ext(ising_strip* s, int colour, double beta, uint32_t ext, int advance,
+                                     int sync) {
+    if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
+    if (ext >= s->g.ghost) return fail(s->ctx, ISING_E_INVALID, "ext must be < ghost depth");
+    return strip_phase_storage_rows(s, colour, beta, s->g.ghost - ext, s->g.ghost + s->g.rows + ext,
+                                    advance, sync);
+}
+
 // one whole colour phase, blocking; the sweep counter advances after colour 1
 extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     return ising_strip_phase_rows(s, colour, beta, 0, s->g.rows, colour == 1, 1);
 }
 
+// storage row r of a colour (local row l is r = ghost + l)
 static uint32_t* strip_row_ptr(ising_strip* s, int colour, uint32_t r) {
-    return s->d_spins + ((size_t)colour * (s->g.rows + 2) + r) * s->g.Wr;
+    return s->d_spins + ((size_t)colour * (s->g.rows + 2 * s->g.ghost) + r) * s->g.Wr;
+}
+
+// Deep halo staging, both colours at once.  buf = uint32[2 sides][2 colours][depth][Lx/64]
+// (host or device memory).  dir = 0: side 0 <- the first `depth` local rows, side 1 <- the last
+// `depth` local rows; dir = 1: side 0 -> the `depth` ghost rows above the first local row,
+// side 1 -> the ghost rows below the last one.  Rows are in increasing global order.  A strip
+// sends side 0 to the strip above and side 1 to the strip below and receives the upper
+// neighbour's side 1 into its side 0.  sync = 0 only enqueues.
+extern "C" int ising_strip_halo_deep(ising_strip* s, int dir, uint32_t depth, void* buf, int sync) {
+    if (!s || !buf) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    const StripGeom& g = s->g;
+    if (depth < 1 || depth > g.ghost || depth > g.rows)
+        return fail(ctx, ISING_E_INVALID, "depth must be 1..min(ghost, rows)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)depth * g.Wr * 4;
+    uint8_t* b = (uint8_t*)buf;
+    for (int side = 0; side < 2; ++side)
+        for (int c = 0; c < 2; ++c) {
+            uint8_t* slot = b + (size_t)(side * 2 + c) * nb;
+            if (dir == 0) {
+                const uint32_t r = side ? g.ghost + g.rows - depth : g.ghost;
+                CUDA_TRY(ctx, cudaMemcpyAsync(slot, strip_row_ptr(s, c, r), nb, cudaMemcpyDefault, ctx->stream));
+            } else {
+                const uint32_t r = side ? g.ghost + g.rows : g.ghost - depth;
+                CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, c, r), slot, nb, cudaMemcpyDefault, ctx->stream));
+            }
+        }
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// single strip covering the whole lattice: periodic wrap of `depth` rows of both colours
+extern "C" int ising_strip_wrap_deep(ising_strip* s, uint32_t depth) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    ising_ctx* ctx = s->ctx;
+    const StripGeom& g = s->g;
+    if (depth < 1 || depth > g.ghost || depth > g.rows)
+        return fail(ctx, ISING_E_INVALID, "depth must be 1..min(ghost, rows)");
+    if (g.rows != g.Ly) return fail(ctx, ISING_E_INVALID, "wrap needs a strip that holds the whole lattice");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)depth * g.Wr * 4;
+    for (int c = 0; c < 2; ++c) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, c, g.ghost - depth), strip_row_ptr(s, c, g.ghost + g.rows - depth),
+                                      nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, c, g.ghost + g.rows), strip_row_ptr(s, c, g.ghost), nb,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return ISING_OK;
 }
 
 // which = 0: first local row, 1: last local row.  dst holds Lx/64 words, host or device memory.
@@ -1513,7 +1589,7 @@ extern "C" int ising_strip_get_boundary(ising_strip* s, int colour, int which, v
     if (!s || !dst || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaMemcpyAsync(dst, strip_row_ptr(s, colour, which ? s->g.rows : 1),
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, strip_row_ptr(s, colour, which ? s->g.ghost + s->g.rows - 1 : s->g.ghost),
                                   (size_t)s->g.Wr * 4, cudaMemcpyDefault, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ISING_OK;
@@ -1530,11 +1606,11 @@ extern "C" int ising_strip_halo_async(ising_strip* s, int colour, int dir, void*
     const size_t nb = (size_t)s->g.Wr * 4;
     uint8_t* b = (uint8_t*)buf_dev;
     if (dir == 0) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(b, strip_row_ptr(s, colour, 1), nb, cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(b + nb, strip_row_ptr(s, colour, s->g.rows), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(b, strip_row_ptr(s, colour, s->g.ghost), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(b + nb, strip_row_ptr(s, colour, s->g.ghost + s->g.rows - 1), nb, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, 0), b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.rows + 1), b + nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost - 1), b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost + s->g.rows), b + nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return ISING_OK;
 }
@@ -1544,7 +1620,7 @@ extern "C" int ising_strip_set_ghost(ising_strip* s, int colour, int which, cons
     if (!s || !src || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, which ? s->g.rows + 1 : 0), src,
+    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, which ? s->g.ghost + s->g.rows : s->g.ghost - 1), src,
                                   (size_t)s->g.Wr * 4, cudaMemcpyDefault, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ISING_OK;
@@ -1556,9 +1632,9 @@ extern "C" int ising_strip_wrap_local(ising_strip* s, int colour) {
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t nb = (size_t)s->g.Wr * 4;
-    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, 0), strip_row_ptr(s, colour, s->g.rows), nb,
+    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost - 1), strip_row_ptr(s, colour, s->g.ghost + s->g.rows - 1), nb,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.rows + 1), strip_row_ptr(s, colour, 1), nb,
+    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost + s->g.rows), strip_row_ptr(s, colour, s->g.ghost), nb,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     return ISING_OK;
 }

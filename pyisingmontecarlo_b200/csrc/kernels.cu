@@ -1336,7 +1336,7 @@ int launch_energy_real(const uint32_t* spins, uint64_t nvars, uint32_t W, const 
 // call): a draw does not depend on how rows are split into strips.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint32_t r, uint32_t j) {
-    return ((size_t)c * (g.rows + 2) + r) * g.Wr + j;
+    return ((size_t)c * (g.rows + 2 * g.ghost) + r) * g.Wr + j;
 }
 
 // V consecutive words of a row per thread (128-bit loads when V == 4; needs Wr % V == 0)
@@ -1345,12 +1345,12 @@ __global__ void __launch_bounds__(256)
 k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, PhiloxKeys pk,
               uint32_t antiferro, MscThresholds th, uint32_t r_begin, uint32_t r_count) {
     const uint32_t groups = g.Wr / V;
-    // block = (x over the word groups of a row, y over rows): local rows [r_begin, r_begin + r_count)
+    // block = (x over the word groups of a row, y over rows): storage rows [r_begin, r_begin + r_count)
     for (uint32_t rr = blockIdx.y * blockDim.y + threadIdx.y; rr < r_count; rr += gridDim.y * blockDim.y)
     for (uint32_t jg = blockIdx.x * blockDim.x + threadIdx.x; jg < groups; jg += gridDim.x * blockDim.x) {
         const uint32_t j = jg * V;
-        const uint32_t r = r_begin + rr + 1;
-        const uint32_t y = g.row0 + r - 1;  // global row
+        const uint32_t r = r_begin + rr;
+        const uint32_t y = strip_global_row(g, r);
         const uint32_t p = (y + c) & 1u;
         const uint32_t o = 1u - c;
         uint32_t s[V], nx[V], nu[V], nd[V];
@@ -1419,8 +1419,8 @@ __global__ void k_strip_init_random(uint32_t* __restrict__ spins, StripGeom g, u
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t)(i / ((uint64_t)g.rows * g.Wr));
         const uint64_t rem = i - (uint64_t)c * g.rows * g.Wr;
-        const uint32_t r = (uint32_t)(rem / g.Wr) + 1, j = (uint32_t)(rem % g.Wr);
-        const u32x4 v = philox4x32<10>(g.row0 + r - 1, (c << 30) | j, 0u, TAG_INIT << 24, k0, k1);
+        const uint32_t r = (uint32_t)(rem / g.Wr) + g.ghost, j = (uint32_t)(rem % g.Wr);
+        const u32x4 v = philox4x32<10>(g.row0 + r - g.ghost, (c << 30) | j, 0u, TAG_INIT << 24, k0, k1);
         spins[strip_off(g, c, r, j)] = v.x;
     }
 }
@@ -1439,8 +1439,8 @@ k_strip_observables(const uint32_t* __restrict__ spins, StripGeom g, uint32_t an
     const uint64_t total = (uint64_t)g.rows * g.Wr;
     for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
          item += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(item / g.Wr) + 1, j = (uint32_t)(item % g.Wr);
-        const uint32_t y = g.row0 + r - 1;
+        const uint32_t r = (uint32_t)(item / g.Wr) + g.ghost, j = (uint32_t)(item % g.Wr);
+        const uint32_t y = g.row0 + r - g.ghost;
         const uint32_t p = y & 1u;  // colour 0
         const uint32_t s = spins[strip_off(g, 0, r, j)];
         const uint32_t nx = spins[strip_off(g, 1, r, j)];
@@ -1475,9 +1475,9 @@ __global__ void k_strip_unpack(const uint32_t* __restrict__ spins, StripGeom g,
     const uint64_t total = (uint64_t)g.rows * Lx;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(i / Lx) + 1;
+        const uint32_t r = (uint32_t)(i / Lx) + g.ghost;
         const uint32_t x = (uint32_t)(i % Lx);
-        const uint32_t y = g.row0 + r - 1;
+        const uint32_t y = g.row0 + r - g.ghost;
         const uint32_t c = (x + y) & 1u, xh = x >> 1;
         out[i] = (uint8_t)((spins[strip_off(g, c, r, xh >> 5)] >> (xh & 31u)) & 1u);
     }

@@ -156,22 +156,35 @@ int launch_transpose_hist_f64(const double* hist, uint64_t E, uint64_t cw, uint6
                               cudaStream_t st);
 
 // ---- one large 2D lattice, bit-packed along x (config 5), uniform J, row strips ---------------
-// Colour-compacted: S[c][r][j], r = 0 .. rows+1 (r = 0 and rows+1 are ghost rows holding the
-// neighbouring strips' boundary rows), j = 0 .. Wr-1, Wr = Lx / 64 words per colour row; bit b
-// of word j of global row y is site x = 2 (32 j + b) + ((y + c) & 1).
+// Colour-compacted: S[c][r][j], r = 0 .. rows + 2 ghost - 1 (the first and last `ghost` rows
+// hold copies of the neighbouring strips' boundary rows; local row l is r = ghost + l),
+// j = 0 .. Wr-1, Wr = Lx / 64 words per colour row; bit b of word j of global row y is site
+// x = 2 (32 j + b) + ((y + c) & 1).
 struct StripGeom {
     uint32_t Wr;        // words per colour row
     uint32_t rows;      // local rows
-    uint32_t row0;      // global index of local row 1
+    uint32_t row0;      // global index of the first local row
     uint32_t Ly;        // global number of rows
+    uint32_t ghost;     // ghost rows on each side (>= 1)
 };
+// global row of storage row r (ghost rows wrap around the torus)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t strip_global_row(const StripGeom& g, uint32_t r) {
+    uint32_t y = g.row0 + r;          // row0 + r - ghost, modulo Ly
+    if (y < g.ghost) y += g.Ly;
+    y -= g.ghost;
+    if (y >= g.Ly) y -= g.Ly;
+    return y;
+}
 struct StripSweepArgs {
-    uint32_t* spins;    // [2][rows + 2][Wr]
+    uint32_t* spins;    // [2][rows + 2 ghost][Wr]
     StripGeom g;
     uint32_t colour, sweep, key0, key1, antiferro;
     int planes, rounds;
     MscThresholds th;   // classes: n_sat = 3 -> dE = 4|J|, n_sat = 4 -> dE = 8|J|
-    uint32_t r_begin, r_count;  // local rows to update (interior / boundary split)
+    uint32_t r_begin, r_count;  // storage rows to update: [r_begin, r_begin + r_count) within [1, rows + 2 ghost - 1)
 };
 int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st);
 int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,

@@ -56,10 +56,56 @@ def exchange_halos(strip, colour, rank, world, dist=None, group=None, device=Non
         strip.set_ghost(colour, 1, recv_bot.numpy().view(np.uint32))
 
 
+def exchange_deep(strip, depth, rank, world, dist=None, group=None, device=None, bufs=None):
+    """The first / last `depth` rows of BOTH colours -> the neighbouring strips' ghost rows, in
+    one message per neighbour.  After it a strip can run depth // 2 sweeps on its own
+    (Strip.phase_ext), so the per-message latency is paid once per batch instead of per phase.
+
+    strip: .halo_deep(direction, depth, buf[, sync]), .wrap_deep(depth), .words.  bufs: optional
+    (send, recv) int32 device tensors of >= 4 * depth * words elements (enqueue-only path)."""
+    if world == 1:
+        strip.wrap_deep(depth)
+        return
+    import torch
+
+    up, down = (rank - 1) % world, (rank + 1) % world
+    n = 4 * depth * strip.words
+    half = n // 2
+    on_gpu = bufs is not None
+    if on_gpu:
+        send, recv = bufs[0][:n], bufs[1][:n]
+        strip.halo_deep(0, depth, send.data_ptr(), sync=False)
+    else:
+        host = np.empty(n, dtype=np.uint32)
+        strip.halo_deep(0, depth, host)
+        send = torch.from_numpy(host.view(np.int32))
+        recv = torch.empty(n, dtype=torch.int32)
+    if world == 2:   # both neighbours are the same peer: match the messages by order / tag
+        ops = [dist.P2POp(dist.isend, send[:half], up, group=group, tag=0),
+               dist.P2POp(dist.isend, send[half:], down, group=group, tag=1),
+               dist.P2POp(dist.irecv, recv[half:], down, group=group, tag=0),   # peer's first rows
+               dist.P2POp(dist.irecv, recv[:half], up, group=group, tag=1)]     # peer's last rows
+    else:
+        ops = [dist.P2POp(dist.isend, send[:half], up, group=group),
+               dist.P2POp(dist.isend, send[half:], down, group=group),
+               dist.P2POp(dist.irecv, recv[:half], up, group=group),
+               dist.P2POp(dist.irecv, recv[half:], down, group=group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()                      # NCCL: a stream-side wait, the host does not block
+    if on_gpu:
+        strip.halo_deep(1, depth, recv.data_ptr(), sync=False)
+    else:
+        strip.halo_deep(1, depth, np.ascontiguousarray(recv.numpy()).view(np.uint32))
+
+
 class SingleLattice2D:
     """Periodic Lx x Ly lattice with uniform coupling j (j < 0 ferromagnetic, README.md:45-46)."""
 
-    def __init__(self, Lx, Ly=None, j=-1.0, seed=0, *, device=None, process_group=None, planes=0, rounds=0):
+    def __init__(self, Lx, Ly=None, j=-1.0, seed=0, *, device=None, process_group=None, planes=0, rounds=0,
+                 exchange_every=8):
+        """exchange_every = k > 0: strips exchange 2k boundary rows once per k sweeps and update
+        the ghost rows redundantly in between (same bits, 1/(2k) of the messages);
+        exchange_every = 0: one boundary row per colour phase, overlapped with the interior."""
         import torch.distributed as dist
 
         self.Lx, self.Ly, self.j = int(Lx), int(Lx if Ly is None else Ly), float(j)
@@ -85,14 +131,20 @@ class SingleLattice2D:
                 import torch
 
                 self._torch_device = torch.device("cpu")
-        self.strip = nat.Strip(ctx, self.Lx, self.Ly, self.row_lo, self.row_hi, j, seed, planes, rounds)
+        # 2k ghost rows must come from the direct neighbour: k <= (rows of the smallest strip) / 2
+        self._k = max(0, min(int(exchange_every), (self.Ly // self.world) // 2))
+        ghost = max(1, 2 * self._k)
+        self.strip = nat.Strip(ctx, self.Lx, self.Ly, self.row_lo, self.row_hi, j, seed, planes, rounds,
+                               ghost=ghost)
         self.nsites = self.Lx * self.Ly
+        self._bufs = None
         if self._async:
             import torch
 
             w = self.strip.words
-            self._send = torch.empty(2 * w, dtype=torch.int32, device=self._torch_device)
-            self._recv = torch.empty(2 * w, dtype=torch.int32, device=self._torch_device)
+            self._send = torch.empty(4 * ghost * w, dtype=torch.int32, device=self._torch_device)
+            self._recv = torch.empty(4 * ghost * w, dtype=torch.int32, device=self._torch_device)
+            self._bufs = (self._send, self._recv)
 
     def _exchange(self, colour):
         exchange_halos(self.strip, colour, self.rank, self.world, self._dist, self._group, self._torch_device)
@@ -108,8 +160,8 @@ class SingleLattice2D:
         rows = self.row_hi - self.row_lo
         up, down = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         self.strip.halo_async(other, 0, self._send.data_ptr())
-        send_top, send_bot = self._send[:w], self._send[w:]
-        recv_top, recv_bot = self._recv[:w], self._recv[w:]
+        send_top, send_bot = self._send[:w], self._send[w:2 * w]
+        recv_top, recv_bot = self._recv[:w], self._recv[w:2 * w]
         if self.world == 2:   # both neighbours are the same peer: match messages by order
             ops = [dist.P2POp(dist.isend, send_top, up, group=self._group),
                    dist.P2POp(dist.isend, send_bot, down, group=self._group),
@@ -136,13 +188,25 @@ class SingleLattice2D:
     def sweeps(self, betas):
         """One checkerboard sweep per beta: exchange the rows of the colour about to be read,
         update the other colour."""
-        for beta in np.atleast_1d(np.asarray(betas, dtype=np.float64)):
-            for colour in (0, 1):
-                if self._async:
-                    self._phase_overlapped(colour, beta)
-                else:
-                    self._exchange(1 - colour)
-                    self.strip.phase(colour, beta)
+        betas = np.atleast_1d(np.asarray(betas, dtype=np.float64))
+        if self._k == 0:
+            for beta in betas:
+                for colour in (0, 1):
+                    if self._async:
+                        self._phase_overlapped(colour, beta)
+                    else:
+                        self._exchange(1 - colour)
+                        self.strip.phase(colour, beta)
+            return
+        i = 0
+        while i < len(betas):
+            nb = min(self._k, len(betas) - i)          # sweeps in this batch
+            exchange_deep(self.strip, 2 * nb, self.rank, self.world, self._dist, self._group,
+                          self._torch_device, self._bufs)
+            for q in range(2 * nb):
+                self.strip.phase_ext(q & 1, betas[i + q // 2], 2 * nb - 1 - q, advance=bool(q & 1),
+                                     sync=not self._async)
+            i += nb
 
     def _global_sums(self):
         if self._async:

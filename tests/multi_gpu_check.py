@@ -63,9 +63,13 @@ def main():
     assert lt.get_total_swaps() == single.total_swaps() > 0
 
     # (3) strips + NCCL halo exchange == one strip
-    lat = pkg.SingleLattice2D(256, 16 * world, seed=5, device=local)
-    sweep_betas = [0.4, 0.5, 0.3, 0.44]
-    lat.sweeps(sweep_betas)
+    sweep_betas = [0.4, 0.5, 0.3, 0.44, 0.6]
+    lats = [pkg.SingleLattice2D(256, 16 * world, seed=5, device=local, exchange_every=k) for k in (0, 2, 8)]
+    for lat in lats:      # per-phase overlapped exchange, batches of 2 (partial last), one deep batch
+        lat.sweeps(sweep_betas)
+    for other in lats[1:]:
+        assert (other.local_rows() == lats[0].local_rows()).all(), "exchange modes differ"
+    lat = lats[2]
     e = lat.energy()
     whole = nat.Strip(ctx, 256, 16 * world, 0, 16 * world, -1.0, 5)
     for b in sweep_betas:

@@ -27,6 +27,52 @@ def test_single_strip_matches_mirror(native, oracle):
         assert lat.magnetization() == s.sum()
 
 
+@pytest.mark.parametrize("k", [0, 1, 3, 8])
+def test_exchange_batches_match_mirror(native, oracle, k):
+    """exchange_every = k (deep ghosts, redundant ghost-row updates, partial last batch) and the
+    per-phase exchange (k = 0) produce the mirror's bits."""
+    import pyisingmontecarlo_b200 as pkg
+
+    Lx, Ly = 128, 16
+    betas = [0.3, 0.44, 0.8, 0.44, 0.5, 0.2, 0.6]
+    lat = pkg.SingleLattice2D(Lx, Ly, j=-1.0, seed=9, exchange_every=k)
+    assert lat.strip.ghost == max(1, 2 * k)
+    lat.sweeps(betas)
+    en_ref, st_ref = oracle.msc_mirror_single(Lx, Ly, -1.0, 9, betas, 6, 10)
+    assert (lat.local_rows() == st_ref).all()
+    assert lat.energy() == en_ref[-1]
+
+
+def test_deep_strips_reproduce_single_strip(native):
+    """Three strips with 4 ghost rows exchanging 4 boundary rows once per 2 sweeps by hand (what
+    exchange_deep does over NCCL) == one strip with the per-phase wrap."""
+    ctx = native.Context.get(0)
+    Lx, Ly, G = 128, 24, 4
+    whole = native.Strip(ctx, Lx, Ly, 0, Ly, -1.0, 5)
+    bounds = ((0, 6), (6, 16), (16, 24))
+    parts = [native.Strip(ctx, Lx, Ly, lo, hi, -1.0, 5, ghost=G) for lo, hi in bounds]
+    betas = (0.4, 0.5, 0.3, 0.6)
+    for beta in betas:
+        for colour in (0, 1):
+            whole.wrap_local(1 - colour)
+            whole.phase(colour, beta)
+    for i in range(0, len(betas), 2):
+        bufs = []
+        for p in parts:
+            b = np.empty((2, 2, G, p.words), dtype=np.uint32)
+            p.halo_deep(0, G, b)
+            bufs.append(b)
+        for k, p in enumerate(parts):
+            r = np.empty((2, 2, G, p.words), dtype=np.uint32)
+            r[0] = bufs[(k - 1) % 3][1]        # upper neighbour's last rows
+            r[1] = bufs[(k + 1) % 3][0]        # lower neighbour's first rows
+            p.halo_deep(1, G, r)
+        for q in range(4):
+            for p in parts:
+                p.phase_ext(q & 1, betas[i + q // 2], 3 - q, advance=bool(q & 1), sync=True)
+    assert (np.concatenate([p.rows() for p in parts]) == whole.rows()).all()
+
+
 def test_strips_reproduce_single_strip(native):
     """Three strips exchanging boundary rows by hand (what the NCCL send/recv does) == one strip."""
     ctx = native.Context.get(0)
@@ -79,5 +125,5 @@ def test_multi_gpu_parity_under_torchrun(native):
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                           f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(root, "tests", "multi_gpu_check.py")],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=240)
     assert "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

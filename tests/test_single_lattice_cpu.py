@@ -47,6 +47,76 @@ class FakeStrip:
         return self.s[:, 1:-1].copy()
 
 
+class DeepFakeStrip:
+    """FakeStrip with `ghost` ghost rows per side and the deep-halo interface of _native.Strip
+    (halo_deep / wrap_deep / phase_ext); same update rule, keyed by the global row."""
+
+    def __init__(self, Lx, Ly, lo, hi, ghost):
+        self.Lx, self.Ly, self.lo, self.hi, self.g = Lx, Ly, lo, hi, ghost
+        self.words = Lx // 64
+        rng = np.random.default_rng(1)
+        full = rng.integers(0, 2**32, size=(2, Ly, self.words), dtype=np.uint64).astype(np.uint32)
+        self.s = np.zeros((2, hi - lo + 2 * ghost, self.words), dtype=np.uint32)
+        self.s[:, ghost:ghost + hi - lo] = full[:, lo:hi]
+        self.t = 0
+
+    def halo_deep(self, direction, depth, buf, sync=True):
+        g, n = self.g, self.hi - self.lo
+        b = buf.reshape(2, 2, depth, self.words)
+        if direction == 0:
+            b[0] = self.s[:, g:g + depth]
+            b[1] = self.s[:, g + n - depth:g + n]
+        else:
+            self.s[:, g - depth:g] = b[0]
+            self.s[:, g + n:g + n + depth] = b[1]
+
+    def wrap_deep(self, depth):
+        g, n = self.g, self.hi - self.lo
+        self.s[:, g - depth:g] = self.s[:, g + n - depth:g + n]
+        self.s[:, g + n:g + n + depth] = self.s[:, g:g + depth]
+
+    def phase_ext(self, colour, beta, ext, advance=False, sync=False):
+        o, g, n = 1 - colour, self.g, self.hi - self.lo
+        a, b = g - ext, g + n + ext                      # storage rows updated
+        rows = ((np.arange(a, b) - g + self.lo) % self.Ly).astype(np.uint32)[:, None]
+        cur = self.s[colour, a:b]
+        mix = (self.s[o, a - 1:b - 1] ^ np.roll(self.s[o, a:b], 1, axis=1)) + self.s[o, a + 1:b + 1] * np.uint32(3) \
+            + self.s[o, a:b] * np.uint32(5) + rows * np.uint32(2654435761) + np.uint32(self.t)
+        self.s[colour, a:b] = cur ^ mix.astype(np.uint32)
+        if advance:
+            self.t += 1
+
+    def interior(self):
+        return self.s[:, self.g:self.g + self.hi - self.lo].copy()
+
+
+def _run_deep(strip, rank, world, k, dist=None):
+    from pyisingmontecarlo_b200.single_lattice import exchange_deep
+    import torch
+
+    done = 0
+    while done < 5:                       # 5 sweeps in batches of k (the last one shorter)
+        nb = min(k, 5 - done)
+        exchange_deep(strip, 2 * nb, rank, world, dist, None, torch.device("cpu"))
+        for q in range(2 * nb):
+            strip.phase_ext(q & 1, 0.4, 2 * nb - 1 - q, advance=bool(q & 1))
+        done += nb
+    return strip.interior()
+
+
+def _worker_deep(rank, world, port, out, k):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from pyisingmontecarlo_b200.tempering import shard_range
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(20, rank, world)
+    res = _run_deep(DeepFakeStrip(128, 20, lo, hi, 2 * k), rank, world, k, dist)
+    np.save(out + f".{rank}.npy", res)
+    dist.destroy_process_group()
+
+
 def _run(strip, rank, world, dist=None):
     from pyisingmontecarlo_b200.single_lattice import exchange_halos
     import torch
@@ -81,5 +151,23 @@ def test_halo_exchange_over_gloo_equals_whole_lattice(native, tmp_path):
     for world in (2, 3):
         mp.spawn(_worker, args=(world, port + world, out), nprocs=world, join=True)
         whole = _run(FakeStrip(128, 20, 0, 20), 0, 1)
+        got = np.concatenate([np.load(out + f".{r}.npy") for r in range(world)], axis=1)
+        assert (got == whole).all()
+
+
+def test_deep_halo_batches_over_gloo_equal_per_phase_exchange(native, tmp_path):
+    """Communication-avoiding batches (one exchange of 2k rows per k sweeps, ghost rows updated
+    redundantly) give the same lattice as one exchange per colour phase."""
+    import torch.multiprocessing as mp
+
+    whole = _run(FakeStrip(128, 20, 0, 20), 0, 1)
+    for k in (1, 2, 3):
+        assert (_run_deep(DeepFakeStrip(128, 20, 0, 20, 2 * k), 0, 1, k) == whole).all()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "deep")
+    for world, k in ((2, 2), (3, 3)):
+        mp.spawn(_worker_deep, args=(world, port + world, out, k), nprocs=world, join=True)
         got = np.concatenate([np.load(out + f".{r}.npy") for r in range(world)], axis=1)
         assert (got == whole).all()
