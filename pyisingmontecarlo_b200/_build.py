@@ -1,38 +1,57 @@
-"""Builds libising_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libising_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+One object per translation unit, compiled in parallel and only when stale; the objects live in
+csrc/_obj (git-ignored), the linked library next to this file so that it travels with the tree."""
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libising_b200.so")
-SOURCES = ["kernels.cu", "api.cu", "graph.cpp"]
-HEADERS = ["kernels.h", "graph.h", "philox.h", os.path.join("..", "..", "include", "ising_b200.h")]
+SOURCES = ["sweep_stencil.cu", "sweep_general.cu", "strip.cu", "observables.cu", "state_io.cu", "api.cu",
+           "graph.cpp"]
+HEADERS = ["kernels.h", "msc_device.cuh", "graph.h", "philox.h",
+           os.path.join("..", "..", "include", "ising_b200.h")]
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+         "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def _compile(src, force, verbose):
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+    newest = max(_mtime(os.path.join(CSRC, f)) for f in [src] + HEADERS)
+    if not force and _mtime(obj) >= newest:
+        return obj, ""
+    cmd = [_nvcc()] + FLAGS + (["-Xptxas=-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+    return obj, res.stderr
 
 
 def build_native(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> libising_b200.so"""
-    if not force and not _stale():
-        return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [
-        nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-        "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-o", LIB,
-    ] + [os.path.join(CSRC, f) for f in SOURCES]
+    os.makedirs(OBJ, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        done = list(pool.map(lambda s: _compile(s, force, verbose), SOURCES))
+    objs = [o for o, _ in done]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        print("".join(log for _, log in done))
+    if force or _mtime(LIB) < max(_mtime(o) for o in objs):
+        res = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -1,4 +1,4 @@
-// Launch wrappers of the sm_100a kernels (kernels.cu).  Host-callable, no CUDA types beyond
+// Launch wrappers of the sm_100a kernels (sweep_stencil.cu, sweep_general.cu, strip.cu, observables.cu, state_io.cu).  Host-callable, no CUDA types beyond
 // cudaStream_t so that api.cpp stays plain C++.
 #pragma once
 #include <cuda_runtime.h>

@@ -1,0 +1,166 @@
+// sm_100a kernels: one large 2D lattice bit-packed along x in row strips (K7).
+#include "msc_device.cuh"
+
+namespace ising {
+
+// ------------------------------------------------------------------------------------------
+// K7: one large 2D lattice bit-packed along x (config 5).  Same decision rule as the replica-
+// packed kernels; here the 32 bits of a word are 32 same-colour sites of one row, so the two
+// x neighbours are the other-colour word at the same index and that word funnel-shifted by one
+// bit (carry from the adjacent word).  Philox counter = (global row, colour << 30 | word, sweep,
+// call): a draw does not depend on how rows are split into strips.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint32_t r, uint32_t j) {
+    return ((size_t)c * (g.rows + 2 * g.ghost) + r) * g.Wr + j;
+}
+
+// V consecutive words of a row per thread (128-bit loads when V == 4; needs Wr % V == 0)
+template <int K, int ROUNDS, int V>
+__global__ void __launch_bounds__(256)
+k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, PhiloxKeys pk,
+              uint32_t antiferro, MscThresholds th, uint32_t r_begin, uint32_t r_count) {
+    const uint32_t groups = g.Wr / V;
+    // block = (x over the word groups of a row, y over rows): storage rows [r_begin, r_begin + r_count)
+    for (uint32_t rr = blockIdx.y * blockDim.y + threadIdx.y; rr < r_count; rr += gridDim.y * blockDim.y)
+    for (uint32_t jg = blockIdx.x * blockDim.x + threadIdx.x; jg < groups; jg += gridDim.x * blockDim.x) {
+        const uint32_t j = jg * V;
+        const uint32_t r = r_begin + rr;
+        const uint32_t y = strip_global_row(g, r);
+        const uint32_t p = (y + c) & 1u;
+        const uint32_t o = 1u - c;
+        uint32_t s[V], nx[V], nu[V], nd[V];
+        load_words<V>(spins + strip_off(g, c, r, j), s);
+        load_words<V>(spins + strip_off(g, o, r, j), nx);
+        load_words<V>(spins + strip_off(g, o, r - 1, j), nu);
+        load_words<V>(spins + strip_off(g, o, r + 1, j), nd);
+        // the x neighbour one bit over: funnel shift with carry from the adjacent word
+        const uint32_t edge = p ? spins[strip_off(g, o, r, j + V == g.Wr ? 0 : j + V)]
+                                : spins[strip_off(g, o, r, j == 0 ? g.Wr - 1 : j - 1)];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            uint32_t nsh;
+            if (p) nsh = __funnelshift_r(nx[v], v + 1 < V ? nx[v + 1 < V ? v + 1 : v] : edge, 1);
+            else nsh = __funnelshift_l(v > 0 ? nx[v > 0 ? v - 1 : 0] : edge, nx[v], 1);
+            uint32_t a[4] = {~(s[v] ^ nx[v] ^ antiferro), ~(s[v] ^ nsh ^ antiferro),
+                             ~(s[v] ^ nu[v] ^ antiferro), ~(s[v] ^ nd[v] ^ antiferro)};
+            uint32_t b0, b1, b2;
+            count_sat<2>(a, b0, b1, b2);
+            s[v] ^= msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, y, (c << 30) | (j + v), sweep, pk);
+        }
+        store_words<V>(spins + strip_off(g, c, r, j), s);
+    }
+}
+
+template <int V>
+static int strip_phase_dispatch(const StripSweepArgs& a, cudaStream_t st) {
+    const uint32_t groups = a.g.Wr / V;
+    const uint32_t bx = groups >= 256 ? 256 : pow2_ceil(groups);
+    const dim3 block(bx, 256 / bx, 1);
+    uint32_t gx = (groups + bx - 1) / bx;
+    if (gx > 64) gx = 64;
+    uint32_t gy = (a.r_count + block.y - 1) / block.y;
+    const uint32_t gy_cap = (148u * 32u + gx - 1) / gx;
+    if (gy > gy_cap) gy = gy_cap;
+    const dim3 grid(gx, gy, 1);
+#define STRIP_LAUNCH(KK, RR)                                                                     \
+    k_strip_phase<KK, RR, V><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,              \
+                                                     philox_round_keys(a.key0, a.key1), a.antiferro, \
+                                                     a.th, a.r_begin, a.r_count)
+#define STRIP_ROUNDS(KK)                                                                         \
+    do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
+    switch (a.planes) {
+        case 5: STRIP_ROUNDS(5); break;
+        case 6: STRIP_ROUNDS(6); break;
+        case 7: STRIP_ROUNDS(7); break;
+        default: return -1;
+    }
+#undef STRIP_ROUNDS
+#undef STRIP_LAUNCH
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st) {
+    if (a.r_count == 0 || a.g.Wr == 0) return 0;
+    // rows are 16-byte aligned when Wr % 4 == 0 (every row starts at a multiple of Wr words)
+    if (a.g.Wr % 4 == 0) return strip_phase_dispatch<4>(a, st);
+    if (a.g.Wr % 2 == 0) return strip_phase_dispatch<2>(a, st);
+    return strip_phase_dispatch<1>(a, st);
+}
+
+__global__ void k_strip_init_random(uint32_t* __restrict__ spins, StripGeom g, uint32_t k0,
+                                    uint32_t k1) {
+    const uint64_t total = 2ull * g.rows * g.Wr;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / ((uint64_t)g.rows * g.Wr));
+        const uint64_t rem = i - (uint64_t)c * g.rows * g.Wr;
+        const uint32_t r = (uint32_t)(rem / g.Wr) + g.ghost, j = (uint32_t)(rem % g.Wr);
+        const u32x4 v = philox4x32<10>(g.row0 + r - g.ghost, (c << 30) | j, 0u, TAG_INIT << 24, k0, k1);
+        spins[strip_off(g, c, r, j)] = v.x;
+    }
+}
+
+int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,
+                             cudaStream_t st) {
+    k_strip_init_random<<<148 * 8, 256, 0, st>>>(spins, g, key0, key1);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// per-lattice observables are plain popcounts in this layout
+__global__ void __launch_bounds__(256)
+k_strip_observables(const uint32_t* __restrict__ spins, StripGeom g, uint32_t antiferro,
+                    unsigned long long* __restrict__ acc) {
+    unsigned long long nsat = 0, up = 0;
+    const uint64_t total = (uint64_t)g.rows * g.Wr;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
+         item += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(item / g.Wr) + g.ghost, j = (uint32_t)(item % g.Wr);
+        const uint32_t y = g.row0 + r - g.ghost;
+        const uint32_t p = y & 1u;  // colour 0
+        const uint32_t s = spins[strip_off(g, 0, r, j)];
+        const uint32_t nx = spins[strip_off(g, 1, r, j)];
+        uint32_t nsh;
+        if (p) nsh = __funnelshift_r(nx, spins[strip_off(g, 1, r, j + 1 == g.Wr ? 0 : j + 1)], 1);
+        else nsh = __funnelshift_l(spins[strip_off(g, 1, r, j == 0 ? g.Wr - 1 : j - 1)], nx, 1);
+        const uint32_t nu = spins[strip_off(g, 1, r - 1, j)];
+        const uint32_t nd = spins[strip_off(g, 1, r + 1, j)];
+        nsat += __popc(~(s ^ nx ^ antiferro)) + __popc(~(s ^ nsh ^ antiferro)) +
+                __popc(~(s ^ nu ^ antiferro)) + __popc(~(s ^ nd ^ antiferro));
+        up += __popc(s) + __popc(nx);
+    }
+    for (int off = 16; off; off >>= 1) {
+        nsat += __shfl_xor_sync(0xFFFFFFFFu, nsat, off);
+        up += __shfl_xor_sync(0xFFFFFFFFu, up, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nsat) atomicAdd(acc, nsat);
+        if (up) atomicAdd(acc + 1, up);
+    }
+}
+
+int launch_strip_observables(const uint32_t* spins, const StripGeom& g, uint32_t antiferro,
+                             unsigned long long* acc, cudaStream_t st) {
+    k_strip_observables<<<148 * 4, 256, 0, st>>>(spins, g, antiferro, acc);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+__global__ void k_strip_unpack(const uint32_t* __restrict__ spins, StripGeom g,
+                               uint8_t* __restrict__ out) {
+    const uint64_t Lx = 64ull * g.Wr;
+    const uint64_t total = (uint64_t)g.rows * Lx;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / Lx) + g.ghost;
+        const uint32_t x = (uint32_t)(i % Lx);
+        const uint32_t y = g.row0 + r - g.ghost;
+        const uint32_t c = (x + y) & 1u, xh = x >> 1;
+        out[i] = (uint8_t)((spins[strip_off(g, c, r, xh >> 5)] >> (xh & 31u)) & 1u);
+    }
+}
+
+int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st) {
+    k_strip_unpack<<<148 * 8, 256, 0, st>>>(spins, g, out_dev);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace ising
