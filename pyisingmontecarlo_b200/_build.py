@@ -41,6 +41,9 @@ def _compile(src, force, verbose):
 
 def build_native(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> libising_b200.so"""
+    newest = max(_mtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS)
+    if not force and _mtime(LIB) >= newest:
+        return LIB          # up to date (e.g. the prebuilt library that travelled to the GPU box)
     os.makedirs(OBJ, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
         done = list(pool.map(lambda s: _compile(s, force, verbose), SOURCES))
