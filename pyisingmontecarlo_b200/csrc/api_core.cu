@@ -1,0 +1,405 @@
+// C ABI of libising_b200.so (include/ising_b200.h).  Host orchestration only: argument
+// checks with the reference's error behaviour, device buffers, kernel launches, CUDA-event
+// timing.  There is deliberately no CPU implementation behind these entry points: without a
+// CUDA device every compute call fails with ISING_E_CUDA.
+#include "api_internal.h"
+
+// ------------------------------------------------------------------------------------------
+// error reporting, context buffer caches
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_global_error;
+
+int fail(ising_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_global_error = buf;
+    return code;
+}
+
+cudaError_t ctx_buf_get(ising_ctx* ctx, size_t bytes, void** out) {
+    bytes = std::max<size_t>(bytes, 256);
+    for (size_t i = 0; i < ctx->free_bufs.size(); ++i)
+        if (ctx->free_bufs[i].second >= bytes && ctx->free_bufs[i].second <= bytes + bytes / 4 + 4096) {
+            *out = ctx->free_bufs[i].first;
+            ctx->free_bytes -= ctx->free_bufs[i].second;
+            ctx->free_bufs.erase(ctx->free_bufs.begin() + i);
+            return cudaSuccess;
+        }
+    return cudaMalloc(out, bytes);
+}
+
+
+void ctx_buf_put(ising_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>(bytes, 256);
+    const size_t cap = (size_t)8 << 30;
+    if (ctx->free_bytes + bytes > cap || ctx->free_bufs.size() >= 64) {
+        cudaFree(p);
+        return;
+    }
+    ctx->free_bufs.emplace_back(p, bytes);
+    ctx->free_bytes += bytes;
+}
+
+cudaError_t ctx_scratch(ising_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+        ctx->scratch[slot] = nullptr;
+        ctx->scratch_bytes[slot] = 0;
+        const size_t want = std::max<size_t>(bytes, 1 << 20);
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess) return e;
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int ising_abi_version(void) { return ISING_ABI_VERSION; }
+
+extern "C" const char* ising_last_error(const ising_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_global_error.c_str();
+}
+
+static int ctx_create_impl(int device, cudaStream_t external, bool use_external, ising_ctx** out);
+
+extern "C" int ising_ctx_create(int device, ising_ctx** out) {
+    return ctx_create_impl(device, nullptr, false, out);
+}
+
+// Same, but every launch and copy of this context goes to the caller's stream (e.g. torch's
+// current stream): work is then ordered with the caller's own kernels and NCCL calls without
+// host synchronisation.
+extern "C" int ising_ctx_create_on_stream(int device, void* cuda_stream, ising_ctx** out) {
+    return ctx_create_impl(device, (cudaStream_t)cuda_stream, true, out);
+}
+
+static int ctx_create_impl(int device, cudaStream_t external, bool use_external, ising_ctx** out) {
+    if (!out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, ISING_E_CUDA,
+                    "no CUDA device available (%s); libising_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, ISING_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, ISING_E_CUDA,
+                    "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    std::unique_ptr<ising_ctx> ctx(new ising_ctx);
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (use_external) {
+        ctx->stream = external;
+        ctx->owns_stream = false;
+    } else {
+        CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    }
+    CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev1));
+    *out = ctx.release();
+    return ISING_OK;
+}
+
+extern "C" void ising_ctx_destroy(ising_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->ev_filled[b]) cudaEventDestroy(ctx->ev_filled[b]);
+        if (ctx->ev_drained[b]) cudaEventDestroy(ctx->ev_drained[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    for (void* p : ctx->scratch) cudaFree(p);
+    for (auto& b : ctx->free_bufs) cudaFree(b.first);
+    delete ctx;
+}
+
+extern "C" int ising_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return fail(nullptr, ISING_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return ISING_OK;
+}
+
+extern "C" void ising_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// graph
+// ------------------------------------------------------------------------------------------
+static int upload_stencil_masks(ising_ctx* ctx, ising_graph* g) {
+    const HostGraph& h = g->h;
+    if (h.kind == ISING_KIND_GENERAL || h.uniform_sign) return ISING_OK;
+    const int dim = h.kind == ISING_KIND_STENCIL3D ? 3 : 2;
+    const uint64_t Lx = h.dims[0], Ly = h.dims[1], Lz = h.dims[2];
+    const uint64_t Lxh = Lx / 2, rows = Ly * Lz, halfN = h.nvars / 2;
+    std::vector<uint32_t> m((size_t)2 * 2 * dim * halfN);
+    auto sgn = [&](uint64_t x, uint64_t y, uint64_t z, int d) -> uint32_t {
+        const uint64_t n = x + Lx * (y + Ly * z);
+        return ((h.fwd_sign[n] >> d) & 1) ? 0xFFFFFFFFu : 0u;
+    };
+    for (uint32_t c = 0; c < 2; ++c)
+        for (uint64_t r = 0; r < rows; ++r) {
+            const uint64_t z = r / Ly, y = r % Ly;
+            const uint32_t p = (uint32_t)((y + z + c) & 1);
+            for (uint64_t xh = 0; xh < Lxh; ++xh) {
+                const uint64_t x = 2 * xh + p;
+                const uint64_t xm = x == 0 ? Lx - 1 : x - 1;
+                const uint64_t ym = y == 0 ? Ly - 1 : y - 1, zm = z == 0 ? Lz - 1 : z - 1;
+                uint32_t* base = m.data() + (size_t)c * 2 * dim * halfN + r * Lxh + xh;
+                // k = 0: neighbour stored at the same half-index (x+1 if p == 0 else x-1)
+                // k = 1: the other x neighbour;  2: y-1  3: y+1  4: z-1  5: z+1
+                const uint32_t jxp = sgn(x, y, z, 0), jxm = sgn(xm, y, z, 0);
+                base[0 * halfN] = p == 0 ? jxp : jxm;
+                base[1 * halfN] = p == 0 ? jxm : jxp;
+                base[2 * halfN] = sgn(x, ym, z, 1);
+                base[3 * halfN] = sgn(x, y, z, 1);
+                if (dim == 3) {
+                    base[4 * halfN] = sgn(x, y, zm, 2);
+                    base[5 * halfN] = sgn(x, y, z, 2);
+                }
+            }
+        }
+    CUDA_TRY(ctx, dev_alloc(&g->d_jmask, m.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jmask, m.data(), m.size() * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice));
+    return ISING_OK;
+}
+
+int ensure_csr_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->d_row) return ISING_OK;
+    g->h.build_csr();
+    const HostGraph& h = g->h;
+    CUDA_TRY(ctx, dev_alloc(&g->d_row, h.row.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_nbr, h.nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_jv, h.jv.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_bias, h.nvars));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_row, h.row.data(), h.row.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_nbr, h.nbr.data(), h.nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jv, h.jv.data(), h.jv.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<double> b(h.nvars, 0.0);
+    if (h.has_bias) b = h.bias;
+    CUDA_TRY(ctx, cudaMemcpy(g->d_bias, b.data(), h.nvars * 8, cudaMemcpyHostToDevice));
+    return ISING_OK;
+}
+
+int ensure_csr32_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->d_row32) return ISING_OK;
+    HostGraph& h = g->h;
+    h.build_csr();
+    if (2 * h.nedges > 0xFFFFFFFFull) return fail(ctx, ISING_E_UNSUPPORTED, "too many edges");
+    const uint64_t N = h.nvars;
+    std::vector<uint32_t> row32(N + 1);
+    for (uint64_t n = 0; n <= N; ++n) row32[n] = (uint32_t)h.row[n];
+    std::vector<uint8_t> anti8(h.jv.size());
+    for (size_t k = 0; k < h.jv.size(); ++k) anti8[k] = h.jv[k] > 0;
+    CUDA_TRY(ctx, dev_alloc(&g->d_row32, row32.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_nbr32, h.nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_anti8, anti8.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_row32, row32.data(), row32.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_nbr32, h.nbr.data(), h.nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_anti8, anti8.data(), anti8.size(), cudaMemcpyHostToDevice));
+    return ISING_OK;
+}
+
+// arbitrary real couplings and biases: colour-ordered site list + float CSR values
+int ensure_real_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->real_built) return ISING_OK;
+    int rc = ensure_csr32_on_device(ctx, g);
+    if (rc) return rc;
+    rc = ensure_csr_on_device(ctx, g);  // f64 couplings / biases for the energy kernel
+    if (rc) return rc;
+    HostGraph& h = g->h;
+    const uint64_t N = h.nvars;
+    std::vector<uint32_t> order(N);
+    g->color_off.assign(h.ncolors + 1, 0);
+    for (uint64_t n = 0; n < N; ++n) g->color_off[h.color_of(n) + 1]++;
+    for (int c = 0; c < h.ncolors; ++c) g->color_off[c + 1] += g->color_off[c];
+    std::vector<uint32_t> fill(g->color_off.begin(), g->color_off.end() - 1);
+    for (uint64_t n = 0; n < N; ++n) order[fill[h.color_of(n)]++] = (uint32_t)n;
+    std::vector<float> jf(h.jv.begin(), h.jv.end());
+    std::vector<float> bf(N, 0.f);
+    if (h.has_bias) for (uint64_t n = 0; n < N; ++n) bf[n] = (float)h.bias[n];
+    CUDA_TRY(ctx, dev_alloc(&g->d_csites, order.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_jf, jf.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_biasf, bf.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_csites, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jf, jf.data(), jf.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_biasf, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice));
+    g->real_built = true;
+    return ISING_OK;
+}
+
+// colour x degree groups of a graph whose couplings all have the same magnitude
+int ensure_general_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->gen_built) return ISING_OK;
+    HostGraph& h = g->h;
+    if (!h.integer_classes)
+        return fail(ctx, ISING_E_INVALID, "internal: integer-class kernels on a real-valued graph");
+    {
+        const int rc32 = ensure_csr32_on_device(ctx, g);
+        if (rc32) return rc32;
+    }
+    const uint64_t N = h.nvars;
+    const int ncol = h.ncolors;
+    // bucket sites by (colour, degree)
+    std::vector<std::vector<uint32_t>> bucket((size_t)ncol * (GEN_MAX_DEG + 1));
+    for (uint64_t n = 0; n < N; ++n) {
+        const uint32_t deg = (uint32_t)(h.row[n + 1] - h.row[n]);
+        bucket[(size_t)h.color_of(n) * (GEN_MAX_DEG + 1) + deg].push_back((uint32_t)n);
+    }
+    std::vector<uint32_t> sites, nbr, anti;
+    struct Off { size_t s, n; uint32_t count, deg; int color; };
+    std::vector<Off> offs;
+    for (int c = 0; c < ncol; ++c)
+        for (int d = 0; d <= GEN_MAX_DEG; ++d) {
+            const auto& b = bucket[(size_t)c * (GEN_MAX_DEG + 1) + d];
+            if (b.empty()) continue;
+            Off o{sites.size(), nbr.size(), (uint32_t)b.size(), (uint32_t)d, c};
+            sites.insert(sites.end(), b.begin(), b.end());
+            nbr.resize(nbr.size() + (size_t)d * b.size());
+            for (size_t i = 0; i < b.size(); ++i) {
+                const uint64_t lo = h.row[b[i]];
+                uint32_t bits = 0;
+                for (int k = 0; k < d; ++k) {
+                    nbr[o.n + (size_t)k * b.size() + i] = h.nbr[lo + k];
+                    if (h.jv[lo + k] > 0) bits |= 1u << k;
+                }
+                anti.push_back(bits);
+            }
+            offs.push_back(o);
+        }
+    CUDA_TRY(ctx, dev_alloc(&g->d_gsites, sites.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_gnbr, nbr.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_ganti, anti.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_gsites, sites.data(), sites.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_gnbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_ganti, anti.data(), anti.size() * 4, cudaMemcpyHostToDevice));
+    for (const Off& o : offs) {
+        GenGroup gg;
+        gg.sites = g->d_gsites + o.s;
+        gg.nbr = g->d_gnbr + o.n;
+        gg.anti = g->d_ganti + o.s;
+        gg.count = o.count;
+        gg.deg = o.deg;
+        g->gen_groups.push_back(gg);
+        g->gen_group_color.push_back(o.color);
+    }
+    g->gen_ncolors = ncol;
+    g->gen_built = true;
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_from_edges(ising_ctx* ctx, uint64_t nvars, uint64_t nedges,
+                                      const uint64_t* a, const uint64_t* b, const double* j,
+                                      const double* biases, ising_graph** out) {
+    if (!ctx || !out) return fail(ctx, ISING_E_INVALID, "ctx/out is NULL");
+    *out = nullptr;
+    if (nedges && (!a || !b || !j)) return fail(ctx, ISING_E_INVALID, "edge arrays are NULL");
+    std::unique_ptr<ising_graph> g(new ising_graph);
+    g->ctx = ctx;
+    const std::string msg = compile_from_edges(nvars, nedges, a, b, j, biases, &g->h);
+    if (!msg.empty()) return fail(ctx, ISING_E_INVALID, "%s", msg.c_str());
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int rc = upload_stencil_masks(ctx, g.get());
+    if (rc) return rc;
+    *out = g.release();
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_torus(ising_ctx* ctx, int dim, const uint64_t* L, double j0, int pmj,
+                                 uint64_t j_seed, ising_graph** out) {
+    if (!ctx || !out || !L) return fail(ctx, ISING_E_INVALID, "ctx/out/L is NULL");
+    *out = nullptr;
+    std::unique_ptr<ising_graph> g(new ising_graph);
+    g->ctx = ctx;
+    const std::string msg = make_torus(dim, L, j0, pmj, j_seed, &g->h);
+    if (!msg.empty()) return fail(ctx, ISING_E_INVALID, "%s", msg.c_str());
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int rc = upload_stencil_masks(ctx, g.get());
+    if (rc) return rc;
+    *out = g.release();
+    return ISING_OK;
+}
+
+extern "C" void ising_graph_destroy(ising_graph* g) {
+    if (!g) return;
+    if (g->ctx) cudaSetDevice(g->ctx->device);
+    cudaFree(g->d_jmask);
+    cudaFree(g->d_row);
+    cudaFree(g->d_nbr);
+    cudaFree(g->d_jv);
+    cudaFree(g->d_bias);
+    cudaFree(g->d_gsites);
+    cudaFree(g->d_gnbr);
+    cudaFree(g->d_ganti);
+    cudaFree(g->d_row32);
+    cudaFree(g->d_nbr32);
+    cudaFree(g->d_anti8);
+    cudaFree(g->d_csites);
+    cudaFree(g->d_jf);
+    cudaFree(g->d_biasf);
+    delete g;
+}
+
+extern "C" int ising_graph_get_info(const ising_graph* g, ising_graph_info* out) {
+    if (!g || !out) return fail(nullptr, ISING_E_INVALID, "graph/out is NULL");
+    const HostGraph& h = g->h;
+    out->nvars = h.nvars;
+    out->nedges = h.nedges;
+    out->kind = h.kind;
+    out->ncolors = h.ncolors;
+    out->max_degree = h.max_degree;
+    out->integer_classes = h.integer_classes ? 1 : 0;
+    out->dims[0] = h.dims[0];
+    out->dims[1] = h.dims[1];
+    out->dims[2] = h.dims[2];
+    out->jabs = h.jabs;
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_get_colors(const ising_graph* g, uint32_t* colors) {
+    if (!g || !colors) return fail(nullptr, ISING_E_INVALID, "graph/colors is NULL");
+    for (uint64_t n = 0; n < g->h.nvars; ++n) colors[n] = g->h.color_of(n);
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_get_edges(const ising_graph* g, uint64_t* a, uint64_t* b, double* j) {
+    if (!g || !a || !b || !j) return fail(nullptr, ISING_E_INVALID, "graph/arrays NULL");
+    for (uint64_t e = 0; e < g->h.nedges; ++e) g->h.edge_at(e, a + e, b + e, j + e);
+    return ISING_OK;
+}
+
+extern "C" int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t* out) {
+    if (n && !out) return fail(nullptr, ISING_E_INVALID, "out is NULL");
+    make_seeds(seed_gen, n, out);
+    return ISING_OK;
+}
+
+extern "C" int ising_schedule_betas(const uint64_t* st, const double* sb, uint64_t n,
+                                    uint64_t timesteps, int linear, double* out) {
+    if ((n && (!st || !sb)) || (timesteps && !out))
+        return fail(nullptr, ISING_E_INVALID, "schedule arrays are NULL");
+    if (!schedule_betas(st, sb, n, timesteps, linear != 0, out))
+        return fail(nullptr, ISING_E_INVALID, "annealing schedule has fewer than two stops");
+    return ISING_OK;
+}

@@ -1,0 +1,307 @@
+// C ABI: one large 2D lattice in row strips (ising_strip_*).
+#include "api_internal.h"
+
+// ------------------------------------------------------------------------------------------
+// one large 2D lattice in row strips (config 5)
+// ------------------------------------------------------------------------------------------
+struct ising_strip {
+    ising_ctx* ctx = nullptr;
+    StripGeom g{};
+    uint64_t Lx = 0;
+    uint32_t* d_spins = nullptr;
+    size_t bytes = 0;
+    unsigned long long* d_acc = nullptr;
+    double j = -1.0;
+    uint64_t seed = 0, sweep = 0, launches = 0;
+    int planes = 6, rounds = 10;
+    double device_ms = 0.0;
+};
+
+extern "C" int ising_strip_create_ex(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
+                                     uint64_t row_hi, double j, uint64_t seed, uint32_t ghost,
+                                     ising_strip** out) {
+    if (!ctx || !out) return fail(ctx, ISING_E_INVALID, "ctx/out is NULL");
+    *out = nullptr;
+    if (ghost < 1 || ghost > row_hi - row_lo || ghost > 1024)
+        return fail(ctx, ISING_E_INVALID, "ghost depth must be 1..min(rows, 1024)");
+    if (Lx < 64 || Lx % 64) return fail(ctx, ISING_E_INVALID, "Lx must be a positive multiple of 64");
+    if (Ly < 2 || (Ly & 1)) return fail(ctx, ISING_E_INVALID, "Ly must be even");
+    if (row_lo >= row_hi || row_hi > Ly) return fail(ctx, ISING_E_INVALID, "need 0 <= row_lo < row_hi <= Ly");
+    if (Ly > 0xFFFFFFFFull || Lx / 64 > 0x3FFFFFFFull) return fail(ctx, ISING_E_INVALID, "lattice too large");
+    if (!(fabs(j) > 0.0) || !std::isfinite(j)) return fail(ctx, ISING_E_INVALID, "j must be finite and non-zero");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<ising_strip> s(new ising_strip);
+    s->ctx = ctx;
+    s->Lx = Lx;
+    s->g.Wr = (uint32_t)(Lx / 64);
+    s->g.rows = (uint32_t)(row_hi - row_lo);
+    s->g.row0 = (uint32_t)row_lo;
+    s->g.Ly = (uint32_t)Ly;
+    s->g.ghost = ghost;
+    s->j = j;
+    s->seed = seed;
+    s->bytes = (size_t)2 * (s->g.rows + 2 * ghost) * s->g.Wr * sizeof(uint32_t);
+    void* p = nullptr;
+    CUDA_TRY(ctx, ctx_buf_get(ctx, s->bytes, &p));
+    s->d_spins = (uint32_t*)p;
+    cudaError_t e = ctx_buf_get(ctx, 2 * sizeof(unsigned long long), &p);
+    if (e != cudaSuccess) { ctx_buf_put(ctx, s->d_spins, s->bytes); CUDA_TRY(ctx, e); }
+    s->d_acc = (unsigned long long*)p;
+    CUDA_TRY(ctx, cudaMemsetAsync(s->d_spins, 0, s->bytes, ctx->stream));
+    if (launch_strip_init_random(s->d_spins, s->g, (uint32_t)seed, (uint32_t)(seed >> 32), ctx->stream) < 0)
+        return fail(ctx, ISING_E_CUDA, "strip init launch failed");
+    s->launches++;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = s.release();
+    return ISING_OK;
+}
+
+extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
+                                  uint64_t row_hi, double j, uint64_t seed, ising_strip** out) {
+    return ising_strip_create_ex(ctx, Lx, Ly, row_lo, row_hi, j, seed, 1, out);
+}
+
+extern "C" void ising_strip_destroy(ising_strip* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    ctx_buf_put(s->ctx, s->d_spins, s->bytes);
+    ctx_buf_put(s->ctx, s->d_acc, 2 * sizeof(unsigned long long));
+    delete s;
+}
+
+extern "C" int ising_strip_configure(ising_strip* s, int planes, int rounds) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    if (planes) {
+        if (planes < 5 || planes > 7) return fail(s->ctx, ISING_E_INVALID, "planes must be 5..7");
+        s->planes = planes;
+    }
+    if (rounds) {
+        if (rounds != 7 && rounds != 10) return fail(s->ctx, ISING_E_INVALID, "rounds must be 7 or 10");
+        s->rounds = rounds;
+    }
+    return ISING_OK;
+}
+
+extern "C" int ising_strip_set_all(ising_strip* s, int up) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    CUDA_TRY(s->ctx, cudaSetDevice(s->ctx->device));
+    CUDA_TRY(s->ctx, cudaMemsetAsync(s->d_spins, up ? 0xFF : 0x00, s->bytes, s->ctx->stream));
+    CUDA_TRY(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    return ISING_OK;
+}
+
+// Local rows [r0, r1) of one colour phase; the ghost rows of the OTHER colour must hold the
+// neighbours' boundary rows when r0 == 0 or r1 == rows.  sync = 0 only enqueues (no host wait,
+// no event timing); advance != 0 bumps the sweep counter (call it on the last piece of colour 1).
+static int strip_phase_storage_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
+                                    int advance, int sync) {
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    StripSweepArgs a;
+    a.spins = s->d_spins;
+    a.g = s->g;
+    a.colour = (uint32_t)colour;
+    a.sweep = (uint32_t)s->sweep;
+    a.key0 = (uint32_t)s->seed;
+    a.key1 = (uint32_t)(s->seed >> 32);
+    a.antiferro = s->j > 0 ? 0xFFFFFFFFu : 0u;
+    a.planes = s->planes;
+    a.rounds = s->rounds;
+    a.r_begin = (uint32_t)r0;
+    a.r_count = (uint32_t)(r1 - r0);
+    memset(&a.th, 0, sizeof a.th);
+    for (int c = 0; c < 2; ++c) {
+        const uint64_t T = threshold64(beta, 4.0 * (c + 1) * fabs(s->j), s->planes);
+        for (int pl = 0; pl < s->planes; ++pl)
+            a.th.plane[c][pl] = ((T >> (s->planes + 31 - pl)) & 1ull) ? 0xFFFFFFFFu : 0u;
+        a.th.low[c] = (uint32_t)(T & 0xFFFFFFFFull);
+    }
+    if (sync) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (launch_strip_phase(a, ctx->stream) < 0)
+        return fail(ctx, ISING_E_CUDA, "strip phase launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (a.r_count) s->launches++;
+    if (sync) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        s->device_ms += ms;
+    }
+    if (advance) s->sweep++;
+    return ISING_OK;
+}
+
+extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
+                                      int advance, int sync) {
+    if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
+    if (r0 > r1 || r1 > s->g.rows) return fail(s->ctx, ISING_E_INVALID, "bad row range");
+    return strip_phase_storage_rows(s, colour, beta, s->g.ghost + r0, s->g.ghost + r1, advance, sync);
+}
+
+// The local rows plus `ext` ghost rows on each side (ext < ghost): the redundant update of
+// ghost rows reproduces the neighbour's bits (Philox is keyed by the global row), so that after
+// one deep exchange of 2k rows a strip can run k sweeps without communicating: phase q of the
+// batch (q = 0 .. 2k-1) is called with ext = 2k - 1 - q.
+extern "C" int ising_strip_phase_ext(ising_strip* s, int colour, double beta, uint32_t ext, int advance,
+                                     int sync) {
+    if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
+    if (ext >= s->g.ghost) return fail(s->ctx, ISING_E_INVALID, "ext must be < ghost depth");
+    return strip_phase_storage_rows(s, colour, beta, s->g.ghost - ext, s->g.ghost + s->g.rows + ext,
+                                    advance, sync);
+}
+
+// one whole colour phase, blocking; the sweep counter advances after colour 1
+extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    return ising_strip_phase_rows(s, colour, beta, 0, s->g.rows, colour == 1, 1);
+}
+
+// storage row r of a colour (local row l is r = ghost + l)
+static uint32_t* strip_row_ptr(ising_strip* s, int colour, uint32_t r) {
+    return s->d_spins + ((size_t)colour * (s->g.rows + 2 * s->g.ghost) + r) * s->g.Wr;
+}
+
+// Deep halo staging, both colours at once.  buf = uint32[2 sides][2 colours][depth][Lx/64]
+// (host or device memory).  dir = 0: side 0 <- the first `depth` local rows, side 1 <- the last
+// `depth` local rows; dir = 1: side 0 -> the `depth` ghost rows above the first local row,
+// side 1 -> the ghost rows below the last one.  Rows are in increasing global order.  A strip
+// sends side 0 to the strip above and side 1 to the strip below and receives the upper
+// neighbour's side 1 into its side 0.  sync = 0 only enqueues.
+extern "C" int ising_strip_halo_deep(ising_strip* s, int dir, uint32_t depth, void* buf, int sync) {
+    if (!s || !buf) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    const StripGeom& g = s->g;
+    if (depth < 1 || depth > g.ghost || depth > g.rows)
+        return fail(ctx, ISING_E_INVALID, "depth must be 1..min(ghost, rows)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)depth * g.Wr * 4;
+    uint8_t* b = (uint8_t*)buf;
+    for (int side = 0; side < 2; ++side)
+        for (int c = 0; c < 2; ++c) {
+            uint8_t* slot = b + (size_t)(side * 2 + c) * nb;
+            if (dir == 0) {
+                const uint32_t r = side ? g.ghost + g.rows - depth : g.ghost;
+                CUDA_TRY(ctx, cudaMemcpyAsync(slot, strip_row_ptr(s, c, r), nb, cudaMemcpyDefault, ctx->stream));
+            } else {
+                const uint32_t r = side ? g.ghost + g.rows : g.ghost - depth;
+                CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, c, r), slot, nb, cudaMemcpyDefault, ctx->stream));
+            }
+        }
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// single strip covering the whole lattice: periodic wrap of `depth` rows of both colours
+extern "C" int ising_strip_wrap_deep(ising_strip* s, uint32_t depth) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    ising_ctx* ctx = s->ctx;
+    const StripGeom& g = s->g;
+    if (depth < 1 || depth > g.ghost || depth > g.rows)
+        return fail(ctx, ISING_E_INVALID, "depth must be 1..min(ghost, rows)");
+    if (g.rows != g.Ly) return fail(ctx, ISING_E_INVALID, "wrap needs a strip that holds the whole lattice");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)depth * g.Wr * 4;
+    for (int c = 0; c < 2; ++c) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, c, g.ghost - depth), strip_row_ptr(s, c, g.ghost + g.rows - depth),
+                                      nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, c, g.ghost + g.rows), strip_row_ptr(s, c, g.ghost), nb,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return ISING_OK;
+}
+
+// which = 0: first local row, 1: last local row.  dst holds Lx/64 words, host or device memory.
+extern "C" int ising_strip_get_boundary(ising_strip* s, int colour, int which, void* dst) {
+    if (!s || !dst || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, strip_row_ptr(s, colour, which ? s->g.ghost + s->g.rows - 1 : s->g.ghost),
+                                  (size_t)s->g.Wr * 4, cudaMemcpyDefault, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// Device-to-device halo staging without a host wait, for contexts created on the caller's
+// stream: dir = 0 copies both boundary rows of `colour` into buf_dev[0..Wr) (first row) and
+// buf_dev[Wr..2Wr) (last row); dir = 1 copies buf_dev[0..Wr) into the ghost row above the first
+// row and buf_dev[Wr..2Wr) into the ghost row below the last row.
+extern "C" int ising_strip_halo_async(ising_strip* s, int colour, int dir, void* buf_dev) {
+    if (!s || !buf_dev || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)s->g.Wr * 4;
+    uint8_t* b = (uint8_t*)buf_dev;
+    if (dir == 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(b, strip_row_ptr(s, colour, s->g.ghost), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(b + nb, strip_row_ptr(s, colour, s->g.ghost + s->g.rows - 1), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost - 1), b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost + s->g.rows), b + nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return ISING_OK;
+}
+
+// which = 0: ghost row above the first local row, 1: ghost row below the last local row
+extern "C" int ising_strip_set_ghost(ising_strip* s, int colour, int which, const void* src) {
+    if (!s || !src || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, which ? s->g.ghost + s->g.rows : s->g.ghost - 1), src,
+                                  (size_t)s->g.Wr * 4, cudaMemcpyDefault, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// single strip covering the whole lattice: periodic wrap of its own boundary rows
+extern "C" int ising_strip_wrap_local(ising_strip* s, int colour) {
+    if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)s->g.Wr * 4;
+    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost - 1), strip_row_ptr(s, colour, s->g.ghost + s->g.rows - 1), nb,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(strip_row_ptr(s, colour, s->g.ghost + s->g.rows), strip_row_ptr(s, colour, s->g.ghost), nb,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    return ISING_OK;
+}
+
+// local sums: satisfied bonds (colour-0 sites see every bond once; needs colour-1 ghosts) and up spins
+extern "C" int ising_strip_observables(ising_strip* s, uint64_t* nsat, uint64_t* up) {
+    if (!s || !nsat || !up) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->d_acc, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (launch_strip_observables(s->d_spins, s->g, s->j > 0 ? 0xFFFFFFFFu : 0u, s->d_acc, ctx->stream) < 0)
+        return fail(ctx, ISING_E_CUDA, "strip observables launch failed");
+    s->launches++;
+    unsigned long long h[2];
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, s->d_acc, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *nsat = h[0];
+    *up = h[1];
+    return ISING_OK;
+}
+
+extern "C" int ising_strip_get_rows(ising_strip* s, uint8_t* rows_out) {
+    if (!s || !rows_out) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)s->g.rows * s->Lx;
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, bytes, &dv));
+    if (launch_strip_unpack(s->d_spins, s->g, (uint8_t*)dv, ctx->stream) < 0)
+        return fail(ctx, ISING_E_CUDA, "strip unpack launch failed");
+    s->launches++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+extern "C" int ising_strip_get_stats(ising_strip* s, uint64_t* launches, double* device_ms, int reset) {
+    if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
+    if (launches) *launches = s->launches;
+    if (device_ms) *device_ms = s->device_ms;
+    if (reset) { s->launches = 0; s->device_ms = 0.0; }
+    return ISING_OK;
+}
