@@ -363,3 +363,40 @@ def test_checkpoints_resume_bit_for_bit(pkg, oracle, tmp_path):
     assert (sx2 == sz2).all() and (ex2 == ez2).all() and x.get_total_swaps() == z.get_total_swaps()
     with pytest.raises(IOError):
         pkg.ClassicIsing.read_from_file(path)
+
+
+def test_reference_readme_usage_runs_unchanged(oracle):
+    """The usage section of the reference's README.md (lines 44-62), verbatim through the
+    `py_monte_carlo` module name: same calls, same return layouts; energies equal the Hamiltonian
+    of the returned states (README.md:46, "J*Sza*Szb so positive is antiferromagnetic")."""
+    import py_monte_carlo
+
+    edges = [
+        ((0, 1), 1.0),
+        ((1, 2), -1.0)
+    ]
+    lat = py_monte_carlo.Lattice(edges)
+    beta, timesteps, num_experiments = 1.0, 20, 40
+    betas = [(0, 0.1), (timesteps, 2.0)]
+
+    def hamiltonian(states):
+        s = states.astype(np.int64) * 2 - 1
+        return 1.0 * s[..., 0] * s[..., 1] - 1.0 * s[..., 1] * s[..., 2]
+
+    e, s = lat.run_monte_carlo(beta, timesteps, num_experiments)
+    assert e.shape == (40,) and s.shape == (40, 3) and s.dtype == np.bool_ and (e == hamiltonian(s)).all()
+    e, s = lat.run_monte_carlo_sampling(beta, timesteps, num_experiments)
+    assert e.shape == (40, 20) and s.shape == (40, 20, 3) and (e == hamiltonian(s)).all()
+    e, s = lat.run_monte_carlo_annealing(betas, timesteps, num_experiments)
+    assert e.shape == (40,) and s.shape == (40, 3) and (e == hamiltonian(s)).all()
+    e, s = lat.run_monte_carlo_annealing_and_get_energies(betas, timesteps, num_experiments)
+    assert e.shape == (40, 20) and s.shape == (40, 3) and (e[:, -1] == hamiltonian(s)).all()
+    # cold end of the anneal: the chain's two ground states have E = -2
+    lat.set_seed_gen(1)
+    e, _ = lat.run_monte_carlo(6.0, 200, 64)
+    assert (e == -2.0).mean() > 0.9
+    lat.set_transverse_field(1.0)
+    with pytest.raises(ValueError, match="Cannot run classic monte carlo with transverse field"):
+        lat.run_monte_carlo(beta, timesteps, num_experiments)
+    with pytest.raises(NotImplementedError):
+        lat.run_quantum_monte_carlo(beta, timesteps, num_experiments)
