@@ -331,8 +331,19 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     a.tplane = nullptr;
     a.tlow = nullptr;
     memset(&a.th, 0, sizeof a.th);
-    const int rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
-                                              (uint32_t)(s->lay.W * 32), ctx->stream);
+    // smallest lattices: one thread-block cluster, hardware barrier between the phases
+    static const bool no_cluster = getenv("ISING_NO_CLUSTER") != nullptr;  // A/B knob
+    int rc = 0;
+    if (!hist && !no_cluster) {
+        rc = launch_sweeps_stencil_cluster(a, (const MscThresholds*)dv, (uint32_t)nt, ctx->stream);
+        if (rc < 0) {
+            cudaGetLastError();
+            rc = 0;
+        }
+    }
+    if (rc == 0)
+        rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
+                                        (uint32_t)(s->lay.W * 32), ctx->stream);
     if (rc < 0) {
         cudaGetLastError();
         return 0;  // e.g. too many blocks to be co-resident: use the per-phase launches

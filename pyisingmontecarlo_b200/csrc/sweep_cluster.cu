@@ -1,0 +1,139 @@
+// sm_100a kernel: whole chunks of sweeps of a SMALL lattice inside one thread-block cluster.
+// A colour phase of BASELINE config 1 (32x32, 64 experiments) is 1024 site-words of work: any
+// launch or grid-wide barrier costs more than the update itself.  Here up to 8 CTAs (one
+// portable cluster) hold the lattice, every thread owns at most a few site-words, and the two
+// colour phases of every sweep are separated by the hardware cluster barrier (~0.2 us) instead
+// of a cooperative grid barrier (~2.5 us) or a kernel boundary.  Same decision rule and Philox
+// stream as every other sweep kernel, so the results are bit-identical.
+#include "sweep_phase.cuh"
+
+namespace ising {
+
+template <int DIM, bool PMJ, int K, int ROUNDS, int V>
+__global__ void __launch_bounds__(256)
+k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict__ jmask, Layout L,
+                        uint32_t sweep0, uint32_t nsweeps, PhiloxKeys pk, uint32_t gw0,
+                        uint32_t antiferro, const MscThresholds* __restrict__ th_table,
+                        uint32_t by_row, uint32_t row_step, uint32_t step_y, uint32_t step_z) {
+    __shared__ MscThresholds th[2];  // this sweep's thresholds / the next sweep's, prefetched
+    cg::cluster_group cluster = cg::this_cluster();
+    const size_t csz = (size_t)L.halfN * L.W;
+    const size_t jsz = (size_t)2 * DIM * L.halfN;
+    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
+    constexpr uint32_t TW = sizeof(MscThresholds) / 4;
+    if (tid < TW) reinterpret_cast<uint32_t*>(&th[0])[tid] = reinterpret_cast<const uint32_t*>(th_table)[tid];
+    __syncthreads();
+    for (uint32_t t = 0; t < nsweeps; ++t) {
+        const MscThresholds& cur = th[t & 1u];
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, false, false, false, true>(
+            spins, spins + csz, PMJ ? jmask : nullptr, L, 0u, sweep0 + t, pk, gw0, antiferro, cur,
+            nullptr, row_step, step_y, step_z, nullptr, nullptr, nullptr, by_row);
+        // the other buffer was last read before the previous barrier: refill it now, so that the
+        // load overlaps the barrier (made visible to the block by the barrier itself)
+        if (t + 1 < nsweeps && tid < TW)
+            reinterpret_cast<uint32_t*>(&th[(t + 1) & 1u])[tid] =
+                reinterpret_cast<const uint32_t*>(th_table + t + 1)[tid];
+        cluster.sync();  // release / acquire at cluster scope: the other colour is complete
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, false, false, false, true>(
+            spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, cur,
+            nullptr, row_step, step_y, step_z, nullptr, nullptr, nullptr, by_row);
+        cluster.sync();
+    }
+}
+
+static_assert(sizeof(MscThresholds) / 4 <= 32, "threshold block is staged by the first warp");
+
+// ncta = CTAs of the cluster: 8 (portable) or 16 (opt-in size, when the GPC has room for it)
+template <int DIM, bool PMJ, int ROUNDS, int V>
+static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                            cudaStream_t st, uint32_t ncta) {
+    const Layout& L = a.lay;
+    const uint32_t groups = L.W / V;
+    const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
+    uint32_t by_row = pow2_ceil(L.Lxh);
+    if (wx * by_row > 256) by_row = 256 / wx;
+    const uint32_t per_row = wx * by_row;                              // threads working on one row
+    const uint64_t want = ((uint64_t)L.rows * per_row + ncta - 1) / ncta;  // threads per CTA
+    uint32_t threads = pow2_ceil((uint32_t)(want > 256 ? 256 : want));
+    if (threads < per_row) threads = per_row;
+    if (threads < 32) threads = 32;
+    const uint32_t rpb = threads / per_row;                             // rows a block works on at a time
+    if (rpb == 0) return 0;
+    uint32_t g = (L.rows + rpb - 1) / rpb;
+    if (g > ncta) g = ncta;
+    const uint32_t row_step = g * rpb;
+    const dim3 block(wx, by_row * rpb, 1);
+    auto kernel = k_sweep_stencil_cluster<DIM, PMJ, 6, ROUNDS, V>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g, 1, 1);
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (g > 8) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+            return -1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1)
+            return -1;
+    }
+    const cudaError_t e = cudaLaunchKernelEx(
+        &cfg, kernel, a.spins, a.jmask, L, a.sweep, nsweeps, philox_round_keys(a.key0, a.key1), a.gw0,
+        a.antiferro, th_dev, by_row, row_step, row_step % L.Ly, row_step / L.Ly);
+    return e == cudaSuccess ? 1 : -1;
+}
+
+template <int DIM, bool PMJ, int ROUNDS, int V>
+static int cluster_launch(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                          cudaStream_t st) {
+    static const int max_cta = getenv("ISING_CLUSTER_MAX") ? atoi(getenv("ISING_CLUSTER_MAX")) : 16;  // A/B knob
+    // more than one word per thread of a portable cluster: try the 16-CTA cluster first
+    if ((uint64_t)a.lay.halfN * a.lay.W > 2048 && max_cta >= 16) {
+        const int rc = cluster_launch_n<DIM, PMJ, ROUNDS, V>(a, th_dev, nsweeps, st, 16);
+        if (rc > 0) return rc;
+        cudaGetLastError();
+    }
+    return cluster_launch_n<DIM, PMJ, ROUNDS, V>(a, th_dev, nsweeps, st, 8);
+}
+
+template <int DIM, bool PMJ, int V>
+static int cluster_rounds(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                          cudaStream_t st) {
+    return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V>(a, th_dev, nsweeps, st)
+                         : cluster_launch<DIM, PMJ, 10, V>(a, th_dev, nsweeps, st);
+}
+
+// Largest lattice taken: 16384 site-words per colour (4 per thread of a 16-CTA cluster).
+// Returns 1 if launched, 0 if this configuration is not handled here, -1 on a launch error.
+int launch_sweeps_stencil_cluster(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
+                                  cudaStream_t st) {
+    const Layout& L = a.lay;
+    const bool d3 = L.kind == ISING_KIND_STENCIL3D;
+    if (!d3 && L.kind != ISING_KIND_STENCIL2D) return 0;
+    if (a.planes != 6 || a.tplane || a.nsat_out) return 0;
+    const uint64_t words = (uint64_t)L.halfN * L.W;
+    static const uint64_t max_words = getenv("ISING_CLUSTER_WORDS") ? strtoull(getenv("ISING_CLUSTER_WORDS"), nullptr, 10) : 16384;
+    if (words > max_words) return 0;
+    const bool pmj = a.jmask != nullptr;
+    // fewest words per thread that still gives every site-word its own thread (4096 threads)
+    int V = 1;
+    if (words > 4096 && L.W % 2 == 0) V = 2;
+    if (words > 8192 && L.W % 4 == 0) V = 4;
+#define CLUSTER_V(VV)                                                                            \
+    (d3 ? (pmj ? cluster_rounds<3, true, VV>(a, th_dev, nsweeps, st)                              \
+               : cluster_rounds<3, false, VV>(a, th_dev, nsweeps, st))                            \
+        : (pmj ? cluster_rounds<2, true, VV>(a, th_dev, nsweeps, st)                              \
+               : cluster_rounds<2, false, VV>(a, th_dev, nsweeps, st)))
+    if (V == 4) return CLUSTER_V(4);
+    if (V == 2) return CLUSTER_V(2);
+    return CLUSTER_V(1);
+#undef CLUSTER_V
+}
+
+}  // namespace ising

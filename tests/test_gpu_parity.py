@@ -122,6 +122,33 @@ def test_many_replica_words_match_mirror(native, oracle, pkg):
     _mirror_check(native, oracle, g2, 2080, 18, [0.44, 0.5], 6, 10)
 
 
+@pytest.mark.parametrize("dims,pmj,E,rounds", [
+    ((32, 32), False, 64, 10),     # BASELINE config 1: 1024 site-words per colour, one per thread
+    ((8, 6), False, 33, 10),       # 2 words, ragged last word
+    ((6, 10), True, 96, 7),        # 3 words (scalar path), +-J, Philox-7
+    ((4, 6, 4), True, 70, 10),     # 3D +-J
+    ((8, 8, 8), True, 256, 10),    # 2048 words: exactly one word per thread of the full cluster
+    ((8, 8, 8), False, 512, 10),   # 4096 words: 2 words per thread
+    ((16, 8, 8), True, 512, 10),   # 8192 words: 4 words per thread, more rows than one pass
+    ((16, 16, 8), True, 512, 10),  # 16384 words: above the cluster limit (cooperative kernel)
+])
+def test_cluster_kernel_matches_mirror(native, oracle, pkg, dims, pmj, E, rounds):
+    """Sweeps without per-sweep energies on small lattices run inside one thread-block cluster
+    (hardware barrier between the colour phases): same bits as the scalar mirror, at every
+    thread / word mapping the launcher can choose."""
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, dims, j0=1.0 if pmj else -1.0, pmj=pmj, j_seed=5)
+    betas = np.linspace(0.2, 1.1, 7)
+    sim = native.Sim(g, E, 99, rounds=rounds)
+    sim.sweeps(betas[:4])
+    sim.sweeps(betas[4:])          # second chunk continues the sweep counter
+    a, b, j = g.edges()
+    en_ref, st_ref = oracle.msc_mirror(a, b, j, g.nvars, g.colors(), E, 99, betas, planes=6, rounds=rounds)
+    assert (sim.states() == st_ref).all()
+    assert (sim.energies() == en_ref).all()
+    assert sim.stats()["kernel_launches"] <= 8     # 2 chunk launches + init / read-back kernels
+
+
 def test_edge_list_torus_is_recognised_and_equal(native, oracle, pkg):
     """The same lattice through Lattice(edges) (config-1 labelling) and through the additive
     torus constructor takes the stencil path and gives identical bits."""
