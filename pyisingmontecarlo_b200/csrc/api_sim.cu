@@ -301,9 +301,6 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     *err = ISING_OK;
     if (s->general || s->real || s->perbeta || nt == 0) return 0;
     if ((uint64_t)s->lay.halfN * s->lay.W > (1ull << 19)) return 0;  // big enough to fill the GPU
-    // measured on B200 (32^2 and 16^3): with fused energies the per-block reduction in lock-step
-    // only pays off for few replica words (6.6 vs 10.2 us/sweep at W = 2, 18.9 vs 13.6 at W = 32)
-    if (hist && s->lay.W > 8) return 0;
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
     std::vector<MscThresholds> th(nt);
@@ -334,14 +331,18 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     // smallest lattices: one thread-block cluster, hardware barrier between the phases
     static const bool no_cluster = getenv("ISING_NO_CLUSTER") != nullptr;  // A/B knob
     int rc = 0;
-    if (!hist && !no_cluster) {
-        rc = launch_sweeps_stencil_cluster(a, (const MscThresholds*)dv, (uint32_t)nt, ctx->stream);
+    if (!no_cluster) {
+        rc = launch_sweeps_stencil_cluster(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
+                                           (uint32_t)(s->lay.W * 32), ctx->stream);
         if (rc < 0) {
             cudaGetLastError();
             rc = 0;
         }
     }
-    if (rc == 0)
+    // cooperative kernel, measured on B200 (32^2 and 16^3): with fused energies the per-block
+    // reduction in lock-step only pays off for few replica words (6.6 vs 10.2 us/sweep at W = 2,
+    // 18.9 vs 13.6 at W = 32)
+    if (rc == 0 && !(hist && s->lay.W > 8))
         rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
                                         (uint32_t)(s->lay.W * 32), ctx->stream);
     if (rc < 0) {

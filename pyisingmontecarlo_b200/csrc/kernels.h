@@ -57,9 +57,9 @@ int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st);
 int launch_sweeps_stencil_coop(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
                                unsigned long long* hist, uint32_t cw, cudaStream_t st);
 // The same for lattices of at most 8192 site-words per colour, inside ONE thread-block cluster
-// (hardware cluster barrier between the colour phases); K = 6, no fused energies.
+// (hardware cluster barrier between the colour phases); K = 6.  hist as above.
 int launch_sweeps_stencil_cluster(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
-                                  cudaStream_t st);
+                                  unsigned long long* hist, uint32_t cw, cudaStream_t st);
 // n_sat[e] += number of satisfied bonds of experiment e (one colour's sites cover every bond)
 int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layout& lay,
                         uint32_t antiferro, unsigned long long* nsat, cudaStream_t st);

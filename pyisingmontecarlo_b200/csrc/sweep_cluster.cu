@@ -9,12 +9,16 @@
 
 namespace ising {
 
-template <int DIM, bool PMJ, int K, int ROUNDS, int V>
+// ACC: the second colour phase of sweep t adds its post-flip satisfied-bond counts to
+// nsat_hist[t * cw + e] (per-sweep energies, lattice.rs:454), reduced per CTA.
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
 __global__ void __launch_bounds__(256)
 k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict__ jmask, Layout L,
                         uint32_t sweep0, uint32_t nsweeps, PhiloxKeys pk, uint32_t gw0,
                         uint32_t antiferro, const MscThresholds* __restrict__ th_table,
-                        uint32_t by_row, uint32_t row_step, uint32_t step_y, uint32_t step_z) {
+                        uint32_t by_row, uint32_t row_step, uint32_t step_y, uint32_t step_z,
+                        unsigned long long* __restrict__ nsat_hist, uint32_t cw) {
+    extern __shared__ uint32_t sm[];  // ACC: reduction scratch
     __shared__ MscThresholds th[2];  // this sweep's thresholds / the next sweep's, prefetched
     cg::cluster_group cluster = cg::this_cluster();
     const size_t csz = (size_t)L.halfN * L.W;
@@ -34,9 +38,10 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
             reinterpret_cast<uint32_t*>(&th[(t + 1) & 1u])[tid] =
                 reinterpret_cast<const uint32_t*>(th_table + t + 1)[tid];
         cluster.sync();  // release / acquire at cluster scope: the other colour is complete
-        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, false, false, false, true>(
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, false, false, true>(
             spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, cur,
-            nullptr, row_step, step_y, step_z, nullptr, nullptr, nullptr, by_row);
+            ACC ? nsat_hist + (size_t)t * cw : nullptr, row_step, step_y, step_z, sm, nullptr, nullptr,
+            by_row);
         cluster.sync();
     }
 }
@@ -44,9 +49,9 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
 static_assert(sizeof(MscThresholds) / 4 <= 32, "threshold block is staged by the first warp");
 
 // ncta = CTAs of the cluster: 8 (portable) or 16 (opt-in size, when the GPC has room for it)
-template <int DIM, bool PMJ, int ROUNDS, int V>
+template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC>
 static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
-                            cudaStream_t st, uint32_t ncta) {
+                            unsigned long long* hist, uint32_t cw, cudaStream_t st, uint32_t ncta) {
     const Layout& L = a.lay;
     const uint32_t groups = L.W / V;
     const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
@@ -63,11 +68,19 @@ static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uin
     if (g > ncta) g = ncta;
     const uint32_t row_step = g * rpb;
     const dim3 block(wx, by_row * rpb, 1);
-    auto kernel = k_sweep_stencil_cluster<DIM, PMJ, 6, ROUNDS, V>;
+    size_t smem = 0;
+    if (ACC) {
+        // the fused counters are flushed once per phase: every thread must stay below their capacity
+        const uint32_t items = ((L.rows + row_step - 1) / row_step) * ((L.Lxh + by_row - 1) / by_row);
+        if (items >= (uint32_t)SW_MAX_ITEMS || block.y < (unsigned)V) return 0;
+        const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
+        smem = (size_t)planes * block.x * block.y * sizeof(uint32_t);
+    }
+    auto kernel = k_sweep_stencil_cluster<DIM, PMJ, 6, ROUNDS, V, ACC>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g, 1, 1);
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -85,34 +98,37 @@ static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uin
     }
     const cudaError_t e = cudaLaunchKernelEx(
         &cfg, kernel, a.spins, a.jmask, L, a.sweep, nsweeps, philox_round_keys(a.key0, a.key1), a.gw0,
-        a.antiferro, th_dev, by_row, row_step, row_step % L.Ly, row_step / L.Ly);
+        a.antiferro, th_dev, by_row, row_step, row_step % L.Ly, row_step / L.Ly, hist, cw);
     return e == cudaSuccess ? 1 : -1;
 }
 
-template <int DIM, bool PMJ, int ROUNDS, int V>
+template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC>
 static int cluster_launch(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
-                          cudaStream_t st) {
+                          unsigned long long* hist, uint32_t cw, cudaStream_t st) {
     static const int max_cta = getenv("ISING_CLUSTER_MAX") ? atoi(getenv("ISING_CLUSTER_MAX")) : 16;  // A/B knob
     // more than one word per thread of a portable cluster: try the 16-CTA cluster first
     if ((uint64_t)a.lay.halfN * a.lay.W > 2048 && max_cta >= 16) {
-        const int rc = cluster_launch_n<DIM, PMJ, ROUNDS, V>(a, th_dev, nsweeps, st, 16);
+        const int rc = cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC>(a, th_dev, nsweeps, hist, cw, st, 16);
         if (rc > 0) return rc;
         cudaGetLastError();
     }
-    return cluster_launch_n<DIM, PMJ, ROUNDS, V>(a, th_dev, nsweeps, st, 8);
+    return cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC>(a, th_dev, nsweeps, hist, cw, st, 8);
 }
 
 template <int DIM, bool PMJ, int V>
 static int cluster_rounds(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
-                          cudaStream_t st) {
-    return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V>(a, th_dev, nsweeps, st)
-                         : cluster_launch<DIM, PMJ, 10, V>(a, th_dev, nsweeps, st);
+                          unsigned long long* hist, uint32_t cw, cudaStream_t st) {
+    if (hist)
+        return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, true>(a, th_dev, nsweeps, hist, cw, st)
+                             : cluster_launch<DIM, PMJ, 10, V, true>(a, th_dev, nsweeps, hist, cw, st);
+    return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, false>(a, th_dev, nsweeps, nullptr, cw, st)
+                         : cluster_launch<DIM, PMJ, 10, V, false>(a, th_dev, nsweeps, nullptr, cw, st);
 }
 
 // Largest lattice taken: 16384 site-words per colour (4 per thread of a 16-CTA cluster).
 // Returns 1 if launched, 0 if this configuration is not handled here, -1 on a launch error.
 int launch_sweeps_stencil_cluster(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
-                                  cudaStream_t st) {
+                                  unsigned long long* hist, uint32_t cw, cudaStream_t st) {
     const Layout& L = a.lay;
     const bool d3 = L.kind == ISING_KIND_STENCIL3D;
     if (!d3 && L.kind != ISING_KIND_STENCIL2D) return 0;
@@ -120,16 +136,19 @@ int launch_sweeps_stencil_cluster(const SweepArgs& a, const MscThresholds* th_de
     const uint64_t words = (uint64_t)L.halfN * L.W;
     static const uint64_t max_words = getenv("ISING_CLUSTER_WORDS") ? strtoull(getenv("ISING_CLUSTER_WORDS"), nullptr, 10) : 16384;
     if (words > max_words) return 0;
+    // with fused energies the per-CTA reduction dominates beyond 8192 words (measured: 12.9 vs
+    // 12.5 us/sweep for 32^2 x 1024 experiments against one launch per colour phase)
+    if (hist && words > 8192) return 0;
     const bool pmj = a.jmask != nullptr;
     // fewest words per thread that still gives every site-word its own thread (4096 threads)
     int V = 1;
     if (words > 4096 && L.W % 2 == 0) V = 2;
     if (words > 8192 && L.W % 4 == 0) V = 4;
 #define CLUSTER_V(VV)                                                                            \
-    (d3 ? (pmj ? cluster_rounds<3, true, VV>(a, th_dev, nsweeps, st)                              \
-               : cluster_rounds<3, false, VV>(a, th_dev, nsweeps, st))                            \
-        : (pmj ? cluster_rounds<2, true, VV>(a, th_dev, nsweeps, st)                              \
-               : cluster_rounds<2, false, VV>(a, th_dev, nsweeps, st)))
+    (d3 ? (pmj ? cluster_rounds<3, true, VV>(a, th_dev, nsweeps, hist, cw, st)                    \
+               : cluster_rounds<3, false, VV>(a, th_dev, nsweeps, hist, cw, st))                  \
+        : (pmj ? cluster_rounds<2, true, VV>(a, th_dev, nsweeps, hist, cw, st)                    \
+               : cluster_rounds<2, false, VV>(a, th_dev, nsweeps, hist, cw, st)))
     if (V == 4) return CLUSTER_V(4);
     if (V == 2) return CLUSTER_V(2);
     return CLUSTER_V(1);
