@@ -299,15 +299,17 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
 static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsigned long long* hist,
                            int* err) {
     *err = ISING_OK;
-    if (s->general || s->real || s->perbeta || nt == 0) return 0;
+    if (s->general || s->real || nt == 0) return 0;
+    if (s->perbeta && (hist || s->planes != 6)) return 0;
     if ((uint64_t)s->lay.halfN * s->lay.W > (1ull << 19)) return 0;  // big enough to fill the GPU
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
-    std::vector<MscThresholds> th(nt);
-    for (uint64_t t = 0; t < nt; ++t) fill_thresholds(h, betas[t], s->planes, &th[t]);
+    // per-sweep thresholds (one beta per sweep); per-replica betas use the sim's device tables
+    std::vector<MscThresholds> th(s->perbeta ? 0 : nt);
+    for (uint64_t t = 0; t < th.size(); ++t) fill_thresholds(h, betas[t], s->planes, &th[t]);
     void* dv = nullptr;
-    cudaError_t e = ctx_scratch(ctx, 3, nt * sizeof(MscThresholds), &dv);
-    if (e == cudaSuccess)
+    cudaError_t e = ctx_scratch(ctx, 3, std::max<size_t>(1, th.size()) * sizeof(MscThresholds), &dv);
+    if (e == cudaSuccess && !th.empty())
         e = cudaMemcpyAsync(dv, th.data(), nt * sizeof(MscThresholds), cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) {
         *err = fail(ctx, ISING_E_CUDA, "threshold table upload: %s", cudaGetErrorString(e));
@@ -325,8 +327,8 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     a.planes = s->planes;
     a.rounds = s->rounds;
     a.nsat_out = nullptr;
-    a.tplane = nullptr;
-    a.tlow = nullptr;
+    a.tplane = s->perbeta ? s->d_tplane : nullptr;
+    a.tlow = s->perbeta ? s->d_tlow : nullptr;
     memset(&a.th, 0, sizeof a.th);
     // smallest lattices: one thread-block cluster, hardware barrier between the phases
     static const bool no_cluster = getenv("ISING_NO_CLUSTER") != nullptr;  // A/B knob
@@ -342,7 +344,7 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     // cooperative kernel, measured on B200 (32^2 and 16^3): with fused energies the per-block
     // reduction in lock-step only pays off for few replica words (6.6 vs 10.2 us/sweep at W = 2,
     // 18.9 vs 13.6 at W = 32)
-    if (rc == 0 && !(hist && s->lay.W > 8))
+    if (rc == 0 && !s->perbeta && !(hist && s->lay.W > 8))
         rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
                                         (uint32_t)(s->lay.W * 32), ctx->stream);
     if (rc < 0) {
@@ -403,7 +405,7 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
         while (t < nsweeps) {
             const uint64_t nt = std::min<uint64_t>(4096, nsweeps - t);
             int err = ISING_OK;
-            const int done = betas ? sim_sweeps_coop(s, betas + t, nt, nullptr, &err) : 0;
+            const int done = (betas || s->perbeta) ? sim_sweeps_coop(s, betas ? betas + t : nullptr, nt, nullptr, &err) : 0;
             if (done < 0) return err;
             if (done) { t += nt; continue; }
             for (uint64_t k = 0; k < nt; ++k) {

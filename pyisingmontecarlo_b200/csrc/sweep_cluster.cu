@@ -11,13 +11,17 @@ namespace ising {
 
 // ACC: the second colour phase of sweep t adds its post-flip satisfied-bond counts to
 // nsat_hist[t * cw + e] (per-sweep energies, lattice.rs:454), reduced per CTA.
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC>
+// PERBETA: every replica bit at its own inverse temperature (parallel tempering between two
+// swap steps): thresholds come from the bit-sliced tables instead of th_table.
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool PERBETA>
 __global__ void __launch_bounds__(256)
 k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict__ jmask, Layout L,
                         uint32_t sweep0, uint32_t nsweeps, PhiloxKeys pk, uint32_t gw0,
                         uint32_t antiferro, const MscThresholds* __restrict__ th_table,
                         uint32_t by_row, uint32_t row_step, uint32_t step_y, uint32_t step_z,
-                        unsigned long long* __restrict__ nsat_hist, uint32_t cw) {
+                        unsigned long long* __restrict__ nsat_hist, uint32_t cw,
+                        const uint32_t* __restrict__ tplane, const uint32_t* __restrict__ tlow) {
+    static_assert(!(PERBETA && ACC), "tempering reads energies at swap steps only");
     extern __shared__ uint32_t sm[];  // ACC: reduction scratch
     __shared__ MscThresholds th[2];  // this sweep's thresholds / the next sweep's, prefetched
     cg::cluster_group cluster = cg::this_cluster();
@@ -25,22 +29,23 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
     const size_t jsz = (size_t)2 * DIM * L.halfN;
     const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
     constexpr uint32_t TW = sizeof(MscThresholds) / 4;
-    if (tid < TW) reinterpret_cast<uint32_t*>(&th[0])[tid] = reinterpret_cast<const uint32_t*>(th_table)[tid];
+    if (!PERBETA && tid < TW)
+        reinterpret_cast<uint32_t*>(&th[0])[tid] = reinterpret_cast<const uint32_t*>(th_table)[tid];
     __syncthreads();
     for (uint32_t t = 0; t < nsweeps; ++t) {
         const MscThresholds& cur = th[t & 1u];
-        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, false, false, false, true>(
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, false, false, PERBETA, true>(
             spins, spins + csz, PMJ ? jmask : nullptr, L, 0u, sweep0 + t, pk, gw0, antiferro, cur,
-            nullptr, row_step, step_y, step_z, nullptr, nullptr, nullptr, by_row);
+            nullptr, row_step, step_y, step_z, nullptr, tplane, tlow, by_row);
         // the other buffer was last read before the previous barrier: refill it now, so that the
         // load overlaps the barrier (made visible to the block by the barrier itself)
-        if (t + 1 < nsweeps && tid < TW)
+        if (!PERBETA && t + 1 < nsweeps && tid < TW)
             reinterpret_cast<uint32_t*>(&th[(t + 1) & 1u])[tid] =
                 reinterpret_cast<const uint32_t*>(th_table + t + 1)[tid];
         cluster.sync();  // release / acquire at cluster scope: the other colour is complete
-        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, false, false, true>(
+        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, false, PERBETA, true>(
             spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, cur,
-            ACC ? nsat_hist + (size_t)t * cw : nullptr, row_step, step_y, step_z, sm, nullptr, nullptr,
+            ACC ? nsat_hist + (size_t)t * cw : nullptr, row_step, step_y, step_z, sm, tplane, tlow,
             by_row);
         cluster.sync();
     }
@@ -49,7 +54,7 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
 static_assert(sizeof(MscThresholds) / 4 <= 32, "threshold block is staged by the first warp");
 
 // ncta = CTAs of the cluster: 8 (portable) or 16 (opt-in size, when the GPC has room for it)
-template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC>
+template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC, bool PERBETA>
 static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
                             unsigned long long* hist, uint32_t cw, cudaStream_t st, uint32_t ncta) {
     const Layout& L = a.lay;
@@ -76,7 +81,7 @@ static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uin
         const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
         smem = (size_t)planes * block.x * block.y * sizeof(uint32_t);
     }
-    auto kernel = k_sweep_stencil_cluster<DIM, PMJ, 6, ROUNDS, V, ACC>;
+    auto kernel = k_sweep_stencil_cluster<DIM, PMJ, 6, ROUNDS, V, ACC, PERBETA>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g, 1, 1);
     cfg.blockDim = block;
@@ -98,31 +103,35 @@ static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uin
     }
     const cudaError_t e = cudaLaunchKernelEx(
         &cfg, kernel, a.spins, a.jmask, L, a.sweep, nsweeps, philox_round_keys(a.key0, a.key1), a.gw0,
-        a.antiferro, th_dev, by_row, row_step, row_step % L.Ly, row_step / L.Ly, hist, cw);
+        a.antiferro, th_dev, by_row, row_step, row_step % L.Ly, row_step / L.Ly, hist, cw, a.tplane,
+        a.tlow);
     return e == cudaSuccess ? 1 : -1;
 }
 
-template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC>
+template <int DIM, bool PMJ, int ROUNDS, int V, bool ACC, bool PERBETA>
 static int cluster_launch(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
                           unsigned long long* hist, uint32_t cw, cudaStream_t st) {
     static const int max_cta = getenv("ISING_CLUSTER_MAX") ? atoi(getenv("ISING_CLUSTER_MAX")) : 16;  // A/B knob
     // more than one word per thread of a portable cluster: try the 16-CTA cluster first
     if ((uint64_t)a.lay.halfN * a.lay.W > 2048 && max_cta >= 16) {
-        const int rc = cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC>(a, th_dev, nsweeps, hist, cw, st, 16);
+        const int rc = cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC, PERBETA>(a, th_dev, nsweeps, hist, cw, st, 16);
         if (rc > 0) return rc;
         cudaGetLastError();
     }
-    return cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC>(a, th_dev, nsweeps, hist, cw, st, 8);
+    return cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC, PERBETA>(a, th_dev, nsweeps, hist, cw, st, 8);
 }
 
 template <int DIM, bool PMJ, int V>
 static int cluster_rounds(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
                           unsigned long long* hist, uint32_t cw, cudaStream_t st) {
+    if (a.tplane)
+        return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, false, true>(a, th_dev, nsweeps, nullptr, cw, st)
+                             : cluster_launch<DIM, PMJ, 10, V, false, true>(a, th_dev, nsweeps, nullptr, cw, st);
     if (hist)
-        return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, true>(a, th_dev, nsweeps, hist, cw, st)
-                             : cluster_launch<DIM, PMJ, 10, V, true>(a, th_dev, nsweeps, hist, cw, st);
-    return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, false>(a, th_dev, nsweeps, nullptr, cw, st)
-                         : cluster_launch<DIM, PMJ, 10, V, false>(a, th_dev, nsweeps, nullptr, cw, st);
+        return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, true, false>(a, th_dev, nsweeps, hist, cw, st)
+                             : cluster_launch<DIM, PMJ, 10, V, true, false>(a, th_dev, nsweeps, hist, cw, st);
+    return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, false, false>(a, th_dev, nsweeps, nullptr, cw, st)
+                         : cluster_launch<DIM, PMJ, 10, V, false, false>(a, th_dev, nsweeps, nullptr, cw, st);
 }
 
 // Largest lattice taken: 16384 site-words per colour (4 per thread of a 16-CTA cluster).
@@ -132,7 +141,7 @@ int launch_sweeps_stencil_cluster(const SweepArgs& a, const MscThresholds* th_de
     const Layout& L = a.lay;
     const bool d3 = L.kind == ISING_KIND_STENCIL3D;
     if (!d3 && L.kind != ISING_KIND_STENCIL2D) return 0;
-    if (a.planes != 6 || a.tplane || a.nsat_out) return 0;
+    if (a.planes != 6 || a.nsat_out || (a.tplane && hist)) return 0;
     const uint64_t words = (uint64_t)L.halfN * L.W;
     static const uint64_t max_words = getenv("ISING_CLUSTER_WORDS") ? strtoull(getenv("ISING_CLUSTER_WORDS"), nullptr, 10) : 16384;
     if (words > max_words) return 0;
