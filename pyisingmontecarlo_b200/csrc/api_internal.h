@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ising_b200.h"
@@ -93,6 +94,11 @@ struct ising_sim {
     uint32_t* d_slot = nullptr;
     uint32_t* d_tplane = nullptr;
     uint32_t* d_tlow = nullptr;
+    // host cache of the general-graph threshold rows T64[deg][cls] by beta (bit pattern): in
+    // parallel tempering the set of betas is fixed and only their assignment to replicas moves,
+    // so a swap step must not recompute thousands of exp()
+    std::unordered_map<uint64_t, std::vector<unsigned long long>> beta_rows;
+    int beta_rows_planes = 0;
 };
 
 int fail(ising_ctx* ctx, int code, const char* fmt, ...);

@@ -38,17 +38,28 @@ extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
     const size_t per = (size_t)(GEN_MAX_DEG + 1) * GEN_MAX_CLS;
     std::vector<unsigned long long> t64((size_t)E32 * per, 0ull);
     std::vector<uint32_t> slot(E32);
+    if (s->beta_rows_planes != s->planes || s->beta_rows.size() > 65536) {
+        s->beta_rows.clear();
+        s->beta_rows_planes = s->planes;
+    }
     for (uint32_t e = 0; e < E32; ++e) {
         slot[e] = e;
         const double beta = betas[e < s->E ? e : 0];  // padding bits: any valid beta
-        for (uint32_t deg = 1; deg <= (uint32_t)GEN_MAX_DEG; ++deg) {
-            const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
-            for (uint32_t j = 0; j < ncls; ++j) {
-                const int cls = 2 * (int)(cmin + j) - (int)deg;
-                t64[(size_t)e * per + (size_t)deg * GEN_MAX_CLS + j] =
-                    threshold64(beta, 2.0 * h.jabs * (double)cls, s->planes);
+        uint64_t key;
+        memcpy(&key, &beta, sizeof key);
+        auto it = s->beta_rows.find(key);
+        if (it == s->beta_rows.end()) {
+            std::vector<unsigned long long> row(per, 0ull);
+            for (uint32_t deg = 1; deg <= (uint32_t)GEN_MAX_DEG; ++deg) {
+                const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
+                for (uint32_t j = 0; j < ncls; ++j) {
+                    const int cls = 2 * (int)(cmin + j) - (int)deg;
+                    row[(size_t)deg * GEN_MAX_CLS + j] = threshold64(beta, 2.0 * h.jabs * (double)cls, s->planes);
+                }
             }
+            it = s->beta_rows.emplace(key, std::move(row)).first;
         }
+        memcpy(&t64[(size_t)e * per], it->second.data(), per * sizeof(unsigned long long));
     }
     if (!s->d_t64) {
         CUDA_TRY(ctx, dev_alloc(&s->d_t64, t64.size()));
