@@ -12,6 +12,14 @@ pub struct ising_ctx {
 pub struct ising_graph {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct ising_sim {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct ising_pt {
+    _p: [u8; 0],
+}
 
 pub const ISING_FLAG_PER_STEP_ENERGIES: u32 = 1 << 1;
 pub const ISING_FLAG_LINEAR_SCHEDULE: u32 = 1 << 2;
@@ -56,6 +64,46 @@ extern "C" {
         ctx: *mut ising_ctx, g: *const ising_graph, args: *const ising_run_args, energies: *mut f64,
         states: *mut u8,
     ) -> c_int;
+    // replay of a recorded (site, uniform) sequence: the bit-exact correctness mode
+    pub fn ising_replay(
+        ctx: *mut ising_ctx, g: *const ising_graph, beta: f64, num_experiments: u64, nattempts: u64,
+        sites: *const u32, u: *const f64, init: *const u8, energies: *mut f64, states: *mut u8,
+    ) -> c_int;
+
+    // src/classicising.rs: device-resident experiments behind ClassicIsing
+    pub fn ising_sim_create(
+        ctx: *mut ising_ctx, g: *const ising_graph, num_experiments: u64, seed: u64, replica_offset: u64,
+        out: *mut *mut ising_sim,
+    ) -> c_int;
+    pub fn ising_sim_destroy(sim: *mut ising_sim);
+    pub fn ising_sim_set_states(sim: *mut ising_sim, states: *const u8) -> c_int;
+    pub fn ising_sim_sweeps(
+        sim: *mut ising_sim, betas: *const f64, nsweeps: u64, energies_per_sweep: *mut f64,
+    ) -> c_int;
+    pub fn ising_sim_run_sampling(
+        sim: *mut ising_sim, beta: f64, thermalization: u64, sampling_freq: u64, n_samples: u64,
+        energies: *mut f64, states: *mut u8,
+    ) -> c_int;
+    pub fn ising_sim_run_observables(
+        sim: *mut ising_sim, beta: f64, thermalization: u64, sampling_freq: u64, n_samples: u64,
+        energies: *mut f64, mags: *mut f64, overlaps: *mut f64,
+    ) -> c_int;
+    pub fn ising_sim_get_energies(sim: *mut ising_sim, energies: *mut f64) -> c_int;
+    pub fn ising_sim_get_states(sim: *mut ising_sim, states: *mut u8) -> c_int;
+
+    // src/tempering.rs: the replica loop of LatticeTempering for classical replicas
+    pub fn ising_pt_create(
+        ctx: *mut ising_ctx, g: *const ising_graph, betas: *const f64, nbetas: u64, cfg_lo: u64, cfg_hi: u64,
+        seed: u64, out: *mut *mut ising_pt,
+    ) -> c_int;
+    pub fn ising_pt_destroy(pt: *mut ising_pt);
+    pub fn ising_pt_sweeps(pt: *mut ising_pt, t: u64, local_energies: *mut f64) -> c_int;
+    pub fn ising_pt_swap_step(pt: *mut ising_pt, all_energies: *const f64) -> c_int;
+    pub fn ising_pt_timesteps_sample(
+        pt: *mut ising_pt, timesteps: u64, replica_swap_freq: u64, sampling_freq: u64, states: *mut u8,
+        energies: *mut f64,
+    ) -> c_int;
+    pub fn ising_pt_total_swaps(pt: *const ising_pt, out: *mut u64) -> c_int;
 }
 
 /// Owns a context + compiled graph; one per `Lattice` (rebuilt when biases change).
