@@ -30,8 +30,8 @@ extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
             CUDA_TRY(ctx, dev_alloc(&s->d_tlow, (size_t)E32 * 3));
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(s->d_t64, t64.data(), t64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        // no host wait: cudaMemcpyAsync from pageable memory returns once the buffer is staged
         count_launch(s, launch_build_tables_stencil(s->d_t64, W, s->planes, s->d_tplane, s->d_tlow, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         s->perbeta = true;
         return ISING_OK;
     }
@@ -71,7 +71,7 @@ extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
     CUDA_TRY(ctx, cudaMemcpyAsync(s->d_slot, slot.data(), slot.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     count_launch(s, launch_build_tables(s->d_t64, s->d_slot, W, s->planes, s->d_tplane, s->d_tlow,
                                         ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // t64/slot are stack-lifetime host buffers
+    // no host wait: cudaMemcpyAsync from pageable memory returns once t64 / slot are staged
     s->perbeta = true;
     return ISING_OK;
 }
@@ -144,8 +144,11 @@ extern "C" int ising_pt_configure(ising_pt* pt, int planes, int rounds) {
 
 extern "C" int ising_pt_sweeps(ising_pt* pt, uint64_t t, double* local_energies) {
     if (!pt) return fail(nullptr, ISING_E_INVALID, "pt is NULL");
-    int rc = ising_sim_sweeps(pt->sim, nullptr, t, nullptr);
-    if (rc || !local_energies) return rc;
+    if (!local_energies) return ising_sim_sweeps(pt->sim, nullptr, t, nullptr);
+    // enqueue only: the energy read-back below is the one host wait of the swap cycle
+    CUDA_TRY(pt->ctx, cudaSetDevice(pt->ctx->device));
+    int rc = sim_enqueue_sweeps(pt->sim, nullptr, t);
+    if (rc) return rc;
     std::vector<double> en(pt->sim->E);
     rc = ising_sim_get_energies(pt->sim, en.data());
     if (rc) return rc;

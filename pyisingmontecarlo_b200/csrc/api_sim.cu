@@ -352,11 +352,14 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
         return 0;  // e.g. too many blocks to be co-resident: use the per-phase launches
     }
     if (rc == 0) return 0;
-    // the host table must outlive the copy
-    e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        *err = fail(ctx, ISING_E_CUDA, "cooperative sweep: %s", cudaGetErrorString(e));
-        return -1;
+    // (the pageable host table has been staged by the time cudaMemcpyAsync returned; per-replica
+    // betas upload nothing)  Launch errors of the chunk surface here when a table was used.
+    if (!th.empty()) {
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            *err = fail(ctx, ISING_E_CUDA, "multi-sweep launch: %s", cudaGetErrorString(e));
+            return -1;
+        }
     }
     count_launch(s, 1);
     s->stats.sweep_kernel_launches += 1;
@@ -387,6 +390,25 @@ int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
     return ISING_OK;
 }
 
+// nsweeps sweeps enqueued on the context's stream, no host wait and no timing (the tempering
+// loop synchronises once per swap step, when it reads the energies)
+int sim_enqueue_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps) {
+    uint64_t t = 0;
+    while (t < nsweeps) {
+        const uint64_t nt = std::min<uint64_t>(4096, nsweeps - t);
+        int err = ISING_OK;
+        const int done = (betas || s->perbeta) ? sim_sweeps_coop(s, betas ? betas + t : nullptr, nt, nullptr, &err) : 0;
+        if (done < 0) return err;
+        if (done) { t += nt; continue; }
+        for (uint64_t k = 0; k < nt; ++k) {
+            const int rc = sim_one_sweep(s, betas ? betas[t + k] : 0.0);
+            if (rc) return rc;
+        }
+        t += nt;
+    }
+    return ISING_OK;
+}
+
 extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps,
                                 double* energies_per_sweep) {
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
@@ -401,19 +423,8 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     const int mult = s->general ? 1 : 2;
     if (!energies_per_sweep) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        uint64_t t = 0;
-        while (t < nsweeps) {
-            const uint64_t nt = std::min<uint64_t>(4096, nsweeps - t);
-            int err = ISING_OK;
-            const int done = (betas || s->perbeta) ? sim_sweeps_coop(s, betas ? betas + t : nullptr, nt, nullptr, &err) : 0;
-            if (done < 0) return err;
-            if (done) { t += nt; continue; }
-            for (uint64_t k = 0; k < nt; ++k) {
-                const int rc = sim_one_sweep(s, betas ? betas[t + k] : 0.0);
-                if (rc) return rc;
-            }
-            t += nt;
-        }
+        const int rc0 = sim_enqueue_sweeps(s, betas, nsweeps);
+        if (rc0) return rc0;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
