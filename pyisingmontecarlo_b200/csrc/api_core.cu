@@ -59,6 +59,22 @@ cudaError_t ctx_scratch(ising_ctx* ctx, int slot, size_t bytes, void** out) {
     return cudaSuccess;
 }
 
+// rows of `width` bytes, device (pitch spitch) to host (pitch dpitch); the 2D copy engine path
+// is limited to pitches below 2^31, longer rows go one by one
+cudaError_t copy_rows_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                                 size_t height, cudaStream_t st) {
+    if (width == 0 || height == 0) return cudaSuccess;
+    if (dpitch < (1ull << 31) && spitch < (1ull << 31))
+        return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, st);
+    for (size_t r = 0; r < height; ++r) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst + r * dpitch, (const char*)src + r * spitch, width,
+                                        cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------

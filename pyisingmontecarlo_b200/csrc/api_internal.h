@@ -119,6 +119,9 @@ static inline cudaError_t dev_alloc(T** p, size_t count) {
 cudaError_t ctx_buf_get(ising_ctx* ctx, size_t bytes, void** out);
 void ctx_buf_put(ising_ctx* ctx, void* p, size_t bytes);
 cudaError_t ctx_scratch(ising_ctx* ctx, int slot, size_t bytes, void** out);
+// rows of `width` bytes from device (pitch spitch) to host (pitch dpitch), enqueued on st
+cudaError_t copy_rows_d2h(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                          size_t height, cudaStream_t st);
 // on-demand device copies of a graph (api_core.cu)
 int ensure_csr_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_csr32_on_device(ising_ctx* ctx, ising_graph* g);

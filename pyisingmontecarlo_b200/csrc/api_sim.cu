@@ -445,7 +445,6 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     CUDA_TRY(ctx, ctx_scratch(ctx, 2, (size_t)E * std::min(chunk_max, nsweeps) * sizeof(double), &sp));
     d_out = (double*)sp;
     cudaError_t e = cudaSuccess;
-    std::vector<double> host;
     int rc = ISING_OK;
     for (uint64_t t0 = 0; t0 < nsweeps && rc == ISING_OK; t0 += chunk_max) {
         const uint64_t nt = std::min(chunk_max, nsweeps - t0);
@@ -476,16 +475,14 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
                                                     d_out, ctx->stream));
         cudaEventRecord(ctx->ev1, ctx->stream);
         if (rc != ISING_OK) break;
-        host.resize((size_t)E * nt);
-        e = cudaMemcpyAsync(host.data(), d_out, host.size() * sizeof(double),
-                            cudaMemcpyDeviceToHost, ctx->stream);
+        // rows [e][t0 .. t0 + nt) straight into the caller's double[E, nsweeps] (strided copy)
+        e = copy_rows_d2h(energies_per_sweep + t0, (size_t)nsweeps * sizeof(double), d_out,
+                          (size_t)nt * sizeof(double), (size_t)nt * sizeof(double), E, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rc = fail(ctx, ISING_E_CUDA, "energy read-back: %s", cudaGetErrorString(e)); break; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         s->stats.sweep_device_ms += ms;
-        for (uint64_t ex = 0; ex < E; ++ex)
-            memcpy(energies_per_sweep + ex * nsweeps + t0, host.data() + ex * nt, nt * sizeof(double));
     }
     return rc;
 }
