@@ -98,6 +98,21 @@ def exchange_deep(strip, depth, rank, world, dist=None, group=None, device=None,
         strip.halo_deep(1, depth, np.ascontiguousarray(recv.numpy()).view(np.uint32))
 
 
+def sweep_batches(strip, betas, k, rank, world, dist=None, group=None, device=None, bufs=None, sync=True):
+    """One checkerboard sweep per beta in batches of at most k sweeps: one deep exchange of 2 nb
+    rows, then 2 nb colour phases that update 2 nb - 1 - q ghost rows next to the local ones
+    (phase q), so that the valid ghost region shrinks by one row per phase and is used up
+    exactly when the batch ends.  strip needs .phase_ext and the interface of exchange_deep."""
+    betas = np.atleast_1d(np.asarray(betas, dtype=np.float64))
+    i = 0
+    while i < len(betas):
+        nb = min(int(k), len(betas) - i)          # sweeps in this batch
+        exchange_deep(strip, 2 * nb, rank, world, dist, group, device, bufs)
+        for q in range(2 * nb):
+            strip.phase_ext(q & 1, betas[i + q // 2], 2 * nb - 1 - q, advance=bool(q & 1), sync=sync)
+        i += nb
+
+
 class SingleLattice2D:
     """Periodic Lx x Ly lattice with uniform coupling j (j < 0 ferromagnetic, README.md:45-46)."""
 
@@ -198,15 +213,8 @@ class SingleLattice2D:
                         self._exchange(1 - colour)
                         self.strip.phase(colour, beta)
             return
-        i = 0
-        while i < len(betas):
-            nb = min(self._k, len(betas) - i)          # sweeps in this batch
-            exchange_deep(self.strip, 2 * nb, self.rank, self.world, self._dist, self._group,
-                          self._torch_device, self._bufs)
-            for q in range(2 * nb):
-                self.strip.phase_ext(q & 1, betas[i + q // 2], 2 * nb - 1 - q, advance=bool(q & 1),
-                                     sync=not self._async)
-            i += nb
+        sweep_batches(self.strip, betas, self._k, self.rank, self.world, self._dist, self._group,
+                      self._torch_device, self._bufs, sync=not self._async)
 
     def _global_sums(self):
         if self._async:

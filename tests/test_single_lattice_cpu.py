@@ -91,16 +91,11 @@ class DeepFakeStrip:
 
 
 def _run_deep(strip, rank, world, k, dist=None):
-    from pyisingmontecarlo_b200.single_lattice import exchange_deep
+    from pyisingmontecarlo_b200.single_lattice import sweep_batches
     import torch
 
-    done = 0
-    while done < 5:                       # 5 sweeps in batches of k (the last one shorter)
-        nb = min(k, 5 - done)
-        exchange_deep(strip, 2 * nb, rank, world, dist, None, torch.device("cpu"))
-        for q in range(2 * nb):
-            strip.phase_ext(q & 1, 0.4, 2 * nb - 1 - q, advance=bool(q & 1))
-        done += nb
+    # 5 sweeps in batches of k (the last one shorter): the loop SingleLattice2D.sweeps runs
+    sweep_batches(strip, [0.4] * 5, k, rank, world, dist, None, torch.device("cpu"))
     return strip.interior()
 
 
