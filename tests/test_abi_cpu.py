@@ -30,6 +30,46 @@ def test_library_exports_every_declared_symbol(native):
     assert native.lib().ising_abi_version() == 1
 
 
+def test_header_is_plain_c_and_links_from_c(native, tmp_path):
+    """The boundary is a C ABI: include/ising_b200.h must compile as C99 (-pedantic, no C++ or
+    torch types) and a C program must link against the library and get the documented error
+    codes from the host-only entry points."""
+    import shutil
+    import subprocess
+
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "consumer.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "ising_b200.h"
+int main(void) {
+    uint64_t seeds[2] = {0, 0};
+    uint64_t st[2] = {0, 10};
+    double sb[2] = {0.1, 1.2}, betas[10];
+    ising_run_args args;
+    if (ising_abi_version() != ISING_ABI_VERSION) return 1;
+    if (ising_make_seeds(0, 2, seeds) != ISING_OK) return 2;
+    if (seeds[0] != 5987356902031041503ull) return 3;
+    if (ising_schedule_betas(st, sb, 2, 10, 0, betas) != ISING_OK) return 4;
+    if (ising_graph_from_edges(NULL, 0, 0, NULL, NULL, NULL, NULL, NULL) != ISING_E_INVALID) return 5;
+    if (sizeof args.struct_size != 4) return 6;
+    printf("%s\n", ising_last_error(NULL) ? "ok" : "no message");
+    return 0;
+}
+""")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(native.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(native.LIB_PATH),
+           "-Wl,-rpath," + libdir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.strip() == "ok", (run.returncode, run.stdout, run.stderr)
+
+
 def test_library_is_sm100a_cuda(native):
     """The product is CUDA for sm_100a: the .so must embed an sm_100a cubin with our kernels."""
     import shutil
