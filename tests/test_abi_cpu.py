@@ -82,6 +82,42 @@ def test_library_is_sm100a_cuda(native):
     assert "sm_100a" in out
 
 
+def test_hot_kernels_keep_their_register_budget(native):
+    """Build-time guard of the launch configuration the measurements rest on: the config 3
+    sweep kernel must fit 3 blocks of 256 threads per SM (<= 85 registers), its accumulating
+    variant 2 blocks (<= 128), the strip kernel 3 blocks, and none of them may spill."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-res-usage", native.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    lines = out.splitlines()
+    for i, line in enumerate(lines):
+        m = re.match(r"\s*Function (\S+):", line)
+        if m and i + 1 < len(lines):
+            r = re.search(r"REG:(\d+) STACK:(\d+)", lines[i + 1])
+            if r:
+                usage[m.group(1)] = (int(r.group(1)), int(r.group(2)))
+
+    def find(fragment):
+        hits = [v for k, v in usage.items() if fragment in k]
+        assert hits, fragment
+        return hits
+
+    # k_sweep_stencil<DIM=3, PMJ, K=6, ROUNDS=10, V=4, ACC>
+    for reg, stack in find("k_sweep_stencilILi3ELb1ELi6ELi10ELi4ELb0"):
+        assert reg <= 85 and stack == 0, (reg, stack)
+    for reg, stack in find("k_sweep_stencilILi3ELb1ELi6ELi10ELi4ELb1"):
+        assert reg <= 128 and stack == 0, (reg, stack)
+    for reg, stack in find("k_strip_phaseILi6ELi10ELi4"):
+        assert reg <= 85 and stack == 0, (reg, stack)
+    for reg, stack in find("k_sweep_generalILi6ELi10ELb1ELi3ELi2"):
+        assert reg <= 64 and stack == 0, (reg, stack)
+
+
 def test_no_cpu_fallback_without_device(native):
     import torch
 
