@@ -187,7 +187,7 @@ def oracle_sample(w, steps, warmup, sample_sweeps=None):
 def run_reference(args, w, world, rank):
     if rank != 0:
         return
-    r = oracle_sample(w, args.steps, args.warmup)
+    r = oracle_sample(w, args.steps, args.warmup, args.ref_sample_sweeps or None)
     line = {
         "impl": "reference", "metric": "spin_flip_attempts_per_sec", "value": r["value"],
         "unit": "flips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -512,6 +512,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=0)
     ap.add_argument("--sweeps", type=int, default=0, help="override sweeps per step (profiling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-sweeps", type=int, default=0,
+                    help="reference arm: timesteps per step of the bounded CPU sample (0 = sized to ~10 s)")
     ap.add_argument("--e2e-full", action="store_true")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
