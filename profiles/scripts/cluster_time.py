@@ -1,5 +1,5 @@
 import sys, os, time
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+sys.path.insert(0, os.getcwd())
 import numpy as np
 from pyisingmontecarlo_b200 import _native as nat
 ctx = nat.Context.get(0)
