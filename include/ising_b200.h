@@ -130,6 +130,13 @@ ISING_API int ising_sim_sweeps(ising_sim *sim, const double *betas, uint64_t nsw
 ISING_API int ising_sim_run_sampling(ising_sim *sim, double beta, uint64_t thermalization,
                            uint64_t sampling_freq, uint64_t n_samples, double *energies,
                            uint8_t *states);
+/* Opt-in packed form of the same loop (additive): samples as
+ * uint32[n_samples, nvars, ceil(E/32)] in natural site order (bit e%32 of word e/32 is
+ * experiment e, as ising_sim_get_packed) -- 8x less D2H than bool[E, n_samples, nvars], the only
+ * practical form at config 2 size (2 GiB instead of 17 GB per sample). */
+ISING_API int ising_sim_run_sampling_packed(ising_sim *sim, double beta, uint64_t thermalization,
+                                  uint64_t sampling_freq, uint64_t n_samples, double *energies,
+                                  uint32_t *words);
 /* The same loop without the state read-back (additive; feeds SURVEY 8(f)2): per sample the
  * energy, the magnetisation M = sum_i s_i and the overlap Q = sum_i s_i^(2p) s_i^(2p+1) of the
  * experiment pairs (2p, 2p+1), all reduced on the device.  energies / mags double[E, n_samples],

@@ -101,6 +101,7 @@ _SIGNATURES = {
     "ising_sim_set_states": (C.c_int, [_P, _P]),
     "ising_sim_sweeps": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "ising_sim_run_sampling": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
+    "ising_sim_run_sampling_packed": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "ising_sim_run_observables": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "ising_sim_get_energies": (C.c_int, [_P, _P]),
     "ising_sim_get_states": (C.c_int, [_P, _P]),
@@ -389,8 +390,16 @@ class Sim:
             raise ValueError("betas must have one entry per experiment")
         check(lib().ising_sim_set_betas(self.handle, ptr(b)), self.ctx.handle)
 
-    def run_sampling(self, beta, thermalization, sampling_freq, n_samples):
+    def run_sampling(self, beta, thermalization, sampling_freq, n_samples, packed=False):
+        """(energies[E, n_s], states bool[E, n_s, nvars]); packed=True returns the samples as
+        uint32[n_s, nvars, ceil(E/32)] instead (bit e%32 of word e/32 = experiment e)."""
         energies = np.empty((self.E, n_samples), dtype=np.float64)
+        if packed:
+            words = PinnedPool.empty((n_samples, self.graph.nvars, (self.E + 31) // 32), np.uint32)
+            check(lib().ising_sim_run_sampling_packed(self.handle, float(beta), int(thermalization),
+                                                      int(sampling_freq), int(n_samples), ptr(energies),
+                                                      ptr(words)), self.ctx.handle)
+            return energies, words
         states = PinnedPool.empty((self.E, n_samples, self.graph.nvars), np.bool_)
         check(lib().ising_sim_run_sampling(self.handle, float(beta), int(thermalization),
                                            int(sampling_freq), int(n_samples), ptr(energies),

@@ -68,15 +68,16 @@ class ClassicIsing:
 
     def run_monte_carlo_sampling(self, beta, timesteps, nspinupdates=None, nedgeupdates=None,
                                  nwormupdates=None, only_basic_moves=None, thermalization_time=None,
-                                 sampling_freq=None):
-        """classicising.rs:119-179 -> (energies float64[E, n_s], states bool[E, n_s, nvars])"""
+                                 sampling_freq=None, *, packed=False):
+        """classicising.rs:119-179 -> (energies float64[E, n_s], states bool[E, n_s, nvars]);
+        packed=True (additive) returns uint32[n_s, nvars, ceil(E/32)] bit-packed samples instead."""
         self._check_moves(nspinupdates, nedgeupdates, nwormupdates)
         thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
         sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
         if sampling_freq == 0:
             raise ZeroDivisionError("sampling_freq must be non-zero (the reference panics)")
         return self._sim.run_sampling(beta, thermalization_time, sampling_freq,
-                                      int(timesteps) // sampling_freq)
+                                      int(timesteps) // sampling_freq, packed=packed)
 
     def run_monte_carlo_observables(self, beta, timesteps, thermalization_time=None, sampling_freq=None,
                                     overlaps=True):

@@ -59,28 +59,29 @@ static cudaError_t ctx_copy_stream(ising_ctx* ctx) {
 // At scale: samples are unpacked into one of two device slabs laid out
 // [E, nk, N]; while the sweeps of the next slab run, the copy stream drains the previous one
 // straight into the caller's [E, ns, N] array with a strided (2D) copy -- no host staging.
-extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t thermalization,
-                                      uint64_t sampling_freq, uint64_t ns, double* energies,
-                                      uint8_t* states) {
-    if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+// packed != nullptr: samples are returned as uint32[ns, nvars, W] (natural site order, bit e%32 of
+// word e/32 = experiment e; 8x less device-to-host traffic) instead of bool[E, ns, nvars].
+static int sim_run_sampling_impl(ising_sim* sim, double beta, uint64_t thermalization, uint64_t sampling_freq,
+                                 uint64_t ns, double* energies, uint8_t* states, uint32_t* packed) {
     ising_ctx* ctx = sim->ctx;
-    if (ns && (!energies || !states)) return fail(ctx, ISING_E_INVALID, "output buffers are NULL");
+    if (ns && (!energies || (!states && !packed))) return fail(ctx, ISING_E_INVALID, "output buffers are NULL");
     if (sim->perbeta) return fail(ctx, ISING_E_INVALID, "sampling runs at one beta");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const uint64_t E = sim->E, N = sim->lay.nvars;
+    const uint64_t E = sim->E, N = sim->lay.nvars, W = sim->lay.W;
     std::vector<double> betas(std::max<uint64_t>(thermalization, sampling_freq), beta);
     int rc = ising_sim_sweeps(sim, betas.data(), thermalization, nullptr);
     if (rc || ns == 0) return rc;
     CUDA_TRY(ctx, ctx_copy_stream(ctx));
     uint64_t slab_bytes = 1ull << 29;
     if (const char* env = getenv("ISING_SAMPLING_SLAB_BYTES")) slab_bytes = strtoull(env, nullptr, 10);  // test knob
-    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, slab_bytes / std::max<uint64_t>(1, E * N)));
+    const uint64_t sample_bytes = packed ? N * W * 4 : E * N;   // one sample on the device
+    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(ns, slab_bytes / std::max<uint64_t>(1, sample_bytes)));
     const int nbuf = slab < ns ? 2 : 1;
     uint8_t* d_st[2] = {nullptr, nullptr};
     double* d_en[2] = {nullptr, nullptr};
     for (int b = 0; b < nbuf; ++b) {
         void* dv = nullptr;
-        CUDA_TRY(ctx, ctx_scratch(ctx, b ? 4 : 0, (size_t)E * slab * N, &dv));
+        CUDA_TRY(ctx, ctx_scratch(ctx, b ? 4 : 0, (size_t)sample_bytes * slab, &dv));
         d_st[b] = (uint8_t*)dv;
         CUDA_TRY(ctx, ctx_scratch(ctx, b ? 5 : 2, (size_t)E * slab * sizeof(double), &dv));
         d_en[b] = (double*)dv;
@@ -93,15 +94,24 @@ extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t ther
         for (uint64_t k = 0; k < nk; ++k) {
             rc = ising_sim_sweeps(sim, betas.data(), sampling_freq, nullptr);
             if (rc) return rc;
-            count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d_st[b] + k * N, E, nk * N,
-                                                   ctx->stream));
+            if (packed)   // device slab [nk][N][W]
+                count_launch(sim, launch_export_natural(sim->d_spins, sim->lay,
+                                                        reinterpret_cast<uint32_t*>(d_st[b]) + k * N * W,
+                                                        ctx->stream));
+            else          // device slab [E][nk][N]
+                count_launch(sim, launch_unpack_states(sim->d_spins, sim->lay, d_st[b] + k * N, E, nk * N,
+                                                       ctx->stream));
             rc = sim_energies_to_device(sim, d_en[b], nk, k);
             if (rc) return rc;
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_filled[b], ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_filled[b], 0));
-        CUDA_TRY(ctx, copy_rows_d2h(states + k0 * N, (size_t)ns * N, d_st[b], (size_t)nk * N,
-                                    (size_t)nk * N, E, ctx->copy_stream));
+        if (packed)
+            CUDA_TRY(ctx, cudaMemcpyAsync(packed + k0 * N * W, d_st[b], (size_t)nk * sample_bytes,
+                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
+        else
+            CUDA_TRY(ctx, copy_rows_d2h(states + k0 * N, (size_t)ns * N, d_st[b], (size_t)nk * N,
+                                        (size_t)nk * N, E, ctx->copy_stream));
         CUDA_TRY(ctx, copy_rows_d2h(energies + k0, (size_t)ns * 8, d_en[b], (size_t)nk * 8,
                                     (size_t)nk * 8, E, ctx->copy_stream));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_drained[b], ctx->copy_stream));
@@ -109,6 +119,22 @@ extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t ther
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ISING_OK;
+}
+
+extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t thermalization,
+                                      uint64_t sampling_freq, uint64_t ns, double* energies,
+                                      uint8_t* states) {
+    if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    if (ns && !states) return fail(sim->ctx, ISING_E_INVALID, "output buffers are NULL");
+    return sim_run_sampling_impl(sim, beta, thermalization, sampling_freq, ns, energies, states, nullptr);
+}
+
+extern "C" int ising_sim_run_sampling_packed(ising_sim* sim, double beta, uint64_t thermalization,
+                                             uint64_t sampling_freq, uint64_t ns, double* energies,
+                                             uint32_t* words) {
+    if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    if (ns && !words) return fail(sim->ctx, ISING_E_INVALID, "output buffers are NULL");
+    return sim_run_sampling_impl(sim, beta, thermalization, sampling_freq, ns, energies, nullptr, words);
 }
 
 // The sampling loop without the state read-back (a sample of config 2 is 17 GB of bools):

@@ -294,6 +294,24 @@ def test_sampling_double_buffered_slabs(pkg, oracle, monkeypatch):
     assert (en1 == en2).all() and (st1 == st2).all()
 
 
+def test_packed_sampling_equals_bool_sampling(native, pkg, monkeypatch):
+    """Opt-in packed samples uint32[n_s, nvars, ceil(E/32)] hold the same bits as bool[E, n_s, nvars]
+    (one slab and two-samples-per-slab double buffering)."""
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (6, 8), j0=-1.0)
+    for slab in (None, str(48 * 3 * 4 * 2)):
+        if slab:
+            monkeypatch.setenv("ISING_SAMPLING_SLAB_BYTES", slab)
+        a, b = native.Sim(g, 70, 5), native.Sim(g, 70, 5)
+        en_b, st = a.run_sampling(0.4, 2, 3, 5)
+        en_p, words = b.run_sampling(0.4, 2, 3, 5, packed=True)
+        assert words.shape == (5, 48, 3) and words.dtype == np.uint32
+        bits = ((words[:, :, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+        bits = bits.reshape(5, 48, 96)[:, :, :70]          # [n_s, nvars, E]
+        assert (bits.transpose(2, 0, 1) == st).all() and (en_p == en_b).all()
+        assert (b.packed() == words[-1]).all()
+
+
 @pytest.mark.parametrize("kind", ["2d", "3d_pmj", "general"])
 def test_device_observables_match_sampled_states(pkg, oracle, kind):
     """run_monte_carlo_observables follows the same trajectories as run_monte_carlo_sampling;
