@@ -536,9 +536,15 @@ class Tempering:
         sim = C.c_void_p()
         check(lib().ising_pt_get_sim(self.handle, C.byref(sim)), self.ctx.handle)
         words = np.ascontiguousarray(ck["packed"], dtype=np.uint32)
+        slots = np.ascontiguousarray(ck["slots"], dtype=np.uint32)
+        E = min(((self.hi + 31) // 32 - self.lo // 32) * 32, self.R - (self.lo // 32) * 32)
+        if words.shape != (self.graph.nvars, (E + 31) // 32):
+            raise ValueError(f"checkpoint holds packed spins of shape {words.shape}, this ladder needs "
+                             f"{(self.graph.nvars, (E + 31) // 32)}")
+        if slots.shape != (self.R,):
+            raise ValueError(f"checkpoint holds {slots.size} slots, this ladder has {self.R}")
         check(lib().ising_sim_set_packed(sim, ptr(words)), self.ctx.handle)
         check(lib().ising_sim_set_counter(sim, int(ck["sweeps"])), self.ctx.handle)
-        slots = np.ascontiguousarray(ck["slots"], dtype=np.uint32)
         check(lib().ising_pt_restore(self.handle, ptr(slots), int(ck["swap_step"]), int(ck["total_swaps"])),
               self.ctx.handle)
 

@@ -27,10 +27,11 @@ class ClassicIsing:
         ctx = nat.Context.get(device)
         bias = None if self._longitudinal == 0.0 else np.full(self.nvars, self._longitudinal)
         self._graph = nat.Graph.from_edges(ctx, self.nvars, self._a, self._b, self._j, bias)
-        self._sim = None
-        self._n = 0
-        for _ in range(1 if num_experiments is None else int(num_experiments)):
-            self.add_graph(None, None)
+        # all initial experiments at once: random starts are a pure function of (seed, site,
+        # replica), so this equals num_experiments calls of add_graph() without their
+        # O(E^2 nvars) state copies (classicising.rs:45-58 builds them in one loop as well)
+        self._n = 1 if num_experiments is None else int(num_experiments)
+        self._sim = nat.Sim(self._graph, self._n, self._seed) if self._n > 0 else None
 
     def add_graph(self, initial_state=None, edge_move_importance_sampling=None):
         """classicising.rs:62-79: one more experiment, random start or the given state."""
@@ -40,6 +41,10 @@ class ClassicIsing:
         old = None if self._sim is None else self._sim.states()
         self._n += 1
         sim = nat.Sim(self._graph, self._n, self._seed)      # experiment e always owns stream e
+        if self._sim is not None:
+            # the random streams are keyed by (site, replica, sweep): keep the sweep counter running
+            # so that the old experiments do not replay the draws of sweeps 0..T-1
+            sim.counter = self._sim.counter
         if old is not None or initial_state is not None:
             st = sim.states()                                   # random start of the new experiment
             if old is not None:

@@ -198,6 +198,16 @@ static int upload_stencil_masks(ising_ctx* ctx, ising_graph* g) {
     CUDA_TRY(ctx, dev_alloc(&g->d_jmask, m.size()));
     CUDA_TRY(ctx, cudaMemcpy(g->d_jmask, m.data(), m.size() * sizeof(uint32_t),
                              cudaMemcpyHostToDevice));
+    // the same masks site-major, [colour][halfN][8] (k = 0..2*dim-1, rest 0): two 128-bit loads
+    // per site in the row-walk kernel instead of 2*dim scalar ones
+    std::vector<uint32_t> m8((size_t)2 * halfN * 8, 0u);
+    for (uint32_t c = 0; c < 2; ++c)
+        for (uint64_t i = 0; i < halfN; ++i)
+            for (int k = 0; k < 2 * dim; ++k)
+                m8[((size_t)c * halfN + i) * 8 + k] = m[(size_t)c * 2 * dim * halfN + (size_t)k * halfN + i];
+    CUDA_TRY(ctx, dev_alloc(&g->d_jmask8, m8.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_jmask8, m8.data(), m8.size() * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice));
     return ISING_OK;
 }
 
@@ -328,6 +338,7 @@ int ensure_general_on_device(ising_ctx* ctx, ising_graph* g) {
 extern "C" int ising_graph_from_edges(ising_ctx* ctx, uint64_t nvars, uint64_t nedges,
                                       const uint64_t* a, const uint64_t* b, const double* j,
                                       const double* biases, ising_graph** out) {
+    CtxLock _lk(ctx);
     if (!ctx || !out) return fail(ctx, ISING_E_INVALID, "ctx/out is NULL");
     *out = nullptr;
     if (nedges && (!a || !b || !j)) return fail(ctx, ISING_E_INVALID, "edge arrays are NULL");
@@ -344,6 +355,7 @@ extern "C" int ising_graph_from_edges(ising_ctx* ctx, uint64_t nvars, uint64_t n
 
 extern "C" int ising_graph_torus(ising_ctx* ctx, int dim, const uint64_t* L, double j0, int pmj,
                                  uint64_t j_seed, ising_graph** out) {
+    CtxLock _lk(ctx);
     if (!ctx || !out || !L) return fail(ctx, ISING_E_INVALID, "ctx/out/L is NULL");
     *out = nullptr;
     std::unique_ptr<ising_graph> g(new ising_graph);
@@ -358,9 +370,11 @@ extern "C" int ising_graph_torus(ising_ctx* ctx, int dim, const uint64_t* L, dou
 }
 
 extern "C" void ising_graph_destroy(ising_graph* g) {
+    CtxLock _lk(g ? g->ctx : nullptr);
     if (!g) return;
     if (g->ctx) cudaSetDevice(g->ctx->device);
     cudaFree(g->d_jmask);
+    cudaFree(g->d_jmask8);
     cudaFree(g->d_row);
     cudaFree(g->d_nbr);
     cudaFree(g->d_jv);
@@ -378,6 +392,7 @@ extern "C" void ising_graph_destroy(ising_graph* g) {
 }
 
 extern "C" int ising_graph_get_info(const ising_graph* g, ising_graph_info* out) {
+    CtxLock _lk(g ? g->ctx : nullptr);
     if (!g || !out) return fail(nullptr, ISING_E_INVALID, "graph/out is NULL");
     const HostGraph& h = g->h;
     out->nvars = h.nvars;
@@ -394,12 +409,14 @@ extern "C" int ising_graph_get_info(const ising_graph* g, ising_graph_info* out)
 }
 
 extern "C" int ising_graph_get_colors(const ising_graph* g, uint32_t* colors) {
+    CtxLock _lk(g ? g->ctx : nullptr);
     if (!g || !colors) return fail(nullptr, ISING_E_INVALID, "graph/colors is NULL");
     for (uint64_t n = 0; n < g->h.nvars; ++n) colors[n] = g->h.color_of(n);
     return ISING_OK;
 }
 
 extern "C" int ising_graph_get_edges(const ising_graph* g, uint64_t* a, uint64_t* b, double* j) {
+    CtxLock _lk(g ? g->ctx : nullptr);
     if (!g || !a || !b || !j) return fail(nullptr, ISING_E_INVALID, "graph/arrays NULL");
     for (uint64_t e = 0; e < g->h.nedges; ++e) g->h.edge_at(e, a + e, b + e, j + e);
     return ISING_OK;

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -25,6 +26,11 @@ using namespace ising;
 // objects
 // ------------------------------------------------------------------------------------------
 struct ising_ctx {
+    // Every extern "C" entry point that touches a context holds this for the call: the scratch
+    // buffers, the free list, the timing events and the copy stream are per-context state, and
+    // ctypes releases the GIL (the pyo3 reference holds it, so its calls were serialised too).
+    // Recursive because entry points are built from each other (create -> randomize, ...).
+    std::recursive_mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
@@ -50,6 +56,7 @@ struct ising_graph {
     HostGraph h;
     // device copies
     uint32_t* d_jmask = nullptr;   // stencil +-J bond masks [2][2*dim][halfN]
+    uint32_t* d_jmask8 = nullptr;  // the same, site-major [2][halfN][8]
     uint64_t* d_row = nullptr;     // CSR for replay / general kernels (uploaded on demand)
     uint32_t* d_nbr = nullptr;
     double* d_jv = nullptr;
@@ -102,6 +109,14 @@ struct ising_sim {
 };
 
 int fail(ising_ctx* ctx, int code, const char* fmt, ...);
+
+struct CtxLock {
+    ising_ctx* c;
+    explicit CtxLock(const ising_ctx* ctx) : c(const_cast<ising_ctx*>(ctx)) { if (c) c->mu.lock(); }
+    ~CtxLock() { if (c) c->mu.unlock(); }
+    CtxLock(const CtxLock&) = delete;
+    CtxLock& operator=(const CtxLock&) = delete;
+};
 
 #define CUDA_TRY(ctx, call)                                                          \
     do {                                                                             \

@@ -5,6 +5,7 @@
 // per-experiment inverse temperatures and classical parallel tempering
 // ------------------------------------------------------------------------------------------
 extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !betas) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
     ising_ctx* ctx = s->ctx;
     if (s->real)
@@ -101,6 +102,7 @@ static int pt_push_betas(ising_pt* pt) {
 extern "C" int ising_pt_create(ising_ctx* ctx, const ising_graph* g, const double* betas,
                                uint64_t nbetas, uint64_t cfg_lo, uint64_t cfg_hi, uint64_t seed,
                                ising_pt** out) {
+    CtxLock _lk(ctx);
     if (!ctx || !g || !betas || !out) return fail(ctx, ISING_E_INVALID, "ctx/graph/betas/out is NULL");
     *out = nullptr;
     if (nbetas == 0 || cfg_lo >= cfg_hi || cfg_hi > nbetas)
@@ -131,18 +133,21 @@ extern "C" int ising_pt_create(ising_ctx* ctx, const ising_graph* g, const doubl
 }
 
 extern "C" void ising_pt_destroy(ising_pt* pt) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt) return;
     ising_sim_destroy(pt->sim);
     delete pt;
 }
 
 extern "C" int ising_pt_configure(ising_pt* pt, int planes, int rounds) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt) return fail(nullptr, ISING_E_INVALID, "pt is NULL");
     const int rc = ising_sim_configure(pt->sim, planes, rounds);
     return rc ? rc : pt_push_betas(pt);
 }
 
 extern "C" int ising_pt_sweeps(ising_pt* pt, uint64_t t, double* local_energies) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt) return fail(nullptr, ISING_E_INVALID, "pt is NULL");
     if (!local_energies) return ising_sim_sweeps(pt->sim, nullptr, t, nullptr);
     // enqueue only: the energy read-back below is the one host wait of the swap cycle
@@ -191,6 +196,7 @@ extern "C" int ising_pt_decide_swaps(const double* betas, uint64_t R, const doub
 }
 
 extern "C" int ising_pt_swap_step(ising_pt* pt, const double* all_energies) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !all_energies) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/energies is NULL");
     uint64_t swaps = 0;
     const int rc = ising_pt_decide_swaps(pt->betas.data(), pt->R, all_energies, pt->seed, pt->swap_step,
@@ -202,12 +208,14 @@ extern "C" int ising_pt_swap_step(ising_pt* pt, const double* all_energies) {
 }
 
 extern "C" int ising_pt_get_slots(const ising_pt* pt, uint32_t* slot_of_config) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !slot_of_config) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
     for (uint64_t c = 0; c < pt->R; ++c) slot_of_config[c] = pt->slot_of_cfg[c];
     return ISING_OK;
 }
 
 extern "C" int ising_pt_get_local_states(ising_pt* pt, uint8_t* states) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !states) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/states is NULL");
     const uint64_t N = pt->g->h.nvars;
     std::vector<uint8_t> all((size_t)pt->sim->E * N);
@@ -220,12 +228,14 @@ extern "C" int ising_pt_get_local_states(ising_pt* pt, uint8_t* states) {
 
 // checkpoint support: the sim behind the ladder, and the permutation / counters
 extern "C" int ising_pt_get_sim(ising_pt* pt, ising_sim** out) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !out) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
     *out = pt->sim;
     return ISING_OK;
 }
 
 extern "C" int ising_pt_get_counters(const ising_pt* pt, uint64_t* swap_step, uint64_t* total_swaps) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !swap_step || !total_swaps) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
     *swap_step = pt->swap_step;
     *total_swaps = pt->total_swaps;
@@ -234,6 +244,7 @@ extern "C" int ising_pt_get_counters(const ising_pt* pt, uint64_t* swap_step, ui
 
 extern "C" int ising_pt_restore(ising_pt* pt, const uint32_t* slot_of_config, uint64_t swap_step,
                                 uint64_t total_swaps) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !slot_of_config) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/slots is NULL");
     std::vector<uint8_t> seen(pt->R, 0);
     for (uint64_t c = 0; c < pt->R; ++c) {
@@ -251,6 +262,7 @@ extern "C" int ising_pt_restore(ising_pt* pt, const uint32_t* slot_of_config, ui
 }
 
 extern "C" int ising_pt_total_swaps(const ising_pt* pt, uint64_t* out) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !out) return fail(nullptr, ISING_E_INVALID, "pt/out is NULL");
     *out = pt->total_swaps;
     return ISING_OK;
@@ -261,6 +273,7 @@ extern "C" int ising_pt_total_swaps(const ising_pt* pt, uint64_t* out) {
 // "the configuration currently at beta_r", energies[R] = sum(E_r after chunk * chunk) / timesteps.
 extern "C" int ising_pt_timesteps_sample(ising_pt* pt, uint64_t timesteps, uint64_t replica_swap_freq,
                                          uint64_t sampling_freq, uint8_t* states, double* energies) {
+    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt || !energies) return fail(pt ? pt->ctx : nullptr, ISING_E_INVALID, "pt/energies is NULL");
     if (pt->lo != 0 || pt->hi != pt->R)
         return fail(pt->ctx, ISING_E_INVALID, "ising_pt_timesteps_sample needs all configurations on this rank");

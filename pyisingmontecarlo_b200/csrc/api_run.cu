@@ -30,6 +30,7 @@ static int make_sim_for_run(ising_ctx* ctx, const ising_graph* g, const ising_ru
 
 extern "C" int ising_run_monte_carlo(ising_ctx* ctx, const ising_graph* g,
                                      const ising_run_args* a, double* energies, uint8_t* states) {
+    CtxLock _lk(ctx);
     int rc = check_run_args(ctx, g, a, energies, states);
     if (rc) return rc;
     if (a->num_experiments == 0) return ISING_OK;
@@ -72,6 +73,15 @@ static int sim_run_sampling_impl(ising_sim* sim, double beta, uint64_t thermaliz
     int rc = ising_sim_sweeps(sim, betas.data(), thermalization, nullptr);
     if (rc || ns == 0) return rc;
     CUDA_TRY(ctx, ctx_copy_stream(ctx));
+    // Every exit below - also the error returns inside the slab loop - first drains both streams:
+    // copies into the caller's arrays and reads of the scratch slabs must not outlive the call.
+    struct Drain {
+        ising_ctx* c;
+        ~Drain() {
+            cudaStreamSynchronize(c->copy_stream);
+            cudaStreamSynchronize(c->stream);
+        }
+    } drain{ctx};
     uint64_t slab_bytes = 1ull << 29;
     if (const char* env = getenv("ISING_SAMPLING_SLAB_BYTES")) slab_bytes = strtoull(env, nullptr, 10);  // test knob
     const uint64_t sample_bytes = packed ? N * W * 4 : E * N;   // one sample on the device
@@ -124,6 +134,7 @@ static int sim_run_sampling_impl(ising_sim* sim, double beta, uint64_t thermaliz
 extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t thermalization,
                                       uint64_t sampling_freq, uint64_t ns, double* energies,
                                       uint8_t* states) {
+    CtxLock _lk(sim ? sim->ctx : nullptr);
     if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     if (ns && !states) return fail(sim->ctx, ISING_E_INVALID, "output buffers are NULL");
     return sim_run_sampling_impl(sim, beta, thermalization, sampling_freq, ns, energies, states, nullptr);
@@ -132,6 +143,7 @@ extern "C" int ising_sim_run_sampling(ising_sim* sim, double beta, uint64_t ther
 extern "C" int ising_sim_run_sampling_packed(ising_sim* sim, double beta, uint64_t thermalization,
                                              uint64_t sampling_freq, uint64_t ns, double* energies,
                                              uint32_t* words) {
+    CtxLock _lk(sim ? sim->ctx : nullptr);
     if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     if (ns && !words) return fail(sim->ctx, ISING_E_INVALID, "output buffers are NULL");
     return sim_run_sampling_impl(sim, beta, thermalization, sampling_freq, ns, energies, nullptr, words);
@@ -144,6 +156,7 @@ extern "C" int ising_sim_run_sampling_packed(ising_sim* sim, double beta, uint64
 extern "C" int ising_sim_run_observables(ising_sim* sim, double beta, uint64_t thermalization,
                                          uint64_t sampling_freq, uint64_t ns, double* energies,
                                          double* mags, double* overlaps) {
+    CtxLock _lk(sim ? sim->ctx : nullptr);
     if (!sim) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     ising_ctx* ctx = sim->ctx;
     if (sim->perbeta) return fail(ctx, ISING_E_INVALID, "sampling runs at one beta");
@@ -200,6 +213,7 @@ extern "C" int ising_sim_run_observables(ising_sim* sim, double beta, uint64_t t
 extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph* g,
                                               const ising_run_args* a, double* energies,
                                               uint8_t* states) {
+    CtxLock _lk(ctx);
     int rc = check_run_args(ctx, g, a, energies, states);
     if (rc) return rc;
     if (a->sampling_freq == 0)
@@ -217,6 +231,7 @@ extern "C" int ising_run_monte_carlo_sampling(ising_ctx* ctx, const ising_graph*
 extern "C" int ising_run_monte_carlo_annealing(ising_ctx* ctx, const ising_graph* g,
                                                const ising_run_args* a, double* energies,
                                                uint8_t* states) {
+    CtxLock _lk(ctx);
     int rc = check_run_args(ctx, g, a, energies, states);
     if (rc) return rc;
     if (a->sched_len && (!a->sched_t || !a->sched_beta))
@@ -246,6 +261,7 @@ extern "C" int ising_run_monte_carlo_annealing(ising_ctx* ctx, const ising_graph
 extern "C" int ising_replay(ising_ctx* ctx, const ising_graph* g, double beta, uint64_t E,
                             uint64_t A, const uint32_t* sites, const double* u,
                             const uint8_t* init, double* energies, uint8_t* states) {
+    CtxLock _lk(ctx);
     if (!ctx || !g) return fail(ctx, ISING_E_INVALID, "ctx/graph is NULL");
     if (E == 0) return ISING_OK;
     if (!init || !energies || !states || (A && (!sites || !u)))

@@ -10,12 +10,16 @@ void count_launch(ising_sim* s, int n) {
 
 extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_t E, uint64_t seed,
                                    uint64_t replica_offset, uint32_t flags, ising_sim** out) {
+    CtxLock _lk(ctx);
     if (!ctx || !g || !out) return fail(ctx, ISING_E_INVALID, "ctx/graph/out is NULL");
     *out = nullptr;
     if (g->ctx != ctx) return fail(ctx, ISING_E_INVALID, "graph belongs to another context");
     if (E == 0) return fail(ctx, ISING_E_INVALID, "num_experiments must be > 0");
     if (replica_offset % 32) return fail(ctx, ISING_E_INVALID, "replica_offset must be a multiple of 32");
     const HostGraph& h = g->h;
+    // Philox counter word 0 is the 32-bit site index
+    if (h.nvars > 0xFFFFFFFFull)
+        return fail(ctx, ISING_E_UNSUPPORTED, "graphs of 2^32 or more sites are not supported (32-bit site index in the RNG counter)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     // integer energy classes (all |J| equal, no bias, degree <= 15) use the bit-sliced kernels;
     // anything else the reference accepts runs on the float-field kernel
@@ -67,10 +71,12 @@ extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_
 
 extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E, uint64_t seed,
                                 uint64_t replica_offset, ising_sim** out) {
+    CtxLock _lk(ctx);
     return ising_sim_create_ex(ctx, g, E, seed, replica_offset, 0u, out);
 }
 
 extern "C" void ising_sim_destroy(ising_sim* s) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
@@ -84,6 +90,7 @@ extern "C" void ising_sim_destroy(ising_sim* s) {
 }
 
 extern "C" int ising_sim_configure(ising_sim* s, int planes, int rounds) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     if (planes) {
         if (planes < 5 || planes > 7) return fail(s->ctx, ISING_E_INVALID, "planes must be 5..7");
@@ -97,6 +104,7 @@ extern "C" int ising_sim_configure(ising_sim* s, int planes, int rounds) {
 }
 
 extern "C" int ising_sim_randomize(ising_sim* s) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -108,6 +116,7 @@ extern "C" int ising_sim_randomize(ising_sim* s) {
 }
 
 extern "C" int ising_sim_set_state(ising_sim* s, const uint8_t* state) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !state) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/state is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -124,6 +133,7 @@ extern "C" int ising_sim_set_state(ising_sim* s, const uint8_t* state) {
 }
 
 extern "C" int ising_sim_set_states(ising_sim* s, const uint8_t* states) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !states) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/states is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -270,6 +280,8 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
     SweepArgs a;
     a.spins = s->d_spins;
     a.jmask = s->g->d_jmask;
+    a.jmask8 = s->g->d_jmask8;
+    a.sm_count = ctx->sm_count;
     a.lay = s->lay;
     a.sweep = (uint32_t)s->sweep_counter;
     a.key0 = (uint32_t)s->seed;
@@ -318,6 +330,8 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     SweepArgs a;
     a.spins = s->d_spins;
     a.jmask = s->g->d_jmask;
+    a.jmask8 = s->g->d_jmask8;
+    a.sm_count = ctx->sm_count;
     a.lay = s->lay;
     a.sweep = (uint32_t)s->sweep_counter;
     a.key0 = (uint32_t)s->seed;
@@ -393,6 +407,12 @@ int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
 // nsweeps sweeps enqueued on the context's stream, no host wait and no timing (the tempering
 // loop synchronises once per swap step, when it reads the energies)
 int sim_enqueue_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps) {
+    // Philox counter word 2 is the 32-bit sweep index: refuse to wrap (a wrapped counter would
+    // silently replay the random streams of sweeps 0, 1, ...)
+    if (s->sweep_counter + nsweeps > 0xFFFFFFFFull || s->sweep_counter + nsweeps < nsweeps)
+        return fail(s->ctx, ISING_E_UNSUPPORTED,
+                    "sweep counter would pass 2^32 (%llu done, %llu requested): start a new simulation or seed",
+                    (unsigned long long)s->sweep_counter, (unsigned long long)nsweeps);
     uint64_t t = 0;
     while (t < nsweeps) {
         const uint64_t nt = std::min<uint64_t>(4096, nsweeps - t);
@@ -411,6 +431,7 @@ int sim_enqueue_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps) {
 
 extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps,
                                 double* energies_per_sweep) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     if (s->perbeta ? betas != nullptr : (nsweeps && !betas))
         return fail(s->ctx, ISING_E_INVALID,
@@ -421,6 +442,10 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     const HostGraph& h = s->g->h;
     const uint64_t E = s->E;
     const int mult = s->general ? 1 : 2;
+    if (s->sweep_counter + nsweeps > 0xFFFFFFFFull || s->sweep_counter + nsweeps < nsweeps)
+        return fail(ctx, ISING_E_UNSUPPORTED,
+                    "sweep counter would pass 2^32 (%llu done, %llu requested): start a new simulation or seed",
+                    (unsigned long long)s->sweep_counter, (unsigned long long)nsweeps);
     if (!energies_per_sweep) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         const int rc0 = sim_enqueue_sweeps(s, betas, nsweeps);
@@ -506,6 +531,7 @@ int sim_energies_to_device(ising_sim* s, double* d_out, uint64_t estride, uint64
 }
 
 extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !energies) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/energies is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -521,6 +547,7 @@ extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
 }
 
 extern "C" int ising_sim_get_magnetization(ising_sim* s, double* m) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !m) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/m is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -551,12 +578,14 @@ int sim_states_to_host(ising_sim* s, uint8_t* states) {
 }
 
 extern "C" int ising_sim_get_states(ising_sim* s, uint8_t* states) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !states) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/states is NULL");
     CUDA_TRY(s->ctx, cudaSetDevice(s->ctx->device));
     return sim_states_to_host(s, states);
 }
 
 extern "C" int ising_sim_get_packed(ising_sim* s, uint32_t* words) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !words) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/words is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -573,6 +602,7 @@ extern "C" int ising_sim_get_packed(ising_sim* s, uint32_t* words) {
 // checkpoint support: the packed state in natural order plus the sweep counter are the whole
 // state of a sim (the RNG is counter-based: seed + counter, nothing else to save)
 extern "C" int ising_sim_set_packed(ising_sim* s, const uint32_t* words) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !words) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/words is NULL");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -586,24 +616,28 @@ extern "C" int ising_sim_set_packed(ising_sim* s, const uint32_t* words) {
 }
 
 extern "C" int ising_sim_get_counter(const ising_sim* s, uint64_t* sweeps_done) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !sweeps_done) return fail(nullptr, ISING_E_INVALID, "sim/out is NULL");
     *sweeps_done = s->sweep_counter;
     return ISING_OK;
 }
 
 extern "C" int ising_sim_set_counter(ising_sim* s, uint64_t sweeps_done) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     s->sweep_counter = sweeps_done;
     return ISING_OK;
 }
 
 extern "C" int ising_sim_get_stats(ising_sim* s, ising_sim_stats* out) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !out) return fail(nullptr, ISING_E_INVALID, "sim/out is NULL");
     *out = s->stats;
     return ISING_OK;
 }
 
 extern "C" int ising_sim_reset_stats(ising_sim* s) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
     s->stats = ising_sim_stats{};
     return ISING_OK;

@@ -20,6 +20,7 @@ struct ising_strip {
 extern "C" int ising_strip_create_ex(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
                                      uint64_t row_hi, double j, uint64_t seed, uint32_t ghost,
                                      ising_strip** out) {
+    CtxLock _lk(ctx);
     if (!ctx || !out) return fail(ctx, ISING_E_INVALID, "ctx/out is NULL");
     *out = nullptr;
     if (ghost < 1 || ghost > row_hi - row_lo || ghost > 1024)
@@ -58,10 +59,12 @@ extern "C" int ising_strip_create_ex(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, u
 
 extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint64_t row_lo,
                                   uint64_t row_hi, double j, uint64_t seed, ising_strip** out) {
+    CtxLock _lk(ctx);
     return ising_strip_create_ex(ctx, Lx, Ly, row_lo, row_hi, j, seed, 1, out);
 }
 
 extern "C" void ising_strip_destroy(ising_strip* s) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
@@ -71,6 +74,7 @@ extern "C" void ising_strip_destroy(ising_strip* s) {
 }
 
 extern "C" int ising_strip_configure(ising_strip* s, int planes, int rounds) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     if (planes) {
         if (planes < 5 || planes > 7) return fail(s->ctx, ISING_E_INVALID, "planes must be 5..7");
@@ -84,6 +88,7 @@ extern "C" int ising_strip_configure(ising_strip* s, int planes, int rounds) {
 }
 
 extern "C" int ising_strip_set_all(ising_strip* s, int up) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     CUDA_TRY(s->ctx, cudaSetDevice(s->ctx->device));
     CUDA_TRY(s->ctx, cudaMemsetAsync(s->d_spins, up ? 0xFF : 0x00, s->bytes, s->ctx->stream));
@@ -97,6 +102,8 @@ extern "C" int ising_strip_set_all(ising_strip* s, int up) {
 static int strip_phase_storage_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
                                     int advance, int sync) {
     ising_ctx* ctx = s->ctx;
+    if (s->sweep > 0xFFFFFFFFull)   // 32-bit sweep index in the Philox counter: refuse to wrap
+        return fail(ctx, ISING_E_UNSUPPORTED, "sweep counter passed 2^32: start a new lattice or seed");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     StripSweepArgs a;
     a.spins = s->d_spins;
@@ -134,6 +141,7 @@ static int strip_phase_storage_rows(ising_strip* s, int colour, double beta, uin
 
 extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, uint64_t r0, uint64_t r1,
                                       int advance, int sync) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
     if (r0 > r1 || r1 > s->g.rows) return fail(s->ctx, ISING_E_INVALID, "bad row range");
     return strip_phase_storage_rows(s, colour, beta, s->g.ghost + r0, s->g.ghost + r1, advance, sync);
@@ -145,6 +153,7 @@ extern "C" int ising_strip_phase_rows(ising_strip* s, int colour, double beta, u
 // batch (q = 0 .. 2k-1) is called with ext = 2k - 1 - q.
 extern "C" int ising_strip_phase_ext(ising_strip* s, int colour, double beta, uint32_t ext, int advance,
                                      int sync) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad strip/colour");
     if (ext >= s->g.ghost) return fail(s->ctx, ISING_E_INVALID, "ext must be < ghost depth");
     return strip_phase_storage_rows(s, colour, beta, s->g.ghost - ext, s->g.ghost + s->g.rows + ext,
@@ -153,6 +162,7 @@ extern "C" int ising_strip_phase_ext(ising_strip* s, int colour, double beta, ui
 
 // one whole colour phase, blocking; the sweep counter advances after colour 1
 extern "C" int ising_strip_phase(ising_strip* s, int colour, double beta) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     return ising_strip_phase_rows(s, colour, beta, 0, s->g.rows, colour == 1, 1);
 }
@@ -169,6 +179,7 @@ static uint32_t* strip_row_ptr(ising_strip* s, int colour, uint32_t r) {
 // sends side 0 to the strip above and side 1 to the strip below and receives the upper
 // neighbour's side 1 into its side 0.  sync = 0 only enqueues.
 extern "C" int ising_strip_halo_deep(ising_strip* s, int dir, uint32_t depth, void* buf, int sync) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !buf) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     const StripGeom& g = s->g;
@@ -194,6 +205,7 @@ extern "C" int ising_strip_halo_deep(ising_strip* s, int dir, uint32_t depth, vo
 
 // single strip covering the whole lattice: periodic wrap of `depth` rows of both colours
 extern "C" int ising_strip_wrap_deep(ising_strip* s, uint32_t depth) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     ising_ctx* ctx = s->ctx;
     const StripGeom& g = s->g;
@@ -213,6 +225,7 @@ extern "C" int ising_strip_wrap_deep(ising_strip* s, uint32_t depth) {
 
 // which = 0: first local row, 1: last local row.  dst holds Lx/64 words, host or device memory.
 extern "C" int ising_strip_get_boundary(ising_strip* s, int colour, int which, void* dst) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !dst || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -227,6 +240,7 @@ extern "C" int ising_strip_get_boundary(ising_strip* s, int colour, int which, v
 // buf_dev[Wr..2Wr) (last row); dir = 1 copies buf_dev[0..Wr) into the ghost row above the first
 // row and buf_dev[Wr..2Wr) into the ghost row below the last row.
 extern "C" int ising_strip_halo_async(ising_strip* s, int colour, int dir, void* buf_dev) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !buf_dev || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -244,6 +258,7 @@ extern "C" int ising_strip_halo_async(ising_strip* s, int colour, int dir, void*
 
 // which = 0: ghost row above the first local row, 1: ghost row below the last local row
 extern "C" int ising_strip_set_ghost(ising_strip* s, int colour, int which, const void* src) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !src || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -255,6 +270,7 @@ extern "C" int ising_strip_set_ghost(ising_strip* s, int colour, int which, cons
 
 // single strip covering the whole lattice: periodic wrap of its own boundary rows
 extern "C" int ising_strip_wrap_local(ising_strip* s, int colour) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || colour < 0 || colour > 1) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -268,6 +284,7 @@ extern "C" int ising_strip_wrap_local(ising_strip* s, int colour) {
 
 // local sums: satisfied bonds (colour-0 sites see every bond once; needs colour-1 ghosts) and up spins
 extern "C" int ising_strip_observables(ising_strip* s, uint64_t* nsat, uint64_t* up) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !nsat || !up) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -284,6 +301,7 @@ extern "C" int ising_strip_observables(ising_strip* s, uint64_t* nsat, uint64_t*
 }
 
 extern "C" int ising_strip_get_rows(ising_strip* s, uint8_t* rows_out) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !rows_out) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
     ising_ctx* ctx = s->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -299,6 +317,7 @@ extern "C" int ising_strip_get_rows(ising_strip* s, uint8_t* rows_out) {
 }
 
 extern "C" int ising_strip_get_stats(ising_strip* s, uint64_t* launches, double* device_ms, int reset) {
+    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return fail(nullptr, ISING_E_INVALID, "strip is NULL");
     if (launches) *launches = s->launches;
     if (device_ms) *device_ms = s->device_ms;

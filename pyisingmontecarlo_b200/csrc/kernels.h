@@ -6,6 +6,10 @@
 
 namespace ising {
 
+// SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device): grids of the
+// persistent / grid-stride kernels are sized in multiples of it, never from a literal.
+unsigned device_sms();
+
 // Replica-bit-packed spin storage.  One 32-bit word = one site in 32 experiments.
 //   general graph : word(n, w) at n * W + w                          (natural site order)
 //   stencil       : colour-compacted checkerboard, word(c, row, xh, w) at
@@ -30,6 +34,8 @@ struct MscThresholds {
 struct SweepArgs {
     uint32_t* spins;
     const uint32_t* jmask;  // stencil +-J: [colour][6 or 4][halfN] bond masks, else nullptr
+    const uint32_t* jmask8 = nullptr;  // the same, site-major [colour][halfN][8] (row-walk kernel)
+    int sm_count = 0;       // SMs of the device (persistent grids)
     Layout lay;
     uint32_t sweep;         // global sweep index (Philox counter word 2)
     uint32_t key0, key1;    // Philox key = seed
@@ -50,6 +56,9 @@ int launch_build_tables_stencil(const unsigned long long* t64, uint32_t W, int K
 
 // both colour phases of one sweep (2 launches); returns launches made or -1
 int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st);
+// the same through the persistent row-walk kernels (sweep_rows.cuh); 0 = configuration not covered
+int launch_sweep_rows_2d(const SweepArgs& a, cudaStream_t st);
+int launch_sweep_rows_3d(const SweepArgs& a, cudaStream_t st);
 // A chunk of nsweeps whole sweeps in ONE cooperative launch (grid barrier between colour phases):
 // for lattices so small that a colour phase is launch-bound.  th_dev[nsweeps] = thresholds per
 // sweep (device memory); hist (or nullptr) receives the per-sweep n_sat at hist[t * cw + e].

@@ -119,6 +119,12 @@ __device__ __forceinline__ void vadd(uint32_t (&acc)[NR], const uint32_t (&x)[NX
     }
 }
 
+#ifndef ISING_SW_NP
+#define ISING_SW_NP 7
+#endif
+constexpr int SW_NP = ISING_SW_NP;                       // fused n_sat counter planes per thread
+constexpr int SW_MAX_ITEMS = ((1 << SW_NP) - 1) / 6;    // sites a thread may accumulate (n_sat <= 6)
+
 constexpr int NS_NR = 20;  // block-level counter planes: 256 threads x 1023 fits 18 bits
 
 // Block-wide reduction of per-thread vertical counters (NP planes, V replica words per thread,

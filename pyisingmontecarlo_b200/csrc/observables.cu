@@ -40,7 +40,7 @@ int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long
     const uint32_t wx = lay.W >= 32 ? 32 : pow2_ceil(lay.W);
     dim3 block(wx, 256 / wx, 1);
     uint64_t g = (lay.nvars + block.y - 1) / block.y;
-    if (g > 148u * 8u) g = 148u * 8u;
+    if (g > device_sms() * 8u) g = device_sms() * 8u;
     if (g == 0) g = 1;
     k_count_up<<<dim3((unsigned)g), block, 0, st>>>(spins, lay.nvars, lay.W, up, pair ? 1u : 0u);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

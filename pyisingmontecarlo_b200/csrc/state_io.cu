@@ -3,6 +3,20 @@
 
 namespace ising {
 
+unsigned device_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = cached[dev];
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 1;
+        cached[dev] = v;   // benign race: every writer stores the same value
+    }
+    return (unsigned)v;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // state initialisation / import / export (not hot)
 // ------------------------------------------------------------------------------------------
@@ -20,7 +34,7 @@ __global__ void k_init_random(uint32_t* __restrict__ spins, Layout L, uint32_t k
 
 int launch_init_random(uint32_t* spins, const Layout& lay, uint32_t key0, uint32_t key1,
                        uint32_t gw0, cudaStream_t st) {
-    k_init_random<<<148 * 8, 256, 0, st>>>(spins, lay, key0, key1, gw0);
+    k_init_random<<<device_sms() * 8, 256, 0, st>>>(spins, lay, key0, key1, gw0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -37,7 +51,7 @@ __global__ void k_init_broadcast(uint32_t* __restrict__ spins, Layout L,
 
 int launch_init_broadcast(uint32_t* spins, const Layout& lay, const uint8_t* state_dev,
                           cudaStream_t st) {
-    k_init_broadcast<<<148 * 8, 256, 0, st>>>(spins, lay, state_dev);
+    k_init_broadcast<<<device_sms() * 8, 256, 0, st>>>(spins, lay, state_dev);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -60,7 +74,7 @@ __global__ void k_pack_states(uint32_t* __restrict__ spins, Layout L,
 
 int launch_pack_states(uint32_t* spins, const Layout& lay, const uint8_t* states_dev, uint64_t E,
                        cudaStream_t st) {
-    k_pack_states<<<148 * 8, 256, 0, st>>>(spins, lay, states_dev, E);
+    k_pack_states<<<device_sms() * 8, 256, 0, st>>>(spins, lay, states_dev, E);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -106,7 +120,7 @@ k_unpack_states(const uint32_t* __restrict__ spins, Layout L, uint8_t* __restric
 
 int launch_unpack_states(const uint32_t* spins, const Layout& lay, uint8_t* out_dev, uint64_t E,
                          uint64_t out_stride, cudaStream_t st) {
-    k_unpack_states<<<148 * 8, 256, 0, st>>>(spins, lay, out_dev, E, out_stride);
+    k_unpack_states<<<device_sms() * 8, 256, 0, st>>>(spins, lay, out_dev, E, out_stride);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -133,13 +147,13 @@ __global__ void k_import_natural(uint32_t* __restrict__ spins, Layout L,
 }
 
 int launch_import_natural(uint32_t* spins, const Layout& lay, const uint32_t* in_dev, cudaStream_t st) {
-    k_import_natural<<<148 * 8, 256, 0, st>>>(spins, lay, in_dev);
+    k_import_natural<<<device_sms() * 8, 256, 0, st>>>(spins, lay, in_dev);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_export_natural(const uint32_t* spins, const Layout& lay, uint32_t* out_dev,
                           cudaStream_t st) {
-    k_export_natural<<<148 * 8, 256, 0, st>>>(spins, lay, out_dev);
+    k_export_natural<<<device_sms() * 8, 256, 0, st>>>(spins, lay, out_dev);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

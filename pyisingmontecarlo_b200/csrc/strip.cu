@@ -59,7 +59,7 @@ static int strip_phase_dispatch(const StripSweepArgs& a, cudaStream_t st) {
     uint32_t gx = (groups + bx - 1) / bx;
     if (gx > 64) gx = 64;
     uint32_t gy = (a.r_count + block.y - 1) / block.y;
-    const uint32_t gy_cap = (148u * 32u + gx - 1) / gx;
+    const uint32_t gy_cap = (device_sms() * 32u + gx - 1) / gx;
     if (gy > gy_cap) gy = gy_cap;
     const dim3 grid(gx, gy, 1);
 #define STRIP_LAUNCH(KK, RR)                                                                     \
@@ -102,7 +102,7 @@ __global__ void k_strip_init_random(uint32_t* __restrict__ spins, StripGeom g, u
 
 int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,
                              cudaStream_t st) {
-    k_strip_init_random<<<148 * 8, 256, 0, st>>>(spins, g, key0, key1);
+    k_strip_init_random<<<device_sms() * 8, 256, 0, st>>>(spins, g, key0, key1);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -140,7 +140,7 @@ k_strip_observables(const uint32_t* __restrict__ spins, StripGeom g, uint32_t an
 
 int launch_strip_observables(const uint32_t* spins, const StripGeom& g, uint32_t antiferro,
                              unsigned long long* acc, cudaStream_t st) {
-    k_strip_observables<<<148 * 4, 256, 0, st>>>(spins, g, antiferro, acc);
+    k_strip_observables<<<device_sms() * 4, 256, 0, st>>>(spins, g, antiferro, acc);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -159,7 +159,7 @@ __global__ void k_strip_unpack(const uint32_t* __restrict__ spins, StripGeom g,
 }
 
 int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st) {
-    k_strip_unpack<<<148 * 8, 256, 0, st>>>(spins, g, out_dev);
+    k_strip_unpack<<<device_sms() * 8, 256, 0, st>>>(spins, g, out_dev);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

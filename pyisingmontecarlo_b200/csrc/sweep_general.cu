@@ -165,7 +165,7 @@ static void gen_launch(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st
     const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
     const dim3 block(wx, 256 / wx, 1);
     uint64_t blocks = ((uint64_t)g.count + block.y - 1) / block.y;
-    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    if (blocks > (uint64_t)device_sms() * 16) blocks = (uint64_t)device_sms() * 16;
     const dim3 grid((unsigned)blocks);
     const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
     if (a.tables.plane != nullptr)
@@ -329,7 +329,7 @@ int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const
     const uint32_t wx = W >= 32 ? 32 : pow2_ceil(W);
     dim3 block(wx, 256 / wx, 1);
     uint64_t g = (nvars + block.y - 1) / block.y;
-    if (g > 148u * 8u) g = 148u * 8u;
+    if (g > device_sms() * 8u) g = device_sms() * 8u;
     if (g == 0) g = 1;
     k_nsat_general<<<dim3((unsigned)g), block, 0, st>>>(spins, nvars, W, row, nbr, anti, nsat2);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -385,7 +385,7 @@ int launch_sweep_real(const RealSweepArgs& a, cudaStream_t st) {
     const uint32_t wx = a.W >= 32 ? 32 : pow2_ceil(a.W);
     const dim3 block(wx, 256 / wx, 1);
     uint64_t blocks = ((uint64_t)a.count + block.y - 1) / block.y;
-    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    if (blocks > (uint64_t)device_sms() * 16) blocks = (uint64_t)device_sms() * 16;
     if (a.rounds == 7) k_sweep_real<7><<<(unsigned)blocks, block, 0, st>>>(a);
     else k_sweep_real<10><<<(unsigned)blocks, block, 0, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -425,7 +425,7 @@ int launch_energy_real(const uint32_t* spins, uint64_t nvars, uint32_t W, const 
     const uint32_t wx = W >= 32 ? 32 : pow2_ceil(W);
     dim3 block(wx, 128 / wx, 1);
     uint64_t g = (nvars + block.y - 1) / block.y;
-    if (g > 148u * 4u) g = 148u * 4u;
+    if (g > device_sms() * 4u) g = device_sms() * 4u;
     if (g == 0) g = 1;
     dim3 grid((unsigned)g, (W + wx - 1) / wx, 1);
     k_energy_real<<<grid, block, 0, st>>>(spins, nvars, W, row, nbr, jv, bias, energies);

@@ -19,14 +19,9 @@ namespace ising {
 #ifndef ISING_SWEEP_MAXV
 #define ISING_SWEEP_MAXV 4
 #endif
-#ifndef ISING_SW_NP
-#define ISING_SW_NP 7
-#endif
 #ifndef ISING_ACC_MIN_BLOCKS
 #define ISING_ACC_MIN_BLOCKS 2
 #endif
-constexpr int SW_NP = ISING_SW_NP;                       // fused n_sat counter planes per thread
-constexpr int SW_MAX_ITEMS = ((1 << SW_NP) - 1) / 6;    // sites a thread may accumulate (n_sat <= 6)
 
 // ACC: this phase also accumulates the post-flip satisfied-bond count of every replica into
 // nsat[] (used for the second colour: its sites see every bond once, so after the phase

@@ -1,0 +1,463 @@
+// K2/K3, large lattices: one colour phase of a checkerboard sweep as a persistent row walk.
+//
+// A block owns a balanced, contiguous range of work units (unit = NRS consecutive rows of one z
+// plane x one tile of half-row positions x one tile of replica-word groups) and a thread keeps its
+// (xh, word group) as long as the tile does not change.  The row geometry of a chunk of units
+// (row offsets of the five neighbour rows, Philox site base, parity) is computed once per chunk
+// into shared memory, so the per-site work is two broadcast LDS, the seven vector loads, the
+// Philox calls, the bit-sliced neighbour count and the Metropolis mask - no per-site index
+// arithmetic on the ALU pipe, which is the pipe this kernel saturates
+// (profiles/r01_sweep_metrics.md: ALU 60-67 %, FMA heavy 42 %).  Two more things move work from
+// the ALU pipe to the FMA pipe:
+//   * the class select of the threshold planes: with one-hot class masks m1, m2 (disjoint) the
+//     plane word is t = c0 + m1 * d1 + m2 * d2 in 32-bit arithmetic (d = difference of the 0/1
+//     threshold bits, c0 = all-ones or 0) - one IMAD per class instead of one LOP3;
+//   * the tie resolver's comparisons r < low_c: the high word of r + (2^64 - low_c), one
+//     IMAD.WIDE, is the all-ones / zero accept mask of class c.
+// Philox: the V words x 2 calls of a site share the counter words (site, sweep), so rounds 1-3
+// need 1 + (V + 2) + (V + 2) multiplications instead of 3 * 4V (written out in philox_site).
+// Results are bit-identical to sweep_colour_phase / oracle/msc_mirror.c.
+#pragma once
+#include "msc_device.cuh"
+
+// tuning knobs (profiles/microbench/rows_variants.sh builds and times the alternatives)
+#ifndef ISING_ROWS_MINB
+#define ISING_ROWS_MINB 3        // resident blocks per SM the plain colour phase is compiled for
+#endif
+#ifndef ISING_ROWS_ACC_MINB
+#define ISING_ROWS_ACC_MINB 2    // ... the accumulating colour phase
+#endif
+#ifndef ISING_ROWS_DEFER_RARE
+#define ISING_ROWS_DEFER_RARE 0  // 1: third-and-later ties of all V words after the word loop
+#endif
+
+namespace ising {
+
+struct MscMux {
+    uint32_t c0[8];   // plane p of class 0 (all-ones / 0)
+    uint32_t d1[8];   // bit(class 1) - bit(class 0)  in {0, 1, 0xFFFFFFFF}
+    uint32_t d2[8];   // bit(class 2) - bit(class 0)
+    uint32_t low[3];
+    uint32_t one;     // 1 (keeps r * one + c an IMAD.WIDE)
+};
+
+inline MscMux make_mux(const MscThresholds& th) {
+    MscMux m;
+    for (int p = 0; p < 8; ++p) {
+        m.c0[p] = th.plane[0][p];
+        m.d1[p] = (th.plane[1][p] & 1u) - (th.plane[0][p] & 1u);
+        m.d2[p] = (th.plane[2][p] & 1u) - (th.plane[0][p] & 1u);
+    }
+    for (int c = 0; c < 3; ++c) m.low[c] = th.low[c];
+    m.one = 1u;
+    return m;
+}
+
+struct RowsArgs {
+    uint32_t* own;          // colour being updated   [rows][Lxh][W]
+    const uint32_t* oth;    // the other colour
+    const uint4* jm8;       // +-J: bond masks of this colour [rows][Lxh][2] uint4 (k = 0..5, 2 pad)
+    uint32_t Lx, Ly, Lz, Lxh, W;
+    uint32_t c, sweep, gw0, antiferro;
+    uint32_t bxh_log;       // threadIdx.y = rsub << bxh_log | xh_local
+    uint32_t nrs_log;       // rows per unit = 1 << nrs_log (divides Ly)
+    uint32_t ygroups, xtiles;
+    uint32_t units;         // tiles * Lz * ygroups, tile = wt * xtiles + xt slowest
+    uint32_t uq, urem;      // units = uq * gridDim.x + urem: block b gets uq (+1 if b < urem) units
+    unsigned long long* nsat;
+    PhiloxKeys pk;
+    MscMux mx;
+};
+
+// geometry of one row of one unit (shared memory, built once per chunk of units)
+struct RowDesc {
+    uint32_t e_row, e_ym, e_yp, e_zm, e_zp;  // row base offsets in vector elements (V words)
+    uint32_t site0;                          // row * Lx + parity
+    uint32_t par_tile;                       // parity | tile << 1;  0xFFFFFFFF = no row (y >= Ly)
+    uint32_t jrow;                           // row * Lxh * 2 (uint4 index of the row's bond masks)
+};
+constexpr int ROWS_DESC_CHUNK = 64;          // RowDesc entries per chunk (2 KiB)
+
+// Two Philox4x32 calls (q = 0, 1) for each of V replica words of one site: counter
+// (site, gw0 + v, sweep, q | TAG_ACCEPT << 24).  r[v][4 q + i] = output word i of call q.
+template <int ROUNDS, int V>
+struct PhiloxSite {
+    // state after round 3, shared parts
+    uint32_t c1v[V], c3q[2], hq0[2], hq1v[V], c1q[2], c3v[V];
+    __device__ __forceinline__ void prepare(uint32_t site, uint32_t gw0v, uint32_t sweep,
+                                            const PhiloxKeys& pk) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        // round 1
+        const uint64_t p0 = (uint64_t)M0 * site;
+        const uint64_t p1 = (uint64_t)M1 * sweep;
+        const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0;
+        const uint32_t h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+        // round 2: c0 = h1 ^ gw ^ k0 (per word), c1 = l1, c2 = h0 ^ cq ^ k1 (per call), c3 = l0
+        uint32_t c0q[2], c2v[V];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t c2 = h0 ^ ((uint32_t)q | (TAG_ACCEPT << 24)) ^ pk.k[1];
+            const uint64_t P1 = (uint64_t)M1 * c2;
+            c0q[q] = (uint32_t)(P1 >> 32) ^ l1 ^ pk.k[2];
+            c1q[q] = (uint32_t)P1;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint32_t c0 = h1 ^ (gw0v + v) ^ pk.k[0];
+            const uint64_t P0 = (uint64_t)M0 * c0;
+            c2v[v] = (uint32_t)(P0 >> 32) ^ l0 ^ pk.k[3];
+            c3v[v] = (uint32_t)P0;
+        }
+        // round 3 products: M0 * c0 (per call), M1 * c2 (per word)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint64_t Q0 = (uint64_t)M0 * c0q[q];
+            hq0[q] = (uint32_t)(Q0 >> 32);
+            c3q[q] = (uint32_t)Q0;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint64_t Q1 = (uint64_t)M1 * c2v[v];
+            hq1v[v] = (uint32_t)(Q1 >> 32);
+            c1v[v] = (uint32_t)Q1;
+        }
+    }
+    // rounds 4 .. ROUNDS of call q of word v
+    __device__ __forceinline__ void finish(int v, int q, const PhiloxKeys& pk, uint32_t* out) const {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        uint32_t c0 = hq1v[v] ^ c1q[q] ^ pk.k[4];
+        uint32_t c1 = c1v[v];
+        uint32_t c2 = hq0[q] ^ c3v[v] ^ pk.k[5];
+        uint32_t c3 = c3q[q];
+#pragma unroll
+        for (int r = 3; r < ROUNDS; ++r) {
+            const uint64_t p0 = (uint64_t)M0 * c0;
+            const uint64_t p1 = (uint64_t)M1 * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[2 * r];
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk.k[2 * r + 1];
+            c1 = (uint32_t)p1;
+            c3 = (uint32_t)p0;
+            c0 = n0;
+            c2 = n2;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+// all-ones iff r < lo, on the FMA pipe: high word of r * 1 + (2^64 - lo)
+__device__ __forceinline__ uint32_t lt_mask(uint32_t r, uint32_t lo, uint32_t one) {
+    const uint64_t neg = 0ull - (uint64_t)lo;
+    return (uint32_t)(((uint64_t)r * one + neg) >> 32);
+}
+
+// Metropolis mask of one word from eight random words r (two Philox calls).
+//   up: dE > 0;  m1, m2: one-hot masks of uphill classes 1 and 2 (class 0 = up & ~m1 & ~m2)
+template <int NCLS, int K, int ROUNDS>
+__device__ __forceinline__ uint32_t msc_flip_mask_mux(uint32_t up, uint32_t m1, uint32_t m2,
+                                                      const MscMux& mx, const uint32_t (&r)[8],
+                                                      uint32_t site, uint32_t gw, uint32_t sweep,
+                                                      const PhiloxKeys& pk, uint32_t* eq_left = nullptr) {
+    static_assert(K >= 4 && K <= 7, "two Philox calls: K planes + (8 - K) resolver words");
+    uint32_t eq = up, borrow = 0;
+#pragma unroll
+    for (int p = K - 1; p >= 0; --p) {
+        uint32_t t = m1 * mx.d1[p] + mx.c0[p];
+        if (NCLS == 3) t += m2 * mx.d2[p];
+        borrow = maj3(~r[p], t, borrow);
+        eq &= ~(r[p] ^ t);
+    }
+    uint32_t flip = ~up | (borrow & ~eq);
+    // Tied bits (2^-K each): the first SPARE of a word, in ascending bit position, compare the
+    // words left over from the two calls against the low threshold bits of their class.
+    constexpr int SPARE = (8 - K) < 2 ? (8 - K) : 2;
+#pragma unroll
+    for (int j = 0; j < SPARE; ++j) {
+        const uint32_t bit = eq & (0u - eq);
+        uint32_t acc = lt_mask(r[K + j], mx.low[0], mx.one);
+        acc = (m1 & lt_mask(r[K + j], mx.low[1], mx.one)) | (~m1 & acc);
+        if (NCLS == 3) acc = (m2 & lt_mask(r[K + j], mx.low[2], mx.one)) | (~m2 & acc);
+        flip |= bit & acc;
+        eq -= bit;
+    }
+    if (eq_left) {  // caller resolves the remaining ties after its word loop (msc_resolve_rest)
+        *eq_left = eq;
+        return flip;
+    }
+    if (eq) {  // third tie of a word (rare): further Philox calls, as msc_flip_mask
+        int j = K + SPARE;
+        u32x4 cur = {r[4], r[5], r[6], r[7]};
+        do {
+            const int b = __ffs((int)eq) - 1;
+            if ((j & 3) == 0 && j >= 8)
+                cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
+            const int m = j & 3;
+            const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
+            uint32_t lo = ((m1 >> b) & 1u) ? mx.low[1] : mx.low[0];
+            if (NCLS == 3 && ((m2 >> b) & 1u)) lo = mx.low[2];
+            if (v < lo) flip |= 1u << b;
+            eq &= eq - 1;
+            ++j;
+        } while (eq);
+    }
+    return flip;
+}
+
+// third and later ties of a word: resolver words 8, 9, ... = Philox calls 2, 3, ... of the word
+template <int NCLS, int K, int ROUNDS>
+__device__ __noinline__ uint32_t msc_resolve_rest(uint32_t eq, uint32_t m1, uint32_t m2, uint32_t low0,
+                                                  uint32_t low1, uint32_t low2, uint32_t site, uint32_t gw,
+                                                  uint32_t sweep, const PhiloxKeys& pk) {
+    uint32_t flip = 0;
+    int j = 8;
+    u32x4 cur = {0, 0, 0, 0};
+    do {
+        const int b = __ffs((int)eq) - 1;
+        if ((j & 3) == 0)
+            cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
+        const int m = j & 3;
+        const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
+        uint32_t lo = ((m1 >> b) & 1u) ? low1 : low0;
+        if (NCLS == 3 && ((m2 >> b) & 1u)) lo = low2;
+        if (v < lo) flip |= 1u << b;
+        eq &= eq - 1;
+        ++j;
+    } while (eq);
+    return flip;
+}
+
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
+__device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm) {
+    typedef typename WordVec<V>::type VecT;
+    __shared__ RowDesc s_desc[ROWS_DESC_CHUNK];
+    const uint32_t Lxh = a.Lxh, W = a.W, Ly = a.Ly, Lz = a.Lz;
+    const uint32_t rowlenV = Lxh * (W / V);  // vector elements per colour row (W % V == 0)
+    const uint32_t wx = blockDim.x;
+    const uint32_t nthreads = blockDim.x * blockDim.y;
+    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t nrs_log = MULTIROW ? a.nrs_log : 0u;
+    const uint32_t bxh = MULTIROW ? (1u << a.bxh_log) : blockDim.y;
+    const uint32_t xh_l = MULTIROW ? (threadIdx.y & (bxh - 1u)) : threadIdx.y;
+    const uint32_t rsub = MULTIROW ? (threadIdx.y >> a.bxh_log) : 0u;
+    // balanced contiguous unit range of this block
+    const uint32_t b = blockIdx.x;
+    const uint32_t u0 = b * a.uq + (b < a.urem ? b : a.urem);
+    const uint32_t u1 = u0 + a.uq + (b < a.urem ? 1u : 0u);
+    const VecT* __restrict__ othv = reinterpret_cast<const VecT*>(a.oth);
+    VecT* __restrict__ ownv = reinterpret_cast<VecT*>(a.own);
+
+    VCount<ACC ? SW_NP : 1> vc[V];
+    if constexpr (ACC) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) vc[v].clear();
+    }
+    int pending = 0;
+    uint32_t cur_tile = 0xFFFFFFFFu;
+    uint32_t w = 0, xh2 = 0, toff = 0, offP = 0, offM = 0, xsite = 0;
+    bool col_ok = false;
+    const uint32_t chunk_units = ROWS_DESC_CHUNK >> nrs_log;
+
+    for (uint32_t uc = u0; uc < u1; uc += chunk_units) {
+        const uint32_t nu = u1 - uc < chunk_units ? u1 - uc : chunk_units;
+        __syncthreads();
+        for (uint32_t i = tid; i < (nu << nrs_log); i += nthreads) {
+            const uint32_t u = uc + (i >> nrs_log), rs = i & ((1u << nrs_log) - 1u);
+            const uint32_t yg = u % a.ygroups;
+            uint32_t t = u / a.ygroups;
+            const uint32_t z = t % Lz, tile = t / Lz;
+            const uint32_t y = (yg << nrs_log) + rs;
+            RowDesc d;
+            if (y < Ly) {
+                const uint32_t ym = y == 0 ? Ly - 1 : y - 1, yp = y + 1 == Ly ? 0 : y + 1;
+                const uint32_t zm = z == 0 ? Lz - 1 : z - 1, zp = z + 1 == Lz ? 0 : z + 1;
+                const uint32_t row = z * Ly + y, p = (y + z + a.c) & 1u;
+                d.e_row = row * rowlenV;
+                d.e_ym = (z * Ly + ym) * rowlenV;
+                d.e_yp = (z * Ly + yp) * rowlenV;
+                d.e_zm = (zm * Ly + y) * rowlenV;
+                d.e_zp = (zp * Ly + y) * rowlenV;
+                d.site0 = row * a.Lx + p;
+                d.par_tile = p | (tile << 1);
+                d.jrow = row * Lxh * 2u;
+            } else {
+                d.e_row = d.e_ym = d.e_yp = d.e_zm = d.e_zp = d.site0 = d.jrow = 0u;
+                d.par_tile = 0xFFFFFFFFu;
+            }
+            s_desc[i] = d;
+        }
+        __syncthreads();
+        for (uint32_t k = 0; k < nu; ++k) {
+            const uint4 da = reinterpret_cast<const uint4*>(&s_desc[(k << nrs_log) + rsub])[0];
+            const uint4 db = reinterpret_cast<const uint4*>(&s_desc[(k << nrs_log) + rsub])[1];
+            // da = (e_row, e_ym, e_yp, e_zm), db = (e_zp, site0, par_tile, jrow)
+            // the tile is the same for every row of a unit, so this branch is block-uniform
+            const uint32_t tile = reinterpret_cast<const uint32_t*>(&s_desc[k << nrs_log])[6] >> 1;
+            if (tile != cur_tile) {
+                if constexpr (ACC) {
+                    if (pending) {
+                        block_reduce_vcount<SW_NP, V>(vc, sm, a.nsat, (cur_tile / a.xtiles) * wx * V, W);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) vc[v].clear();
+                        pending = 0;
+                    }
+                }
+                cur_tile = tile;
+                const uint32_t xt = tile % a.xtiles, wt = tile / a.xtiles;
+                w = (wt * wx + threadIdx.x) * V;
+                const uint32_t xh = xt * bxh + xh_l;
+                col_ok = w < W && xh < Lxh;
+                const uint32_t wv = w / V;
+                toff = xh * (W / V) + wv;
+                offP = (xh + 1 == Lxh ? 0u : xh + 1) * (W / V) + wv;
+                offM = (xh == 0 ? Lxh - 1 : xh - 1) * (W / V) + wv;
+                xh2 = 2u * xh;
+                xsite = 2u * xh;
+            }
+            if (col_ok && db.z != 0xFFFFFFFFu) {
+                const uint32_t p = db.z & 1u;
+                const uint32_t xsoff = p ? offP : offM;
+                const uint32_t e_own = da.x + toff;
+                uint32_t s[V], n[2 * DIM][V];
+                {
+                    const VecT t0 = ownv[e_own];
+                    const VecT t1 = othv[e_own];
+                    const VecT t2 = othv[da.x + xsoff];
+                    const VecT t3 = othv[da.y + toff];
+                    const VecT t4 = othv[da.z + toff];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        s[v] = reinterpret_cast<const uint32_t*>(&t0)[v];
+                        n[0][v] = reinterpret_cast<const uint32_t*>(&t1)[v];
+                        n[1][v] = reinterpret_cast<const uint32_t*>(&t2)[v];
+                        n[2][v] = reinterpret_cast<const uint32_t*>(&t3)[v];
+                        n[3][v] = reinterpret_cast<const uint32_t*>(&t4)[v];
+                    }
+                    if (DIM == 3) {
+                        const VecT t5 = othv[da.w + toff];
+                        const VecT t6 = othv[db.x + toff];
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            n[4][v] = reinterpret_cast<const uint32_t*>(&t5)[v];
+                            n[5][v] = reinterpret_cast<const uint32_t*>(&t6)[v];
+                        }
+                    }
+                }
+                uint32_t m[2 * DIM];
+                if (PMJ) {
+                    const uint4* jp = a.jm8 + (db.w + xh2);
+                    const uint4 j0 = __ldg(jp);
+                    m[0] = j0.x; m[1] = j0.y; m[2] = j0.z; m[3] = j0.w;
+                    if (DIM == 3) {
+                        const uint2 j1 = __ldg(reinterpret_cast<const uint2*>(jp + 1));
+                        m[4] = j1.x; m[5] = j1.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < 2 * DIM; ++k2) m[k2] = a.antiferro;
+                }
+                const uint32_t site = db.y + xsite;
+                uint32_t s0[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) s0[v] = s[v];
+                PhiloxSite<ROUNDS, V> ph;
+                ph.prepare(site, a.gw0 + w, a.sweep, a.pk);
+                constexpr bool kDefer = ISING_ROWS_DEFER_RARE != 0;
+                uint32_t left[V], lm1[V], lm2[V];
+                uint32_t any_left = 0;
+                uint32_t nb0[V], nb1[V], nb2[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    uint32_t r[8];
+                    ph.finish(v, 0, a.pk, r);
+                    ph.finish(v, 1, a.pk, r + 4);
+                    uint32_t av[2 * DIM];
+#pragma unroll
+                    for (int k2 = 0; k2 < 2 * DIM; ++k2) av[k2] = ~(s[v] ^ n[k2][v] ^ m[k2]);
+                    uint32_t b0, b1, b2;
+                    count_sat<DIM>(av, b0, b1, b2);
+                    // 3D: n_sat 4, 5, 6 -> dE = 4, 8, 12 |J|;  2D: n_sat 3, 4 -> dE = 4, 8 |J|
+                    const uint32_t up = DIM == 3 ? b2 : (b2 | (b1 & b0));
+                    const uint32_t m1 = DIM == 3 ? (b2 & b0) : b2;
+                    const uint32_t m2 = DIM == 3 ? (b2 & b1) : 0u;
+                    left[v] = 0;
+                    const uint32_t flip = msc_flip_mask_mux<DIM == 3 ? 3 : 2, K, ROUNDS>(
+                        up, m1, m2, a.mx, r, site, a.gw0 + w + v, a.sweep, a.pk, kDefer ? &left[v] : nullptr);
+                    s[v] ^= flip;
+                    if constexpr (kDefer) {
+                        lm1[v] = m1;
+                        lm2[v] = m2;
+                        any_left |= left[v];
+                        nb0[v] = b0; nb1[v] = b1; nb2[v] = b2;
+                    }
+                    if constexpr (ACC && !kDefer) {
+                        // a flipped spin turns its n_sat satisfied bonds into 2*DIM - n_sat
+                        uint32_t c1, c2;
+                        if (DIM == 3) {
+                            c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
+                            c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
+                        } else {
+                            c1 = (flip & (b1 ^ b0)) | (~flip & b1);
+                            c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
+                        }
+                        vc[v].add3(b0, c1, c2);
+                    }
+                }
+                if constexpr (kDefer) {
+                    uint32_t extra[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) extra[v] = 0;
+                    if (any_left) {  // a word with three or more ties (rare)
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            if (left[v])
+                                extra[v] = msc_resolve_rest<DIM == 3 ? 3 : 2, K, ROUNDS>(
+                                    left[v], lm1[v], lm2[v], a.mx.low[0], a.mx.low[1], a.mx.low[2], site,
+                                    a.gw0 + w + v, a.sweep, a.pk);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) s[v] ^= extra[v];
+                    }
+                    if constexpr (ACC) {
+                        // s0 = spins before the update: flip = s ^ s0 is not kept, recompute from
+                        // the stored word: flipped bits = bits where the final s differs
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            const uint32_t b0 = nb0[v], b1 = nb1[v], b2 = nb2[v];
+                            const uint32_t flip = s[v] ^ s0[v];
+                            uint32_t c1, c2;
+                            if (DIM == 3) {
+                                c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
+                                c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
+                            } else {
+                                c1 = (flip & (b1 ^ b0)) | (~flip & b1);
+                                c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
+                            }
+                            vc[v].add3(b0, c1, c2);
+                        }
+                    }
+                }
+                VecT o;
+#pragma unroll
+                for (int v = 0; v < V; ++v) reinterpret_cast<uint32_t*>(&o)[v] = s[v];
+                ownv[e_own] = o;
+            }
+            if constexpr (ACC) {
+                if (++pending == SW_MAX_ITEMS) {  // counters full: reduce and start over
+                    block_reduce_vcount<SW_NP, V>(vc, sm, a.nsat, (cur_tile / a.xtiles) * wx * V, W);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) vc[v].clear();
+                    pending = 0;
+                }
+            }
+        }
+    }
+    if constexpr (ACC) {
+        if (pending) block_reduce_vcount<SW_NP, V>(vc, sm, a.nsat, (cur_tile / a.xtiles) * wx * V, W);
+    }
+}
+
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
+__global__ void __launch_bounds__(256, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB) k_sweep_rows(const __grid_constant__ RowsArgs a) {
+    extern __shared__ uint32_t sm[];
+    sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>(a, sm);
+}
+
+}  // namespace ising

@@ -83,7 +83,7 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
                     0u, 0u);
             } else {
                 if (block.y < (unsigned)V) block.y = V;
-                uint32_t g = 148u * ISING_ACC_MIN_BLOCKS;
+                uint32_t g = device_sms() * ISING_ACC_MIN_BLOCKS;
                 if (g > L.rows) g = L.rows;
                 const int nthreads = block.x * block.y;
                 const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
@@ -104,7 +104,7 @@ static void sweep_launch_phase(const SweepArgs& a, cudaStream_t st, dim3 grid, d
     // fused accumulation: persistent blocks so that the per-block reduction is amortised, but
     // never more sites per thread than the SW_NP-plane counters can hold
     if (block.y < (unsigned)V) block.y = V;
-    uint32_t g = 148u * ISING_ACC_MIN_BLOCKS;
+    uint32_t g = device_sms() * ISING_ACC_MIN_BLOCKS;
     if (g > L.rows) g = L.rows;
     const int nthreads = block.x * block.y;
     const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
@@ -148,7 +148,7 @@ static void stencil_block_shape(const Layout& L, uint32_t V, dim3* grid, dim3* b
     if (wx * by < 32) by = 32 / wx;
     *block = dim3(wx, by, 1);
     uint32_t g = L.rows;
-    if (persistent && g > 148u * 8u) g = 148u * 8u;
+    if (persistent && g > device_sms() * 8u) g = device_sms() * 8u;
     *grid = dim3(g, 1, 1);
 }
 
@@ -168,6 +168,13 @@ static int sweep_dispatch_kind(const SweepArgs& a, cudaStream_t st) {
 
 int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st) {
     if (a.tplane && a.planes != 6) return -1;  // per-replica tables are built for K = 6
+    static const bool v1 = getenv("ISING_SWEEP_V1") != nullptr;  // A/B knob: round-1 launch shape
+    if (!v1 && !a.tplane && a.planes == 6) {
+        int rc = 0;
+        if (a.lay.kind == ISING_KIND_STENCIL3D) rc = launch_sweep_rows_3d(a, st);
+        else if (a.lay.kind == ISING_KIND_STENCIL2D) rc = launch_sweep_rows_2d(a, st);
+        if (rc != 0) return rc;
+    }
     // widest vector the replica-word count allows (rows then stay 16-byte aligned)
     if (ISING_SWEEP_MAXV >= 4 && a.lay.W % 4 == 0) return sweep_dispatch_kind<4>(a, st);
     if (ISING_SWEEP_MAXV >= 2 && a.lay.W % 2 == 0) return sweep_dispatch_kind<2>(a, st);
@@ -324,7 +331,7 @@ static int nsat_dispatch(const uint32_t* spins, const uint32_t* jmask, const Lay
     dim3 grid, block;
     stencil_block_shape(lay, V, &grid, &block, false);
     if (block.y < (unsigned)V) block.y = V;  // the reduction needs >= one thread per word column
-    uint64_t g = 148ull * 2;  // persistent; counters are reduced every NS_MAX_ITEMS sites
+    uint64_t g = (uint64_t)device_sms() * 2;  // persistent; counters are reduced every NS_MAX_ITEMS sites
     if (g > lay.rows) g = lay.rows;
     grid = dim3((unsigned)g, 1, 1);
     const int nthreads = block.x * block.y;

@@ -321,6 +321,11 @@ def test_classic_ising_stateful_api(pkg, oracle, native):
     ci.add_graph(init)
     s2 = ci.get_states()
     assert s2.shape == (6, 64) and (s2[:5] == st[:, 1]).all() and (s2[5] == init).all()
+    # ... and keeps their random streams running: run -> add_graph -> run equals the
+    # uninterrupted run for the old experiments (no replay of the draws of sweeps 0..T-1)
+    ci.run_monte_carlo(0.4, 4)
+    sim.sweeps([0.4] * 4)
+    assert (ci.get_states()[:5] == sim.states()).all()
     with pytest.raises(NotImplementedError):
         ci.run_monte_carlo(0.4, 1, 5)
     cb = pkg.ClassicIsing([((0, 1), 1.0), ((1, 2), 1.0)], 0.7, 2000, 3)   # longitudinal field
