@@ -5,11 +5,12 @@ attempts / s, device-timed, max over ranks, + fraction of the HBM roofline).
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2]
 
 Workload c3 (default; the configuration BASELINE.json's target is quoted on): 3D Edwards-
-Anderson +-J spin glass, L = 64 periodic, 1024 replicas per GPU, one step =
+Anderson +-J spin glass, L = 64 periodic, 1024 replicas IN TOTAL, one step =
 run_monte_carlo_annealing_and_get_energies with a (0, 0.1) -> (T, 1.2) schedule of T sweeps and
 the energy of every replica after every sweep.  Replicas are the sharding unit (the reference's
-rayon axis, lattice.rs:192-197): every rank simulates its own 1024 replicas, no data-path
-collective, scaling = weak.
+rayon axis, lattice.rs:192-197): with N ranks every rank simulates 1024 / N of them ("sharded
+across 8 B200" in BASELINE.json's config 3), no data-path collective, scaling = strong.  The
+1024-replicas-per-GPU figure (weak scaling) is reported beside it as `weak_value`.
 
 `value`  : all ranks' flip attempts / device time of K steps, state resident in HBM.
 `e2e`    : the same metric through Lattice.run_monte_carlo_annealing_and_get_energies with host
@@ -36,7 +37,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 WORKLOADS = {
     # name: (dims, pmj, j0, replicas per GPU, sweeps per step, schedule ends)
     "c3": dict(dims=(64, 64, 64), pmj=True, j0=1.0, replicas=1024, sweeps=1000, beta=(0.1, 1.2),
-               desc="3D EA +-J spin glass L=64 periodic, 1024 replicas/GPU, "
+               desc="3D EA +-J spin glass L=64 periodic, 1024 replicas in total (sharded over the ranks), "
                     "run_monte_carlo_annealing_and_get_energies, 1000 sweeps/step"),
     "c2": dict(dims=(4096, 4096), pmj=False, j0=-1.0, replicas=1024, sweeps=20, beta=(0.43, 0.43),
                desc="2D square ferromagnet 4096x4096 checkerboard, 1024 experiments/GPU, "
@@ -329,6 +330,21 @@ def run_single(args, w, world, rank, local):
         dist.destroy_process_group()
 
 
+def instruction_bound(kind):
+    """Model time of one site group (4 replica words) of the sweep kernel from its SASS instruction
+    mix (profiles/r02_sass_mix.json) and the pipe rates measured by profiles/microbench/pipe_bench.cu
+    (profiles/r02_pipe_bench.json): cycles = 2.07 per ALU-pipe instruction + ~2.4 per 32x32->64
+    multiply that does not overlap + ~0.85 per IMAD + 1 per other issue slot."""
+    try:
+        mix = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_mix.json")))[kind]
+        rates = json.load(open(os.path.join(ROOT, "profiles", "r02_pipe_bench.json")))["model"]
+    except Exception:
+        return None
+    cyc = (mix["alu"] * rates["alu"] + mix["mul_wide_or_hi"] * rates["mul_wide_or_hi"] +
+           mix["imad"] * rates["imad"] + mix["other"] * rates["other"])
+    return {"cycles_per_site_group": cyc, "mix": mix, "rates": rates}
+
+
 def run_b200(args, w, world, rank, local):
     import torch
 
@@ -363,88 +379,124 @@ def run_b200(args, w, world, rank, local):
         return float(t.item())
 
     ctx = nat.Context.get(local)
-    E = w["replicas"]
+    E_total = w["replicas"]
+    if E_total % (32 * world):
+        raise SystemExit(f"{E_total} replicas do not split into whole 32-replica words over {world} ranks")
+    E = E_total // world                      # strong scaling: the replicas are sharded over the ranks
     n = int(np.prod(w["dims"]))
     betas = betas_for(w)
     graph = nat.Graph.torus(ctx, w["dims"], j0=w["j0"], pmj=w["pmj"], j_seed=2024)
     sim = nat.Sim(graph, E, seed=31337, replica_offset=rank * E, planes=args.planes, rounds=args.rounds)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    # -------- value: device-resident, sweeps + per-sweep energies, CUDA events in the library
-    def step_resident():
-        sim.sweeps(betas, per_sweep_energies=True)
+    def timed(the_sim, per_sweep_energies, steps):
+        """steps x (L2 flush, all sweeps) -> stats of the timed region (device time from the library's
+        CUDA events on its stream, max over ranks taken by the caller)"""
+        the_sim.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            the_sim.sweeps(betas, per_sweep_energies=per_sweep_energies)
+        barrier()
+        return the_sim.stats(), time.perf_counter() - t0
 
+    # -------- value: device-resident, sweeps + per-sweep energies
     for _ in range(args.warmup):
         flush.zero_()
-        step_resident()
+        sim.sweeps(betas, per_sweep_energies=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    sim.reset_stats()
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        step_resident()
-    barrier()
-    wall = time.perf_counter() - wall0
-    st = sim.stats()
+    st, wall = timed(sim, True, args.steps)
     dev_ms = max_over_ranks(st["sweep_device_ms"])
     launches = st["kernel_launches"]
-    flips_rank = float(st["flip_attempts"])
-    flips_all = sum_over_ranks(flips_rank)
+    flips_all = sum_over_ranks(float(st["flip_attempts"]))
     value = flips_all / (dev_ms * 1e-3)
 
-    # -------- roofline: the sweep kernel alone (same state, same betas, no energy kernel)
-    sim.reset_stats()
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        sim.sweeps(betas)
-    barrier()
-    st2 = sim.stats()
+    # -------- the plain colour phase alone (same state, same betas, no energy accumulation)
+    st2, _ = timed(sim, False, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    k_ms = st2["sweep_kernel_ms"] / max(1, st2["sweep_kernel_launches"])
+    plain_ms = max_over_ranks(st2["sweep_kernel_ms"] / max(1, st2["sweep_kernel_launches"]))
+    sweep_only_value = sum_over_ranks(float(st2["flip_attempts"])) / (max_over_ranks(st2["sweep_device_ms"]) * 1e-3)
+    # the accumulating colour phase (second launch of every sweep of the `value` region): what is
+    # left of a sweep after one plain phase (this charges it the per-chunk memset / conversion too)
+    per_sweep_ms = dev_ms / (args.steps * len(betas))
+    acc_ms = max(per_sweep_ms - plain_ms, 1e-9)
     bpf, _ = algorithmic_bytes_per_flip(w)
-    flips_per_launch = E * n / 2.0  # one colour class per launch
-    achieved = bpf * flips_per_launch / (k_ms * 1e-3) / 1e9
+    flips_per_launch = E * n / 2.0  # one colour class per launch, per rank
     peak, peak_src = peaks()
-    traffic = None   # dram__bytes_read + write per launch of this kernel, from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
+    traffic = None   # dram__bytes_read + write per launch, from the committed ncu capture (1-GPU shape)
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and world == 1:
         tj = json.load(open(tpath)).get(args.workload)
         if tj:
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-    sweep_only_value = sum_over_ranks(float(st2["flip_attempts"])) / (max_over_ranks(st2["sweep_device_ms"]) * 1e-3)
 
-    # -------- the same sweep-only region with Philox4x32-7 (Crush-resistant minimum of the
-    # Random123 paper; the library default stays at 10 rounds)
-    philox7_value = None
-    if not args.rounds:
-        sim7 = nat.Sim(graph, E, seed=31337, replica_offset=rank * E, planes=args.planes, rounds=7)
-        sim7.sweeps(betas[: max(1, len(betas) // 10)])
-        sim7.reset_stats()
-        barrier()
-        sim7.sweeps(betas)
-        barrier()
-        s7 = sim7.stats()
-        philox7_value = sum_over_ranks(float(s7["flip_attempts"])) / (max_over_ranks(s7["sweep_device_ms"]) * 1e-3)
-        sim7.close()
+    def roof(ms, kernel, kind):
+        ach = bpf * flips_per_launch / (ms * 1e-3) / 1e9
+        d = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "traffic": traffic, "peak_source": peak_src, "kernel": kernel, "kernel_ms": ms,
+             "algorithmic_bytes_per_flip": bpf, "algorithmic_bytes_per_launch": int(bpf * flips_per_launch)}
+        ib = instruction_bound(kind) if world == 1 and args.workload == "c3" and not args.rounds else None
+        if ib and clocks and clocks.get("sm_mhz"):
+            site_groups = flips_per_launch / 128.0           # 4 words x 32 replicas per thread item
+            smsp = 4 * torch.cuda.get_device_properties(local).multi_processor_count
+            model_ms = ib["cycles_per_site_group"] * (site_groups / 32.0) / smsp / (clocks["sm_mhz"] * 1e3)
+            d["instruction_bound"] = {"model_ms": model_ms, "frac_of_instruction_bound": model_ms / ms,
+                                      "cycles_per_site_group": ib["cycles_per_site_group"], "mix": ib["mix"],
+                                      "note": "kernel is bound by the integer pipes, not by HBM: see DESIGN.md 5 and "
+                                              "profiles/microbench/pipe_bench.cu"}
+        return d
 
-    # -------- e2e: the public API with host buffers
+    roofline = roof(acc_ms, "k_sweep_rows<ACC=1> (second colour phase + fused per-sweep energies): the kernel "
+                            "that dominates `value`", "acc")
+    roofline["plain_phase"] = roof(plain_ms, "k_sweep_rows<ACC=0> (first colour phase)", "plain")
+    roofline["whole_step_frac"] = bpf * (flips_all / world) / (dev_ms * 1e-3) / 1e9 / peak
+
+    # -------- the same sweep-only region with Philox4x32-10 (the library default is 7 rounds)
+    philox10_value = None
+    if not args.rounds and world == 1:
+        sim10 = nat.Sim(graph, E, seed=31337, replica_offset=rank * E, planes=args.planes, rounds=10)
+        sim10.sweeps(betas[: max(1, len(betas) // 10)])
+        sim10.reset_stats()
+        barrier()
+        sim10.sweeps(betas)
+        barrier()
+        s10 = sim10.stats()
+        philox10_value = float(s10["flip_attempts"]) / (s10["sweep_device_ms"] * 1e-3)
+        sim10.close()
+
+    # -------- weak scaling beside it: 1024 replicas on every GPU (what round 1 reported as `value`)
+    weak_value = None
+    if world > 1:
+        simw = nat.Sim(graph, E_total, seed=31337, replica_offset=rank * E_total, planes=args.planes,
+                       rounds=args.rounds)
+        simw.sweeps(betas[: max(1, len(betas) // 10)], per_sweep_energies=True)
+        simw.reset_stats()
+        barrier()
+        simw.sweeps(betas, per_sweep_energies=True)
+        barrier()
+        sw = simw.stats()
+        weak_value = sum_over_ranks(float(sw["flip_attempts"])) / (max_over_ranks(sw["sweep_device_ms"]) * 1e-3)
+        simw.close()
+
+    # -------- e2e: the public API with host buffers; the ranks shard the experiments exactly as
+    # above (Lattice.distributed), every rank reads back its own rows
     if len(w["dims"]) == 3 or args.e2e_full:
-        lat = pkg.Lattice.torus(w["dims"], j=w["j0"], pmj=w["pmj"], j_seed=2024, seed_gen=31337 + rank,
-                                device=local)
+        lat = pkg.Lattice.torus(w["dims"], j=w["j0"], pmj=w["pmj"], j_seed=2024, seed_gen=31337, device=local)
         lat.linear_annealing = True
-        rng = np.random.default_rng(rank)
+        if world > 1:
+            lat.distributed = True
+            lat.gather_results = False
+        rng = np.random.default_rng(0)
         init = rng.integers(0, 2, n).astype(bool)
         stops = [(0, w["beta"][0]), (w["sweeps"], w["beta"][1])]
 
         def step_e2e():
             lat.set_initial_state(init)  # N bools H2D inside the call
-            en, stt = lat.run_monte_carlo_annealing_and_get_energies(stops, w["sweeps"], E)
+            en, stt = lat.run_monte_carlo_annealing_and_get_energies(stops, w["sweeps"], E_total)
             return float(en[0, -1]) + float(stt[0, 0])
 
         for _ in range(min(args.warmup, 2)):
@@ -455,11 +507,12 @@ def run_b200(args, w, world, rank, local):
             step_e2e()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * E * n * w["sweeps"] * args.steps / e2e_s, "unit": "flips/s",
-               "h2d_bytes_per_step": int(n + 16 * len(stops)),
-               "d2h_bytes_per_step": int(E * w["sweeps"] * 8 + E * n),
+        e2e = {"value": E_total * n * w["sweeps"] * args.steps / e2e_s, "unit": "flips/s",
+               "h2d_bytes_per_step": int(world * (n + 16 * len(stops))),
+               "d2h_bytes_per_step": int(E_total * w["sweeps"] * 8 + E_total * n),
                "ms_per_step": 1e3 * e2e_s / args.steps,
-               "api": "Lattice.run_monte_carlo_annealing_and_get_energies (host buffers in/out)"}
+               "api": "Lattice.run_monte_carlo_annealing_and_get_energies (host buffers in/out; "
+                      "experiments sharded over the ranks, bytes summed over the ranks)"}
     else:
         e2e = None
 
@@ -473,24 +526,21 @@ def run_b200(args, w, world, rank, local):
         line = {
             "metric": "spin_flip_attempts_per_sec", "value": value, "unit": "flips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 bit-sliced (1 bit per spin per replica)",
             "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "replicas_total": world * E,
-                       "parallelism": f"replicas x{world} (no collective)",
-                       "l2": "256 MiB flush between steps; within a step the 32 MiB state is L2-resident by design"
-                       if n * E / 8 < 100e6 else "state larger than L2",
-                       "msc_planes": args.planes or 6, "philox_rounds": args.rounds or 10},
+            "config": {"workload": args.workload + ": " + w["desc"], "replicas_total": E_total,
+                       "replicas_per_gpu": E,
+                       "parallelism": f"replicas sharded x{world} (no collective)",
+                       "l2": "256 MiB flush between steps; within a step the %d MiB state is L2-resident by design"
+                             % (n * E // 8 >> 20) if n * E / 8 < 100e6 else "state larger than L2",
+                       "msc_planes": args.planes or 6, "philox_rounds": args.rounds or 7},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "sweep_only_value": sweep_only_value,
-            "sweep_only_value_philox7": philox7_value,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "traffic_note": "ncu --set full capture (profiles/r01_sweep_metrics.md), cold caches; "
-                                         "algorithmic bytes per launch = %d" % int(bpf * flips_per_launch),
-                         "kernel": "k_sweep_stencil (one colour class per launch)",
-                         "kernel_ms": k_ms, "algorithmic_bytes_per_flip": bpf,
-                         "note": "kernel is integer-ALU bound (bit-sliced Metropolis + Philox), see DESIGN.md"},
+            "sweep_only_value_philox10": philox10_value,
+            "weak_value": weak_value,
+            "weak_note": "all ranks' flips/s with 1024 replicas on EVERY GPU (round 1's `value`)" if weak_value else None,
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

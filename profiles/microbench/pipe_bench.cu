@@ -14,7 +14,7 @@
 constexpr int CHAINS = 8;   // independent dependency chains per thread (the sweep has 8 Philox calls in flight)
 
 // One "step" issues NL LOP3, NW IMAD.WIDE and NI IMAD per chain group, interleaved.
-template <int NL, int NW, int NI>
+template <int NL, int NW, int NI, int MODE = 0>
 __global__ void __launch_bounds__(256, 3) k_mix(uint32_t* out, uint32_t seed, int iters) {
     uint32_t a[CHAINS], b[CHAINS], c[CHAINS];
 #pragma unroll
@@ -29,10 +29,18 @@ __global__ void __launch_bounds__(256, 3) k_mix(uint32_t* out, uint32_t seed, in
         for (int j = 0; j < NMAX; ++j) {
 #pragma unroll
             for (int k = 0; k < CHAINS; ++k) {
-                if (j < NW) {   // IMAD.WIDE.U32: 32x32 -> 64, both halves used (a Philox round)
-                    const uint64_t p = (uint64_t)a[k] * 0xD2511F53u;
-                    a[k] = (uint32_t)(p >> 32) ^ b[k];
-                    b[k] = (uint32_t)p;
+                if (j < NW) {   // 32x32 -> 64, both halves used (a Philox round)
+                    if (MODE == 0) {          // IMAD.WIDE.U32
+                        const uint64_t p = (uint64_t)a[k] * 0xD2511F53u;
+                        a[k] = (uint32_t)(p >> 32) ^ b[k];
+                        b[k] = (uint32_t)p;
+                    } else {                  // IMAD.HI.U32 + IMAD (MODE 2: high half only)
+                        uint32_t hi, lo = a[k];
+                        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(a[k]), "r"(0xD2511F53u));
+                        if (MODE == 1) asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(a[k]), "r"(0xD2511F53u));
+                        a[k] = hi ^ b[k];
+                        b[k] = lo;
+                    }
                 }
                 if (j < NL) {   // LOP3 with three register operands (majority)
                     asm volatile("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c[k]) : "r"(c[k]), "r"(a[k]), "r"(b[k]));
@@ -49,30 +57,31 @@ __global__ void __launch_bounds__(256, 3) k_mix(uint32_t* out, uint32_t seed, in
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-template <int NL, int NW, int NI>
+template <int NL, int NW, int NI, int MODE = 0>
 static void run(const char* name, uint32_t* d_out, int sms, double clock_hz) {
     const int iters = 2000, blocks = sms * 3;
-    k_mix<NL, NW, NI><<<blocks, 256>>>(d_out, 1u, 10);
+    k_mix<NL, NW, NI, MODE><<<blocks, 256>>>(d_out, 1u, 10);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
-        k_mix<NL, NW, NI><<<blocks, 256>>>(d_out, 1u, iters);
+        k_mix<NL, NW, NI, MODE><<<blocks, 256>>>(d_out, 1u, iters);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
-    // the xor after IMAD.WIDE is a LOP3 as well
-    const double per_thread = (double)iters * CHAINS * (NL + 2.0 * NW + NI);
+    // per chain and iteration: NL majority LOP3; NW x (multiply [2 instructions when split] + xor);
+    // NI x (IMAD + the OR that makes its multiplier odd)
+    const double per_thread = (double)iters * CHAINS * (NL + (MODE == 1 ? 3.0 : 2.0) * NW + 2.0 * NI);
     const double warp_inst = per_thread * blocks * 256 / 32.0;
     const double cycles = best * 1e-3 * clock_hz;
     printf("{\"mix\": \"%s\", \"lop3\": %d, \"imad_wide\": %d, \"imad\": %d, \"ms\": %.4f, "
            "\"warp_inst_per_clk_per_smsp\": %.4f, \"cycles_per_group\": %.3f}\n",
-           name, NL + NW, NW, NI, best, warp_inst / cycles / (sms * 4.0),
+           name, NL + NW + NI, NW, NI, best, warp_inst / cycles / (sms * 4.0),
            cycles * sms * 4.0 / ((double)iters * CHAINS * blocks * 8.0));
 }
 
@@ -92,6 +101,12 @@ int main() {
     run<2, 2, 0>("lop3 : imad.wide 2:1 (+xor)", d_out, prop.multiProcessorCount, clock_hz);
     run<6, 3, 4>("sweep kernel mix (9 lop3 : 3 imad.wide : 4 imad)", d_out, prop.multiProcessorCount, clock_hz);
     run<6, 3, 0>("round-1 kernel mix (9 lop3 : 3 imad.wide)", d_out, prop.multiProcessorCount, clock_hz);
+    run<0, 4, 0, 2>("imad.hi + its xor", d_out, prop.multiProcessorCount, clock_hz);
+    run<0, 4, 0, 1>("imad.hi + imad.lo + xor", d_out, prop.multiProcessorCount, clock_hz);
+    run<6, 3, 0, 1>("9 lop3 : 3 (imad.hi + imad.lo)", d_out, prop.multiProcessorCount, clock_hz);
+    run<6, 3, 4, 1>("9 lop3 : 3 (imad.hi + imad.lo) : 4 imad", d_out, prop.multiProcessorCount, clock_hz);
+    run<8, 1, 0, 0>("9 lop3 : 1 imad.wide", d_out, prop.multiProcessorCount, clock_hz);
+    run<8, 2, 0, 0>("10 lop3 : 2 imad.wide", d_out, prop.multiProcessorCount, clock_hz);
     cudaFree(d_out);
     return 0;
 }

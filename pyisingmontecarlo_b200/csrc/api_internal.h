@@ -91,7 +91,7 @@ struct ising_sim {
     unsigned long long* d_counts = nullptr;  // per-experiment integer accumulator [W*32]
     size_t spins_bytes = 0, counts_bytes = 0;
     uint64_t sweep_counter = 0;
-    int planes = 6, rounds = 10;
+    int planes = 6, rounds = kDefaultRounds;
     ising_sim_stats stats{};
     bool general = false;          // natural-order layout + colour/degree groups
     bool real = false;             // general layout, float local fields (real J / biases)

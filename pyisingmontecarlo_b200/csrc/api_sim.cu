@@ -355,10 +355,11 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
             rc = 0;
         }
     }
-    // cooperative kernel, measured on B200 (32^2 and 16^3): with fused energies the per-block
-    // reduction in lock-step only pays off for few replica words (6.6 vs 10.2 us/sweep at W = 2,
-    // 18.9 vs 13.6 at W = 32)
-    if (rc == 0 && !s->perbeta && !(hist && s->lay.W > 8))
+    // Above the cluster limit one launch per colour phase wins: with programmatic dependent launch
+    // a phase of 64^3 x 128 replicas takes 5.8 us, the cooperative kernel (two grid barriers per
+    // sweep) 13.6 us.  ISING_COOP=1 keeps the cooperative kernel reachable for A/B runs.
+    static const bool use_coop = getenv("ISING_COOP") != nullptr;
+    if (rc == 0 && use_coop && !s->perbeta && !(hist && s->lay.W > 8))
         rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
                                         (uint32_t)(s->lay.W * 32), ctx->stream);
     if (rc < 0) {

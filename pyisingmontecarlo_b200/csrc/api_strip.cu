@@ -13,7 +13,7 @@ struct ising_strip {
     unsigned long long* d_acc = nullptr;
     double j = -1.0;
     uint64_t seed = 0, sweep = 0, launches = 0;
-    int planes = 6, rounds = 10;
+    int planes = 6, rounds = kDefaultRounds;
     double device_ms = 0.0;
 };
 

@@ -6,6 +6,12 @@
 
 namespace ising {
 
+// Philox4x32 rounds of the production streams: 7 is the Crush-resistant minimum of the Random123
+// paper (Salmon et al., SC'11, table 2) and the default; 10 is the paper's recommended safety
+// margin, selectable per simulation (ising_sim_configure).  The launch-bound fast paths
+// (cooperative kernel, degree-specialised general kernels, row walk) are built for the default.
+constexpr int kDefaultRounds = 7;
+
 // SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device): grids of the
 // persistent / grid-stride kernels are sized in multiples of it, never from a literal.
 unsigned device_sms();

@@ -179,7 +179,7 @@ static void gen_launch(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st
 // degree-specialised kernels only for the default (K, rounds)
 template <int K, int ROUNDS, int V>
 static void gen_launch_degree(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st) {
-    if constexpr (K == 6 && ROUNDS == 10) {
+    if constexpr (K == 6 && ROUNDS == kDefaultRounds) {
         if (g.deg == 3) return gen_launch<K, ROUNDS, 3, V>(a, g, st);
         if (g.deg == 4) return gen_launch<K, ROUNDS, 4, V>(a, g, st);
         if (g.deg == 6) return gen_launch<K, ROUNDS, 6, V>(a, g, st);

@@ -24,11 +24,23 @@
 #ifndef ISING_ROWS_MINB
 #define ISING_ROWS_MINB 3        // resident blocks per SM the plain colour phase is compiled for
 #endif
+#ifndef ISING_ROWS_TMA_MINB
+#define ISING_ROWS_TMA_MINB 4    // ... the TMA-staged plain colour phase (no registers for loads in flight)
+#endif
 #ifndef ISING_ROWS_ACC_MINB
 #define ISING_ROWS_ACC_MINB 2    // ... the accumulating colour phase
 #endif
 #ifndef ISING_ROWS_DEFER_RARE
-#define ISING_ROWS_DEFER_RARE 0  // 1: third-and-later ties of all V words after the word loop
+#define ISING_ROWS_DEFER_RARE 1  // 1: third-and-later ties of all V words after the word loop
+#endif
+#ifndef ISING_ROWS_SPLIT_ACC_DEFAULT
+#define ISING_ROWS_SPLIT_ACC_DEFAULT 0  // 1: per-sweep energies by a count-only pass instead of the fused phase
+#endif
+#ifndef ISING_ROWS_LT_SEL
+#define ISING_ROWS_LT_SEL 0      // 1: tie compare with ISETP + SEL instead of the multiply-add carry
+#endif
+#ifndef ISING_ROWS_MUL_SPLIT
+#define ISING_ROWS_MUL_SPLIT 1   // 1: Philox products as mul.hi + mul.lo instead of one 32x32->64 multiply
 #endif
 
 namespace ising {
@@ -77,6 +89,17 @@ struct RowDesc {
     uint32_t jrow;                           // row * Lxh * 2 (uint4 index of the row's bond masks)
 };
 constexpr int ROWS_DESC_CHUNK = 64;          // RowDesc entries per chunk (2 KiB)
+
+__device__ __forceinline__ void mulhilo(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
+#if ISING_ROWS_MUL_SPLIT
+    hi = __umulhi(m, x);
+    lo = m * x;
+#else
+    const uint64_t p = (uint64_t)m * x;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
 
 // Two Philox4x32 calls (q = 0, 1) for each of V replica words of one site: counter
 // (site, gw0 + v, sweep, q | TAG_ACCEPT << 24).  r[v][4 q + i] = output word i of call q.
@@ -131,12 +154,13 @@ struct PhiloxSite {
         uint32_t c3 = c3q[q];
 #pragma unroll
         for (int r = 3; r < ROUNDS; ++r) {
-            const uint64_t p0 = (uint64_t)M0 * c0;
-            const uint64_t p1 = (uint64_t)M1 * c2;
-            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k[2 * r];
-            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk.k[2 * r + 1];
-            c1 = (uint32_t)p1;
-            c3 = (uint32_t)p0;
+            uint32_t h0, l0, h1, l1;
+            mulhilo(M0, c0, h0, l0);
+            mulhilo(M1, c2, h1, l1);
+            const uint32_t n0 = h1 ^ c1 ^ pk.k[2 * r];
+            const uint32_t n2 = h0 ^ c3 ^ pk.k[2 * r + 1];
+            c1 = l1;
+            c3 = l0;
             c0 = n0;
             c2 = n2;
         }
@@ -146,8 +170,12 @@ struct PhiloxSite {
 
 // all-ones iff r < lo, on the FMA pipe: high word of r * 1 + (2^64 - lo)
 __device__ __forceinline__ uint32_t lt_mask(uint32_t r, uint32_t lo, uint32_t one) {
+#if ISING_ROWS_LT_SEL
+    return r < lo ? 0xFFFFFFFFu : 0u;
+#else
     const uint64_t neg = 0ull - (uint64_t)lo;
     return (uint32_t)(((uint64_t)r * one + neg) >> 32);
+#endif
 }
 
 // Metropolis mask of one word from eight random words r (two Philox calls).
@@ -225,7 +253,98 @@ __device__ __noinline__ uint32_t msc_resolve_rest(uint32_t eq, uint32_t m1, uint
     return flip;
 }
 
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
+// The update of one site for V replica words: two Philox calls per word, bit-sliced count of the
+// satisfied bonds, Metropolis mask, (ACC) accumulation of the post-flip count.
+//   s: the site's words (updated in place);  n[k]: neighbour words;  m[k]: bond masks
+template <int DIM, int K, int ROUNDS, int V, bool ACC>
+__device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n)[2 * DIM][V],
+                                            const uint32_t (&m)[2 * DIM], uint32_t site, uint32_t gw0w,
+                                            uint32_t sweep, const PhiloxKeys& pk, const MscMux& mx,
+                                            VCount<ACC ? SW_NP : 1> (&vc)[V]) {
+    uint32_t s0[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) s0[v] = s[v];
+    PhiloxSite<ROUNDS, V> ph;
+    ph.prepare(site, gw0w, sweep, pk);
+    constexpr bool kDefer = ISING_ROWS_DEFER_RARE != 0;
+    uint32_t left[V], lm1[V], lm2[V];
+    uint32_t any_left = 0;
+    uint32_t nb0[V], nb1[V], nb2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        uint32_t r[8];
+        ph.finish(v, 0, pk, r);
+        ph.finish(v, 1, pk, r + 4);
+        uint32_t av[2 * DIM];
+#pragma unroll
+        for (int k2 = 0; k2 < 2 * DIM; ++k2) av[k2] = ~(s[v] ^ n[k2][v] ^ m[k2]);
+        uint32_t b0, b1, b2;
+        count_sat<DIM>(av, b0, b1, b2);
+        // 3D: n_sat 4, 5, 6 -> dE = 4, 8, 12 |J|;  2D: n_sat 3, 4 -> dE = 4, 8 |J|
+        const uint32_t up = DIM == 3 ? b2 : (b2 | (b1 & b0));
+        const uint32_t m1 = DIM == 3 ? (b2 & b0) : b2;
+        const uint32_t m2 = DIM == 3 ? (b2 & b1) : 0u;
+        left[v] = 0;
+        const uint32_t flip = msc_flip_mask_mux<DIM == 3 ? 3 : 2, K, ROUNDS>(
+            up, m1, m2, mx, r, site, gw0w + v, sweep, pk, kDefer ? &left[v] : nullptr);
+        s[v] ^= flip;
+        if constexpr (kDefer) {
+            lm1[v] = m1;
+            lm2[v] = m2;
+            any_left |= left[v];
+            nb0[v] = b0; nb1[v] = b1; nb2[v] = b2;
+        }
+        if constexpr (ACC && !kDefer) {
+            // a flipped spin turns its n_sat satisfied bonds into 2*DIM - n_sat
+            uint32_t c1, c2;
+            if (DIM == 3) {
+                c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
+                c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
+            } else {
+                c1 = (flip & (b1 ^ b0)) | (~flip & b1);
+                c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
+            }
+            vc[v].add3(b0, c1, c2);
+        }
+    }
+    if constexpr (kDefer) {
+        uint32_t extra[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) extra[v] = 0;
+        if (any_left) {  // a word with three or more ties (rare)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (left[v])
+                    extra[v] = msc_resolve_rest<DIM == 3 ? 3 : 2, K, ROUNDS>(
+                        left[v], lm1[v], lm2[v], mx.low[0], mx.low[1], mx.low[2], site,
+                        gw0w + v, sweep, pk);
+#pragma unroll
+            for (int v = 0; v < V; ++v) s[v] ^= extra[v];
+        }
+        if constexpr (ACC) {
+            // s0 = spins before the update: flip = s ^ s0 is not kept, recompute from
+            // the stored word: flipped bits = bits where the final s differs
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint32_t b0 = nb0[v], b1 = nb1[v], b2 = nb2[v];
+                const uint32_t flip = s[v] ^ s0[v];
+                uint32_t c1, c2;
+                if (DIM == 3) {
+                    c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
+                    c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
+                } else {
+                    c1 = (flip & (b1 ^ b0)) | (~flip & b1);
+                    c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
+                }
+                vc[v].add3(b0, c1, c2);
+            }
+        }
+    }
+}
+
+// COUNT_ONLY (with ACC): no update, nsat[e] += satisfied bonds seen from the sites of this colour
+// (every bond once) - get_energy() of the current configuration with the same row walk.
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT_ONLY = false>
 __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm) {
     typedef typename WordVec<V>::type VecT;
     __shared__ RowDesc s_desc[ROWS_DESC_CHUNK];
@@ -244,6 +363,11 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
     const uint32_t u1 = u0 + a.uq + (b < a.urem ? 1u : 0u);
     const VecT* __restrict__ othv = reinterpret_cast<const VecT*>(a.oth);
     VecT* __restrict__ ownv = reinterpret_cast<VecT*>(a.own);
+    // Programmatic dependent launch: the next colour phase may be scheduled while this one
+    // drains (its blocks start as SMs free up and run their preamble), and this phase must not
+    // touch the spins before the previous one has completed.  No-ops on an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     VCount<ACC ? SW_NP : 1> vc[V];
     if constexpr (ACC) {
@@ -354,90 +478,24 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
 #pragma unroll
                     for (int k2 = 0; k2 < 2 * DIM; ++k2) m[k2] = a.antiferro;
                 }
-                const uint32_t site = db.y + xsite;
-                uint32_t s0[V];
+                if constexpr (COUNT_ONLY) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) s0[v] = s[v];
-                PhiloxSite<ROUNDS, V> ph;
-                ph.prepare(site, a.gw0 + w, a.sweep, a.pk);
-                constexpr bool kDefer = ISING_ROWS_DEFER_RARE != 0;
-                uint32_t left[V], lm1[V], lm2[V];
-                uint32_t any_left = 0;
-                uint32_t nb0[V], nb1[V], nb2[V];
+                    for (int v = 0; v < V; ++v) {
+                        uint32_t av[2 * DIM];
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    uint32_t r[8];
-                    ph.finish(v, 0, a.pk, r);
-                    ph.finish(v, 1, a.pk, r + 4);
-                    uint32_t av[2 * DIM];
-#pragma unroll
-                    for (int k2 = 0; k2 < 2 * DIM; ++k2) av[k2] = ~(s[v] ^ n[k2][v] ^ m[k2]);
-                    uint32_t b0, b1, b2;
-                    count_sat<DIM>(av, b0, b1, b2);
-                    // 3D: n_sat 4, 5, 6 -> dE = 4, 8, 12 |J|;  2D: n_sat 3, 4 -> dE = 4, 8 |J|
-                    const uint32_t up = DIM == 3 ? b2 : (b2 | (b1 & b0));
-                    const uint32_t m1 = DIM == 3 ? (b2 & b0) : b2;
-                    const uint32_t m2 = DIM == 3 ? (b2 & b1) : 0u;
-                    left[v] = 0;
-                    const uint32_t flip = msc_flip_mask_mux<DIM == 3 ? 3 : 2, K, ROUNDS>(
-                        up, m1, m2, a.mx, r, site, a.gw0 + w + v, a.sweep, a.pk, kDefer ? &left[v] : nullptr);
-                    s[v] ^= flip;
-                    if constexpr (kDefer) {
-                        lm1[v] = m1;
-                        lm2[v] = m2;
-                        any_left |= left[v];
-                        nb0[v] = b0; nb1[v] = b1; nb2[v] = b2;
+                        for (int k2 = 0; k2 < 2 * DIM; ++k2) av[k2] = ~(s[v] ^ n[k2][v] ^ m[k2]);
+                        uint32_t b0, b1, b2;
+                        count_sat<DIM>(av, b0, b1, b2);
+                        vc[v].add3(b0, b1, b2);
                     }
-                    if constexpr (ACC && !kDefer) {
-                        // a flipped spin turns its n_sat satisfied bonds into 2*DIM - n_sat
-                        uint32_t c1, c2;
-                        if (DIM == 3) {
-                            c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
-                            c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
-                        } else {
-                            c1 = (flip & (b1 ^ b0)) | (~flip & b1);
-                            c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
-                        }
-                        vc[v].add3(b0, c1, c2);
-                    }
+                } else {
+                    const uint32_t site = db.y + xsite;
+                    update_site<DIM, K, ROUNDS, V, ACC>(s, n, m, site, a.gw0 + w, a.sweep, a.pk, a.mx, vc);
+                    VecT o;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) reinterpret_cast<uint32_t*>(&o)[v] = s[v];
+                    ownv[e_own] = o;
                 }
-                if constexpr (kDefer) {
-                    uint32_t extra[V];
-#pragma unroll
-                    for (int v = 0; v < V; ++v) extra[v] = 0;
-                    if (any_left) {  // a word with three or more ties (rare)
-#pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            if (left[v])
-                                extra[v] = msc_resolve_rest<DIM == 3 ? 3 : 2, K, ROUNDS>(
-                                    left[v], lm1[v], lm2[v], a.mx.low[0], a.mx.low[1], a.mx.low[2], site,
-                                    a.gw0 + w + v, a.sweep, a.pk);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) s[v] ^= extra[v];
-                    }
-                    if constexpr (ACC) {
-                        // s0 = spins before the update: flip = s ^ s0 is not kept, recompute from
-                        // the stored word: flipped bits = bits where the final s differs
-#pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            const uint32_t b0 = nb0[v], b1 = nb1[v], b2 = nb2[v];
-                            const uint32_t flip = s[v] ^ s0[v];
-                            uint32_t c1, c2;
-                            if (DIM == 3) {
-                                c1 = (flip & ~(b1 ^ b0)) | (~flip & b1);
-                                c2 = (flip & ~b2 & ~(b1 & b0)) | (~flip & b2);
-                            } else {
-                                c1 = (flip & (b1 ^ b0)) | (~flip & b1);
-                                c2 = (flip & ~(b2 | b1 | b0)) | (~flip & b2);
-                            }
-                            vc[v].add3(b0, c1, c2);
-                        }
-                    }
-                }
-                VecT o;
-#pragma unroll
-                for (int v = 0; v < V; ++v) reinterpret_cast<uint32_t*>(&o)[v] = s[v];
-                ownv[e_own] = o;
             }
             if constexpr (ACC) {
                 if (++pending == SW_MAX_ITEMS) {  // counters full: reduce and start over
@@ -458,6 +516,220 @@ template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
 __global__ void __launch_bounds__(256, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB) k_sweep_rows(const __grid_constant__ RowsArgs a) {
     extern __shared__ uint32_t sm[];
     sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>(a, sm);
+}
+
+template <int DIM, bool PMJ, int V, bool MULTIROW>
+__global__ void __launch_bounds__(256, 3) k_nsat_rows(const __grid_constant__ RowsArgs a) {
+    extern __shared__ uint32_t sm[];
+    sweep_rows_phase<DIM, PMJ, 6, 7, V, true, MULTIROW, true>(a, sm);
+}
+
+// ------------------------------------------------------------------------------------------
+// The same colour phase with the neighbour rows staged in shared memory by the TMA unit
+// (cp.async.bulk global -> shared, completion on an mbarrier): whole-row units only (one tile
+// covers the row: Lxh * W / V <= threads per block / rows per unit), W % 4 == 0.
+//
+// A unit = R consecutive rows y0 .. y0+R-1 of plane z.  One stage of the ring holds
+//   OWN  R rows of the colour being updated
+//   OTH  R + 2 rows of the other colour: y0-1 (periodic), y0 .. y0+R-1, y0+R (periodic)
+//   ZM, ZP  R rows of planes z-1, z+1 (3D)
+//   JM   R rows of bond masks (+-J)
+// filled by seven bulk copies of >= 512 B issued by thread 0, two units ahead of their use, so a
+// warp never waits for global memory and needs no registers for in-flight loads nor 64-bit
+// addresses: a thread's shared-memory offsets are constants of the launch.  Consumers release a
+// stage by one mbarrier arrive per warp; only thread 0 waits for that before it refills the stage.
+// ------------------------------------------------------------------------------------------
+struct RowsTmaArgs {
+    RowsArgs r;
+    uint32_t row_bytes;     // Lxh * W * 4
+    uint32_t jrow_bytes;    // Lxh * 32 (0 without bond masks)
+    uint32_t stage_bytes;   // one stage of the ring (multiple of 128)
+    uint32_t off_oth, off_zm, off_zp, off_jm;   // byte offsets inside a stage (OWN at 0)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1D bulk copy global -> shared::cta of `bytes` (multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct RowsStageMeta {   // written by the producer thread before it arms the stage's barrier
+    uint32_t row0;       // z * Ly + y0
+    uint32_t par0;       // (y0 + z + colour) & 1
+    uint32_t pad[2];
+};
+
+template <int DIM, bool PMJ, int K, int ROUNDS, bool ACC>
+__device__ __forceinline__ void sweep_rows_tma_phase(const RowsTmaArgs& ta, unsigned char* smem) {
+    constexpr int V = 4;
+    constexpr int NSTAGE = 2;
+    const RowsArgs& a = ta.r;
+    __shared__ __align__(8) unsigned long long s_full[NSTAGE], s_empty[NSTAGE];
+    __shared__ RowsStageMeta s_meta[NSTAGE];
+    const uint32_t Lxh = a.Lxh, W = a.W, Ly = a.Ly, Lz = a.Lz;
+    const uint32_t wx = blockDim.x;
+    const uint32_t nthreads = blockDim.x * blockDim.y;
+    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t bxh = 1u << a.bxh_log;
+    const uint32_t xh = threadIdx.y & (bxh - 1u);
+    const uint32_t rsub = threadIdx.y >> a.bxh_log;
+    const uint32_t R = 1u << a.nrs_log;
+    const uint32_t b = blockIdx.x;
+    const uint32_t u0 = b * a.uq + (b < a.urem ? b : a.urem);
+    const uint32_t nsteps = a.uq + (b < a.urem ? 1u : 0u);
+    const uint32_t w = threadIdx.x * V;
+    const bool col_ok = w < W && xh < Lxh;
+    // shared-memory byte offsets of this thread's words inside a stage
+    const uint32_t o_site = ((rsub * Lxh + xh) * W + w) * 4u;
+    const uint32_t o_xp = (((rsub + 1u) * Lxh + (xh + 1 == Lxh ? 0u : xh + 1)) * W + w) * 4u;
+    const uint32_t o_xm = (((rsub + 1u) * Lxh + (xh == 0 ? Lxh - 1 : xh - 1)) * W + w) * 4u;
+    const uint32_t o_jm = (rsub * Lxh + xh) * 32u;
+    const uint32_t rowlenV = Lxh * (W / V);
+    const uint32_t toffV = xh * (W / V) + threadIdx.x;
+    uint4* __restrict__ ownv = reinterpret_cast<uint4*>(a.own);
+    const uint32_t smem_base = smem_u32(smem);
+
+    // producer (thread 0): fill stage `st` with the rows of unit u0 + k
+    auto produce = [&](uint32_t k, uint32_t st) {
+        const uint32_t u = u0 + k;
+        const uint32_t yg = u % a.ygroups, z = u / a.ygroups;
+        const uint32_t y0 = yg << a.nrs_log;
+        const uint32_t ym = y0 == 0 ? Ly - 1 : y0 - 1, yp = y0 + R == Ly ? 0u : y0 + R;
+        const uint32_t zm = z == 0 ? Lz - 1 : z - 1, zp = z + 1 == Lz ? 0u : z + 1;
+        const uint32_t row0 = z * Ly + y0;
+        s_meta[st].row0 = row0;
+        s_meta[st].par0 = (y0 + z + a.c) & 1u;
+        const uint32_t bar = smem_u32(&s_full[st]);
+        const uint32_t dst = smem_base + st * ta.stage_bytes;
+        const uint32_t rb = ta.row_bytes;
+        const unsigned char* own = reinterpret_cast<const unsigned char*>(a.own);
+        const unsigned char* oth = reinterpret_cast<const unsigned char*>(a.oth);
+        uint32_t total = (2u * R + 2u) * rb;
+        if (DIM == 3) total += 2u * R * rb;
+        if (PMJ) total += R * ta.jrow_bytes;
+        mbar_expect_tx(bar, total);
+        tma_load_1d(dst, own + (size_t)row0 * rb, R * rb, bar);
+        tma_load_1d(dst + ta.off_oth, oth + (size_t)(z * Ly + ym) * rb, rb, bar);
+        tma_load_1d(dst + ta.off_oth + rb, oth + (size_t)row0 * rb, R * rb, bar);
+        tma_load_1d(dst + ta.off_oth + (R + 1u) * rb, oth + (size_t)(z * Ly + yp) * rb, rb, bar);
+        if (DIM == 3) {
+            tma_load_1d(dst + ta.off_zm, oth + (size_t)(zm * Ly + y0) * rb, R * rb, bar);
+            tma_load_1d(dst + ta.off_zp, oth + (size_t)(zp * Ly + y0) * rb, R * rb, bar);
+        }
+        if (PMJ)
+            tma_load_1d(dst + ta.off_jm, reinterpret_cast<const unsigned char*>(a.jm8) + (size_t)row0 * ta.jrow_bytes,
+                        R * ta.jrow_bytes, bar);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < NSTAGE; ++st) {
+            mbar_init(smem_u32(&s_full[st]), 1u);
+            mbar_init(smem_u32(&s_empty[st]), nthreads / 32u);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
+        for (uint32_t k = 0; k < NSTAGE && k < nsteps; ++k) produce(k, k);
+    }
+
+    VCount<ACC ? SW_NP : 1> vc[V];
+    if constexpr (ACC) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) vc[v].clear();
+    }
+    int pending = 0;
+    uint32_t* red = reinterpret_cast<uint32_t*>(smem + NSTAGE * ta.stage_bytes);  // ACC: block reduction area
+
+    for (uint32_t k = 0; k < nsteps; ++k) {
+        const uint32_t st = k & (NSTAGE - 1), ph = (k / NSTAGE) & 1u;
+        mbar_wait(smem_u32(&s_full[st]), ph);
+        const unsigned char* sb = smem + st * ta.stage_bytes;
+        if (col_ok) {
+            const uint32_t row = s_meta[st].row0 + rsub;
+            const uint32_t p = (s_meta[st].par0 ^ rsub) & 1u;
+            uint32_t s[V], n[2 * DIM][V];
+            auto ld = [&](uint32_t off, uint32_t (&out)[V]) {
+                const uint4 t = *reinterpret_cast<const uint4*>(sb + off);
+                out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+            };
+            ld(o_site, s);
+            ld(ta.off_oth + ta.row_bytes + o_site, n[0]);
+            ld(ta.off_oth + (p ? o_xp : o_xm), n[1]);
+            ld(ta.off_oth + o_site, n[2]);
+            ld(ta.off_oth + 2u * ta.row_bytes + o_site, n[3]);
+            if (DIM == 3) {
+                ld(ta.off_zm + o_site, n[4]);
+                ld(ta.off_zp + o_site, n[5]);
+            }
+            uint32_t m[2 * DIM];
+            if (PMJ) {
+                const uint4 j0 = *reinterpret_cast<const uint4*>(sb + ta.off_jm + o_jm);
+                m[0] = j0.x; m[1] = j0.y; m[2] = j0.z; m[3] = j0.w;
+                if (DIM == 3) {
+                    const uint2 j1 = *reinterpret_cast<const uint2*>(sb + ta.off_jm + o_jm + 16u);
+                    m[4] = j1.x; m[5] = j1.y;
+                }
+            } else {
+#pragma unroll
+                for (int k2 = 0; k2 < 2 * DIM; ++k2) m[k2] = a.antiferro;
+            }
+            const uint32_t site = row * a.Lx + 2u * xh + p;
+            update_site<DIM, K, ROUNDS, V, ACC>(s, n, m, site, a.gw0 + w, a.sweep, a.pk, a.mx, vc);
+            ownv[row * rowlenV + toffV] = make_uint4(s[0], s[1], s[2], s[3]);
+        }
+        // this warp is done with the stage
+        __syncwarp();
+        if ((tid & 31u) == 0) mbar_arrive(smem_u32(&s_empty[st]));
+        if (tid == 0 && k + NSTAGE < nsteps) {
+            mbar_wait(smem_u32(&s_empty[st]), ph);   // every warp has read step k's rows
+            produce(k + NSTAGE, st);
+        }
+        if constexpr (ACC) {
+            if (++pending == SW_MAX_ITEMS) {
+                block_reduce_vcount<SW_NP, V>(vc, red, a.nsat, 0u, W);
+#pragma unroll
+                for (int v = 0; v < V; ++v) vc[v].clear();
+                pending = 0;
+            }
+        }
+    }
+    if constexpr (ACC) {
+        if (pending) block_reduce_vcount<SW_NP, V>(vc, red, a.nsat, 0u, W);
+    }
+}
+
+template <int DIM, bool PMJ, int K, int ROUNDS, bool ACC>
+__global__ void __launch_bounds__(256, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_TMA_MINB)
+k_sweep_rows_tma(const __grid_constant__ RowsTmaArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    sweep_rows_tma_phase<DIM, PMJ, K, ROUNDS, ACC>(ta, smem_raw);
 }
 
 }  // namespace ising

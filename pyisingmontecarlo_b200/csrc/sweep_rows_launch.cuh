@@ -6,10 +6,73 @@
 
 namespace ising {
 
-// ---- persistent row walk (sweep_rows.cuh): the default for lattices that fill the GPU ----------
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
-static int rows_launch(RowsArgs& ra, dim3 block, int sms, cudaStream_t st) {
-    auto kern = k_sweep_rows<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>;
+// Launch with programmatic stream serialisation: consecutive colour phases overlap launch latency
+// and preamble with the tail of the previous phase (the kernels order themselves with
+// griddepcontrol.wait).  Measured on BASELINE config 3: 61.8 -> 59.3 us per sweep at 1024
+// replicas, 16.4 -> 11.5 us at 128 replicas per GPU (the 8-GPU split).  ISING_NO_PDL=1 launches
+// the ordinary way (A/B knob).
+template <typename Kern, typename Args>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Args& args) {
+    static const bool no_pdl = getenv("ISING_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+static uint32_t log2_exact(uint32_t v) {
+    uint32_t lg = 0;
+    while ((1u << lg) < v) ++lg;
+    return lg;
+}
+
+// Thread decomposition of a colour phase: block = (wx word groups) x (bxh half-row positions x nrs
+// rows); unit = nrs consecutive rows of one z plane x one (xh, word) tile.
+struct RowsShape {
+    uint32_t wx, bxh, nrs, xtiles, wtiles;
+    uint64_t units;
+};
+
+static bool rows_shape(const Layout& L, uint32_t V, RowsShape* out) {
+    const uint32_t groups = L.W / V;
+    RowsShape s;
+    s.wx = groups >= 32 ? 32 : pow2_ceil(groups);
+    const uint32_t by = 256 / s.wx;
+    s.bxh = pow2_ceil(L.Lxh);
+    if (s.bxh > by) s.bxh = by;
+    s.nrs = by / s.bxh;
+    while (s.nrs > 1 && L.Ly % s.nrs) s.nrs >>= 1;
+    if ((uint32_t)ROWS_DESC_CHUNK < s.nrs) return false;
+    s.xtiles = (L.Lxh + s.bxh - 1) / s.bxh;
+    s.wtiles = (groups + s.wx - 1) / s.wx;
+    s.units = (uint64_t)L.Lz * (L.Ly / s.nrs) * s.xtiles * s.wtiles;
+    if (s.units > 0x7FFFFFFFull) return false;
+    *out = s;
+    return true;
+}
+
+// one resident wave of blocks; every block gets a balanced, contiguous range of units
+static void rows_partition(RowsArgs& ra, int per_sm, int sms, uint32_t* grid) {
+    uint32_t g = (uint32_t)(per_sm * sms);
+    if (g > ra.units) g = ra.units;
+    ra.uq = ra.units / g;
+    ra.urem = ra.units % g;
+    *grid = g;
+}
+
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT>
+static int rows_launch(RowsArgs& ra, const RowsShape& sh, int sms, cudaStream_t st) {
+    void (*kern)(const RowsArgs);
+    if constexpr (COUNT) kern = k_nsat_rows<DIM, PMJ, V, MULTIROW>;
+    else kern = k_sweep_rows<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>;
+    const dim3 block(sh.wx, sh.bxh * sh.nrs, 1);
     const int nthreads = block.x * block.y;
     const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
     const size_t smem = ACC ? (size_t)planes * nthreads * sizeof(uint32_t) : 0;
@@ -23,71 +86,130 @@ static int rows_launch(RowsArgs& ra, dim3 block, int sms, cudaStream_t st) {
         per_sm = n;
         per_sm_threads = nthreads;
     }
-    // one resident wave; every block gets a balanced, contiguous range of units
-    uint32_t g = (uint32_t)(per_sm * sms);
-    if (g > ra.units) g = ra.units;
-    ra.uq = ra.units / g;
-    ra.urem = ra.units % g;
-    kern<<<dim3(g, 1, 1), block, smem, st>>>(ra);
+    uint32_t g = 0;
+    rows_partition(ra, per_sm, sms, &g);
+    if (launch_pdl(kern, dim3(g, 1, 1), block, smem, st, ra) != cudaSuccess) return -1;
     return 1;
 }
 
-static uint32_t log2_exact(uint32_t v) {
-    uint32_t lg = 0;
-    while ((1u << lg) < v) ++lg;
-    return lg;
+// ---- TMA-staged variant (opt-in, ISING_TMA=1): whole-row units, W % 4 == 0 ---------------------
+template <int DIM, bool PMJ, int K, int ROUNDS, bool ACC>
+static int rows_tma_launch(RowsTmaArgs& ta, dim3 block, size_t smem, int sms, cudaStream_t st) {
+    auto kern = k_sweep_rows_tma<DIM, PMJ, K, ROUNDS, ACC>;
+    const int nthreads = block.x * block.y;
+    static int per_sm = 0, per_sm_threads = 0;
+    static size_t per_sm_smem = 0;
+    if (per_sm == 0 || per_sm_threads != nthreads || per_sm_smem != smem) {
+        int n = 0;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, nthreads, smem) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            return 0;
+        }
+        per_sm = n;
+        per_sm_threads = nthreads;
+        per_sm_smem = smem;
+    }
+    uint32_t g = 0;
+    rows_partition(ta.r, per_sm, sms, &g);
+    if (launch_pdl(kern, dim3(g, 1, 1), block, smem, st, ta) != cudaSuccess) return -1;
+    return 1;
 }
 
+// returns 1 when launched, 0 when the shape does not fit the staged kernel (caller uses the
+// direct-load row walk)
+template <int DIM, bool PMJ, int K, int ROUNDS>
+static int rows_tma_phase(const Layout& L, const RowsArgs& ra, const RowsShape& sh, bool acc, int sms,
+                          cudaStream_t st) {
+    if (L.W % 4 || sh.xtiles != 1 || sh.wtiles != 1) return 0;
+    RowsTmaArgs ta;
+    ta.r = ra;
+    ta.row_bytes = L.Lxh * L.W * 4u;
+    ta.jrow_bytes = PMJ ? L.Lxh * 32u : 0u;
+    auto up128 = [](uint32_t v) { return (v + 127u) & ~127u; };
+    uint32_t off = up128(sh.nrs * ta.row_bytes);
+    ta.off_oth = off;
+    off += up128((sh.nrs + 2u) * ta.row_bytes);
+    ta.off_zm = off;
+    if (DIM == 3) off += up128(sh.nrs * ta.row_bytes);
+    ta.off_zp = off;
+    if (DIM == 3) off += up128(sh.nrs * ta.row_bytes);
+    ta.off_jm = off;
+    if (PMJ) off += up128(sh.nrs * ta.jrow_bytes);
+    ta.stage_bytes = off;
+    const dim3 block(sh.wx, sh.bxh * sh.nrs, 1);
+    const int nthreads = block.x * block.y;
+    const int planes = SW_NP * 4 > NS_NR ? SW_NP * 4 : NS_NR;
+    const size_t smem = 2 * (size_t)ta.stage_bytes + (acc ? (size_t)planes * nthreads * sizeof(uint32_t) : 0);
+    if (smem > 200 * 1024 || nthreads % 32) return 0;
+    return acc ? rows_tma_launch<DIM, PMJ, K, ROUNDS, true>(ta, block, smem, sms, st)
+               : rows_tma_launch<DIM, PMJ, K, ROUNDS, false>(ta, block, smem, sms, st);
+}
+
+// mode: 0 = plain colour phase, 1 = colour phase + accumulation of the post-flip satisfied-bond
+// counts into a.nsat_out, 2 = count only (no update).  Returns launches made, 0 when this
+// configuration is not covered, -1 on error.
 template <int DIM, bool PMJ, int K, int ROUNDS, int V>
-static int rows_phase(const SweepArgs& a, cudaStream_t st, uint32_t c, bool acc) {
+static int rows_phase(const SweepArgs& a, cudaStream_t st, uint32_t c, int mode) {
     const Layout& L = a.lay;
     const size_t csz = (size_t)L.halfN * L.W;
     if (csz / V > 0xFFFFFFFFull || L.nvars > 0xFFFFFFFFull) return 0;  // 32-bit element offsets
+    RowsShape sh;
+    if (!rows_shape(L, V, &sh)) return 0;
+    const bool acc = mode != 0;
+    if (acc && sh.bxh * sh.nrs < (uint32_t)V) return 0;  // the block reduction wants >= V thread rows
     RowsArgs ra;
     ra.own = a.spins + c * csz;
     ra.oth = a.spins + (1 - c) * csz;
     ra.jm8 = PMJ ? reinterpret_cast<const uint4*>(a.jmask8 + (size_t)c * L.halfN * 8) : nullptr;
     ra.Lx = L.Lx; ra.Ly = L.Ly; ra.Lz = L.Lz; ra.Lxh = L.Lxh; ra.W = L.W;
     ra.c = c; ra.sweep = a.sweep; ra.gw0 = a.gw0; ra.antiferro = a.antiferro;
-    // thread decomposition: x = word group, y = (row within the unit, half-row position)
-    const uint32_t groups = L.W / V;
-    const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
-    uint32_t by = 256 / wx;
-    uint32_t bxh = pow2_ceil(L.Lxh);
-    if (bxh > by) bxh = by;
-    uint32_t nrs = by / bxh;
-    while (nrs > 1 && L.Ly % nrs) nrs >>= 1;
-    if ((uint32_t)ROWS_DESC_CHUNK < nrs) return 0;
-    if (acc && bxh * nrs < (uint32_t)V) return 0;  // the block reduction wants >= V thread rows
-    ra.bxh_log = log2_exact(bxh);
-    ra.nrs_log = log2_exact(nrs);
-    ra.ygroups = L.Ly / nrs;
-    ra.xtiles = (L.Lxh + bxh - 1) / bxh;
-    const uint32_t wtiles = (groups + wx - 1) / wx;
-    const uint64_t units = (uint64_t)L.Lz * ra.ygroups * ra.xtiles * wtiles;
-    if (units > 0x7FFFFFFFull) return 0;
-    ra.units = (uint32_t)units;
     ra.nsat = acc ? a.nsat_out : nullptr;
     ra.pk = philox_round_keys(a.key0, a.key1);
     ra.mx = make_mux(a.th);
-    const dim3 block(wx, bxh * nrs, 1);
+    ra.bxh_log = log2_exact(sh.bxh);
+    ra.nrs_log = log2_exact(sh.nrs);
+    ra.ygroups = L.Ly / sh.nrs;
+    ra.xtiles = sh.xtiles;
+    ra.units = (uint32_t)sh.units;
+    ra.uq = ra.urem = 0;
     const int sms = a.sm_count > 0 ? a.sm_count : (int)device_sms();
-    if (nrs > 1)
-        return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, true>(ra, block, sms, st)
-                   : rows_launch<DIM, PMJ, K, ROUNDS, V, false, true>(ra, block, sms, st);
-    return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, false>(ra, block, sms, st)
-               : rows_launch<DIM, PMJ, K, ROUNDS, V, false, false>(ra, block, sms, st);
+    if (mode == 2)
+        return sh.nrs > 1 ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, true, true>(ra, sh, sms, st)
+                          : rows_launch<DIM, PMJ, K, ROUNDS, V, true, false, true>(ra, sh, sms, st);
+#ifndef ISING_ROWS_NO_TMA
+    static const bool use_tma = getenv("ISING_TMA") != nullptr;   // opt-in: measured slower
+    if (V == 4 && use_tma) {
+        const int rc = rows_tma_phase<DIM, PMJ, K, ROUNDS>(L, ra, sh, acc, sms, st);
+        if (rc != 0) return rc;
+    }
+#endif
+    if (sh.nrs > 1)
+        return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, true, false>(ra, sh, sms, st)
+                   : rows_launch<DIM, PMJ, K, ROUNDS, V, false, true, false>(ra, sh, sms, st);
+    return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, false, false>(ra, sh, sms, st)
+               : rows_launch<DIM, PMJ, K, ROUNDS, V, false, false, false>(ra, sh, sms, st);
 }
 
+// Both colour phases of one sweep.  With a.nsat_out the per-experiment satisfied-bond count after
+// the sweep is added to it, fused into the second phase.  ISING_ROWS_SPLIT_ACC=1 (A/B knob) runs
+// two plain phases and a count-only pass instead: measured slower on BASELINE config 3 (92.9 vs
+// 76.3 us per sweep) - re-reading the lattice through L2 costs more than the fused accumulation.
 template <int DIM, bool PMJ, int V>
 static int rows_sweep(const SweepArgs& a, cudaStream_t st) {
+    if (a.rounds != kDefaultRounds) return 0;   // other round counts: the one-row-per-block launch
+    static const int split_env = getenv("ISING_ROWS_SPLIT_ACC") ? atoi(getenv("ISING_ROWS_SPLIT_ACC")) : -1;
+    const bool split = a.nsat_out != nullptr && (split_env >= 0 ? split_env != 0 : ISING_ROWS_SPLIT_ACC_DEFAULT != 0);
     int n = 0;
     for (uint32_t c = 0; c < 2; ++c) {
-        const bool acc = a.nsat_out != nullptr && c == 1;
-        int rc;
-        if (a.rounds == 7) rc = rows_phase<DIM, PMJ, 6, 7, V>(a, st, c, acc);
-        else rc = rows_phase<DIM, PMJ, 6, 10, V>(a, st, c, acc);
+        const int mode = (a.nsat_out != nullptr && c == 1 && !split) ? 1 : 0;
+        const int rc = rows_phase<DIM, PMJ, 6, kDefaultRounds, V>(a, st, c, mode);
         if (rc <= 0) return c == 0 ? rc : -1;
+        n += rc;
+    }
+    if (split) {
+        const int rc = rows_phase<DIM, PMJ, 6, kDefaultRounds, V>(a, st, 0u, 2);
+        if (rc <= 0) return -1;
         n += rc;
     }
     return cudaGetLastError() == cudaSuccess ? n : -1;
@@ -108,6 +230,5 @@ static int launch_sweep_rows_dim(const SweepArgs& a, cudaStream_t st) {
     if (a.lay.W % 2 == 0) return rows_dispatch<DIM, 2>(a, st);
     return rows_dispatch<DIM, 1>(a, st);
 }
-
 
 }  // namespace ising

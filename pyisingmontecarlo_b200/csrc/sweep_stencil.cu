@@ -216,9 +216,9 @@ template <int DIM, bool PMJ, int V>
 static int coop_dispatch(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
                          unsigned long long* hist, uint32_t cw, cudaStream_t st) {
     // the cooperative path is an optimisation for launch-bound sizes: default planes / rounds only
-    if (a.planes != 6 || a.rounds != 10) return 0;
-    return hist ? coop_launch<DIM, PMJ, 6, 10, V, true>(a, th_dev, nsweeps, hist, cw, st)
-                : coop_launch<DIM, PMJ, 6, 10, V, false>(a, th_dev, nsweeps, nullptr, cw, st);
+    if (a.planes != 6 || a.rounds != kDefaultRounds) return 0;
+    return hist ? coop_launch<DIM, PMJ, 6, kDefaultRounds, V, true>(a, th_dev, nsweeps, hist, cw, st)
+                : coop_launch<DIM, PMJ, 6, kDefaultRounds, V, false>(a, th_dev, nsweeps, nullptr, cw, st);
 }
 
 // returns 1 when the chunk was launched cooperatively, 0 when this configuration has no

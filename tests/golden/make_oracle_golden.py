@@ -43,14 +43,22 @@ def cases():
                 col[s] = (x + y + z) & 1
                 for nb in (idx((x + 1) % L[0], y, z), idx(x, (y + 1) % L[1], z), idx(x, y, (z + 1) % L[2])):
                     a.append(s); b.append(nb); j.append(float(rng.choice([-1.0, 1.0])))
-    en, st = o.msc_mirror(a, b, j, n, col, 70, 12345, np.linspace(0.2, 1.3, 5), per_sweep=True)
+    en, st = o.msc_mirror(a, b, j, n, col, 70, 12345, np.linspace(0.2, 1.3, 5), per_sweep=True, rounds=10)
     out["mirror_edges"] = np.array([a, b]); out["mirror_j"] = np.array(j); out["mirror_colors"] = col
     out["mirror_energies"], out["mirror_states"] = en, np.packbits(st, axis=1)
-    st_pt, en_pt, swaps, slots = o.msc_mirror_pt(a, b, j, n, col, np.geomspace(0.2, 1.4, 12), 77, 25, 3, 5)
+    st_pt, en_pt, swaps, slots = o.msc_mirror_pt(a, b, j, n, col, np.geomspace(0.2, 1.4, 12), 77, 25, 3, 5, rounds=10)
     out["mirror_pt_states"], out["mirror_pt_energies"] = np.packbits(st_pt, axis=2), en_pt
     out["mirror_pt_swaps"], out["mirror_pt_slots"] = np.array([swaps]), slots
-    en, st = o.msc_mirror_single(128, 8, -1.0, 9, [0.4, 0.44, 0.5])
+    en, st = o.msc_mirror_single(128, 8, -1.0, 9, [0.4, 0.44, 0.5], rounds=10)
     out["single_energies"], out["single_state"] = en, np.packbits(st, axis=1)
+    # the same three with Philox4x32-7, the library default since round 2
+    en, st = o.msc_mirror(a, b, j, n, col, 70, 12345, np.linspace(0.2, 1.3, 5), per_sweep=True, rounds=7)
+    out["mirror7_energies"], out["mirror7_states"] = en, np.packbits(st, axis=1)
+    st_pt, en_pt, swaps, slots = o.msc_mirror_pt(a, b, j, n, col, np.geomspace(0.2, 1.4, 12), 77, 25, 3, 5, rounds=7)
+    out["mirror7_pt_states"], out["mirror7_pt_energies"] = np.packbits(st_pt, axis=2), en_pt
+    out["mirror7_pt_swaps"], out["mirror7_pt_slots"] = np.array([swaps]), slots
+    en, st = o.msc_mirror_single(128, 8, -1.0, 9, [0.4, 0.44, 0.5], rounds=7)
+    out["single7_energies"], out["single7_state"] = en, np.packbits(st, axis=1)
     return out
 
 

@@ -246,7 +246,7 @@ def philox4x32(ctr, key, rounds=10):
     return out
 
 
-def msc_mirror(a, b, j, nvars, colors, E, seed, betas, *, replica_offset=0, planes=6, rounds=10,
+def msc_mirror(a, b, j, nvars, colors, E, seed, betas, *, replica_offset=0, planes=6, rounds=7,
                init_state=None, states=None, sweep0=0, per_sweep=False, per_replica_beta=None,
                nsweeps=None):
     """Scalar restatement of the production sweep (oracle/msc_mirror.c).
@@ -279,7 +279,7 @@ def msc_mirror(a, b, j, nvars, colors, E, seed, betas, *, replica_offset=0, plan
 
 
 def msc_mirror_pt(a, b, j, nvars, colors, betas, seed, timesteps, replica_swap_freq=1,
-                  sampling_freq=1, planes=6, rounds=10):
+                  sampling_freq=1, planes=6, rounds=7):
     """Parallel tempering as the device runs it (oracle/msc_mirror.c: msc_mirror_pt)."""
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
@@ -299,7 +299,7 @@ def msc_mirror_pt(a, b, j, nvars, colors, betas, seed, timesteps, replica_swap_f
     return states.astype(bool), energies, int(swaps.value), slots
 
 
-def msc_mirror_single(Lx, Ly, j, seed, betas, planes=6, rounds=10, state=None):
+def msc_mirror_single(Lx, Ly, j, seed, betas, planes=6, rounds=7, state=None):
     """One bit-packed 2D lattice as the device runs it (oracle/msc_mirror.c: msc_mirror_single)."""
     betas = np.ascontiguousarray(betas, dtype=np.float64)
     st = np.zeros((Ly, Lx), dtype=np.uint8) if state is None else np.ascontiguousarray(state, dtype=np.uint8).copy()

@@ -107,14 +107,17 @@ def test_hot_kernels_keep_their_register_budget(native):
         assert hits, fragment
         return hits
 
-    # k_sweep_stencil<DIM=3, PMJ, K=6, ROUNDS=10, V=4, ACC>
+    # row-walk kernel of config 3: k_sweep_rows<DIM=3, PMJ, K=6, ROUNDS=7, V=4, ACC, MULTIROW>
+    for reg, stack in find("k_sweep_rowsILi3ELb1ELi6ELi7ELi4ELb0ELb0"):
+        assert reg <= 85 and stack == 0, (reg, stack)
+    for reg, stack in find("k_sweep_rowsILi3ELb1ELi6ELi7ELi4ELb1ELb0"):
+        assert reg <= 128 and stack == 0, (reg, stack)
+    # one-row-per-block launch (other Philox round counts): k_sweep_stencil<3, PMJ, 6, 10, 4, ACC>
     for reg, stack in find("k_sweep_stencilILi3ELb1ELi6ELi10ELi4ELb0"):
         assert reg <= 85 and stack == 0, (reg, stack)
-    for reg, stack in find("k_sweep_stencilILi3ELb1ELi6ELi10ELi4ELb1"):
-        assert reg <= 128 and stack == 0, (reg, stack)
-    for reg, stack in find("k_strip_phaseILi6ELi10ELi4"):
+    for reg, stack in find("k_strip_phaseILi6ELi7ELi4"):
         assert reg <= 85 and stack == 0, (reg, stack)
-    for reg, stack in find("k_sweep_generalILi6ELi10ELb1ELi3ELi2"):
+    for reg, stack in find("k_sweep_generalILi6ELi7ELb1ELi3ELi2"):
         assert reg <= 64 and stack == 0, (reg, stack)
 
 

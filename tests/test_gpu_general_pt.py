@@ -45,7 +45,7 @@ def irregular_graph(n, rng, maxdeg=7):
     return out
 
 
-def _check_vs_mirror(native, oracle, graph, E, seed, betas, planes=6, rounds=10, general=False):
+def _check_vs_mirror(native, oracle, graph, E, seed, betas, planes=6, rounds=7, general=False):
     a, b, j = graph.edges()
     sim = native.Sim(graph, E, seed, planes=planes, rounds=rounds, general_layout=general)
     en = sim.sweeps(betas, per_sweep_energies=True)
@@ -69,7 +69,7 @@ def test_random_regular_graph_matches_mirror(native, oracle, pkg):
     a, b, _ = g.edges()
     assert (colors[a.astype(int)] != colors[b.astype(int)]).all()   # proper colouring
     _check_vs_mirror(native, oracle, g, 70, 11, np.linspace(0.1, 1.5, 6))
-    _check_vs_mirror(native, oracle, g, 33, 12, [0.8, 0.8], planes=5, rounds=7)
+    _check_vs_mirror(native, oracle, g, 33, 12, [0.8, 0.8], planes=5, rounds=10)
 
 
 def test_irregular_pmj_graph_matches_mirror(native, oracle, pkg):

@@ -38,7 +38,7 @@ def test_exchange_batches_match_mirror(native, oracle, k):
     lat = pkg.SingleLattice2D(Lx, Ly, j=-1.0, seed=9, exchange_every=k)
     assert lat.strip.ghost == max(1, 2 * k)
     lat.sweeps(betas)
-    en_ref, st_ref = oracle.msc_mirror_single(Lx, Ly, -1.0, 9, betas, 6, 10)
+    en_ref, st_ref = oracle.msc_mirror_single(Lx, Ly, -1.0, 9, betas, 6, 7)
     assert (lat.local_rows() == st_ref).all()
     assert lat.energy() == en_ref[-1]
 

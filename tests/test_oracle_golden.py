@@ -30,22 +30,24 @@ def test_device_matches_committed_fixtures(native):
     lat = pkg.Lattice.from_arrays(a, b, j)
     g = lat.graph()
     assert g.kind == native.KIND_STENCIL3D and (g.colors() == GOLD["mirror_colors"]).all()
-    sim = native.Sim(g, 70, 12345)
-    en = sim.sweeps(np.linspace(0.2, 1.3, 5), per_sweep_energies=True)
-    assert np.array_equal(en, GOLD["mirror_energies"])
-    assert np.array_equal(np.packbits(sim.states(), axis=1), GOLD["mirror_states"])
-    pt = native.Tempering(g, np.geomspace(0.2, 1.4, 12), seed=77)
-    st, e = pt.timesteps_sample(25, 3, 5)
-    assert np.array_equal(np.packbits(st, axis=2), GOLD["mirror_pt_states"])
-    assert np.array_equal(e, GOLD["mirror_pt_energies"])
-    assert pt.total_swaps() == int(GOLD["mirror_pt_swaps"][0]) and (pt.slots() == GOLD["mirror_pt_slots"]).all()
-    sl = pkg.SingleLattice2D(128, 8, seed=9)
-    ens = []
-    for beta in (0.4, 0.44, 0.5):
-        sl.sweeps([beta])
-        ens.append(sl.energy())
-    assert ens == list(GOLD["single_energies"])
-    assert np.array_equal(np.packbits(sl.local_rows(), axis=1), GOLD["single_state"])
+    for rounds, tag in ((10, ""), (7, "7")):        # 7 = the library default
+        sim = native.Sim(g, 70, 12345, rounds=rounds if rounds == 10 else 0)
+        en = sim.sweeps(np.linspace(0.2, 1.3, 5), per_sweep_energies=True)
+        assert np.array_equal(en, GOLD[f"mirror{tag}_energies"])
+        assert np.array_equal(np.packbits(sim.states(), axis=1), GOLD[f"mirror{tag}_states"])
+        pt = native.Tempering(g, np.geomspace(0.2, 1.4, 12), seed=77, rounds=rounds if rounds == 10 else 0)
+        st, e = pt.timesteps_sample(25, 3, 5)
+        assert np.array_equal(np.packbits(st, axis=2), GOLD[f"mirror{tag}_pt_states"])
+        assert np.array_equal(e, GOLD[f"mirror{tag}_pt_energies"])
+        assert pt.total_swaps() == int(GOLD[f"mirror{tag}_pt_swaps"][0])
+        assert (pt.slots() == GOLD[f"mirror{tag}_pt_slots"]).all()
+        sl = pkg.SingleLattice2D(128, 8, seed=9, rounds=rounds if rounds == 10 else 0)
+        ens = []
+        for beta in (0.4, 0.44, 0.5):
+            sl.sweeps([beta])
+            ens.append(sl.energy())
+        assert ens == list(GOLD[f"single{tag}_energies"])
+        assert np.array_equal(np.packbits(sl.local_rows(), axis=1), GOLD[f"single{tag}_state"])
     # replay of the reference-algorithm trace fixture (512 attempts of two experiments)
     from oracle_lib import square_edges  # lattice helper only
     lat1 = pkg.Lattice(square_edges(32), seed_gen=0)
