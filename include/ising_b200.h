@@ -46,6 +46,7 @@ typedef struct ising_graph ising_graph;
 typedef struct ising_sim ising_sim;
 typedef struct ising_pt ising_pt;
 typedef struct ising_strip ising_strip;
+typedef struct ising_comm ising_comm;
 
 /* ---- context ---------------------------------------------------------------------------- */
 ISING_API int ising_abi_version(void);
@@ -220,6 +221,20 @@ ISING_API int ising_replay(ising_ctx *ctx, const ising_graph *g, double beta, ui
                  uint64_t nattempts, const uint32_t *sites, const double *u,
                  const uint8_t *init, double *energies, uint8_t *states);
 
+/* ---- communicator of the multi-GPU paths (one process per GPU) ----------------------------- */
+/* The reference's only parallel axes are rayon loops inside one process (experiments,
+ * lattice.rs:192-197; tempering replicas, tempering.rs:179-186).  Across GPUs the same axes are
+ * sharded over processes, and what the hot path exchanges - the replica energies of a tempering
+ * swap step, the boundary rows of a strip decomposition - moves through NCCL calls this library
+ * makes on the context's stream.  NCCL is bound at run time (dlopen of libnccl.so.2, shared with
+ * whatever copy the process already loaded).  Rank 0 obtains an id, the host layer broadcasts
+ * its ISING_COMM_ID_BYTES bytes by any means, every rank creates its communicator from it. */
+#define ISING_COMM_ID_BYTES 128
+ISING_API int ising_comm_unique_id(uint8_t *out, uint64_t capacity);
+ISING_API int ising_comm_create(ising_ctx *ctx, const uint8_t *id, int rank, int world, ising_comm **out);
+ISING_API void ising_comm_destroy(ising_comm *comm);
+ISING_API int ising_comm_info(const ising_comm *comm, int *rank, int *world);
+
 /* ---- classical parallel tempering with the cadence of tempering.rs:156-222 --------------- */
 /* One configuration per inverse temperature ("slot"), every configuration one replica bit of
  * the packed layout, so a whole temperature ladder advances in one sweep.  A swap exchanges the
@@ -253,8 +268,19 @@ ISING_API int ising_pt_restore(ising_pt *pt, const uint32_t *slot_of_config, uin
                      uint64_t total_swaps);
 /* LatticeTempering::get_total_swaps, tempering.rs:297-299 */
 ISING_API int ising_pt_total_swaps(const ising_pt *pt, uint64_t *out);
-/* LatticeTempering::qmc_timesteps_sample (tempering.rs:156-222) on one rank:
- * states bool[R, timesteps / sampling_freq, nvars], energies[R]. */
+/* Swaps attempted / accepted per pair of neighbouring betas (pair a = slots a and a + 1;
+ * attempts[nbetas - 1], accepts[nbetas - 1]): the per-pair view of get_total_swaps. */
+ISING_API int ising_pt_get_pair_stats(const ising_pt *pt, uint64_t *attempts, uint64_t *accepts);
+/* Shards the ladder over the ranks of a communicator (tempering.rs:179-186 is the reference's
+ * replica axis): rank r must have been created with the r-th contiguous block of configurations
+ * (blocks of nbetas / world, remainder to the first ranks).  From then on
+ * ising_pt_timesteps_sample all-gathers the energies (and the sampled states) with NCCL on the
+ * context's stream and every rank returns the full arrays. */
+ISING_API int ising_pt_set_comm(ising_pt *pt, ising_comm *comm);
+/* LatticeTempering::qmc_timesteps_sample (tempering.rs:156-222):
+ * states bool[R, timesteps / sampling_freq, nvars], energies[R].  Device-resident: sweeps,
+ * energies, swap decisions (Philox + a fixed-sequence exp, identical to ising_pt_decide_swaps),
+ * threshold tables and samples are all enqueued on the context's stream; the host waits once. */
 ISING_API int ising_pt_timesteps_sample(ising_pt *pt, uint64_t timesteps, uint64_t replica_swap_freq,
                               uint64_t sampling_freq, uint8_t *states, double *energies);
 
@@ -296,6 +322,14 @@ ISING_API int ising_strip_get_boundary(ising_strip *s, int colour, int which, vo
 ISING_API int ising_strip_set_ghost(ising_strip *s, int colour, int which, const void *src_words);
 ISING_API int ising_strip_wrap_local(ising_strip *s, int colour);
 ISING_API int ising_strip_observables(ising_strip *s, uint64_t *nsat_local, uint64_t *up_local);
+/* nsweeps whole sweeps of a lattice split in row strips over the ranks of `comm` (NULL: this
+ * strip holds the whole lattice): batches of `exchange_every` sweeps, one deep halo exchange of
+ * 2 * exchange_every boundary rows per side (ncclSend / ncclRecv on the context's stream) per
+ * batch, ghost rows updated redundantly in between.  exchange_every is clipped to ghost / 2. */
+ISING_API int ising_strip_sweeps(ising_strip *s, ising_comm *comm, const double *betas, uint64_t nsweeps,
+                       uint32_t exchange_every);
+/* satisfied bonds and up spins of the WHOLE lattice (halo exchange + all-reduce inside) */
+ISING_API int ising_strip_global_sums(ising_strip *s, ising_comm *comm, uint64_t *nsat, uint64_t *up);
 ISING_API int ising_strip_get_rows(ising_strip *s, uint8_t *rows_out /* (row_hi-row_lo)*Lx bool */);
 ISING_API int ising_strip_get_stats(ising_strip *s, uint64_t *launches, double *device_ms, int reset);
 

@@ -197,6 +197,36 @@ ORC_EXPORT int msc_mirror_run(uint64_t nvars, uint64_t nedges, const uint64_t *e
     return 0;
 }
 
+/* exp(d), d <= 0, as the fixed sequence of IEEE double operations the device's swap kernel and
+ * ising_pt_decide_swaps use (pyisingmontecarlo_b200/csrc/pt_exp.h), restated here so that the
+ * mirror's swap decisions are bit-identical to the device's: d = k ln2 + r, degree-13 Taylor
+ * polynomial of exp(r) in Horner form, 2^k from the exponent bits.  Compiled without FMA
+ * contraction (the Makefile passes -ffp-contract=off). */
+static double pt_exp_nonpos(double d) {
+    if (!(d <= 0.0)) return 1.0;
+    if (d < -700.0) return 0.0;
+    const double INV_LN2 = 1.4426950408889634074;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double t = d * INV_LN2;
+    const long long ki = (long long)(t + -0.5);
+    const double kf = (double)ki;
+    double r = d + -(kf * LN2_HI);
+    r = r + -(kf * LN2_LO);
+    static const double c[13] = {1.6059043836821613e-10, 2.0876756987868098e-09, 2.5052108385441720e-08,
+                                 2.7557319223985888e-07, 2.7557319223985893e-06, 2.4801587301587302e-05,
+                                 1.9841269841269841e-04, 1.3888888888888889e-03, 8.3333333333333332e-03,
+                                 4.1666666666666664e-02, 1.6666666666666666e-01, 5.0000000000000000e-01,
+                                 1.0000000000000000e+00};
+    double p = c[0];
+    for (int i = 1; i < 13; ++i) p = p * r + c[i];
+    p = p * r + 1.0;
+    const uint64_t bits = (uint64_t)(1023 + ki) << 52;
+    double scale;
+    memcpy(&scale, &bits, sizeof scale);
+    return p * scale;
+}
+
 /* Parallel tempering exactly as libising_b200 runs it (ising_pt_timesteps_sample): one
  * configuration per replica bit, betas[R] by slot, cadence of tempering.rs:156-222, swap rule
  * and Philox draw of ising_pt_decide_swaps.  states[R, n_s, nvars], energies[R]. */
@@ -238,7 +268,7 @@ ORC_EXPORT int msc_mirror_pt(uint64_t nvars, uint64_t nedges, const uint64_t *ea
                         uint32_t c4[4] = {(uint32_t)a, (uint32_t)parity, (uint32_t)swap_step, 2u << 24};
                         philox4x32(10, c4, m.k0, m.k1);
                         const double uu = ((double)c4[0] + 0.5) * (1.0 / 4294967296.0);
-                        accept = uu < exp(d);
+                        accept = uu < pt_exp_nonpos(d);
                     }
                     if (accept) {
                         cfg_of_slot[a] = cb; cfg_of_slot[a + 1] = ca;

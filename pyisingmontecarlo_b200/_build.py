@@ -12,8 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libising_b200.so")
 SOURCES = ["sweep_rows3d.cu", "sweep_rows2d.cu", "sweep_stencil.cu", "sweep_cluster.cu", "sweep_general.cu", "strip.cu", "observables.cu", "state_io.cu",
-           "api_core.cu", "api_sim.cu", "api_pt.cu", "api_strip.cu", "api_run.cu", "graph.cpp"]
-HEADERS = ["kernels.h", "msc_device.cuh", "sweep_phase.cuh", "sweep_rows.cuh", "sweep_rows_launch.cuh", "api_internal.h", "graph.h", "philox.h",
+           "api_core.cu", "api_sim.cu", "api_pt.cu", "api_comm.cu", "pt_device.cu", "api_strip.cu", "api_run.cu", "graph.cpp"]
+HEADERS = ["kernels.h", "msc_device.cuh", "sweep_phase.cuh", "sweep_rows.cuh", "sweep_rows_launch.cuh", "api_internal.h", "graph.h", "philox.h", "pt_exp.h",
            os.path.join("..", "..", "include", "ising_b200.h")]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-fvisibility=hidden"]

@@ -129,6 +129,14 @@ _SIGNATURES = {
     "ising_pt_get_local_states": (C.c_int, [_P, _P]),
     "ising_pt_total_swaps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ising_pt_timesteps_sample": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
+    "ising_strip_sweeps": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32]),
+    "ising_strip_global_sums": (C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ising_pt_set_comm": (C.c_int, [_P, _P]),
+    "ising_pt_get_pair_stats": (C.c_int, [_P, _P, _P]),
+    "ising_comm_unique_id": (C.c_int, [_P, C.c_uint64]),
+    "ising_comm_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "ising_comm_destroy": (None, [_P]),
+    "ising_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ising_strip_create": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(_P)]),
     "ising_strip_create_ex": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
     "ising_strip_phase_ext": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32, C.c_int, C.c_int]),
@@ -474,6 +482,58 @@ class Sim:
             pass
 
 
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """NCCL communicator owned by the library (ising_comm), one rank per process / GPU.  The
+    collectives of the hot path (tempering energies, strip halos) are issued by the C library on
+    the context's stream; the host layer only has to get rank 0's unique id to every rank."""
+
+    def __init__(self, ctx, unique_id, rank, world):
+        self.ctx = ctx
+        idb = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        if idb.size != COMM_ID_BYTES:
+            raise ValueError("unique id must be %d bytes" % COMM_ID_BYTES)
+        h = C.c_void_p()
+        check(lib().ising_comm_create(ctx.handle, ptr(idb), int(rank), int(world), C.byref(h)), ctx.handle)
+        self.handle = h
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id():
+        out = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+        check(lib().ising_comm_unique_id(ptr(out), COMM_ID_BYTES), None)
+        return out.tobytes()
+
+    @classmethod
+    def from_torch(cls, ctx, group=None):
+        """Bootstraps over an initialised torch.distributed group (any backend): rank 0 creates
+        the id, a broadcast carries its 128 bytes.  torch is used for this exchange only."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", ctx.device) if backend == "nccl" else torch.device("cpu")
+        buf = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(ctx, bytes(buf.cpu().numpy().tobytes()), rank, world)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().ising_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Tempering:
     """Classical parallel tempering on the device (ising_pt): configurations [cfg_lo, cfg_hi)
     of a ladder of `betas` live on this rank."""
@@ -518,6 +578,19 @@ class Tempering:
         n = C.c_uint64(0)
         check(lib().ising_pt_total_swaps(self.handle, C.byref(n)), self.ctx.handle)
         return int(n.value)
+
+    def set_comm(self, comm):
+        """Shards the ladder over the ranks of `comm` (this object must hold the rank's block):
+        timesteps_sample then gathers energies and samples with NCCL inside the library."""
+        check(lib().ising_pt_set_comm(self.handle, comm.handle if comm is not None else None), self.ctx.handle)
+        self._comm = comm
+
+    def pair_stats(self):
+        """(attempts, accepts) uint64[R - 1] of the swaps between neighbouring betas."""
+        att = np.zeros(max(self.R - 1, 0), dtype=np.uint64)
+        acc = np.zeros(max(self.R - 1, 0), dtype=np.uint64)
+        check(lib().ising_pt_get_pair_stats(self.handle, ptr(att), ptr(acc)), self.ctx.handle)
+        return att, acc
 
     def checkpoint(self):
         """Everything needed to continue this ladder bit for bit (see restore)."""
@@ -586,6 +659,20 @@ class Strip:
 
     def set_all(self, up):
         check(lib().ising_strip_set_all(self.handle, int(bool(up))), self.ctx.handle)
+
+    def sweeps(self, betas, comm=None, exchange_every=8):
+        """One checkerboard sweep per beta with the halo exchange inside the library
+        (ising_strip_sweeps): comm = None for a strip that holds the whole lattice."""
+        b = np.ascontiguousarray(np.atleast_1d(betas), dtype=np.float64)
+        check(lib().ising_strip_sweeps(self.handle, comm.handle if comm is not None else None, ptr(b), len(b),
+                                       int(exchange_every)), self.ctx.handle)
+
+    def global_sums(self, comm=None):
+        """(satisfied bonds, up spins) of the whole lattice over all ranks of comm."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib().ising_strip_global_sums(self.handle, comm.handle if comm is not None else None,
+                                            C.byref(a), C.byref(b)), self.ctx.handle)
+        return int(a.value), int(b.value)
 
     def phase(self, colour, beta):
         check(lib().ising_strip_phase(self.handle, int(colour), float(beta)), self.ctx.handle)

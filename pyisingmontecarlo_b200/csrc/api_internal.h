@@ -80,6 +80,8 @@ struct ising_graph {
     float* d_biasf = nullptr;
 };
 
+struct ising_comm;
+
 struct ising_sim {
     ising_ctx* ctx = nullptr;
     const ising_graph* g = nullptr;
@@ -99,6 +101,7 @@ struct ising_sim {
     bool perbeta = false;
     unsigned long long* d_t64 = nullptr;
     uint32_t* d_slot = nullptr;
+    uint32_t t64_rows = 0;         // rows of d_t64 (per replica bit, or per ladder slot)
     uint32_t* d_tplane = nullptr;
     uint32_t* d_tlow = nullptr;
     // host cache of the general-graph threshold rows T64[deg][cls] by beta (bit pattern): in

@@ -300,6 +300,102 @@ extern "C" int ising_strip_observables(ising_strip* s, uint64_t* nsat, uint64_t*
     return ISING_OK;
 }
 
+int comm_world(const ising_comm* c);
+int comm_ring_exchange(ising_comm* c, const void* send_up, const void* send_down, void* recv_up,
+                       void* recv_down, size_t bytes, cudaStream_t st);
+int comm_allreduce_sum_u64(ising_comm* c, const void* send, void* recv, size_t count, cudaStream_t st);
+
+// `depth` boundary rows of both colours to the neighbouring strips' ghost rows (periodic ring of
+// ranks), straight from / into the spin array: the rows of one colour are contiguous, so a
+// message is one ncclSend of depth * Lx/64 words.  comm = NULL (or one rank): the strip wraps
+// onto itself.  Enqueue only.
+static int strip_exchange_deep(ising_strip* s, ising_comm* comm, uint32_t depth) {
+    if (!comm || comm_world(comm) == 1) return ising_strip_wrap_deep(s, depth);
+    const StripGeom& g = s->g;
+    if (depth < 1 || depth > g.ghost || depth > g.rows)
+        return fail(s->ctx, ISING_E_INVALID, "depth must be 1..min(ghost, rows)");
+    const size_t nb = (size_t)depth * g.Wr * 4;
+    for (int c = 0; c < 2; ++c) {
+        const int rc = comm_ring_exchange(comm, strip_row_ptr(s, c, g.ghost), strip_row_ptr(s, c, g.ghost + g.rows - depth),
+                                          strip_row_ptr(s, c, g.ghost - depth), strip_row_ptr(s, c, g.ghost + g.rows), nb,
+                                          s->ctx->stream);
+        if (rc) return rc;
+    }
+    return ISING_OK;
+}
+
+// nsweeps checkerboard sweeps of a lattice that is split in row strips over the ranks of `comm`
+// (BASELINE config 5; the reference cannot run it, lattice.rs:197-212): batches of k =
+// exchange_every sweeps, each one deep halo exchange of 2k rows per side (NCCL send/recv over
+// NVLink, issued here on the context's stream) followed by 2k colour phases that update the
+// shrinking valid part of the ghost rows redundantly.  The host waits once, at the end.
+extern "C" int ising_strip_sweeps(ising_strip* s, ising_comm* comm, const double* betas, uint64_t nsweeps,
+                                  uint32_t exchange_every) {
+    CtxLock _lk(s ? s->ctx : nullptr);
+    if (!s || (nsweeps && !betas)) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "strip/betas is NULL");
+    ising_ctx* ctx = s->ctx;
+    const StripGeom& g = s->g;
+    uint32_t k = exchange_every ? exchange_every : 1;
+    if (2 * k > g.ghost) k = g.ghost / 2;
+    if (2 * k > g.rows) k = g.rows / 2;
+    if (k < 1) return fail(ctx, ISING_E_INVALID, "strip needs >= 2 ghost rows and >= 2 local rows for batched sweeps");
+    if ((!comm || comm_world(comm) == 1) && g.rows != g.Ly)
+        return fail(ctx, ISING_E_INVALID, "a strip that holds only part of the lattice needs a communicator");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = ISING_OK;
+    for (uint64_t i = 0; i < nsweeps && rc == ISING_OK;) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(k, nsweeps - i);
+        rc = strip_exchange_deep(s, comm, 2 * nb);
+        for (uint32_t q = 0; q < 2 * nb && rc == ISING_OK; ++q)
+            rc = strip_phase_storage_rows(s, (int)(q & 1u), betas[i + q / 2], g.ghost - (2 * nb - 1 - q),
+                                          g.ghost + g.rows + (2 * nb - 1 - q), (int)(q & 1u), 0);
+        i += nb;
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, ISING_E_CUDA, "strip sweeps: %s", cudaGetErrorString(e));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) s->device_ms += ms;
+    return ISING_OK;
+}
+
+// Global sums over all strips: satisfied bonds and up spins of the whole lattice (halo exchange
+// of one colour-1 row, local reduction, NCCL all-reduce).
+extern "C" int ising_strip_global_sums(ising_strip* s, ising_comm* comm, uint64_t* nsat, uint64_t* up) {
+    CtxLock _lk(s ? s->ctx : nullptr);
+    if (!s || !nsat || !up) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    ising_ctx* ctx = s->ctx;
+    const StripGeom& g = s->g;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!comm || comm_world(comm) == 1) {
+        if (g.rows != g.Ly) return fail(ctx, ISING_E_INVALID, "a partial strip needs a communicator");
+        const int rc = ising_strip_wrap_local(s, 1);
+        if (rc) return rc;
+    } else {
+        const size_t nb = (size_t)g.Wr * 4;
+        const int rc = comm_ring_exchange(comm, strip_row_ptr(s, 1, g.ghost), strip_row_ptr(s, 1, g.ghost + g.rows - 1),
+                                          strip_row_ptr(s, 1, g.ghost - 1), strip_row_ptr(s, 1, g.ghost + g.rows), nb,
+                                          ctx->stream);
+        if (rc) return rc;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(s->d_acc, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (launch_strip_observables(s->d_spins, s->g, s->j > 0 ? 0xFFFFFFFFu : 0u, s->d_acc, ctx->stream) < 0)
+        return fail(ctx, ISING_E_CUDA, "strip observables launch failed");
+    s->launches++;
+    if (comm && comm_world(comm) > 1) {
+        const int rc = comm_allreduce_sum_u64(comm, s->d_acc, s->d_acc, 2, ctx->stream);
+        if (rc) return rc;
+    }
+    unsigned long long h[2];
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, s->d_acc, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *nsat = h[0];
+    *up = h[1];
+    return ISING_OK;
+}
+
 extern "C" int ising_strip_get_rows(ising_strip* s, uint8_t* rows_out) {
     CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !rows_out) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");

@@ -57,8 +57,9 @@ struct SweepArgs {
     const uint32_t* tplane;
     const uint32_t* tlow;
 };
-int launch_build_tables_stencil(const unsigned long long* t64, uint32_t W, int K, uint32_t* plane_out,
-                                uint32_t* low_out, cudaStream_t st);
+// T64[row * 3 + cls], row = slot_of_replica[e] (nullptr: row = e) -> tplane / tlow of the stencil kernels
+int launch_build_tables_stencil(const unsigned long long* t64, const uint32_t* slot_of_replica, uint32_t W,
+                                int K, uint32_t* plane_out, uint32_t* low_out, cudaStream_t st);
 
 // both colour phases of one sweep (2 launches); returns launches made or -1
 int launch_sweep_stencil(const SweepArgs& a, cudaStream_t st);
@@ -148,6 +149,17 @@ int launch_build_tables(const unsigned long long* t64, const uint32_t* slot_of_r
 int launch_nsat_general(const uint32_t* spins, uint64_t nvars, uint32_t W, const uint32_t* row,
                         const uint32_t* nbr, const uint8_t* anti, unsigned long long* nsat2,
                         cudaStream_t st);
+
+// ---- device-resident replica exchange (pt_device.cu) ------------------------------------------
+int launch_pt_swap(const double* betas, const double* e_all, const uint32_t* gidx, uint32_t* slot_of_cfg,
+                   uint32_t* cfg_of_slot, uint32_t R, uint64_t seed, unsigned long long* stats,
+                   uint32_t* slot_of_replica, uint32_t word_lo, uint32_t e32, cudaStream_t st);
+int launch_pt_local_slots(const uint32_t* slot_of_cfg, uint32_t R, uint32_t* slot_of_replica,
+                          uint32_t word_lo, uint32_t e32, cudaStream_t st);
+int launch_pt_accumulate(double* acc, const double* e_all, const uint32_t* gidx, const uint32_t* cfg_of_slot,
+                         uint32_t R, double t, cudaStream_t st);
+int launch_pt_gather_rows(const uint8_t* rows, uint64_t n, const uint32_t* gidx, const uint32_t* cfg_of_slot,
+                          uint32_t R, uint8_t* out, cudaStream_t st);
 
 // ---- arbitrary real couplings and biases (float local field per replica bit) -----------------
 struct RealSweepArgs {

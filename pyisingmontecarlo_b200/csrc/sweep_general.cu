@@ -235,14 +235,16 @@ __global__ void k_build_tables(const unsigned long long* __restrict__ t64,
 }
 
 // stencil variant: T64[e * 3 + cls] per replica -> tplane[(w * 3 + cls) * 8 + p], tlow[(e) * 3 + cls]
-__global__ void k_build_tables_stencil(const unsigned long long* __restrict__ t64, uint32_t W, int K,
+__global__ void k_build_tables_stencil(const unsigned long long* __restrict__ t64,
+                                       const uint32_t* __restrict__ slot_of_replica, uint32_t W, int K,
                                        uint32_t* __restrict__ plane_out, uint32_t* __restrict__ low_out) {
     const uint32_t b = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < W * 3; idx += warps) {
         const uint32_t cls = idx % 3, w = idx / 3;
         const uint32_t e = w * 32 + b;
-        const unsigned long long T = t64[(size_t)e * 3 + cls];
+        const uint32_t row = slot_of_replica ? slot_of_replica[e] : e;
+        const unsigned long long T = t64[(size_t)row * 3 + cls];
         low_out[(size_t)e * 3 + cls] = (uint32_t)(T & 0xFFFFFFFFull);
         uint32_t mine = 0;
         for (int p = 0; p < 8; ++p) {
@@ -253,10 +255,12 @@ __global__ void k_build_tables_stencil(const unsigned long long* __restrict__ t6
     }
 }
 
-int launch_build_tables_stencil(const unsigned long long* t64, uint32_t W, int K, uint32_t* plane_out,
-                                uint32_t* low_out, cudaStream_t st) {
+int launch_build_tables_stencil(const unsigned long long* t64, const uint32_t* slot_of_replica, uint32_t W,
+                                int K, uint32_t* plane_out, uint32_t* low_out, cudaStream_t st) {
     const uint32_t blocks = (W * 3 + 3) / 4;   // 4 warps per block
-    k_build_tables_stencil<<<blocks < 1184u ? blocks : 1184u, 128, 0, st>>>(t64, W, K, plane_out, low_out);
+    const uint32_t cap = device_sms() * 8u;
+    k_build_tables_stencil<<<blocks < cap ? blocks : cap, 128, 0, st>>>(t64, slot_of_replica, W, K, plane_out,
+                                                                        low_out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -264,7 +268,8 @@ int launch_build_tables(const unsigned long long* t64, const uint32_t* slot_of_r
                         int K, uint32_t* plane_out, uint32_t* low_out, cudaStream_t st) {
     const uint32_t total = (GEN_MAX_DEG + 1) * W * GEN_MAX_CLS;
     const uint32_t blocks = (total + 3) / 4;
-    k_build_tables<<<blocks < 1184u ? blocks : 1184u, 128, 0, st>>>(t64, slot_of_replica, W, K, plane_out, low_out);
+    const uint32_t cap = device_sms() * 8u;
+    k_build_tables<<<blocks < cap ? blocks : cap, 128, 0, st>>>(t64, slot_of_replica, W, K, plane_out, low_out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -131,7 +131,14 @@ class SingleLattice2D:
         self.row_lo, self.row_hi = shard_range(self.Ly, self.rank, self.world)
         self._torch_device = None
         self._async = False
-        if active and dist.get_backend(process_group) == "nccl":
+        self._comm = None
+        self._native_comm = (active and dist.get_backend(process_group) == "nccl" and int(exchange_every) > 0)
+        if self._native_comm:
+            # multi-GPU, batched exchange: the halo send/recv are the library's own NCCL calls on
+            # its stream (ising_strip_sweeps); torch.distributed only carries the NCCL id
+            ctx = nat.Context.get(device)
+            self._comm = nat.Comm.from_torch(ctx, process_group)
+        elif active and dist.get_backend(process_group) == "nccl":
             # multi-GPU: run the library on torch's current stream, so that halo copies, NCCL
             # send/recv and the sweep kernels are ordered on the device without host waits
             import torch
@@ -204,6 +211,9 @@ class SingleLattice2D:
         """One checkerboard sweep per beta: exchange the rows of the colour about to be read,
         update the other colour."""
         betas = np.atleast_1d(np.asarray(betas, dtype=np.float64))
+        if self._native_comm or (self.world == 1 and self._k > 0):
+            self.strip.sweeps(betas, self._comm, max(self._k, 1))   # whole loop inside the library
+            return
         if self._k == 0:
             for beta in betas:
                 for colour in (0, 1):
@@ -217,6 +227,8 @@ class SingleLattice2D:
                       self._torch_device, self._bufs, sync=not self._async)
 
     def _global_sums(self):
+        if self._native_comm:
+            return self.strip.global_sums(self._comm)
         if self._async:
             import torch
 

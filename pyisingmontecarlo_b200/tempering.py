@@ -7,9 +7,12 @@ the same cadence and return layout -- around a classical stepper: every temperat
 replica bit of the packed device layout, so the whole ladder advances in one sweep, and a swap
 exchanges two betas instead of moving configurations.
 
-Multi-GPU (one process per GPU, torch.distributed): rank r owns a contiguous block of
-configurations; per swap step there is one all-gather of R energies, then every rank takes the
-same Philox-keyed decisions.
+Multi-GPU (one process per GPU): rank r owns a contiguous block of configurations; per swap step
+there is one all-gather of R energies, then every rank takes the same Philox-keyed decisions.
+On GPUs the whole cycle - energies, NCCL all-gather, swap kernel, threshold tables, samples - is
+enqueued by the C library on its stream (ising_pt_set_comm + ising_pt_timesteps_sample);
+torch.distributed only carries the 128-byte NCCL id at start-up.  `run_tempering_loop` is the
+same loop in host code over any torch.distributed backend (gloo in the CPU tests).
 """
 import secrets
 
@@ -155,6 +158,11 @@ class LatticeTempering:
             if self._coll.active and self._seed is None:
                 raise ValueError("a seed is required when tempering across ranks")
             self._pt = nat.Tempering(self._graph, self._betas, seed, lo, hi)
+            self._comm = None
+            if self._coll.active and self._coll.dist.get_backend(self._group) == "nccl":
+                # the collectives of the swap cycle are the library's own NCCL calls
+                self._comm = nat.Comm.from_torch(ctx, self._group)
+                self._pt.set_comm(self._comm)
         return self._pt
 
     def qmc_timesteps(self, t):
@@ -167,7 +175,7 @@ class LatticeTempering:
         sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
         replica_swap_freq = 1 if replica_swap_freq is None else int(replica_swap_freq)
         pt = self._ensure()
-        if not self._coll.active:
+        if not self._coll.active or self._comm is not None:
             if replica_swap_freq <= 0 or sampling_freq <= 0:
                 raise ValueError("replica_swap_freq and sampling_freq must be > 0 "
                                  "(the reference's loop never terminates on 0)")
