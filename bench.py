@@ -44,8 +44,8 @@ WORKLOADS = {
                     "beta=0.43, 20 sweeps/step"),
     "c4": dict(kind="tempering", n=1_000_000, degree=3, replicas=64, sweeps=100, swap_every=10,
                beta=(0.1, 1.5), dims=(1_000_000,), pmj=False, j0=-1.0,
-               desc="random 3-regular graph N=1e6 (greedy colouring), parallel tempering 64 betas "
-                    "geometric in [0.1, 1.5], swap every 10 sweeps, 100 sweeps/step, one ladder per GPU"),
+               desc="random 3-regular graph N=1e6 (greedy colouring), parallel tempering: ONE ladder of 64 betas "
+                    "geometric in [0.1, 1.5] sharded over the ranks, swap every 10 sweeps, 100 sweeps/step"),
     "c5": dict(kind="single", dims=(65536, 65536), pmj=False, j0=-1.0, sweeps=20, beta=(0.44, 0.44), replicas=1,
                desc="2D ferromagnet 65536x65536 single lattice bit-packed along x, row strips over the "
                     "ranks with halo exchange, beta=0.44, 20 sweeps/step"),
@@ -138,7 +138,7 @@ def betas_for(w):
 # ------------------------------------------------------------------------------------------------
 # reference arm: CPU restatement of the reference algorithm, all host threads
 # ------------------------------------------------------------------------------------------------
-def oracle_sample(w, steps, warmup, sample_sweeps=None):
+def oracle_sample(w, steps, warmup, sample_sweeps=None, with_energies=True):
     import oracle_lib
 
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
@@ -174,7 +174,7 @@ def oracle_sample(w, steps, warmup, sample_sweeps=None):
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        g.run_annealing(stops, sample_sweeps, seeds, q1_compat=False, per_step_energies=True)
+        g.run_annealing(stops, sample_sweeps, seeds, q1_compat=False, per_step_energies=with_energies)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -182,17 +182,75 @@ def oracle_sample(w, steps, warmup, sample_sweeps=None):
     total = sum(times)
     return dict(value=attempts * len(times) / total, ms_per_step=1e3 * total / len(times), cores=threads,
                 sample=f"{E} experiments (one per host thread) x {sample_sweeps} timesteps of {n} "
-                       f"random-site attempts + get_energy each, lattice {'x'.join(map(str, dims))}")
+                       f"random-site attempts{' + get_energy' if with_energies else ''} each, "
+                       f"lattice {'x'.join(map(str, dims))}")
+
+
+def regular_graph(n, d, seed):
+    """random d-regular graph, pairing model with rejection of self loops / multi-edges"""
+    rng = np.random.default_rng(seed)
+    while True:
+        stubs = np.repeat(np.arange(n, dtype=np.int64), d)
+        rng.shuffle(stubs)
+        a, b = stubs[0::2], stubs[1::2]
+        key = np.minimum(a, b) * n + np.maximum(a, b)
+        if not (a == b).any() and len(np.unique(key)) == len(key):
+            return a, b
+
+
+def oracle_sample_tempering(w, steps, warmup):
+    """CPU restatement of the tempering loop (oracle/ising_oracle.c: orc_pt_run, cadence of
+    tempering.rs:156-222, random-site Metropolis per replica) on a bounded sample: the same graph
+    family at N = 50 000 sites, the same 64 betas and swap cadence, all host threads over replicas."""
+    import oracle_lib
+
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    oracle_lib.lib().orc_set_num_threads(ncores)
+    threads = oracle_lib.lib().orc_num_threads()
+    n = 50_000
+    a, b = regular_graph(n, w["degree"], 2026)
+    g = oracle_lib.Graph(arrays=(a, b, np.full(len(a), w["j0"])), nvars=n)
+    betas = np.geomspace(w["beta"][0], w["beta"][1], w["replicas"])
+    sweeps = 2 * w["swap_every"]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        g.pt_run(betas, 7, sweeps, w["swap_every"], sweeps)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=w["replicas"] * n * sweeps * len(times) / total, ms_per_step=1e3 * total / len(times),
+                cores=threads,
+                sample=f"{w['replicas']} betas x {sweeps} timesteps of {n} random-site attempts each on a random "
+                       f"{w['degree']}-regular graph of N = {n} (full size: N = {w['n']}), swap every {w['swap_every']}")
+
+
+def cpu_sample_for(w, steps, warmup, ref_sample_sweeps=None):
+    if w.get("kind") == "tempering":
+        return oracle_sample_tempering(w, steps, warmup)
+    if w.get("kind") == "single":
+        # the reference cannot hold a 65536^2 lattice (206 GB of edges, lattice.rs:31): its algorithm
+        # is timed on 2048^2 lattices, one per host thread
+        ws = dict(w)
+        ws["dims"] = (2048, 2048)
+        r = oracle_sample(ws, steps, warmup, ref_sample_sweeps, with_energies=False)
+        r["sample"] += " (config 5 is ONE 65536x65536 lattice, which the reference cannot hold)"
+        return r
+    return oracle_sample(w, steps, warmup, ref_sample_sweeps)
 
 
 def run_reference(args, w, world, rank):
     if rank != 0:
         return
-    r = oracle_sample(w, args.steps, args.warmup, args.ref_sample_sweeps or None)
+    r = cpu_sample_for(w, args.steps, args.warmup, args.ref_sample_sweeps or None)
     line = {
         "impl": "reference", "metric": "spin_flip_attempts_per_sec", "value": r["value"],
         "unit": "flips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "parallelism": "host threads over experiments"},
         "cpu_baseline": {"value": r["value"], "unit": "flips/s", "cores": r["cores"], "kind": "port",
@@ -206,67 +264,136 @@ def run_reference(args, w, world, rank):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def _dist_helpers(world, local):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    return dist, barrier, reduce
+
+
 def run_tempering(args, w, world, rank, local):
-    """config 4: one temperature ladder per GPU (a temperature is one replica bit, so 64 betas
-    are 2 words per site); wall-clock timed with device synchronisation around K steps."""
+    """config 4 as BASELINE states it: ONE ladder of 64 betas on a random 3-regular graph of 10^6
+    sites, its configurations sharded over the N ranks (rank r holds block r of the betas; the
+    energies of a swap step travel in one NCCL all-gather issued by the library).  A temperature
+    is one replica BIT, so a rank that owns 8 of the 64 configurations still sweeps whole 32-bit
+    words: the stated split cannot go faster than one GPU - `ladders_value` beside
+    it is what N GPUs are good for on this workload, one independent ladder per GPU."""
     import torch
 
     import pyisingmontecarlo_b200 as pkg
     from pyisingmontecarlo_b200 import _native as nat
+    from pyisingmontecarlo_b200.tempering import shard_range
 
     torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-    rng = np.random.default_rng(2026)
+    dist, barrier, reduce = _dist_helpers(world, local)
     n, d = w["n"], w["degree"]
-    while True:
-        stubs = np.repeat(np.arange(n, dtype=np.int64), d)
-        rng.shuffle(stubs)
-        a, b = stubs[0::2], stubs[1::2]
-        key = np.minimum(a, b) * n + np.maximum(a, b)
-        if not (a == b).any() and len(np.unique(key)) == len(key):
-            break
-    lat = pkg.Lattice.from_arrays(a, b, np.full(len(a), w["j0"]), device=local)
-    g = lat.graph()
+    a, b = regular_graph(n, d, 2026)
+    ctx = nat.Context.get(local)
+    g = nat.Graph.from_edges(ctx, n, a.astype(np.uint64), b.astype(np.uint64), np.full(len(a), w["j0"]))
     betas = np.geomspace(w["beta"][0], w["beta"][1], w["replicas"])
-    pt = nat.Tempering(g, betas, seed=7 + rank)
+    lo, hi = shard_range(w["replicas"], rank, world)
+    pt = nat.Tempering(g, betas, seed=7, cfg_lo=lo, cfg_hi=hi, planes=args.planes, rounds=args.rounds)
+    comm = None
+    if world > 1:
+        comm = nat.Comm.from_torch(ctx)
+        pt.set_comm(comm)
+    T, swap = w["sweeps"], w["swap_every"]
 
-    def step():
-        for _ in range(w["sweeps"] // w["swap_every"]):
-            en = pt.sweeps(w["swap_every"])
-            pt.swap_step(en)
+    def step(the_pt):   # device-resident loop of tempering.rs:156-222, no samples
+        the_pt.timesteps_sample(T, swap, T + 1)
 
     for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+        step(pt)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = pt.sim_stats()["kernel_launches"]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+        step(pt)
+    barrier()
+    dt = reduce(time.perf_counter() - t0, "MAX")
+    launches = pt.sim_stats()["kernel_launches"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    flips = float(w["replicas"]) * n * T * args.steps
+    value = flips / dt
+
+    # one independent ladder per GPU (weak), for comparison
+    ladders_value = None
     if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    flips = world * w["replicas"] * n * w["sweeps"] * args.steps
+        own = nat.Tempering(g, betas, seed=100 + rank, planes=args.planes, rounds=args.rounds)
+        step(own)
+        barrier()
+        t0 = time.perf_counter()
+        step(own)
+        barrier()
+        ladders_value = world * float(w["replicas"]) * n * T / reduce(time.perf_counter() - t0, "MAX")
+        own.close()
+
+    # e2e: the public LatticeTempering API with host buffers: the sampled states of all 64 betas
+    # (64 x 10^6 bools) are read back once per step
+    edges = list(zip(zip(a.tolist(), b.tolist()), [w["j0"]] * len(a)))
+    lt = pkg.LatticeTempering(edges, seed=7, device=local)
+    for beta in betas:
+        lt.add_graph(0.0, 0.0, float(beta))
+    lt.qmc_timesteps_sample(T, swap, T)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st, en = lt.qmc_timesteps_sample(T, swap, T)
+        _ = float(en[0]) + float(st[0, 0, 0])
+    barrier()
+    e2e_s = reduce(time.perf_counter() - t0, "MAX")
+    e2e = {"value": flips / e2e_s, "unit": "flips/s", "h2d_bytes_per_step": 0,
+           "d2h_bytes_per_step": int(w["replicas"] * n + 8 * w["replicas"]), "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "LatticeTempering.qmc_timesteps_sample (states of all betas + time-averaged energies to host; "
+                  "graph and ladder stay resident between calls, so there is no per-step H2D)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = oracle_sample_tempering(w, 1, 0)
+        cpu = {"value": r["value"], "unit": "flips/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     # SURVEY 8(d): 2 spin bits + CSR indices streamed once per sweep per replica block
     bpf = (2 * w["replicas"] / 8 + d * 4 + 4 + 4) / w["replicas"]
     peak, peak_src = peaks()
+    att, acc = pt.pair_stats()
     if rank == 0:
         print(json.dumps({
-            "metric": "spin_flip_attempts_per_sec", "value": flips / dt, "unit": "flips/s",
+            "metric": "spin_flip_attempts_per_sec", "value": value, "unit": "flips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 bit-sliced (1 bit per spin per replica)", "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "ncolors": g.ncolors,
-                       "timing": "host clock around synchronised steps (includes swap decisions on the host)"},
-            "roofline": {"bound": "hbm", "achieved": bpf * flips / dt / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": bpf * flips / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_sweep_general", "algorithmic_bytes_per_flip": bpf},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": None,
+                       "parallelism": f"one ladder, configurations sharded x{world}, NCCL all-gather of the "
+                                      "energies per swap step inside the library",
+                       "timing": "host clock around device-synchronised steps; the loop itself never waits for the host",
+                       "l2": "8 MiB of spins + 12 MB of indices per rank: L2-resident"},
+            "ladders_value": ladders_value,
+            "ladders_note": "N independent ladders, one per GPU (weak scaling)" if ladders_value else None,
+            "roofline": {"bound": "hbm", "achieved": bpf * flips / dt / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": bpf * flips / dt / 1e9 / world / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_sweep_general (whole step, per GPU)", "algorithmic_bytes_per_flip": bpf},
+            "swap_acceptance": float(acc.sum()) / max(1.0, float(att.sum())),
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "total_swaps": pt.total_swaps(),
         }), flush=True)
     if world > 1:
@@ -274,57 +401,83 @@ def run_tempering(args, w, world, rank, local):
 
 
 def run_single(args, w, world, rank, local):
-    """config 5: ONE lattice split in row strips (strong scaling: total work fixed)."""
+    """config 5: ONE lattice split in row strips (strong scaling: total work fixed); halo rows by
+    ncclSend/ncclRecv inside the library, one deep exchange per 8 sweeps."""
     import torch
 
     import pyisingmontecarlo_b200 as pkg
 
     torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    dist, barrier, reduce = _dist_helpers(world, local)
     Lx, Ly = w["dims"]
     lat = pkg.SingleLattice2D(Lx, Ly, j=w["j0"], seed=9, device=local, planes=args.planes, rounds=args.rounds)
     betas = [w["beta"][0]] * w["sweeps"]
     for _ in range(args.warmup):
         lat.sweeps(betas)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
     lat.strip.stats(reset=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         lat.sweeps(betas)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    kernel_ms = lat.strip.stats()["device_ms"]
-    if world > 1:
-        t = torch.tensor([dt, kernel_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, kernel_ms = float(t[0]), float(t[1])
+    barrier()
+    wall = reduce(time.perf_counter() - t0, "MAX")
+    stt = lat.strip.stats()
+    dev_ms = reduce(stt["device_ms"], "MAX")
+    clocks = sampler.stop() if rank == 0 else None
     flips = float(Lx) * Ly * w["sweeps"] * args.steps
-    launches = 2 * w["sweeps"] * args.steps
+    launches = stt["launches"]
+    value = flips / (dev_ms * 1e-3)
+
+    # e2e: public API, a fresh all-up lattice every step, the energy of the final state to the host
+    def step_e2e():
+        lat.set_all(True)
+        lat.sweeps(betas)
+        return lat.energy()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = reduce(time.perf_counter() - t0, "MAX")
+    e2e = {"value": flips / e2e_s, "unit": "flips/s", "h2d_bytes_per_step": int(8 * len(betas)),
+           "d2h_bytes_per_step": 16 * world, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "SingleLattice2D.set_all + sweeps + energy (the lattice lives on the device: the inputs of a "
+                  "step are its betas, the result its energy)"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_sample_for(w, 1, 0)
+        cpu = {"value": r["value"], "unit": "flips/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     peak, peak_src = peaks()
     bpf = 0.25
-    # multi-GPU runs enqueue everything asynchronously on torch's stream (no per-kernel events):
-    # fall back to the whole-step time for the per-launch figure
-    k_ms = (kernel_ms if kernel_ms > 0 else 1e3 * dt) / launches
+    per_launch_ms = dev_ms / max(1, launches)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        tj = json.load(open(tpath)).get(args.workload)
+        if tj:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     if rank == 0:
+        ach = bpf * (flips / world / max(1, launches)) / (per_launch_ms * 1e-3) / 1e9
         print(json.dumps({
-            "metric": "spin_flip_attempts_per_sec", "value": flips / dt, "unit": "flips/s",
+            "metric": "spin_flip_attempts_per_sec", "value": value, "unit": "flips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 bit-sliced (1 bit per spin)", "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"],
-                       "timing": "host clock around synchronised steps (kernels + halo exchange); "
-                                 "kernel_ms from CUDA events on the library stream",
-                       "l2": "512 MiB lattice, larger than L2"},
-            "kernel_only_value": flips / (kernel_ms * 1e-3) if kernel_ms > 0 else None,
-            "roofline": {"bound": "hbm", "achieved": bpf * (flips / launches) / (k_ms * 1e-3) / 1e9 / world,
-                         "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
-                         "frac": bpf * (flips / launches) / (k_ms * 1e-3) / 1e9 / world / peak,
-                         "kernel": "k_strip_phase (per GPU)", "kernel_ms": k_ms, "algorithmic_bytes_per_flip": bpf},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": launches,
+                       "parallelism": f"row strips x{world}, ncclSend/ncclRecv of 16 boundary rows per side every 8 sweeps",
+                       "timing": "CUDA events of the library around each batch of sweeps (kernels + halo exchange), "
+                                 "max over ranks",
+                       "l2": "512 MiB lattice, larger than L2" if world == 1 else "%d MiB per rank" % (512 // world)},
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "traffic": traffic,
+                         "peak_source": peak_src, "frac": ach / peak, "kernel": "k_strip_phase (one colour phase, per GPU)",
+                         "kernel_ms": per_launch_ms, "algorithmic_bytes_per_flip": bpf},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -572,8 +725,6 @@ def main():
         w["desc"] += f" [sweeps/step overridden to {args.sweeps}]"
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
-        if w.get("kind") in ("tempering", "single"):
-            raise SystemExit("--impl reference is defined for the lattice workloads")
         run_reference(args, w, world, rank)
     elif w.get("kind") == "tempering":
         run_tempering(args, w, world, rank, local)

@@ -331,6 +331,8 @@ ISING_API int ising_strip_sweeps(ising_strip *s, ising_comm *comm, const double 
 /* satisfied bonds and up spins of the WHOLE lattice (halo exchange + all-reduce inside) */
 ISING_API int ising_strip_global_sums(ising_strip *s, ising_comm *comm, uint64_t *nsat, uint64_t *up);
 ISING_API int ising_strip_get_rows(ising_strip *s, uint8_t *rows_out /* (row_hi-row_lo)*Lx bool */);
+/* local rows [r0, r1) only: bool[r1 - r0, Lx] */
+ISING_API int ising_strip_get_row_range(ising_strip *s, uint64_t r0, uint64_t r1, uint8_t *rows_out);
 ISING_API int ising_strip_get_stats(ising_strip *s, uint64_t *launches, double *device_ms, int reset);
 
 #ifdef __cplusplus

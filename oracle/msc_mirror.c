@@ -361,3 +361,65 @@ ORC_EXPORT int msc_mirror_single(uint64_t Lx, uint64_t Ly, double jcoupling, uin
     }
     return 0;
 }
+
+/* A band of rows of the same lattice: state = bool[nrows, Lx] holds the global rows
+ * y0 .. y0 + nrows - 1 (0 < y0, y0 + nrows < Ly: no periodic wrap inside the band).  The decision
+ * of a site depends only on its global coordinates, so the band reproduces the big lattice
+ * wherever its neighbours are known: colour phase q (q = 0 .. 2 nsweeps - 1) updates the rows
+ * [q + 1, nrows - q - 1), and after nsweeps sweeps the rows [2 nsweeps, nrows - 2 nsweeps) equal
+ * those of the full lattice - the check a 65536^2 lattice allows on a CPU. */
+ORC_EXPORT int msc_mirror_single_band(uint64_t Lx, uint64_t y0, uint64_t nrows, double jcoupling, uint64_t seed,
+                                      int K, int rounds, int randomize, const double *betas, uint64_t nsweeps,
+                                      uint8_t *state) {
+    if (Lx % 64 || K < 1 || K > 8 || nrows < 4 * nsweeps + 1) return -1;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const double jabs = fabs(jcoupling);
+    const int anti = jcoupling > 0;
+    const uint64_t Wr = Lx / 64;
+    if (randomize)
+        for (uint64_t r = 0; r < nrows; ++r)
+            for (uint32_t c = 0; c < 2; ++c)
+                for (uint64_t j = 0; j < Wr; ++j) {
+                    const uint64_t y = y0 + r;
+                    uint32_t ctr[4] = {(uint32_t)y, (c << 30) | (uint32_t)j, 0u, 1u << 24};
+                    philox4x32(10, ctr, k0, k1);
+                    for (uint32_t b = 0; b < 32; ++b) {
+                        const uint64_t x = 2 * (32 * j + b) + ((y + c) & 1);
+                        state[r * Lx + x] = (ctr[0] >> b) & 1u;
+                    }
+                }
+    for (uint64_t t = 0; t < nsweeps; ++t)
+        for (uint32_t c = 0; c < 2; ++c) {
+            const uint64_t q = 2 * t + c;
+            for (uint64_t r = q + 1; r + q + 1 < nrows; ++r)
+                for (uint64_t j = 0; j < Wr; ++j) {
+                    const uint64_t y = y0 + r;
+                    int tie_rank = 0;
+                    for (uint32_t b = 0; b < 32; ++b) {
+                        const uint64_t x = 2 * (32 * j + b) + ((y + c) & 1);
+                        const uint8_t s = state[r * Lx + x];
+                        const uint8_t nb[4] = {state[r * Lx + (x + 1) % Lx], state[r * Lx + (x + Lx - 1) % Lx],
+                                               state[(r + 1) * Lx + x], state[(r - 1) * Lx + x]};
+                        int nsat = 0;
+                        for (int k = 0; k < 4; ++k) nsat += anti ? (s != nb[k]) : (s == nb[k]);
+                        const int cls = 2 * nsat - 4;
+                        if (cls <= 0) { state[r * Lx + x] ^= 1; continue; }
+                        const uint64_t T = threshold(betas[t], 2.0 * jabs * (double)cls, K);
+                        const uint32_t gw = (c << 30) | (uint32_t)j;
+                        int decided = 0, accept = 0;
+                        for (int p = 0; p < K && !decided; ++p) {
+                            const uint32_t rb = (stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)p, k0, k1) >> b) & 1u;
+                            const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
+                            if (rb != tb) { decided = 1; accept = rb < tb; }
+                        }
+                        if (!decided) {
+                            const uint32_t v = stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)(K + tie_rank), k0, k1);
+                            accept = v < (uint32_t)(T & 0xFFFFFFFFull);
+                            ++tie_rank;
+                        }
+                        if (accept) state[r * Lx + x] ^= 1;
+                    }
+                }
+        }
+    return 0;
+}

@@ -129,6 +129,7 @@ _SIGNATURES = {
     "ising_pt_get_local_states": (C.c_int, [_P, _P]),
     "ising_pt_total_swaps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ising_pt_timesteps_sample": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
+    "ising_strip_get_row_range": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
     "ising_strip_sweeps": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32]),
     "ising_strip_global_sums": (C.c_int, [_P, _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ising_pt_set_comm": (C.c_int, [_P, _P]),
@@ -579,6 +580,14 @@ class Tempering:
         check(lib().ising_pt_total_swaps(self.handle, C.byref(n)), self.ctx.handle)
         return int(n.value)
 
+    def sim_stats(self):
+        """Launch / sweep counters of the sim behind the ladder (ising_sim_stats)."""
+        sim = C.c_void_p()
+        check(lib().ising_pt_get_sim(self.handle, C.byref(sim)), self.ctx.handle)
+        st = SimStats()
+        check(lib().ising_sim_get_stats(sim, C.byref(st)), self.ctx.handle)
+        return {k: getattr(st, k) for k, _ in SimStats._fields_}
+
     def set_comm(self, comm):
         """Shards the ladder over the ranks of `comm` (this object must hold the rank's block):
         timesteps_sample then gathers energies and samples with NCCL inside the library."""
@@ -623,7 +632,8 @@ class Tempering:
 
     def timesteps_sample(self, timesteps, replica_swap_freq=1, sampling_freq=1):
         ns = int(timesteps) // int(sampling_freq) if sampling_freq else 0
-        states = PinnedPool.empty((self.R, ns, self.graph.nvars), np.bool_)
+        states = PinnedPool.empty((self.R, ns, self.graph.nvars), np.bool_) if ns else \
+            np.zeros((self.R, 0, self.graph.nvars), dtype=np.bool_)
         energies = np.empty(self.R, dtype=np.float64)
         check(lib().ising_pt_timesteps_sample(self.handle, int(timesteps), int(replica_swap_freq),
                                               int(sampling_freq), ptr(states), ptr(energies)),
@@ -723,9 +733,16 @@ class Strip:
         check(lib().ising_strip_observables(self.handle, C.byref(a), C.byref(b)), self.ctx.handle)
         return int(a.value), int(b.value)
 
-    def rows(self):
-        out = np.empty((self.row_hi - self.row_lo, self.Lx), dtype=np.bool_)
-        check(lib().ising_strip_get_rows(self.handle, ptr(out)), self.ctx.handle)
+    def rows(self, r0=None, r1=None):
+        """bool[rows, Lx] of all local rows, or of the local rows [r0, r1)."""
+        if r0 is None and r1 is None:
+            out = np.empty((self.row_hi - self.row_lo, self.Lx), dtype=np.bool_)
+            check(lib().ising_strip_get_rows(self.handle, ptr(out)), self.ctx.handle)
+            return out
+        r0 = 0 if r0 is None else int(r0)
+        r1 = self.row_hi - self.row_lo if r1 is None else int(r1)
+        out = np.empty((r1 - r0, self.Lx), dtype=np.bool_)
+        check(lib().ising_strip_get_row_range(self.handle, r0, r1, ptr(out)), self.ctx.handle)
         return out
 
     def stats(self, reset=False):

@@ -110,11 +110,13 @@ extern "C" int ising_comm_create(ising_ctx* ctx, const uint8_t* id_bytes, int ra
     c->world = world;
     NCCL_TRY(ctx, n.CommInitRank(&c->comm, world, id, rank));
     *out = c.release();
+    ctx_retain(ctx);
     return ISING_OK;
 }
 
 extern "C" void ising_comm_destroy(ising_comm* c) {
     if (!c) return;
+    struct Release { ising_ctx* c; ~Release() { ctx_release(c); } } _rel{c->ctx};   // after the lock is gone
     CtxLock _lk(c->ctx);
     if (c->comm) {
         cudaSetDevice(c->ctx->device);

@@ -132,7 +132,18 @@ static int ctx_create_impl(int device, cudaStream_t external, bool use_external,
 
 extern "C" void ising_ctx_destroy(ising_ctx* ctx) {
     if (!ctx) return;
+    bool now;
+    {
+        std::lock_guard<std::recursive_mutex> g(ctx->mu);
+        ctx->destroy_requested = true;
+        now = ctx->children == 0;
+    }
+    if (now) ctx_really_destroy(ctx);
+}
+
+void ctx_really_destroy(ising_ctx* ctx) {
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int b = 0; b < 2; ++b) {
@@ -350,6 +361,7 @@ extern "C" int ising_graph_from_edges(ising_ctx* ctx, uint64_t nvars, uint64_t n
     const int rc = upload_stencil_masks(ctx, g.get());
     if (rc) return rc;
     *out = g.release();
+    ctx_retain(ctx);
     return ISING_OK;
 }
 
@@ -366,12 +378,15 @@ extern "C" int ising_graph_torus(ising_ctx* ctx, int dim, const uint64_t* L, dou
     const int rc = upload_stencil_masks(ctx, g.get());
     if (rc) return rc;
     *out = g.release();
+    ctx_retain(ctx);
     return ISING_OK;
 }
 
 extern "C" void ising_graph_destroy(ising_graph* g) {
-    CtxLock _lk(g ? g->ctx : nullptr);
     if (!g) return;
+    ising_ctx* owner = g->ctx;
+    struct Release { ising_ctx* c; ~Release() { ctx_release(c); } } _rel{owner};   // after the lock is gone
+    CtxLock _lk(owner);
     if (g->ctx) cudaSetDevice(g->ctx->device);
     cudaFree(g->d_jmask);
     cudaFree(g->d_jmask8);

@@ -31,6 +31,11 @@ struct ising_ctx {
     // ctypes releases the GIL (the pyo3 reference holds it, so its calls were serialised too).
     // Recursive because entry points are built from each other (create -> randomize, ...).
     std::recursive_mutex mu;
+    // Objects created from a context (graphs, sims, ladders, strips, communicators) keep it alive:
+    // ising_ctx_destroy with live children only marks the context, the last child to go frees it.
+    // Host languages with garbage collection destroy handles in no particular order.
+    int children = 0;
+    bool destroy_requested = false;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
@@ -112,6 +117,22 @@ struct ising_sim {
 };
 
 int fail(ising_ctx* ctx, int code, const char* fmt, ...);
+
+void ctx_really_destroy(ising_ctx* ctx);   // api_core.cu
+inline void ctx_retain(ising_ctx* ctx) {
+    if (!ctx) return;
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
+    ++ctx->children;
+}
+inline void ctx_release(ising_ctx* ctx) {
+    if (!ctx) return;
+    bool last;
+    {
+        std::lock_guard<std::recursive_mutex> g(ctx->mu);
+        last = --ctx->children == 0 && ctx->destroy_requested;
+    }
+    if (last) ctx_really_destroy(ctx);
+}
 
 struct CtxLock {
     ising_ctx* c;

@@ -303,6 +303,7 @@ extern "C" int ising_pt_create(ising_ctx* ctx, const ising_graph* g, const doubl
     if (rc == ISING_OK) rc = pt_push_state(pt.get());
     if (rc) return bail(rc);
     *out = pt.release();
+    ctx_retain(ctx);
     return ISING_OK;
 }
 
@@ -325,8 +326,9 @@ extern "C" int ising_pt_set_comm(ising_pt* pt, ising_comm* comm) {
 }
 
 extern "C" void ising_pt_destroy(ising_pt* pt) {
-    CtxLock _lk(pt ? pt->ctx : nullptr);
     if (!pt) return;
+    struct Release { ising_ctx* c; ~Release() { ctx_release(c); } } _rel{pt->ctx};   // after the lock is gone
+    CtxLock _lk(pt->ctx);
     cudaSetDevice(pt->ctx->device);
     cudaStreamSynchronize(pt->ctx->stream);
     pt_free_device(pt);

@@ -66,6 +66,7 @@ extern "C" int ising_sim_create_ex(ising_ctx* ctx, const ising_graph* g, uint64_
     }
     s->d_counts = (unsigned long long*)p;
     *out = s.release();
+    ctx_retain(ctx);
     return ising_sim_randomize(*out);
 }
 
@@ -76,8 +77,9 @@ extern "C" int ising_sim_create(ising_ctx* ctx, const ising_graph* g, uint64_t E
 }
 
 extern "C" void ising_sim_destroy(ising_sim* s) {
-    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return;
+    struct Release { ising_ctx* c; ~Release() { ctx_release(c); } } _rel{s->ctx};   // after the lock is gone
+    CtxLock _lk(s->ctx);
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     ctx_buf_put(s->ctx, s->d_spins, s->spins_bytes);

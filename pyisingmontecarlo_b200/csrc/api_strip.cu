@@ -54,6 +54,7 @@ extern "C" int ising_strip_create_ex(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, u
     s->launches++;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *out = s.release();
+    ctx_retain(ctx);
     return ISING_OK;
 }
 
@@ -64,8 +65,9 @@ extern "C" int ising_strip_create(ising_ctx* ctx, uint64_t Lx, uint64_t Ly, uint
 }
 
 extern "C" void ising_strip_destroy(ising_strip* s) {
-    CtxLock _lk(s ? s->ctx : nullptr);
     if (!s) return;
+    struct Release { ising_ctx* c; ~Release() { ctx_release(c); } } _rel{s->ctx};   // after the lock is gone
+    CtxLock _lk(s->ctx);
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     ctx_buf_put(s->ctx, s->d_spins, s->bytes);
@@ -405,6 +407,25 @@ extern "C" int ising_strip_get_rows(ising_strip* s, uint8_t* rows_out) {
     void* dv = nullptr;
     CUDA_TRY(ctx, ctx_scratch(ctx, 0, bytes, &dv));
     if (launch_strip_unpack(s->d_spins, s->g, (uint8_t*)dv, ctx->stream) < 0)
+        return fail(ctx, ISING_E_CUDA, "strip unpack launch failed");
+    s->launches++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISING_OK;
+}
+
+// local rows [r0, r1) only (a band of a lattice too large to read back whole)
+extern "C" int ising_strip_get_row_range(ising_strip* s, uint64_t r0, uint64_t r1, uint8_t* rows_out) {
+    CtxLock _lk(s ? s->ctx : nullptr);
+    if (!s || !rows_out) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "bad argument");
+    if (r0 > r1 || r1 > s->g.rows) return fail(s->ctx, ISING_E_INVALID, "bad row range");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)(r1 - r0) * s->Lx;
+    if (bytes == 0) return ISING_OK;
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, bytes, &dv));
+    if (launch_strip_unpack(s->d_spins, s->g, (uint8_t*)dv, ctx->stream, (uint32_t)r0, (uint32_t)(r1 - r0)) < 0)
         return fail(ctx, ISING_E_CUDA, "strip unpack launch failed");
     s->launches++;
     CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, dv, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -223,8 +223,9 @@ int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0,
 // acc[0] += satisfied bonds seen from colour-0 sites (every bond once), acc[1] += up spins
 int launch_strip_observables(const uint32_t* spins, const StripGeom& g, uint32_t antiferro,
                              unsigned long long* acc, cudaStream_t st);
-// bool rows [rows][Lx] from the packed strip
-int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st);
+// bool rows [nrows][Lx] of local rows l0 .. l0 + nrows - 1 from the packed strip (default: all)
+int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st,
+                        uint32_t l0 = 0, uint32_t nrows = 0xFFFFFFFFu);
 
 struct ReplayArgs {
     uint64_t E, N, A;

@@ -145,12 +145,12 @@ int launch_strip_observables(const uint32_t* spins, const StripGeom& g, uint32_t
 }
 
 __global__ void k_strip_unpack(const uint32_t* __restrict__ spins, StripGeom g,
-                               uint8_t* __restrict__ out) {
+                               uint8_t* __restrict__ out, uint32_t l0, uint32_t nrows) {
     const uint64_t Lx = 64ull * g.Wr;
-    const uint64_t total = (uint64_t)g.rows * Lx;
+    const uint64_t total = (uint64_t)nrows * Lx;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(i / Lx) + g.ghost;
+        const uint32_t r = (uint32_t)(i / Lx) + l0 + g.ghost;
         const uint32_t x = (uint32_t)(i % Lx);
         const uint32_t y = g.row0 + r - g.ghost;
         const uint32_t c = (x + y) & 1u, xh = x >> 1;
@@ -158,8 +158,10 @@ __global__ void k_strip_unpack(const uint32_t* __restrict__ spins, StripGeom g,
     }
 }
 
-int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st) {
-    k_strip_unpack<<<device_sms() * 8, 256, 0, st>>>(spins, g, out_dev);
+int launch_strip_unpack(const uint32_t* spins, const StripGeom& g, uint8_t* out_dev, cudaStream_t st,
+                        uint32_t l0, uint32_t nrows) {
+    if (nrows == 0xFFFFFFFFu) nrows = g.rows - l0;
+    k_strip_unpack<<<device_sms() * 8, 256, 0, st>>>(spins, g, out_dev, l0, nrows);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

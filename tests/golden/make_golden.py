@@ -51,7 +51,7 @@ def main():
         for beta in (0.3, 0.4, 0.44, 0.5):
             e, c = kaufman(beta, L)
             out["kaufman"][f"L{L}_b{beta}"] = {"L": L, "beta": beta, "e_per_site": e, "c_per_site": c}
-    for beta in (0.30, 0.40, 0.43, 0.44, 0.45, 0.46, 0.48, 0.50, 0.60):
+    for beta in (0.30, 0.40, 0.42, 0.43, 0.44, 0.45, 0.46, 0.48, 0.50, 0.60):
         e, m = onsager(beta)
         out["onsager"][f"b{beta}"] = {"beta": beta, "e_per_site": e, "m": m}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "exact_2d_ising.json")

@@ -299,6 +299,19 @@ def msc_mirror_pt(a, b, j, nvars, colors, betas, seed, timesteps, replica_swap_f
     return states.astype(bool), energies, int(swaps.value), slots
 
 
+def msc_mirror_single_band(Lx, y0, nrows, j, seed, betas, planes=6, rounds=7):
+    """Rows y0 .. y0 + nrows - 1 of a large lattice from its Philox initial state; after len(betas)
+    sweeps the rows [2 n, nrows - 2 n) of the result equal the full lattice's (msc_mirror.c)."""
+    betas = np.ascontiguousarray(betas, dtype=np.float64)
+    st = np.zeros((nrows, Lx), dtype=np.uint8)
+    fn = lib().msc_mirror_single_band
+    fn.restype = C.c_int
+    fn.argtypes = [_U64, _U64, _U64, C.c_double, _U64, C.c_int, C.c_int, C.c_int, _P, _U64, _P]
+    rc = fn(Lx, y0, nrows, float(j), int(seed), planes, rounds, 1, _p(betas), len(betas), _p(st))
+    assert rc == 0, rc
+    return st.astype(bool)
+
+
 def msc_mirror_single(Lx, Ly, j, seed, betas, planes=6, rounds=7, state=None):
     """One bit-packed 2D lattice as the device runs it (oracle/msc_mirror.c: msc_mirror_single)."""
     betas = np.ascontiguousarray(betas, dtype=np.float64)

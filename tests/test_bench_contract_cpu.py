@@ -20,7 +20,7 @@ def test_reference_arm_prints_the_contract_line(oracle):
     assert d["impl"] == "reference" and d["metric"] == "spin_flip_attempts_per_sec" and d["unit"] == "flips/s"
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
-    assert d["scaling"] == "weak" and isinstance(d["dtype"], str) and "workload" in d["config"]
+    assert d["scaling"] == "strong" and isinstance(d["dtype"], str) and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     e2e = d["e2e"]
