@@ -29,6 +29,11 @@ import time
 
 import numpy as np
 
+# the contract is ONE line on stdout: keep NCCL's "NCCL version ..." banner (printed to stdout at
+# NCCL_DEBUG=VERSION, which some launchers export) out of it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:

@@ -66,8 +66,8 @@ want = [
 idx = {h: i for i, h in enumerate(hdr)}
 with open(os.path.join(out_dir, f"{tag}_sweep_metrics.md"), "w") as f:
     f.write(f"# {tag}: ncu --set full of the sweep kernel (one capture per distinct kernel)\n\n")
-    f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:k_sweep_stencil -s 6 -c 4 "
-            "python bench.py --steps 1 --warmup 1 --sweeps 20 --no-cpu-baseline` on one B200.  ncu flushes caches "
+    f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:k_sweep_rows -s 4 -c 4 "
+            "python profiles/scripts/prof_c3.py 7 6` on one B200.  ncu flushes caches "
             "between replays, so `dram__bytes_read` is the cold-cache figure (whole state + couplings); in the "
             "benchmark loop the 32 MiB state stays in L2.\n\n")
     seen = set()

@@ -5,7 +5,7 @@ import secrets
 import numpy as np
 
 from . import _native as nat
-from .lattice import _edges_to_arrays
+from .lattice import _edges_to_arrays, warn_non_basic_moves
 
 _U64 = 2**64 - 1
 
@@ -68,6 +68,7 @@ class ClassicIsing:
     def run_monte_carlo(self, beta, timesteps, nspinupdates=None, nedgeupdates=None, nwormupdates=None,
                         only_basic_moves=None):
         """classicising.rs:88-110: advances every experiment, returns nothing."""
+        warn_non_basic_moves(only_basic_moves if only_basic_moves is not None else self._use_basic_moves)
         self._check_moves(nspinupdates, nedgeupdates, nwormupdates)
         self._sim.sweeps(np.full(int(timesteps), float(beta)))
 

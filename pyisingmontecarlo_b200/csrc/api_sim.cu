@@ -274,7 +274,8 @@ static int sim_energy_real(ising_sim* s, double* d_tmp /* [32 W] */) {
     return ISING_OK;
 }
 
-static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr) {
+static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr,
+                         uint32_t nsat_copies = 1) {
     if (s->real) return sim_one_sweep_real(s, beta);
     if (s->general) return sim_one_sweep_general(s, beta);
     ising_ctx* ctx = s->ctx;
@@ -295,6 +296,8 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
     if (s->perbeta) memset(&a.th, 0, sizeof a.th);
     else fill_thresholds(h, beta, s->planes, &a.th);
     a.nsat_out = nsat_out;
+    a.nsat_copies = nsat_copies;
+    a.nsat_stride = s->lay.W * 32;
     a.tplane = s->perbeta ? s->d_tplane : nullptr;
     a.tlow = s->perbeta ? s->d_tlow : nullptr;
     const int n = launch_sweep_stencil(a, ctx->stream);
@@ -311,7 +314,8 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
 // Launch-bound sizes: a whole chunk of sweeps in one cooperative launch.  Returns 1 when done
 // that way, 0 when the caller should fall back to per-phase launches, < 0 on error (rc in *err).
 static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsigned long long* hist,
-                           int* err) {
+                           int* err, uint32_t hist_stride = 0) {
+    if (hist_stride == 0) hist_stride = s->lay.W * 32;   // words of history per sweep
     *err = ISING_OK;
     if (s->general || s->real || nt == 0) return 0;
     if (s->perbeta && (hist || s->planes != 6)) return 0;
@@ -350,8 +354,8 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     static const bool no_cluster = getenv("ISING_NO_CLUSTER") != nullptr;  // A/B knob
     int rc = 0;
     if (!no_cluster) {
-        rc = launch_sweeps_stencil_cluster(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
-                                           (uint32_t)(s->lay.W * 32), ctx->stream);
+        rc = launch_sweeps_stencil_cluster(a, (const MscThresholds*)dv, (uint32_t)nt, hist, hist_stride,
+                                           ctx->stream);
         if (rc < 0) {
             cudaGetLastError();
             rc = 0;
@@ -362,8 +366,8 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
     // sweep) 13.6 us.  ISING_COOP=1 keeps the cooperative kernel reachable for A/B runs.
     static const bool use_coop = getenv("ISING_COOP") != nullptr;
     if (rc == 0 && use_coop && !s->perbeta && !(hist && s->lay.W > 8))
-        rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist,
-                                        (uint32_t)(s->lay.W * 32), ctx->stream);
+        rc = launch_sweeps_stencil_coop(a, (const MscThresholds*)dv, (uint32_t)nt, hist, hist_stride,
+                                        ctx->stream);
     if (rc < 0) {
         cudaGetLastError();
         return 0;  // e.g. too many blocks to be co-resident: use the per-phase launches
@@ -465,10 +469,15 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     // double[E, nsweeps] there, one D2H per chunk
     const uint64_t chunk_max = 2048;
     const size_t cw = (size_t)s->lay.W * 32;
+    // lattices: several copies of a sweep's counters, so that the blocks of the accumulating
+    // phase do not serialise their atomics on W * 32 addresses (SweepArgs::nsat_copies)
+    const uint32_t copies = (s->general || s->real) ? 1u
+                            : (uint32_t)std::max<size_t>(1, std::min<size_t>(16, 4096 / std::max<size_t>(cw, 1)));
+    const size_t hstride = cw * copies;   // words of history per sweep
     unsigned long long* d_hist = nullptr;
     double* d_out = nullptr;
     void* sp = nullptr;
-    CUDA_TRY(ctx, ctx_scratch(ctx, 1, cw * std::min(chunk_max, nsweeps) * sizeof(unsigned long long), &sp));
+    CUDA_TRY(ctx, ctx_scratch(ctx, 1, hstride * std::min(chunk_max, nsweeps) * sizeof(unsigned long long), &sp));
     d_hist = (unsigned long long*)sp;
     CUDA_TRY(ctx, ctx_scratch(ctx, 2, (size_t)E * std::min(chunk_max, nsweeps) * sizeof(double), &sp));
     d_out = (double*)sp;
@@ -477,14 +486,14 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
     for (uint64_t t0 = 0; t0 < nsweeps && rc == ISING_OK; t0 += chunk_max) {
         const uint64_t nt = std::min(chunk_max, nsweeps - t0);
         cudaEventRecord(ctx->ev0, ctx->stream);
-        cudaMemsetAsync(d_hist, 0, cw * nt * sizeof(unsigned long long), ctx->stream);
+        cudaMemsetAsync(d_hist, 0, hstride * nt * sizeof(unsigned long long), ctx->stream);
         // the second colour phase of every sweep adds its post-flip satisfied-bond counts
         // into that sweep's slot of the history (fused, no separate energy pass)
         int coop_err = ISING_OK;
-        const int coop = betas ? sim_sweeps_coop(s, betas + t0, nt, d_hist, &coop_err) : 0;
+        const int coop = betas ? sim_sweeps_coop(s, betas + t0, nt, d_hist, &coop_err, (uint32_t)hstride) : 0;
         if (coop < 0) rc = coop_err;
         for (uint64_t t = 0; coop == 0 && t < nt && rc == ISING_OK; ++t) {
-            rc = sim_one_sweep(s, betas ? betas[t0 + t] : 0.0, d_hist + t * cw);
+            rc = sim_one_sweep(s, betas ? betas[t0 + t] : 0.0, d_hist + t * hstride, copies);
             if (rc == ISING_OK && s->real) {
                 rc = sim_energy_real(s, reinterpret_cast<double*>(d_hist + t * cw));
             } else if (rc == ISING_OK && s->general) {  // no fused accumulation on general graphs
@@ -500,7 +509,7 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
                                                       d_out, ctx->stream));
         else if (rc == ISING_OK)
             count_launch(s, launch_energy_from_hist(d_hist, E, cw, nt, h.jabs, h.nedges, mult,
-                                                    d_out, ctx->stream));
+                                                    d_out, ctx->stream, copies));
         cudaEventRecord(ctx->ev1, ctx->stream);
         if (rc != ISING_OK) break;
         // rows [e][t0 .. t0 + nt) straight into the caller's double[E, nsweeps] (strided copy)

@@ -74,20 +74,22 @@ __global__ void k_energy_from_nsat(const unsigned long long* __restrict__ nsat, 
 // energies[e * nt + t] = scale * (nbonds - 2 * hist[t * cw + e]) for a chunk of nt sweeps
 __global__ void k_energy_from_hist(const unsigned long long* __restrict__ hist, uint64_t E,
                                    uint64_t cw, uint64_t nt, double scale, uint64_t nbonds,
-                                   int mult, double* __restrict__ out) {
+                                   int mult, double* __restrict__ out, uint32_t copies) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E * nt) return;
     const uint64_t e = i / nt, t = i - e * nt;
-    const long long v = (long long)nbonds - (long long)mult * (long long)hist[t * cw + e];
+    unsigned long long n = 0;
+    for (uint32_t c = 0; c < copies; ++c) n += hist[(t * copies + c) * cw + e];
+    const long long v = (long long)nbonds - (long long)mult * (long long)n;
     out[i] = scale * (double)v;
 }
 
 int launch_energy_from_hist(const unsigned long long* hist, uint64_t E, uint64_t cw, uint64_t nt,
                             double scale, uint64_t nbonds, int mult, double* out_dev,
-                            cudaStream_t st) {
+                            cudaStream_t st, uint32_t copies) {
     const uint64_t n = E * nt;
     const unsigned g = (unsigned)((n + 255) / 256);
-    k_energy_from_hist<<<g ? g : 1, 256, 0, st>>>(hist, E, cw, nt, scale, nbonds, mult, out_dev);
+    k_energy_from_hist<<<g ? g : 1, 256, 0, st>>>(hist, E, cw, nt, scale, nbonds, mult, out_dev, copies);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -77,6 +77,7 @@ struct RowsArgs {
     uint32_t units;         // tiles * Lz * ygroups, tile = wt * xtiles + xt slowest
     uint32_t uq, urem;      // units = uq * gridDim.x + urem: block b gets uq (+1 if b < urem) units
     unsigned long long* nsat;
+    uint32_t nsat_copies, nsat_stride;   // blocks add into copy (block % copies), see SweepArgs
     PhiloxKeys pk;
     MscMux mx;
 };
@@ -374,6 +375,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
 #pragma unroll
         for (int v = 0; v < V; ++v) vc[v].clear();
     }
+    unsigned long long* const nsat = ACC ? a.nsat + (size_t)(blockIdx.x % a.nsat_copies) * a.nsat_stride : nullptr;
     int pending = 0;
     uint32_t cur_tile = 0xFFFFFFFFu;
     uint32_t w = 0, xh2 = 0, toff = 0, offP = 0, offM = 0, xsite = 0;
@@ -418,7 +420,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
             if (tile != cur_tile) {
                 if constexpr (ACC) {
                     if (pending) {
-                        block_reduce_vcount<SW_NP, V>(vc, sm, a.nsat, (cur_tile / a.xtiles) * wx * V, W);
+                        block_reduce_vcount<SW_NP, V>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
 #pragma unroll
                         for (int v = 0; v < V; ++v) vc[v].clear();
                         pending = 0;
@@ -499,7 +501,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
             }
             if constexpr (ACC) {
                 if (++pending == SW_MAX_ITEMS) {  // counters full: reduce and start over
-                    block_reduce_vcount<SW_NP, V>(vc, sm, a.nsat, (cur_tile / a.xtiles) * wx * V, W);
+                    block_reduce_vcount<SW_NP, V>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
 #pragma unroll
                     for (int v = 0; v < V; ++v) vc[v].clear();
                     pending = 0;
@@ -508,7 +510,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
         }
     }
     if constexpr (ACC) {
-        if (pending) block_reduce_vcount<SW_NP, V>(vc, sm, a.nsat, (cur_tile / a.xtiles) * wx * V, W);
+        if (pending) block_reduce_vcount<SW_NP, V>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
     }
 }
 
@@ -665,6 +667,7 @@ __device__ __forceinline__ void sweep_rows_tma_phase(const RowsTmaArgs& ta, unsi
         for (int v = 0; v < V; ++v) vc[v].clear();
     }
     int pending = 0;
+    unsigned long long* const nsat = ACC ? a.nsat + (size_t)(blockIdx.x % a.nsat_copies) * a.nsat_stride : nullptr;
     uint32_t* red = reinterpret_cast<uint32_t*>(smem + NSTAGE * ta.stage_bytes);  // ACC: block reduction area
 
     for (uint32_t k = 0; k < nsteps; ++k) {
@@ -713,7 +716,7 @@ __device__ __forceinline__ void sweep_rows_tma_phase(const RowsTmaArgs& ta, unsi
         }
         if constexpr (ACC) {
             if (++pending == SW_MAX_ITEMS) {
-                block_reduce_vcount<SW_NP, V>(vc, red, a.nsat, 0u, W);
+                block_reduce_vcount<SW_NP, V>(vc, red, nsat, 0u, W);
 #pragma unroll
                 for (int v = 0; v < V; ++v) vc[v].clear();
                 pending = 0;
@@ -721,7 +724,7 @@ __device__ __forceinline__ void sweep_rows_tma_phase(const RowsTmaArgs& ta, unsi
         }
     }
     if constexpr (ACC) {
-        if (pending) block_reduce_vcount<SW_NP, V>(vc, red, a.nsat, 0u, W);
+        if (pending) block_reduce_vcount<SW_NP, V>(vc, red, nsat, 0u, W);
     }
 }
 

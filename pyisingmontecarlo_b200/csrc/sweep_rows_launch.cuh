@@ -165,6 +165,8 @@ static int rows_phase(const SweepArgs& a, cudaStream_t st, uint32_t c, int mode)
     ra.Lx = L.Lx; ra.Ly = L.Ly; ra.Lz = L.Lz; ra.Lxh = L.Lxh; ra.W = L.W;
     ra.c = c; ra.sweep = a.sweep; ra.gw0 = a.gw0; ra.antiferro = a.antiferro;
     ra.nsat = acc ? a.nsat_out : nullptr;
+    ra.nsat_copies = a.nsat_copies ? a.nsat_copies : 1;
+    ra.nsat_stride = a.nsat_stride;
     ra.pk = philox_round_keys(a.key0, a.key1);
     ra.mx = make_mux(a.th);
     ra.bxh_log = log2_exact(sh.bxh);

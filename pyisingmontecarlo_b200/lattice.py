@@ -10,12 +10,29 @@ reference.  Documented deviations of the GPU path:
       attempts at uniformly random sites: same Boltzmann law, different transient.
 """
 import secrets
+import warnings
 
 import numpy as np
 
 from . import _native as nat
 
 _U64 = 2**64 - 1
+_warned_basic_moves = False
+
+
+def warn_non_basic_moves(only_basic_moves):
+    """Deviation D1, said out loud once per process: with only_basic_moves None / False the
+    reference's timestep also performs two-spin edge flips and worm updates (lattice.rs:205,
+    classicising.rs:100-106; their rules live in the out-of-tree `qmc` crate).  The GPU path
+    performs single-spin Metropolis sweeps - the same Boltzmann distribution, other dynamics."""
+    global _warned_basic_moves
+    if only_basic_moves or _warned_basic_moves:
+        return
+    _warned_basic_moves = True
+    warnings.warn("only_basic_moves is None/False: the reference would also perform edge-flip and worm "
+                  "moves in each timestep; the B200 engine performs single-spin Metropolis sweeps only "
+                  "(same equilibrium distribution, different dynamics; see DESIGN.md deviation D1). "
+                  "Pass only_basic_moves=True to state that this is what you want.", UserWarning, stacklevel=3)
 
 
 def _edges_to_arrays(edges):
@@ -222,7 +239,10 @@ class Lattice:
     # ---- classical runs, lattice.rs:163-470 -------------------------------------------------
     def run_monte_carlo(self, beta, timesteps, num_experiments, only_basic_moves=None,
                         edge_move_importance_sampling=None):
-        """lattice.rs:171-221 -> (energies float64[E], states bool[E, nvars])"""
+        """lattice.rs:171-221 -> (energies float64[E], states bool[E, nvars])
+
+        only_basic_moves=None/False: single-spin sweeps all the same (deviation D1, warned once)."""
+        warn_non_basic_moves(only_basic_moves)
         flags = self._check_classical(edge_move_importance_sampling)
         energies = np.zeros(num_experiments, dtype=np.float64)
         states = nat.PinnedPool.empty((num_experiments, self.nvars), np.bool_)
@@ -234,6 +254,7 @@ class Lattice:
                                  thermalization_time=None, sampling_freq=None,
                                  edge_move_importance_sampling=None):
         """lattice.rs:231-299 -> (energies float64[E, n_s], states bool[E, n_s, nvars])"""
+        warn_non_basic_moves(only_basic_moves)
         flags = self._check_classical(edge_move_importance_sampling)
         thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
         sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
@@ -290,12 +311,14 @@ class Lattice:
     def run_monte_carlo_annealing(self, betas, timesteps, num_experiments, only_basic_moves=None,
                                   edge_move_importance_sampling=None):
         """lattice.rs:309-385 -> (energies float64[E], states bool[E, nvars])"""
+        warn_non_basic_moves(only_basic_moves)
         return self._annealing(betas, timesteps, num_experiments, edge_move_importance_sampling, False)
 
     def run_monte_carlo_annealing_and_get_energies(self, betas, timesteps, num_experiments,
                                                    only_basic_moves=None,
                                                    edge_move_importance_sampling=None):
         """lattice.rs:395-470 -> (energies float64[E, timesteps], states bool[E, nvars])"""
+        warn_non_basic_moves(only_basic_moves)
         return self._annealing(betas, timesteps, num_experiments, edge_move_importance_sampling, True)
 
     # ---- replay mode (north-star correctness check 1) -----------------------------------------

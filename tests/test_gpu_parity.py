@@ -459,3 +459,22 @@ def test_tma_staged_kernel_matches_direct_loads(native):
         assert len(res["direct"]) == len(res["tma"]) == 9
         for x, y in zip(res["direct"], res["tma"]):
             assert x.shape == y.shape and (x == y).all()
+
+
+def test_default_moves_warn_once(pkg, oracle):
+    """only_basic_moves=None/False (the reference's default) runs single-spin sweeps and says so
+    once per process (deviation D1); only_basic_moves=True is silent."""
+    import warnings
+
+    from pyisingmontecarlo_b200 import lattice as lattice_mod
+
+    lat = pkg.Lattice(oracle.square_edges(4), seed_gen=1)
+    lattice_mod._warned_basic_moves = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        lat.run_monte_carlo(0.4, 2, 4, True)            # explicit: no warning
+    with pytest.warns(UserWarning, match="single-spin Metropolis"):
+        lat.run_monte_carlo(0.4, 2, 4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        lat.run_monte_carlo(0.4, 2, 4)                  # once per process
