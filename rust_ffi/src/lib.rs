@@ -17,6 +17,10 @@ pub struct ising_sim {
     _p: [u8; 0],
 }
 #[repr(C)]
+pub struct ising_comm {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct ising_pt {
     _p: [u8; 0],
 }
@@ -104,6 +108,16 @@ extern "C" {
         energies: *mut f64,
     ) -> c_int;
     pub fn ising_pt_total_swaps(pt: *const ising_pt, out: *mut u64) -> c_int;
+    pub fn ising_pt_get_pair_stats(pt: *const ising_pt, attempts: *mut u64, accepts: *mut u64) -> c_int;
+    // multi-GPU: NCCL communicator owned by the library (one process per GPU); only the
+    // ISING_COMM_ID_BYTES = 128 bytes of the unique id travel through the host program
+    pub fn ising_comm_unique_id(out: *mut u8, capacity: u64) -> c_int;
+    pub fn ising_comm_create(
+        ctx: *mut ising_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut ising_comm,
+    ) -> c_int;
+    pub fn ising_comm_destroy(comm: *mut ising_comm);
+    pub fn ising_comm_info(comm: *const ising_comm, rank: *mut c_int, world: *mut c_int) -> c_int;
+    pub fn ising_pt_set_comm(pt: *mut ising_pt, comm: *mut ising_comm) -> c_int;
 }
 
 /// Owns a context + compiled graph; one per `Lattice` (rebuilt when biases change).
