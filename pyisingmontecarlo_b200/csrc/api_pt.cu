@@ -168,6 +168,7 @@ struct ising_pt {
     double* d_e_local = nullptr;      // [32 W] energies of the locally held replica bits
     double* d_e_all = nullptr;        // [world * cmax] gathered, rank-major
     double* d_acc = nullptr;          // [R] sum of E * t by slot
+    unsigned long long* d_nsat = nullptr;   // [32 W] satisfied-bond counters of the cycle (kept zeroed by k_pt_cycle)
     unsigned long long* d_stats = nullptr;
     uint64_t cmax = 0;                // configurations per rank in the gathered arrays
     int world = 1, rank = 0;
@@ -244,6 +245,7 @@ static void pt_free_device(ising_pt* pt) {
     cudaFree(pt->d_e_local);
     cudaFree(pt->d_e_all);
     cudaFree(pt->d_acc);
+    cudaFree(pt->d_nsat);
     cudaFree(pt->d_stats);
 }
 
@@ -291,6 +293,8 @@ extern "C" int ising_pt_create(ising_ctx* ctx, const ising_graph* g, const doubl
     if (e == cudaSuccess) e = dev_alloc(&pt->d_e_local, e32 + nbetas);
     if (e == cudaSuccess) e = dev_alloc(&pt->d_acc, nbetas);
     if (e == cudaSuccess) e = dev_alloc(&pt->d_stats, pt->stats.size());
+    if (e == cudaSuccess) e = dev_alloc(&pt->d_nsat, e32);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pt->d_nsat, 0, e32 * sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(pt->d_acc, 0, nbetas * sizeof(double), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(pt->d_e_local, 0, (e32 + nbetas) * sizeof(double), ctx->stream);
     if (e == cudaSuccess)
@@ -345,21 +349,6 @@ extern "C" int ising_pt_configure(ising_pt* pt, int planes, int rounds) {
     if (rc) return rc;
     rc = sim_set_slot_thresholds(pt->sim, pt->betas.data(), pt->R);   // thresholds depend on the plane count
     return rc ? rc : pt_push_state(pt);
-}
-
-// energies of every configuration into d_e_all (gathered layout), enqueue only
-static int pt_gather_energies(ising_pt* pt) {
-    ising_ctx* ctx = pt->ctx;
-    int rc = sim_energies_to_device(pt->sim, pt->d_e_local, 1, 0);
-    if (rc) return rc;
-    const double* mine = pt->d_e_local + (pt->lo - pt->word_lo * 32);   // owned configurations
-    if (pt->comm && pt->world > 1)
-        return comm_allgather_bytes(pt->comm, mine, pt->d_e_all, pt->cmax * sizeof(double), ctx->stream);
-    if (pt->world == 1 && pt->lo == 0 && pt->hi == pt->R) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(pt->d_e_all, mine, pt->R * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        return ISING_OK;
-    }
-    return fail(ctx, ISING_E_INVALID, "a sharded ladder needs a communicator (ising_pt_set_comm)");
 }
 
 extern "C" int ising_pt_sweeps(ising_pt* pt, uint64_t t, double* local_energies) {
@@ -423,6 +412,69 @@ static int pt_device_swap(ising_pt* pt) {
     count_launch(pt->sim, n);
     pt->host_stale = true;
     return sim_tables_from_slots(pt->sim);
+}
+
+// One launch for everything between two batches of sweeps (see k_pt_cycle); with a communicator
+// the energies are computed first, gathered, and the rest follows in one launch.
+static int pt_cycle(ising_pt* pt, uint64_t t, bool do_swap) {
+    ising_ctx* ctx = pt->ctx;
+    ising_sim* sim = pt->sim;
+    if (sim->real) return fail(ctx, ISING_E_UNSUPPORTED, "tempering needs integer energy classes");
+    const HostGraph& h = pt->g->h;
+    const bool multi = pt->comm && pt->world > 1;
+    int rc = sim_count_nsat(sim, pt->d_nsat, false);
+    if (rc) return rc;
+    PtCycleArgs a;
+    a.nsat = pt->d_nsat;
+    a.e_local = pt->d_e_local;
+    a.e_all = pt->d_e_all;
+    a.E = (uint32_t)sim->E;
+    a.e32 = sim->lay.W * 32;
+    a.identity = multi ? 0u : 1u;
+    a.scale = h.jabs;
+    a.nbonds = h.nedges;
+    a.mult = sim->general ? 1 : 2;
+    a.gidx = pt->d_gidx;
+    a.betas = pt->d_betas;
+    a.slot_of_cfg = pt->d_slot_of_cfg;
+    a.cfg_of_slot = pt->d_cfg_of_slot;
+    a.R = (uint32_t)pt->R;
+    a.key0 = (uint32_t)pt->seed;
+    a.key1 = (uint32_t)(pt->seed >> 32);
+    a.stats = pt->d_stats;
+    a.slot_of_replica = sim->d_slot;
+    a.word_lo = (uint32_t)pt->word_lo;
+    a.acc = pt->d_acc;
+    a.t = (double)t;
+    a.do_swap = do_swap ? 1 : 0;
+    const bool fuse_tables = do_swap && !sim->general;
+    a.t64 = fuse_tables ? sim->d_t64 : nullptr;
+    a.W = sim->lay.W;
+    a.K = sim->planes;
+    a.tplane = sim->d_tplane;
+    a.tlow = sim->d_tlow;
+    if (multi) {
+        // energies first (no accumulate / swap: R = 0), all-gather, then the rest without the energy part
+        PtCycleArgs e = a;
+        e.R = 0;
+        e.do_swap = 0;
+        e.t64 = nullptr;
+        if (launch_pt_cycle(e, ctx->stream) < 0) return fail(ctx, ISING_E_CUDA, "tempering cycle launch failed");
+        count_launch(sim, 1);
+        const double* mine = pt->d_e_local + (pt->lo - pt->word_lo * 32);
+        rc = comm_allgather_bytes(pt->comm, mine, pt->d_e_all, pt->cmax * sizeof(double), ctx->stream);
+        if (rc) return rc;
+        a.nsat = nullptr;
+    } else if (!(pt->lo == 0 && pt->hi == pt->R)) {
+        return fail(ctx, ISING_E_INVALID, "a sharded ladder needs a communicator (ising_pt_set_comm)");
+    }
+    if (launch_pt_cycle(a, ctx->stream) < 0) return fail(ctx, ISING_E_CUDA, "tempering cycle launch failed");
+    count_launch(sim, 1);
+    if (do_swap) {
+        pt->host_stale = true;
+        if (!fuse_tables) return sim_tables_from_slots(sim);
+    }
+    return ISING_OK;
 }
 
 extern "C" int ising_pt_swap_step(ising_pt* pt, const double* all_energies) {
@@ -569,16 +621,10 @@ extern "C" int ising_pt_timesteps_sample(ising_pt* pt, uint64_t timesteps, uint6
         const uint64_t t = std::min(std::min(to_sample, to_swap), remaining);
         rc = sim_enqueue_sweeps(pt->sim, nullptr, t);
         if (rc) break;
-        rc = pt_gather_energies(pt);
-        if (rc) break;
-        count_launch(pt->sim, launch_pt_accumulate(pt->d_acc, pt->d_e_all, pt->d_gidx, pt->d_cfg_of_slot,
-                                                   (uint32_t)R, (double)t, ctx->stream));
         to_sample -= t; to_swap -= t; remaining -= t;
-        if (to_swap == 0) {
-            rc = pt_device_swap(pt);
-            if (rc) break;
-            to_swap = replica_swap_freq;
-        }
+        rc = pt_cycle(pt, t, to_swap == 0);    // energies, (all-gather,) time average, swap step, tables
+        if (rc) break;
+        if (to_swap == 0) to_swap = replica_swap_freq;
         if (to_sample == 0) {
             if (k < ns) {
                 count_launch(pt->sim, launch_unpack_states(pt->sim->d_spins, pt->sim->lay, d_rows, E, N, ctx->stream));

@@ -391,11 +391,12 @@ static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsig
 }
 
 // n_sat per experiment into s->d_counts (zeroed first)
-int sim_count_nsat(ising_sim* s, unsigned long long* d_counts) {
+int sim_count_nsat(ising_sim* s, unsigned long long* d_counts, bool zero_first) {
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
-    CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)s->lay.W * 32 * sizeof(unsigned long long),
-                                  ctx->stream));
+    if (zero_first)
+        CUDA_TRY(ctx, cudaMemsetAsync(d_counts, 0, (size_t)s->lay.W * 32 * sizeof(unsigned long long),
+                                      ctx->stream));
     if (s->general) {
         const int n = launch_nsat_general(s->d_spins, s->lay.nvars, s->lay.W, s->g->d_row32,
                                           s->g->d_nbr32, s->g->d_anti8, d_counts, ctx->stream);

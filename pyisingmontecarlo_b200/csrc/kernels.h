@@ -162,10 +162,37 @@ int launch_pt_swap(const double* betas, const double* e_all, const uint32_t* gid
                    uint32_t* slot_of_replica, uint32_t word_lo, uint32_t e32, cudaStream_t st);
 int launch_pt_local_slots(const uint32_t* slot_of_cfg, uint32_t R, uint32_t* slot_of_replica,
                           uint32_t word_lo, uint32_t e32, cudaStream_t st);
-int launch_pt_accumulate(double* acc, const double* e_all, const uint32_t* gidx, const uint32_t* cfg_of_slot,
-                         uint32_t R, double t, cudaStream_t st);
 int launch_pt_gather_rows(const uint8_t* rows, uint64_t n, const uint32_t* gidx, const uint32_t* cfg_of_slot,
                           uint32_t R, uint8_t* out, cudaStream_t st);
+
+// fused post-sweep part of a tempering cycle (one block), see pt_device.cu
+struct PtCycleArgs {
+    unsigned long long* nsat;      // [e32] local satisfied-bond counters (zeroed on exit), or nullptr
+    double* e_local;               // [e32] local energies (written when nsat != nullptr)
+    double* e_all;                 // gathered energies; written from e_local when `identity`
+    uint32_t E, e32, identity;     // local experiments; 32 W; 1: one rank holds everything (gidx = id)
+    double scale;                  // |J|
+    unsigned long long nbonds;
+    int mult;
+    const uint32_t* gidx;
+    const double* betas;
+    uint32_t* slot_of_cfg;
+    uint32_t* cfg_of_slot;
+    uint32_t R, key0, key1;
+    unsigned long long* stats;
+    uint32_t* slot_of_replica;
+    uint32_t word_lo;
+    double* acc;
+    double t;                      // sweeps since the last energies (weight of the time average)
+    int do_swap;
+    // stencil threshold tables (W * 3 rows), nullptr: the caller rebuilds tables itself
+    const unsigned long long* t64;
+    uint32_t W;
+    int K;
+    uint32_t* tplane;
+    uint32_t* tlow;
+};
+int launch_pt_cycle(const PtCycleArgs& a, cudaStream_t st);
 
 // ---- arbitrary real couplings and biases (float local field per replica bit) -----------------
 struct RealSweepArgs {

@@ -83,20 +83,6 @@ int launch_pt_local_slots(const uint32_t* slot_of_cfg, uint32_t R, uint32_t* slo
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-// acc[slot] += E(configuration at slot) * t   (tempering.rs:184-186: energy_acc[r] += te * t)
-__global__ void k_pt_accumulate(double* __restrict__ acc, const double* __restrict__ e_all,
-                                const uint32_t* __restrict__ gidx, const uint32_t* __restrict__ cfg_of_slot,
-                                uint32_t R, double t) {
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < R; s += gridDim.x * blockDim.x)
-        acc[s] = __dadd_rn(acc[s], __dmul_rn(e_all[gidx[cfg_of_slot[s]]], t));
-}
-
-int launch_pt_accumulate(double* acc, const double* e_all, const uint32_t* gidx, const uint32_t* cfg_of_slot,
-                         uint32_t R, double t, cudaStream_t st) {
-    k_pt_accumulate<<<(R + 255) / 256, 256, 0, st>>>(acc, e_all, gidx, cfg_of_slot, R, t);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
 // out[s][0..n) = rows[gidx[cfg_of_slot[s]]][0..n): the sampled states in slot order ("the
 // configuration currently at beta_s", tempering.rs:195-211); 16-byte vectors when n allows
 __global__ void __launch_bounds__(256)
@@ -123,6 +109,92 @@ int launch_pt_gather_rows(const uint8_t* rows, uint64_t n, const uint32_t* gidx,
     if (bx < 1) bx = 1;
     if (bx > device_sms() * 4u) bx = device_sms() * 4u;
     k_pt_gather_rows<<<dim3((unsigned)bx, R, 1), 256, 0, st>>>(rows, n, gidx, cfg_of_slot, R, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// The whole post-sweep part of a tempering cycle in ONE block (integer-class sims, one rank or
+// after the all-gather): energies from the satisfied-bond counters (which it zeroes for the next
+// cycle), time-averaged energies, the swap step when due, the replica -> slot map and - for the
+// checkerboard layout, whose tables are W * 3 warps of work - the bit-sliced threshold tables.
+// Replaces memset + energy + copy + accumulate + swap + tables (six launches of ~2.5 us each
+// around ten 2.8 us sweeps of an 8^3 lattice).  Same arithmetic in the same order as the separate
+// kernels, so results are bit-identical.
+// ------------------------------------------------------------------------------------------
+
+
+__global__ void __launch_bounds__(256) k_pt_cycle(const __grid_constant__ PtCycleArgs a) {
+    __shared__ unsigned int s_swaps;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_swaps = 0;
+    if (a.nsat) {
+        for (uint32_t e = tid; e < a.e32; e += blockDim.x) {
+            if (e < a.E) {
+                const long long v = (long long)a.nbonds - (long long)a.mult * (long long)a.nsat[e];
+                const double en = a.scale * (double)v;
+                a.e_local[e] = en;
+                if (a.identity) a.e_all[e] = en;
+            }
+            a.nsat[e] = 0ull;
+        }
+    }
+    __syncthreads();
+    for (uint32_t s = tid; s < a.R; s += blockDim.x)
+        a.acc[s] = __dadd_rn(a.acc[s], __dmul_rn(a.e_all[a.gidx[a.cfg_of_slot[s]]], a.t));
+    if (!a.do_swap) return;
+    __syncthreads();
+    const uint32_t swap_step = (uint32_t)a.stats[0];
+    for (uint32_t parity = 0; parity < 2; ++parity) {
+        for (uint32_t p = parity + 2 * tid; p + 1 < a.R; p += 2 * blockDim.x) {
+            const uint32_t ca = a.cfg_of_slot[p], cb = a.cfg_of_slot[p + 1];
+            const double d = __dmul_rn(__dsub_rn(a.betas[p], a.betas[p + 1]),
+                                       __dsub_rn(a.e_all[a.gidx[ca]], a.e_all[a.gidx[cb]]));
+            bool acc = true;
+            if (d < 0.0) {
+                const u32x4 r = philox4x32<10>(p, parity, swap_step, TAG_SWAP << 24, a.key0, a.key1);
+                const double uu = __dmul_rn(__dadd_rn((double)r.x, 0.5), 1.0 / 4294967296.0);
+                acc = uu < pt_exp_nonpos(d);
+            }
+            a.stats[2 + p] += 1ull;
+            if (acc) {
+                a.cfg_of_slot[p] = cb;
+                a.cfg_of_slot[p + 1] = ca;
+                a.slot_of_cfg[cb] = p;
+                a.slot_of_cfg[ca] = p + 1;
+                a.stats[2 + a.R + p] += 1ull;
+                atomicAdd(&s_swaps, 1u);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.stats[0] += 1ull;
+        a.stats[1] += (unsigned long long)s_swaps;
+    }
+    for (uint32_t e = tid; e < a.e32; e += blockDim.x) {
+        const uint32_t c = a.word_lo * 32u + e;
+        a.slot_of_replica[e] = c < a.R ? a.slot_of_cfg[c] : 0u;
+    }
+    if (!a.t64) return;
+    __syncthreads();
+    // threshold tables of the checkerboard kernels: one warp per (word, class), as k_build_tables_stencil
+    const uint32_t b = tid & 31u;
+    for (uint32_t idx = tid >> 5; idx < a.W * 3; idx += blockDim.x >> 5) {
+        const uint32_t cls = idx % 3, w = idx / 3;
+        const uint32_t e = w * 32 + b;
+        const unsigned long long T = a.t64[(size_t)a.slot_of_replica[e] * 3 + cls];
+        a.tlow[(size_t)e * 3 + cls] = (uint32_t)(T & 0xFFFFFFFFull);
+        uint32_t mine = 0;
+        for (int p = 0; p < 8; ++p) {
+            const uint32_t m = p < a.K ? __ballot_sync(0xFFFFFFFFu, (T >> (a.K + 31 - p)) & 1ull) : 0u;
+            if (b == (uint32_t)p) mine = m;
+        }
+        if (b < 8) a.tplane[((size_t)w * 3 + cls) * 8 + b] = mine;
+    }
+}
+
+int launch_pt_cycle(const PtCycleArgs& a, cudaStream_t st) {
+    k_pt_cycle<<<1, 256, 0, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -1,5 +1,5 @@
 // sm_100a kernels: one large 2D lattice bit-packed along x in row strips (K7).
-#include "msc_device.cuh"
+#include "sweep_rows.cuh"
 
 namespace ising {
 
@@ -14,12 +14,18 @@ __device__ __forceinline__ size_t strip_off(const StripGeom& g, uint32_t c, uint
     return ((size_t)c * (g.rows + 2 * g.ghost) + r) * g.Wr + j;
 }
 
-// V consecutive words of a row per thread (128-bit loads when V == 4; needs Wr % V == 0)
+// V consecutive words of a row per thread (128-bit loads when V == 4; needs Wr % V == 0).  The
+// site update is the row walk's (sweep_rows.cuh: update_site): Philox rounds 1-3 shared over the
+// V words and both calls (counter = (row, colour << 30 | word, sweep, call), i.e. the words of a
+// thread differ in counter word 1 only), threshold planes selected with IMAD, rare ties deferred.
 template <int K, int ROUNDS, int V>
-__global__ void __launch_bounds__(256)
-k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sweep, PhiloxKeys pk,
-              uint32_t antiferro, MscThresholds th, uint32_t r_begin, uint32_t r_count) {
+__global__ void __launch_bounds__(256, 3)
+k_strip_phase(uint32_t* __restrict__ spins, const __grid_constant__ StripGeom g, uint32_t c, uint32_t sweep,
+              const __grid_constant__ PhiloxKeys pk, uint32_t antiferro, const __grid_constant__ MscMux mx,
+              uint32_t r_begin, uint32_t r_count) {
     const uint32_t groups = g.Wr / V;
+    const uint32_t o = 1u - c;
+    VCount<1> unused[V];
     // block = (x over the word groups of a row, y over rows): storage rows [r_begin, r_begin + r_count)
     for (uint32_t rr = blockIdx.y * blockDim.y + threadIdx.y; rr < r_count; rr += gridDim.y * blockDim.y)
     for (uint32_t jg = blockIdx.x * blockDim.x + threadIdx.x; jg < groups; jg += gridDim.x * blockDim.x) {
@@ -27,27 +33,23 @@ k_strip_phase(uint32_t* __restrict__ spins, StripGeom g, uint32_t c, uint32_t sw
         const uint32_t r = r_begin + rr;
         const uint32_t y = strip_global_row(g, r);
         const uint32_t p = (y + c) & 1u;
-        const uint32_t o = 1u - c;
-        uint32_t s[V], nx[V], nu[V], nd[V];
-        load_words<V>(spins + strip_off(g, c, r, j), s);
-        load_words<V>(spins + strip_off(g, o, r, j), nx);
-        load_words<V>(spins + strip_off(g, o, r - 1, j), nu);
-        load_words<V>(spins + strip_off(g, o, r + 1, j), nd);
+        uint32_t s[V], n[4][V];
+        uint32_t* own = spins + strip_off(g, c, r, j);
+        const uint32_t* orow = spins + strip_off(g, o, r, 0);
+        load_words<V>(own, s);
+        load_words<V>(orow + j, n[0]);
+        load_words<V>(orow + j - g.Wr, n[2]);
+        load_words<V>(orow + j + g.Wr, n[3]);
         // the x neighbour one bit over: funnel shift with carry from the adjacent word
-        const uint32_t edge = p ? spins[strip_off(g, o, r, j + V == g.Wr ? 0 : j + V)]
-                                : spins[strip_off(g, o, r, j == 0 ? g.Wr - 1 : j - 1)];
+        const uint32_t edge = p ? orow[j + V == g.Wr ? 0 : j + V] : orow[j == 0 ? g.Wr - 1 : j - 1];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            uint32_t nsh;
-            if (p) nsh = __funnelshift_r(nx[v], v + 1 < V ? nx[v + 1 < V ? v + 1 : v] : edge, 1);
-            else nsh = __funnelshift_l(v > 0 ? nx[v > 0 ? v - 1 : 0] : edge, nx[v], 1);
-            uint32_t a[4] = {~(s[v] ^ nx[v] ^ antiferro), ~(s[v] ^ nsh ^ antiferro),
-                             ~(s[v] ^ nu[v] ^ antiferro), ~(s[v] ^ nd[v] ^ antiferro)};
-            uint32_t b0, b1, b2;
-            count_sat<2>(a, b0, b1, b2);
-            s[v] ^= msc_flip_mask<2, K, ROUNDS>(b2 | (b1 & b0), b2, 0u, th, y, (c << 30) | (j + v), sweep, pk);
+            if (p) n[1][v] = __funnelshift_r(n[0][v], v + 1 < V ? n[0][v + 1 < V ? v + 1 : v] : edge, 1);
+            else n[1][v] = __funnelshift_l(v > 0 ? n[0][v > 0 ? v - 1 : 0] : edge, n[0][v], 1);
         }
-        store_words<V>(spins + strip_off(g, c, r, j), s);
+        const uint32_t m[4] = {antiferro, antiferro, antiferro, antiferro};
+        update_site<2, K, ROUNDS, V, false>(s, n, m, y, (c << 30) | j, sweep, pk, mx, unused);
+        store_words<V>(own, s);
     }
 }
 
@@ -65,7 +67,7 @@ static int strip_phase_dispatch(const StripSweepArgs& a, cudaStream_t st) {
 #define STRIP_LAUNCH(KK, RR)                                                                     \
     k_strip_phase<KK, RR, V><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,              \
                                                      philox_round_keys(a.key0, a.key1), a.antiferro, \
-                                                     a.th, a.r_begin, a.r_count)
+                                                     make_mux(a.th), a.r_begin, a.r_count)
 #define STRIP_ROUNDS(KK)                                                                         \
     do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {

@@ -478,3 +478,41 @@ def test_default_moves_warn_once(pkg, oracle):
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         lat.run_monte_carlo(0.4, 2, 4)                  # once per process
+
+
+def test_philox7_statistical_regression(pkg, native, oracle):
+    """Philox4x32-7 is the default since round 2 (Random123's Crush-resistant minimum).  With 4096
+    experiments - twice to four times the statistics of the parity tests above - the default
+    streams must still hit (i) Kaufman's exact <E> of the 32 x 32 torus at beta = 0.44 within 3
+    sigma and its exact specific heat within 8 %, (ii) the reference algorithm's <E> and spread on
+    one 6^3 +-J sample at beta = 0.6 within 3 sigma, (iii) and agree with the 10-round streams."""
+    L, E = 32, 4096
+    lat = pkg.Lattice(oracle.square_edges(L), seed_gen=20261018)
+    en, st = lat.run_monte_carlo(0.44, 3000, E, True)
+    exact = GOLD["kaufman"]["L32_b0.44"]
+    e = en / (L * L)
+    sigma = np.sqrt(exact["c_per_site"] / (0.44**2 * L * L))
+    assert abs(e.mean() - exact["e_per_site"]) < 3 * sigma / np.sqrt(E), (e.mean(), exact["e_per_site"])
+    assert abs(e.var(ddof=1) / sigma**2 - 1) < 0.08, (e.var(ddof=1), sigma**2)
+    m = (st.sum(1) * 2.0 - L * L) / (L * L)
+    assert abs(m.mean()) < 3 * np.sqrt((m**2).mean() / E)          # Z2 symmetry of the sample
+    # the same lattice with 10 rounds: the two estimates of <E> agree within their errors
+    ctx = native.Context.get(0)
+    g = lat.graph()
+    s10 = native.Sim(g, E, 7, rounds=10)
+    s10.sweeps(np.full(3000, 0.44))
+    e10 = s10.energies() / (L * L)
+    assert abs(e.mean() - e10.mean()) < 3 * np.hypot(e.std(ddof=1), e10.std(ddof=1)) / np.sqrt(E)
+    s10.close()
+    # 6^3 +-J glass against the reference algorithm (random-site, xoshiro256++), 4096 vs 1024
+    Lg = 6
+    rng = np.random.default_rng(3)
+    signs = rng.integers(0, 2, size=(Lg**3, 3)) * 2.0 - 1.0
+    edges = oracle.cubic_edges(Lg, lambda n, d: float(signs[n, d]))
+    glass = pkg.Lattice(edges, seed_gen=5)
+    en_g, _ = glass.run_monte_carlo(0.6, 3000, E, True)
+    en_o, _ = oracle.Graph(edges).run_monte_carlo(0.6, 3000, oracle.make_seeds(11, 1024))
+    a, b = en_g / Lg**3, en_o / Lg**3
+    err = np.hypot(a.std(ddof=1) / np.sqrt(len(a)), b.std(ddof=1) / np.sqrt(len(b)))
+    assert abs(a.mean() - b.mean()) < 3 * err, (a.mean(), b.mean(), err)
+    assert abs(a.std(ddof=1) / b.std(ddof=1) - 1) < 0.08
