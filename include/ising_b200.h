@@ -114,6 +114,29 @@ ISING_API int ising_sim_set_betas(ising_sim *sim, const double *betas /* E */);
 /* Tuning knobs of the multi-spin-coded kernel; 0 keeps the default.  planes = bit-planes
  * compared before the per-bit resolver (5..7), rounds = Philox4x32 rounds (7 or 10).      */
 ISING_API int ising_sim_configure(ising_sim *sim, int planes, int rounds);
+/* What one timestep consists of: the arguments of qmc GraphState::do_time_step(beta,
+ * nspinupdates, nedgeupdates, nwormupdates, only_basic_moves) as the reference passes them at
+ * lattice.rs:205, 272, 278, 366, 452 and classicising.rs:100-106, 146-165, in units of whole
+ * passes.  Default (never called, or moves = NULL): one colour-class sweep, no other move.
+ *   spin_sweeps      0 or 1 colour-class sweeps of single-spin Metropolis attempts
+ *   edge_passes      passes over all bonds of two-spin moves (both ends of a bond flip together),
+ *                    one launch per class of a strong edge colouring
+ *   worms, worm_len  worm moves per experiment: a self-avoiding chain of worm_len (1..8) sites
+ *                    from a uniformly random site, flipped as a whole; worm_len = 1 is the
+ *                    reference's attempt at a uniformly random site
+ *   edge_importance  GraphState::enable_edge_importance_sampling (lattice.rs:200, classicising.rs:76):
+ *                    a bond is attempted at a rate proportional to |J|
+ * All are Metropolis moves with symmetric (or ratio-corrected) proposals, so any mix keeps the
+ * Boltzmann distribution; their rules inside the `qmc` crate could not be read. */
+typedef struct ising_moves {
+    uint32_t struct_size;      /* sizeof(ising_moves) */
+    uint32_t spin_sweeps;
+    uint32_t edge_passes;
+    uint32_t worms;
+    uint32_t worm_len;
+    uint32_t edge_importance;
+} ising_moves;
+ISING_API int ising_sim_set_moves(ising_sim *sim, const ising_moves *moves);
 /* Random start (GraphState::new's make_random_spin_state, one Philox bit per spin) ...     */
 ISING_API int ising_sim_randomize(ising_sim *sim);
 /* ... or the same given state for every experiment (Lattice.set_initial_state, :201-203).  */
@@ -166,6 +189,8 @@ typedef struct ising_sim_stats {
     double sweep_device_ms;    /* CUDA-event time of the sweep kernels (on the ctx stream)   */
     double sweep_kernel_ms;    /* same, summed over sweep-kernel launches only               */
     uint64_t sweep_kernel_launches;
+    uint64_t edge_attempts;    /* two-spin edge moves attempted (ising_sim_set_moves)        */
+    uint64_t worm_attempts;    /* worm moves attempted                                       */
 } ising_sim_stats;
 ISING_API int ising_sim_get_stats(ising_sim *sim, ising_sim_stats *out);
 ISING_API int ising_sim_reset_stats(ising_sim *sim);
@@ -175,7 +200,9 @@ enum {
     ISING_FLAG_ONLY_BASIC_MOVES = 1u << 0,  /* informational: the GPU path is always basic  */
     ISING_FLAG_PER_STEP_ENERGIES = 1u << 1, /* annealing_and_get_energies                   */
     ISING_FLAG_LINEAR_SCHEDULE = 1u << 2,   /* documented interpolation instead of quirk Q1 */
-    ISING_FLAG_EDGE_IMPORTANCE = 1u << 3    /* -> ISING_E_UNSUPPORTED (deviation D2)        */
+    ISING_FLAG_EDGE_IMPORTANCE = 1u << 3,   /* needs ISING_FLAG_NON_BASIC_MOVES, else ISING_E_UNSUPPORTED */
+    ISING_FLAG_NON_BASIC_MOVES = 1u << 4    /* every timestep also runs one pass of edge moves and one
+                                               worm of 4 sites per experiment (ising_sim_set_moves) */
 };
 
 typedef struct ising_run_args {

@@ -25,6 +25,8 @@
  *   orc_attempt ............... qmc GraphState::do_spin_flip / should_flip, called through
  *                               do_time_step at src/lattice.rs:205,272,278,366,452
  *   orc_energy ................ qmc GraphState::get_energy, src/lattice.rs:208,284,370,454
+ *   orc_run_moves ............. do_time_step with non-basic moves (edge / worm), restated as the
+ *                               library defines them (the crate's rules are not readable here)
  *   orc_pt_* .................. src/tempering.rs:156-222 (run / swap / sample cadence) with the
  *                               classical swap rule min(1, exp((b_a-b_b)(E_a-E_b)))
  *   rng ....................... rand 0.8 SmallRng = xoshiro256++ (64-bit targets), seed_from_u64
@@ -263,6 +265,113 @@ ORC_EXPORT int orc_run_sampling(const orc_graph *g, double beta, uint64_t timest
         }
         free(st);
     }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Non-basic moves of GraphState::do_time_step(beta, nspinupdates, nedgeupdates, nwormupdates,
+ * only_basic_moves = false), called at src/lattice.rs:205,272,278,366,452 and
+ * src/classicising.rs:100-106.  [RECALLED + RESTATED]  The crate's rules are not readable here;
+ * what follows is the sequential form of the moves the CUDA library implements (csrc/moves.cu),
+ * pinned by exact enumeration (tests/test_oracle_moves.py):
+ *   edge move: a bond (a, b) chosen uniformly - or, with importance sampling
+ *     (enable_edge_importance_sampling, src/lattice.rs:200), with probability |J| / sum |J| -
+ *     flips both of its spins with min(1, exp(-beta dE)); bonds between a and b keep their energy;
+ *   worm move: a chain of `len` distinct sites grown from a uniform site along uniform adjacency
+ *     entries (given up when it bites itself) flips as a whole with
+ *     min(1, deg(first)/deg(last) exp(-beta dE)).
+ * ---------------------------------------------------------------------------------------- */
+static inline double orc_delta_e_excluding(const orc_graph *g, const uint8_t *state, uint64_t site,
+                                           const uint64_t *skip, uint64_t nskip) {
+    double de = 0.0;
+    uint8_t cur = state[site];
+    for (uint64_t k = g->row[site]; k < g->row[site + 1]; ++k) {
+        int inside = 0;
+        for (uint64_t q = 0; q < nskip; ++q) inside |= skip[q] == g->nbr[k];
+        if (inside) continue;
+        double coupling = (cur == state[g->nbr[k]]) ? 1.0 : -1.0;
+        de += -2.0 * g->jv[k] * coupling;
+    }
+    return de + 2.0 * g->bias[site] * (cur ? 1.0 : -1.0);
+}
+
+static inline void orc_edge_attempt(const orc_graph *g, const uint64_t *ea, const uint64_t *eb,
+                                    const double *cumw, uint8_t *state, uint64_t rng[4], double beta) {
+    uint64_t e;
+    if (cumw) {   /* cumulative absolute weights, binary search of u * total */
+        double x = orc_gen_f64(rng) * cumw[g->nedges - 1];
+        uint64_t lo = 0, hi = g->nedges - 1;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) / 2;
+            if (cumw[mid] > x) hi = mid; else lo = mid + 1;
+        }
+        e = lo;
+    } else {
+        e = orc_gen_range(rng, g->nedges);
+    }
+    uint64_t pair[2] = {ea[e], eb[e]};
+    double de = orc_delta_e_excluding(g, state, pair[0], pair, 2) +
+                orc_delta_e_excluding(g, state, pair[1], pair, 2);
+    int flip = 1;
+    if (de > 0.0) flip = orc_gen_f64(rng) < exp(-beta * de);
+    if (flip) {
+        state[pair[0]] = !state[pair[0]];
+        state[pair[1]] = !state[pair[1]];
+    }
+}
+
+#define ORC_WORM_MAX 8
+static inline void orc_worm_attempt(const orc_graph *g, uint8_t *state, uint64_t rng[4], double beta,
+                                    uint64_t len) {
+    uint64_t path[ORC_WORM_MAX];
+    path[0] = orc_gen_range(rng, g->nvars);
+    for (uint64_t t = 1; t < len; ++t) {
+        uint64_t head = path[t - 1];
+        uint64_t deg = g->row[head + 1] - g->row[head];
+        if (deg == 0) return;
+        uint64_t nxt = g->nbr[g->row[head] + orc_gen_range(rng, deg)];
+        for (uint64_t q = 0; q < t; ++q)
+            if (path[q] == nxt) return;
+        path[t] = nxt;
+    }
+    double de = 0.0;
+    for (uint64_t t = 0; t < len; ++t) de += orc_delta_e_excluding(g, state, path[t], path, len);
+    double ratio = 1.0;
+    if (len > 1)
+        ratio = (double)(g->row[path[0] + 1] - g->row[path[0]]) /
+                (double)(g->row[path[len - 1] + 1] - g->row[path[len - 1]]);
+    double p = ratio * exp(-beta * de);
+    int flip = p >= 1.0 || orc_gen_f64(rng) < p;
+    if (flip)
+        for (uint64_t t = 0; t < len; ++t) state[path[t]] = !state[path[t]];
+}
+
+/* The loop of src/lattice.rs:204-211 with explicit move counts per timestep. */
+ORC_EXPORT int orc_run_moves(const orc_graph *g, const uint64_t *ea, const uint64_t *eb, const double *ej,
+                             double beta, uint64_t timesteps, uint64_t nexp, const uint64_t *seeds,
+                             const uint8_t *initial_state, uint64_t nspin, uint64_t nedge, uint64_t nworm,
+                             uint64_t worm_len, int importance, double *energies, uint8_t *states) {
+    if (worm_len < 1 || worm_len > ORC_WORM_MAX) return -1;
+    double *cumw = NULL;
+    if (importance) {
+        cumw = (double *)malloc(sizeof(double) * (g->nedges ? g->nedges : 1));
+        double acc = 0.0;
+        for (uint64_t e = 0; e < g->nedges; ++e) { acc += fabs(ej[e]); cumw[e] = acc; }
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t e = 0; e < (int64_t)nexp; ++e) {
+        uint64_t rng[4];
+        uint8_t *st = states + (uint64_t)e * g->nvars;
+        orc_seed_from_u64(seeds[e], rng);
+        orc_init_state(g, rng, initial_state, st);
+        for (uint64_t t = 0; t < timesteps; ++t) {
+            for (uint64_t a = 0; a < nspin; ++a) orc_attempt(g, st, rng, beta, NULL, NULL);
+            for (uint64_t a = 0; a < nedge; ++a) orc_edge_attempt(g, ea, eb, cumw, st, rng, beta);
+            for (uint64_t a = 0; a < nworm; ++a) orc_worm_attempt(g, st, rng, beta, worm_len);
+        }
+        energies[e] = orc_energy(g, st);
+    }
+    free(cumw);
     return 0;
 }
 

@@ -20,6 +20,7 @@ FLAG_ONLY_BASIC_MOVES = 1 << 0
 FLAG_PER_STEP_ENERGIES = 1 << 1
 FLAG_LINEAR_SCHEDULE = 1 << 2
 FLAG_EDGE_IMPORTANCE = 1 << 3
+FLAG_NON_BASIC_MOVES = 1 << 4
 
 KIND_GENERAL, KIND_STENCIL2D, KIND_STENCIL3D = 0, 2, 3
 
@@ -53,6 +54,19 @@ class SimStats(C.Structure):
         ("sweep_device_ms", C.c_double),
         ("sweep_kernel_ms", C.c_double),
         ("sweep_kernel_launches", C.c_uint64),
+        ("edge_attempts", C.c_uint64),
+        ("worm_attempts", C.c_uint64),
+    ]
+
+
+class Moves(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("spin_sweeps", C.c_uint32),
+        ("edge_passes", C.c_uint32),
+        ("worms", C.c_uint32),
+        ("worm_len", C.c_uint32),
+        ("edge_importance", C.c_uint32),
     ]
 
 
@@ -96,6 +110,7 @@ _SIGNATURES = {
     "ising_sim_set_betas": (C.c_int, [_P, _P]),
     "ising_sim_destroy": (None, [_P]),
     "ising_sim_configure": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ising_sim_set_moves": (C.c_int, [_P, C.POINTER(Moves)]),
     "ising_sim_randomize": (C.c_int, [_P]),
     "ising_sim_set_state": (C.c_int, [_P, _P]),
     "ising_sim_set_states": (C.c_int, [_P, _P]),
@@ -368,6 +383,13 @@ class Sim:
 
     def randomize(self):
         check(lib().ising_sim_randomize(self.handle), self.ctx.handle)
+
+    def set_moves(self, spin_sweeps=1, edge_passes=0, worms=0, worm_len=4, edge_importance=False):
+        """What a timestep consists of (ising_sim_set_moves); set_moves() alone restores the
+        default of one colour-class sweep."""
+        m = Moves(C.sizeof(Moves), int(spin_sweeps), int(edge_passes), int(worms), int(worm_len),
+                  1 if edge_importance else 0)
+        check(lib().ising_sim_set_moves(self.handle, C.byref(m)), self.ctx.handle)
 
     def set_state(self, state):
         s = np.ascontiguousarray(state, dtype=np.uint8)

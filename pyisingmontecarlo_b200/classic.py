@@ -23,6 +23,9 @@ class ClassicIsing:
         self._longitudinal = 0.0 if longitudinal is None else float(longitudinal)
         self._seed = (int(seed) & _U64) if seed is not None else secrets.randbits(64)
         self._use_basic_moves = bool(use_basic_moves) if use_basic_moves is not None else False
+        self._edge_importance = False
+        # worm moves of a timestep: sites per worm (1..8); see csrc/moves.cu
+        self.worm_len = 4
         self._device = device
         ctx = nat.Context.get(device)
         bias = None if self._longitudinal == 0.0 else np.full(self.nvars, self._longitudinal)
@@ -34,10 +37,11 @@ class ClassicIsing:
         self._sim = nat.Sim(self._graph, self._n, self._seed) if self._n > 0 else None
 
     def add_graph(self, initial_state=None, edge_move_importance_sampling=None):
-        """classicising.rs:62-79: one more experiment, random start or the given state."""
-        if edge_move_importance_sampling:
-            raise NotImplementedError("edge_move_importance_sampling only affects the reference's "
-                                      "non-basic edge moves, which the GPU path does not perform")
+        """classicising.rs:62-79: one more experiment, random start or the given state.
+        edge_move_importance_sampling (classicising.rs:75-77) is a property of the object here:
+        all experiments share one packed state, so the last value given applies to all of them."""
+        if edge_move_importance_sampling is not None:
+            self._edge_importance = bool(edge_move_importance_sampling)
         old = None if self._sim is None else self._sim.states()
         self._n += 1
         sim = nat.Sim(self._graph, self._n, self._seed)      # experiment e always owns stream e
@@ -59,17 +63,35 @@ class ClassicIsing:
             self._sim.close()
         self._sim = sim
 
-    def _check_moves(self, nspinupdates, nedgeupdates, nwormupdates):
-        if nspinupdates not in (None, self.nvars):
-            raise NotImplementedError("a timestep is one sweep of nvars single-spin attempts on the GPU path")
-        if nedgeupdates or nwormupdates:
-            raise NotImplementedError("edge / worm updates are not performed on the GPU path")
+    def _set_moves(self, nspinupdates, nedgeupdates, nwormupdates, only_basic_moves):
+        """The move counts of do_time_step (classicising.rs:100-106) in units of whole passes:
+        nspinupdates in {None, nvars, 0} = one / no colour-class sweep, nedgeupdates = k * nedges
+        = k passes of two-spin edge moves, nwormupdates = worm moves per experiment.  With all
+        three None and only_basic_moves None / False only the sweep runs, with a warning (D1)."""
+        basic = only_basic_moves if only_basic_moves is not None else self._use_basic_moves
+        if nspinupdates not in (None, 0, self.nvars):
+            raise NotImplementedError("nspinupdates must be None, 0 or nvars: single-spin attempts come as "
+                                      "whole colour-class sweeps on the GPU path")
+        nedges = len(self._a)
+        if nedgeupdates is not None and nedgeupdates % nedges:
+            raise NotImplementedError("nedgeupdates must be a multiple of the number of edges: edge moves "
+                                      "come as whole passes over the bonds on the GPU path")
+        spin = 0 if nspinupdates == 0 else 1
+        edge = 0 if nedgeupdates is None else int(nedgeupdates) // nedges
+        worms = 0 if nwormupdates is None else int(nwormupdates)
+        if basic:
+            edge = worms = 0
+        elif nedgeupdates is None and nwormupdates is None:
+            warn_non_basic_moves(False)
+        if self._edge_importance and not edge:
+            raise NotImplementedError("edge_move_importance_sampling only affects the edge moves: pass "
+                                      "nedgeupdates (a multiple of the number of edges)")
+        self._sim.set_moves(spin, edge, worms, self.worm_len, self._edge_importance)
 
     def run_monte_carlo(self, beta, timesteps, nspinupdates=None, nedgeupdates=None, nwormupdates=None,
                         only_basic_moves=None):
         """classicising.rs:88-110: advances every experiment, returns nothing."""
-        warn_non_basic_moves(only_basic_moves if only_basic_moves is not None else self._use_basic_moves)
-        self._check_moves(nspinupdates, nedgeupdates, nwormupdates)
+        self._set_moves(nspinupdates, nedgeupdates, nwormupdates, only_basic_moves)
         self._sim.sweeps(np.full(int(timesteps), float(beta)))
 
     def run_monte_carlo_sampling(self, beta, timesteps, nspinupdates=None, nedgeupdates=None,
@@ -77,7 +99,7 @@ class ClassicIsing:
                                  sampling_freq=None, *, packed=False):
         """classicising.rs:119-179 -> (energies float64[E, n_s], states bool[E, n_s, nvars]);
         packed=True (additive) returns uint32[n_s, nvars, ceil(E/32)] bit-packed samples instead."""
-        self._check_moves(nspinupdates, nedgeupdates, nwormupdates)
+        self._set_moves(nspinupdates, nedgeupdates, nwormupdates, only_basic_moves)
         thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
         sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
         if sampling_freq == 0:

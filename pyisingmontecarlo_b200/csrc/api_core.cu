@@ -286,6 +286,27 @@ int ensure_real_on_device(ising_ctx* ctx, ising_graph* g) {
     return ISING_OK;
 }
 
+// non-basic moves: f32 CSR + the classes of a strong edge colouring
+int ensure_moves_on_device(ising_ctx* ctx, ising_graph* g) {
+    if (g->moves_built) return ISING_OK;
+    int rc = ensure_real_on_device(ctx, g);
+    if (rc) return rc;
+    if (g->h.nedges > 0xFFFFFFFFull) return fail(ctx, ISING_E_UNSUPPORTED, "too many edges");
+    EdgeClasses ec;
+    strong_edge_colouring(&g->h, &ec);
+    CUDA_TRY(ctx, dev_alloc(&g->d_mea, ec.ea.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_meb, ec.eb.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_meid, ec.eid.size()));
+    CUDA_TRY(ctx, dev_alloc(&g->d_mwrel, ec.wrel.size()));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_mea, ec.ea.data(), ec.ea.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_meb, ec.eb.data(), ec.eb.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_meid, ec.eid.data(), ec.eid.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(g->d_mwrel, ec.wrel.data(), ec.wrel.size() * 4, cudaMemcpyHostToDevice));
+    g->medge_off = ec.off;
+    g->moves_built = true;
+    return ISING_OK;
+}
+
 // colour x degree groups of a graph whose couplings all have the same magnitude
 int ensure_general_on_device(ising_ctx* ctx, ising_graph* g) {
     if (g->gen_built) return ISING_OK;
@@ -403,6 +424,10 @@ extern "C" void ising_graph_destroy(ising_graph* g) {
     cudaFree(g->d_csites);
     cudaFree(g->d_jf);
     cudaFree(g->d_biasf);
+    cudaFree(g->d_mea);
+    cudaFree(g->d_meb);
+    cudaFree(g->d_meid);
+    cudaFree(g->d_mwrel);
     delete g;
 }
 

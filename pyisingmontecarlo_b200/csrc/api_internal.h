@@ -83,6 +83,13 @@ struct ising_graph {
     std::vector<uint32_t> color_off;   // ncolors + 1 offsets into d_csites
     float* d_jf = nullptr;
     float* d_biasf = nullptr;
+    // non-basic moves: classes of the strong edge colouring (built on demand)
+    bool moves_built = false;
+    uint32_t* d_mea = nullptr;
+    uint32_t* d_meb = nullptr;
+    uint32_t* d_meid = nullptr;
+    float* d_mwrel = nullptr;
+    std::vector<uint32_t> medge_off;   // nclasses + 1 offsets into the four arrays
 };
 
 struct ising_comm;
@@ -114,6 +121,9 @@ struct ising_sim {
     // so a swap step must not recompute thousands of exp()
     std::unordered_map<uint64_t, std::vector<unsigned long long>> beta_rows;
     int beta_rows_planes = 0;
+    // what a timestep consists of (ising_sim_set_moves); default: one colour-class sweep
+    bool moves_active = false;
+    ising_moves mv{};
 };
 
 int fail(ising_ctx* ctx, int code, const char* fmt, ...);
@@ -166,6 +176,7 @@ int ensure_csr_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_csr32_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_real_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_general_on_device(ising_ctx* ctx, ising_graph* g);
+int ensure_moves_on_device(ising_ctx* ctx, ising_graph* g);
 // simulation object (api_sim.cu)
 void count_launch(ising_sim* s, int n);
 uint64_t threshold64(double beta, double de, int K);

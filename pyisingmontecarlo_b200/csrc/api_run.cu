@@ -10,10 +10,12 @@ static int check_run_args(ising_ctx* ctx, const ising_graph* g, const ising_run_
     if (a->struct_size != sizeof(ising_run_args))
         return fail(ctx, ISING_E_INVALID, "ising_run_args.struct_size mismatch (%u != %zu)",
                     a->struct_size, sizeof(ising_run_args));
-    if (a->flags & ISING_FLAG_EDGE_IMPORTANCE)
+    if ((a->flags & ISING_FLAG_EDGE_IMPORTANCE) && !(a->flags & ISING_FLAG_NON_BASIC_MOVES))
         return fail(ctx, ISING_E_UNSUPPORTED,
-                    "edge_move_importance_sampling only affects the reference's non-basic edge "
-                    "moves, which the GPU path does not perform");
+                    "edge_move_importance_sampling only affects the non-basic edge moves: pass "
+                    "ISING_FLAG_NON_BASIC_MOVES as well");
+    if ((a->flags & ISING_FLAG_NON_BASIC_MOVES) && (a->flags & ISING_FLAG_ONLY_BASIC_MOVES))
+        return fail(ctx, ISING_E_INVALID, "ISING_FLAG_NON_BASIC_MOVES contradicts ISING_FLAG_ONLY_BASIC_MOVES");
     if (a->num_experiments && (!energies || !states))
         return fail(ctx, ISING_E_INVALID, "output buffers are NULL");
     return ISING_OK;
@@ -24,6 +26,16 @@ static int make_sim_for_run(ising_ctx* ctx, const ising_graph* g, const ising_ru
     int rc = ising_sim_create(ctx, g, a->num_experiments, a->seed, a->replica_offset, sim);
     if (rc) return rc;
     if (a->initial_state) rc = ising_sim_set_state(*sim, a->initial_state);
+    if (rc == ISING_OK && (a->flags & ISING_FLAG_NON_BASIC_MOVES)) {
+        ising_moves mv{};
+        mv.struct_size = sizeof mv;
+        mv.spin_sweeps = 1;
+        mv.edge_passes = 1;
+        mv.worms = 1;
+        mv.worm_len = 4;
+        mv.edge_importance = (a->flags & ISING_FLAG_EDGE_IMPORTANCE) ? 1u : 0u;
+        rc = ising_sim_set_moves(*sim, &mv);
+    }
     if (rc) { ising_sim_destroy(*sim); *sim = nullptr; }
     return rc;
 }

@@ -274,8 +274,8 @@ static int sim_energy_real(ising_sim* s, double* d_tmp /* [32 W] */) {
     return ISING_OK;
 }
 
-static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr,
-                         uint32_t nsat_copies = 1) {
+static int sim_one_sweep_basic(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr,
+                               uint32_t nsat_copies = 1) {
     if (s->real) return sim_one_sweep_real(s, beta);
     if (s->general) return sim_one_sweep_general(s, beta);
     ising_ctx* ctx = s->ctx;
@@ -311,13 +311,115 @@ static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out
     return ISING_OK;
 }
 
+// The non-basic part of a timestep (ising_sim_set_moves): passes of two-spin edge moves over the
+// classes of the strong edge colouring, then the worm moves.  t = index of the timestep.
+static int sim_non_basic_moves(ising_sim* s, double beta, uint64_t t) {
+    ising_ctx* ctx = s->ctx;
+    const ising_graph* g = s->g;
+    const MoveGraph mg{g->d_row32, g->d_nbr32, g->d_jf, g->d_biasf};
+    int launches = 0;
+    for (uint32_t pass = 0; pass < s->mv.edge_passes; ++pass)
+        for (size_t c = 0; c + 1 < g->medge_off.size(); ++c) {
+            EdgeMoveArgs a;
+            a.spins = s->d_spins;
+            a.lay = s->lay;
+            a.g = mg;
+            const uint32_t o = g->medge_off[c];
+            a.ea = g->d_mea + o;
+            a.eb = g->d_meb + o;
+            a.eid = g->d_meid + o;
+            a.wrel = s->mv.edge_importance ? g->d_mwrel + o : nullptr;
+            a.count = g->medge_off[c + 1] - o;
+            a.beta = (float)beta;
+            a.sweep = (uint32_t)t;
+            a.key0 = (uint32_t)s->seed;
+            a.key1 = (uint32_t)(s->seed >> 32);
+            a.gw0 = (uint32_t)(s->replica_offset / 32);
+            a.pass = pass;
+            a.rounds = s->rounds;
+            const int n = launch_edge_moves(a, ctx->stream);
+            if (n < 0) return fail(ctx, ISING_E_CUDA, "edge-move launch failed: %s",
+                                   cudaGetErrorString(cudaGetLastError()));
+            launches += n;
+        }
+    if (s->mv.worms) {
+        WormArgs a;
+        a.spins = s->d_spins;
+        a.lay = s->lay;
+        a.g = mg;
+        a.E = s->E;
+        a.replica_offset = s->replica_offset;
+        a.nworms = s->mv.worms;
+        a.worm0 = 0;
+        a.len = s->mv.worm_len;
+        a.beta = (float)beta;
+        a.sweep = (uint32_t)t;
+        a.key0 = (uint32_t)s->seed;
+        a.key1 = (uint32_t)(s->seed >> 32);
+        a.rounds = s->rounds;
+        const int n = launch_worm_moves(a, ctx->stream);
+        if (n < 0) return fail(ctx, ISING_E_CUDA, "worm-move launch failed: %s",
+                               cudaGetErrorString(cudaGetLastError()));
+        launches += n;
+    }
+    count_launch(s, launches);
+    s->stats.edge_attempts += (uint64_t)s->mv.edge_passes * s->g->h.nedges * s->E;
+    s->stats.worm_attempts += (uint64_t)s->mv.worms * s->E;
+    return ISING_OK;
+}
+
+// One timestep: the colour-class sweep and, when ising_sim_set_moves asked for them, the non-basic
+// moves.  nsat_out (fused per-sweep energy accumulation) only without non-basic moves.
+static int sim_one_sweep(ising_sim* s, double beta, unsigned long long* nsat_out = nullptr,
+                         uint32_t nsat_copies = 1) {
+    if (!s->moves_active) return sim_one_sweep_basic(s, beta, nsat_out, nsat_copies);
+    const uint64_t t = s->sweep_counter;
+    if (s->mv.spin_sweeps) {
+        const int rc = sim_one_sweep_basic(s, beta);
+        if (rc) return rc;
+    } else {
+        s->sweep_counter++;
+        s->stats.sweeps++;
+    }
+    return sim_non_basic_moves(s, beta, t);
+}
+
+extern "C" int ising_sim_set_moves(ising_sim* s, const ising_moves* mv) {
+    CtxLock _lk(s ? s->ctx : nullptr);
+    if (!s) return fail(nullptr, ISING_E_INVALID, "sim is NULL");
+    ising_ctx* ctx = s->ctx;
+    if (!mv) {   // back to the default timestep
+        s->moves_active = false;
+        return ISING_OK;
+    }
+    if (mv->struct_size != sizeof(ising_moves))
+        return fail(ctx, ISING_E_INVALID, "ising_moves.struct_size mismatch (%u != %zu)", mv->struct_size,
+                    sizeof(ising_moves));
+    if (mv->spin_sweeps > 1)
+        return fail(ctx, ISING_E_UNSUPPORTED, "spin_sweeps must be 0 or 1 (a timestep holds at most one colour-class sweep)");
+    if (mv->worms && (mv->worm_len < 1 || mv->worm_len > (uint32_t)WORM_MAX_LEN))
+        return fail(ctx, ISING_E_INVALID, "worm_len must be 1..%d", WORM_MAX_LEN);
+    if (mv->edge_passes > 255) return fail(ctx, ISING_E_INVALID, "edge_passes must be <= 255");
+    const bool non_basic = mv->edge_passes || mv->worms;
+    if (non_basic && s->perbeta)
+        return fail(ctx, ISING_E_UNSUPPORTED, "non-basic moves run at one beta per timestep, not at per-experiment betas");
+    if (non_basic) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        const int rc = ensure_moves_on_device(ctx, const_cast<ising_graph*>(s->g));
+        if (rc) return rc;
+    }
+    s->mv = *mv;
+    s->moves_active = non_basic || mv->spin_sweeps == 0;
+    return ISING_OK;
+}
+
 // Launch-bound sizes: a whole chunk of sweeps in one cooperative launch.  Returns 1 when done
 // that way, 0 when the caller should fall back to per-phase launches, < 0 on error (rc in *err).
 static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsigned long long* hist,
                            int* err, uint32_t hist_stride = 0) {
     if (hist_stride == 0) hist_stride = s->lay.W * 32;   // words of history per sweep
     *err = ISING_OK;
-    if (s->general || s->real || nt == 0) return 0;
+    if (s->general || s->real || s->moves_active || nt == 0) return 0;
     if (s->perbeta && (hist || s->planes != 6)) return 0;
     if ((uint64_t)s->lay.halfN * s->lay.W > (1ull << 19)) return 0;  // big enough to fill the GPU
     ising_ctx* ctx = s->ctx;
@@ -497,6 +599,13 @@ extern "C" int ising_sim_sweeps(ising_sim* s, const double* betas, uint64_t nswe
             rc = sim_one_sweep(s, betas ? betas[t0 + t] : 0.0, d_hist + t * hstride, copies);
             if (rc == ISING_OK && s->real) {
                 rc = sim_energy_real(s, reinterpret_cast<double*>(d_hist + t * cw));
+            } else if (rc == ISING_OK && s->moves_active && !s->general) {
+                // the non-basic moves ran after the sweep: count the satisfied bonds of the result
+                const int n = launch_nsat_stencil(s->d_spins, s->g->d_jmask, s->lay,
+                                                  h.uniform_antiferro ? 0xFFFFFFFFu : 0u,
+                                                  d_hist + t * hstride, ctx->stream);
+                if (n < 0) rc = fail(ctx, ISING_E_CUDA, "energy launch failed");
+                else count_launch(s, n);
             } else if (rc == ISING_OK && s->general) {  // no fused accumulation on general graphs
                 const int n = launch_nsat_general(s->d_spins, s->lay.nvars, s->lay.W, s->g->d_row32,
                                                   s->g->d_nbr32, s->g->d_anti8, d_hist + t * cw,

@@ -318,6 +318,74 @@ std::string compile_from_edges(uint64_t nvars, uint64_t nedges, const uint64_t* 
     return "";
 }
 
+void strong_edge_colouring(HostGraph* g, EdgeClasses* out) {
+    g->build_csr();
+    const uint64_t N = g->nvars, M = g->nedges;
+    // incident edge ids per site
+    std::vector<uint64_t> irow(N + 1, 0);
+    std::vector<uint32_t> ea(M), eb(M);
+    std::vector<float> wj(M);
+    double jmax = 0.0;
+    for (uint64_t e = 0; e < M; ++e) {
+        uint64_t a, b;
+        double j;
+        g->edge_at(e, &a, &b, &j);
+        ea[e] = (uint32_t)a;
+        eb[e] = (uint32_t)b;
+        wj[e] = (float)fabs(j);
+        jmax = std::max(jmax, fabs(j));
+        irow[a + 1]++;
+        irow[b + 1]++;
+    }
+    for (uint64_t i = 0; i < N; ++i) irow[i + 1] += irow[i];
+    std::vector<uint32_t> inc(2 * M);
+    {
+        std::vector<uint64_t> fill(irow.begin(), irow.end() - 1);
+        for (uint64_t e = 0; e < M; ++e) {
+            inc[fill[ea[e]]++] = (uint32_t)e;
+            inc[fill[eb[e]]++] = (uint32_t)e;
+        }
+    }
+    std::vector<uint32_t> cls(M, 0xFFFFFFFFu);
+    std::vector<uint64_t> stamp;   // stamp[c] == e + 1: class c is taken around edge e
+    uint32_t ncls = 0;
+    auto forbid_site = [&](uint64_t v, uint64_t e) {
+        for (uint64_t k = irow[v]; k < irow[v + 1]; ++k) {
+            const uint32_t c = cls[inc[k]];
+            if (c != 0xFFFFFFFFu) stamp[c] = e + 1;
+        }
+    };
+    for (uint64_t e = 0; e < M; ++e) {
+        const uint32_t end[2] = {ea[e], eb[e]};
+        for (int s = 0; s < 2; ++s) {
+            forbid_site(end[s], e);
+            for (uint64_t k = g->row[end[s]]; k < g->row[end[s] + 1]; ++k) forbid_site(g->nbr[k], e);
+        }
+        uint32_t c = 0;
+        while (c < ncls && stamp[c] == e + 1) ++c;
+        if (c == ncls) {
+            ++ncls;
+            stamp.push_back(0);
+        }
+        cls[e] = c;
+    }
+    out->off.assign(ncls + 1, 0);
+    for (uint64_t e = 0; e < M; ++e) out->off[cls[e] + 1]++;
+    for (uint32_t c = 0; c < ncls; ++c) out->off[c + 1] += out->off[c];
+    out->ea.resize(M);
+    out->eb.resize(M);
+    out->eid.resize(M);
+    out->wrel.resize(M);
+    std::vector<uint32_t> fill(out->off.begin(), out->off.end() - 1);
+    for (uint64_t e = 0; e < M; ++e) {
+        const uint32_t p = fill[cls[e]]++;
+        out->ea[p] = ea[e];
+        out->eb[p] = eb[e];
+        out->eid[p] = (uint32_t)e;
+        out->wrel[p] = jmax > 0.0 ? (float)(wj[e] / jmax) : 1.f;
+    }
+}
+
 std::string make_torus(int dim, const uint64_t* L, double j0, int pmj, uint64_t j_seed,
                        HostGraph* g) {
     if (dim != 2 && dim != 3) return "dim must be 2 or 3";

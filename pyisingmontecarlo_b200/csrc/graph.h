@@ -52,6 +52,19 @@ std::string compile_from_edges(uint64_t nvars, uint64_t nedges, const uint64_t* 
 std::string make_torus(int dim, const uint64_t* L, double j0, int pmj, uint64_t j_seed,
                        HostGraph* out);
 
+// Classes of edges that may be flipped as pairs in parallel (the two-spin "edge moves" of
+// qmc GraphState::do_time_step, call sites src/lattice.rs:205, src/classicising.rs:100-106):
+// a strong edge colouring - two edges of one class share no site and no bond joins them, so the
+// energy change of one two-spin flip does not depend on another of the same class.
+// Greedy in edge order; edges come out sorted by class.
+struct EdgeClasses {
+    std::vector<uint32_t> ea, eb;   // end points, class-sorted
+    std::vector<uint32_t> eid;      // index in the edge list (Philox counter word 0)
+    std::vector<float> wrel;        // |J_e| / max |J| (importance sampling of the edge choice)
+    std::vector<uint32_t> off;      // nclasses + 1 offsets
+};
+void strong_edge_colouring(HostGraph* g, EdgeClasses* out);
+
 // rand 0.8 SmallRng restated for Lattice::make_seeds (src/lattice.rs:83-91)
 void make_seeds(uint64_t seed_gen, uint64_t n, uint64_t* out);
 

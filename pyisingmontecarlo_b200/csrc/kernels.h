@@ -214,6 +214,40 @@ int launch_energy_real(const uint32_t* spins, uint64_t nvars, uint32_t W, const 
                        const uint32_t* nbr, const double* jv, const double* bias,
                        double* energies /* [32 W], zeroed */, cudaStream_t st);
 
+// ---- non-basic moves of a timestep (moves.cu): two-spin edge moves and worm (chain) moves ------
+struct MoveGraph {            // CSR with f32 couplings and biases (ensure_real_on_device)
+    const uint32_t* row;
+    const uint32_t* nbr;
+    const float* jf;
+    const float* biasf;
+};
+struct EdgeMoveArgs {
+    uint32_t* spins;
+    Layout lay;
+    MoveGraph g;
+    const uint32_t* ea;       // one class of the strong edge colouring
+    const uint32_t* eb;
+    const uint32_t* eid;      // index of the edge in the edge list (Philox counter word 0)
+    const float* wrel;        // |J| / max |J| per edge (importance sampling) or nullptr
+    uint32_t count;
+    float beta;
+    uint32_t sweep, key0, key1, gw0, pass;
+    int rounds;
+};
+int launch_edge_moves(const EdgeMoveArgs& a, cudaStream_t st);
+constexpr int WORM_MAX_LEN = 8;
+struct WormArgs {
+    uint32_t* spins;
+    Layout lay;
+    MoveGraph g;
+    uint64_t E, replica_offset;
+    uint32_t nworms, worm0, len;   // worms per experiment of this launch, index of the first, sites per worm
+    float beta;
+    uint32_t sweep, key0, key1;
+    int rounds;
+};
+int launch_worm_moves(const WormArgs& a, cudaStream_t st);
+
 int launch_copy_strided_f64(const double* in, uint64_t E, double* out, uint64_t estride,
                             uint64_t eoff, cudaStream_t st);
 int launch_transpose_hist_f64(const double* hist, uint64_t E, uint64_t cw, uint64_t nt, double* out,

@@ -20,6 +20,8 @@ enum : uint32_t {
     TAG_INIT = 1u,    // random initial state
     TAG_SWAP = 2u,    // parallel-tempering swap decisions
     TAG_BOND = 3u,    // +-J disorder of ising_graph_torus
+    TAG_EDGE = 4u,    // two-spin edge moves: counter (edge, replica word, timestep, call | pass << 8)
+    TAG_WORM = 5u,    // worm moves: counter (experiment, worm, timestep, call)
 };
 
 struct u32x4 {

@@ -4,8 +4,13 @@ classical Monte-Carlo path, running on libising_b200 (CUDA, sm_100a) through its
 Same names, argument order, defaults, return dtypes/shapes and error behaviour as the
 reference's `py_monte_carlo.Lattice`; the quantum methods (lattice.rs:472-1069) stay on the
 reference.  Documented deviations of the GPU path:
-  D1  only single-spin Metropolis moves are performed whatever `only_basic_moves` says;
-  D2  `edge_move_importance_sampling=True` raises NotImplementedError instead of being ignored;
+  D1  with `only_basic_moves` None / False the reference's timestep also performs two-spin edge
+      moves and worm moves whose rules live in the out-of-tree `qmc` crate.  By default only
+      single-spin sweeps run (warned once per process); `Lattice.non_basic_moves = True` makes
+      such calls also run one pass of two-spin edge moves and one 4-site worm move per
+      experiment in every timestep (this engine's restatement of those moves, csrc/moves.cu);
+  D2  `edge_move_importance_sampling=True` needs `non_basic_moves` (it only affects the edge
+      moves) and raises NotImplementedError without it;
   D3  a timestep is one colour-class sweep (every site attempted once) instead of nvars
       attempts at uniformly random sites: same Boltzmann law, different transient.
 """
@@ -32,7 +37,9 @@ def warn_non_basic_moves(only_basic_moves):
     warnings.warn("only_basic_moves is None/False: the reference would also perform edge-flip and worm "
                   "moves in each timestep; the B200 engine performs single-spin Metropolis sweeps only "
                   "(same equilibrium distribution, different dynamics; see DESIGN.md deviation D1). "
-                  "Pass only_basic_moves=True to state that this is what you want.", UserWarning, stacklevel=3)
+                  "Pass only_basic_moves=True to state that this is what you want, or set "
+                  "Lattice.non_basic_moves = True to run this engine's edge and worm moves as well.",
+                  UserWarning, stacklevel=4)
 
 
 def _edges_to_arrays(edges):
@@ -76,6 +83,9 @@ class Lattice:
         self._graph = None
         # knobs of the device path that do not exist in the reference (defaults = parity mode)
         self.linear_annealing = False   # False reproduces the reference's schedule quirk Q1
+        # True: calls with only_basic_moves None / False also run two-spin edge moves and worm
+        # moves in every timestep (deviation D1); False: single-spin sweeps only, with a warning
+        self.non_basic_moves = False
         # multi-GPU (one process per GPU, torch.distributed initialised): shard the experiments
         # over the ranks in blocks of 32 (the reference's rayon axis, lattice.rs:192-197) and,
         # when gather_results is set, all-gather so that every rank returns the full arrays
@@ -188,10 +198,16 @@ class Lattice:
                                                    self._biases())
         return self._graph
 
-    def _check_classical(self, edge_move_importance_sampling):
+    def _check_classical(self, edge_move_importance_sampling, only_basic_moves=True):
+        """-> flags of the run: which moves a timestep performs (lattice.rs:181, 200, 205)."""
         if self._transverse is not None:
             raise ValueError("Cannot run classic monte carlo with transverse field")
-        return nat.FLAG_EDGE_IMPORTANCE if edge_move_importance_sampling else 0
+        if only_basic_moves:
+            return nat.FLAG_ONLY_BASIC_MOVES      # importance sampling has no move to act on
+        if self.non_basic_moves:
+            return nat.FLAG_NON_BASIC_MOVES | (nat.FLAG_EDGE_IMPORTANCE if edge_move_importance_sampling else 0)
+        warn_non_basic_moves(only_basic_moves)
+        return nat.FLAG_EDGE_IMPORTANCE if edge_move_importance_sampling else 0   # -> NotImplementedError (D2)
 
     def _run_seed(self):
         return self._seed_gen if self._seed_gen is not None else secrets.randbits(64)
@@ -241,9 +257,9 @@ class Lattice:
                         edge_move_importance_sampling=None):
         """lattice.rs:171-221 -> (energies float64[E], states bool[E, nvars])
 
-        only_basic_moves=None/False: single-spin sweeps all the same (deviation D1, warned once)."""
-        warn_non_basic_moves(only_basic_moves)
-        flags = self._check_classical(edge_move_importance_sampling)
+        only_basic_moves=None/False: single-spin sweeps only (deviation D1, warned once) unless
+        `non_basic_moves` is set, which adds an edge-move pass and a worm move to every timestep."""
+        flags = self._check_classical(edge_move_importance_sampling, only_basic_moves)
         energies = np.zeros(num_experiments, dtype=np.float64)
         states = nat.PinnedPool.empty((num_experiments, self.nvars), np.bool_)
         args = self._args(flags, beta=float(beta), timesteps=int(timesteps),
@@ -254,8 +270,7 @@ class Lattice:
                                  thermalization_time=None, sampling_freq=None,
                                  edge_move_importance_sampling=None):
         """lattice.rs:231-299 -> (energies float64[E, n_s], states bool[E, n_s, nvars])"""
-        warn_non_basic_moves(only_basic_moves)
-        flags = self._check_classical(edge_move_importance_sampling)
+        flags = self._check_classical(edge_move_importance_sampling, only_basic_moves)
         thermalization_time = 0 if thermalization_time is None else int(thermalization_time)
         sampling_freq = 1 if sampling_freq is None else int(sampling_freq)
         if sampling_freq == 0:
@@ -291,8 +306,9 @@ class Lattice:
         finally:
             sim.close()
 
-    def _annealing(self, betas, timesteps, num_experiments, edge_move_importance_sampling, per_step):
-        flags = self._check_classical(edge_move_importance_sampling)
+    def _annealing(self, betas, timesteps, num_experiments, only_basic_moves,
+                   edge_move_importance_sampling, per_step):
+        flags = self._check_classical(edge_move_importance_sampling, only_basic_moves)
         if per_step:
             flags |= nat.FLAG_PER_STEP_ENERGIES
         if self.linear_annealing:
@@ -311,15 +327,15 @@ class Lattice:
     def run_monte_carlo_annealing(self, betas, timesteps, num_experiments, only_basic_moves=None,
                                   edge_move_importance_sampling=None):
         """lattice.rs:309-385 -> (energies float64[E], states bool[E, nvars])"""
-        warn_non_basic_moves(only_basic_moves)
-        return self._annealing(betas, timesteps, num_experiments, edge_move_importance_sampling, False)
+        return self._annealing(betas, timesteps, num_experiments, only_basic_moves,
+                               edge_move_importance_sampling, False)
 
     def run_monte_carlo_annealing_and_get_energies(self, betas, timesteps, num_experiments,
                                                    only_basic_moves=None,
                                                    edge_move_importance_sampling=None):
         """lattice.rs:395-470 -> (energies float64[E, timesteps], states bool[E, nvars])"""
-        warn_non_basic_moves(only_basic_moves)
-        return self._annealing(betas, timesteps, num_experiments, edge_move_importance_sampling, True)
+        return self._annealing(betas, timesteps, num_experiments, only_basic_moves,
+                               edge_move_importance_sampling, True)
 
     # ---- replay mode (north-star correctness check 1) -----------------------------------------
     def replay(self, beta, sites, uniforms, init_states):

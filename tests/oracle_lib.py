@@ -55,6 +55,9 @@ def lib():
         h.orc_energy.argtypes = [_P, _P]
         h.orc_run_monte_carlo.restype = C.c_int
         h.orc_run_monte_carlo.argtypes = [_P, C.c_double, _U64, _U64, _P, _P, _U64, _P, _P]
+        h.orc_run_moves.restype = C.c_int
+        h.orc_run_moves.argtypes = [_P, _P, _P, _P, C.c_double, _U64, _U64, _P, _P, _U64, _U64, _U64, _U64,
+                                    C.c_int, _P, _P]
         h.orc_run_sampling.restype = C.c_int
         h.orc_run_sampling.argtypes = [_P, C.c_double, _U64, _U64, _P, _P, _U64, _U64, _U64, _P, _P]
         h.orc_schedule_betas.restype = C.c_int
@@ -157,6 +160,20 @@ class Graph:
         init = self._init(initial_state)
         rc = lib().orc_run_monte_carlo(self.h, float(beta), timesteps, E, _p(seeds), _p(init),
                                        attempts_per_step, _p(energies), _p(states))
+        assert rc == 0
+        return energies, states.astype(bool)
+
+    def run_moves(self, beta, timesteps, seeds, nspin=0, nedge=0, nworm=0, worm_len=4, importance=False,
+                  initial_state=None):
+        """Timesteps of explicit move counts (orc_run_moves) -> (energies[E], states bool[E, nvars])."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        E = len(seeds)
+        energies = np.zeros(E)
+        states = np.zeros((E, self.nvars), dtype=np.uint8)
+        init = self._init(initial_state)
+        rc = lib().orc_run_moves(self.h, _p(self.a), _p(self.b), _p(self.j), float(beta), timesteps, E,
+                                 _p(seeds), _p(init), nspin, nedge, nworm, worm_len, int(importance),
+                                 _p(energies), _p(states))
         assert rc == 0
         return energies, states.astype(bool)
 

@@ -1,0 +1,46 @@
+"""The non-basic moves (two-spin edge moves, worm moves) as the oracle restates them keep the
+Boltzmann distribution: chains made of those moves alone reproduce exact enumeration."""
+import numpy as np
+import pytest
+
+from moves_cases import boltzmann, histogram_z, irregular_graph
+
+
+@pytest.mark.parametrize("moves", [
+    dict(nedge=7, nworm=2, worm_len=3),                       # no single-spin move at all
+    dict(nedge=7, nworm=2, worm_len=3, importance=True),      # edges drawn with probability ~ |J|
+    dict(nworm=6, worm_len=1),                                # worm of one site = random-site attempt
+    dict(nedge=7, nworm=4, worm_len=4),                       # even moves only: parity sectors
+    dict(nspin=6, nedge=7, nworm=1, worm_len=2),              # everything together
+])
+def test_moves_alone_sample_the_boltzmann_law(oracle, moves):
+    edges, n, biases = irregular_graph()
+    beta = 0.8
+    g = oracle.Graph(edges, biases=biases)
+    E = 40000
+    seeds = oracle.make_seeds(11, E)
+    _, st = g.run_moves(beta, 60, seeds, **moves)
+    _, p, _ = boltzmann(edges, n, beta, biases)
+    # chains of even-length moves only keep the parity of the number of up spins: compare per sector
+    if moves.get("nspin", 0) == 0 and moves.get("worm_len", 1) % 2 == 0:
+        par = st.sum(1) % 2
+        parity_of_state = np.array([bin(i).count("1") % 2 for i in range(2 ** n)])
+        for sector in (0, 1):
+            sel = st[par == sector]
+            ps = np.where(parity_of_state == sector, p, 0.0)
+            ps = ps / ps.sum()
+            z = histogram_z(sel, ps)[parity_of_state == sector]
+            assert np.abs(z).max() < 4.5, z
+        return
+    z = histogram_z(st, p)
+    assert np.abs(z).max() < 4.5, z
+
+
+def test_edge_move_leaves_the_shared_bond_alone(oracle):
+    # one bond, strong coupling: flipping both ends never changes the energy, so every edge move
+    # is accepted and the pair keeps its relative orientation
+    g = oracle.Graph([((0, 1), -5.0)])
+    seeds = oracle.make_seeds(3, 64)
+    en, st = g.run_moves(3.0, 9, seeds, nedge=1, initial_state=[True, True])
+    assert (en == -5.0).all() and (st[:, 0] == st[:, 1]).all()
+    assert (st[:, 0] == False).all()      # 9 accepted double flips
