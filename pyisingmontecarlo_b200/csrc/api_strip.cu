@@ -9,6 +9,7 @@ struct ising_strip {
     StripGeom g{};
     uint64_t Lx = 0;
     uint32_t* d_spins = nullptr;
+    uint32_t* d_alt = nullptr;     // second array of the fused (out-of-place) sweep, allocated on first use
     size_t bytes = 0;
     unsigned long long* d_acc = nullptr;
     double j = -1.0;
@@ -71,6 +72,7 @@ extern "C" void ising_strip_destroy(ising_strip* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     ctx_buf_put(s->ctx, s->d_spins, s->bytes);
+    if (s->d_alt) ctx_buf_put(s->ctx, s->d_alt, s->bytes);
     ctx_buf_put(s->ctx, s->d_acc, 2 * sizeof(unsigned long long));
     delete s;
 }
@@ -98,6 +100,57 @@ extern "C" int ising_strip_set_all(ising_strip* s, int up) {
     return ISING_OK;
 }
 
+static void strip_fill_args(const ising_strip* s, double beta, StripSweepArgs* a) {
+    a->spins = s->d_spins;
+    a->g = s->g;
+    a->sweep = (uint32_t)s->sweep;
+    a->key0 = (uint32_t)s->seed;
+    a->key1 = (uint32_t)(s->seed >> 32);
+    a->antiferro = s->j > 0 ? 0xFFFFFFFFu : 0u;
+    a->planes = s->planes;
+    a->rounds = s->rounds;
+    memset(&a->th, 0, sizeof a->th);
+    for (int c = 0; c < 2; ++c) {
+        const uint64_t T = threshold64(beta, 4.0 * (c + 1) * fabs(s->j), s->planes);
+        for (int pl = 0; pl < s->planes; ++pl)
+            a->th.plane[c][pl] = ((T >> (s->planes + 31 - pl)) & 1ull) ? 0xFFFFFFFFu : 0u;
+        a->th.low[c] = (uint32_t)(T & 0xFFFFFFFFull);
+    }
+}
+
+// One whole sweep as a single out-of-place pass (launch_strip_sweep_fused): colour 0 on storage rows
+// [r0, r1), colour 1 on [r0 + 1, r1 - 1).  Returns 1 when done that way (the two arrays swap roles),
+// 0 when the caller should run the two colour phases, < 0 on error (message set).
+static int strip_sweep_fused(ising_strip* s, double beta, uint64_t r0, uint64_t r1) {
+    static const bool on = getenv("ISING_STRIP_FUSE") != nullptr;   // opt-in: measured slower, see strip.cu
+    if (!on || r1 < r0 + 4) return 0;
+    ising_ctx* ctx = s->ctx;
+    if (s->sweep > 0xFFFFFFFFull) return 0;   // the phase path reports the overflow
+    if (!s->d_alt) {
+        void* p = nullptr;
+        if (ctx_buf_get(ctx, s->bytes, &p) != cudaSuccess) {   // no room for a second array: two phases
+            cudaGetLastError();
+            return 0;
+        }
+        s->d_alt = (uint32_t*)p;
+        // rows the sweeps never write (outermost ghost rows) must not hold garbage the observables read
+        if (cudaMemcpyAsync(s->d_alt, s->d_spins, s->bytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+            return -fail(ctx, ISING_E_CUDA, "strip: copy into the second array failed");
+    }
+    StripSweepArgs a;
+    strip_fill_args(s, beta, &a);
+    a.colour = 0;
+    a.r_begin = (uint32_t)r0;
+    a.r_count = (uint32_t)(r1 - r0);
+    const int n = launch_strip_sweep_fused(a, s->d_spins, s->d_alt, ctx->stream);
+    if (n < 0) return -fail(ctx, ISING_E_CUDA, "fused strip sweep launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (n == 0) return 0;
+    std::swap(s->d_spins, s->d_alt);
+    s->launches++;
+    s->sweep++;
+    return 1;
+}
+
 // Local rows [r0, r1) of one colour phase; the ghost rows of the OTHER colour must hold the
 // neighbours' boundary rows when r0 == 0 or r1 == rows.  sync = 0 only enqueues (no host wait,
 // no event timing); advance != 0 bumps the sweep counter (call it on the last piece of colour 1).
@@ -108,24 +161,10 @@ static int strip_phase_storage_rows(ising_strip* s, int colour, double beta, uin
         return fail(ctx, ISING_E_UNSUPPORTED, "sweep counter passed 2^32: start a new lattice or seed");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     StripSweepArgs a;
-    a.spins = s->d_spins;
-    a.g = s->g;
+    strip_fill_args(s, beta, &a);
     a.colour = (uint32_t)colour;
-    a.sweep = (uint32_t)s->sweep;
-    a.key0 = (uint32_t)s->seed;
-    a.key1 = (uint32_t)(s->seed >> 32);
-    a.antiferro = s->j > 0 ? 0xFFFFFFFFu : 0u;
-    a.planes = s->planes;
-    a.rounds = s->rounds;
     a.r_begin = (uint32_t)r0;
     a.r_count = (uint32_t)(r1 - r0);
-    memset(&a.th, 0, sizeof a.th);
-    for (int c = 0; c < 2; ++c) {
-        const uint64_t T = threshold64(beta, 4.0 * (c + 1) * fabs(s->j), s->planes);
-        for (int pl = 0; pl < s->planes; ++pl)
-            a.th.plane[c][pl] = ((T >> (s->planes + 31 - pl)) & 1ull) ? 0xFFFFFFFFu : 0u;
-        a.th.low[c] = (uint32_t)(T & 0xFFFFFFFFull);
-    }
     if (sync) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     if (launch_strip_phase(a, ctx->stream) < 0)
         return fail(ctx, ISING_E_CUDA, "strip phase launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -349,9 +388,16 @@ extern "C" int ising_strip_sweeps(ising_strip* s, ising_comm* comm, const double
     for (uint64_t i = 0; i < nsweeps && rc == ISING_OK;) {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(k, nsweeps - i);
         rc = strip_exchange_deep(s, comm, 2 * nb);
-        for (uint32_t q = 0; q < 2 * nb && rc == ISING_OK; ++q)
-            rc = strip_phase_storage_rows(s, (int)(q & 1u), betas[i + q / 2], g.ghost - (2 * nb - 1 - q),
-                                          g.ghost + g.rows + (2 * nb - 1 - q), (int)(q & 1u), 0);
+        for (uint32_t q = 0; q < 2 * nb && rc == ISING_OK; q += 2) {
+            // ISING_STRIP_FUSE=1: both colours in one out-of-place pass (6 -> 4 bits of DRAM traffic per
+            // site and sweep, but measured 7 % slower: strip.cu); default: the two phase launches
+            const int fused = strip_sweep_fused(s, betas[i + q / 2], g.ghost - (2 * nb - 1 - q),
+                                                g.ghost + g.rows + (2 * nb - 1 - q));
+            if (fused < 0) rc = -fused;
+            for (uint32_t c = 0; c < 2 && fused == 0 && rc == ISING_OK; ++c)
+                rc = strip_phase_storage_rows(s, (int)c, betas[i + q / 2], g.ghost - (2 * nb - 1 - q - c),
+                                              g.ghost + g.rows + (2 * nb - 1 - q - c), (int)c, 0);
+        }
         i += nb;
     }
     cudaEventRecord(ctx->ev1, ctx->stream);

@@ -285,6 +285,10 @@ struct StripSweepArgs {
     uint32_t r_begin, r_count;  // storage rows to update: [r_begin, r_begin + r_count) within [1, rows + 2 ghost - 1)
 };
 int launch_strip_phase(const StripSweepArgs& a, cudaStream_t st);
+// Both colour phases of one sweep in a single out-of-place pass (src -> dst): colour 0 on storage
+// rows [r_begin, r_begin + r_count), colour 1 on [r_begin + 1, r_begin + r_count - 1); a.colour is
+// ignored.  Returns 1 when launched, 0 when the geometry is not covered, -1 on error.
+int launch_strip_sweep_fused(const StripSweepArgs& a, const uint32_t* src, uint32_t* dst, cudaStream_t st);
 int launch_strip_init_random(uint32_t* spins, const StripGeom& g, uint32_t key0, uint32_t key1,
                              cudaStream_t st);
 // acc[0] += satisfied bonds seen from colour-0 sites (every bond once), acc[1] += up spins

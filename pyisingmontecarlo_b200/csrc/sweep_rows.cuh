@@ -21,6 +21,9 @@
 #include "msc_device.cuh"
 
 // tuning knobs (profiles/microbench/rows_variants.sh builds and times the alternatives)
+#ifndef ISING_ROWS_THREADS
+#define ISING_ROWS_THREADS 256   // threads per block of the row walk
+#endif
 #ifndef ISING_ROWS_MINB
 #define ISING_ROWS_MINB 3        // resident blocks per SM the plain colour phase is compiled for
 #endif
@@ -31,7 +34,13 @@
 #define ISING_ROWS_ACC_MINB 2    // ... the accumulating colour phase
 #endif
 #ifndef ISING_ROWS_DEFER_RARE
-#define ISING_ROWS_DEFER_RARE 1  // 1: third-and-later ties of all V words after the word loop
+// third-and-later ties of a word: 0 = divergent loop inside the word, 1 = all V words after the
+// word loop (default), 2 = after the word loop, the warp voting word by word and resolving ties
+// 3..6 in straight-line code on a Philox call that shares rounds 1-3 with calls 0 and 1.
+// Mode 2 is bit-identical and its rare path is cheaper (10.7 instead of 13.1 us per sweep between
+// beta = 0.1 and 1.2 on config 3), but keeping the shared Philox products alive behind the word
+// loop spills: 74.4 vs 69.0 us per sweep on the annealing ramp (profiles/r02_rare_path_ab.log).
+#define ISING_ROWS_DEFER_RARE 1
 #endif
 #ifndef ISING_ROWS_SPLIT_ACC_DEFAULT
 #define ISING_ROWS_SPLIT_ACC_DEFAULT 0  // 1: per-sweep energies by a count-only pass instead of the fused phase
@@ -146,13 +155,28 @@ struct PhiloxSite {
             c1v[v] = (uint32_t)Q1;
         }
     }
+    // call q >= 2 of word v (resolver words 4 q .. 4 q + 3, needed by words with three or more
+    // ties): the per-call part of rounds 2-3 is computed here, the per-word part is shared with
+    // calls 0 and 1
+    // (round 1 is recomputed rather than kept in registers: this runs for 1 word in 100)
+    __device__ __forceinline__ void finish_call(int v, uint32_t q, uint32_t site, uint32_t sweep,
+                                                const PhiloxKeys& pk, uint32_t* out) const {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        const uint32_t h0r1 = __umulhi(M0, site), l1r1 = M1 * sweep;
+        const uint32_t c2r = h0r1 ^ (q | (TAG_ACCEPT << 24)) ^ pk.k[1];
+        const uint64_t P1 = (uint64_t)M1 * c2r;
+        const uint32_t c0q2 = (uint32_t)(P1 >> 32) ^ l1r1 ^ pk.k[2];
+        const uint32_t c1q2 = (uint32_t)P1;
+        const uint64_t Q0 = (uint64_t)M0 * c0q2;
+        rounds_from_4(hq1v[v] ^ c1q2 ^ pk.k[4], c1v[v], (uint32_t)(Q0 >> 32) ^ c3v[v] ^ pk.k[5], (uint32_t)Q0, pk, out);
+    }
     // rounds 4 .. ROUNDS of call q of word v
     __device__ __forceinline__ void finish(int v, int q, const PhiloxKeys& pk, uint32_t* out) const {
+        rounds_from_4(hq1v[v] ^ c1q[q] ^ pk.k[4], c1v[v], hq0[q] ^ c3v[v] ^ pk.k[5], c3q[q], pk, out);
+    }
+    __device__ __forceinline__ static void rounds_from_4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         const PhiloxKeys& pk, uint32_t* out) {
         const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-        uint32_t c0 = hq1v[v] ^ c1q[q] ^ pk.k[4];
-        uint32_t c1 = c1v[v];
-        uint32_t c2 = hq0[q] ^ c3v[v] ^ pk.k[5];
-        uint32_t c3 = c3q[q];
 #pragma unroll
         for (int r = 3; r < ROUNDS; ++r) {
             uint32_t h0, l0, h1, l1;
@@ -235,9 +259,9 @@ __device__ __forceinline__ uint32_t msc_flip_mask_mux(uint32_t up, uint32_t m1, 
 template <int NCLS, int K, int ROUNDS>
 __device__ __noinline__ uint32_t msc_resolve_rest(uint32_t eq, uint32_t m1, uint32_t m2, uint32_t low0,
                                                   uint32_t low1, uint32_t low2, uint32_t site, uint32_t gw,
-                                                  uint32_t sweep, const PhiloxKeys& pk) {
+                                                  uint32_t sweep, const PhiloxKeys& pk, int j0 = 8) {
     uint32_t flip = 0;
-    int j = 8;
+    int j = j0;   // multiple of 4: the first word comes from a fresh call
     u32x4 cur = {0, 0, 0, 0};
     do {
         const int b = __ffs((int)eq) - 1;
@@ -268,6 +292,7 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
     PhiloxSite<ROUNDS, V> ph;
     ph.prepare(site, gw0w, sweep, pk);
     constexpr bool kDefer = ISING_ROWS_DEFER_RARE != 0;
+    constexpr bool kVote = ISING_ROWS_DEFER_RARE == 2;
     uint32_t left[V], lm1[V], lm2[V];
     uint32_t any_left = 0;
     uint32_t nb0[V], nb1[V], nb2[V];
@@ -286,7 +311,7 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
         const uint32_t m1 = DIM == 3 ? (b2 & b0) : b2;
         const uint32_t m2 = DIM == 3 ? (b2 & b1) : 0u;
         left[v] = 0;
-        const uint32_t flip = msc_flip_mask_mux<DIM == 3 ? 3 : 2, K, ROUNDS>(
+        uint32_t flip = msc_flip_mask_mux<DIM == 3 ? 3 : 2, K, ROUNDS>(
             up, m1, m2, mx, r, site, gw0w + v, sweep, pk, kDefer ? &left[v] : nullptr);
         s[v] ^= flip;
         if constexpr (kDefer) {
@@ -312,7 +337,32 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
         uint32_t extra[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) extra[v] = 0;
-        if (any_left) {  // a word with three or more ties (rare)
+        if (kVote && __any_sync(__activemask(), any_left != 0u)) {
+            // Words with three or more ties: 1 % of the words at low temperature, so three warps
+            // in four meet one per site group.  The warp goes through the V words together; ties
+            // 3..6 of a word are resolved in straight-line code on Philox call 2, whose rounds 1-3
+            // share the per-word products with calls 0 and 1 (q = 3: seven or more ties).
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                uint32_t eq = left[v];
+                for (uint32_t q = 2; __any_sync(__activemask(), eq != 0u); ++q) {
+                    uint32_t r2[4];
+                    ph.finish_call(v, q, site, sweep, pk, r2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t bit = eq & (0u - eq);
+                        uint32_t acc = lt_mask(r2[j], mx.low[0], mx.one);
+                        acc = (lm1[v] & lt_mask(r2[j], mx.low[1], mx.one)) | (~lm1[v] & acc);
+                        if (DIM == 3) acc = (lm2[v] & lt_mask(r2[j], mx.low[2], mx.one)) | (~lm2[v] & acc);
+                        extra[v] |= bit & acc;
+                        eq -= bit;
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) s[v] ^= extra[v];
+        }
+        if (!kVote && any_left) {  // a word with three or more ties (rare)
 #pragma unroll
             for (int v = 0; v < V; ++v)
                 if (left[v])
@@ -515,13 +565,13 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
 }
 
 template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
-__global__ void __launch_bounds__(256, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB) k_sweep_rows(const __grid_constant__ RowsArgs a) {
+__global__ void __launch_bounds__(ISING_ROWS_THREADS, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB) k_sweep_rows(const __grid_constant__ RowsArgs a) {
     extern __shared__ uint32_t sm[];
     sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>(a, sm);
 }
 
 template <int DIM, bool PMJ, int V, bool MULTIROW>
-__global__ void __launch_bounds__(256, 3) k_nsat_rows(const __grid_constant__ RowsArgs a) {
+__global__ void __launch_bounds__(ISING_ROWS_THREADS, ISING_ROWS_MINB) k_nsat_rows(const __grid_constant__ RowsArgs a) {
     extern __shared__ uint32_t sm[];
     sweep_rows_phase<DIM, PMJ, 6, 7, V, true, MULTIROW, true>(a, sm);
 }
@@ -729,7 +779,7 @@ __device__ __forceinline__ void sweep_rows_tma_phase(const RowsTmaArgs& ta, unsi
 }
 
 template <int DIM, bool PMJ, int K, int ROUNDS, bool ACC>
-__global__ void __launch_bounds__(256, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_TMA_MINB)
+__global__ void __launch_bounds__(ISING_ROWS_THREADS, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_TMA_MINB)
 k_sweep_rows_tma(const __grid_constant__ RowsTmaArgs ta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     sweep_rows_tma_phase<DIM, PMJ, K, ROUNDS, ACC>(ta, smem_raw);

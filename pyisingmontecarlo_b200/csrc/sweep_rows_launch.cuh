@@ -44,7 +44,7 @@ static bool rows_shape(const Layout& L, uint32_t V, RowsShape* out) {
     const uint32_t groups = L.W / V;
     RowsShape s;
     s.wx = groups >= 32 ? 32 : pow2_ceil(groups);
-    const uint32_t by = 256 / s.wx;
+    const uint32_t by = ISING_ROWS_THREADS / s.wx;
     s.bxh = pow2_ceil(L.Lxh);
     if (s.bxh > by) s.bxh = by;
     s.nrs = by / s.bxh;

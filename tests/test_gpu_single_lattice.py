@@ -92,6 +92,21 @@ def test_strips_reproduce_single_strip(native):
     assert (np.concatenate([p.rows() for p in parts]) == whole.rows()).all()
 
 
+def test_fused_two_colour_sweep_matches_mirror_and_phases(native):
+    """The single-pass sweep (both colours, out of place, bands with redundant halo rows) against the
+    CPU mirror and the two-phase path.  Opt-in (ISING_STRIP_FUSE=1: it is slower than two launches,
+    strip.cu); switched on, and forced on for short bands, in a process of its own."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ({}, {"ISING_STRIP_NO_TMA": "1"}):      # rows staged by TMA / loaded by the warps
+        env = dict(os.environ, ISING_STRIP_FUSE="1", ISING_STRIP_FUSE_MIN_ROWS="1", **extra)
+        res = subprocess.run([sys.executable, os.path.join(root, "tests", "strip_fused_check.py")],
+                             capture_output=True, text=True, timeout=600, env=env)
+        assert "STRIP_FUSED_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
 def test_large_lattice_vs_onsager(native):
     """8192 x 8192 single lattice (64 Mi spins): equilibrium energy and magnetisation on both
     sides of T_c against Onsager."""
