@@ -26,6 +26,9 @@ k_strip_phase(uint32_t* __restrict__ spins, const __grid_constant__ StripGeom g,
     const uint32_t groups = g.Wr / V;
     const uint32_t o = 1u - c;
     VCount<1> unused[V];
+    // programmatic dependent launch: the next phase is scheduled while this one drains
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // block = (x over the word groups of a row, y over rows): storage rows [r_begin, r_begin + r_count)
     for (uint32_t rr = blockIdx.y * blockDim.y + threadIdx.y; rr < r_count; rr += gridDim.y * blockDim.y)
     for (uint32_t jg = blockIdx.x * blockDim.x + threadIdx.x; jg < groups; jg += gridDim.x * blockDim.x) {
@@ -65,9 +68,8 @@ static int strip_phase_dispatch(const StripSweepArgs& a, cudaStream_t st) {
     if (gy > gy_cap) gy = gy_cap;
     const dim3 grid(gx, gy, 1);
 #define STRIP_LAUNCH(KK, RR)                                                                     \
-    k_strip_phase<KK, RR, V><<<grid, block, 0, st>>>(a.spins, a.g, a.colour, a.sweep,              \
-                                                     philox_round_keys(a.key0, a.key1), a.antiferro, \
-                                                     make_mux(a.th), a.r_begin, a.r_count)
+    launch_pdl_v(k_strip_phase<KK, RR, V>, grid, block, 0, st, a.spins, a.g, a.colour, a.sweep,    \
+                 philox_round_keys(a.key0, a.key1), a.antiferro, make_mux(a.th), a.r_begin, a.r_count)
 #define STRIP_ROUNDS(KK)                                                                         \
     do { if (a.rounds == 7) STRIP_LAUNCH(KK, 7); else STRIP_LAUNCH(KK, 10); } while (0)
     switch (a.planes) {

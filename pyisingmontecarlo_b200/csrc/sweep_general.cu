@@ -22,6 +22,19 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
     constexpr int NPL = DEG == 0 ? 4 : (DEG < 2 ? 1 : (DEG < 4 ? 2 : (DEG < 8 ? 3 : 4)));
     const uint32_t deg = DEG > 0 ? (uint32_t)DEG : g.deg;
     const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
+    // Programmatic dependent launch (as the row walk, sweep_rows.cuh): the next colour group may be
+    // scheduled while this one drains; the graph arrays of this thread's first site - constant data -
+    // are pulled towards the SM before the wait, the spins are not touched until after it.
+    asm volatile("griddepcontrol.launch_dependents;");
+    {
+        const uint32_t i0 = blockIdx.x * blockDim.y + threadIdx.y;
+        if (i0 < g.count) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g.sites + i0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g.anti + i0));
+            for (uint32_t k = 0; k < deg; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.nbr + (size_t)k * g.count + i0));
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // block = (wx lanes over replica word groups, by over sites): no division to split an item index
     for (uint32_t i = blockIdx.x * blockDim.y + threadIdx.y; i < g.count; i += gridDim.x * blockDim.y)
     for (uint32_t w0 = threadIdx.x * V; w0 < W; w0 += blockDim.x * V) {
@@ -169,11 +182,11 @@ static void gen_launch(const GenSweepArgs& a, const GenGroup& g, cudaStream_t st
     const dim3 grid((unsigned)blocks);
     const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
     if (a.tables.plane != nullptr)
-        k_sweep_general<K, ROUNDS, true, DEG, V><<<grid, block, 0, st>>>(a.spins, g, a.W, a.sweep, pk, a.gw0,
-                                                                         a.th, a.tables);
+        launch_pdl_v(k_sweep_general<K, ROUNDS, true, DEG, V>, grid, block, 0, st, a.spins, g, a.W, a.sweep, pk, a.gw0,
+                     a.th, a.tables);
     else
-        k_sweep_general<K, ROUNDS, false, DEG, V><<<grid, block, 0, st>>>(a.spins, g, a.W, a.sweep, pk, a.gw0,
-                                                                          a.th, a.tables);
+        launch_pdl_v(k_sweep_general<K, ROUNDS, false, DEG, V>, grid, block, 0, st, a.spins, g, a.W, a.sweep, pk, a.gw0,
+                     a.th, a.tables);
 }
 
 // degree-specialised kernels only for the default (K, rounds)

@@ -417,8 +417,10 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
     // Programmatic dependent launch: the next colour phase may be scheduled while this one
     // drains (its blocks start as SMs free up and run their preamble), and this phase must not
     // touch the spins before the previous one has completed.  No-ops on an ordinary launch.
+    // The wait sits behind the first chunk's row geometry (which touches no spins): that part of the
+    // preamble overlaps the tail of the previous phase as well.
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool waited = false;
 
     VCount<ACC ? SW_NP : 1> vc[V];
     if constexpr (ACC) {
@@ -459,6 +461,10 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
                 d.par_tile = 0xFFFFFFFFu;
             }
             s_desc[i] = d;
+        }
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            waited = true;
         }
         __syncthreads();
         for (uint32_t k = 0; k < nu; ++k) {

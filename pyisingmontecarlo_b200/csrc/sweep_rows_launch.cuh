@@ -6,27 +6,6 @@
 
 namespace ising {
 
-// Launch with programmatic stream serialisation: consecutive colour phases overlap launch latency
-// and preamble with the tail of the previous phase (the kernels order themselves with
-// griddepcontrol.wait).  Measured on BASELINE config 3: 61.8 -> 59.3 us per sweep at 1024
-// replicas, 16.4 -> 11.5 us at 128 replicas per GPU (the 8-GPU split).  ISING_NO_PDL=1 launches
-// the ordinary way (A/B knob).
-template <typename Kern, typename Args>
-static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Args& args) {
-    static const bool no_pdl = getenv("ISING_NO_PDL") != nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, args);
-}
-
 static uint32_t log2_exact(uint32_t v) {
     uint32_t lg = 0;
     while ((1u << lg) < v) ++lg;
@@ -61,6 +40,12 @@ static bool rows_shape(const Layout& L, uint32_t V, RowsShape* out) {
 // one resident wave of blocks; every block gets a balanced, contiguous range of units
 static void rows_partition(RowsArgs& ra, int per_sm, int sms, uint32_t* grid) {
     uint32_t g = (uint32_t)(per_sm * sms);
+    // A/B knob: a grid that fills only part of the resident slots lets the blocks of the next colour
+    // phase (programmatic dependent launch) become resident and run their preamble while this
+    // phase still computes
+    static const int grid_pct = getenv("ISING_ROWS_GRID_PCT") ? atoi(getenv("ISING_ROWS_GRID_PCT")) : 100;
+    if (grid_pct > 0 && grid_pct < 100) g = (uint32_t)((uint64_t)g * grid_pct / 100);
+    if (g < 1) g = 1;
     if (g > ra.units) g = ra.units;
     ra.uq = ra.units / g;
     ra.urem = ra.units % g;
