@@ -654,7 +654,7 @@ def run_b200(args, w, world, rank, local):
 
         def step_e2e():
             lat.set_initial_state(init)  # N bools H2D inside the call
-            en, stt = lat.run_monte_carlo_annealing_and_get_energies(stops, w["sweeps"], E_total)
+            en, stt = lat.run_monte_carlo_annealing_and_get_energies(stops, w["sweeps"], E_total, only_basic_moves=True)
             return float(en[0, -1]) + float(stt[0, 0])
 
         for _ in range(min(args.warmup, 2)):

@@ -13,8 +13,11 @@ namespace ising {
 // DEG > 0: compile-time degree (neighbour loads unrolled and in flight together); DEG = 0: runtime.
 // V consecutive replica words of a site per thread: one index load / address computation and one
 // 4V-byte gather per neighbour for V words (needs W % V == 0).
+#ifndef ISING_GEN_MINB
+#define ISING_GEN_MINB 4   // resident blocks per SM the general sweep is compiled for
+#endif
 template <int K, int ROUNDS, bool PERBETA, int DEG, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, ISING_GEN_MINB)
 k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t sweep, PhiloxKeys pk,
                 uint32_t gw0, GenThresholds th, GenTables tab) {
     constexpr int NCALL = K / 4 + 1;

@@ -570,8 +570,16 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
     }
 }
 
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW>
-__global__ void __launch_bounds__(ISING_ROWS_THREADS, ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB) k_sweep_rows(const __grid_constant__ RowsArgs a) {
+// SMALL: the same kernel compiled for blocks of 128 threads, 7 (plain) / 4 (accumulating) of them per
+// SM.  When a colour phase has only one or two site groups per resident thread (the 8-GPU split of
+// config 3: 128 replicas per GPU), 1024 units of 128 threads fit the 148 x 7 slots in ONE wave where
+// 512 units of 256 threads need a second, mostly empty one (profiles/r02_small_w_ab.log: 20.9 ->
+// 18.6 us per sweep with energies at 128 replicas; at 512 and more the 256-thread shape is faster).
+constexpr int ROWS_SMALL_THREADS = 128;
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool SMALL = false>
+__global__ void __launch_bounds__(SMALL ? ROWS_SMALL_THREADS : ISING_ROWS_THREADS,
+                                  SMALL ? (ACC ? 4 : 7) : (ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB))
+k_sweep_rows(const __grid_constant__ RowsArgs a) {
     extern __shared__ uint32_t sm[];
     sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>(a, sm);
 }

@@ -19,11 +19,11 @@ struct RowsShape {
     uint64_t units;
 };
 
-static bool rows_shape(const Layout& L, uint32_t V, RowsShape* out) {
+static bool rows_shape(const Layout& L, uint32_t V, RowsShape* out, uint32_t threads = ISING_ROWS_THREADS) {
     const uint32_t groups = L.W / V;
     RowsShape s;
     s.wx = groups >= 32 ? 32 : pow2_ceil(groups);
-    const uint32_t by = ISING_ROWS_THREADS / s.wx;
+    const uint32_t by = threads / s.wx;
     s.bxh = pow2_ceil(L.Lxh);
     if (s.bxh > by) s.bxh = by;
     s.nrs = by / s.bxh;
@@ -52,11 +52,11 @@ static void rows_partition(RowsArgs& ra, int per_sm, int sms, uint32_t* grid) {
     *grid = g;
 }
 
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT>
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT, bool SMALL = false>
 static int rows_launch(RowsArgs& ra, const RowsShape& sh, int sms, cudaStream_t st) {
     void (*kern)(const RowsArgs);
     if constexpr (COUNT) kern = k_nsat_rows<DIM, PMJ, V, MULTIROW>;
-    else kern = k_sweep_rows<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>;
+    else kern = k_sweep_rows<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW, SMALL>;
     const dim3 block(sh.wx, sh.bxh * sh.nrs, 1);
     const int nthreads = block.x * block.y;
     const int planes = SW_NP * V > NS_NR ? SW_NP * V : NS_NR;
@@ -140,7 +140,14 @@ static int rows_phase(const SweepArgs& a, cudaStream_t st, uint32_t c, int mode)
     const size_t csz = (size_t)L.halfN * L.W;
     if (csz / V > 0xFFFFFFFFull || L.nvars > 0xFFFFFFFFull) return 0;  // 32-bit element offsets
     RowsShape sh;
-    if (!rows_shape(L, V, &sh)) return 0;
+    // few site groups per resident thread: the 128-thread shape (k_sweep_rows<..., SMALL>)
+    static const bool no_small = getenv("ISING_ROWS_NO_SMALL") != nullptr;   // A/B knob
+    const int sms0 = a.sm_count > 0 ? a.sm_count : (int)device_sms();
+    static const bool tma_env = getenv("ISING_TMA") != nullptr;
+    bool small = V == 4 && mode != 2 && !no_small && !tma_env && ISING_ROWS_THREADS == 256 &&
+                 (uint64_t)L.halfN * (L.W / V) * 2u < (uint64_t)sms0 * 768u * (mode == 1 ? 5u : 3u);   // < 2.5 / 1.5 per thread
+    if (small && (!rows_shape(L, V, &sh, ROWS_SMALL_THREADS) || sh.bxh * sh.nrs < (uint32_t)V)) small = false;
+    if (!small && !rows_shape(L, V, &sh)) return 0;
     const bool acc = mode != 0;
     if (acc && sh.bxh * sh.nrs < (uint32_t)V) return 0;  // the block reduction wants >= V thread rows
     RowsArgs ra;
@@ -171,6 +178,15 @@ static int rows_phase(const SweepArgs& a, cudaStream_t st, uint32_t c, int mode)
         if (rc != 0) return rc;
     }
 #endif
+    if constexpr (V == 4) {
+        if (small) {
+            if (sh.nrs > 1)
+                return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, true, false, true>(ra, sh, sms, st)
+                           : rows_launch<DIM, PMJ, K, ROUNDS, V, false, true, false, true>(ra, sh, sms, st);
+            return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, false, false, true>(ra, sh, sms, st)
+                       : rows_launch<DIM, PMJ, K, ROUNDS, V, false, false, false, true>(ra, sh, sms, st);
+        }
+    }
     if (sh.nrs > 1)
         return acc ? rows_launch<DIM, PMJ, K, ROUNDS, V, true, true, false>(ra, sh, sms, st)
                    : rows_launch<DIM, PMJ, K, ROUNDS, V, false, true, false>(ra, sh, sms, st);

@@ -25,6 +25,17 @@ _U64 = 2**64 - 1
 _warned_basic_moves = False
 
 
+def _user_stacklevel():
+    """stacklevel that points a warning at the first frame outside this package"""
+    import sys
+
+    here = __name__.rsplit(".", 1)[0]
+    level, f = 1, sys._getframe(1)
+    while f is not None and f.f_globals.get("__name__", "").startswith(here):
+        level, f = level + 1, f.f_back
+    return level
+
+
 def warn_non_basic_moves(only_basic_moves):
     """Deviation D1, said out loud once per process: with only_basic_moves None / False the
     reference's timestep also performs two-spin edge flips and worm updates (lattice.rs:205,
@@ -39,7 +50,7 @@ def warn_non_basic_moves(only_basic_moves):
                   "(same equilibrium distribution, different dynamics; see DESIGN.md deviation D1). "
                   "Pass only_basic_moves=True to state that this is what you want, or set "
                   "Lattice.non_basic_moves = True to run this engine's edge and worm moves as well.",
-                  UserWarning, stacklevel=4)
+                  UserWarning, stacklevel=_user_stacklevel())
 
 
 def _edges_to_arrays(edges):

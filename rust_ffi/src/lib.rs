@@ -28,6 +28,19 @@ pub struct ising_pt {
 pub const ISING_FLAG_PER_STEP_ENERGIES: u32 = 1 << 1;
 pub const ISING_FLAG_LINEAR_SCHEDULE: u32 = 1 << 2;
 pub const ISING_FLAG_EDGE_IMPORTANCE: u32 = 1 << 3;
+pub const ISING_FLAG_NON_BASIC_MOVES: u32 = 1 << 4;
+
+/// What one timestep consists of (ising_sim_set_moves): the nspinupdates / nedgeupdates /
+/// nwormupdates of GraphState::do_time_step in units of whole passes (classicising.rs:100-106).
+#[repr(C)]
+pub struct ising_moves {
+    pub struct_size: u32,
+    pub spin_sweeps: u32,
+    pub edge_passes: u32,
+    pub worms: u32,
+    pub worm_len: u32,
+    pub edge_importance: u32,
+}
 
 #[repr(C)]
 pub struct ising_run_args {
@@ -80,6 +93,7 @@ extern "C" {
         out: *mut *mut ising_sim,
     ) -> c_int;
     pub fn ising_sim_destroy(sim: *mut ising_sim);
+    pub fn ising_sim_set_moves(sim: *mut ising_sim, moves: *const ising_moves) -> c_int;
     pub fn ising_sim_set_states(sim: *mut ising_sim, states: *const u8) -> c_int;
     pub fn ising_sim_sweeps(
         sim: *mut ising_sim, betas: *const f64, nsweeps: u64, energies_per_sweep: *mut f64,
