@@ -118,7 +118,8 @@ static int cluster_launch(const SweepArgs& a, const MscThresholds* th_dev, uint3
         if (rc > 0) return rc;
         cudaGetLastError();
     }
-    return cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC, PERBETA>(a, th_dev, nsweeps, hist, cw, st, 8);
+    return cluster_launch_n<DIM, PMJ, ROUNDS, V, ACC, PERBETA>(a, th_dev, nsweeps, hist, cw, st,
+                                                               max_cta >= 8 ? 8u : (uint32_t)(max_cta < 1 ? 1 : max_cta));
 }
 
 template <int DIM, bool PMJ, int V>
