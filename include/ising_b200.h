@@ -92,6 +92,10 @@ ISING_API void ising_graph_destroy(ising_graph *g);
 ISING_API int ising_graph_get_info(const ising_graph *g, ising_graph_info *out);
 ISING_API int ising_graph_get_colors(const ising_graph *g, uint32_t *colors /* nvars */);
 ISING_API int ising_graph_get_edges(const ising_graph *g, uint64_t *a, uint64_t *b, double *j);
+/* Class of every bond in the strong edge colouring the two-spin edge moves are launched by
+ * (ising_sim_set_moves): cls[nedges], two bonds of a class share no site and no bond joins them.
+ * The CPU mirror of the tests needs it to replay a pass in the library's order. */
+ISING_API int ising_graph_get_edge_classes(ising_graph *g, uint32_t *cls);
 
 /* ---- seeds (Lattice::make_seeds, lattice.rs:83-91, seed_gen = Some(seed)) ---------------- */
 ISING_API int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t *out);

@@ -197,6 +197,90 @@ ORC_EXPORT int msc_mirror_run(uint64_t nvars, uint64_t nedges, const uint64_t *e
     return 0;
 }
 
+/* One pass of two-spin edge moves (pyisingmontecarlo_b200/csrc/moves.cu: k_edge_general), the
+ * classes of the library's strong edge colouring one after the other.  The pair (a, b) counts the
+ * satisfied bonds among its D outer bonds (adjacency entries of a and b that do not lead to the
+ * other end); dE = 2|J|(2 n_sat - D); same threshold / plane / resolver rule as a site of degree D,
+ * on the stream (edge, replica word, timestep, call | pass << 8 | 4 << 24). */
+static uint32_t edge_stream_word(int rounds, uint32_t eid, uint32_t gw, uint32_t sweep, uint32_t pass,
+                                 uint32_t m, uint32_t k0, uint32_t k1) {
+    uint32_t c[4] = {eid, gw, sweep, (m >> 2) | (pass << 8) | (4u << 24)};
+    philox4x32(rounds, c, k0, k1);
+    return c[m & 3];
+}
+
+static void mirror_edge_pass(const mirror_t *m, const uint32_t *edge_cls, uint32_t ncls, uint64_t E,
+                             uint8_t *states, double beta, uint32_t sweep, uint32_t pass) {
+    const uint64_t W = (E + 31) / 32, nvars = m->nvars;
+    const int K = m->K;
+    for (uint32_t c = 0; c < ncls; ++c)
+        for (uint64_t e = 0; e < m->nedges; ++e) {
+            if (edge_cls[e] != c) continue;
+            const uint64_t end[2] = {m->ea[e], m->eb[e]};
+            for (uint64_t w = 0; w < W; ++w) {
+                int j = 0;
+                for (uint64_t b = 0; b < 32 && w * 32 + b < E; ++b) {
+                    uint8_t *st = states + (w * 32 + b) * nvars;
+                    int nsat = 0, d = 0;
+                    for (int s = 0; s < 2; ++s) {
+                        const uint64_t u = end[s], other = end[1 - s];
+                        for (uint64_t k = m->row[u]; k < m->row[u + 1]; ++k) {
+                            if (m->nbr[k] == other) continue;
+                            const int equal = st[u] == st[m->nbr[k]];
+                            nsat += m->anti[k] ? !equal : equal;
+                            ++d;
+                        }
+                    }
+                    const int cls = 2 * nsat - d;
+                    int accept = 1;
+                    if (cls > 0) {
+                        const uint64_t T = threshold(beta, 2.0 * m->jabs * (double)cls, K);
+                        int decided = 0;
+                        accept = 0;
+                        for (int p = 0; p < K && !decided; ++p) {
+                            const uint32_t rb = (edge_stream_word(m->rounds, (uint32_t)e, m->gw0 + (uint32_t)w, sweep,
+                                                                  pass, (uint32_t)p, m->k0, m->k1) >> b) & 1u;
+                            const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
+                            if (rb != tb) { decided = 1; accept = rb < tb; }
+                        }
+                        if (!decided) {
+                            const uint32_t v = edge_stream_word(m->rounds, (uint32_t)e, m->gw0 + (uint32_t)w, sweep,
+                                                                pass, (uint32_t)(K + j), m->k0, m->k1);
+                            accept = v < (uint32_t)(T & 0xFFFFFFFFull);
+                            ++j;
+                        }
+                    }
+                    if (accept) { st[end[0]] ^= 1; st[end[1]] ^= 1; }
+                }
+            }
+        }
+}
+
+/* Timesteps of [one colour-class sweep] + edge_passes passes of edge moves, one beta per timestep
+ * (ising_sim_set_moves with worms = 0).  states bool[E, nvars] in/out, filled from Philox when
+ * randomize != 0; energies_per_step double[E, nsteps] or NULL. */
+ORC_EXPORT int msc_mirror_moves(uint64_t nvars, uint64_t nedges, const uint64_t *ea, const uint64_t *eb,
+                                const double *ej, const uint32_t *colors, uint32_t ncolors,
+                                const uint32_t *edge_cls, uint32_t nedge_cls, uint64_t E, uint64_t seed,
+                                uint64_t replica_offset, int K, int rounds, int randomize, const double *betas,
+                                uint64_t nsteps, int spin_sweeps, uint32_t edge_passes, uint8_t *states,
+                                double *energies_per_step) {
+    mirror_t m;
+    int rc = mirror_init(&m, nvars, nedges, ea, eb, ej, colors, ncolors, seed, replica_offset, K, rounds);
+    if (rc) return rc;
+    if (randomize) mirror_randomize(&m, E, states);
+    for (uint64_t t = 0; t < nsteps; ++t) {
+        if (spin_sweeps) mirror_sweep(&m, E, states, betas + t, 0, (uint32_t)t);
+        for (uint32_t pass = 0; pass < edge_passes; ++pass)
+            mirror_edge_pass(&m, edge_cls, nedge_cls, E, states, betas[t], (uint32_t)t, pass);
+        if (energies_per_step)
+            for (uint64_t e = 0; e < E; ++e)
+                energies_per_step[e * nsteps + t] = mirror_energy(&m, states + e * nvars);
+    }
+    mirror_free(&m);
+    return 0;
+}
+
 /* exp(d), d <= 0, as the fixed sequence of IEEE double operations the device's swap kernel and
  * ising_pt_decide_swaps use (pyisingmontecarlo_b200/csrc/pt_exp.h), restated here so that the
  * mirror's swap decisions are bit-identical to the device's: d = k ln2 + r, degree-13 Taylor

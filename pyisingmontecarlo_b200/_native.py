@@ -104,6 +104,7 @@ _SIGNATURES = {
     "ising_graph_get_info": (C.c_int, [_P, C.POINTER(GraphInfo)]),
     "ising_graph_get_colors": (C.c_int, [_P, _P]),
     "ising_graph_get_edges": (C.c_int, [_P, _P, _P, _P]),
+    "ising_graph_get_edge_classes": (C.c_int, [_P, _P]),
     "ising_make_seeds": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
     "ising_sim_create": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
     "ising_sim_create_ex": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
@@ -347,6 +348,12 @@ class Graph:
     def colors(self):
         out = np.empty(self.nvars, dtype=np.uint32)
         check(lib().ising_graph_get_colors(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def edge_classes(self):
+        """class of every bond in the strong edge colouring of the edge moves (uint32[nedges])"""
+        out = np.empty(self.nedges, dtype=np.uint32)
+        check(lib().ising_graph_get_edge_classes(self.handle, ptr(out)), self.ctx.handle)
         return out
 
     def edges(self):

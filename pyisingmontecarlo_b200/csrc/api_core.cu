@@ -303,7 +303,92 @@ int ensure_moves_on_device(ising_ctx* ctx, ising_graph* g) {
     CUDA_TRY(ctx, cudaMemcpy(g->d_meid, ec.eid.data(), ec.eid.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(g->d_mwrel, ec.wrel.data(), ec.wrel.size() * 4, cudaMemcpyHostToDevice));
     g->medge_off = ec.off;
+    g->medge = std::move(ec);
     g->moves_built = true;
+    return ISING_OK;
+}
+
+// (class, outer degree) groups of the bit-sliced edge-move kernel (moves.cu: k_edge_general)
+int ensure_edge_general_on_device(ising_ctx* ctx, ising_graph* g, bool stencil_layout) {
+    ising_graph::EdgeGen& eg = g->edge_gen[stencil_layout ? 1 : 0];
+    if (eg.built) return ISING_OK;
+    int rc = ensure_moves_on_device(ctx, g);
+    if (rc) return rc;
+    HostGraph& h = g->h;
+    eg.built = true;
+    eg.usable = false;
+    if (!h.integer_classes) return ISING_OK;
+    const EdgeClasses& ec = g->medge;
+    const uint64_t M = ec.ea.size();
+    const uint64_t Lx = h.dims[0], Ly = h.dims[1], Lxh = Lx / 2, rows = h.dims[1] * h.dims[2];
+    auto slot = [&](uint32_t n) -> uint32_t {
+        if (!stencil_layout) return n;
+        const uint64_t x = n % Lx, r = n / Lx, y = r % Ly, z = r / Ly;
+        const uint64_t c = (x + y + z) & 1u;
+        return (uint32_t)((c * rows + r) * Lxh + (x >> 1));
+    };
+    // outer bonds of every edge: the adjacency entries of a and of b that do not lead to the other end
+    struct Item { uint32_t sa, sb, eid, anti, endp, deg; uint32_t nb[GEN_MAX_DEG]; };
+    std::vector<Item> items(M);
+    for (uint64_t i = 0; i < M; ++i) {
+        Item& it = items[i];
+        const uint32_t a = ec.ea[i], b = ec.eb[i];
+        it.sa = slot(a); it.sb = slot(b); it.eid = ec.eid[i]; it.anti = 0; it.endp = 0; it.deg = 0;
+        for (int end = 0; end < 2; ++end) {
+            const uint32_t u = end ? b : a, other = end ? a : b;
+            for (uint64_t k = h.row[u]; k < h.row[u + 1]; ++k) {
+                if (h.nbr[k] == other) continue;
+                if (it.deg >= (uint32_t)GEN_MAX_DEG) return ISING_OK;   // too many outer bonds: float kernel
+                if (h.jv[k] > 0) it.anti |= 1u << it.deg;
+                if (end) it.endp |= 1u << it.deg;
+                it.nb[it.deg++] = slot(h.nbr[k]);
+            }
+        }
+    }
+    // blob layout per group: sa | sb | eid | anti | endp | nbr[deg][count]
+    std::vector<uint32_t> blob;
+    struct Off { size_t at; uint32_t count, deg; };
+    std::vector<Off> offs;
+    for (size_t c = 0; c + 1 < ec.off.size(); ++c)
+        for (uint32_t d = 0; d <= (uint32_t)GEN_MAX_DEG; ++d) {
+            std::vector<uint32_t> idx;
+            for (uint32_t i = ec.off[c]; i < ec.off[c + 1]; ++i)
+                if (items[i].deg == d) idx.push_back(i);
+            if (idx.empty()) continue;
+            const uint32_t n = (uint32_t)idx.size();
+            Off o{blob.size(), n, d};
+            blob.resize(blob.size() + (size_t)(5 + d) * n);
+            uint32_t* p = blob.data() + o.at;
+            for (uint32_t q = 0; q < n; ++q) {
+                const Item& it = items[idx[q]];
+                p[q] = it.sa; p[n + q] = it.sb; p[2 * n + q] = it.eid; p[3 * n + q] = it.anti; p[4 * n + q] = it.endp;
+                for (uint32_t k = 0; k < d; ++k) p[(size_t)(5 + k) * n + q] = it.nb[k];
+            }
+            offs.push_back(o);
+        }
+    CUDA_TRY(ctx, dev_alloc(&eg.d_blob, blob.size()));
+    CUDA_TRY(ctx, cudaMemcpy(eg.d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+    for (const Off& o : offs) {
+        EdgeGroup gr;
+        const uint32_t* p = eg.d_blob + o.at;
+        gr.sa = p; gr.sb = p + o.count; gr.eid = p + 2 * (size_t)o.count; gr.anti = p + 3 * (size_t)o.count;
+        gr.endp = p + 4 * (size_t)o.count; gr.nbr = p + 5 * (size_t)o.count;
+        gr.count = o.count; gr.deg = o.deg;
+        eg.groups.push_back(gr);
+    }
+    eg.usable = true;
+    return ISING_OK;
+}
+
+extern "C" int ising_graph_get_edge_classes(ising_graph* g, uint32_t* cls) {
+    CtxLock _lk(g ? g->ctx : nullptr);
+    if (!g || !cls) return fail(nullptr, ISING_E_INVALID, "graph/cls is NULL");
+    CUDA_TRY(g->ctx, cudaSetDevice(g->ctx->device));
+    const int rc = ensure_moves_on_device(g->ctx, g);
+    if (rc) return rc;
+    const EdgeClasses& ec = g->medge;
+    for (size_t c = 0; c + 1 < ec.off.size(); ++c)
+        for (uint32_t i = ec.off[c]; i < ec.off[c + 1]; ++i) cls[ec.eid[i]] = (uint32_t)c;
     return ISING_OK;
 }
 
@@ -428,6 +513,8 @@ extern "C" void ising_graph_destroy(ising_graph* g) {
     cudaFree(g->d_meb);
     cudaFree(g->d_meid);
     cudaFree(g->d_mwrel);
+    cudaFree(g->edge_gen[0].d_blob);
+    cudaFree(g->edge_gen[1].d_blob);
     delete g;
 }
 

@@ -90,6 +90,14 @@ struct ising_graph {
     uint32_t* d_meid = nullptr;
     float* d_mwrel = nullptr;
     std::vector<uint32_t> medge_off;   // nclasses + 1 offsets into the four arrays
+    EdgeClasses medge;                 // host copy (class of every bond: ising_graph_get_edge_classes)
+    // bit-sliced edge moves (integer classes): (class, outer degree) groups in ELL form, built on
+    // demand once per spin layout ([0] natural order, [1] checkerboard) because they hold slots
+    struct EdgeGen {
+        bool built = false, usable = false;
+        std::vector<EdgeGroup> groups;   // in class order
+        uint32_t* d_blob = nullptr;
+    } edge_gen[2];
 };
 
 struct ising_comm;
@@ -177,6 +185,7 @@ int ensure_csr32_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_real_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_general_on_device(ising_ctx* ctx, ising_graph* g);
 int ensure_moves_on_device(ising_ctx* ctx, ising_graph* g);
+int ensure_edge_general_on_device(ising_ctx* ctx, ising_graph* g, bool stencil_layout);
 // simulation object (api_sim.cu)
 void count_launch(ising_sim* s, int n);
 uint64_t threshold64(double beta, double de, int K);

@@ -318,7 +318,36 @@ static int sim_non_basic_moves(ising_sim* s, double beta, uint64_t t) {
     const ising_graph* g = s->g;
     const MoveGraph mg{g->d_row32, g->d_nbr32, g->d_jf, g->d_biasf};
     int launches = 0;
-    for (uint32_t pass = 0; pass < s->mv.edge_passes; ++pass)
+    // all |J| equal, no bias, <= 15 outer bonds per pair: the bit-sliced kernel with exact integer
+    // thresholds (importance sampling weights every bond alike there); else float local fields
+    const ising_graph::EdgeGen& eg = g->edge_gen[s->general ? 0 : 1];
+    static const bool force_float = getenv("ISING_EDGE_FLOAT") != nullptr;   // A/B knob
+    const bool bitsliced = eg.usable && !s->real && !force_float;
+    for (uint32_t pass = 0; bitsliced && pass < s->mv.edge_passes; ++pass) {
+        GenSweepArgs ga;
+        ga.spins = s->d_spins;
+        ga.W = s->lay.W;
+        ga.sweep = (uint32_t)t;
+        ga.key0 = (uint32_t)s->seed;
+        ga.key1 = (uint32_t)(s->seed >> 32);
+        ga.gw0 = (uint32_t)(s->replica_offset / 32);
+        ga.planes = s->planes;
+        ga.rounds = s->rounds;
+        ga.tables.plane = nullptr;
+        ga.tables.low = nullptr;
+        uint32_t th_deg = 0xFFFFFFFFu;
+        for (const EdgeGroup& gr : eg.groups) {
+            if (gr.deg != th_deg) {
+                fill_gen_thresholds(g->h.jabs, beta, s->planes, gr.deg, &ga.th);
+                th_deg = gr.deg;
+            }
+            const int n = launch_edge_general(ga, gr, pass, ctx->stream);
+            if (n < 0) return fail(ctx, ISING_E_CUDA, "edge-move launch failed: %s",
+                                   cudaGetErrorString(cudaGetLastError()));
+            launches += n;
+        }
+    }
+    for (uint32_t pass = 0; !bitsliced && pass < s->mv.edge_passes; ++pass)
         for (size_t c = 0; c + 1 < g->medge_off.size(); ++c) {
             EdgeMoveArgs a;
             a.spins = s->d_spins;
@@ -405,7 +434,9 @@ extern "C" int ising_sim_set_moves(ising_sim* s, const ising_moves* mv) {
         return fail(ctx, ISING_E_UNSUPPORTED, "non-basic moves run at one beta per timestep, not at per-experiment betas");
     if (non_basic) {
         CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-        const int rc = ensure_moves_on_device(ctx, const_cast<ising_graph*>(s->g));
+        int rc = ensure_moves_on_device(ctx, const_cast<ising_graph*>(s->g));
+        if (rc == ISING_OK && mv->edge_passes)
+            rc = ensure_edge_general_on_device(ctx, const_cast<ising_graph*>(s->g), !s->general);
         if (rc) return rc;
     }
     s->mv = *mv;

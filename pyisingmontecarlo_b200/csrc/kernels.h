@@ -235,6 +235,19 @@ struct EdgeMoveArgs {
     int rounds;
 };
 int launch_edge_moves(const EdgeMoveArgs& a, cudaStream_t st);
+// bit-sliced edge moves (all |J| equal, no bias): the bonds of one class of the strong edge
+// colouring that see the same number of outer bonds, in ELL form; spins addressed by slot
+struct EdgeGroup {
+    const uint32_t* sa;       // [count] slot (word base / W) of end a
+    const uint32_t* sb;       // [count] slot of end b
+    const uint32_t* eid;      // [count] index in the edge list (Philox counter word 0)
+    const uint32_t* anti;     // [count] bit k set iff outer bond k has J > 0
+    const uint32_t* endp;     // [count] bit k set iff outer bond k hangs on end b
+    const uint32_t* nbr;      // [deg][count] slot of the far end of outer bond k
+    uint32_t count, deg;
+};
+// a.th = thresholds of degree g.deg (fill_gen_thresholds), a.sweep = timestep
+int launch_edge_general(const GenSweepArgs& a, const EdgeGroup& g, uint32_t pass, cudaStream_t st);
 constexpr int WORM_MAX_LEN = 8;
 struct WormArgs {
     uint32_t* spins;

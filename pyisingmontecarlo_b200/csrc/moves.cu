@@ -84,6 +84,146 @@ int launch_edge_moves(const EdgeMoveArgs& a, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// ------------------------------------------------------------------------------------------
+// Edge moves on graphs whose couplings all have the same magnitude and that carry no bias: the
+// pair (a, b) sees D = deg(a) + deg(b) - 2 (bonds between a and b) outer bonds, flipping both spins
+// turns its n_sat satisfied outer bonds into D - n_sat, so dE = 2|J|(2 n_sat - D) - the integer
+// classes of a site of degree D.  Same bit-sliced machinery as k_sweep_general (4-plane counter,
+// thresholds of degree D, K planes + resolver words, ties in ascending bit position), exact
+// integer thresholds, hence bit-exact against oracle/msc_mirror.c (msc_mirror_moves).  Philox
+// counter = (edge index, replica word, timestep, call | pass << 8 | TAG_EDGE << 24).
+// Spins are addressed by SLOT (word base / W), computed on the host for the sim's layout.
+// ------------------------------------------------------------------------------------------
+template <int K, int ROUNDS>
+__device__ __forceinline__ uint32_t edge_flip_mask(const uint32_t (&cnt)[4], uint32_t deg, uint32_t eid, uint32_t gw,
+                                                   uint32_t sweep, uint32_t tagw, const PhiloxKeys& pk,
+                                                   const GenThresholds& th) {
+    constexpr int NCALL = K / 4 + 1;
+    const uint32_t cmin = deg / 2 + 1, ncls = deg - deg / 2;
+    uint32_t oh[GEN_MAX_CLS];
+    uint32_t up = 0;
+#pragma unroll
+    for (int j = 0; j < GEN_MAX_CLS; ++j) {
+        oh[j] = 0;
+        if ((uint32_t)j < ncls) {
+            const uint32_t val = cmin + j;
+            uint32_t o = 0xFFFFFFFFu;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) o &= ((val >> l) & 1u) ? cnt[l] : ~cnt[l];
+            oh[j] = o;
+            up |= o;
+        }
+    }
+    uint32_t r[NCALL * 4];
+#pragma unroll
+    for (int q = 0; q < NCALL; ++q) {
+        const u32x4 o = philox4x32_keys<ROUNDS>(eid, gw, sweep, (uint32_t)q | tagw, pk);
+        r[4 * q + 0] = o.x; r[4 * q + 1] = o.y; r[4 * q + 2] = o.z; r[4 * q + 3] = o.w;
+    }
+    uint32_t eq = up, borrow = 0;
+#pragma unroll
+    for (int p = K - 1; p >= 0; --p) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int j = 0; j < GEN_MAX_CLS; ++j)
+            if ((uint32_t)j < ncls) t |= oh[j] & th.plane[j][p];
+        borrow = maj3(~r[p], t, borrow);
+        eq &= ~(r[p] ^ t);
+    }
+    uint32_t flip = ~up | (borrow & ~eq);
+    int jj = K;   // tied bits in ascending position: resolver words K, K + 1, ...
+    u32x4 cur = {r[4 * (NCALL - 1)], r[4 * (NCALL - 1) + 1], r[4 * (NCALL - 1) + 2], r[4 * (NCALL - 1) + 3]};
+    while (eq) {
+        const int b = __ffs((int)eq) - 1;
+        if ((jj & 3) == 0 && jj >= 4 * NCALL)
+            cur = philox4x32_keys<ROUNDS>(eid, gw, sweep, (uint32_t)(jj >> 2) | tagw, pk);
+        const int m = jj & 3;
+        const uint32_t val = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
+        uint32_t cls = 0;
+#pragma unroll
+        for (int j = 1; j < GEN_MAX_CLS; ++j)
+            if ((oh[j] >> b) & 1u) cls = j;
+        if (val < th.low[cls]) flip |= 1u << b;
+        eq &= eq - 1;
+        ++jj;
+    }
+    return flip;
+}
+
+template <int K, int ROUNDS, int V>
+__global__ void __launch_bounds__(256)
+k_edge_general(uint32_t* __restrict__ spins, EdgeGroup g, uint32_t W, uint32_t sweep, uint32_t pass, PhiloxKeys pk,
+               uint32_t gw0, GenThresholds th) {
+    const uint32_t tagw = (pass << 8) | (TAG_EDGE << 24);
+    // programmatic dependent launch: a pass is one small launch per (class, outer degree) group
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (uint32_t i = blockIdx.x * blockDim.y + threadIdx.y; i < g.count; i += gridDim.x * blockDim.y)
+    for (uint32_t w0 = threadIdx.x * V; w0 < W; w0 += blockDim.x * V) {
+        const uint32_t ab = g.anti[i], eb = g.endp[i], eid = g.eid[i];
+        uint32_t* pa = spins + (size_t)g.sa[i] * W + w0;
+        uint32_t* pb = spins + (size_t)g.sb[i] * W + w0;
+        uint32_t sa[V], sb[V];
+        load_words<V>(pa, sa);
+        load_words<V>(pb, sb);
+        uint32_t cntv[V][4];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) cntv[v][l] = 0;
+        for (uint32_t k = 0; k < g.deg; ++k) {
+            uint32_t x[V];
+            load_words<V>(spins + (size_t)g.nbr[(size_t)k * g.count + i] * W + w0, x);
+            const uint32_t m = 0u - ((ab >> k) & 1u);
+            const uint32_t e = 0u - ((eb >> k) & 1u);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint32_t s = (sa[v] & ~e) | (sb[v] & e);   // the end of the pair this bond hangs on
+                uint32_t c = ~(s ^ x[v] ^ m);                    // satisfied bond
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const uint32_t t = cntv[v][l] & c;
+                    cntv[v][l] ^= c;
+                    c = t;
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint32_t flip = edge_flip_mask<K, ROUNDS>(cntv[v], g.deg, eid, gw0 + w0 + v, sweep, tagw, pk, th);
+            sa[v] ^= flip;
+            sb[v] ^= flip;
+        }
+        store_words<V>(pa, sa);
+        store_words<V>(pb, sb);
+    }
+}
+
+template <int K, int ROUNDS>
+static int edge_general_launch(const GenSweepArgs& a, const EdgeGroup& g, uint32_t pass, cudaStream_t st) {
+    const bool v2 = a.W % 2 == 0;
+    const uint32_t groups = v2 ? a.W / 2 : a.W;
+    const uint32_t wx = groups >= 32 ? 32 : pow2_ceil(groups);
+    const dim3 block(wx, 256 / wx, 1);
+    uint64_t blocks = ((uint64_t)g.count + block.y - 1) / block.y;
+    if (blocks > (uint64_t)device_sms() * 16) blocks = (uint64_t)device_sms() * 16;
+    const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
+    cudaError_t e;
+    if (v2) e = launch_pdl_v(k_edge_general<K, ROUNDS, 2>, dim3((unsigned)blocks), block, 0, st, a.spins, g, a.W, a.sweep, pass,
+                             pk, a.gw0, a.th);
+    else e = launch_pdl_v(k_edge_general<K, ROUNDS, 1>, dim3((unsigned)blocks), block, 0, st, a.spins, g, a.W, a.sweep, pass,
+                          pk, a.gw0, a.th);
+    return e == cudaSuccess ? 1 : -1;
+}
+
+int launch_edge_general(const GenSweepArgs& a, const EdgeGroup& g, uint32_t pass, cudaStream_t st) {
+    if (g.count == 0) return 0;
+    if (g.deg > (uint32_t)GEN_MAX_DEG || a.planes < 5 || a.planes > 7) return -1;
+#define EDGE_ROUNDS(KK) (a.rounds == 7 ? edge_general_launch<KK, 7>(a, g, pass, st) : edge_general_launch<KK, 10>(a, g, pass, st))
+    return a.planes == 5 ? EDGE_ROUNDS(5) : (a.planes == 6 ? EDGE_ROUNDS(6) : EDGE_ROUNDS(7));
+#undef EDGE_ROUNDS
+}
+
 // word m of the worm's random stream: counter (experiment, worm, sweep, call | TAG_WORM << 24)
 template <int ROUNDS>
 struct WormStream {

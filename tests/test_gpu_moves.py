@@ -55,6 +55,77 @@ def test_moves_sample_the_boltzmann_law(native, moves):
     assert stats["worm_attempts"] == 80 * moves.get("worms", 0) * E
 
 
+@pytest.mark.parametrize("case", ["torus2d", "torus3d_pmj", "regular3", "irregular_pm", "general_layout"])
+def test_bit_sliced_edge_moves_match_the_mirror(native, oracle, case):
+    """Graphs with equal |J| and no bias take the bit-sliced edge-move kernel (exact integer
+    thresholds): states and per-timestep energies equal the CPU mirror's bit for bit, for the
+    checkerboard and the natural spin layout, odd experiment counts, several passes."""
+    ctx = native.Context.get(0)
+    rng = np.random.default_rng(12)
+    general_layout = False
+    if case == "torus2d":
+        g, E, passes = native.Graph.torus(ctx, (8, 6), j0=-1.0), 70, 1
+    elif case == "torus3d_pmj":
+        g, E, passes = native.Graph.torus(ctx, (4, 6, 4), j0=1.0, pmj=True, j_seed=5), 33, 2
+    elif case == "general_layout":
+        g, E, passes, general_layout = native.Graph.torus(ctx, (6, 4), j0=1.0, pmj=True, j_seed=9), 64, 1, True
+    elif case == "regular3":
+        n = 60
+        while True:
+            stubs = np.repeat(np.arange(n), 3)
+            rng.shuffle(stubs)
+            a, b = stubs[0::2], stubs[1::2]
+            if not (a == b).any() and len({(min(x, y), max(x, y)) for x, y in zip(a, b)}) == len(a):
+                break
+        g = native.Graph.from_edges(ctx, n, a.astype(np.uint64), b.astype(np.uint64), np.full(len(a), -1.0))
+        E, passes = 96, 1
+    else:   # irregular degrees (a leaf, an isolated pair), mixed signs, a multi-edge
+        edges = [(0, 1), (1, 2), (2, 0), (2, 3), (3, 4), (4, 5), (5, 6), (6, 3), (7, 8), (1, 4), (1, 4), (9, 5)]
+        a = np.array([e[0] for e in edges], dtype=np.uint64)
+        b = np.array([e[1] for e in edges], dtype=np.uint64)
+        j = np.where(rng.random(len(edges)) < 0.5, 1.0, -1.0)
+        g = native.Graph.from_edges(ctx, 10, a, b, j)
+        E, passes = 40, 3
+    betas = np.array([0.2, 0.5, 0.9, 1.4, 0.7])
+    sim = native.Sim(g, E, 31, general_layout=general_layout)
+    sim.set_moves(1, passes, 0)
+    en = sim.sweeps(betas, per_sweep_energies=True)
+    st = sim.states()
+    ea, eb, ej = g.edges()
+    en_ref, st_ref = oracle.msc_mirror_moves(ea, eb, ej, g.nvars, g.colors(), g.edge_classes(), E, 31, betas,
+                                             spin_sweeps=1, edge_passes=passes, per_step=True)
+    assert (st == st_ref).all() and (en == en_ref).all()
+    # edge moves alone (no sweep), from the state reached
+    sim2 = native.Sim(g, E, 77, general_layout=general_layout)
+    sim2.set_moves(0, 1, 0)
+    sim2.sweeps(betas[:3])
+    _, st2 = oracle.msc_mirror_moves(ea, eb, ej, g.nvars, g.colors(), g.edge_classes(), E, 77, betas[:3],
+                                     spin_sweeps=0, edge_passes=1)
+    assert (sim2.states() == st2).all()
+
+
+def test_strong_edge_colouring_is_strong(native):
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (6, 4, 4), j0=1.0, pmj=True, j_seed=1)
+    ea, eb, _ = g.edges()
+    cls = g.edge_classes()
+    adj = {}
+    for x, y in zip(ea, eb):
+        adj.setdefault(int(x), set()).add(int(y))
+        adj.setdefault(int(y), set()).add(int(x))
+    for c in range(int(cls.max()) + 1):
+        members = [(int(ea[i]), int(eb[i])) for i in np.nonzero(cls == c)[0]]
+        touched = {}
+        for k, (x, y) in enumerate(members):
+            for v in (x, y):
+                assert v not in touched, "two bonds of a class share a site"
+                touched[v] = k
+        for k, (x, y) in enumerate(members):
+            for v in (x, y):
+                for u in adj[v]:
+                    assert touched.get(u, k) == k, "a bond joins two bonds of a class"
+
+
 def test_edge_pass_at_beta_zero_flips_every_site_degree_times(native):
     # at beta = 0 every move is accepted: one pass over the bonds flips a site once per incident
     # bond, whatever the couplings - the strong edge colouring covers every bond exactly once
