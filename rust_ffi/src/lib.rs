@@ -68,6 +68,7 @@ extern "C" {
         biases: *const f64, out: *mut *mut ising_graph,
     ) -> c_int;
     pub fn ising_graph_destroy(g: *mut ising_graph);
+    pub fn ising_graph_get_edge_classes(g: *mut ising_graph, cls: *mut u32) -> c_int;
     pub fn ising_make_seeds(seed_gen: u64, n: u64, out: *mut u64) -> c_int;
     pub fn ising_run_monte_carlo(
         ctx: *mut ising_ctx, g: *const ising_graph, args: *const ising_run_args, energies: *mut f64,
