@@ -183,6 +183,10 @@ ISING_API int ising_sim_get_packed(ising_sim *sim, uint32_t *words);
 ISING_API int ising_sim_set_packed(ising_sim *sim, const uint32_t *words);
 ISING_API int ising_sim_get_counter(const ising_sim *sim, uint64_t *sweeps_done);
 ISING_API int ising_sim_set_counter(ising_sim *sim, uint64_t sweeps_done);
+/* One timestep at beta and, per experiment, the number of spins it changed (= accepted single-spin
+ * flips for the default timestep, in which every site is attempted exactly once).  The per-run
+ * acceptance metric; measured by differencing the packed state, at no cost to the sweep kernels. */
+ISING_API int ising_sim_step_acceptance(ising_sim *sim, double beta, uint64_t *changed /* E */);
 /* per-experiment magnetisation sum_i s_i */
 ISING_API int ising_sim_get_magnetization(ising_sim *sim, double *m /* E */);
 

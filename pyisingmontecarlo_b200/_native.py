@@ -123,6 +123,7 @@ _SIGNATURES = {
     "ising_sim_get_states": (C.c_int, [_P, _P]),
     "ising_sim_get_packed": (C.c_int, [_P, _P]),
     "ising_sim_get_magnetization": (C.c_int, [_P, _P]),
+    "ising_sim_step_acceptance": (C.c_int, [_P, C.c_double, _P]),
     "ising_sim_set_packed": (C.c_int, [_P, _P]),
     "ising_sim_get_counter": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "ising_sim_set_counter": (C.c_int, [_P, C.c_uint64]),
@@ -458,6 +459,12 @@ class Sim:
     def energies(self):
         out = np.empty(self.E, dtype=np.float64)
         check(lib().ising_sim_get_energies(self.handle, ptr(out)), self.ctx.handle)
+        return out
+
+    def step_acceptance(self, beta):
+        """one timestep at beta -> spins changed per experiment (uint64[E]): the accepted flips"""
+        out = np.empty(self.E, dtype=np.uint64)
+        check(lib().ising_sim_step_acceptance(self.handle, float(beta), ptr(out)), self.ctx.handle)
         return out
 
     def magnetization(self):

@@ -699,6 +699,34 @@ extern "C" int ising_sim_get_energies(ising_sim* s, double* energies) {
     return ISING_OK;
 }
 
+// Accepted flips of ONE timestep at beta, per experiment: the packed state is copied, the timestep
+// runs, and the positional popcount of before ^ after counts the spins that changed - every site
+// is attempted exactly once per colour-class sweep, so with the default timestep this is the number
+// of accepted single-spin flips.  Costs nothing on the sweep kernels' own path.
+extern "C" int ising_sim_step_acceptance(ising_sim* s, double beta, uint64_t* changed) {
+    CtxLock _lk(s ? s->ctx : nullptr);
+    if (!s || !changed) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/changed is NULL");
+    if (s->perbeta) return fail(s->ctx, ISING_E_UNSUPPORTED, "per-experiment betas: use ising_sim_sweeps");
+    ising_ctx* ctx = s->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* dv = nullptr;
+    CUDA_TRY(ctx, ctx_scratch(ctx, 0, s->spins_bytes, &dv));
+    uint32_t* before = (uint32_t*)dv;
+    CUDA_TRY(ctx, cudaMemcpyAsync(before, s->d_spins, s->spins_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int rc = sim_enqueue_sweeps(s, &beta, 1);
+    if (rc) return rc;
+    const size_t cw = (size_t)s->lay.W * 32;
+    count_launch(s, launch_xor_words(before, s->d_spins, s->spins_bytes / 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(s->d_counts, 0, cw * sizeof(unsigned long long), ctx->stream));
+    count_launch(s, launch_count_up(before, s->lay, s->d_counts, ctx->stream));
+    std::vector<unsigned long long> h(cw);
+    CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), s->d_counts, cw * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint64_t e = 0; e < s->E; ++e) changed[e] = h[e];
+    return ISING_OK;
+}
+
 extern "C" int ising_sim_get_magnetization(ising_sim* s, double* m) {
     CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !m) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/m is NULL");

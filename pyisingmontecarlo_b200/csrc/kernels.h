@@ -87,6 +87,8 @@ int launch_nsat_stencil(const uint32_t* spins, const uint32_t* jmask, const Layo
 // up[e] += number of up spins of experiment e
 int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long* up,
                     cudaStream_t st, bool pair = false);
+// a[i] ^= b[i] for n words
+int launch_xor_words(uint32_t* a, const uint32_t* b, uint64_t n, cudaStream_t st);
 int launch_overlap_from_counts(const unsigned long long* dis, uint64_t P, uint64_t nsites,
                                double* out_dev, uint64_t stride, uint64_t off, cudaStream_t st);
 int launch_init_random(uint32_t* spins, const Layout& lay, uint32_t key0, uint32_t key1,

@@ -46,6 +46,20 @@ int launch_count_up(const uint32_t* spins, const Layout& lay, unsigned long long
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// a ^= b over n words (flipped spins of a sweep: before ^ after)
+__global__ void k_xor_words(uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        a[i] ^= b[i];
+}
+
+int launch_xor_words(uint32_t* a, const uint32_t* b, uint64_t n, cudaStream_t st) {
+    uint64_t g = (n + 255) / 256;
+    if (g > device_sms() * 8u) g = device_sms() * 8u;
+    if (g == 0) g = 1;
+    k_xor_words<<<(unsigned)g, 256, 0, st>>>(a, b, n);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 // overlap of the experiment pair (2p, 2p+1) from the pair-mode counts: q = N - 2 * disagreements
 __global__ void k_overlap_from_counts(const unsigned long long* __restrict__ dis, uint64_t P,
                                       uint64_t nsites, double* __restrict__ out, uint64_t stride,

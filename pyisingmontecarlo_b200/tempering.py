@@ -188,23 +188,33 @@ class LatticeTempering:
 
     # tempering.rs:307-347 (save_to_file / read_from_file) for the classical ladder.  Unlike the
     # reference ("Does not save state of RNG") a restored ladder continues bit for bit: the RNG
-    # is counter-based, so seed + counters are its whole state.  Single rank only.
+    # is counter-based, so seed + counters are its whole state.  A ladder that is sharded over ranks
+    # writes one file per rank (path + ".rank<r>of<n>": the rank's configurations, the shared slot
+    # permutation and counters) and is read back by the same number of ranks.
+    @staticmethod
+    def _rank_path(path, coll):
+        return f"{path}.rank{coll.rank}of{coll.world}" if coll.active else path
+
     def save_to_file(self, path):
         pt = self._ensure()
-        if self._coll.active:
-            raise NotImplementedError("checkpointing a ladder that is sharded over ranks")
         ck = pt.checkpoint()
-        with open(path, "wb") as f:
+        with open(self._rank_path(path, self._coll), "wb") as f:
             np.savez_compressed(f, kind="LatticeTempering", a=self._a, b=self._b, j=self._j,
-                                betas=np.asarray(self._betas), seed=np.uint64(pt.seed), **ck)
+                                betas=np.asarray(self._betas), seed=np.uint64(pt.seed),
+                                world=self._coll.world, rank=self._coll.rank, **ck)
 
     @staticmethod
-    def read_from_file(path, reseed=None, *, device=None):
-        with np.load(path) as d:
+    def read_from_file(path, reseed=None, *, device=None, process_group=None):
+        coll = _Collective(process_group)
+        with np.load(LatticeTempering._rank_path(path, coll)) as d:
             if str(d["kind"]) != "LatticeTempering":
                 raise IOError(f"{path} is not a LatticeTempering checkpoint")
+            if int(d["world"]) != coll.world or int(d["rank"]) != coll.rank:
+                raise IOError(f"{path} was written by rank {int(d['rank'])} of {int(d['world'])}, "
+                              f"this is rank {coll.rank} of {coll.world}")
             edges = [((int(x), int(y)), float(w)) for x, y, w in zip(d["a"], d["b"], d["j"])]
-            obj = LatticeTempering(edges, int(d["seed"]) if reseed is None else int(reseed), device=device)
+            obj = LatticeTempering(edges, int(d["seed"]) if reseed is None else int(reseed), device=device,
+                                   process_group=process_group)
             for b in d["betas"]:
                 obj.add_graph(0.0, 0.0, float(b))
             pt = obj._ensure()

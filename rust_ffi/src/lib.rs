@@ -95,6 +95,7 @@ extern "C" {
     ) -> c_int;
     pub fn ising_sim_destroy(sim: *mut ising_sim);
     pub fn ising_sim_set_moves(sim: *mut ising_sim, moves: *const ising_moves) -> c_int;
+    pub fn ising_sim_step_acceptance(sim: *mut ising_sim, beta: f64, changed: *mut u64) -> c_int;
     pub fn ising_sim_set_states(sim: *mut ising_sim, states: *const u8) -> c_int;
     pub fn ising_sim_sweeps(
         sim: *mut ising_sim, betas: *const f64, nsweeps: u64, energies_per_sweep: *mut f64,

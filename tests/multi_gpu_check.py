@@ -61,6 +61,18 @@ def main():
     st1, en1 = single.timesteps_sample(40, 3, 8)
     assert (states == st1).all() and np.array_equal(energies, en1), "sharded tempering differs"
     assert lt.get_total_swaps() == single.total_swaps() > 0
+    # a sharded ladder checkpoints per rank and continues bit for bit
+    import tempfile
+    ckdir = [tempfile.mkdtemp() if rank == 0 else None]
+    dist.broadcast_object_list(ckdir, src=0)
+    ck = os.path.join(ckdir[0], "ladder.npz")
+    lt.save_to_file(ck)
+    dist.barrier()
+    st_a, en_a = lt.qmc_timesteps_sample(24, replica_swap_freq=3, sampling_freq=8)
+    lt2 = pkg.LatticeTempering.read_from_file(ck, device=local)
+    st_b, en_b = lt2.qmc_timesteps_sample(24, replica_swap_freq=3, sampling_freq=8)
+    assert (st_a == st_b).all() and np.array_equal(en_a, en_b), "restored sharded ladder differs"
+    assert lt2.get_total_swaps() == lt.get_total_swaps()
 
     # (3) strips + NCCL halo exchange == one strip
     sweep_betas = [0.4, 0.5, 0.3, 0.44, 0.6]

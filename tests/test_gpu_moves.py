@@ -214,3 +214,19 @@ def test_lattice_and_classic_faces(native):
     assert abs(e.mean() - exact0) < 4.5 * sd0 / np.sqrt(len(e))
     with pytest.raises(NotImplementedError):
         ci.run_monte_carlo(beta, 1, nedgeupdates=3)
+
+
+def test_step_acceptance_counts_the_flipped_spins(native):
+    ctx = native.Context.get(0)
+    g = native.Graph.torus(ctx, (16, 16), j0=-1.0)
+    sim = native.Sim(g, 70, 4)
+    # beta = 0: every attempt is accepted, every site is attempted once per sweep
+    assert (sim.step_acceptance(0.0) == g.nvars).all()
+    before = sim.states()
+    acc = sim.step_acceptance(0.6)
+    assert (acc == (before != sim.states()).sum(axis=1)).all()
+    assert 0 < acc.mean() < g.nvars
+    # the ordered ferromagnet at a very low temperature does not move
+    sim.set_state(np.ones(g.nvars, dtype=bool))
+    assert (sim.step_acceptance(50.0) == 0).all()
+    assert sim.counter == 3
