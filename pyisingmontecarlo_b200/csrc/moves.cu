@@ -150,11 +150,14 @@ __device__ __forceinline__ uint32_t edge_flip_mask(const uint32_t (&cnt)[4], uin
     return flip;
 }
 
-template <int K, int ROUNDS, int V>
+// DEG > 0: compile-time number of outer bonds (the gathers are unrolled and in flight together:
+// the pass is bound by gather latency, like k_sweep_general); DEG = 0: runtime
+template <int K, int ROUNDS, int V, int DEG>
 __global__ void __launch_bounds__(256)
 k_edge_general(uint32_t* __restrict__ spins, EdgeGroup g, uint32_t W, uint32_t sweep, uint32_t pass, PhiloxKeys pk,
                uint32_t gw0, GenThresholds th) {
     const uint32_t tagw = (pass << 8) | (TAG_EDGE << 24);
+    const uint32_t deg = DEG > 0 ? (uint32_t)DEG : g.deg;
     // programmatic dependent launch: a pass is one small launch per (class, outer degree) group
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -171,9 +174,7 @@ k_edge_general(uint32_t* __restrict__ spins, EdgeGroup g, uint32_t W, uint32_t s
         for (int v = 0; v < V; ++v)
 #pragma unroll
             for (int l = 0; l < 4; ++l) cntv[v][l] = 0;
-        for (uint32_t k = 0; k < g.deg; ++k) {
-            uint32_t x[V];
-            load_words<V>(spins + (size_t)g.nbr[(size_t)k * g.count + i] * W + w0, x);
+        auto add_bond = [&](uint32_t k, const uint32_t (&x)[V]) {
             const uint32_t m = 0u - ((ab >> k) & 1u);
             const uint32_t e = 0u - ((eb >> k) & 1u);
 #pragma unroll
@@ -187,10 +188,24 @@ k_edge_general(uint32_t* __restrict__ spins, EdgeGroup g, uint32_t W, uint32_t s
                     c = t;
                 }
             }
+        };
+        if constexpr (DEG > 0) {
+            uint32_t x[DEG][V];
+#pragma unroll
+            for (int k = 0; k < DEG; ++k)
+                load_words<V>(spins + (size_t)g.nbr[(size_t)k * g.count + i] * W + w0, x[k]);
+#pragma unroll
+            for (int k = 0; k < DEG; ++k) add_bond((uint32_t)k, x[k]);
+        } else {
+            for (uint32_t k = 0; k < deg; ++k) {
+                uint32_t x[V];
+                load_words<V>(spins + (size_t)g.nbr[(size_t)k * g.count + i] * W + w0, x);
+                add_bond(k, x);
+            }
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const uint32_t flip = edge_flip_mask<K, ROUNDS>(cntv[v], g.deg, eid, gw0 + w0 + v, sweep, tagw, pk, th);
+            const uint32_t flip = edge_flip_mask<K, ROUNDS>(cntv[v], deg, eid, gw0 + w0 + v, sweep, tagw, pk, th);
             sa[v] ^= flip;
             sb[v] ^= flip;
         }
@@ -199,7 +214,7 @@ k_edge_general(uint32_t* __restrict__ spins, EdgeGroup g, uint32_t W, uint32_t s
     }
 }
 
-template <int K, int ROUNDS>
+template <int K, int ROUNDS, int DEG>
 static int edge_general_launch(const GenSweepArgs& a, const EdgeGroup& g, uint32_t pass, cudaStream_t st) {
     const bool v2 = a.W % 2 == 0;
     const uint32_t groups = v2 ? a.W / 2 : a.W;
@@ -209,17 +224,28 @@ static int edge_general_launch(const GenSweepArgs& a, const EdgeGroup& g, uint32
     if (blocks > (uint64_t)device_sms() * 16) blocks = (uint64_t)device_sms() * 16;
     const PhiloxKeys pk = philox_round_keys(a.key0, a.key1);
     cudaError_t e;
-    if (v2) e = launch_pdl_v(k_edge_general<K, ROUNDS, 2>, dim3((unsigned)blocks), block, 0, st, a.spins, g, a.W, a.sweep, pass,
-                             pk, a.gw0, a.th);
-    else e = launch_pdl_v(k_edge_general<K, ROUNDS, 1>, dim3((unsigned)blocks), block, 0, st, a.spins, g, a.W, a.sweep, pass,
-                          pk, a.gw0, a.th);
+    if (v2) e = launch_pdl_v(k_edge_general<K, ROUNDS, 2, DEG>, dim3((unsigned)blocks), block, 0, st, a.spins, g, a.W, a.sweep,
+                             pass, pk, a.gw0, a.th);
+    else e = launch_pdl_v(k_edge_general<K, ROUNDS, 1, DEG>, dim3((unsigned)blocks), block, 0, st, a.spins, g, a.W, a.sweep,
+                          pass, pk, a.gw0, a.th);
     return e == cudaSuccess ? 1 : -1;
+}
+
+// outer degrees of the regular lattices (square 6, cubic 10, 3-regular 4) for the default (K, rounds)
+template <int K, int ROUNDS>
+static int edge_general_degree(const GenSweepArgs& a, const EdgeGroup& g, uint32_t pass, cudaStream_t st) {
+    if constexpr (K == 6 && ROUNDS == kDefaultRounds) {
+        if (g.deg == 4) return edge_general_launch<K, ROUNDS, 4>(a, g, pass, st);
+        if (g.deg == 6) return edge_general_launch<K, ROUNDS, 6>(a, g, pass, st);
+        if (g.deg == 10) return edge_general_launch<K, ROUNDS, 10>(a, g, pass, st);
+    }
+    return edge_general_launch<K, ROUNDS, 0>(a, g, pass, st);
 }
 
 int launch_edge_general(const GenSweepArgs& a, const EdgeGroup& g, uint32_t pass, cudaStream_t st) {
     if (g.count == 0) return 0;
     if (g.deg > (uint32_t)GEN_MAX_DEG || a.planes < 5 || a.planes > 7) return -1;
-#define EDGE_ROUNDS(KK) (a.rounds == 7 ? edge_general_launch<KK, 7>(a, g, pass, st) : edge_general_launch<KK, 10>(a, g, pass, st))
+#define EDGE_ROUNDS(KK) (a.rounds == 7 ? edge_general_degree<KK, 7>(a, g, pass, st) : edge_general_degree<KK, 10>(a, g, pass, st))
     return a.planes == 5 ? EDGE_ROUNDS(5) : (a.planes == 6 ? EDGE_ROUNDS(6) : EDGE_ROUNDS(7));
 #undef EDGE_ROUNDS
 }
