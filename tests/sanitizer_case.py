@@ -43,4 +43,31 @@ assert (st_r == st_o).all()
 # single lattice strips
 sl = pkg.SingleLattice2D(128, 8, seed=1)
 sl.sweeps([0.4, 0.5]); sl.energy(); sl.magnetization(); sl.local_rows()
+# non-basic moves: bit-sliced edge moves (checkerboard and natural layout, runtime / unrolled outer
+# degrees), float edge moves with importance weights, worms, the acceptance counter
+for dims, gl in (((4, 6, 4), False), ((6, 4), False), ((6, 4), True)):
+    g = nat.Graph.torus(ctx, dims, j0=1.0, pmj=True, j_seed=2)
+    sim = nat.Sim(g, 70, 6, general_layout=gl)
+    sim.set_moves(1, 2, 2, 3)
+    sim.sweeps([0.4, 0.9], per_sweep_energies=True)
+    sim.step_acceptance(0.5)
+    sim.close()
+sim = nat.Sim(lat.graph(), 40, 2)
+sim.set_moves(1, 1, 1, 4)
+sim.sweeps([0.5, 0.5])
+sim.close()
+lr.non_basic_moves = True
+lr.run_monte_carlo(0.7, 3, 40, edge_move_importance_sampling=True)
+# the 128-thread shape of the row walk (few site groups per thread) and the 256-thread one
+for E in (128, 4096):
+    g = nat.Graph.torus(ctx, (16, 16, 16), j0=1.0, pmj=True, j_seed=3)
+    sim = nat.Sim(g, E, 7)
+    sim.sweeps([0.5, 0.8], per_sweep_energies=True)
+    sim.close()
+# strips through ising_strip_sweeps; with ISING_STRIP_FUSE=1 ISING_STRIP_FUSE_MIN_ROWS=1 in the
+# environment this is the fused two-colour pass (TMA-staged for Lx = 8192, warp loads for 256)
+for Lx in (256, 8192):
+    st = nat.Strip(ctx, Lx, 24, 0, 24, -1.0, 3, ghost=4)
+    st.sweeps([0.4, 0.5, 0.6], None, 2)
+    st.rows(); st.close()
 print("SANITIZER_CASE_OK")
