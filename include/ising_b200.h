@@ -96,6 +96,9 @@ ISING_API int ising_graph_get_edges(const ising_graph *g, uint64_t *a, uint64_t 
  * (ising_sim_set_moves): cls[nedges], two bonds of a class share no site and no bond joins them.
  * The CPU mirror of the tests needs it to replay a pass in the library's order. */
 ISING_API int ising_graph_get_edge_classes(ising_graph *g, uint32_t *cls);
+/* The colouring alone, on the host (no context, no device): cls[nedges], *nclasses. */
+ISING_API int ising_strong_edge_colouring(uint64_t nvars, uint64_t nedges, const uint64_t *a, const uint64_t *b,
+                                uint32_t *cls, uint32_t *nclasses);
 
 /* ---- seeds (Lattice::make_seeds, lattice.rs:83-91, seed_gen = Some(seed)) ---------------- */
 ISING_API int ising_make_seeds(uint64_t seed_gen, uint64_t n, uint64_t *out);

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "ising_graph_get_colors": (C.c_int, [_P, _P]),
     "ising_graph_get_edges": (C.c_int, [_P, _P, _P, _P]),
     "ising_graph_get_edge_classes": (C.c_int, [_P, _P]),
+    "ising_strong_edge_colouring": (C.c_int, [C.c_uint64, C.c_uint64, _P, _P, _P, C.POINTER(C.c_uint32)]),
     "ising_make_seeds": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
     "ising_sim_create": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
     "ising_sim_create_ex": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
@@ -796,6 +797,17 @@ class Strip:
             self.close()
         except Exception:
             pass
+
+
+def strong_edge_colouring(nvars, a, b):
+    """Host only: class of every bond such that two bonds of a class share no site and no bond
+    joins them (ising_strong_edge_colouring) -> (uint32[nedges], number of classes)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    cls = np.empty(len(a), dtype=np.uint32)
+    n = C.c_uint32(0)
+    check(lib().ising_strong_edge_colouring(int(nvars), len(a), ptr(a), ptr(b), ptr(cls), C.byref(n)))
+    return cls, int(n.value)
 
 
 def decide_swaps(betas, all_energies, seed, swap_step, slot_of_config, config_of_slot):

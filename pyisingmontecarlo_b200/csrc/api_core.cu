@@ -380,6 +380,29 @@ int ensure_edge_general_on_device(ising_ctx* ctx, ising_graph* g, bool stencil_l
     return ISING_OK;
 }
 
+// host only: no context, no device
+extern "C" int ising_strong_edge_colouring(uint64_t nvars, uint64_t nedges, const uint64_t* a, const uint64_t* b,
+                                           uint32_t* cls, uint32_t* nclasses) {
+    if ((nedges && (!a || !b || !cls)) || !nclasses) return fail(nullptr, ISING_E_INVALID, "null argument");
+    if (nedges > 0xFFFFFFFFull || nvars > 0xFFFFFFFFull) return fail(nullptr, ISING_E_UNSUPPORTED, "graph too large");
+    HostGraph h;
+    h.nvars = nvars;
+    h.nedges = nedges;
+    h.ea.assign(a, a + nedges);
+    h.eb.assign(b, b + nedges);
+    h.ej.assign(nedges, 1.0);
+    for (uint64_t e = 0; e < nedges; ++e)
+        if (a[e] >= nvars || b[e] >= nvars || a[e] == b[e])
+            return fail(nullptr, ISING_E_INVALID, "edge %llu: end points must be distinct sites below nvars",
+                        (unsigned long long)e);
+    EdgeClasses ec;
+    strong_edge_colouring(&h, &ec);
+    for (size_t c = 0; c + 1 < ec.off.size(); ++c)
+        for (uint32_t i = ec.off[c]; i < ec.off[c + 1]; ++i) cls[ec.eid[i]] = (uint32_t)c;
+    *nclasses = (uint32_t)(ec.off.size() - 1);
+    return ISING_OK;
+}
+
 extern "C" int ising_graph_get_edge_classes(ising_graph* g, uint32_t* cls) {
     CtxLock _lk(g ? g->ctx : nullptr);
     if (!g || !cls) return fail(nullptr, ISING_E_INVALID, "graph/cls is NULL");

@@ -69,6 +69,9 @@ extern "C" {
     ) -> c_int;
     pub fn ising_graph_destroy(g: *mut ising_graph);
     pub fn ising_graph_get_edge_classes(g: *mut ising_graph, cls: *mut u32) -> c_int;
+    pub fn ising_strong_edge_colouring(
+        nvars: u64, nedges: u64, a: *const u64, b: *const u64, cls: *mut u32, nclasses: *mut u32,
+    ) -> c_int;
     pub fn ising_make_seeds(seed_gen: u64, n: u64, out: *mut u64) -> c_int;
     pub fn ising_run_monte_carlo(
         ctx: *mut ising_ctx, g: *const ising_graph, args: *const ising_run_args, energies: *mut f64,

@@ -191,3 +191,42 @@ def test_lattice_config_surface_without_gpu(native, oracle):
     assert lat._bias_global == 0.0
     with pytest.raises(NotImplementedError, match="remains on the reference"):
         lat.run_quantum_monte_carlo_sampling
+
+
+def test_strong_edge_colouring_on_the_host(native):
+    """Classes of the two-spin edge moves: no two bonds of a class share a site or are joined by a
+    third bond; every bond gets a class; lattices need few classes."""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+
+    def check_strong(nvars, a, b):
+        cls, ncls = native.strong_edge_colouring(nvars, a, b)
+        assert cls.max() + 1 == ncls
+        adj = [set() for _ in range(nvars)]
+        for x, y in zip(a, b):
+            adj[int(x)].add(int(y))
+            adj[int(y)].add(int(x))
+        for c in range(ncls):
+            owner = {}
+            idx = np.nonzero(cls == c)[0]
+            for k in idx:
+                for v in (int(a[k]), int(b[k])):
+                    assert v not in owner
+                    owner[v] = k
+            for k in idx:
+                for v in (int(a[k]), int(b[k])):
+                    assert all(owner.get(u, k) == k for u in adj[v])
+        return ncls
+
+    L = 8
+    a = [x + L * y for y in range(L) for x in range(L)] * 2
+    b = [(x + 1) % L + L * y for y in range(L) for x in range(L)] + [x + L * ((y + 1) % L) for y in range(L) for x in range(L)]
+    assert check_strong(L * L, a, b) <= 16          # 8 suffice; the greedy pass may use a few more
+    n = 300
+    e = {(min(int(u), int(v)), max(int(u), int(v))) for u, v in rng.integers(0, n, (700, 2)) if u != v}
+    a, b = [x for x, _ in e], [y for _, y in e]
+    check_strong(n, a, b)
+    check_strong(4, [0, 0, 0], [1, 2, 3])            # a star: every bond its own class
+    with pytest.raises(ValueError):
+        native.strong_edge_colouring(3, [0], [0])    # self-loop
