@@ -130,8 +130,9 @@ constexpr int NS_NR = 20;  // block-level counter planes: 256 threads x 1023 fit
 // Block-wide reduction of per-thread vertical counters (NP planes, V replica words per thread,
 // block = (wx, by)) into per-experiment integers: bit-sliced tree through shared memory, then
 // one SWAR bit-transpose per word column and 32 integer atomics per column.
-//   sm: max(NP * V, NS_NR) * nthreads words;  out[(w0 + column) * 32 + bit] += count
-template <int NP, int V>
+//   sm: max(NP * V, NR) * nthreads words;  out[(w0 + column) * 32 + bit] += count
+//   NR = planes of the block-level counters: nthreads * (2^NP - 1) must stay below 2^NR
+template <int NP, int V, int NR = NS_NR>
 __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], uint32_t* sm,
                                                     unsigned long long* __restrict__ out,
                                                     uint32_t w0, uint32_t W) {
@@ -148,28 +149,28 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
     const uint32_t Q = nthreads / C;
     const uint32_t c = tid % C, q = tid / C;
     const uint32_t cx = c / V, cv = c % V;
-    uint32_t acc[NS_NR];
+    uint32_t acc[NR];
 #pragma unroll
-    for (int l = 0; l < NS_NR; ++l) acc[l] = 0;
+    for (int l = 0; l < NR; ++l) acc[l] = 0;
     for (uint32_t ty = q; ty < by; ty += Q) {
         uint32_t x[NP];
 #pragma unroll
         for (int l = 0; l < NP; ++l) x[l] = sm[(l * V + cv) * nthreads + ty * wx + cx];
-        vadd<NS_NR, NP>(acc, x);
+        vadd<NR, NP>(acc, x);
     }
     __syncthreads();
 #pragma unroll
-    for (int l = 0; l < NS_NR; ++l) sm[l * nthreads + tid] = acc[l];  // [plane][q][c]
+    for (int l = 0; l < NR; ++l) sm[l * nthreads + tid] = acc[l];  // [plane][q][c]
     __syncthreads();
     // stage B1: tree over the Q parts of every column (all threads of the surviving parts work)
     for (uint32_t half = Q >> 1; half >= 1; half >>= 1) {
         if (q < half) {
-            uint32_t x[NS_NR];
+            uint32_t x[NR];
 #pragma unroll
-            for (int l = 0; l < NS_NR; ++l) x[l] = sm[l * nthreads + (q + half) * C + c];
-            vadd<NS_NR, NS_NR>(acc, x);
+            for (int l = 0; l < NR; ++l) x[l] = sm[l * nthreads + (q + half) * C + c];
+            vadd<NR, NR>(acc, x);
 #pragma unroll
-            for (int l = 0; l < NS_NR; ++l) sm[l * nthreads + tid] = acc[l];
+            for (int l = 0; l < NR; ++l) sm[l * nthreads + tid] = acc[l];
         }
         __syncthreads();
     }
@@ -178,7 +179,7 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
     if (w0 + c < W) {
         if (q != 0) {
 #pragma unroll
-            for (int l = 0; l < NS_NR; ++l) acc[l] = sm[l * nthreads + c];
+            for (int l = 0; l < NR; ++l) acc[l] = sm[l * nthreads + c];
         }
         unsigned long long* o = out + (size_t)(w0 + c) * 32;
         for (uint32_t g = q; g < 8; g += Q) {
@@ -186,8 +187,8 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
 #pragma unroll
             for (int l = 0; l < 8; ++l) {
                 lo += ((acc[l] >> g) & 0x01010101u) << l;
-                hi += ((acc[l + 8] >> g) & 0x01010101u) << l;
-                if (l + 16 < NS_NR) top += ((acc[l + 16] >> g) & 0x01010101u) << l;
+                if (l + 8 < NR) hi += ((acc[l + 8] >> g) & 0x01010101u) << l;
+                if (l + 16 < NR) top += ((acc[l + 16] >> g) & 0x01010101u) << l;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

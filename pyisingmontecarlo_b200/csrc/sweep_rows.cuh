@@ -281,11 +281,12 @@ __device__ __noinline__ uint32_t msc_resolve_rest(uint32_t eq, uint32_t m1, uint
 // The update of one site for V replica words: two Philox calls per word, bit-sliced count of the
 // satisfied bonds, Metropolis mask, (ACC) accumulation of the post-flip count.
 //   s: the site's words (updated in place);  n[k]: neighbour words;  m[k]: bond masks
-template <int DIM, int K, int ROUNDS, int V, bool ACC>
+//   NPC: planes of the per-thread counters (ACC)
+template <int DIM, int K, int ROUNDS, int V, bool ACC, int NPC = SW_NP>
 __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n)[2 * DIM][V],
                                             const uint32_t (&m)[2 * DIM], uint32_t site, uint32_t gw0w,
                                             uint32_t sweep, const PhiloxKeys& pk, const MscMux& mx,
-                                            VCount<ACC ? SW_NP : 1> (&vc)[V]) {
+                                            VCount<ACC ? NPC : 1> (&vc)[V]) {
     uint32_t s0[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) s0[v] = s[v];
@@ -395,8 +396,14 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
 
 // COUNT_ONLY (with ACC): no update, nsat[e] += satisfied bonds seen from the sites of this colour
 // (every bond once) - get_energy() of the current configuration with the same row walk.
-template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT_ONLY = false>
+// NPC / NRC: planes of the per-thread and of the block-level counters of the accumulating phase.  The
+// 128-thread shape runs with 5 / 12 (at most 5 site groups between two reductions, 128 * 31 < 2^12)
+// instead of 7 / 20: at one or two site groups per thread the block reduction is a third of the
+// phase's instructions (profiles/r02_sweep_small_metrics.md), and it shrinks with the plane counts.
+template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT_ONLY = false,
+          int NPC = SW_NP, int NRC = NS_NR>
 __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm) {
+    constexpr int MAX_ITEMS = ((1 << NPC) - 1) / 6;
     typedef typename WordVec<V>::type VecT;
     __shared__ RowDesc s_desc[ROWS_DESC_CHUNK];
     const uint32_t Lxh = a.Lxh, W = a.W, Ly = a.Ly, Lz = a.Lz;
@@ -422,7 +429,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
     asm volatile("griddepcontrol.launch_dependents;");
     bool waited = false;
 
-    VCount<ACC ? SW_NP : 1> vc[V];
+    VCount<ACC ? NPC : 1> vc[V];
     if constexpr (ACC) {
 #pragma unroll
         for (int v = 0; v < V; ++v) vc[v].clear();
@@ -476,7 +483,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
             if (tile != cur_tile) {
                 if constexpr (ACC) {
                     if (pending) {
-                        block_reduce_vcount<SW_NP, V>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
+                        block_reduce_vcount<NPC, V, NRC>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
 #pragma unroll
                         for (int v = 0; v < V; ++v) vc[v].clear();
                         pending = 0;
@@ -548,7 +555,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
                     }
                 } else {
                     const uint32_t site = db.y + xsite;
-                    update_site<DIM, K, ROUNDS, V, ACC>(s, n, m, site, a.gw0 + w, a.sweep, a.pk, a.mx, vc);
+                    update_site<DIM, K, ROUNDS, V, ACC, NPC>(s, n, m, site, a.gw0 + w, a.sweep, a.pk, a.mx, vc);
                     VecT o;
 #pragma unroll
                     for (int v = 0; v < V; ++v) reinterpret_cast<uint32_t*>(&o)[v] = s[v];
@@ -556,8 +563,8 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
                 }
             }
             if constexpr (ACC) {
-                if (++pending == SW_MAX_ITEMS) {  // counters full: reduce and start over
-                    block_reduce_vcount<SW_NP, V>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
+                if (++pending == MAX_ITEMS) {  // counters full: reduce and start over
+                    block_reduce_vcount<NPC, V, NRC>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
 #pragma unroll
                     for (int v = 0; v < V; ++v) vc[v].clear();
                     pending = 0;
@@ -566,7 +573,7 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
         }
     }
     if constexpr (ACC) {
-        if (pending) block_reduce_vcount<SW_NP, V>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
+        if (pending) block_reduce_vcount<NPC, V, NRC>(vc, sm, nsat, (cur_tile / a.xtiles) * wx * V, W);
     }
 }
 
@@ -576,12 +583,14 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
 // 512 units of 256 threads need a second, mostly empty one (profiles/r02_small_w_ab.log: 20.9 ->
 // 18.6 us per sweep with energies at 128 replicas; at 512 and more the 256-thread shape is faster).
 constexpr int ROWS_SMALL_THREADS = 128;
+constexpr int ROWS_SMALL_NP = 5, ROWS_SMALL_NR = 12;   // counter planes of the small shape (sweep_rows_phase)
 template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool SMALL = false>
 __global__ void __launch_bounds__(SMALL ? ROWS_SMALL_THREADS : ISING_ROWS_THREADS,
                                   SMALL ? (ACC ? 4 : 7) : (ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB))
 k_sweep_rows(const __grid_constant__ RowsArgs a) {
     extern __shared__ uint32_t sm[];
-    sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW>(a, sm);
+    sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW, false, SMALL ? ROWS_SMALL_NP : SW_NP,
+                     SMALL ? ROWS_SMALL_NR : NS_NR>(a, sm);
 }
 
 template <int DIM, bool PMJ, int V, bool MULTIROW>
