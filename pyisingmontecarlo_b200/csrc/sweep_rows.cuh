@@ -584,13 +584,15 @@ __device__ __forceinline__ void sweep_rows_phase(const RowsArgs& a, uint32_t* sm
 // 18.6 us per sweep with energies at 128 replicas; at 512 and more the 256-thread shape is faster).
 constexpr int ROWS_SMALL_THREADS = 128;
 constexpr int ROWS_SMALL_NP = 5, ROWS_SMALL_NR = 12;   // counter planes of the small shape (sweep_rows_phase)
+constexpr int ROWS_NR = 15;                             // 256 threads x (2^7 - 1) < 2^15
+static_assert(ISING_ROWS_THREADS * ((1 << SW_NP) - 1) < (1 << ROWS_NR), "block counters too narrow");
 template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool SMALL = false>
 __global__ void __launch_bounds__(SMALL ? ROWS_SMALL_THREADS : ISING_ROWS_THREADS,
                                   SMALL ? (ACC ? 4 : 7) : (ACC ? ISING_ROWS_ACC_MINB : ISING_ROWS_MINB))
 k_sweep_rows(const __grid_constant__ RowsArgs a) {
     extern __shared__ uint32_t sm[];
     sweep_rows_phase<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW, false, SMALL ? ROWS_SMALL_NP : SW_NP,
-                     SMALL ? ROWS_SMALL_NR : NS_NR>(a, sm);
+                     SMALL ? ROWS_SMALL_NR : ROWS_NR>(a, sm);
 }
 
 template <int DIM, bool PMJ, int V, bool MULTIROW>

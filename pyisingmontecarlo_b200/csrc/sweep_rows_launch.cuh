@@ -59,7 +59,7 @@ static int rows_launch(RowsArgs& ra, const RowsShape& sh, int sms, cudaStream_t 
     else kern = k_sweep_rows<DIM, PMJ, K, ROUNDS, V, ACC, MULTIROW, SMALL>;
     const dim3 block(sh.wx, sh.bxh * sh.nrs, 1);
     const int nthreads = block.x * block.y;
-    constexpr int np = SMALL ? ROWS_SMALL_NP : SW_NP, nr = SMALL ? ROWS_SMALL_NR : NS_NR;
+    constexpr int np = SMALL ? ROWS_SMALL_NP : SW_NP, nr = SMALL ? ROWS_SMALL_NR : (COUNT ? NS_NR : ROWS_NR);
     const int planes = np * V > nr ? np * V : nr;
     const size_t smem = ACC ? (size_t)planes * nthreads * sizeof(uint32_t) : 0;
     static int per_sm = 0, per_sm_threads = 0;  // per instantiation
