@@ -230,3 +230,28 @@ def test_strong_edge_colouring_on_the_host(native):
     check_strong(4, [0, 0, 0], [1, 2, 3])            # a star: every bond its own class
     with pytest.raises(ValueError):
         native.strong_edge_colouring(3, [0], [0])    # self-loop
+
+
+def test_move_flags_of_the_lattice_face(native):
+    """only_basic_moves / edge_move_importance_sampling -> run flags (lattice.rs:181, 200, 205)."""
+    import warnings
+
+    import pyisingmontecarlo_b200 as pkg
+    from pyisingmontecarlo_b200 import lattice as lattice_mod
+
+    lat = pkg.Lattice([((0, 1), 1.0), ((1, 2), -1.0)], seed_gen=0)
+    assert lat._check_classical(None, True) == native.FLAG_ONLY_BASIC_MOVES
+    assert lat._check_classical(True, True) == native.FLAG_ONLY_BASIC_MOVES      # nothing for it to act on
+    lat.non_basic_moves = True
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                                            # the flag is the user's answer
+        assert lat._check_classical(None, None) == native.FLAG_NON_BASIC_MOVES
+        assert lat._check_classical(True, False) == native.FLAG_NON_BASIC_MOVES | native.FLAG_EDGE_IMPORTANCE
+    lat.non_basic_moves = False
+    lattice_mod._warned_basic_moves = False
+    with pytest.warns(UserWarning, match="non_basic_moves"):
+        assert lat._check_classical(None, None) == 0
+    assert lat._check_classical(True, None) == native.FLAG_EDGE_IMPORTANCE       # the library refuses this one
+    lat.set_transverse_field(0.5)
+    with pytest.raises(ValueError, match="transverse field"):
+        lat._check_classical(None, True)
