@@ -3,7 +3,7 @@ Boltzmann distribution: chains made of those moves alone reproduce exact enumera
 import numpy as np
 import pytest
 
-from moves_cases import boltzmann, histogram_z, irregular_graph
+from moves_cases import boltzmann, histogram_z, irregular_graph  # noqa: E402
 
 
 @pytest.mark.parametrize("moves", [
@@ -44,3 +44,38 @@ def test_edge_move_leaves_the_shared_bond_alone(oracle):
     en, st = g.run_moves(3.0, 9, seeds, nedge=1, initial_state=[True, True])
     assert (en == -5.0).all() and (st[:, 0] == st[:, 1]).all()
     assert (st[:, 0] == False).all()      # 9 accepted double flips
+
+
+def test_bit_sliced_edge_pass_of_the_mirror_samples_the_boltzmann_law(oracle, native):
+    """The device's bit-sliced edge move (restated in oracle/msc_mirror.c, to which the GPU kernel is
+    compared bit for bit) against exact enumeration: 4x4 torus, sweeps + edge passes, and edge
+    passes alone within a parity sector."""
+    L = 4
+    a = [x + L * y for y in range(L) for x in range(L)] * 2
+    b = [(x + 1) % L + L * y for y in range(L) for x in range(L)] + [x + L * ((y + 1) % L) for y in range(L) for x in range(L)]
+    j = [-1.0] * len(a)
+    edges = [((int(x), int(y)), w) for x, y, w in zip(a, b, j)]
+    colors = np.array([(n % L + n // L) & 1 for n in range(L * L)], dtype=np.uint32)
+    cls, ncls = native.strong_edge_colouring(L * L, a, b)
+    beta = 0.35
+    _, p, en = boltzmann(edges, L * L, beta)
+    exact = float((p * en).sum())
+    var = float((p * en * en).sum()) - exact ** 2
+    E = 2048
+    en_m, st = oracle.msc_mirror_moves(a, b, j, L * L, colors, cls, E, 5, np.full(40, beta), spin_sweeps=1,
+                                       edge_passes=1, per_step=True)
+    e = en_m[:, -1]
+    assert abs(e.mean() - exact) < 4 * np.sqrt(var / E), (e.mean(), exact)
+    # edge passes alone keep the parity of the number of up spins: compare within the even sector
+    _, st2 = oracle.msc_mirror_moves(a, b, j, L * L, colors, cls, E, 9, np.full(60, beta), spin_sweeps=0,
+                                     edge_passes=2)
+    even = st2[st2.sum(1) % 2 == 0]
+    parity = np.array([bin(i).count("1") % 2 for i in range(2 ** (L * L))])
+    pe = np.where(parity == 0, p, 0.0)
+    pe /= pe.sum()
+    exact_even = float((pe * en).sum())
+    var_even = float((pe * en * en).sum()) - exact_even ** 2
+    g = oracle.Graph(edges)
+    e_even = np.array([g.energy(s) for s in even])
+    assert len(even) > E // 4
+    assert abs(e_even.mean() - exact_even) < 4 * np.sqrt(var_even / len(even)), (e_even.mean(), exact_even)
