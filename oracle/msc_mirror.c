@@ -15,7 +15,8 @@
  *       words R_m = output m%4 of Philox4x32-R(key = seed, ctr = (n, w, t, m/4));
  *       bit b of R_0..R_{K-1} are the K most significant bits of U for replica 32w+b, compared
  *       MSB first; bits of the word still tied after K planes are taken in ascending b and the
- *       j-th of them accepts iff R_{K+j} < T mod 2^32.
+ *       j-th of them accepts iff R_{K+j} < T mod 2^32.  Words beyond the K/4 + 1 calls every
+ *       update makes are continuation rounds of the last block (stream_word_tag below).
  *   initial state: bit b of Philox4x32-10(key, ctr = (n, w, 0, 1<<24)).x
  *   energy: |J| (n_edges - 2 n_sat_total)
  */
@@ -49,11 +50,27 @@ ORC_EXPORT void msc_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t
     memcpy(out, c, sizeof c);
 }
 
-static uint32_t stream_word(int rounds, uint32_t site, uint32_t gw, uint32_t sweep, uint32_t m,
-                            uint32_t k0, uint32_t k1) {
-    uint32_t c[4] = {site, gw, sweep, m >> 2};
-    philox4x32(rounds, c, k0, k1);
+/* Word R_m of a decision stream with K planes on counter (c0, c1, c2, call | tag): the NCALL =
+ * K/4 + 1 calls every update makes give R_0 .. R_{4 NCALL - 1}; later words (third and later
+ * ties of a word) are continuation rounds of the last block: R_m = output m%4 of
+ * Philox4x32-(rounds + m/4 - NCALL + 1) on the counter of call NCALL - 1 (msc_device.cuh). */
+static uint32_t stream_word_tag(int rounds, int K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag,
+                                uint32_t m, uint32_t k0, uint32_t k1) {
+    const uint32_t ncall = (uint32_t)K / 4 + 1;
+    uint32_t call = m >> 2;
+    int extra = 0;
+    if (call >= ncall) {
+        extra = (int)(call - ncall) + 1;
+        call = ncall - 1;
+    }
+    uint32_t c[4] = {c0, c1, c2, call | tag};
+    philox4x32(rounds + extra, c, k0, k1);
     return c[m & 3];
+}
+
+static uint32_t stream_word(int rounds, int K, uint32_t site, uint32_t gw, uint32_t sweep, uint32_t m,
+                            uint32_t k0, uint32_t k1) {
+    return stream_word_tag(rounds, K, site, gw, sweep, 0u, m, k0, k1);
 }
 
 static uint64_t threshold(double beta, double de, int K) {
@@ -141,13 +158,13 @@ static void mirror_sweep(const mirror_t *m, uint64_t E, uint8_t *states, const d
                     const uint64_t T = threshold(bt, 2.0 * m->jabs * (double)cls, K);
                     int decided = 0, accept = 0;
                     for (int p = 0; p < K && !decided; ++p) {
-                        const uint32_t rb = (stream_word(m->rounds, (uint32_t)n, m->gw0 + (uint32_t)w,
+                        const uint32_t rb = (stream_word(m->rounds, K, (uint32_t)n, m->gw0 + (uint32_t)w,
                                                          sweep, (uint32_t)p, m->k0, m->k1) >> b) & 1u;
                         const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
                         if (rb != tb) { decided = 1; accept = rb < tb; }
                     }
                     if (!decided) {
-                        const uint32_t v = stream_word(m->rounds, (uint32_t)n, m->gw0 + (uint32_t)w,
+                        const uint32_t v = stream_word(m->rounds, K, (uint32_t)n, m->gw0 + (uint32_t)w,
                                                        sweep, (uint32_t)(K + j), m->k0, m->k1);
                         accept = v < (uint32_t)(T & 0xFFFFFFFFull);
                         ++j;
@@ -202,11 +219,9 @@ ORC_EXPORT int msc_mirror_run(uint64_t nvars, uint64_t nedges, const uint64_t *e
  * satisfied bonds among its D outer bonds (adjacency entries of a and b that do not lead to the
  * other end); dE = 2|J|(2 n_sat - D); same threshold / plane / resolver rule as a site of degree D,
  * on the stream (edge, replica word, timestep, call | pass << 8 | 4 << 24). */
-static uint32_t edge_stream_word(int rounds, uint32_t eid, uint32_t gw, uint32_t sweep, uint32_t pass,
+static uint32_t edge_stream_word(int rounds, int K, uint32_t eid, uint32_t gw, uint32_t sweep, uint32_t pass,
                                  uint32_t m, uint32_t k0, uint32_t k1) {
-    uint32_t c[4] = {eid, gw, sweep, (m >> 2) | (pass << 8) | (4u << 24)};
-    philox4x32(rounds, c, k0, k1);
-    return c[m & 3];
+    return stream_word_tag(rounds, K, eid, gw, sweep, (pass << 8) | (4u << 24), m, k0, k1);
 }
 
 static void mirror_edge_pass(const mirror_t *m, const uint32_t *edge_cls, uint32_t ncls, uint64_t E,
@@ -238,13 +253,13 @@ static void mirror_edge_pass(const mirror_t *m, const uint32_t *edge_cls, uint32
                         int decided = 0;
                         accept = 0;
                         for (int p = 0; p < K && !decided; ++p) {
-                            const uint32_t rb = (edge_stream_word(m->rounds, (uint32_t)e, m->gw0 + (uint32_t)w, sweep,
+                            const uint32_t rb = (edge_stream_word(m->rounds, K, (uint32_t)e, m->gw0 + (uint32_t)w, sweep,
                                                                   pass, (uint32_t)p, m->k0, m->k1) >> b) & 1u;
                             const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
                             if (rb != tb) { decided = 1; accept = rb < tb; }
                         }
                         if (!decided) {
-                            const uint32_t v = edge_stream_word(m->rounds, (uint32_t)e, m->gw0 + (uint32_t)w, sweep,
+                            const uint32_t v = edge_stream_word(m->rounds, K, (uint32_t)e, m->gw0 + (uint32_t)w, sweep,
                                                                 pass, (uint32_t)(K + j), m->k0, m->k1);
                             accept = v < (uint32_t)(T & 0xFFFFFFFFull);
                             ++j;
@@ -419,12 +434,12 @@ ORC_EXPORT int msc_mirror_single(uint64_t Lx, uint64_t Ly, double jcoupling, uin
                         const uint32_t gw = (c << 30) | (uint32_t)j;
                         int decided = 0, accept = 0;
                         for (int p = 0; p < K && !decided; ++p) {
-                            const uint32_t rb = (stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)p, k0, k1) >> b) & 1u;
+                            const uint32_t rb = (stream_word(rounds, K, (uint32_t)y, gw, (uint32_t)t, (uint32_t)p, k0, k1) >> b) & 1u;
                             const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
                             if (rb != tb) { decided = 1; accept = rb < tb; }
                         }
                         if (!decided) {
-                            const uint32_t v = stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)(K + tie_rank), k0, k1);
+                            const uint32_t v = stream_word(rounds, K, (uint32_t)y, gw, (uint32_t)t, (uint32_t)(K + tie_rank), k0, k1);
                             accept = v < (uint32_t)(T & 0xFFFFFFFFull);
                             ++tie_rank;
                         }
@@ -492,12 +507,12 @@ ORC_EXPORT int msc_mirror_single_band(uint64_t Lx, uint64_t y0, uint64_t nrows, 
                         const uint32_t gw = (c << 30) | (uint32_t)j;
                         int decided = 0, accept = 0;
                         for (int p = 0; p < K && !decided; ++p) {
-                            const uint32_t rb = (stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)p, k0, k1) >> b) & 1u;
+                            const uint32_t rb = (stream_word(rounds, K, (uint32_t)y, gw, (uint32_t)t, (uint32_t)p, k0, k1) >> b) & 1u;
                             const uint32_t tb = (uint32_t)((T >> (K + 31 - p)) & 1ull);
                             if (rb != tb) { decided = 1; accept = rb < tb; }
                         }
                         if (!decided) {
-                            const uint32_t v = stream_word(rounds, (uint32_t)y, gw, (uint32_t)t, (uint32_t)(K + tie_rank), k0, k1);
+                            const uint32_t v = stream_word(rounds, K, (uint32_t)y, gw, (uint32_t)t, (uint32_t)(K + tie_rank), k0, k1);
                             accept = v < (uint32_t)(T & 0xFFFFFFFFull);
                             ++tie_rank;
                         }

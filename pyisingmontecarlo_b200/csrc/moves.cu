@@ -136,7 +136,7 @@ __device__ __forceinline__ uint32_t edge_flip_mask(const uint32_t (&cnt)[4], uin
     while (eq) {
         const int b = __ffs((int)eq) - 1;
         if ((jj & 3) == 0 && jj >= 4 * NCALL)
-            cur = philox4x32_keys<ROUNDS>(eid, gw, sweep, (uint32_t)(jj >> 2) | tagw, pk);
+            cur = philox4x32_more(cur, (uint32_t)(ROUNDS + (jj >> 2) - NCALL), pk.k[0], pk.k[1]);
         const int m = jj & 3;
         const uint32_t val = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
         uint32_t cls = 0;

@@ -209,7 +209,10 @@ __device__ __forceinline__ void block_reduce_vcount(const VCount<NP> (&vc)[V], u
 //   subtraction U_top - T_top (one majority LOP3 per plane, LSB first); bits whose top K bits
 //   tie (probability 2^-K) are resolved by a fresh 32-bit word against the low 32 threshold
 //   bits, tied bits taken in ascending position.  Word R_m is output m%4 of Philox call m/4
-//   on counter (site, replica word, sweep, call).
+//   on counter (site, replica word, sweep, call) for the NCALL = K/4 + 1 calls every update
+//   makes; later words (the third tie of a word and beyond, 1 word in 100) are the outputs of
+//   continuation rounds of the last of those blocks: R_m = output m%4 of
+//   Philox4x32-(ROUNDS + m/4 - NCALL + 1) on the counter of call NCALL - 1.
 // returns the flip mask (downhill bits always flip)
 // ------------------------------------------------------------------------------------------
 // PERBETA: every replica bit has its own inverse temperature (parallel tempering): the plane
@@ -247,7 +250,7 @@ __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, ui
     uint32_t flip = ~up | (borrow & ~eq);
     // Tied bits (2^-K each).  The first SPARE of them use the words left over from the calls
     // above in straight-line predicated code (no divergent loop for the common case); anything
-    // beyond that, rare, draws further Philox calls in a loop.
+    // beyond that, rare, takes further rounds of the last block in a loop.
     constexpr int SPARE = (4 * NCALL - K) < 2 ? (4 * NCALL - K) : 2;
 #pragma unroll
     for (int j = 0; j < SPARE; ++j) {
@@ -271,7 +274,7 @@ __device__ __forceinline__ uint32_t msc_flip_mask(uint32_t up, uint32_t sel0, ui
         do {
             const int b = __ffs((int)eq) - 1;
             if ((j & 3) == 0 && j >= 4 * NCALL)
-                cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
+                cur = philox4x32_more(cur, (uint32_t)(ROUNDS + (j >> 2) - NCALL), pk.k[0], pk.k[1]);
             const int m = j & 3;
             const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
             uint32_t lo;

@@ -50,6 +50,23 @@ ISING_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     return out;
 }
 
+// One more round on a finished block: round index `round` (0-based) of the same key schedule, so
+// philox4x32_more(philox4x32<R>(ctr, key), R, key) == philox4x32<R + 1>(ctr, key).  The tie
+// resolver takes its words beyond the calls a site update makes anyway from these continuation
+// rounds of its last block: two multiplications instead of a fresh call.
+ISING_HD u32x4 philox4x32_more(const u32x4& s, uint32_t round, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    const uint64_t p0 = (uint64_t)M0 * s.x;
+    const uint64_t p1 = (uint64_t)M1 * s.z;
+    u32x4 out;
+    out.x = (uint32_t)(p1 >> 32) ^ s.y ^ (k0 + round * W0);
+    out.y = (uint32_t)p1;
+    out.z = (uint32_t)(p0 >> 32) ^ s.w ^ (k1 + round * W1);
+    out.w = (uint32_t)p0;
+    return out;
+}
+
 // Round keys precomputed on the host (key schedule k += W per round): passed as a kernel
 // parameter they sit in the constant bank and feed LOP3 directly, instead of 2 integer adds per
 // round per thread.

@@ -154,7 +154,7 @@ k_sweep_general(uint32_t* __restrict__ spins, GenGroup g, uint32_t W, uint32_t s
             do {
                 const int b = __ffs((int)eq) - 1;
                 if ((jj & 3) == 0 && jj >= 4 * NCALL)
-                    cur = philox4x32_keys<ROUNDS>(n, gw0 + w, sweep, (uint32_t)(jj >> 2) | (TAG_ACCEPT << 24), pk);
+                    cur = philox4x32_more(cur, (uint32_t)(ROUNDS + (jj >> 2) - NCALL), pk.k[0], pk.k[1]);
                 const int m = jj & 3;
                 const uint32_t val = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
                 uint32_t cls = 0;

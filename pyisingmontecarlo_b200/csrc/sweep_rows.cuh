@@ -34,13 +34,12 @@
 #define ISING_ROWS_ACC_MINB 2    // ... the accumulating colour phase
 #endif
 #ifndef ISING_ROWS_DEFER_RARE
-// third-and-later ties of a word: 0 = divergent loop inside the word, 1 = all V words after the
-// word loop (default), 2 = after the word loop, the warp voting word by word and resolving ties
-// 3..6 in straight-line code on a Philox call that shares rounds 1-3 with calls 0 and 1.
-// Mode 2 is bit-identical and its rare path is cheaper (10.7 instead of 13.1 us per sweep between
-// beta = 0.1 and 1.2 on config 3), but keeping the shared Philox products alive behind the word
-// loop spills: 74.4 vs 69.0 us per sweep on the annealing ramp (profiles/r02_rare_path_ab.log).
-#define ISING_ROWS_DEFER_RARE 1
+// third-and-later ties of a word (their words come from continuation rounds of the word's second
+// Philox block, msc_device.cuh): 0 = divergent loop inside the word, where that block is still in
+// registers; 1 = all V words after the word loop (the blocks are kept: 4 V registers).
+// History (profiles/r02_rare_path_ab.log): while those words came from a third Philox call the
+// deferred form was the faster one, and a warp-voted form with shared rounds 1-3 spilled.
+#define ISING_ROWS_DEFER_RARE 0
 #endif
 #ifndef ISING_ROWS_SPLIT_ACC_DEFAULT
 #define ISING_ROWS_SPLIT_ACC_DEFAULT 0  // 1: per-sweep energies by a count-only pass instead of the fused phase
@@ -155,21 +154,6 @@ struct PhiloxSite {
             c1v[v] = (uint32_t)Q1;
         }
     }
-    // call q >= 2 of word v (resolver words 4 q .. 4 q + 3, needed by words with three or more
-    // ties): the per-call part of rounds 2-3 is computed here, the per-word part is shared with
-    // calls 0 and 1
-    // (round 1 is recomputed rather than kept in registers: this runs for 1 word in 100)
-    __device__ __forceinline__ void finish_call(int v, uint32_t q, uint32_t site, uint32_t sweep,
-                                                const PhiloxKeys& pk, uint32_t* out) const {
-        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-        const uint32_t h0r1 = __umulhi(M0, site), l1r1 = M1 * sweep;
-        const uint32_t c2r = h0r1 ^ (q | (TAG_ACCEPT << 24)) ^ pk.k[1];
-        const uint64_t P1 = (uint64_t)M1 * c2r;
-        const uint32_t c0q2 = (uint32_t)(P1 >> 32) ^ l1r1 ^ pk.k[2];
-        const uint32_t c1q2 = (uint32_t)P1;
-        const uint64_t Q0 = (uint64_t)M0 * c0q2;
-        rounds_from_4(hq1v[v] ^ c1q2 ^ pk.k[4], c1v[v], (uint32_t)(Q0 >> 32) ^ c3v[v] ^ pk.k[5], (uint32_t)Q0, pk, out);
-    }
     // rounds 4 .. ROUNDS of call q of word v
     __device__ __forceinline__ void finish(int v, int q, const PhiloxKeys& pk, uint32_t* out) const {
         rounds_from_4(hq1v[v] ^ c1q[q] ^ pk.k[4], c1v[v], hq0[q] ^ c3v[v] ^ pk.k[5], c3q[q], pk, out);
@@ -236,13 +220,13 @@ __device__ __forceinline__ uint32_t msc_flip_mask_mux(uint32_t up, uint32_t m1, 
         *eq_left = eq;
         return flip;
     }
-    if (eq) {  // third tie of a word (rare): further Philox calls, as msc_flip_mask
+    if (eq) {  // third tie of a word (rare): continuation rounds of the second block, as msc_flip_mask
         int j = K + SPARE;
         u32x4 cur = {r[4], r[5], r[6], r[7]};
         do {
             const int b = __ffs((int)eq) - 1;
             if ((j & 3) == 0 && j >= 8)
-                cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
+                cur = philox4x32_more(cur, (uint32_t)(ROUNDS + (j >> 2) - 2), pk.k[0], pk.k[1]);
             const int m = j & 3;
             const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
             uint32_t lo = ((m1 >> b) & 1u) ? mx.low[1] : mx.low[0];
@@ -255,18 +239,19 @@ __device__ __forceinline__ uint32_t msc_flip_mask_mux(uint32_t up, uint32_t m1, 
     return flip;
 }
 
-// third and later ties of a word: resolver words 8, 9, ... = Philox calls 2, 3, ... of the word
+// third and later ties of a word (deferred form): resolver words 8, 9, ... = continuation rounds
+// of the word's second Philox block `cur` (K + SPARE = 8: the first word needs a fresh round)
 template <int NCLS, int K, int ROUNDS>
 __device__ __noinline__ uint32_t msc_resolve_rest(uint32_t eq, uint32_t m1, uint32_t m2, uint32_t low0,
-                                                  uint32_t low1, uint32_t low2, uint32_t site, uint32_t gw,
-                                                  uint32_t sweep, const PhiloxKeys& pk, int j0 = 8) {
+                                                  uint32_t low1, uint32_t low2, u32x4 cur,
+                                                  const PhiloxKeys& pk) {
+    static_assert(K >= 6, "deferred ties start at resolver word 8");
     uint32_t flip = 0;
-    int j = j0;   // multiple of 4: the first word comes from a fresh call
-    u32x4 cur = {0, 0, 0, 0};
+    int j = 8;
     do {
         const int b = __ffs((int)eq) - 1;
         if ((j & 3) == 0)
-            cur = philox4x32_keys<ROUNDS>(site, gw, sweep, (uint32_t)(j >> 2) | (TAG_ACCEPT << 24), pk);
+            cur = philox4x32_more(cur, (uint32_t)(ROUNDS + (j >> 2) - 2), pk.k[0], pk.k[1]);
         const int m = j & 3;
         const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
         uint32_t lo = ((m1 >> b) & 1u) ? low1 : low0;
@@ -292,9 +277,10 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
     for (int v = 0; v < V; ++v) s0[v] = s[v];
     PhiloxSite<ROUNDS, V> ph;
     ph.prepare(site, gw0w, sweep, pk);
+    static_assert(ISING_ROWS_DEFER_RARE == 0 || ISING_ROWS_DEFER_RARE == 1, "see the knob's description");
     constexpr bool kDefer = ISING_ROWS_DEFER_RARE != 0;
-    constexpr bool kVote = ISING_ROWS_DEFER_RARE == 2;
     uint32_t left[V], lm1[V], lm2[V];
+    u32x4 blk1[kDefer ? V : 1];   // deferred form: the second Philox block of every word
     uint32_t any_left = 0;
     uint32_t nb0[V], nb1[V], nb2[V];
 #pragma unroll
@@ -316,6 +302,7 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
             up, m1, m2, mx, r, site, gw0w + v, sweep, pk, kDefer ? &left[v] : nullptr);
         s[v] ^= flip;
         if constexpr (kDefer) {
+            blk1[v] = u32x4{r[4], r[5], r[6], r[7]};
             lm1[v] = m1;
             lm2[v] = m2;
             any_left |= left[v];
@@ -338,38 +325,12 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
         uint32_t extra[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) extra[v] = 0;
-        if (kVote && __any_sync(__activemask(), any_left != 0u)) {
-            // Words with three or more ties: 1 % of the words at low temperature, so three warps
-            // in four meet one per site group.  The warp goes through the V words together; ties
-            // 3..6 of a word are resolved in straight-line code on Philox call 2, whose rounds 1-3
-            // share the per-word products with calls 0 and 1 (q = 3: seven or more ties).
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                uint32_t eq = left[v];
-                for (uint32_t q = 2; __any_sync(__activemask(), eq != 0u); ++q) {
-                    uint32_t r2[4];
-                    ph.finish_call(v, q, site, sweep, pk, r2);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t bit = eq & (0u - eq);
-                        uint32_t acc = lt_mask(r2[j], mx.low[0], mx.one);
-                        acc = (lm1[v] & lt_mask(r2[j], mx.low[1], mx.one)) | (~lm1[v] & acc);
-                        if (DIM == 3) acc = (lm2[v] & lt_mask(r2[j], mx.low[2], mx.one)) | (~lm2[v] & acc);
-                        extra[v] |= bit & acc;
-                        eq -= bit;
-                    }
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < V; ++v) s[v] ^= extra[v];
-        }
-        if (!kVote && any_left) {  // a word with three or more ties (rare)
+        if (any_left) {  // a word with three or more ties (rare)
 #pragma unroll
             for (int v = 0; v < V; ++v)
                 if (left[v])
                     extra[v] = msc_resolve_rest<DIM == 3 ? 3 : 2, K, ROUNDS>(
-                        left[v], lm1[v], lm2[v], mx.low[0], mx.low[1], mx.low[2], site,
-                        gw0w + v, sweep, pk);
+                        left[v], lm1[v], lm2[v], mx.low[0], mx.low[1], mx.low[2], blk1[v], pk);
 #pragma unroll
             for (int v = 0; v < V; ++v) s[v] ^= extra[v];
         }

@@ -2,7 +2,10 @@
 
 The reference has no tests; these vectors come from the generators' authors (Vigna's
 xoshiro256++ reference output, SplitMix64, Random123's kat_vectors for Philox4x32-10)."""
+import os
+
 import numpy as np
+import pytest
 
 
 def test_xoshiro256pp_reference_vector(oracle):
@@ -81,3 +84,45 @@ def test_philox4x32_7_kat(oracle):
     # Random123 kat_vectors, philox4x32 7 rounds
     got = oracle.philox4x32([0, 0, 0, 0], [0, 0], 7)
     assert list(got) == [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]
+
+
+def test_continuation_rounds_of_the_library_header(oracle, tmp_path):
+    """The tie resolver's words beyond the calls a site update makes anyway are continuation
+    rounds of its last Philox block (csrc/philox.h: philox4x32_more, oracle/msc_mirror.c:
+    stream_word_tag).  The library's header is host + device code: compiled here for the host,
+    one more round on a finished R-round block must equal the (R + 1)-round function of the same
+    counter, for the library's own philox4x32 and for the mirror's."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    src = tmp_path / "more.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "philox.h"
+using namespace ising;
+int main() {
+    const uint32_t c[4] = {0x243f6a88u, 0x85a308d3u, 0x13198a2eu, 0x01000001u};
+    const uint32_t k0 = 0xa4093822u, k1 = 0x299f31d0u;
+    u32x4 s7 = philox4x32<7>(c[0], c[1], c[2], c[3], k0, k1);
+    u32x4 m8 = philox4x32_more(s7, 7, k0, k1), m9 = philox4x32_more(m8, 8, k0, k1);
+    u32x4 f8 = philox4x32<8>(c[0], c[1], c[2], c[3], k0, k1), f9 = philox4x32<9>(c[0], c[1], c[2], c[3], k0, k1);
+    const PhiloxKeys pk = philox_round_keys(k0, k1);
+    u32x4 p7 = philox4x32_keys<7>(c[0], c[1], c[2], c[3], pk);
+    u32x4 q8 = philox4x32_more(p7, 7, pk.k[0], pk.k[1]);
+    const int ok = m8.x == f8.x && m8.y == f8.y && m8.z == f8.z && m8.w == f8.w &&
+                   m9.x == f9.x && m9.y == f9.y && m9.z == f9.z && m9.w == f9.w &&
+                   q8.x == f8.x && q8.y == f8.y && q8.z == f8.z && q8.w == f8.w;
+    std::printf("%d %08x %08x %08x %08x\n", ok, f8.x, f8.y, f8.z, f8.w);
+    return ok ? 0 : 1;
+}
+''')
+    exe = tmp_path / "more"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyisingmontecarlo_b200", "csrc")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "1"
+    want = oracle.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x01000001], [0xa4093822, 0x299f31d0], 8)
+    assert [int(x, 16) for x in out[1:]] == [int(v) for v in want]
