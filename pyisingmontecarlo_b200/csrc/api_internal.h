@@ -190,6 +190,7 @@ int ensure_edge_general_on_device(ising_ctx* ctx, ising_graph* g, bool stencil_l
 void count_launch(ising_sim* s, int n);
 uint64_t threshold64(double beta, double de, int K);
 int sim_enqueue_sweeps(ising_sim* s, const double* betas, uint64_t nsweeps);
+int sim_enqueue_sweeps_counting(ising_sim* s, uint64_t nsweeps, unsigned long long* d_counts, bool* counted);
 // zero_first = false: the caller guarantees a zeroed buffer (the tempering cycle zeroes it in k_pt_cycle)
 int sim_count_nsat(ising_sim* s, unsigned long long* d_counts, bool zero_first = true);
 int sim_energies_to_device(ising_sim* s, double* d_out, uint64_t estride, uint64_t eoff);

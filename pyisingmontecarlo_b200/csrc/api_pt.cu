@@ -416,13 +416,14 @@ static int pt_device_swap(ising_pt* pt) {
 
 // One launch for everything between two batches of sweeps (see k_pt_cycle); with a communicator
 // the energies are computed first, gathered, and the rest follows in one launch.
-static int pt_cycle(ising_pt* pt, uint64_t t, bool do_swap) {
+// counted: the sweeps before left the satisfied-bond counts in pt->d_nsat (sim_enqueue_sweeps_counting)
+static int pt_cycle(ising_pt* pt, uint64_t t, bool do_swap, bool counted = false) {
     ising_ctx* ctx = pt->ctx;
     ising_sim* sim = pt->sim;
     if (sim->real) return fail(ctx, ISING_E_UNSUPPORTED, "tempering needs integer energy classes");
     const HostGraph& h = pt->g->h;
     const bool multi = pt->comm && pt->world > 1;
-    int rc = sim_count_nsat(sim, pt->d_nsat, false);
+    int rc = counted ? ISING_OK : sim_count_nsat(sim, pt->d_nsat, false);
     if (rc) return rc;
     PtCycleArgs a;
     a.nsat = pt->d_nsat;
@@ -619,10 +620,11 @@ extern "C" int ising_pt_timesteps_sample(ising_pt* pt, uint64_t timesteps, uint6
     int rc = ISING_OK;
     while (remaining > 0 && rc == ISING_OK) {
         const uint64_t t = std::min(std::min(to_sample, to_swap), remaining);
-        rc = sim_enqueue_sweeps(pt->sim, nullptr, t);
+        bool counted = false;
+        rc = sim_enqueue_sweeps_counting(pt->sim, t, pt->d_nsat, &counted);
         if (rc) break;
         to_sample -= t; to_swap -= t; remaining -= t;
-        rc = pt_cycle(pt, t, to_swap == 0);    // energies, (all-gather,) time average, swap step, tables
+        rc = pt_cycle(pt, t, to_swap == 0, counted);    // energies, (all-gather,) time average, swap step, tables
         if (rc) break;
         if (to_swap == 0) to_swap = replica_swap_freq;
         if (to_sample == 0) {

@@ -446,12 +446,14 @@ extern "C" int ising_sim_set_moves(ising_sim* s, const ising_moves* mv) {
 
 // Launch-bound sizes: a whole chunk of sweeps in one cooperative launch.  Returns 1 when done
 // that way, 0 when the caller should fall back to per-phase launches, < 0 on error (rc in *err).
+// counts_last (per-replica betas only): hist[e] receives the counts of the LAST sweep of the chunk
+// (k_sweep_stencil_cluster<ACC, PERBETA>) instead of a history of all sweeps.
 static int sim_sweeps_coop(ising_sim* s, const double* betas, uint64_t nt, unsigned long long* hist,
-                           int* err, uint32_t hist_stride = 0) {
+                           int* err, uint32_t hist_stride = 0, bool counts_last = false) {
     if (hist_stride == 0) hist_stride = s->lay.W * 32;   // words of history per sweep
     *err = ISING_OK;
     if (s->general || s->real || s->moves_active || nt == 0) return 0;
-    if (s->perbeta && (hist || s->planes != 6)) return 0;
+    if (s->perbeta ? (s->planes != 6 || (hist != nullptr) != counts_last) : counts_last) return 0;
     if ((uint64_t)s->lay.halfN * s->lay.W > (1ull << 19)) return 0;  // big enough to fill the GPU
     ising_ctx* ctx = s->ctx;
     const HostGraph& h = s->g->h;
@@ -543,6 +545,30 @@ int sim_count_nsat(ising_sim* s, unsigned long long* d_counts, bool zero_first) 
     if (n < 0) return fail(ctx, ISING_E_CUDA, "energy launch failed");
     count_launch(s, n);
     return ISING_OK;
+}
+
+// The sweeps of one tempering chunk (per-replica betas), enqueued like sim_enqueue_sweeps; when the
+// lattice runs inside one thread-block cluster the last sweep also leaves the satisfied-bond counts
+// of the final configuration in d_counts (zeroed by the caller) and *counted is set: the swap cycle
+// then needs no separate count pass.  ISING_PT_NO_FUSED_COUNTS=1 is the A/B knob.
+int sim_enqueue_sweeps_counting(ising_sim* s, uint64_t nsweeps, unsigned long long* d_counts, bool* counted) {
+    *counted = false;
+    static const bool off = getenv("ISING_PT_NO_FUSED_COUNTS") != nullptr;
+    if (off || !s->perbeta || nsweeps == 0) return sim_enqueue_sweeps(s, nullptr, nsweeps);
+    if (nsweeps > 4096) {
+        const int rc = sim_enqueue_sweeps(s, nullptr, nsweeps - 4096);
+        if (rc) return rc;
+        nsweeps = 4096;
+    }
+    if (s->sweep_counter + nsweeps > 0xFFFFFFFFull) return sim_enqueue_sweeps(s, nullptr, nsweeps);  // reports the wrap
+    int err = ISING_OK;
+    const int done = sim_sweeps_coop(s, nullptr, nsweeps, d_counts, &err, 0, true);
+    if (done < 0) return err;
+    if (done) {
+        *counted = true;
+        return ISING_OK;
+    }
+    return sim_enqueue_sweeps(s, nullptr, nsweeps);
 }
 
 // nsweeps sweeps enqueued on the context's stream, no host wait and no timing (the tempering

@@ -2,6 +2,7 @@
 // bookkeeping, time-averaged energies, slot-ordered sample rows.  Everything a tempering cycle
 // needs between two sweeps stays on the stream; the host only enqueues.
 #include "kernels.h"
+#include "msc_device.cuh"
 #include "philox.h"
 #include "pt_exp.h"
 
@@ -127,6 +128,10 @@ __global__ void __launch_bounds__(256) k_pt_cycle(const __grid_constant__ PtCycl
     __shared__ unsigned int s_swaps;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) s_swaps = 0;
+    // programmatic dependent launch: scheduled while the sweeps before drain, and the sweeps after
+    // are scheduled while this block works (both sides wait for their predecessor's completion)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (a.nsat) {
         for (uint32_t e = tid; e < a.e32; e += blockDim.x) {
             if (e < a.E) {
@@ -194,8 +199,7 @@ __global__ void __launch_bounds__(256) k_pt_cycle(const __grid_constant__ PtCycl
 }
 
 int launch_pt_cycle(const PtCycleArgs& a, cudaStream_t st) {
-    k_pt_cycle<<<1, 256, 0, st>>>(a);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    return launch_pdl(k_pt_cycle, dim3(1), dim3(256), 0, st, a) == cudaSuccess ? 1 : -1;
 }
 
 }  // namespace ising

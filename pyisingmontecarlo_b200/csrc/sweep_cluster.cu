@@ -13,6 +13,9 @@ namespace ising {
 // nsat_hist[t * cw + e] (per-sweep energies, lattice.rs:454), reduced per CTA.
 // PERBETA: every replica bit at its own inverse temperature (parallel tempering between two
 // swap steps): thresholds come from the bit-sliced tables instead of th_table.
+// ACC && PERBETA: tempering reads energies at the end of a chunk only - the LAST sweep's second
+// phase adds its counts to nsat_hist[e] (the swap cycle's satisfied-bond counters), which saves
+// the separate count pass between the sweeps and the swap step.
 template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool PERBETA>
 __global__ void __launch_bounds__(256)
 k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict__ jmask, Layout L,
@@ -21,7 +24,7 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
                         uint32_t by_row, uint32_t row_step, uint32_t step_y, uint32_t step_z,
                         unsigned long long* __restrict__ nsat_hist, uint32_t cw,
                         const uint32_t* __restrict__ tplane, const uint32_t* __restrict__ tlow) {
-    static_assert(!(PERBETA && ACC), "tempering reads energies at swap steps only");
+    constexpr bool ACC_EVERY = ACC && !PERBETA, ACC_LAST = ACC && PERBETA;
     extern __shared__ uint32_t sm[];  // ACC: reduction scratch
     __shared__ MscThresholds th[2];  // this sweep's thresholds / the next sweep's, prefetched
     cg::cluster_group cluster = cg::this_cluster();
@@ -29,6 +32,10 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
     const size_t jsz = (size_t)2 * DIM * L.halfN;
     const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
     constexpr uint32_t TW = sizeof(MscThresholds) / 4;
+    // programmatic dependent launch (no-ops on an ordinary launch): between two chunks of a tempering
+    // run sits one small kernel (k_pt_cycle) - each is scheduled while its predecessor drains
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!PERBETA && tid < TW)
         reinterpret_cast<uint32_t*>(&th[0])[tid] = reinterpret_cast<const uint32_t*>(th_table)[tid];
     __syncthreads();
@@ -43,10 +50,15 @@ k_sweep_stencil_cluster(uint32_t* __restrict__ spins, const uint32_t* __restrict
             reinterpret_cast<uint32_t*>(&th[(t + 1) & 1u])[tid] =
                 reinterpret_cast<const uint32_t*>(th_table + t + 1)[tid];
         cluster.sync();  // release / acquire at cluster scope: the other colour is complete
-        sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC, false, PERBETA, true>(
-            spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, cur,
-            ACC ? nsat_hist + (size_t)t * cw : nullptr, row_step, step_y, step_z, sm, tplane, tlow,
-            by_row);
+        if (ACC_LAST && t + 1 == nsweeps)
+            sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC_LAST, false, PERBETA, true>(
+                spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, cur,
+                nsat_hist, row_step, step_y, step_z, sm, tplane, tlow, by_row);
+        else
+            sweep_colour_phase<DIM, PMJ, K, ROUNDS, V, ACC_EVERY, false, PERBETA, true>(
+                spins + csz, spins, PMJ ? jmask + jsz : nullptr, L, 1u, sweep0 + t, pk, gw0, antiferro, cur,
+                ACC_EVERY ? nsat_hist + (size_t)t * cw : nullptr, row_step, step_y, step_z, sm, tplane, tlow,
+                by_row);
         cluster.sync();
     }
 }
@@ -87,13 +99,16 @@ static int cluster_launch_n(const SweepArgs& a, const MscThresholds* th_dev, uin
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    static const bool no_pdl = getenv("ISING_NO_PDL") != nullptr;
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = g;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (PERBETA && !no_pdl) ? 2 : 1;   // tempering chunks alternate with k_pt_cycle
     if (g > 8) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
             return -1;
@@ -125,6 +140,9 @@ static int cluster_launch(const SweepArgs& a, const MscThresholds* th_dev, uint3
 template <int DIM, bool PMJ, int V>
 static int cluster_rounds(const SweepArgs& a, const MscThresholds* th_dev, uint32_t nsweeps,
                           unsigned long long* hist, uint32_t cw, cudaStream_t st) {
+    if (a.tplane && hist)   // tempering chunk that ends with the satisfied-bond counts of its last sweep
+        return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, true, true>(a, th_dev, nsweeps, hist, cw, st)
+                             : cluster_launch<DIM, PMJ, 10, V, true, true>(a, th_dev, nsweeps, hist, cw, st);
     if (a.tplane)
         return a.rounds == 7 ? cluster_launch<DIM, PMJ, 7, V, false, true>(a, th_dev, nsweeps, nullptr, cw, st)
                              : cluster_launch<DIM, PMJ, 10, V, false, true>(a, th_dev, nsweeps, nullptr, cw, st);
@@ -142,7 +160,7 @@ int launch_sweeps_stencil_cluster(const SweepArgs& a, const MscThresholds* th_de
     const Layout& L = a.lay;
     const bool d3 = L.kind == ISING_KIND_STENCIL3D;
     if (!d3 && L.kind != ISING_KIND_STENCIL2D) return 0;
-    if (a.planes != 6 || a.nsat_out || (a.tplane && hist)) return 0;
+    if (a.planes != 6 || a.nsat_out) return 0;
     const uint64_t words = (uint64_t)L.halfN * L.W;
     static const uint64_t max_words = getenv("ISING_CLUSTER_WORDS") ? strtoull(getenv("ISING_CLUSTER_WORDS"), nullptr, 10) : 16384;
     if (words > max_words) return 0;

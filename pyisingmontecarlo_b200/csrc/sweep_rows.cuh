@@ -36,10 +36,13 @@
 #ifndef ISING_ROWS_DEFER_RARE
 // third-and-later ties of a word (their words come from continuation rounds of the word's second
 // Philox block, msc_device.cuh): 0 = divergent loop inside the word, where that block is still in
-// registers; 1 = all V words after the word loop (the blocks are kept: 4 V registers).
-// History (profiles/r02_rare_path_ab.log): while those words came from a third Philox call the
-// deferred form was the faster one, and a warp-voted form with shared rounds 1-3 spilled.
-#define ISING_ROWS_DEFER_RARE 0
+// registers; 1 = all V words after the word loop (the blocks are kept: 4 V registers); 2 = form 1 in
+// the plain colour phase, form 0 in the accumulating phase and in the 128-thread shape, which
+// have no registers to spare.
+// Config 3 on the annealing ramp, us per sweep without / with energies (profiles/
+// r02_beta_dependence.log): form 0 63.6 / 72.0, form 1 62.3 / 72.2; with the third Philox call
+// these words used to cost (r02_rare_path_ab.log): 68.9 / 79.0.
+#define ISING_ROWS_DEFER_RARE 2
 #endif
 #ifndef ISING_ROWS_SPLIT_ACC_DEFAULT
 #define ISING_ROWS_SPLIT_ACC_DEFAULT 0  // 1: per-sweep energies by a count-only pass instead of the fused phase
@@ -240,17 +243,17 @@ __device__ __forceinline__ uint32_t msc_flip_mask_mux(uint32_t up, uint32_t m1, 
 }
 
 // third and later ties of a word (deferred form): resolver words 8, 9, ... = continuation rounds
-// of the word's second Philox block `cur` (K + SPARE = 8: the first word needs a fresh round)
+// of the word's second Philox block `cur`
 template <int NCLS, int K, int ROUNDS>
 __device__ __noinline__ uint32_t msc_resolve_rest(uint32_t eq, uint32_t m1, uint32_t m2, uint32_t low0,
                                                   uint32_t low1, uint32_t low2, u32x4 cur,
                                                   const PhiloxKeys& pk) {
-    static_assert(K >= 6, "deferred ties start at resolver word 8");
+    constexpr int SPARE = (8 - K) < 2 ? (8 - K) : 2;
     uint32_t flip = 0;
-    int j = 8;
+    int j = K + SPARE;   // below 8: words of the second block that the straight-line ties left over
     do {
         const int b = __ffs((int)eq) - 1;
-        if ((j & 3) == 0)
+        if ((j & 3) == 0 && j >= 8)
             cur = philox4x32_more(cur, (uint32_t)(ROUNDS + (j >> 2) - 2), pk.k[0], pk.k[1]);
         const int m = j & 3;
         const uint32_t v = m == 0 ? cur.x : (m == 1 ? cur.y : (m == 2 ? cur.z : cur.w));
@@ -277,8 +280,9 @@ __device__ __forceinline__ void update_site(uint32_t (&s)[V], const uint32_t (&n
     for (int v = 0; v < V; ++v) s0[v] = s[v];
     PhiloxSite<ROUNDS, V> ph;
     ph.prepare(site, gw0w, sweep, pk);
-    static_assert(ISING_ROWS_DEFER_RARE == 0 || ISING_ROWS_DEFER_RARE == 1, "see the knob's description");
-    constexpr bool kDefer = ISING_ROWS_DEFER_RARE != 0;
+    static_assert(ISING_ROWS_DEFER_RARE >= 0 && ISING_ROWS_DEFER_RARE <= 2, "see the knob's description");
+    // (NPC != SW_NP marks the 128-thread shape: compiled for 73 registers, it would spill the kept blocks)
+    constexpr bool kDefer = ISING_ROWS_DEFER_RARE == 1 || (ISING_ROWS_DEFER_RARE == 2 && !ACC && NPC == SW_NP);
     uint32_t left[V], lm1[V], lm2[V];
     u32x4 blk1[kDefer ? V : 1];   // deferred form: the second Philox block of every word
     uint32_t any_left = 0;
