@@ -110,7 +110,8 @@ def run_tempering_loop(stepper, nbetas, nvars, timesteps, replica_swap_freq, sam
 
 class LatticeTempering:
     """Replica container with the reference's surface (tempering.rs:43-113): add_graph(..., beta),
-    qmc_timesteps, qmc_timesteps_sample, get_total_swaps.  Classical replicas only."""
+    qmc_timesteps, qmc_timesteps_sample, get_total_swaps, get_graph_itime, clone, save_to_file /
+    read_from_file.  Classical replicas only."""
 
     def __init__(self, edges, seed=None, use_allocator=None, *, device=None, process_group=None):
         if len(edges) == 0:
@@ -227,8 +228,34 @@ class LatticeTempering:
     def get_total_swaps(self):
         return 0 if self._pt is None else self._pt.total_swaps()
 
+    def clone(self):
+        """tempering.rs:302-304: a copy of the container and of all its graphs.  The copy owns its
+        own device state (configurations, slot permutation, sweep and swap counters); the RNG is
+        counter-based, so original and copy continue identically until they are driven differently.
+        A ladder that is sharded over ranks is cloned rank by rank (a collective-free call)."""
+        edges = [((int(x), int(y)), float(w)) for x, y, w in zip(self._a, self._b, self._j)]
+        obj = LatticeTempering(edges, self._seed, device=self._device, process_group=self._group)
+        obj._betas = list(self._betas)
+        if self._pt is not None:
+            obj._seed = int(self._pt.seed)
+            obj._ensure().restore(self._pt.checkpoint())
+        return obj
+
+    def get_graph_itime(self, g):
+        """tempering.rs:119-148 returns the imaginary-time slices bool[cutoff, nvars] of QMC graph g;
+        a classical replica has one slice: bool[1, nvars], the configuration currently at beta_g."""
+        n = len(self._betas)
+        if not 0 <= int(g) < n:
+            raise ValueError(f"Attempted to get graph {g} of {n}")
+        pt = self._ensure()
+        if self._coll.active:
+            states = self._coll.allgather_concat(pt.local_states(), self._counts)
+        else:
+            states = pt.local_states()
+        cfg = int(np.argsort(pt.slots().astype(np.int64))[int(g)])   # configuration at slot g
+        return np.ascontiguousarray(states[cfg][None, :])
+
     def __getattr__(self, name):
-        if name in ("get_graph_itime", "clone") or name.startswith(
-                "run_quantum_monte_carlo"):
+        if name.startswith("run_quantum_monte_carlo"):
             raise NotImplementedError(f"{name}: only the classical replica loop is provided here")
         raise AttributeError(name)

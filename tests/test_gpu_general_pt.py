@@ -370,6 +370,31 @@ def test_checkpoints_resume_bit_for_bit(pkg, oracle, tmp_path):
         pkg.ClassicIsing.read_from_file(path)
 
 
+def test_lattice_tempering_clone_and_graph_itime(pkg, oracle):
+    """tempering.rs:302-304 (clone) and 119-148 (get_graph_itime, one slice for a classical replica):
+    a clone owns its own device state and continues exactly like the original; graph g is the
+    configuration currently at beta_g, i.e. row g of a sample taken at the same time."""
+    edges = oracle.square_edges(6)
+    lt = pkg.LatticeTempering(edges, seed=11)
+    for beta in np.linspace(0.2, 0.8, 7):
+        lt.add_graph(0.0, 0.0, beta)
+    assert lt.clone().get_num_graphs() == 7           # before the first run: nothing on the device yet
+    states, _ = lt.qmc_timesteps_sample(12, 2, 12)
+    assert lt.get_total_swaps() > 0
+    for g in range(7):
+        it = lt.get_graph_itime(g)
+        assert it.shape == (1, 36) and it.dtype == np.bool_ and (it[0] == states[g, 0]).all()
+    with pytest.raises(ValueError, match="Attempted to get graph 7 of 7"):
+        lt.get_graph_itime(7)
+    cp = lt.clone()
+    assert cp.get_total_swaps() == lt.get_total_swaps()
+    s1, e1 = lt.qmc_timesteps_sample(15, 3, 5)
+    for g in range(7):                                # the clone did not move with the original
+        assert (cp.get_graph_itime(g)[0] == states[g, 0]).all()
+    s2, e2 = cp.qmc_timesteps_sample(15, 3, 5)
+    assert (s1 == s2).all() and (e1 == e2).all() and cp.get_total_swaps() == lt.get_total_swaps()
+
+
 def test_reference_readme_usage_runs_unchanged(oracle):
     """The usage section of the reference's README.md (lines 44-62), verbatim through the
     `py_monte_carlo` module name: same calls, same return layouts; energies equal the Hamiltonian
