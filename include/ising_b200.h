@@ -115,8 +115,9 @@ ISING_API int ising_sim_create_ex(ising_ctx *ctx, const ising_graph *g, uint64_t
                         uint64_t seed, uint64_t replica_offset, uint32_t flags, ising_sim **out);
 ISING_API void ising_sim_destroy(ising_sim *sim);
 /* Experiment e runs at betas[e] from now on (parallel tempering: one replica bit per
- * temperature); afterwards ising_sim_sweeps takes betas = NULL.  Needs integer energy classes
- * (all |J| equal, no bias); on lattices the threshold tables exist for planes = 6. */
+ * temperature); afterwards ising_sim_sweeps takes betas = NULL.  Graphs with integer energy
+ * classes (all |J| equal, no bias) get bit-sliced per-replica threshold tables (on lattices for
+ * planes = 6); real couplings / biases run on the float-field kernel with one beta per replica bit. */
 ISING_API int ising_sim_set_betas(ising_sim *sim, const double *betas /* E */);
 /* Tuning knobs of the multi-spin-coded kernel; 0 keeps the default.  planes = bit-planes
  * compared before the per-bit resolver (5..7), rounds = Philox4x32 rounds (7 or 10).      */
@@ -279,7 +280,10 @@ ISING_API int ising_comm_info(const ising_comm *comm, int *rank, int *world);
  * betas of two configurations (equivalent to exchanging the configurations, tempering.rs:192),
  * nothing moves.  Multi-GPU: rank r owns configurations [cfg_lo, cfg_hi); after an all-gather
  * of the per-configuration energies every rank takes identical swap decisions (Philox keyed
- * by seed and swap step), so there is no second collective. */
+ * by seed and swap step), so there is no second collective.  Any graph ising_sim_create takes:
+ * integer-class graphs are bit-exact against the CPU mirror; real couplings / biases (a longitudinal
+ * field, tempering.rs:70-75) use the float-field kernel and f64 energies from the device, whose
+ * atomic summation order can move a swap decision that sits within an ulp of its threshold. */
 ISING_API int ising_pt_create(ising_ctx *ctx, const ising_graph *g, const double *betas, uint64_t nbetas,
                     uint64_t cfg_lo, uint64_t cfg_hi, uint64_t seed, ising_pt **out);
 ISING_API void ising_pt_destroy(ising_pt *pt);

@@ -39,7 +39,8 @@ NcclApi& nccl_api() {
             if (api.handle) break;
         }
         if (!api.handle) {
-            api.err = std::string("cannot load NCCL: ") + (dlerror() ? dlerror() : "libnccl.so.2 not found");
+            const char* why = dlerror();   // (a second call would return NULL: the message is consumed)
+            api.err = std::string("cannot load NCCL: ") + (why ? why : "libnccl.so.2 not found");
             return;
         }
         bool ok = true;

@@ -9,12 +9,31 @@ extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
     CtxLock _lk(s ? s->ctx : nullptr);
     if (!s || !betas) return fail(s ? s->ctx : nullptr, ISING_E_INVALID, "sim/betas is NULL");
     ising_ctx* ctx = s->ctx;
-    if (s->real)
-        return fail(ctx, ISING_E_UNSUPPORTED,
-                    "per-experiment betas need integer energy classes (all |J| equal, no bias)");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const HostGraph& h = s->g->h;
     const uint32_t W = s->lay.W, E32 = 32 * W;
+    if (s->real) {
+        // float-field kernel: no tables, the betas themselves (f64 bit patterns) by replica bit
+        std::vector<unsigned long long> bits(E32);
+        std::vector<uint32_t> slot(E32);
+        for (uint32_t e = 0; e < E32; ++e) {
+            const double beta = betas[e < s->E ? e : 0];
+            memcpy(&bits[e], &beta, sizeof beta);
+            slot[e] = e;
+        }
+        if (!s->d_t64 || s->t64_rows != E32) {
+            cudaFree(s->d_t64); cudaFree(s->d_slot);
+            s->d_t64 = nullptr; s->d_slot = nullptr;
+            CUDA_TRY(ctx, dev_alloc(&s->d_t64, (size_t)E32));
+            CUDA_TRY(ctx, dev_alloc(&s->d_slot, (size_t)E32));
+            s->t64_rows = E32;
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(s->d_t64, bits.data(), bits.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(s->d_slot, slot.data(), slot.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // locals
+        s->perbeta = true;
+        return ISING_OK;
+    }
     if (!s->general) {
         // checkerboard layout: classes dE = 4|J|, 8|J| (, 12|J|); tables are built for 6 planes
         if (s->planes != 6)
@@ -89,11 +108,25 @@ extern "C" int ising_sim_set_betas(ising_sim* s, const double* betas) {
 // rebuilds the bit-sliced tables from the resident rows - no exp(), no upload, no host wait.
 static int sim_set_slot_thresholds(ising_sim* s, const double* betas_by_slot, uint64_t R) {
     ising_ctx* ctx = s->ctx;
-    if (s->real)
-        return fail(ctx, ISING_E_UNSUPPORTED,
-                    "per-experiment betas need integer energy classes (all |J| equal, no bias)");
     const HostGraph& h = s->g->h;
     const uint32_t W = s->lay.W, E32 = 32 * W;
+    if (s->real) {
+        // real couplings / biases: the float-field kernel takes exp(-beta dE) per replica bit, so the
+        // "rows" are the betas themselves (f64 bit patterns by slot) behind the same replica -> slot map
+        std::vector<unsigned long long> bits(R);
+        for (uint64_t r = 0; r < R; ++r) memcpy(&bits[r], &betas_by_slot[r], sizeof(double));
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        cudaFree(s->d_t64); s->d_t64 = nullptr;
+        cudaFree(s->d_slot); s->d_slot = nullptr;
+        CUDA_TRY(ctx, dev_alloc(&s->d_t64, (size_t)R));
+        CUDA_TRY(ctx, dev_alloc(&s->d_slot, (size_t)E32));
+        CUDA_TRY(ctx, cudaMemsetAsync(s->d_slot, 0, (size_t)E32 * 4, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(s->d_t64, bits.data(), bits.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // bits is a local
+        s->perbeta = true;
+        s->t64_rows = (uint32_t)R;
+        return ISING_OK;
+    }
     const size_t per = s->general ? (size_t)(GEN_MAX_DEG + 1) * GEN_MAX_CLS : 3;
     if (!s->general && s->planes != 6)
         return fail(ctx, ISING_E_UNSUPPORTED, "per-experiment betas on a lattice need planes = 6");
@@ -137,6 +170,7 @@ static int sim_set_slot_thresholds(ising_sim* s, const double* betas_by_slot, ui
 // bit-sliced threshold tables of the sim from its resident rows and slot_of_replica (enqueue only)
 static int sim_tables_from_slots(ising_sim* s) {
     ising_ctx* ctx = s->ctx;
+    if (s->real) return ISING_OK;   // the float-field kernel reads the betas through the slot map
     const int n = s->general ? launch_build_tables(s->d_t64, s->d_slot, s->lay.W, s->planes, s->d_tplane,
                                                    s->d_tlow, ctx->stream)
                              : launch_build_tables_stencil(s->d_t64, s->d_slot, s->lay.W, s->planes,
@@ -420,13 +454,21 @@ static int pt_device_swap(ising_pt* pt) {
 static int pt_cycle(ising_pt* pt, uint64_t t, bool do_swap, bool counted = false) {
     ising_ctx* ctx = pt->ctx;
     ising_sim* sim = pt->sim;
-    if (sim->real) return fail(ctx, ISING_E_UNSUPPORTED, "tempering needs integer energy classes");
     const HostGraph& h = pt->g->h;
     const bool multi = pt->comm && pt->world > 1;
-    int rc = counted ? ISING_OK : sim_count_nsat(sim, pt->d_nsat, false);
+    int rc = ISING_OK;
+    if (sim->real) {
+        // real couplings / biases: f64 energies from the CSR energy kernel instead of bond counters
+        rc = sim_energies_to_device(sim, pt->d_e_local, 1, 0);
+        if (rc == ISING_OK && !multi)
+            CUDA_TRY(ctx, cudaMemcpyAsync(pt->d_e_all, pt->d_e_local, sim->E * sizeof(double),
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (!counted) {
+        rc = sim_count_nsat(sim, pt->d_nsat, false);
+    }
     if (rc) return rc;
     PtCycleArgs a;
-    a.nsat = pt->d_nsat;
+    a.nsat = sim->real ? nullptr : pt->d_nsat;
     a.e_local = pt->d_e_local;
     a.e_all = pt->d_e_all;
     a.E = (uint32_t)sim->E;
@@ -456,12 +498,14 @@ static int pt_cycle(ising_pt* pt, uint64_t t, bool do_swap, bool counted = false
     a.tlow = sim->d_tlow;
     if (multi) {
         // energies first (no accumulate / swap: R = 0), all-gather, then the rest without the energy part
-        PtCycleArgs e = a;
-        e.R = 0;
-        e.do_swap = 0;
-        e.t64 = nullptr;
-        if (launch_pt_cycle(e, ctx->stream) < 0) return fail(ctx, ISING_E_CUDA, "tempering cycle launch failed");
-        count_launch(sim, 1);
+        if (!sim->real) {
+            PtCycleArgs e = a;
+            e.R = 0;
+            e.do_swap = 0;
+            e.t64 = nullptr;
+            if (launch_pt_cycle(e, ctx->stream) < 0) return fail(ctx, ISING_E_CUDA, "tempering cycle launch failed");
+            count_launch(sim, 1);
+        }
         const double* mine = pt->d_e_local + (pt->lo - pt->word_lo * 32);
         rc = comm_allgather_bytes(pt->comm, mine, pt->d_e_all, pt->cmax * sizeof(double), ctx->stream);
         if (rc) return rc;

@@ -240,6 +240,8 @@ static int sim_one_sweep_real(ising_sim* s, double beta) {
     a.biasf = g->d_biasf;
     a.W = s->lay.W;
     a.beta = (float)beta;
+    a.beta_slots = s->perbeta ? s->d_t64 : nullptr;   // real sims keep the betas themselves in d_t64
+    a.slot_of_replica = s->perbeta ? s->d_slot : nullptr;
     a.sweep = (uint32_t)s->sweep_counter;
     a.key0 = (uint32_t)s->seed;
     a.key1 = (uint32_t)(s->seed >> 32);

@@ -207,6 +207,10 @@ struct RealSweepArgs {
     const float* biasf;       // per site
     uint32_t W;
     float beta;
+    // per-replica inverse temperatures (tempering): replica bit e of this sim runs at the f64 whose
+    // bit pattern is beta_slots[slot_of_replica[e]]; nullptr = `beta` for every replica
+    const unsigned long long* beta_slots;
+    const uint32_t* slot_of_replica;
     uint32_t sweep, key0, key1, gw0;
     int rounds;
 };

@@ -391,7 +391,10 @@ k_sweep_real(RealSweepArgs a) {
                 const float de = 2.f * si * (bias - h[q]);
                 bool acc = true;
                 if (de > 0.f) {
-                    const float pth = __expf(-a.beta * de) * 4294967296.f;
+                    const float beta = a.beta_slots
+                        ? (float)__longlong_as_double((long long)__ldg(a.beta_slots + __ldg(a.slot_of_replica + w * 32u + b0 + q)))
+                        : a.beta;
+                    const float pth = __expf(-beta * de) * 4294967296.f;
                     acc = rr[q] < __float2uint_rz(pth);  // saturating conversion
                 }
                 if (acc) flip |= 1u << (b0 + q);

@@ -122,6 +122,7 @@ class LatticeTempering:
         self._device = device
         self._group = process_group
         self._betas = []
+        self._longitudinal = None
         self._pt = None
         self._graph = None
 
@@ -131,12 +132,16 @@ class LatticeTempering:
         if transverse != 0.0:
             raise NotImplementedError("SSE quantum replicas (transverse field > 0) remain on the "
                                       "reference; the B200 engine tempers classical replicas")
-        if longitudinal != 0.0:
-            raise NotImplementedError("biases are not supported by the bit-sliced tempering kernels")
         if edges is not None:
             raise NotImplementedError("per-replica edge lists are not supported: replicas share the lattice")
         if self._pt is not None:
             raise RuntimeError("add_graph after the first run is not supported")
+        # replicas of a ladder differ in beta only: one longitudinal field for all of them (a field or
+        # couplings of unequal size put the ladder on the float-field kernels, like Lattice)
+        if self._longitudinal is not None and float(longitudinal) != self._longitudinal:
+            raise NotImplementedError("replicas of one ladder share the longitudinal field: got "
+                                      f"{longitudinal} after {self._longitudinal}")
+        self._longitudinal = float(longitudinal)
         self._betas.append(float(beta))
 
     def get_num_graphs(self):
@@ -147,7 +152,8 @@ class LatticeTempering:
             if not self._betas:
                 raise ValueError("no replicas: call add_graph first")
             ctx = nat.Context.get(self._device)
-            self._graph = nat.Graph.from_edges(ctx, self.nvars, self._a, self._b, self._j)
+            bias = np.full(self.nvars, self._longitudinal) if self._longitudinal else None
+            self._graph = nat.Graph.from_edges(ctx, self.nvars, self._a, self._b, self._j, bias)
             self._coll = _Collective(self._group)
             R = len(self._betas)
             self._counts = [shard_range(R, r, self._coll.world)[1] - shard_range(R, r, self._coll.world)[0]
@@ -202,6 +208,7 @@ class LatticeTempering:
         with open(self._rank_path(path, self._coll), "wb") as f:
             np.savez_compressed(f, kind="LatticeTempering", a=self._a, b=self._b, j=self._j,
                                 betas=np.asarray(self._betas), seed=np.uint64(pt.seed),
+                                longitudinal=np.float64(self._longitudinal or 0.0),
                                 world=self._coll.world, rank=self._coll.rank, **ck)
 
     @staticmethod
@@ -216,8 +223,9 @@ class LatticeTempering:
             edges = [((int(x), int(y)), float(w)) for x, y, w in zip(d["a"], d["b"], d["j"])]
             obj = LatticeTempering(edges, int(d["seed"]) if reseed is None else int(reseed), device=device,
                                    process_group=process_group)
+            longitudinal = float(d["longitudinal"]) if "longitudinal" in d.files else 0.0
             for b in d["betas"]:
-                obj.add_graph(0.0, 0.0, float(b))
+                obj.add_graph(0.0, longitudinal, float(b))
             pt = obj._ensure()
             ck = {k: d[k] for k in ("packed", "sweeps", "slots", "swap_step", "total_swaps")}
             if reseed is not None:
@@ -236,6 +244,7 @@ class LatticeTempering:
         edges = [((int(x), int(y)), float(w)) for x, y, w in zip(self._a, self._b, self._j)]
         obj = LatticeTempering(edges, self._seed, device=self._device, process_group=self._group)
         obj._betas = list(self._betas)
+        obj._longitudinal = self._longitudinal
         if self._pt is not None:
             obj._seed = int(self._pt.seed)
             obj._ensure().restore(self._pt.checkpoint())

@@ -370,6 +370,49 @@ def test_checkpoints_resume_bit_for_bit(pkg, oracle, tmp_path):
         pkg.ClassicIsing.read_from_file(path)
 
 
+def test_tempering_on_real_couplings_and_a_field(pkg, oracle, native):
+    """A ladder over a graph outside the integer-class kernels (Gaussian couplings, a longitudinal
+    field: tempering.rs:70-113 takes a longitudinal field per replica) runs on the float-field kernel
+    with one inverse temperature per replica bit: time-averaged energies per beta against exact
+    enumeration, samples are valid configurations, and per-experiment betas without swaps agree too."""
+    rng = np.random.default_rng(3)
+    n = 9
+    pairs = [(i, (i + 1) % n) for i in range(n)] + [(0, 4), (2, 7), (3, 8)]
+    edges = [(p, float(rng.normal())) for p in pairs]
+    field = 0.3
+    betas = [0.2, 0.35, 0.5, 0.7, 0.9, 1.2]
+    lt = pkg.LatticeTempering(edges, seed=21)
+    for b in betas:
+        lt.add_graph(0.0, field, b)
+    with pytest.raises(NotImplementedError):
+        lt.add_graph(0.0, 0.1, 0.5)          # one field per ladder
+    lt.qmc_timesteps(300)
+    states, energies = lt.qmc_timesteps_sample(40000, replica_swap_freq=2, sampling_freq=4000)
+    assert states.shape == (6, 10, n) and energies.shape == (6,)
+    assert lt.get_total_swaps() > 1000
+    for beta, got in zip(betas, energies):
+        mean, sd, _ = _exact(edges, n, beta, [field] * n)
+        assert abs(got - mean) < 0.15 * sd + 0.05, (beta, got, mean, sd)
+    # a clone continues on the same kernels
+    cp = lt.clone()
+    s1, e1 = lt.qmc_timesteps_sample(40, 2, 20)
+    s2, e2 = cp.qmc_timesteps_sample(40, 2, 20)
+    assert s1.shape == s2.shape == (6, 2, n)
+    # per-experiment betas without swaps (ising_sim_set_betas on a real-coupling sim)
+    lat = pkg.Lattice(edges, seed_gen=2)
+    lat.set_global_bias(field)
+    E = 4096
+    sim = native.Sim(lat.graph(), E, 17)
+    per = np.where(np.arange(E) % 2 == 0, 0.35, 0.9)
+    sim.set_betas(per)
+    sim.sweeps(400)
+    en = sim.energies()
+    for beta, sel in ((0.35, slice(0, None, 2)), (0.9, slice(1, None, 2))):
+        mean, sd, _ = _exact(edges, n, beta, [field] * n)
+        assert abs(en[sel].mean() - mean) < 4.5 * sd / np.sqrt(E / 2) + 1e-6, (beta, en[sel].mean(), mean)
+    sim.close()
+
+
 def test_lattice_tempering_clone_and_graph_itime(pkg, oracle):
     """tempering.rs:302-304 (clone) and 119-148 (get_graph_itime, one slice for a classical replica):
     a clone owns its own device state and continues exactly like the original; graph g is the
