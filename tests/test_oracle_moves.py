@@ -79,3 +79,35 @@ def test_bit_sliced_edge_pass_of_the_mirror_samples_the_boltzmann_law(oracle, na
     e_even = np.array([g.energy(s) for s in even])
     assert len(even) > E // 4
     assert abs(e_even.mean() - exact_even) < 4 * np.sqrt(var_even / len(even)), (e_even.mean(), exact_even)
+
+
+@pytest.mark.parametrize("planes", [1, 2, 6])
+def test_tie_words_of_the_mirror_are_sound_uniforms(oracle, planes):
+    """The production rule takes the resolver words beyond the calls a site update makes anyway from
+    continuation rounds of its last Philox block (philox.h: philox4x32_more).  With six planes only
+    one word in a hundred gets that far; with ONE plane every second uphill decision is a tie, so a
+    word meets ~8 of them and most decisions hang on continuation words (R_4 .. of a single call).
+    The sweep must still sample the Boltzmann law: 4 x 4 ferromagnet and a frustrated +-J torus
+    against exact enumeration, the mean energy at 4 sigma and the histogram of the energy levels at
+    4.5 sigma."""
+    L = 4
+    a = [x + L * y for y in range(L) for x in range(L)] * 2
+    b = [(x + 1) % L + L * y for y in range(L) for x in range(L)] + [x + L * ((y + 1) % L) for y in range(L) for x in range(L)]
+    rng = np.random.default_rng(4)
+    colors = np.array([(n % L + n // L) & 1 for n in range(L * L)], dtype=np.uint32)
+    for j, beta in (([-1.0] * len(a), 0.4), (list(rng.choice([-1.0, 1.0], len(a))), 0.9)):
+        edges = [((int(x), int(y)), w) for x, y, w in zip(a, b, j)]
+        _, p, en = boltzmann(edges, L * L, beta)
+        exact = float((p * en).sum())
+        var = float((p * en * en).sum()) - exact ** 2
+        E = 4096
+        en_m, _ = oracle.msc_mirror(a, b, j, L * L, colors, E, 77 + planes, np.full(50, beta), planes=planes,
+                                    per_sweep=True)
+        e = en_m[:, -1]
+        assert abs(e.mean() - exact) < 4 * np.sqrt(var / E), (planes, beta, e.mean(), exact)
+        # energy-level histogram (levels are multiples of 4 |J|)
+        levels = np.unique(en)
+        pl = np.array([p[en == lv].sum() for lv in levels])
+        counts = np.array([(e == lv).sum() for lv in levels])
+        z = (counts - E * pl) / np.sqrt(np.maximum(E * pl * (1 - pl), 1e-12))
+        assert np.abs(z[pl * E > 5]).max() < 4.5, (planes, beta, z)
