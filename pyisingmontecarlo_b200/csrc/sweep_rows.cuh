@@ -50,6 +50,13 @@
 #ifndef ISING_ROWS_LT_SEL
 #define ISING_ROWS_LT_SEL 0      // 1: tie compare with ISETP + SEL instead of the multiply-add carry
 #endif
+#ifndef ISING_ROWS_ZSKIP
+// 1: the leading planes whose threshold bit is zero in every class (floor(5.77 beta |J|) of them on a
+// cubic lattice: all six from beta = 1.04) skip the class select: a uniform is below such a threshold
+// prefix only if its own bits are zero there, so Z planes cost ceil((Z - 1) / 2) + 2 LOP3 instead of
+// 2 Z LOP3 + 2 Z IMAD.  The plane count is a launch constant (MscMux::z): a uniform switch per word.
+#define ISING_ROWS_ZSKIP 0
+#endif
 #ifndef ISING_ROWS_MUL_SPLIT
 #define ISING_ROWS_MUL_SPLIT 1   // 1: Philox products as mul.hi + mul.lo instead of one 32x32->64 multiply
 #endif
@@ -62,6 +69,7 @@ struct MscMux {
     uint32_t d2[8];   // bit(class 2) - bit(class 0)
     uint32_t low[3];
     uint32_t one;     // 1 (keeps r * one + c an IMAD.WIDE)
+    uint32_t z;       // planes 0 .. z-1 (the most significant ones) are zero in every class
 };
 
 inline MscMux make_mux(const MscThresholds& th) {
@@ -73,6 +81,8 @@ inline MscMux make_mux(const MscThresholds& th) {
     }
     for (int c = 0; c < 3; ++c) m.low[c] = th.low[c];
     m.one = 1u;
+    m.z = 0;
+    while (m.z < 8 && (th.plane[0][m.z] | th.plane[1][m.z] | th.plane[2][m.z]) == 0u) ++m.z;
     return m;
 }
 
@@ -190,6 +200,28 @@ __device__ __forceinline__ uint32_t lt_mask(uint32_t r, uint32_t lo, uint32_t on
 #endif
 }
 
+// The K compare steps of one word with the Z most significant planes known to be zero in every class
+// (borrow of U_top - T_top and the mask of the bits that tie): planes K-1 .. Z in full, then the
+// leading ones at once - U_top < T_top and U_top == T_top both need the uniform's bits to be zero there.
+template <int NCLS, int K, int Z>
+__device__ __forceinline__ void msc_compare_planes(uint32_t m1, uint32_t m2, const MscMux& mx,
+                                                   const uint32_t (&r)[8], uint32_t& eq, uint32_t& borrow) {
+#pragma unroll
+    for (int p = K - 1; p >= Z; --p) {
+        uint32_t t = m1 * mx.d1[p] + mx.c0[p];
+        if (NCLS == 3) t += m2 * mx.d2[p];
+        borrow = maj3(~r[p], t, borrow);
+        eq &= ~(r[p] ^ t);
+    }
+    if (Z > 0) {
+        uint32_t nr = r[0];
+#pragma unroll
+        for (int p = 1; p < Z; ++p) nr |= r[p];
+        borrow &= ~nr;
+        eq &= ~nr;
+    }
+}
+
 // Metropolis mask of one word from eight random words r (two Philox calls).
 //   up: dE > 0;  m1, m2: one-hot masks of uphill classes 1 and 2 (class 0 = up & ~m1 & ~m2)
 template <int NCLS, int K, int ROUNDS>
@@ -199,13 +231,20 @@ __device__ __forceinline__ uint32_t msc_flip_mask_mux(uint32_t up, uint32_t m1, 
                                                       const PhiloxKeys& pk, uint32_t* eq_left = nullptr) {
     static_assert(K >= 4 && K <= 7, "two Philox calls: K planes + (8 - K) resolver words");
     uint32_t eq = up, borrow = 0;
-#pragma unroll
-    for (int p = K - 1; p >= 0; --p) {
-        uint32_t t = m1 * mx.d1[p] + mx.c0[p];
-        if (NCLS == 3) t += m2 * mx.d2[p];
-        borrow = maj3(~r[p], t, borrow);
-        eq &= ~(r[p] ^ t);
+#if ISING_ROWS_ZSKIP
+    switch (mx.z < (uint32_t)K ? mx.z : (uint32_t)K) {   // launch constant: a uniform branch
+        case 0: msc_compare_planes<NCLS, K, 0>(m1, m2, mx, r, eq, borrow); break;
+        case 1: msc_compare_planes<NCLS, K, 1>(m1, m2, mx, r, eq, borrow); break;
+        case 2: msc_compare_planes<NCLS, K, 2>(m1, m2, mx, r, eq, borrow); break;
+        case 3: msc_compare_planes<NCLS, K, 3>(m1, m2, mx, r, eq, borrow); break;
+        case 4: msc_compare_planes<NCLS, K, 4>(m1, m2, mx, r, eq, borrow); break;
+        case 5: msc_compare_planes<NCLS, K, (K >= 5 ? 5 : K)>(m1, m2, mx, r, eq, borrow); break;
+        case 6: msc_compare_planes<NCLS, K, (K >= 6 ? 6 : K)>(m1, m2, mx, r, eq, borrow); break;
+        default: msc_compare_planes<NCLS, K, K>(m1, m2, mx, r, eq, borrow); break;
     }
+#else
+    msc_compare_planes<NCLS, K, 0>(m1, m2, mx, r, eq, borrow);
+#endif
     uint32_t flip = ~up | (borrow & ~eq);
     // Tied bits (2^-K each): the first SPARE of a word, in ascending bit position, compare the
     // words left over from the two calls against the low threshold bits of their class.
