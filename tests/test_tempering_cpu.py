@@ -154,3 +154,36 @@ def test_cadence_matches_reference_loop(native):
                      ("run", 2), ("swap",), ("run", 1), ("sample",), ("run", 1)]
     with pytest.raises(ValueError):
         run_tempering_loop(st, 2, 4, 10, 0, 3)
+
+
+def test_lattice_tempering_surface_without_gpu():
+    """The argument handling of LatticeTempering (tempering.rs:43-117) needs no device: replicas are
+    classical (transverse field 0), share the lattice and one longitudinal field, and nothing is
+    compiled before the first run."""
+    import pyisingmontecarlo_b200 as pkg
+
+    with pytest.raises(ValueError, match="Must supply some edges for graph"):
+        pkg.LatticeTempering([])
+    edges = [((0, 1), -1.0), ((1, 2), 0.5), ((2, 0), 1.25)]
+    lt = pkg.LatticeTempering(edges, seed=3)
+    assert lt.nvars == 3 and lt.get_num_graphs() == 0 and lt.get_total_swaps() == 0
+    lt.add_graph(0.0, 0.25, 0.4)
+    lt.add_graph(0.0, 0.25, 0.8, None, None, None)
+    assert lt.get_num_graphs() == 2
+    with pytest.raises(NotImplementedError, match="transverse"):
+        lt.add_graph(0.5, 0.25, 1.0)
+    with pytest.raises(NotImplementedError, match="share the longitudinal field"):
+        lt.add_graph(0.0, 0.0, 1.0)
+    with pytest.raises(NotImplementedError, match="per-replica edge lists"):
+        lt.add_graph(0.0, 0.25, 1.0, edges)
+    assert lt.get_num_graphs() == 2
+    cp = lt.clone()                       # nothing on the device yet: a host-side copy
+    assert cp.get_num_graphs() == 2 and cp.nvars == 3 and cp is not lt
+    cp.add_graph(0.0, 0.25, 1.2)
+    assert lt.get_num_graphs() == 2 and cp.get_num_graphs() == 3
+    with pytest.raises(ValueError, match="Attempted to get graph 5 of 2"):
+        lt.get_graph_itime(5)
+    with pytest.raises(NotImplementedError):
+        lt.run_quantum_monte_carlo_and_measure_variable_autocorrelation
+    with pytest.raises(AttributeError):
+        lt.no_such_method
