@@ -48,6 +48,42 @@
 #define ORC_EXPORT __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------------------------------
+ * Named choices of the RECALLED crate semantics (A4-A6, A11).  Nothing in
+ * /root/reference can settle them; the defaults are what this restatement believes `qmc` and
+ * `rand` do, and every alternative is one switch away for a maintainer who can read the crates.
+ * None of them changes the stationary distribution (tests/test_oracle_dynamics.py checks each
+ * against exact enumeration); they change which random numbers a run consumes, i.e. whether a
+ * trace of the reference could be reproduced draw by draw.
+ *   ORC_OPT_UNIFORM_ALWAYS  0*: gen::<f64>() is drawn only when dE > 0        1: once per attempt
+ *   ORC_OPT_ZERO_DRAWS      0*: dE == 0 flips without a draw (dE <= 0)        1: dE == 0 draws (and accepts: u < 1)
+ *   ORC_OPT_INIT_DRAWS      1*: GraphState::new draws nvars bools even when set_state follows
+ *                               (lattice.rs:199-203)                          0: no draw when a state is given
+ *   ORC_OPT_BIAS_SIGN       +1*: E = sum J s s' - sum b s                     -1: E = sum J s s' + sum b s
+ *   ORC_OPT_PT_PAIRS        0*: a tempering step tries the even pairs, then the odd pairs
+ *                           1: one parity per step, alternating from even
+ *                           2: one parity per step, chosen by gen::<bool>() of the container rng
+ * (* = default).  Process-wide, not thread-safe: test infrastructure.
+ * ---------------------------------------------------------------------------------------- */
+enum { ORC_OPT_UNIFORM_ALWAYS = 0, ORC_OPT_ZERO_DRAWS = 1, ORC_OPT_INIT_DRAWS = 2, ORC_OPT_BIAS_SIGN = 3,
+       ORC_OPT_PT_PAIRS = 4, ORC_OPT_COUNT = 5 };
+static int g_opt[ORC_OPT_COUNT] = {0, 0, 1, 1, 0};
+
+ORC_EXPORT int orc_set_option(int which, int value) {
+    if (which < 0 || which >= ORC_OPT_COUNT) return -1;
+    if (which == ORC_OPT_BIAS_SIGN && value != 1 && value != -1) return -2;
+    if (which == ORC_OPT_PT_PAIRS && (value < 0 || value > 2)) return -2;
+    g_opt[which] = value;
+    return 0;
+}
+
+ORC_EXPORT int orc_get_option(int which) { return (which < 0 || which >= ORC_OPT_COUNT) ? -1 : g_opt[which]; }
+
+ORC_EXPORT void orc_reset_options(void) {
+    g_opt[ORC_OPT_UNIFORM_ALWAYS] = 0; g_opt[ORC_OPT_ZERO_DRAWS] = 0; g_opt[ORC_OPT_INIT_DRAWS] = 1;
+    g_opt[ORC_OPT_BIAS_SIGN] = 1; g_opt[ORC_OPT_PT_PAIRS] = 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * rand 0.8 SmallRng (xoshiro256++), as used at src/lattice.rs:85-90,198
  * ---------------------------------------------------------------------------------------- */
 static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
@@ -136,7 +172,8 @@ ORC_EXPORT orc_graph *orc_graph_new(uint64_t nvars, uint64_t nedges, const uint6
     g->nbr = (uint64_t *)malloc(sizeof(uint64_t) * 2 * (nedges ? nedges : 1));
     g->jv = (double *)malloc(sizeof(double) * 2 * (nedges ? nedges : 1));
     g->bias = (double *)calloc(nvars ? nvars : 1, sizeof(double));
-    if (biases) memcpy(g->bias, biases, sizeof(double) * nvars);
+    if (biases)
+        for (uint64_t i = 0; i < nvars; ++i) g->bias[i] = g_opt[ORC_OPT_BIAS_SIGN] * biases[i];
     for (uint64_t e = 0; e < nedges; ++e) {
         g->row[ea[e] + 1]++;
         g->row[eb[e] + 1]++;
@@ -200,10 +237,9 @@ static inline void orc_attempt(const orc_graph *g, uint8_t *state, uint64_t rng[
     double de = orc_delta_e(g, state, site);
     double u = 2.0;
     int flip = 1;
-    if (de > 0.0) {
-        double chance = exp(-beta * de);
+    if (de > 0.0 || g_opt[ORC_OPT_UNIFORM_ALWAYS] || (de == 0.0 && g_opt[ORC_OPT_ZERO_DRAWS])) {
         u = orc_gen_f64(rng);
-        flip = u < chance;
+        if (de > 0.0) flip = u < exp(-beta * de);
     }
     if (flip) state[site] = !state[site];
     if (site_out) *site_out = (uint32_t)site;
@@ -214,7 +250,8 @@ static inline void orc_attempt(const orc_graph *g, uint8_t *state, uint64_t rng[
  * afterwards (src/lattice.rs:199-203), so the rng is advanced either way. */
 static void orc_init_state(const orc_graph *g, uint64_t rng[4], const uint8_t *initial_state,
                            uint8_t *state) {
-    for (uint64_t i = 0; i < g->nvars; ++i) state[i] = (uint8_t)orc_gen_bool(rng);
+    if (!initial_state || g_opt[ORC_OPT_INIT_DRAWS])
+        for (uint64_t i = 0; i < g->nvars; ++i) state[i] = (uint8_t)orc_gen_bool(rng);
     if (initial_state) memcpy(state, initial_state, g->nvars);
 }
 
@@ -508,7 +545,7 @@ ORC_EXPORT int orc_pt_run(const orc_graph *g, uint64_t R, const double *betas,
         energies[r] = 0.0;
     }
     uint64_t remaining = timesteps, to_swap = replica_swap_freq, to_sample = sampling_freq;
-    uint64_t sample_idx = 0, swaps = 0;
+    uint64_t sample_idx = 0, swaps = 0, pt_step = 0;
     while (remaining > 0) {
         uint64_t t = to_sample < to_swap ? to_sample : to_swap;
         if (remaining < t) t = remaining;
@@ -521,7 +558,12 @@ ORC_EXPORT int orc_pt_run(const orc_graph *g, uint64_t R, const double *betas,
         }
         to_sample -= t; to_swap -= t; remaining -= t;
         if (to_swap == 0) {
-            for (int parity = 0; parity < 2; ++parity)
+            /* ORC_OPT_PT_PAIRS: both parities (default) / one, alternating / one, drawn */
+            int p_lo = 0, p_hi = 2;
+            if (g_opt[ORC_OPT_PT_PAIRS] == 1) { p_lo = (int)(pt_step & 1u); p_hi = p_lo + 1; }
+            if (g_opt[ORC_OPT_PT_PAIRS] == 2) { p_lo = orc_gen_bool(crng); p_hi = p_lo + 1; }
+            ++pt_step;
+            for (int parity = p_lo; parity < p_hi; ++parity)
                 for (uint64_t a = parity; a + 1 < R; a += 2) {
                     double d = (betas[a] - betas[a + 1]) * (ecur[a] - ecur[a + 1]);
                     int acc = 1;

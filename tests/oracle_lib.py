@@ -278,6 +278,39 @@ def msc_mirror_moves(a, b, j, nvars, colors, edge_cls, E, seed, betas, *, spin_s
     return en, st.astype(bool)
 
 
+OPTIONS = {"uniform_always": 0, "zero_draws": 1, "init_draws": 2, "bias_sign": 3, "pt_pairs": 4}
+
+
+class options:
+    """with oracle_lib.options(uniform_always=1): ...  -- the named alternatives of the recalled
+    crate semantics (oracle/ising_oracle.c: ORC_OPT_*); the defaults come back on exit."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        h = lib()
+        h.orc_set_option.restype = C.c_int
+        h.orc_set_option.argtypes = [C.c_int, C.c_int]
+        for k, v in self.kw.items():
+            rc = h.orc_set_option(OPTIONS[k], int(v))
+            if rc:
+                h.orc_reset_options()
+                raise ValueError(f"oracle option {k} = {v} rejected")
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_reset_options()
+        return False
+
+
+def get_option(name):
+    h = lib()
+    h.orc_get_option.restype = C.c_int
+    h.orc_get_option.argtypes = [C.c_int]
+    return int(h.orc_get_option(OPTIONS[name]))
+
+
 def philox4x32(ctr, key, rounds=10):
     c = np.ascontiguousarray(ctr, dtype=np.uint32)
     k = np.ascontiguousarray(key, dtype=np.uint32)

@@ -155,3 +155,58 @@ def test_pt_cadence_and_swaps(oracle):
     # with the swap period longer than the run nothing is ever swapped
     _, _, no_swaps = g.pt_run(betas, 99, timesteps=40, replica_swap_freq=1000, sampling_freq=10)
     assert no_swaps == 0
+
+
+@pytest.mark.parametrize("opts", [
+    dict(uniform_always=1), dict(zero_draws=1), dict(init_draws=0), dict(uniform_always=1, zero_draws=1),
+])
+def test_named_alternatives_of_the_recalled_semantics(oracle, opts):
+    """Every choice the restatement had to make about the absent crates (when a uniform is drawn,
+    whether GraphState::new draws under a given state) is a named option of the oracle.  An
+    alternative consumes different random numbers - a run diverges from the default one - and
+    samples the same Boltzmann law."""
+    edges = [((0, 1), -1.0), ((0, 2), 0.5), ((0, 3), 1.5), ((1, 2), -0.7), ((1, 3), 0.3), ((2, 3), 1.0),
+             ((3, 4), 1.0), ((4, 0), -1.0)]                  # the last two make dE == 0 possible
+    n, bias, beta = 5, None, 0.5
+    g = oracle.Graph(edges, biases=bias)
+    seeds = oracle.make_seeds(7, 256)
+    init = [True, False, True, True, False]
+    _, st_default = g.run_monte_carlo(beta, 30, seeds, initial_state=init)
+    with oracle.options(**opts):
+        assert all(oracle.get_option(k) == v for k, v in opts.items())
+        _, st_alt = g.run_monte_carlo(beta, 30, seeds, initial_state=init)
+        en, _ = g.run_sampling(beta, 400, seeds, thermalization=50, sampling_freq=2, attempts_per_step=n)
+    assert oracle.get_option("uniform_always") == 0 and oracle.get_option("init_draws") == 1   # defaults are back
+    assert (st_alt != st_default).any()
+    per_exp = en.mean(axis=1)
+    mean, err = per_exp.mean(), per_exp.std(ddof=1) / np.sqrt(len(per_exp))
+    exact, _, _ = exact_moments(edges, n, beta, bias)
+    assert abs(mean - exact) < 4 * err + 1e-12, (opts, mean, exact, err)
+
+
+def test_bias_sign_and_tempering_pair_options(oracle):
+    edges = [((0, 1), -1.0), ((1, 2), 0.5), ((2, 0), 1.5)]
+    bias = [0.3, -0.2, 0.6]
+    st = np.array([1, 0, 1], dtype=np.uint8)
+    plus = oracle.Graph(edges, biases=bias).energy(st)
+    with oracle.options(bias_sign=-1):
+        minus = oracle.Graph(edges, biases=bias).energy(st)
+        flipped = oracle.Graph(edges, biases=[-b for b in bias]).energy(st)
+    assert abs(flipped - plus) < 1e-12                   # sign -1 of the negated biases = the default
+    assert abs(minus - oracle.Graph(edges, biases=[-b for b in bias]).energy(st)) < 1e-12
+    assert abs(plus - minus) > 0.1
+    with pytest.raises(ValueError):
+        with oracle.options(bias_sign=0):
+            pass
+    # tempering: one parity per step attempts about half as many swaps as both parities
+    g = oracle.Graph(oracle.square_edges(6))
+    betas = np.linspace(0.2, 0.6, 6)
+    _, en0, both = g.pt_run(betas, 99, timesteps=400, replica_swap_freq=2, sampling_freq=100)
+    results = {}
+    for rule in (1, 2):
+        with oracle.options(pt_pairs=rule):
+            _, en, swaps = g.pt_run(betas, 99, timesteps=400, replica_swap_freq=2, sampling_freq=100)
+        results[rule] = swaps
+        assert 0.3 * both < swaps < 0.75 * both, (rule, swaps, both)
+        assert en[0] > en[-1]
+    assert results[1] != results[2]
