@@ -1,0 +1,84 @@
+// TEST INFRASTRUCTURE (CPU suite only): just enough of the CUDA execution model to run the
+// library's own row-walk kernel source (pyisingmontecarlo_b200/csrc/sweep_rows.cuh) on the host,
+// one OS thread per CUDA thread, so that the kernel source itself - row geometry, shared Philox
+// rounds, bit-sliced compare, tie words, vertical counters and their block reduction - is compared
+// bit for bit with oracle/msc_mirror.c without a GPU.  Nothing of the product links or loads this.
+//
+// What stands in for what:
+//   threadIdx / blockIdx / blockDim / gridDim   thread_local variables set by emu_launch()
+//   __syncthreads()                             a pthread barrier over the block's threads
+//   __shared__ (static)                         a function-local static: blocks run one at a time
+//   extern __shared__ (dynamic)                 emu::dyn_smem, allocated per launch
+//   atomicAdd, __ldg, __umulhi, __ffs, __popc   their plain C++ meaning (atomicAdd under a mutex)
+// The prepared copy of the header (tests/test_device_source_on_host.py: prepare_sources) has the
+// griddepcontrol / mbarrier PTX and the TMA-staged variant cut out; every cut is asserted there.
+#pragma once
+#include <cuda_runtime.h>   // vector types (uint2, uint4, dim3) and the host API's typedefs only
+#include <pthread.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __launch_bounds__(...)
+#define __grid_constant__
+// (host_defines.h leaves this one to nvcc; defined after the standard headers, which spell the
+// attribute with the same token)
+#define __noinline__ __attribute__((noinline))
+#define EMU_SHARED static
+
+namespace emu {
+inline thread_local uint3 t_threadIdx, t_blockIdx;
+inline thread_local dim3 t_blockDim, t_gridDim;
+inline thread_local pthread_barrier_t* t_barrier = nullptr;
+inline uint32_t* dyn_smem = nullptr;
+inline std::mutex atomic_mu;
+}  // namespace emu
+
+#define threadIdx emu::t_threadIdx
+#define blockIdx emu::t_blockIdx
+#define blockDim emu::t_blockDim
+#define gridDim emu::t_gridDim
+
+static inline void __syncthreads() { pthread_barrier_wait(emu::t_barrier); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+    std::lock_guard<std::mutex> g(emu::atomic_mu);
+    const unsigned long long old = *p;
+    *p = old + v;
+    return old;
+}
+
+namespace emu {
+// <<<grid, block, smem_bytes>>> of a kernel taking one by-value argument: blocks one after the
+// other, the threads of a block concurrently
+template <typename Args>
+void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, const Args& args) {
+    const unsigned nthreads = block.x * block.y * block.z;
+    std::vector<uint32_t> smem(smem_bytes / 4 + 1);
+    dyn_smem = smem.data();
+    for (unsigned b = 0; b < grid.x; ++b) {
+        pthread_barrier_t bar;
+        pthread_barrier_init(&bar, nullptr, nthreads);
+        std::vector<std::thread> th;
+        th.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([=, &bar, &args] {
+                t_threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+                t_blockIdx = uint3{b, 0, 0};
+                t_blockDim = block;
+                t_gridDim = grid;
+                t_barrier = &bar;
+                kern(args);
+            });
+        for (auto& x : th) x.join();
+        pthread_barrier_destroy(&bar);
+    }
+    dyn_smem = nullptr;
+}
+}  // namespace emu
