@@ -19,6 +19,7 @@
 
 #include <mutex>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #define __launch_bounds__(...)
@@ -80,5 +81,17 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
         pthread_barrier_destroy(&bar);
     }
     dyn_smem = nullptr;
+}
+}  // namespace emu
+
+namespace emu {
+// the same for kernels that take several parameters
+template <typename... KArgs, typename... Args>
+void launch_v(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+    struct Pack { void (*k)(KArgs...); std::tuple<KArgs...> a; };
+    Pack p{kern, std::tuple<KArgs...>(KArgs(args)...)};
+    const Pack* pp = &p;
+    void (*tramp)(const Pack*) = [](const Pack* q) { std::apply(q->k, q->a); };
+    launch<const Pack*>(tramp, grid, block, smem_bytes, pp);
 }
 }  // namespace emu

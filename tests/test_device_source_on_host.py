@@ -1,4 +1,4 @@
-"""The row-walk sweep kernel's own source, run on the host, against the mirror (CPU suite).
+"""The sweep kernels' own source, run on the host, against the mirror (CPU suite).
 
 `csrc/sweep_rows.cuh` is the kernel behind BASELINE configs 2 and 3.  Its GPU parity tests need
 a B200; this one needs none: tests/host_emulation/ runs the kernel source itself one OS thread
@@ -9,7 +9,10 @@ tiles, wrap-around rows, parities), the Philox rounds shared between the words o
 multiply-add forms of the class select and of the tie compare, the vertical counters of the
 accumulating phase with their block reduction, in every instantiation the launcher can choose
 (2D / 3D, uniform / +-J, 1 / 2 / 4 words per thread, one row or several per unit, the
-256-thread and the 128-thread shape).  The library itself is not involved and stays CUDA-only.
+256-thread and the 128-thread shape).  `k_sweep_general` of csrc/sweep_general.cu - config 4 and
+every graph that is not a torus - gets the same treatment: uniform and per-replica inverse
+temperatures (tempering), the degree-specialised and the run-time-degree kernels, 5 / 6 / 7
+planes, 7 / 10 Philox rounds.  The library itself is not involved and stays CUDA-only.
 """
 import ctypes as C
 import os
@@ -75,6 +78,16 @@ def prepare_sources(dst):
     rows = rows.replace("__shared__", "EMU_SHARED")
     open(os.path.join(dst, "sweep_rows.cuh"), "w").write(rows)
 
+    gen = open(os.path.join(CSRC, "sweep_general.cu")).read()
+    gen = _cut(gen, "template <int K, int ROUNDS, int DEG, int V>\nstatic void gen_launch(", None,
+               "launchers and other kernels of sweep_general.cu") + "\n}  // namespace ising\n"
+    # dependent-launch control and the L2 prefetches of the graph arrays in front of the wait
+    gen = _cut(gen, '    asm volatile("griddepcontrol.launch_dependents;");\n', "    // block = (wx lanes over replica word groups",
+               "PTX preamble of k_sweep_general")
+    assert "asm" not in re.sub(r"//.*", "", gen) and "__shared__" not in gen and "__syncthreads" not in gen
+    assert gen.count("__global__") == 1
+    open(os.path.join(dst, "sweep_general_kernel.cuh"), "w").write(gen)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -88,7 +101,8 @@ def emu(tmp_path_factory):
     prepare_sources(os.path.join(build, "prepared"))
     so = os.path.join(build, "libemu_rows.so")
     cmd = ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
-           "-I", "/usr/local/cuda/include", os.path.join(EMU, "emu_rows.cpp"), "-o", so]
+           "-I", "/usr/local/cuda/include", os.path.join(EMU, "emu_rows.cpp"), os.path.join(EMU, "emu_general.cpp"),
+           "-o", so]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(so)
@@ -96,6 +110,10 @@ def emu(tmp_path_factory):
     lib.emu_rows_phase.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
                                    C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
                                    C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.emu_general_group.restype = C.c_int
+    lib.emu_general_group.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double,
+                                      C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
     return lib
 
 
@@ -233,3 +251,149 @@ def test_row_walk_source_equals_the_mirror(emu, oracle, dims, E, V, pmj, small, 
     assert rc == 0, rc
     assert (nsat[:E] == satisfied_bonds(got, a, b, j)).all()
     assert (unpack(words, dims, E) == got).all()                  # count only: no update
+
+
+# ---- general graphs (config 4's kernel) -----------------------------------------------------------------
+def random_regular(n, d, rng):
+    """pairing model, self-loops and double edges rejected"""
+    while True:
+        stubs = rng.permutation(np.repeat(np.arange(n), d))
+        a, b = stubs[0::2], stubs[1::2]
+        if (a != b).all() and len({(min(x, y), max(x, y)) for x, y in zip(a, b)}) == len(a):
+            return a.astype(np.uint64), b.astype(np.uint64)
+
+
+def random_sparse(n, m, rng, max_deg):
+    edges, deg = set(), np.zeros(n, dtype=int)
+    while len(edges) < m:
+        x, y = (int(v) for v in rng.integers(0, n, size=2))
+        if x != y and (min(x, y), max(x, y)) not in edges and deg[x] < max_deg and deg[y] < max_deg:
+            edges.add((min(x, y), max(x, y)))
+            deg[x] += 1
+            deg[y] += 1
+    e = np.array(sorted(edges), dtype=np.uint64)
+    return e[:, 0].copy(), e[:, 1].copy()
+
+
+def greedy_colouring(n, a, b):
+    adj = [[] for _ in range(n)]
+    for x, y in zip(a.astype(int), b.astype(int)):
+        adj[x].append(y)
+        adj[y].append(x)
+    col = np.full(n, -1)
+    for v in range(n):
+        used = {col[u] for u in adj[v]}
+        col[v] = next(c for c in range(n) if c not in used)
+    return col.astype(np.uint32), adj
+
+
+def colour_degree_groups(n, a, b, j, col, adj):
+    """(colour, degree) groups in the ELL form of kernels.h (GenGroup), colours ascending"""
+    sign = {}
+    for x, y, w in zip(a.astype(int), b.astype(int), j):
+        sign[(x, y)] = sign[(y, x)] = w > 0
+    groups = []
+    for c in range(int(col.max()) + 1):
+        for d in sorted({len(adj[v]) for v in range(n) if col[v] == c}):
+            sites = np.array([v for v in range(n) if col[v] == c and len(adj[v]) == d], dtype=np.uint32)
+            nbr = np.zeros((max(d, 1), len(sites)), dtype=np.uint32)
+            anti = np.zeros(len(sites), dtype=np.uint32)
+            for i, v in enumerate(sites):
+                for k, u in enumerate(adj[v]):
+                    nbr[k, i] = u
+                    anti[i] |= np.uint32(int(sign[(int(v), u)]) << k)
+            groups.append((d, sites, nbr, anti))
+    return groups
+
+
+def per_replica_tables(betas, W, K, jabs):
+    """GenTables (kernels.h) from per-replica betas: what k_build_tables makes of the host's T64 rows"""
+    import math
+
+    plane = np.zeros((16, W, 8, 8), dtype=np.uint32)
+    low = np.zeros((16, 32 * W, 8), dtype=np.uint32)
+    for deg in range(16):
+        cmin, ncls = deg // 2 + 1, deg - deg // 2
+        for cls in range(min(ncls, 8)):
+            de = 2.0 * jabs * (2 * (cmin + cls) - deg)
+            for e, beta in enumerate(betas):
+                scaled = math.ldexp(math.exp(-beta * de), K + 32)
+                T = min(int(math.floor(scaled)), (1 << (K + 32)) - 1)
+                low[deg, e, cls] = T & 0xFFFFFFFF
+                for p in range(K):
+                    plane[deg, e // 32, cls, p] |= np.uint32(((T >> (K + 31 - p)) & 1) << (e % 32))
+    return plane, low
+
+
+def pack_natural(states, W):
+    E, N = states.shape
+    bits = np.zeros((N, W * 32), dtype=np.uint8)
+    bits[:, :E] = states.T
+    return (bits.reshape(N, W, 32).astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(axis=2, dtype=np.uint32)
+
+
+def unpack_natural(words, E):
+    bits = (words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1
+    return bits.reshape(words.shape[0], -1)[:, :E].T.astype(bool)
+
+
+GENERAL_CASES = [
+    # graph, E, planes, rounds, per-replica betas, degree-specialised kernels, blocks
+    ("3-regular", 64, 6, 7, True, True, 3),      # config 4: one beta per replica bit, V = 2, DEG = 3
+    ("3-regular", 96, 6, 7, False, True, 64),    # uniform beta, V = 1
+    ("3-regular", 64, 6, 7, False, False, 2),    # the run-time-degree kernel on the same graph
+    ("mixed", 64, 6, 7, True, True, 5),          # degrees 1 .. 9: up to 5 uphill classes, +-J
+    ("mixed", 32, 7, 10, False, False, 4),       # 7 planes, Philox4x32-10
+    ("mixed", 64, 5, 7, False, False, 4),        # 5 planes (3 spare words for ties)
+    ("cubic", 64, 6, 7, False, True, 7),         # a 4 x 4 x 4 torus as a general graph: DEG = 6
+    ("square", 128, 6, 10, False, False, 3),     # DEG = 4 sites through the run-time-degree kernel, 10 rounds
+]
+
+
+@pytest.mark.parametrize("graph,E,K,rounds,perbeta,specialise,blocks", GENERAL_CASES)
+def test_general_graph_source_equals_the_mirror(emu, oracle, graph, E, K, rounds, perbeta, specialise, blocks):
+    rng = np.random.default_rng(len(graph) * 1000 + E + K)
+    if graph == "3-regular":
+        n = 200
+        a, b = random_regular(n, 3, rng)
+        j = np.full(len(a), -1.0)
+    elif graph == "mixed":
+        n = 120
+        a, b = random_sparse(n, 300, rng, 9)
+        j = rng.choice([-0.5, 0.5], size=len(a))
+    elif graph == "cubic":
+        a, b, j = torus((4, 4, 4), rng, True, -1.0)
+        n = 64
+    else:
+        a, b, j = torus((6, 4, 1), rng, False, 2.0)
+        n = 24
+    jabs = float(abs(j[0]))
+    col, adj = greedy_colouring(n, a, b)
+    groups = colour_degree_groups(n, a, b, j, col, adj)
+    W = (E + 31) // 32
+    V = 2 if W % 2 == 0 else 1
+    init = rng.integers(0, 2, size=(E, n)).astype(bool)
+    words = pack_natural(init, W)
+    seed, sweep0, gw0, nsweeps = 0xC0FFEE1234, 11, 2, 3
+    if perbeta:
+        betas_e = np.geomspace(0.1, 1.5, E)
+        plane, low = per_replica_tables(betas_e, W, K, jabs)
+        tp, tl = plane.ctypes.data, low.ctypes.data
+        sweep_betas = [0.0] * nsweeps
+    else:
+        tp = tl = None
+        sweep_betas = [0.2, 0.6, 1.1]
+    for s, beta in enumerate(sweep_betas):
+        for d, sites, nbr, anti in groups:
+            rc = emu.emu_general_group(words.ctypes.data, W, V, sites.ctypes.data, nbr.ctypes.data, anti.ctypes.data,
+                                       len(sites), d, sweep0 + s, seed, gw0, K, rounds, float(beta), jabs, tp, tl,
+                                       int(specialise), blocks)
+            assert rc == 0, rc
+    got = unpack_natural(words, E)
+    kw = dict(replica_offset=32 * gw0, planes=K, rounds=rounds, states=init, sweep0=sweep0)
+    if perbeta:
+        _, st_ref = oracle.msc_mirror(a, b, j, n, col, E, seed, None, per_replica_beta=betas_e, nsweeps=nsweeps, **kw)
+    else:
+        _, st_ref = oracle.msc_mirror(a, b, j, n, col, E, seed, sweep_betas, **kw)
+    assert (got == st_ref).all(), "kernel source on the host differs from the mirror"
+    assert (got != init).mean() > 0.05
