@@ -46,6 +46,13 @@ static inline void __syncthreads() { pthread_barrier_wait(emu::t_barrier); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+// (lo, hi) as one 64-bit value shifted by n & 31: the low word (_r) / the high word (_l) of the result
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t n) {
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (n & 31));
+}
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t n) {
+    return (uint32_t)(((((uint64_t)hi << 32) | lo) << (n & 31)) >> 32);
+}
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
@@ -63,7 +70,7 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
     const unsigned nthreads = block.x * block.y * block.z;
     std::vector<uint32_t> smem(smem_bytes / 4 + 1);
     dyn_smem = smem.data();
-    for (unsigned b = 0; b < grid.x; ++b) {
+    for (unsigned b = 0; b < grid.x * grid.y; ++b) {
         pthread_barrier_t bar;
         pthread_barrier_init(&bar, nullptr, nthreads);
         std::vector<std::thread> th;
@@ -71,7 +78,7 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
         for (unsigned t = 0; t < nthreads; ++t)
             th.emplace_back([=, &bar, &args] {
                 t_threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-                t_blockIdx = uint3{b, 0, 0};
+                t_blockIdx = uint3{b % grid.x, b / grid.x, 0};
                 t_blockDim = block;
                 t_gridDim = grid;
                 t_barrier = &bar;

@@ -12,7 +12,9 @@ accumulating phase with their block reduction, in every instantiation the launch
 256-thread and the 128-thread shape).  `k_sweep_general` of csrc/sweep_general.cu - config 4 and
 every graph that is not a torus - gets the same treatment: uniform and per-replica inverse
 temperatures (tempering), the degree-specialised and the run-time-degree kernels, 5 / 6 / 7
-planes, 7 / 10 Philox rounds.  The library itself is not involved and stays CUDA-only.
+planes, 7 / 10 Philox rounds; and `k_strip_phase` of csrc/strip.cu - config 5, one lattice
+bit-packed along x - as one strip and as two strips that exchange their ghost rows.  The library
+itself is not involved and stays CUDA-only.
 """
 import ctypes as C
 import os
@@ -88,6 +90,16 @@ def prepare_sources(dst):
     assert gen.count("__global__") == 1
     open(os.path.join(dst, "sweep_general_kernel.cuh"), "w").write(gen)
 
+    strip = open(os.path.join(CSRC, "strip.cu")).read()
+    strip = _cut(strip, "template <int V>\nstatic int strip_phase_dispatch(", None,
+                 "launchers and other kernels of strip.cu") + "\n}  // namespace ising\n"
+    for ptx in ('    asm volatile("griddepcontrol.launch_dependents;");\n',
+                '    asm volatile("griddepcontrol.wait;" ::: "memory");\n'):
+        assert strip.count(ptx) == 1, ptx
+        strip = strip.replace(ptx, "")
+    assert "asm" not in re.sub(r"//.*", "", strip) and "__shared__" not in strip and strip.count("__global__") == 1
+    open(os.path.join(dst, "strip_phase_kernel.cuh"), "w").write(strip)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -102,7 +114,7 @@ def emu(tmp_path_factory):
     so = os.path.join(build, "libemu_rows.so")
     cmd = ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
            "-I", "/usr/local/cuda/include", os.path.join(EMU, "emu_rows.cpp"), os.path.join(EMU, "emu_general.cpp"),
-           "-o", so]
+           os.path.join(EMU, "emu_strip.cpp"), "-o", so]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(so)
@@ -114,6 +126,9 @@ def emu(tmp_path_factory):
     lib.emu_general_group.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                       C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double,
                                       C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
+    lib.emu_strip_phase.restype = C.c_int
+    lib.emu_strip_phase.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
+                                                                      C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     return lib
 
 
@@ -396,4 +411,63 @@ def test_general_graph_source_equals_the_mirror(emu, oracle, graph, E, K, rounds
     else:
         _, st_ref = oracle.msc_mirror(a, b, j, n, col, E, seed, sweep_betas, **kw)
     assert (got == st_ref).all(), "kernel source on the host differs from the mirror"
+    assert (got != init).mean() > 0.05
+
+
+# ---- one lattice bit-packed along x in row strips (config 5's kernel) ---------------------------------------
+def strip_pack(state, Wr):
+    """bool[rows, Lx] (global rows y0 ..) -> words[2][rows][Wr]: bit b of word j of colour c of global
+    row y is site x = 2 (32 j + b) + ((y + c) & 1)  (kernels.h, StripGeom).  Needs y0 even."""
+    rows, Lx = state.shape
+    out = np.zeros((2, rows, Wr), dtype=np.uint32)
+    for c in range(2):
+        for r in range(rows):
+            xs = 2 * np.arange(Lx // 2) + ((r + c) & 1)
+            out[c, r] = (state[r, xs].reshape(Wr, 32).astype(np.uint32) << np.arange(32, dtype=np.uint32)).sum(
+                axis=1, dtype=np.uint32)
+    return out
+
+
+def strip_unpack(words, Lx):
+    _, rows, Wr = words.shape
+    st = np.zeros((rows, Lx), dtype=bool)
+    for c in range(2):
+        for r in range(rows):
+            xs = 2 * np.arange(Lx // 2) + ((r + c) & 1)
+            st[r, xs] = ((words[c, r][:, None] >> np.arange(32, dtype=np.uint32)) & 1).ravel().astype(bool)
+    return st
+
+
+@pytest.mark.parametrize("Lx,Ly,nstrips,K,rounds,j", [(256, 12, 1, 6, 7, -1.0), (128, 16, 2, 6, 7, 1.0),
+                                                      (192, 8, 2, 7, 10, -1.0), (64 * 40, 6, 1, 5, 7, -1.0)])
+def test_strip_source_equals_the_mirror(emu, oracle, Lx, Ly, nstrips, K, rounds, j):
+    rng = np.random.default_rng(Lx + Ly)
+    Wr = Lx // 64
+    init = rng.integers(0, 2, size=(Ly, Lx)).astype(bool)
+    betas = [0.3, 0.44, 0.7]
+    seed = 0xABCDEF0123456789
+    full = strip_pack(init, Wr)                                   # [2][Ly][Wr]
+    rows = Ly // nstrips                                          # even, so local parities are the global ones
+    assert rows % 2 == 0
+    strips = []
+    for k in range(nstrips):
+        buf = np.zeros((2, rows + 2, Wr), dtype=np.uint32)        # ghost = 1
+        buf[:, 1:-1] = full[:, k * rows:(k + 1) * rows]
+        strips.append(buf)
+
+    def exchange(c):                                              # ghost rows of colour c from the neighbours
+        for k, buf in enumerate(strips):
+            buf[c, 0] = strips[(k - 1) % nstrips][c, rows]
+            buf[c, rows + 1] = strips[(k + 1) % nstrips][c, 1]
+
+    for t, beta in enumerate(betas):
+        for c in (0, 1):
+            exchange(1 - c)
+            for k, buf in enumerate(strips):
+                rc = emu.emu_strip_phase(buf.ctypes.data, Wr, rows, k * rows, Ly, 1, c, t, seed,
+                                         0xFFFFFFFF if j > 0 else 0, float(beta), abs(j), K, rounds, 1, rows, 2 + k)
+                assert rc == 0, rc
+    got = strip_unpack(np.concatenate([b[:, 1:-1] for b in strips], axis=1), Lx)
+    _, ref = oracle.msc_mirror_single(Lx, Ly, j, seed, betas, planes=K, rounds=rounds, state=init)
+    assert (got == ref).all(), "kernel source on the host differs from the mirror"
     assert (got != init).mean() > 0.05
