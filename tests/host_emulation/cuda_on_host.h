@@ -55,6 +55,16 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t n) {
 }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
+// round-to-nearest add / multiply that the compiler must not contract into a fused multiply-add:
+// plain operations here (the emulation is built with -ffp-contract=off)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) {
+    std::lock_guard<std::mutex> g(emu::atomic_mu);
+    const unsigned int old = *p;
+    *p = old + v;
+    return old;
+}
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
     std::lock_guard<std::mutex> g(emu::atomic_mu);
     const unsigned long long old = *p;

@@ -13,8 +13,10 @@ accumulating phase with their block reduction, in every instantiation the launch
 every graph that is not a torus - gets the same treatment: uniform and per-replica inverse
 temperatures (tempering), the degree-specialised and the run-time-degree kernels, 5 / 6 / 7
 planes, 7 / 10 Philox rounds; and `k_strip_phase` of csrc/strip.cu - config 5, one lattice
-bit-packed along x - as one strip and as two strips that exchange their ghost rows.  The library
-itself is not involved and stays CUDA-only.
+bit-packed along x - as one strip and as two strips that exchange their ghost rows; and the
+kernels of csrc/state_io.cu: the Philox initial state, bool <-> packed in both spin layouts, and
+`k_replay`, the replay of the reference algorithm's own (site, uniform) trace, against
+oracle/ising_oracle.c.  The library itself is not involved and stays CUDA-only.
 """
 import ctypes as C
 import os
@@ -100,6 +102,13 @@ def prepare_sources(dst):
     assert "asm" not in re.sub(r"//.*", "", strip) and "__shared__" not in strip and strip.count("__global__") == 1
     open(os.path.join(dst, "strip_phase_kernel.cuh"), "w").write(strip)
 
+    io = open(os.path.join(CSRC, "state_io.cu")).read()
+    # the host-side wrappers (<<< >>> launches, the SM-count query) go; the kernels stay as they are
+    io, nwrap = re.subn(r"\n(?:int launch_\w+|unsigned device_sms)\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", io)
+    assert nwrap == 8 and "<<<" not in io and "cudaGetDevice" not in io, nwrap
+    assert io.count("__global__") == 7
+    open(os.path.join(dst, "state_io_kernels.cuh"), "w").write(io)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -112,9 +121,9 @@ def emu(tmp_path_factory):
     build = str(tmp_path_factory.mktemp("host_emulation"))
     prepare_sources(os.path.join(build, "prepared"))
     so = os.path.join(build, "libemu_rows.so")
-    cmd = ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
            "-I", "/usr/local/cuda/include", os.path.join(EMU, "emu_rows.cpp"), os.path.join(EMU, "emu_general.cpp"),
-           os.path.join(EMU, "emu_strip.cpp"), "-o", so]
+           os.path.join(EMU, "emu_strip.cpp"), os.path.join(EMU, "emu_state.cpp"), "-o", so]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(so)
@@ -129,6 +138,13 @@ def emu(tmp_path_factory):
     lib.emu_strip_phase.restype = C.c_int
     lib.emu_strip_phase.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
                                                                       C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.emu_replay.restype = C.c_uint
+    lib.emu_replay.argtypes = [C.c_uint64] * 3 + [C.c_void_p] * 8 + [C.c_double]
+    lay = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]
+    lib.emu_init_random.argtypes = [C.c_void_p] + lay + [C.c_uint64, C.c_uint32, C.c_uint]
+    lib.emu_pack_states.argtypes = [C.c_void_p] + lay + [C.c_void_p, C.c_uint64, C.c_uint]
+    lib.emu_unpack_states.argtypes = [C.c_void_p] + lay + [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint]
+    lib.emu_init_broadcast.argtypes = [C.c_void_p] + lay + [C.c_void_p, C.c_uint]
     return lib
 
 
@@ -471,3 +487,94 @@ def test_strip_source_equals_the_mirror(emu, oracle, Lx, Ly, nstrips, K, rounds,
     _, ref = oracle.msc_mirror_single(Lx, Ly, j, seed, betas, planes=K, rounds=rounds, state=init)
     assert (got == ref).all(), "kernel source on the host differs from the mirror"
     assert (got != init).mean() > 0.05
+
+
+# ---- state initialisation / conversion and the replay kernel (csrc/state_io.cu) -----------------------------
+@pytest.mark.parametrize("dims,E", [((8, 6, 4), 100), ((10, 4, 1), 33), (None, 70)])
+def test_state_kernels_on_the_host(emu, oracle, dims, E):
+    """k_init_random == the mirror's initial state; k_pack_states / k_unpack_states / k_init_broadcast
+    against numpy, in the stencil layouts and in the natural-order layout of general graphs"""
+    rng = np.random.default_rng(E)
+    if dims is None:
+        kind, n, lay3 = emu.emu_kind(0), 203, (0, 0, 0)           # general graph: natural order, odd nvars
+        a = np.arange(n - 1, dtype=np.uint64)
+        b = a + 1
+        colors = (np.arange(n) & 1).astype(np.uint32)
+    else:
+        kind = emu.emu_kind(3 if dims[2] > 1 else 2)
+        n, lay3 = dims[0] * dims[1] * dims[2], dims
+        a, b, _ = torus(dims, rng, False, -1.0)
+        _, colors = layout_index(dims)
+    W = (E + 31) // 32
+    seed, gw0 = 0x0123456789ABCDEF, 4
+    lay = (kind, lay3[0], lay3[1], lay3[2], n, W)
+
+    def unpack_k(words, stride=None):
+        stride = n if stride is None else stride
+        out = np.full((E, stride), 7, dtype=np.uint8)
+        emu.emu_unpack_states(words.ctypes.data, *lay, out.ctypes.data, E, stride, 3)
+        assert (out[:, n:] == 7).all()                            # nothing written beyond a row
+        return out[:, :n].astype(bool)
+
+    words = np.zeros(n * W, dtype=np.uint32)
+    emu.emu_init_random(words.ctypes.data, *lay, seed, gw0, 2)
+    _, st_ref = oracle.msc_mirror(a, b, np.full(len(a), -1.0), n, colors, E, seed, [], replica_offset=32 * gw0)
+    assert (unpack_k(words) == st_ref).all()
+    assert (unpack_k(words, stride=n + 5) == st_ref).all()        # the scalar store path (unaligned rows)
+
+    states = rng.integers(0, 2, size=(E, n)).astype(np.uint8)
+    words2 = np.zeros(n * W, dtype=np.uint32)
+    emu.emu_pack_states(words2.ctypes.data, *lay, states.ctypes.data, E, 5)
+    assert (unpack_k(words2) == states.astype(bool)).all()
+    if dims is not None:
+        assert (words2.reshape(n, W) == pack(states.astype(bool), dims, W)).all()      # Layout as documented
+    else:
+        assert (words2.reshape(n, W) == pack_natural(states.astype(bool), W)).all()
+    one = rng.integers(0, 2, size=n).astype(np.uint8)
+    emu.emu_init_broadcast(words2.ctypes.data, *lay, one.ctypes.data, 1)
+    assert (unpack_k(words2) == one.astype(bool)[None, :]).all()
+
+
+def csr_sorted(n, a, b, j):
+    """adjacency both ways, neighbours ascending, ties in edge-list order (graph.h: HostGraph)"""
+    src = np.concatenate([a, b]).astype(np.int64)
+    dst = np.concatenate([b, a]).astype(np.int64)
+    w = np.concatenate([j, j])
+    order = np.lexsort((np.concatenate([np.arange(len(a))] * 2), dst, src))
+    row = np.zeros(n + 1, dtype=np.uint64)
+    np.add.at(row, src + 1, 1)
+    return np.cumsum(row).astype(np.uint64), dst[order].astype(np.uint32), w[order].copy()
+
+
+@pytest.mark.parametrize("case", ["config1", "real"])
+def test_replay_kernel_source_equals_the_reference_restatement(emu, oracle, case):
+    """K1 on the host: the oracle (the reference algorithm restated, oracle/ising_oracle.c) emits its
+    own (site, uniform) trace; the kernel source must land on the same states and energies."""
+    rng = np.random.default_rng(3)
+    if case == "config1":                                         # BASELINE config 1, shortened
+        edges = oracle.square_edges(32)
+        og = oracle.Graph(edges)
+        beta, E, A = 0.44, 16, 30 * 1024
+        bias = np.zeros(og.nvars)
+    else:                                                         # real couplings and biases
+        n = 40
+        a0, b0 = random_sparse(n, 90, rng, 8)
+        edges = [((int(x), int(y)), float(w)) for x, y, w in zip(a0, b0, rng.normal(size=len(a0)))]
+        bias = rng.normal(size=n) * 0.3
+        og = oracle.Graph(edges, biases=bias)
+        beta, E, A = 0.8, 130, 4000
+    n = og.nvars
+    a = np.array([e[0][0] for e in edges], dtype=np.uint64)
+    b = np.array([e[0][1] for e in edges], dtype=np.uint64)
+    j = np.array([e[1] for e in edges], dtype=np.float64)
+    seeds = rng.integers(0, 2**63, size=E).astype(np.uint64)
+    sites, u, init, en_o, st_o = og.trace(beta, seeds, A)
+    row, nbr, jv = csr_sorted(n, a, b, j)
+    states = np.ascontiguousarray(init, dtype=np.uint8).copy()
+    energies = np.zeros(E)
+    bias = np.ascontiguousarray(bias, dtype=np.float64)
+    amb = emu.emu_replay(E, n, A, row.ctypes.data, nbr.ctypes.data, jv.ctypes.data, bias.ctypes.data,
+                         sites.ctypes.data, u.ctypes.data, states.ctypes.data, energies.ctypes.data, beta)
+    assert amb == 0
+    assert (states.astype(bool) == st_o).all()
+    assert (energies == en_o).all()
