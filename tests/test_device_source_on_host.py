@@ -16,7 +16,8 @@ planes, 7 / 10 Philox rounds; and `k_strip_phase` of csrc/strip.cu - config 5, o
 bit-packed along x - as one strip and as two strips that exchange their ghost rows; and the
 kernels of csrc/state_io.cu: the Philox initial state, bool <-> packed in both spin layouts, and
 `k_replay`, the replay of the reference algorithm's own (site, uniform) trace, against
-oracle/ising_oracle.c.  The library itself is not involved and stays CUDA-only.
+oracle/ising_oracle.c; and `k_edge_general` of csrc/moves.cu, the bit-sliced two-spin edge moves.
+The library itself is not involved and stays CUDA-only.
 """
 import ctypes as C
 import os
@@ -109,6 +110,20 @@ def prepare_sources(dst):
     assert io.count("__global__") == 7
     open(os.path.join(dst, "state_io_kernels.cuh"), "w").write(io)
 
+    mv = open(os.path.join(CSRC, "moves.cu")).read()
+    head = ("// ------------------------------------------------------------------------------------------\n"
+            "// Edge moves on graphs whose couplings all have the same magnitude")
+    i = mv.find(head)
+    k = mv.find("template <int K, int ROUNDS, int DEG>\nstatic int edge_general_launch(")
+    assert 0 <= i < k
+    mv = '#include "msc_device.cuh"\nnamespace ising {\n' + mv[i:k] + "\n}  // namespace ising\n"
+    for ptx in ('    asm volatile("griddepcontrol.launch_dependents;");\n',
+                '    asm volatile("griddepcontrol.wait;" ::: "memory");\n'):
+        assert mv.count(ptx) == 1, ptx
+        mv = mv.replace(ptx, "")
+    assert "asm" not in re.sub(r"//.*", "", mv) and mv.count("__global__") == 1
+    open(os.path.join(dst, "edge_general_kernel.cuh"), "w").write(mv)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -123,7 +138,8 @@ def emu(tmp_path_factory):
     so = os.path.join(build, "libemu_rows.so")
     cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
            "-I", "/usr/local/cuda/include", os.path.join(EMU, "emu_rows.cpp"), os.path.join(EMU, "emu_general.cpp"),
-           os.path.join(EMU, "emu_strip.cpp"), os.path.join(EMU, "emu_state.cpp"), "-o", so]
+           os.path.join(EMU, "emu_strip.cpp"), os.path.join(EMU, "emu_state.cpp"),
+           os.path.join(EMU, "emu_moves.cpp"), "-o", so]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(so)
@@ -138,6 +154,9 @@ def emu(tmp_path_factory):
     lib.emu_strip_phase.restype = C.c_int
     lib.emu_strip_phase.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
                                                                       C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.emu_edge_group.restype = C.c_int
+    lib.emu_edge_group.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] * 4 + [
+        C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint]
     lib.emu_replay.restype = C.c_uint
     lib.emu_replay.argtypes = [C.c_uint64] * 3 + [C.c_void_p] * 8 + [C.c_double]
     lay = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]
@@ -578,3 +597,94 @@ def test_replay_kernel_source_equals_the_reference_restatement(emu, oracle, case
     assert amb == 0
     assert (states.astype(bool) == st_o).all()
     assert (energies == en_o).all()
+
+
+# ---- bit-sliced two-spin edge moves (csrc/moves.cu: k_edge_general) -----------------------------------------
+def strong_edge_colouring(n, a, b):
+    """greedy: two bonds of a class share no site and no bond joins them (graph.h: EdgeClasses)"""
+    adj = [set() for _ in range(n)]
+    for x, y in zip(a.astype(int), b.astype(int)):
+        adj[x].add(y)
+        adj[y].add(x)
+    cls = np.zeros(len(a), dtype=np.uint32)
+    members = []                                                  # per class: set of sites blocked (ends + their neighbours)
+    for e, (x, y) in enumerate(zip(a.astype(int), b.astype(int))):
+        for c, blocked in enumerate(members):
+            if x not in blocked and y not in blocked:
+                break
+        else:
+            members.append(set())
+            c = len(members) - 1
+        cls[e] = c
+        members[c] |= {x, y} | adj[x] | adj[y]
+    return cls
+
+
+def edge_groups(n, a, b, j, cls):
+    """(class, outer degree) groups in the ELL form of kernels.h (EdgeGroup), natural-order slots"""
+    inc = [[] for _ in range(n)]                                  # (far end, J > 0) per adjacency entry
+    for x, y, w in zip(a.astype(int), b.astype(int), j):
+        inc[x].append((y, w > 0))
+        inc[y].append((x, w > 0))
+    out = []
+    for c in range(int(cls.max()) + 1):
+        per_deg = {}
+        for e in np.nonzero(cls == c)[0]:
+            x, y = int(a[e]), int(b[e])
+            outer = [(u, anti, 0) for u, anti in inc[x] if u != y] + [(u, anti, 1) for u, anti in inc[y] if u != x]
+            per_deg.setdefault(len(outer), []).append((x, y, int(e), outer))
+        for d in sorted(per_deg):
+            items = per_deg[d]
+            g = dict(sa=np.array([i[0] for i in items], dtype=np.uint32), sb=np.array([i[1] for i in items], dtype=np.uint32),
+                     eid=np.array([i[2] for i in items], dtype=np.uint32), anti=np.zeros(len(items), dtype=np.uint32),
+                     endp=np.zeros(len(items), dtype=np.uint32), nbr=np.zeros((max(d, 1), len(items)), dtype=np.uint32), deg=d)
+            for i, (_, _, _, outer) in enumerate(items):
+                for k, (u, anti, end) in enumerate(outer):
+                    g["nbr"][k, i] = u
+                    g["anti"][i] |= np.uint32(int(anti) << k)
+                    g["endp"][i] |= np.uint32(end << k)
+            out.append(g)
+    return out
+
+
+@pytest.mark.parametrize("graph,E,K,rounds,specialise", [("square", 64, 6, 7, True), ("3-regular", 96, 6, 7, True),
+                                                         ("cubic", 64, 6, 7, True), ("mixed", 64, 6, 7, False),
+                                                         ("mixed", 40, 5, 10, False), ("3-regular", 32, 7, 7, False)])
+def test_edge_move_source_equals_the_mirror(emu, oracle, graph, E, K, rounds, specialise):
+    rng = np.random.default_rng(E * K)
+    if graph == "3-regular":
+        n = 120
+        a, b = random_regular(n, 3, rng)
+        j = rng.choice([-1.0, 1.0], size=len(a))
+    elif graph == "mixed":
+        n = 80
+        a, b = random_sparse(n, 130, rng, 6)
+        j = rng.choice([-0.5, 0.5], size=len(a))
+    elif graph == "cubic":
+        a, b, j = torus((4, 4, 4), rng, True, -1.0)
+        n = 64
+    else:
+        a, b, j = torus((8, 6, 1), rng, False, -1.0)
+        n = 48
+    jabs = float(abs(j[0]))
+    cls = strong_edge_colouring(n, a, b)
+    groups = edge_groups(n, a, b, j, cls)
+    assert max(g["deg"] for g in groups) <= 15
+    W = (E + 31) // 32
+    init = rng.integers(0, 2, size=(E, n)).astype(bool)
+    words = pack_natural(init, W)
+    seed, gw0, betas, passes = 0x5EED5EED5EED, 1, [0.3, 0.8], 2
+    for t, beta in enumerate(betas):
+        for p in range(passes):
+            for g in groups:
+                rc = emu.emu_edge_group(words.ctypes.data, W, g["sa"].ctypes.data, g["sb"].ctypes.data,
+                                        g["eid"].ctypes.data, g["anti"].ctypes.data, g["endp"].ctypes.data,
+                                        g["nbr"].ctypes.data, len(g["sa"]), g["deg"], t, p, seed, gw0, K, rounds,
+                                        float(beta), jabs, int(specialise), 3)
+                assert rc == 0, rc
+    got = unpack_natural(words, E)
+    col, _ = greedy_colouring(n, a, b)
+    _, ref = oracle.msc_mirror_moves(a, b, j, n, col, cls, E, seed, betas, spin_sweeps=0, edge_passes=passes,
+                                     replica_offset=32 * gw0, planes=K, rounds=rounds, states=init)
+    assert (got == ref).all(), "kernel source on the host differs from the mirror"
+    assert (got != init).mean() > 0.05
