@@ -8,7 +8,8 @@
 //   threadIdx / blockIdx / blockDim / gridDim   thread_local variables set by emu_launch()
 //   __syncthreads()                             a pthread barrier over the block's threads
 //   __shared__ (static)                         a function-local static: blocks run one at a time
-//   extern __shared__ (dynamic)                 emu::dyn_smem, allocated per launch
+//   extern __shared__ (dynamic)                 emu::dyn_smem, allocated per launch (per block when resident)
+//   cg::this_grid().sync(), this_cluster().sync()  a barrier over all threads of a resident launch
 //   atomicAdd, __ldg, __umulhi, __ffs, __popc   their plain C++ meaning (atomicAdd under a mutex)
 // The prepared copy of the header (tests/test_device_source_on_host.py: prepare_sources) has the
 // griddepcontrol / mbarrier PTX and the TMA-staged variant cut out; every cut is asserted there.
@@ -33,9 +34,19 @@ namespace emu {
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local pthread_barrier_t* t_barrier = nullptr;
-inline uint32_t* dyn_smem = nullptr;
+inline thread_local uint32_t* dyn_smem = nullptr;   // the block's dynamic shared memory
+inline thread_local pthread_barrier_t* t_grid_barrier = nullptr;   // cooperative / cluster launches only
 inline std::mutex atomic_mu;
 }  // namespace emu
+
+// what the kernels use of <cooperative_groups.h>: the grid barrier of a cooperative launch and the
+// barrier of a thread-block cluster, both a barrier over every thread of an emu::launch_resident
+namespace cooperative_groups {
+struct grid_group { void sync() const { pthread_barrier_wait(emu::t_grid_barrier); } };
+struct cluster_group { void sync() const { pthread_barrier_wait(emu::t_grid_barrier); } };
+inline grid_group this_grid() { return {}; }
+inline cluster_group this_cluster() { return {}; }
+}  // namespace cooperative_groups
 
 #define threadIdx emu::t_threadIdx
 #define blockIdx emu::t_blockIdx
@@ -79,7 +90,7 @@ template <typename Args>
 void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, const Args& args) {
     const unsigned nthreads = block.x * block.y * block.z;
     std::vector<uint32_t> smem(smem_bytes / 4 + 1);
-    dyn_smem = smem.data();
+    uint32_t* const smem_p = smem.data();
     for (unsigned b = 0; b < grid.x * grid.y; ++b) {
         pthread_barrier_t bar;
         pthread_barrier_init(&bar, nullptr, nthreads);
@@ -92,23 +103,55 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
                 t_blockDim = block;
                 t_gridDim = grid;
                 t_barrier = &bar;
+                dyn_smem = smem_p;
                 kern(args);
             });
         for (auto& x : th) x.join();
         pthread_barrier_destroy(&bar);
     }
-    dyn_smem = nullptr;
+}
+
+// Cooperative / cluster launch: all blocks resident at once (every thread of the grid is an OS
+// thread), so that a grid-wide or cluster-wide barrier can be waited on.  Function-local statics
+// standing in for __shared__ are then shared by the blocks: fine for the kernels run this way,
+// whose static shared data is the same in every block (the thresholds of the current sweep).
+template <typename Args>
+void launch_resident(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, const Args& args) {
+    const unsigned nthreads = block.x * block.y * block.z, nblocks = grid.x * grid.y;
+    std::vector<std::vector<uint32_t>> smem(nblocks, std::vector<uint32_t>(smem_bytes / 4 + 1));
+    std::vector<pthread_barrier_t> bars(nblocks);
+    pthread_barrier_t all;
+    pthread_barrier_init(&all, nullptr, nthreads * nblocks);
+    for (auto& b : bars) pthread_barrier_init(&b, nullptr, nthreads);
+    std::vector<std::thread> th;
+    th.reserve((size_t)nthreads * nblocks);
+    for (unsigned b = 0; b < nblocks; ++b)
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([=, &bars, &all, &smem, &args] {
+                t_threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+                t_blockIdx = uint3{b % grid.x, b / grid.x, 0};
+                t_blockDim = block;
+                t_gridDim = grid;
+                t_barrier = &bars[b];
+                t_grid_barrier = &all;
+                dyn_smem = smem[b].data();
+                kern(args);
+            });
+    for (auto& x : th) x.join();
+    for (auto& b : bars) pthread_barrier_destroy(&b);
+    pthread_barrier_destroy(&all);
 }
 }  // namespace emu
 
 namespace emu {
 // the same for kernels that take several parameters
-template <typename... KArgs, typename... Args>
+template <bool RESIDENT = false, typename... KArgs, typename... Args>
 void launch_v(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
     struct Pack { void (*k)(KArgs...); std::tuple<KArgs...> a; };
     Pack p{kern, std::tuple<KArgs...>(KArgs(args)...)};
     const Pack* pp = &p;
     void (*tramp)(const Pack*) = [](const Pack* q) { std::apply(q->k, q->a); };
-    launch<const Pack*>(tramp, grid, block, smem_bytes, pp);
+    if (RESIDENT) launch_resident<const Pack*>(tramp, grid, block, smem_bytes, pp);
+    else launch<const Pack*>(tramp, grid, block, smem_bytes, pp);
 }
 }  // namespace emu

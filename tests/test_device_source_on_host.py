@@ -16,7 +16,11 @@ planes, 7 / 10 Philox rounds; and `k_strip_phase` of csrc/strip.cu - config 5, o
 bit-packed along x - as one strip and as two strips that exchange their ghost rows; and the
 kernels of csrc/state_io.cu: the Philox initial state, bool <-> packed in both spin layouts, and
 `k_replay`, the replay of the reference algorithm's own (site, uniform) trace, against
-oracle/ising_oracle.c; and `k_edge_general` of csrc/moves.cu, the bit-sliced two-spin edge moves.
+oracle/ising_oracle.c; `k_edge_general` of csrc/moves.cu, the bit-sliced two-spin edge moves; and
+the other checkerboard kernels: one launch per colour phase (non-default planes / rounds, per-replica
+betas), the cooperative chunk behind a grid barrier, the thread-block-cluster chunk that small
+lattices run (with per-sweep energies, with per-replica betas, with the satisfied-bond counts of
+the last sweep that a tempering cycle reads), and the count-only pass.
 The library itself is not involved and stays CUDA-only.
 """
 import ctypes as C
@@ -53,9 +57,9 @@ def prepare_sources(dst):
             g.write(f.read())
 
     msc = open(os.path.join(CSRC, "msc_device.cuh")).read()
-    for line in ("#include <cooperative_groups.h>\n", "namespace cg = cooperative_groups;\n"):
-        assert msc.count(line) == 1
-        msc = msc.replace(line, "")
+    line = "#include <cooperative_groups.h>\n"               # cuda_on_host.h stands in for what is used of it
+    assert msc.count(line) == 1 and msc.count("namespace cg = cooperative_groups;\n") == 1
+    msc = msc.replace(line, "")
     inc = '#include "../../include/ising_b200.h"'
     assert msc.count(inc) == 1
     msc = msc.replace(inc, '#include "%s"' % os.path.join(ROOT, "include", "ising_b200.h"))
@@ -124,6 +128,44 @@ def prepare_sources(dst):
     assert "asm" not in re.sub(r"//.*", "", mv) and mv.count("__global__") == 1
     open(os.path.join(dst, "edge_general_kernel.cuh"), "w").write(mv)
 
+    with open(os.path.join(CSRC, "sweep_phase.cuh")) as f:
+        phase = f.read()
+    assert "__shared__" not in phase and "asm" not in re.sub(r"//.*", "", phase)
+    open(os.path.join(dst, "sweep_phase.cuh"), "w").write(phase)
+
+    st = open(os.path.join(CSRC, "sweep_stencil.cu")).read()
+    kernels = _cut(st, "template <int DIM, bool PMJ, int K, int ROUNDS, int V>\nstatic void sweep_launch_phase(", None,
+                   "launchers of sweep_stencil.cu")
+    i = st.find("static void stencil_block_shape(")
+    k = st.find("template <int V>\nstatic int sweep_dispatch_kind(")
+    assert 0 <= i < k
+    shape = st[i:k]
+    i = st.find("constexpr int NS_NP = 10;")
+    k = st.find("template <int V>\nstatic int nsat_dispatch(")
+    assert 0 <= i < k
+    st = kernels + shape + st[i:k] + "\n}  // namespace ising\n"
+    dyn = "    extern __shared__ uint32_t sm[];"
+    assert st.count(dyn) == 4
+    st = st.replace(dyn, "    uint32_t* sm = emu::dyn_smem;")
+    assert st.count("__shared__") == 1            # the cooperative kernel's thresholds of the current sweep
+    st = st.replace("__shared__", "EMU_SHARED")
+    assert "asm" not in re.sub(r"//.*", "", st) and "<<<" not in st and st.count("__global__") == 4
+    open(os.path.join(dst, "stencil_kernels.cuh"), "w").write(st)
+
+    cl = open(os.path.join(CSRC, "sweep_cluster.cu")).read()
+    cl = _cut(cl, "static_assert(sizeof(MscThresholds) / 4 <= 32", None, "launchers of sweep_cluster.cu") + \
+        "\n}  // namespace ising\n"
+    for ptx in ('    asm volatile("griddepcontrol.launch_dependents;");\n',
+                '    asm volatile("griddepcontrol.wait;" ::: "memory");\n'):
+        assert cl.count(ptx) == 1, ptx
+        cl = cl.replace(ptx, "")
+    assert cl.count(dyn) == 1
+    cl = cl.replace(dyn, "    uint32_t* sm = emu::dyn_smem;")
+    assert cl.count("__shared__") == 1            # th[2]: this sweep's and the next sweep's thresholds
+    cl = cl.replace("__shared__", "EMU_SHARED")
+    assert "asm" not in re.sub(r"//.*", "", cl) and cl.count("__global__") == 1
+    open(os.path.join(dst, "cluster_kernel.cuh"), "w").write(cl)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -136,11 +178,16 @@ def emu(tmp_path_factory):
     build = str(tmp_path_factory.mktemp("host_emulation"))
     prepare_sources(os.path.join(build, "prepared"))
     so = os.path.join(build, "libemu_rows.so")
-    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
-           "-I", "/usr/local/cuda/include", os.path.join(EMU, "emu_rows.cpp"), os.path.join(EMU, "emu_general.cpp"),
-           os.path.join(EMU, "emu_strip.cpp"), os.path.join(EMU, "emu_state.cpp"),
-           os.path.join(EMU, "emu_moves.cpp"), "-o", so]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
+             "-I", "/usr/local/cuda/include"]
+    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil"]
+    procs = [subprocess.Popen(flags + ["-c", os.path.join(EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for u in units]
+    for u, pr in zip(units, procs):
+        _, err = pr.communicate()
+        assert pr.returncode == 0, u + ":\n" + err[-4000:]
+    res = subprocess.run(["g++", "-shared", "-pthread", "-o", so] + [os.path.join(build, u + ".o") for u in units],
+                         capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(so)
     lib.emu_rows_phase.restype = C.c_int
@@ -154,6 +201,10 @@ def emu(tmp_path_factory):
     lib.emu_strip_phase.restype = C.c_int
     lib.emu_strip_phase.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
                                                                       C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.emu_stencil.restype = C.c_int
+    lib.emu_stencil.argtypes = [C.c_int, C.c_int] + [C.c_uint32] * 4 + [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
+                                C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
     lib.emu_edge_group.restype = C.c_int
     lib.emu_edge_group.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] * 4 + [
         C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint]
@@ -688,3 +739,97 @@ def test_edge_move_source_equals_the_mirror(emu, oracle, graph, E, K, rounds, sp
                                      replica_offset=32 * gw0, planes=K, rounds=rounds, states=init)
     assert (got == ref).all(), "kernel source on the host differs from the mirror"
     assert (got != init).mean() > 0.05
+
+
+# ---- the other checkerboard kernels: per-phase launch, cooperative chunk, cluster chunk, count only ---------
+def stencil_tables(betas_e, W, dim, jabs, K=6):
+    """per-replica tables of the lattice kernels: tplane[(w * 3 + cls) * 8 + p] bit b, tlow[(w * 32 + b) * 3 + cls]"""
+    import math
+
+    tplane = np.zeros((W, 3, 8), dtype=np.uint32)
+    tlow = np.zeros((W * 32, 3), dtype=np.uint32)
+    for e, beta in enumerate(betas_e):
+        for c in range(dim):
+            scaled = math.ldexp(math.exp(-beta * 4.0 * (c + 1) * jabs), K + 32)
+            T = min(int(math.floor(scaled)), (1 << (K + 32)) - 1)
+            tlow[e, c] = T & 0xFFFFFFFF
+            for p in range(K):
+                tplane[e // 32, c, p] |= np.uint32(((T >> (K + 31 - p)) & 1) << (e % 32))
+    return tplane, tlow
+
+
+STENCIL_CASES = [
+    # mode, dims, E, V, pmj, K, rounds, per-replica betas, energies, SMs or CTAs of the cluster
+    ("phase", (8, 6, 4), 128, 4, True, 5, 7, False, True, 2),
+    ("phase", (8, 6, 4), 128, 4, True, 7, 10, False, False, 2),
+    ("phase", (6, 4, 1), 20, 1, False, 7, 10, False, True, 3),
+    ("phase", (4, 4, 4), 64, 2, False, 6, 7, True, True, 1),         # tempering on a lattice: one beta per replica bit
+    ("phase", (12, 4, 1), 64, 2, True, 6, 7, True, False, 2),
+    ("coop", (8, 4, 4), 128, 4, True, 6, 7, False, True, 5),
+    ("coop", (16, 6, 1), 128, 4, False, 6, 7, False, False, 4),
+    ("cluster", (8, 4, 4), 128, 4, True, 6, 7, False, True, 8),      # per-sweep energies (config 1's production path)
+    ("cluster", (32, 32, 1), 32, 1, False, 6, 7, False, True, 16),   # BASELINE config 1's lattice, 16-CTA cluster
+    ("cluster", (4, 4, 4), 32, 1, True, 6, 7, False, False, 8),
+    ("cluster", (4, 4, 4), 64, 2, False, 6, 7, True, True, 8),       # tempering chunk ending with the counts
+    ("cluster", (8, 6, 1), 64, 2, True, 6, 7, True, False, 4),
+]
+
+
+@pytest.mark.parametrize("mode,dims,E,V,pmj,K,rounds,perbeta,energies,units", STENCIL_CASES)
+def test_checkerboard_kernels_equal_the_mirror(emu, oracle, mode, dims, E, V, pmj, K, rounds, perbeta, energies, units):
+    rng = np.random.default_rng(sum(dims) * 7 + E + K)
+    dim = 3 if dims[2] > 1 else 2
+    a, b, j = torus(dims, rng, pmj, -1.0)
+    N = dims[0] * dims[1] * dims[2]
+    _, colors = layout_index(dims)
+    W = (E + 31) // 32
+    assert W % V == 0
+    init = rng.integers(0, 2, size=(E, N)).astype(bool)
+    words = pack(init, dims, W)
+    jmask = None
+    if pmj:                                                       # [2][2 dim][halfN]: the k-major form of the masks
+        jmask = np.ascontiguousarray(bond_masks(dims, a, b, j).reshape(2, N // 2, 8)[:, :, :2 * dim].transpose(0, 2, 1))
+    seed, sweep0, gw0, cw = 0xFEEDFACE12345, 9, 2, W * 32
+    nsw = 3
+    if perbeta:
+        betas_e = np.geomspace(0.1, 1.4, E)
+        tplane, tlow = stencil_tables(betas_e, W, dim, 1.0)
+        tp, tl = tplane.ctypes.data, tlow.ctypes.data
+        betas = np.zeros(nsw)
+    else:
+        tp = tl = None
+        betas = np.array([0.2, 0.5, 1.0])
+    jm = None if jmask is None else jmask.ctypes.data
+    nb = len(a)
+
+    def call(m, colour, sweep, n, bts, acc, hist):
+        return emu.emu_stencil(m, dim, dims[0], dims[1], dims[2], W, V, jm, 0, words.ctypes.data, colour, seed, sweep, n,
+                               gw0, K, rounds, bts.ctypes.data, 1.0, tp, tl, int(acc), hist.ctypes.data, cw, units)
+
+    if mode == "phase":
+        hist = np.zeros((nsw, cw), dtype=np.uint64)
+        for t in range(nsw):
+            for colour in (0, 1):
+                assert call(0, colour, sweep0 + t, 1, betas[t:t + 1], energies and colour == 1, hist[t]) == 0
+    else:
+        last_only = perbeta                                       # a tempering chunk leaves the last sweep's counts
+        hist = np.zeros((1 if last_only else nsw, cw), dtype=np.uint64)
+        assert call(1 if mode == "coop" else 2, 0, sweep0, nsw, betas, energies, hist) == 0
+    got = unpack(words, dims, E)
+    kw = dict(replica_offset=32 * gw0, planes=K, rounds=rounds, states=init, sweep0=sweep0, per_sweep=True)
+    if perbeta:
+        en_ref, st_ref = oracle.msc_mirror(a, b, j, N, colors, E, seed, None, per_replica_beta=betas_e, nsweeps=nsw, **kw)
+    else:
+        en_ref, st_ref = oracle.msc_mirror(a, b, j, N, colors, E, seed, betas, **kw)
+    assert (got == st_ref).all(), "kernel source on the host differs from the mirror"
+    assert (got != init).mean() > 0.05
+    if energies:
+        en = nb - 2.0 * hist[:, :E].astype(np.float64).T
+        if mode != "phase" and perbeta:
+            assert (en[:, 0] == en_ref[:, -1]).all()
+        else:
+            assert (en == en_ref).all()
+    # the count-only pass on the final configuration
+    cnt = np.zeros(cw, dtype=np.uint64)
+    assert call(3, 0, 0, 0, betas, 0, cnt) == 0
+    assert (cnt[:E] == satisfied_bonds(got, a, b, j)).all()
