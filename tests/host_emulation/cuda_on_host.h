@@ -11,6 +11,7 @@
 //   extern __shared__ (dynamic)                 emu::dyn_smem, allocated per launch (per block when resident)
 //   cg::this_grid().sync(), this_cluster().sync()  a barrier over all threads of a resident launch
 //   atomicAdd, __ldg, __umulhi, __ffs, __popc   their plain C++ meaning (atomicAdd under a mutex)
+//   __ballot_sync (full mask)                   a barrier over the warp's 32 threads around a scratch row
 // The prepared copy of the header (tests/test_device_source_on_host.py: prepare_sources) has the
 // griddepcontrol / mbarrier PTX and the TMA-staged variant cut out; every cut is asserted there.
 #pragma once
@@ -36,6 +37,8 @@ inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local pthread_barrier_t* t_barrier = nullptr;
 inline thread_local uint32_t* dyn_smem = nullptr;   // the block's dynamic shared memory
 inline thread_local pthread_barrier_t* t_grid_barrier = nullptr;   // cooperative / cluster launches only
+inline thread_local pthread_barrier_t* t_warp_barrier = nullptr;   // the 32 consecutive threads of a warp
+inline thread_local uint32_t* t_warp_scratch = nullptr;            // 32 words per warp (warp votes)
 inline std::mutex atomic_mu;
 }  // namespace emu
 
@@ -70,6 +73,7 @@ static inline T __ldg(const T* p) { return *p; }
 // plain operations here (the emulation is built with -ffp-contract=off)
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) {
     std::lock_guard<std::mutex> g(emu::atomic_mu);
     const unsigned int old = *p;
@@ -83,6 +87,17 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
     return old;
 }
 
+// warp vote over the full warp: lanes post their predicate, meet, read all 32
+static inline uint32_t __ballot_sync(uint32_t, int pred) {
+    const unsigned lane = (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u;
+    emu::t_warp_scratch[lane] = pred ? 1u : 0u;
+    pthread_barrier_wait(emu::t_warp_barrier);
+    uint32_t r = 0;
+    for (unsigned l = 0; l < 32; ++l) r |= emu::t_warp_scratch[l] << l;
+    pthread_barrier_wait(emu::t_warp_barrier);
+    return r;
+}
+
 namespace emu {
 // <<<grid, block, smem_bytes>>> of a kernel taking one by-value argument: blocks one after the
 // other, the threads of a block concurrently
@@ -91,6 +106,12 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
     const unsigned nthreads = block.x * block.y * block.z;
     std::vector<uint32_t> smem(smem_bytes / 4 + 1);
     uint32_t* const smem_p = smem.data();
+    const unsigned nwarps = nthreads % 32 == 0 ? nthreads / 32 : 0;   // warp votes need whole warps
+    std::vector<pthread_barrier_t> wbar(nwarps);
+    std::vector<uint32_t> wscratch((size_t)nwarps * 32 + 1);
+    for (auto& w : wbar) pthread_barrier_init(&w, nullptr, 32);
+    pthread_barrier_t* const wbar_p = wbar.data();
+    uint32_t* const wscratch_p = wscratch.data();
     for (unsigned b = 0; b < grid.x * grid.y; ++b) {
         pthread_barrier_t bar;
         pthread_barrier_init(&bar, nullptr, nthreads);
@@ -104,11 +125,14 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
                 t_gridDim = grid;
                 t_barrier = &bar;
                 dyn_smem = smem_p;
+                t_warp_barrier = nwarps ? wbar_p + t / 32 : nullptr;
+                t_warp_scratch = wscratch_p + (size_t)(t / 32) * 32;
                 kern(args);
             });
         for (auto& x : th) x.join();
         pthread_barrier_destroy(&bar);
     }
+    for (auto& w : wbar) pthread_barrier_destroy(&w);
 }
 
 // Cooperative / cluster launch: all blocks resident at once (every thread of the grid is an OS

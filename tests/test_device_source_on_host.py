@@ -20,7 +20,10 @@ oracle/ising_oracle.c; `k_edge_general` of csrc/moves.cu, the bit-sliced two-spi
 the other checkerboard kernels: one launch per colour phase (non-default planes / rounds, per-replica
 betas), the cooperative chunk behind a grid barrier, the thread-block-cluster chunk that small
 lattices run (with per-sweep energies, with per-replica betas, with the satisfied-bond counts of
-the last sweep that a tempering cycle reads), and the count-only pass.
+the last sweep that a tempering cycle reads), and the count-only pass.  With `k_pt_cycle` of
+csrc/pt_device.cu on top, a whole tempering run - chunks of sweeps, energies, time averages, swap
+decisions, slot maps, rebuilt threshold tables, slot-ordered samples - is replayed on the host as
+ising_pt_timesteps_sample enqueues it and compared with the mirror's.
 The library itself is not involved and stays CUDA-only.
 """
 import ctypes as C
@@ -166,6 +169,20 @@ def prepare_sources(dst):
     assert "asm" not in re.sub(r"//.*", "", cl) and cl.count("__global__") == 1
     open(os.path.join(dst, "cluster_kernel.cuh"), "w").write(cl)
 
+    with open(os.path.join(CSRC, "pt_exp.h")) as f:
+        open(os.path.join(dst, "pt_exp.h"), "w").write(f.read())
+    pt = open(os.path.join(CSRC, "pt_device.cu")).read()
+    pt, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", pt)
+    assert nwrap == 4 and "<<<" not in pt and "launch_pdl" not in pt, nwrap
+    for ptx in ('    asm volatile("griddepcontrol.launch_dependents;");\n',
+                '    asm volatile("griddepcontrol.wait;" ::: "memory");\n'):
+        assert pt.count(ptx) == 1, ptx
+        pt = pt.replace(ptx, "")
+    assert pt.count("__shared__") == 2            # the swap counters of k_pt_swap and k_pt_cycle (one block each)
+    pt = pt.replace("__shared__", "EMU_SHARED")
+    assert "asm" not in re.sub(r"//.*", "", pt)
+    open(os.path.join(dst, "pt_device_kernels.cuh"), "w").write(pt)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -180,7 +197,7 @@ def emu(tmp_path_factory):
     so = os.path.join(build, "libemu_rows.so")
     flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
              "-I", "/usr/local/cuda/include"]
-    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil"]
+    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt"]
     procs = [subprocess.Popen(flags + ["-c", os.path.join(EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for u in units]
     for u, pr in zip(units, procs):
@@ -205,6 +222,11 @@ def emu(tmp_path_factory):
     lib.emu_stencil.argtypes = [C.c_int, C.c_int] + [C.c_uint32] * 4 + [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
                                 C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                 C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.emu_pt_cycle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_uint64, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_uint32, C.c_int,
+                                 C.c_void_p, C.c_void_p]
+    lib.emu_pt_swap.argtypes = [C.c_void_p] * 5 + [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.emu_edge_group.restype = C.c_int
     lib.emu_edge_group.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] * 4 + [
         C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint]
@@ -833,3 +855,92 @@ def test_checkerboard_kernels_equal_the_mirror(emu, oracle, mode, dims, E, V, pm
     cnt = np.zeros(cw, dtype=np.uint64)
     assert call(3, 0, 0, 0, betas, 0, cnt) == 0
     assert (cnt[:E] == satisfied_bonds(got, a, b, j)).all()
+
+
+# ---- a whole tempering run: cluster chunks + k_pt_cycle, as ising_pt_timesteps_sample enqueues them ----------
+@pytest.mark.parametrize("dims,R,timesteps,swap_freq,sampling_freq,pmj", [((4, 4, 4), 32, 24, 3, 4, True),
+                                                                          ((8, 4, 1), 20, 30, 5, 2, False),
+                                                                          ((4, 4, 2), 64, 12, 1, 3, False)])
+def test_tempering_run_on_the_host_equals_the_mirror(emu, oracle, native, dims, R, timesteps, swap_freq, sampling_freq, pmj):
+    import math
+
+    rng = np.random.default_rng(R + timesteps)
+    dim = 3 if dims[2] > 1 else 2
+    a, b, j = torus(dims, rng, pmj, -1.0)
+    N, nb = dims[0] * dims[1] * dims[2], len(a)
+    _, colors = layout_index(dims)
+    W = (R + 31) // 32
+    V = 2 if W % 2 == 0 else 1
+    e32, K, seed = W * 32, 6, 0x7E57AB1E5EED
+    betas = np.geomspace(0.15, 1.3, R)
+    kind = emu.emu_kind(dim)
+    words = np.zeros(N * W, dtype=np.uint32)
+    emu.emu_init_random(words.ctypes.data, kind, dims[0], dims[1], dims[2], N, W, seed, 0, 2)
+    jmask = None
+    if pmj:
+        jmask = np.ascontiguousarray(bond_masks(dims, a, b, j).reshape(2, N // 2, 8)[:, :, :2 * dim].transpose(0, 2, 1))
+    # device-resident state of the ladder (api_pt.cu: ising_pt)
+    slot_of_cfg = np.arange(R, dtype=np.uint32)
+    cfg_of_slot = np.arange(R, dtype=np.uint32)
+    gidx = np.arange(R, dtype=np.uint32)
+    stats = np.zeros(2 + 2 * R, dtype=np.uint64)
+    slot_of_replica = np.zeros(e32, dtype=np.uint32)
+    slot_of_replica[:R] = np.arange(R)
+    t64 = np.zeros((R, 3), dtype=np.uint64)                       # thresholds by SLOT (host-computed, libm exp)
+    for s_, beta in enumerate(betas):
+        for c in range(dim):
+            t64[s_, c] = min(int(math.floor(math.ldexp(math.exp(-beta * 4.0 * (c + 1)), K + 32))), (1 << (K + 32)) - 1)
+    tplane, tlow = stencil_tables(betas[slot_of_replica[:R]], W, dim, 1.0)
+    nsat = np.zeros(e32, dtype=np.uint64)
+    e_local, e_all, acc = np.zeros(e32), np.zeros(e32), np.zeros(R)
+    ns = timesteps // sampling_freq
+    samples = np.zeros((R, ns, N), dtype=bool)
+    none = np.zeros(1)
+    remaining, to_swap, to_sample, k, sweep = timesteps, swap_freq, sampling_freq, 0, 0
+    while remaining > 0:                                          # ising_pt_timesteps_sample's loop
+        t = min(to_sample, to_swap, remaining)
+        rc = emu.emu_stencil(2, dim, dims[0], dims[1], dims[2], W, V, None if jmask is None else jmask.ctypes.data, 0,
+                             words.ctypes.data, 0, seed, sweep, t, 0, K, 7, none.ctypes.data, 1.0, tplane.ctypes.data,
+                             tlow.ctypes.data, 1, nsat.ctypes.data, e32, 8)
+        assert rc == 0, rc
+        sweep += t
+        to_sample -= t
+        to_swap -= t
+        remaining -= t
+        emu.emu_pt_cycle(nsat.ctypes.data, e_local.ctypes.data, e_all.ctypes.data, R, e32, 1.0, nb, 2, gidx.ctypes.data,
+                         betas.ctypes.data, slot_of_cfg.ctypes.data, cfg_of_slot.ctypes.data, R, seed, stats.ctypes.data,
+                         slot_of_replica.ctypes.data, acc.ctypes.data, float(t), int(to_swap == 0),
+                         t64.ctypes.data if to_swap == 0 else None, W, K, tplane.ctypes.data, tlow.ctypes.data)
+        assert (nsat == 0).all()                                  # zeroed for the next cycle
+        if to_swap == 0:
+            to_swap = swap_freq
+        if to_sample == 0:
+            if k < ns:
+                samples[:, k, :] = unpack(words.reshape(N, W), dims, R)[cfg_of_slot]
+            k += 1
+            to_sample = sampling_freq
+    st_ref, en_ref, swaps_ref, slots_ref = oracle.msc_mirror_pt(a, b, j, N, colors, betas, seed, timesteps, swap_freq,
+                                                                sampling_freq)
+    assert (samples == st_ref).all()
+    assert (acc / timesteps == en_ref).all()
+    assert int(stats[1]) == swaps_ref and int(stats[0]) == timesteps // swap_freq
+    assert (slot_of_cfg == slots_ref).all()
+    assert swaps_ref > 0
+    # per-pair counters: every pair attempted once per swap step
+    assert (stats[2:2 + R - 1] == timesteps // swap_freq).all() and int(stats[2 + R:].sum()) == swaps_ref
+
+    # k_pt_swap alone == the host's ising_pt_decide_swaps on the same energies
+    en = rng.normal(size=R) * 20
+    s1, c1 = np.arange(R, dtype=np.uint32), np.arange(R, dtype=np.uint32)
+    st1 = np.zeros(2 + 2 * R, dtype=np.uint64)
+    st1[0] = 5
+    emu.emu_pt_swap(betas.ctypes.data, en.ctypes.data, gidx.ctypes.data, s1.ctypes.data, c1.ctypes.data, R, seed,
+                    st1.ctypes.data, slot_of_replica.ctypes.data, e32)
+    s2, c2 = np.arange(R, dtype=np.uint32), np.arange(R, dtype=np.uint32)
+    nsw = C.c_uint64(0)
+    lib = native.lib()
+    rc = lib.ising_pt_decide_swaps(betas.ctypes.data_as(C.c_void_p), C.c_uint64(R), en.ctypes.data_as(C.c_void_p),
+                                   C.c_uint64(seed), C.c_uint64(5), s2.ctypes.data_as(C.c_void_p),
+                                   c2.ctypes.data_as(C.c_void_p), C.byref(nsw))
+    assert rc == 0
+    assert (s1 == s2).all() and (c1 == c2).all() and int(st1[1]) == nsw.value and int(st1[0]) == 6
