@@ -183,6 +183,23 @@ def prepare_sources(dst):
     assert "asm" not in re.sub(r"//.*", "", pt)
     open(os.path.join(dst, "pt_device_kernels.cuh"), "w").write(pt)
 
+    g2 = open(os.path.join(CSRC, "sweep_general.cu")).read()
+    i = g2.find("// per-replica threshold tables from host-computed 64-bit thresholds")
+    k = g2.find("// ------------------------------------------------------------------------------------------\n"
+                "// Colour-class sweep for arbitrary real couplings and biases")
+    assert 0 <= i < k
+    g2, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", g2[i:k])
+    assert nwrap == 3 and "<<<" not in g2 and g2.count("__global__") == 3, nwrap
+    assert g2.count("__shared__") == 1            # the per-bit counters of k_nsat_general
+    g2 = '#include "msc_device.cuh"\nnamespace ising {\n' + g2.replace("__shared__", "EMU_SHARED") + "\n}  // namespace ising\n"
+    open(os.path.join(dst, "general_aux_kernels.cuh"), "w").write(g2)
+
+    ob = open(os.path.join(CSRC, "observables.cu")).read()
+    ob, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", ob)
+    assert nwrap == 7 and "<<<" not in ob and ob.count("__global__") == 7, nwrap
+    assert ob.count("__shared__") == 1
+    open(os.path.join(dst, "observables_kernels.cuh"), "w").write(ob.replace("__shared__", "EMU_SHARED"))
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -197,7 +214,7 @@ def emu(tmp_path_factory):
     so = os.path.join(build, "libemu_rows.so")
     flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
              "-I", "/usr/local/cuda/include"]
-    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt"]
+    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt", "emu_aux"]
     procs = [subprocess.Popen(flags + ["-c", os.path.join(EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for u in units]
     for u, pr in zip(units, procs):
@@ -227,6 +244,14 @@ def emu(tmp_path_factory):
                                  C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_uint32, C.c_int,
                                  C.c_void_p, C.c_void_p]
     lib.emu_pt_swap.argtypes = [C.c_void_p] * 5 + [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.emu_build_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
+    lib.emu_nsat_general.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    lib.emu_count_up.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_uint]
+    lib.emu_overlap_from_counts.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.emu_energy_from_hist.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, C.c_int,
+                                         C.c_void_p, C.c_uint32]
+    lib.emu_energy_from_nsat.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                         C.c_uint64]
     lib.emu_edge_group.restype = C.c_int
     lib.emu_edge_group.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] * 4 + [
         C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint]
@@ -944,3 +969,82 @@ def test_tempering_run_on_the_host_equals_the_mirror(emu, oracle, native, dims, 
                                    c2.ctypes.data_as(C.c_void_p), C.byref(nsw))
     assert rc == 0
     assert (s1 == s2).all() and (c1 == c2).all() and int(st1[1]) == nsw.value and int(st1[0]) == 6
+
+
+# ---- the smaller kernels around the sweeps ------------------------------------------------------------------
+def test_table_builders_on_the_host(emu):
+    """k_build_tables / k_build_tables_stencil (warp votes) == the tables the tests above build in numpy,
+    under a non-trivial replica -> slot permutation"""
+    import math
+
+    rng = np.random.default_rng(11)
+    R, W, K = 50, 2, 6
+    betas = np.geomspace(0.1, 1.5, R)                              # by slot
+    slot_of_replica = np.zeros(W * 32, dtype=np.uint32)
+    slot_of_replica[:R] = rng.permutation(R)
+
+    def t64_of(beta, de):
+        return min(int(math.floor(math.ldexp(math.exp(-beta * de), K + 32))), (1 << (K + 32)) - 1)
+
+    jabs = 0.5
+    t64 = np.zeros((R, 16, 8), dtype=np.uint64)                    # general: [slot][deg][cls]
+    for s_, beta in enumerate(betas):
+        for deg in range(16):
+            for cls in range(min(deg - deg // 2, 8)):
+                t64[s_, deg, cls] = t64_of(beta, 2.0 * jabs * (2 * (deg // 2 + 1 + cls) - deg))
+    plane = np.zeros((16, W, 8, 8), dtype=np.uint32)
+    low = np.zeros((16, 32 * W, 8), dtype=np.uint32)
+    emu.emu_build_tables(t64.ctypes.data, slot_of_replica.ctypes.data, W, K, plane.ctypes.data, low.ctypes.data, 0, 7)
+    per_replica = np.concatenate([betas[slot_of_replica[:R]], np.full(W * 32 - R, betas[0])])   # padding bits: slot 0
+    plane_ref, low_ref = per_replica_tables(per_replica, W, K, jabs)
+    assert (plane == plane_ref).all() and (low == low_ref).all()
+
+    t64s = np.zeros((R, 3), dtype=np.uint64)                       # lattices: [slot][cls]
+    for s_, beta in enumerate(betas):
+        for c in range(3):
+            t64s[s_, c] = t64_of(beta, 4.0 * (c + 1) * jabs)
+    tplane = np.zeros((W, 3, 8), dtype=np.uint32)
+    tlow = np.zeros((W * 32, 3), dtype=np.uint32)
+    emu.emu_build_tables(t64s.ctypes.data, slot_of_replica.ctypes.data, W, K, tplane.ctypes.data, tlow.ctypes.data, 1, 2)
+    tp_ref, tl_ref = stencil_tables(per_replica, W, 3, jabs)
+    assert (tplane == tp_ref).all() and (tlow == tl_ref).all()
+
+
+@pytest.mark.parametrize("E", [37, 128])
+def test_count_and_energy_kernels_on_the_host(emu, E):
+    """get_energy on a general graph (k_nsat_general), magnetisation and pair overlaps (k_count_up),
+    bond counts -> energies, against numpy"""
+    rng = np.random.default_rng(E)
+    n = 150
+    a, b = random_sparse(n, 400, rng, 15)
+    j = rng.choice([-1.5, 1.5], size=len(a))
+    W = (E + 31) // 32
+    states = rng.integers(0, 2, size=(E, n)).astype(bool)
+    words = pack_natural(states, W)
+    row, nbr, jv = csr_sorted(n, a, b, j)
+    row32, anti = row.astype(np.uint32), (jv > 0).astype(np.uint8)
+    nsat2 = np.zeros(W * 32, dtype=np.uint64)
+    emu.emu_nsat_general(words.ctypes.data, n, W, row32.ctypes.data, nbr.ctypes.data, anti.ctypes.data, nsat2.ctypes.data, 3)
+    sat = satisfied_bonds(states, a, b, j)
+    assert (nsat2[:E] == 2 * sat).all()                           # every bond seen from both ends
+    en = np.zeros((E, 3))
+    emu.emu_energy_from_nsat(nsat2.ctypes.data, E, 1.5, len(a), 1, en.ctypes.data, 3, 1)
+    s = states.astype(np.int64) * 2 - 1
+    e_ref = (s[:, a.astype(int)] * s[:, b.astype(int)] * j[None, :]).sum(axis=1)
+    assert (en[:, 1] == e_ref).all() and (en[:, 0] == 0).all() and (en[:, 2] == 0).all()
+
+    up = np.zeros(W * 32, dtype=np.uint64)
+    emu.emu_count_up(words.ctypes.data, n, W, up.ctypes.data, 0, 4)
+    assert (up[:E] == states.sum(axis=1)).all()
+    dis = np.zeros(W * 32, dtype=np.uint64)
+    emu.emu_count_up(words.ctypes.data, n, W, dis.ctypes.data, 1, 4)
+    P = E // 2
+    q = np.zeros((P, 2))
+    emu.emu_overlap_from_counts(dis.ctypes.data, P, n, q.ctypes.data, 2, 0)
+    assert (q[:, 0] == (s[0:2 * P:2] * s[1:2 * P:2]).sum(axis=1)).all()
+
+    nt, cw, copies = 4, W * 32, 3                                 # per-sweep histories spread over counter copies
+    hist = rng.integers(0, 50, size=(nt, copies, cw)).astype(np.uint64)
+    out = np.zeros((E, nt))
+    emu.emu_energy_from_hist(hist.ctypes.data, E, cw, nt, 1.5, len(a), 2, out.ctypes.data, copies)
+    assert (out == 1.5 * (len(a) - 2.0 * hist.sum(axis=1)[:, :E].T.astype(np.float64))).all()
