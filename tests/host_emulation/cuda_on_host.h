@@ -16,7 +16,9 @@
 // griddepcontrol / mbarrier PTX and the TMA-staged variant cut out; every cut is asserted there.
 #pragma once
 #include <cuda_runtime.h>   // vector types (uint2, uint4, dim3) and the host API's typedefs only
+#include <math.h>
 #include <pthread.h>
+#include <string.h>
 #include <stdint.h>
 
 #include <mutex>
@@ -74,9 +76,35 @@ static inline T __ldg(const T* p) { return *p; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
+// float kernels (real couplings, float moves): bit casts, the fast exponential as libm's expf (their
+// parity gate is statistical on the GPU as well), the saturating float -> uint32 conversion
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+#define __expf(x) expf(x)   /* (glibc declares a function of this name itself) */
+static inline uint32_t __float2uint_rz(float f) {
+    if (!(f > 0.f)) return 0u;                       // NaN and negatives
+    if (f >= 4294967296.f) return 0xFFFFFFFFu;
+    return (uint32_t)f;
+}
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+template <typename T>
+static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) {
     std::lock_guard<std::mutex> g(emu::atomic_mu);
     const unsigned int old = *p;
+    *p = old + v;
+    return old;
+}
+static inline unsigned int atomicXor(unsigned int* p, unsigned int v) {
+    std::lock_guard<std::mutex> g(emu::atomic_mu);
+    const unsigned int old = *p;
+    *p = old ^ v;
+    return old;
+}
+static inline double atomicAdd(double* p, double v) {
+    std::lock_guard<std::mutex> g(emu::atomic_mu);
+    const double old = *p;
     *p = old + v;
     return old;
 }

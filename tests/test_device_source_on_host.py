@@ -200,6 +200,21 @@ def prepare_sources(dst):
     assert ob.count("__shared__") == 1
     open(os.path.join(dst, "observables_kernels.cuh"), "w").write(ob.replace("__shared__", "EMU_SHARED"))
 
+    g3 = open(os.path.join(CSRC, "sweep_general.cu")).read()
+    i = g3.find("template <int ROUNDS>\n__global__ void __launch_bounds__(256)\nk_sweep_real(")
+    assert i >= 0
+    g3, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", g3[i:])
+    assert nwrap == 2 and "<<<" not in g3 and g3.count("__global__") == 2, nwrap
+    open(os.path.join(dst, "real_kernels.cuh"), "w").write('#include "msc_device.cuh"\nnamespace ising {\n' + g3)
+
+    mv2 = open(os.path.join(CSRC, "moves.cu")).read()
+    i = mv2.find(head)
+    k = mv2.find("// word m of the worm's random stream")
+    assert 0 <= i < k
+    mv2, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", mv2[:i] + mv2[k:])
+    assert nwrap == 2 and "<<<" not in mv2 and mv2.count("__global__") == 2, nwrap
+    open(os.path.join(dst, "float_moves_kernels.cuh"), "w").write(mv2)
+
     launch = open(os.path.join(CSRC, "sweep_rows_launch.cuh")).read()
     launch = _cut(launch, "template <int DIM, bool PMJ, int K, int ROUNDS, int V, bool ACC, bool MULTIROW, bool COUNT,",
                   None, "launchers of sweep_rows_launch.cuh") + "\n}  // namespace ising\n"
@@ -214,7 +229,7 @@ def emu(tmp_path_factory):
     so = os.path.join(build, "libemu_rows.so")
     flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
              "-I", "/usr/local/cuda/include"]
-    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt", "emu_aux"]
+    units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt", "emu_aux", "emu_float"]
     procs = [subprocess.Popen(flags + ["-c", os.path.join(EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for u in units]
     for u, pr in zip(units, procs):
@@ -252,6 +267,13 @@ def emu(tmp_path_factory):
                                          C.c_void_p, C.c_uint32]
     lib.emu_energy_from_nsat.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
                                          C.c_uint64]
+    lib.emu_sweep_real.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint32, C.c_float, C.c_uint32,
+                                                                                           C.c_uint64, C.c_uint32]
+    lib.emu_energy_real.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 5
+    lib.emu_edge_moves.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32, C.c_float, C.c_uint32,
+                                                                                           C.c_uint64, C.c_uint32, C.c_uint32]
+    lib.emu_worm_moves.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint32, C.c_uint32,
+                                                                                           C.c_float, C.c_uint32, C.c_uint64]
     lib.emu_edge_group.restype = C.c_int
     lib.emu_edge_group.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32] * 4 + [
         C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint]
@@ -1048,3 +1070,62 @@ def test_count_and_energy_kernels_on_the_host(emu, E):
     out = np.zeros((E, nt))
     emu.emu_energy_from_hist(hist.ctypes.data, E, cw, nt, 1.5, len(a), 2, out.ctypes.data, copies)
     assert (out == 1.5 * (len(a) - 2.0 * hist.sum(axis=1)[:, :E].T.astype(np.float64))).all()
+
+
+# ---- the float-field kernels: statistics against exact enumeration ------------------------------------------
+@pytest.mark.parametrize("moves", [False, True])
+def test_float_kernels_on_the_host_sample_the_boltzmann_law(emu, moves):
+    """k_sweep_real (real couplings, biases) alone, and with passes of float edge moves (importance
+    weights included) and 4-site worm moves in every timestep: <E> and <m> within 4 sigma of the exact
+    enumeration of the 2^10 states; k_energy_real against numpy."""
+    rng = np.random.default_rng(17 + moves)
+    n, E, beta = 10, 1024, 0.6
+    a, b = random_sparse(n, 18, rng, 6)
+    j = rng.normal(size=len(a))
+    bias = rng.normal(size=n) * 0.4
+    W = E // 32
+    row, nbr, jv = csr_sorted(n, a, b, j)
+    row32, jf, biasf = row.astype(np.uint32), jv.astype(np.float32), bias.astype(np.float32)
+    col, _ = greedy_colouring(n, a, b)
+    colour_sites = [np.nonzero(col == c)[0].astype(np.uint32) for c in range(int(col.max()) + 1)]
+    cls = strong_edge_colouring(n, a, b)
+    classes = []
+    for c in range(int(cls.max()) + 1):
+        ids = np.nonzero(cls == c)[0].astype(np.uint32)
+        wrel = (np.abs(j[ids]) / np.abs(j).max()).astype(np.float32)
+        classes.append((a[ids].astype(np.uint32), b[ids].astype(np.uint32), ids, wrel))
+    # exact: E(s) = sum J s s - sum b s over all 2^n states, in the f32 couplings the kernels see
+    st = ((np.arange(2 ** n)[:, None] >> np.arange(n)) & 1) * 2 - 1
+    jq, bq = j.astype(np.float32).astype(np.float64), bias.astype(np.float32).astype(np.float64)
+    en_all = (st[:, a.astype(int)] * st[:, b.astype(int)] * jq).sum(axis=1) - (st * bq).sum(axis=1)
+    wgt = np.exp(-beta * (en_all - en_all.min()))
+    wgt /= wgt.sum()
+    e_exact, m_exact = (wgt * en_all).sum(), (wgt * st.sum(axis=1)).sum()
+
+    words = pack_natural(rng.integers(0, 2, size=(E, n)).astype(bool), W)
+    seed, burn, total, every = 0xF10A7, 30, 90, 4
+    e_samples, m_samples = [], []
+    for t in range(total):
+        for sites in colour_sites:
+            emu.emu_sweep_real(words.ctypes.data, sites.ctypes.data, len(sites), row32.ctypes.data, nbr.ctypes.data,
+                               jf.ctypes.data, biasf.ctypes.data, W, beta, t, seed, 0)
+        if moves:
+            for ea, eb, ids, wrel in classes:
+                emu.emu_edge_moves(words.ctypes.data, n, W, row32.ctypes.data, nbr.ctypes.data, jf.ctypes.data,
+                                   biasf.ctypes.data, ea.ctypes.data, eb.ctypes.data, ids.ctypes.data, wrel.ctypes.data,
+                                   len(ids), beta, t, seed, 0, 0)
+            emu.emu_worm_moves(words.ctypes.data, n, W, row32.ctypes.data, nbr.ctypes.data, jf.ctypes.data,
+                               biasf.ctypes.data, E, 2, 4, beta, t, seed)
+        if t >= burn and (t - burn) % every == 0:
+            en = np.zeros(W * 32)
+            emu.emu_energy_real(words.ctypes.data, n, W, row32.ctypes.data, nbr.ctypes.data, jv.ctypes.data,
+                                bias.ctypes.data, en.ctypes.data)
+            s = unpack_natural(words, E).astype(np.int64) * 2 - 1
+            ref = (s[:, a.astype(int)] * s[:, b.astype(int)] * j).sum(axis=1) - (s * bias).sum(axis=1)
+            assert np.allclose(en, ref, rtol=0, atol=1e-10)
+            e_samples.append(en)
+            m_samples.append(s.sum(axis=1))
+    for samples, exact in ((e_samples, e_exact), (m_samples, m_exact)):
+        per_exp = np.mean(samples, axis=0)                        # experiments are independent chains
+        err = per_exp.std(ddof=1) / np.sqrt(E)
+        assert abs(per_exp.mean() - exact) < 4 * err + 2e-3, (per_exp.mean(), exact, err)
