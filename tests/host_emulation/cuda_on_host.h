@@ -11,7 +11,7 @@
 //   extern __shared__ (dynamic)                 emu::dyn_smem, allocated per launch (per block when resident)
 //   cg::this_grid().sync(), this_cluster().sync()  a barrier over all threads of a resident launch
 //   atomicAdd, __ldg, __umulhi, __ffs, __popc   their plain C++ meaning (atomicAdd under a mutex)
-//   __ballot_sync (full mask)                   a barrier over the warp's 32 threads around a scratch row
+//   __ballot_sync, __shfl_xor_sync (full mask)  a barrier over the warp's 32 threads around a scratch row
 // The prepared copy of the header (tests/test_device_source_on_host.py: prepare_sources) has the
 // griddepcontrol / mbarrier PTX and the TMA-staged variant cut out; every cut is asserted there.
 #pragma once
@@ -40,7 +40,7 @@ inline thread_local pthread_barrier_t* t_barrier = nullptr;
 inline thread_local uint32_t* dyn_smem = nullptr;   // the block's dynamic shared memory
 inline thread_local pthread_barrier_t* t_grid_barrier = nullptr;   // cooperative / cluster launches only
 inline thread_local pthread_barrier_t* t_warp_barrier = nullptr;   // the 32 consecutive threads of a warp
-inline thread_local uint32_t* t_warp_scratch = nullptr;            // 32 words per warp (warp votes)
+inline thread_local uint64_t* t_warp_scratch = nullptr;            // 32 slots per warp (votes, shuffles)
 inline std::mutex atomic_mu;
 }  // namespace emu
 
@@ -121,9 +121,24 @@ static inline uint32_t __ballot_sync(uint32_t, int pred) {
     emu::t_warp_scratch[lane] = pred ? 1u : 0u;
     pthread_barrier_wait(emu::t_warp_barrier);
     uint32_t r = 0;
-    for (unsigned l = 0; l < 32; ++l) r |= emu::t_warp_scratch[l] << l;
+    for (unsigned l = 0; l < 32; ++l) r |= (uint32_t)emu::t_warp_scratch[l] << l;
     pthread_barrier_wait(emu::t_warp_barrier);
     return r;
+}
+// butterfly exchange over the full warp (values of up to 64 bits)
+template <typename T>
+static inline T __shfl_xor_sync(uint32_t, T v, int lane_mask) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    const unsigned lane = (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u;
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    emu::t_warp_scratch[lane] = raw;
+    pthread_barrier_wait(emu::t_warp_barrier);
+    raw = emu::t_warp_scratch[lane ^ (unsigned)lane_mask];
+    pthread_barrier_wait(emu::t_warp_barrier);
+    T out;
+    memcpy(&out, &raw, sizeof(T));
+    return out;
 }
 
 namespace emu {
@@ -136,10 +151,10 @@ void launch(void (*kern)(const Args), dim3 grid, dim3 block, size_t smem_bytes, 
     uint32_t* const smem_p = smem.data();
     const unsigned nwarps = nthreads % 32 == 0 ? nthreads / 32 : 0;   // warp votes need whole warps
     std::vector<pthread_barrier_t> wbar(nwarps);
-    std::vector<uint32_t> wscratch((size_t)nwarps * 32 + 1);
+    std::vector<uint64_t> wscratch((size_t)nwarps * 32 + 1);
     for (auto& w : wbar) pthread_barrier_init(&w, nullptr, 32);
     pthread_barrier_t* const wbar_p = wbar.data();
-    uint32_t* const wscratch_p = wscratch.data();
+    uint64_t* const wscratch_p = wscratch.data();
     for (unsigned b = 0; b < grid.x * grid.y; ++b) {
         pthread_barrier_t bar;
         pthread_barrier_init(&bar, nullptr, nthreads);

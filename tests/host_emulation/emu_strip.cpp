@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "prepared/strip_phase_kernel.cuh"
+#include "prepared/strip_aux_kernels.cuh"
 
 using namespace ising;
 
@@ -65,4 +66,22 @@ extern "C" int emu_strip_phase(uint32_t* spins, uint32_t Wr, uint32_t rows, uint
     if (K == 7 && rounds == 10) GO(7, 10);
 #undef GO
     return -2;
+}
+
+// the strip's Philox initial state, its observables (satisfied bonds, up spins: acc[2]) and its
+// conversion to bool rows: k_strip_init_random / k_strip_observables / k_strip_unpack
+extern "C" void emu_strip_init_random(uint32_t* spins, uint32_t Wr, uint32_t rows, uint32_t row0, uint32_t Ly,
+                                      uint32_t ghost, uint64_t seed, unsigned blocks) {
+    emu::launch_v(k_strip_init_random, dim3(blocks), dim3(256), 0, spins, StripGeom{Wr, rows, row0, Ly, ghost},
+                  (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+extern "C" void emu_strip_observables(const uint32_t* spins, uint32_t Wr, uint32_t rows, uint32_t row0, uint32_t Ly,
+                                      uint32_t ghost, uint32_t antiferro, unsigned long long* acc, unsigned blocks) {
+    emu::launch_v(k_strip_observables, dim3(blocks), dim3(256), 0, spins, StripGeom{Wr, rows, row0, Ly, ghost}, antiferro, acc);
+}
+
+extern "C" void emu_strip_unpack(const uint32_t* spins, uint32_t Wr, uint32_t rows, uint32_t row0, uint32_t Ly,
+                                 uint32_t ghost, uint8_t* out, uint32_t l0, uint32_t nrows, unsigned blocks) {
+    emu::launch_v(k_strip_unpack, dim3(blocks), dim3(256), 0, spins, StripGeom{Wr, rows, row0, Ly, ghost}, out, l0, nrows);
 }

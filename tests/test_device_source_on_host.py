@@ -109,6 +109,12 @@ def prepare_sources(dst):
         strip = strip.replace(ptx, "")
     assert "asm" not in re.sub(r"//.*", "", strip) and "__shared__" not in strip and strip.count("__global__") == 1
     open(os.path.join(dst, "strip_phase_kernel.cuh"), "w").write(strip)
+    aux = open(os.path.join(CSRC, "strip.cu")).read()
+    i = aux.find("__global__ void k_strip_init_random(")
+    assert i >= 0
+    aux, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", aux[i:])
+    assert nwrap == 3 and "<<<" not in aux and aux.count("__global__") == 3, nwrap
+    open(os.path.join(dst, "strip_aux_kernels.cuh"), "w").write("namespace ising {\n" + aux)
 
     io = open(os.path.join(CSRC, "state_io.cu")).read()
     # the host-side wrappers (<<< >>> launches, the SM-count query) go; the kernels stay as they are
@@ -247,6 +253,9 @@ def emu(tmp_path_factory):
     lib.emu_general_group.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                       C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double,
                                       C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
+    lib.emu_strip_init_random.argtypes = [C.c_void_p] + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint]
+    lib.emu_strip_observables.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [C.c_void_p, C.c_uint]
+    lib.emu_strip_unpack.argtypes = [C.c_void_p] + [C.c_uint32] * 5 + [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint]
     lib.emu_strip_phase.restype = C.c_int
     lib.emu_strip_phase.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
                                                                       C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -1129,3 +1138,33 @@ def test_float_kernels_on_the_host_sample_the_boltzmann_law(emu, moves):
         per_exp = np.mean(samples, axis=0)                        # experiments are independent chains
         err = per_exp.std(ddof=1) / np.sqrt(E)
         assert abs(per_exp.mean() - exact) < 4 * err + 2e-3, (per_exp.mean(), exact, err)
+
+
+def test_strip_state_kernels_on_the_host(emu, oracle):
+    """k_strip_init_random == the mirror's Philox initial state (two strips of one lattice);
+    k_strip_unpack and k_strip_observables against numpy"""
+    Lx, Ly, seed, j = 192, 12, 0x51DE5EED, 1.0
+    Wr, rows = Lx // 64, Ly // 2
+    _, ref = oracle.msc_mirror_single(Lx, Ly, j, seed, [])        # no sweeps: the initial state
+    full = strip_pack(ref, Wr)
+    for k in range(2):
+        buf = np.zeros((2, rows + 2, Wr), dtype=np.uint32)
+        emu.emu_strip_init_random(buf.ctypes.data, Wr, rows, k * rows, Ly, 1, seed, 3)
+        assert (buf[:, 1:-1] == full[:, k * rows:(k + 1) * rows]).all()
+        assert (buf[:, 0] == 0).all() and (buf[:, -1] == 0).all()  # ghost rows come from the neighbours
+        for c in range(2):
+            buf[c, 0] = full[c, (k * rows - 1) % Ly]
+            buf[c, -1] = full[c, ((k + 1) * rows) % Ly]
+        out = np.zeros((rows - 1, Lx), dtype=np.uint8)
+        emu.emu_strip_unpack(buf.ctypes.data, Wr, rows, k * rows, Ly, 1, out.ctypes.data, 1, rows - 1, 2)
+        assert (out.astype(bool) == ref[k * rows + 1:(k + 1) * rows]).all()
+        acc = np.zeros(2, dtype=np.uint64)
+        emu.emu_strip_observables(buf.ctypes.data, Wr, rows, k * rows, Ly, 1, 0xFFFFFFFF, acc.ctypes.data, 2)
+        # satisfied (antiferromagnetic: unequal) bonds seen from the colour-0 sites of the strip's rows; all up spins
+        y = np.arange(k * rows, (k + 1) * rows)
+        sat = 0
+        for yy in y:
+            xs = np.arange(Lx)[(np.arange(Lx) + yy) % 2 == 0]
+            for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+                sat += int((ref[yy, xs] != ref[(yy + dy) % Ly, (xs + dx) % Lx]).sum())
+        assert int(acc[0]) == sat and int(acc[1]) == int(ref[y].sum())
