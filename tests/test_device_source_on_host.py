@@ -1112,7 +1112,7 @@ def test_float_kernels_on_the_host_sample_the_boltzmann_law(emu, moves):
     e_exact, m_exact = (wgt * en_all).sum(), (wgt * st.sum(axis=1)).sum()
 
     words = pack_natural(rng.integers(0, 2, size=(E, n)).astype(bool), W)
-    seed, burn, total, every = 0xF10A7, 30, 90, 4
+    seed, burn, total, every = 0xF10A7, 22, 66, 4
     e_samples, m_samples = [], []
     for t in range(total):
         for sites in colour_sites:
