@@ -65,3 +65,14 @@ extern "C" unsigned emu_replay(uint64_t E, uint64_t N, uint64_t A, const uint64_
     emu::launch_v(k_replay, dim3(g ? g : 1), dim3(128), 0, a);
     return ambiguous;
 }
+
+// packed words between the sim's layout and natural site order (checkpoints, ising_sim_get_packed)
+extern "C" void emu_export_natural(const uint32_t* spins, int kind, uint32_t Lx, uint32_t Ly, uint32_t Lz,
+                                   uint64_t nvars, uint32_t W, uint32_t* out, unsigned blocks) {
+    emu::launch_v(k_export_natural, dim3(blocks), dim3(256), 0, spins, make_layout(kind, Lx, Ly, Lz, nvars, W), out);
+}
+
+extern "C" void emu_import_natural(uint32_t* spins, int kind, uint32_t Lx, uint32_t Ly, uint32_t Lz, uint64_t nvars,
+                                   uint32_t W, const uint32_t* in, unsigned blocks) {
+    emu::launch_v(k_import_natural, dim3(blocks), dim3(256), 0, spins, make_layout(kind, Lx, Ly, Lz, nvars, W), in);
+}
