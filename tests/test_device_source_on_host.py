@@ -230,11 +230,16 @@ def prepare_sources(dst):
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
+    import shutil
+
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA toolkit headers (vector types) to build the host emulation")
     build = str(tmp_path_factory.mktemp("host_emulation"))
     prepare_sources(os.path.join(build, "prepared"))
     so = os.path.join(build, "libemu_rows.so")
     flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
-             "-I", "/usr/local/cuda/include"]
+             "-I", cuda_inc]
     units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt", "emu_aux", "emu_float"]
     procs = [subprocess.Popen(flags + ["-c", os.path.join(EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for u in units]
