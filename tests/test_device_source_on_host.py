@@ -1213,3 +1213,53 @@ def test_every_kernel_is_run_here_or_accounted_for():
     stale = (set(NOT_EMULATED) | run_here) - kernels
     assert not stale, f"names that are no kernels of the library (any more): {sorted(stale)}"
     assert not (set(NOT_EMULATED) & run_here)
+
+
+# ---- the build-time variants of the row walk (A/B knobs of sweep_rows.cuh) give the same bits ------------------
+VARIANTS = ["-DISING_ROWS_ZSKIP=1", "-DISING_ROWS_DEFER_RARE=0", "-DISING_ROWS_DEFER_RARE=1", "-DISING_ROWS_LT_SEL=1",
+            "-DISING_ROWS_MUL_SPLIT=0"]
+
+
+def test_row_walk_build_variants_give_the_same_bits(emu, oracle, tmp_path):
+    """Every opt-in formulation kept in the source behind a macro (leading zero planes without the class
+    select, the three placements of the rare tie path, ISETP/SEL tie compare, unsplit Philox products) is
+    compiled for the host and must land on the mirror's bits like the default build - at a low and at a
+    high inverse temperature (where all six threshold planes of a class are zero and ties are frequent)."""
+    import shutil
+
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    build = str(tmp_path)
+    prepare_sources(os.path.join(build, "prepared"))
+    procs = []
+    for k, flag in enumerate(VARIANTS):
+        so = os.path.join(build, f"variant{k}.so")
+        procs.append((flag, so, subprocess.Popen(
+            ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", flag, "-I", EMU, "-I", build, "-I", cuda_inc,
+             os.path.join(EMU, "emu_rows.cpp"), "-o", so], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    rng = np.random.default_rng(5)
+    dims, E, W, V = (8, 4, 4), 128, 4, 4
+    a, b, j = torus(dims, rng, True, -1.0)
+    N = 128
+    _, colors = layout_index(dims)
+    init = rng.integers(0, 2, size=(E, N)).astype(bool)
+    jm8 = bond_masks(dims, a, b, j)
+    betas, seed = [0.1, 1.2, 2.0], 0x7A21A275
+    en_ref, st_ref = oracle.msc_mirror(a, b, j, N, colors, E, seed, betas, states=init, per_sweep=True)
+    for flag, so, pr in procs:
+        _, err = pr.communicate()
+        assert pr.returncode == 0, flag + ":\n" + err[-3000:]
+        lib = C.CDLL(so)
+        lib.emu_rows_phase.restype = C.c_int
+        lib.emu_rows_phase.argtypes = emu.emu_rows_phase.argtypes
+        for small in (0, 1):
+            words = pack(init, dims, W)
+            ens = []
+            for s_, beta in enumerate(betas):
+                for colour in (0, 1):
+                    nsat = np.zeros(W * 32, dtype=np.uint64)
+                    rc = lib.emu_rows_phase(3, dims[0], dims[1], dims[2], W, V, jm8.ctypes.data, 0, words.ctypes.data, colour,
+                                            seed, s_, 0, float(beta), 1.0, int(colour == 1), nsat.ctypes.data, small, 3)
+                    assert rc == 0, (flag, rc)
+                ens.append(len(a) - 2.0 * nsat[:E].astype(np.float64))
+            assert (unpack(words, dims, E) == st_ref).all(), flag
+            assert (np.array(ens).T == en_ref).all(), flag
