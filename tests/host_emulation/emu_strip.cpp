@@ -10,6 +10,7 @@
 
 #include "prepared/strip_phase_kernel.cuh"
 #include "prepared/strip_aux_kernels.cuh"
+#include "prepared/strip_fused_kernel.cuh"
 
 using namespace ising;
 
@@ -84,4 +85,26 @@ extern "C" void emu_strip_observables(const uint32_t* spins, uint32_t Wr, uint32
 extern "C" void emu_strip_unpack(const uint32_t* spins, uint32_t Wr, uint32_t rows, uint32_t row0, uint32_t Ly,
                                  uint32_t ghost, uint8_t* out, uint32_t l0, uint32_t nrows, unsigned blocks) {
     emu::launch_v(k_strip_unpack, dim3(blocks), dim3(256), 0, spins, StripGeom{Wr, rows, row0, Ly, ghost}, out, l0, nrows);
+}
+
+// Both colour phases of a sweep in one out-of-place pass (k_strip_sweep_fused, the opt-in variant whose
+// rows are loaded by the warps): colour 0 on storage rows [r0, r0 + n0), colour 1 on [r0 + 1, r0 + n0 - 1),
+// src -> dst; block shape as launch_strip_sweep_fused() chooses it.  Returns 0, or 1 where that launcher declines.
+extern "C" int emu_strip_fused(const uint32_t* src, uint32_t* dst, uint32_t Wr, uint32_t rows, uint32_t row0, uint32_t Ly,
+                               uint32_t ghost, uint32_t sweep, uint64_t seed, uint32_t antiferro, double beta, double jabs,
+                               uint32_t r0, uint32_t n0, uint32_t nbands) {
+    constexpr int V = 4;
+    if (Wr % V || Wr / V > 256u || n0 < 4) return 1;
+    const uint32_t groups = Wr / V;
+    const uint32_t bx = pow2_ceil(groups) < 32u ? 32u : pow2_ceil(groups);
+    const uint32_t by = 256u / bx;
+    const size_t smem = (size_t)by * 4u * Wr * sizeof(uint32_t);
+    if (nbands > n0 / 2) nbands = n0 / 2;
+    if (nbands < 1) return 1;
+    MscThresholds th;
+    thresholds2d(jabs, beta, 6, &th);
+    emu::launch_v(k_strip_sweep_fused<6, kDefaultRounds, V>, dim3((nbands + by - 1) / by), dim3(bx, by, 1), smem, src, dst,
+                  StripGeom{Wr, rows, row0, Ly, ghost}, sweep, philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32)),
+                  antiferro, make_mux(th), r0, n0, nbands);
+    return 0;
 }

@@ -115,6 +115,15 @@ def prepare_sources(dst):
     aux, nwrap = re.subn(r"\nint launch_\w+\([^{]*\{\n(?:    .*\n|\n)*?\}\n", "\n", aux[i:])
     assert nwrap == 3 and "<<<" not in aux and aux.count("__global__") == 3, nwrap
     open(os.path.join(dst, "strip_aux_kernels.cuh"), "w").write("namespace ising {\n" + aux)
+    fu = open(os.path.join(CSRC, "strip.cu")).read()
+    i = fu.find("template <int K, int ROUNDS, int V>\n__global__ void __launch_bounds__(256, 3)\nk_strip_sweep_fused(")
+    k = fu.find("// The same pass with every row staged in shared memory by the TMA unit")
+    assert 0 <= i < k
+    fu = fu[i:k]
+    ring = "    extern __shared__ uint32_t ring_all[];"
+    assert fu.count(ring) == 1 and fu.count("__shared__") == 1 and "asm" not in re.sub(r"//.*", "", fu)
+    open(os.path.join(dst, "strip_fused_kernel.cuh"), "w").write(
+        "namespace ising {\n" + fu.replace(ring, "    uint32_t* ring_all = emu::dyn_smem;") + "\n}  // namespace ising\n")
 
     io = open(os.path.join(CSRC, "state_io.cu")).read()
     # the host-side wrappers (<<< >>> launches, the SM-count query) go; the kernels stay as they are
@@ -261,6 +270,9 @@ def emu(tmp_path_factory):
     lib.emu_strip_init_random.argtypes = [C.c_void_p] + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint]
     lib.emu_strip_observables.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [C.c_void_p, C.c_uint]
     lib.emu_strip_unpack.argtypes = [C.c_void_p] + [C.c_uint32] * 5 + [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint]
+    lib.emu_strip_fused.restype = C.c_int
+    lib.emu_strip_fused.argtypes = [C.c_void_p, C.c_void_p] + [C.c_uint32] * 6 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
+                                                                                 C.c_uint32, C.c_uint32, C.c_uint32]
     lib.emu_strip_phase.restype = C.c_int
     lib.emu_strip_phase.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_uint64, C.c_uint32, C.c_double, C.c_double,
                                                                       C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -1187,7 +1199,6 @@ def test_strip_state_kernels_on_the_host(emu, oracle):
 NOT_EMULATED = {
     "k_sweep_rows_tma": "opt-in (ISING_TMA=1) variant staged by cp.async.bulk + mbarrier PTX; bit-identical to k_sweep_rows on the GPU",
     "k_strip_sweep_fused_tma": "opt-in (ISING_STRIP_FUSE=1), cp.async.bulk + mbarrier PTX",
-    "k_strip_sweep_fused": "opt-in (ISING_STRIP_FUSE=1) single-pass variant, measured slower; GPU test strip_fused_check.py",
     "k_pt_gather_rows": "row copy by index (slot-ordered samples); the tempering test above does the same gather in numpy",
     "k_pt_local_slots": "three-line index map, the tail of k_pt_swap which is run here",
     "k_copy_strided_f64": "strided copy",
@@ -1263,3 +1274,27 @@ def test_row_walk_build_variants_give_the_same_bits(emu, oracle, tmp_path):
                 ens.append(len(a) - 2.0 * nsat[:E].astype(np.float64))
             assert (unpack(words, dims, E) == st_ref).all(), flag
             assert (np.array(ens).T == en_ref).all(), flag
+
+
+@pytest.mark.parametrize("Lx,Ly,nbands,j", [(256, 16, 3, -1.0), (512, 10, 5, 1.0), (256, 8, 1, -1.0)])
+def test_fused_strip_pass_equals_the_mirror(emu, oracle, Lx, Ly, nbands, j):
+    """k_strip_sweep_fused (opt-in): both colours of a sweep in one out-of-place pass over bands of rows with
+    redundantly recomputed boundary rows - the same bits as two colour phases, hence as the mirror."""
+    rng = np.random.default_rng(Lx + Ly + nbands)
+    Wr, G = Lx // 64, 2
+    init = rng.integers(0, 2, size=(Ly, Lx)).astype(bool)
+    betas, seed = [0.35, 0.6, 0.9], 0x0DDBA11
+    cur = np.zeros((2, Ly + 2 * G, Wr), dtype=np.uint32)
+    cur[:, G:-G] = strip_pack(init, Wr)
+    for t, beta in enumerate(betas):
+        for c in range(2):                                        # periodic ghost rows of the source
+            cur[c, :G] = cur[c, Ly:Ly + G]
+            cur[c, -G:] = cur[c, G:2 * G]
+        nxt = np.zeros_like(cur)
+        rc = emu.emu_strip_fused(cur.ctypes.data, nxt.ctypes.data, Wr, Ly, 0, Ly, G, t, seed, 0xFFFFFFFF if j > 0 else 0,
+                                 float(beta), abs(j), G - 1, Ly + 2, nbands)
+        assert rc == 0
+        cur = nxt
+    got = strip_unpack(cur[:, G:-G], Lx)
+    _, ref = oracle.msc_mirror_single(Lx, Ly, j, seed, betas, state=init)
+    assert (got == ref).all()
