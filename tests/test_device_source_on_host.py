@@ -247,15 +247,17 @@ def emu(tmp_path_factory):
     build = str(tmp_path_factory.mktemp("host_emulation"))
     prepare_sources(os.path.join(build, "prepared"))
     so = os.path.join(build, "libemu_rows.so")
+    # EMU_SANITIZE=thread builds the emulation under ThreadSanitizer (tests/host_emulation/racecheck.py)
+    san = ["-fsanitize=" + os.environ["EMU_SANITIZE"], "-g"] if os.environ.get("EMU_SANITIZE") else []
     flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", build,
-             "-I", cuda_inc]
+             "-I", cuda_inc] + san
     units = ["emu_rows", "emu_general", "emu_strip", "emu_state", "emu_moves", "emu_stencil", "emu_pt", "emu_aux", "emu_float"]
     procs = [subprocess.Popen(flags + ["-c", os.path.join(EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for u in units]
     for u, pr in zip(units, procs):
         _, err = pr.communicate()
         assert pr.returncode == 0, u + ":\n" + err[-4000:]
-    res = subprocess.run(["g++", "-shared", "-pthread", "-o", so] + [os.path.join(build, u + ".o") for u in units],
+    res = subprocess.run(["g++", "-shared", "-pthread"] + san[:1] + ["-o", so] + [os.path.join(build, u + ".o") for u in units],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-4000:]
     lib = C.CDLL(so)
