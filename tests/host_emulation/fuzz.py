@@ -6,7 +6,11 @@ emulation once under a temporary directory and draws lattice sizes, replica coun
 plane / round counts, uniform and per-replica betas at random for the row walk, the per-phase /
 cooperative / cluster checkerboard kernels, the general-graph kernel and the strip kernel; every case
 must equal oracle/msc_mirror.c bit for bit (or be declined the way the library's launcher declines it).
-Last run of the committed kernels: 500 + 300 + 150 + 150 cases, no mismatch."""
+Last run of the committed kernels: 500 + 300 + 150 + 150 cases, no mismatch.
+
+EMU_SANITIZE=address (or thread) with the sanitizer runtime preloaded builds the emulation under that
+sanitizer: `ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) EMU_SANITIZE=address
+python tests/host_emulation/fuzz.py 80` is a memcheck over random shapes (last run: 320 cases, no report)."""
 import ctypes as C
 import os
 import subprocess
@@ -29,11 +33,12 @@ NCASES = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 T.prepare_sources(os.path.join(build, 'prepared'))
 so = os.path.join(build, 'libemu.so')
 if True:
-    flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", T.EMU, "-I", build, "-I", "/usr/local/cuda/include"]
+    san = ["-fsanitize=" + os.environ["EMU_SANITIZE"], "-g"] if os.environ.get("EMU_SANITIZE") else []   # with LD_PRELOAD of the runtime
+    flags = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", T.EMU, "-I", build, "-I", "/usr/local/cuda/include"] + san
     units = ["emu_rows", "emu_stencil", "emu_general", "emu_strip"]
     ps = [subprocess.Popen(flags + ["-c", os.path.join(T.EMU, u + ".cpp"), "-o", os.path.join(build, u + ".o")]) for u in units]
     for p in ps: assert p.wait() == 0
-    assert subprocess.run(["g++", "-shared", "-pthread", "-o", so] + [os.path.join(build, u + ".o") for u in units]).returncode == 0
+    assert subprocess.run(["g++", "-shared", "-pthread"] + san[:1] + ["-o", so] + [os.path.join(build, u + ".o") for u in units]).returncode == 0
 lib = C.CDLL(so)
 lib.emu_rows_phase.restype = C.c_int
 lib.emu_rows_phase.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,

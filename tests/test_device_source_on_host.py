@@ -978,7 +978,7 @@ def test_tempering_run_on_the_host_equals_the_mirror(emu, oracle, native, dims, 
     e_local, e_all, acc = np.zeros(e32), np.zeros(e32), np.zeros(R)
     ns = timesteps // sampling_freq
     samples = np.zeros((R, ns, N), dtype=bool)
-    none = np.zeros(1)
+    none = np.zeros(timesteps)                                    # (betas of a chunk: unused with per-replica tables)
     remaining, to_swap, to_sample, k, sweep = timesteps, swap_freq, sampling_freq, 0, 0
     while remaining > 0:                                          # ising_pt_timesteps_sample's loop
         t = min(to_sample, to_swap, remaining)
