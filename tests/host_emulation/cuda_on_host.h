@@ -1,19 +1,21 @@
 // TEST INFRASTRUCTURE (CPU suite only): just enough of the CUDA execution model to run the
-// library's own row-walk kernel source (pyisingmontecarlo_b200/csrc/sweep_rows.cuh) on the host,
-// one OS thread per CUDA thread, so that the kernel source itself - row geometry, shared Philox
-// rounds, bit-sliced compare, tie words, vertical counters and their block reduction - is compared
-// bit for bit with oracle/msc_mirror.c without a GPU.  Nothing of the product links or loads this.
+// library's own kernel sources (pyisingmontecarlo_b200/csrc/*.cu, *.cuh) on the host, one OS thread
+// per CUDA thread, so that the kernel source itself - row geometry, shared Philox rounds, bit-sliced
+// compare, tie words, vertical counters and their block reduction, the tempering cycle - is compared
+// bit for bit with oracle/msc_mirror.c without a GPU, and can be run under Thread / Address /
+// UndefinedBehavior sanitizers.  Nothing of the product links or loads this.
 //
 // What stands in for what:
-//   threadIdx / blockIdx / blockDim / gridDim   thread_local variables set by emu_launch()
+//   threadIdx / blockIdx / blockDim / gridDim   thread_local variables set by emu::launch()
 //   __syncthreads()                             a pthread barrier over the block's threads
 //   __shared__ (static)                         a function-local static: blocks run one at a time
 //   extern __shared__ (dynamic)                 emu::dyn_smem, allocated per launch (per block when resident)
 //   cg::this_grid().sync(), this_cluster().sync()  a barrier over all threads of a resident launch
 //   atomicAdd, __ldg, __umulhi, __ffs, __popc   their plain C++ meaning (atomicAdd under a mutex)
 //   __ballot_sync, __shfl_xor_sync (full mask)  a barrier over the warp's 32 threads around a scratch row
-// The prepared copy of the header (tests/test_device_source_on_host.py: prepare_sources) has the
-// griddepcontrol / mbarrier PTX and the TMA-staged variant cut out; every cut is asserted there.
+// The prepared copies of the sources (tests/test_device_source_on_host.py: prepare_sources) have the
+// griddepcontrol PTX, the TMA-staged variants and the <<< >>> launch wrappers cut out; every cut is
+// an asserted exact-text edit there.
 #pragma once
 #include <cuda_runtime.h>   // vector types (uint2, uint4, dim3) and the host API's typedefs only
 #include <math.h>
